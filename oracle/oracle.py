@@ -1,0 +1,266 @@
+"""ctypes binding of the CPU oracle (oracle/liborb_oracle.so).  TEST INFRASTRUCTURE ONLY.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs import
+this module.  The product (jetracer-orbslam2_b200) never does.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+
+KEYPOINT_DTYPE = np.dtype(
+    [("x", "<f4"), ("y", "<f4"), ("size", "<f4"), ("angle", "<f4"), ("response", "<f4"),
+     ("octave", "<i4"), ("class_id", "<i4")]
+)
+CAND_DTYPE = np.dtype([("x", "<i4"), ("y", "<i4"), ("response", "<i4")])
+
+
+class Params(C.Structure):
+    _fields_ = [("nfeatures", C.c_int32), ("scale_factor", C.c_float), ("nlevels", C.c_int32),
+                ("ini_th_fast", C.c_int32), ("min_th_fast", C.c_int32)]
+
+
+def build(native: bool = False) -> str:
+    """Compile the oracle with its Makefile (gcc only) and return the .so path."""
+    target = "native" if native else "all"
+    subprocess.run(["make", "-C", _HERE, target], check=True, capture_output=True)
+    return os.path.join(_HERE, "liborb_oracle_native.so" if native else "liborb_oracle.so")
+
+
+_lib = None
+
+
+def lib(native: bool = False):
+    global _lib
+    if _lib is not None and not native:
+        return _lib
+    path = os.path.join(_HERE, "liborb_oracle_native.so" if native else "liborb_oracle.so")
+    if not os.path.exists(path):
+        path = build(native)
+    L = C.CDLL(path)
+    u8p, i32p, f32p = C.POINTER(C.c_uint8), C.POINTER(C.c_int32), C.POINTER(C.c_float)
+    vp = C.c_void_p
+    L.orbo_resize_linear_u8.argtypes = [vp, C.c_int, C.c_int, C.c_size_t, vp, C.c_int, C.c_int, C.c_size_t]
+    L.orbo_resize_linear_u8.restype = None
+    L.orbo_border_reflect101.argtypes = [vp, C.c_int, C.c_int, C.c_size_t, C.c_int]
+    L.orbo_border_reflect101.restype = None
+    L.orbo_fast9_window.argtypes = [vp, C.c_int, C.c_int, C.c_size_t, C.c_int, C.c_int, vp, C.c_int]
+    L.orbo_fast9_window.restype = C.c_int
+    L.orbo_fast_score_map.argtypes = [vp, C.c_int, C.c_int, C.c_size_t, vp, C.c_size_t]
+    L.orbo_fast_score_map.restype = None
+    L.orbo_gaussian_blur7.argtypes = [vp, C.c_int, C.c_int, C.c_size_t, vp, C.c_size_t]
+    L.orbo_gaussian_blur7.restype = None
+    L.orbo_fast_atan2.argtypes = [C.c_float, C.c_float]
+    L.orbo_fast_atan2.restype = C.c_float
+    L.orbo_match_knn.argtypes = [vp, C.c_int, vp, C.c_int, C.c_int, C.c_float, vp, vp, vp]
+    L.orbo_match_knn.restype = C.c_int
+    L.orbo_create.argtypes = [C.POINTER(vp), C.POINTER(Params), C.c_int, C.c_int]
+    L.orbo_create.restype = C.c_int
+    L.orbo_destroy.argtypes = [vp]
+    L.orbo_destroy.restype = None
+    L.orbo_nlevels.argtypes = [vp]
+    L.orbo_nlevels.restype = C.c_int
+    L.orbo_get_geometry.argtypes = [vp, vp, vp, vp, vp, vp]
+    L.orbo_get_geometry.restype = None
+    L.orbo_get_umax.argtypes = [vp, vp]
+    L.orbo_get_umax.restype = None
+    L.orbo_extract.argtypes = [vp, vp, C.c_size_t, vp, vp, C.c_int]
+    L.orbo_extract.restype = C.c_int
+    L.orbo_compute_pyramid.argtypes = [vp, vp, C.c_size_t]
+    L.orbo_compute_pyramid.restype = C.c_int
+    L.orbo_level_padded.argtypes = [vp, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_size_t)]
+    L.orbo_level_padded.restype = vp
+    L.orbo_level_candidates.argtypes = [vp, C.c_int, vp, C.c_int]
+    L.orbo_level_candidates.restype = C.c_int
+    L.orbo_distribute_octree.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, C.c_int]
+    L.orbo_distribute_octree.restype = C.c_int
+    L.orbo_level_blurred.argtypes = [vp, C.c_int, vp]
+    L.orbo_level_blurred.restype = C.c_int
+    L.orbo_ic_angle.argtypes = [vp, C.c_int, C.c_float, C.c_float]
+    L.orbo_ic_angle.restype = C.c_float
+    L.orbo_descriptor.argtypes = [vp, C.c_size_t, C.c_float, C.c_float, C.c_float, vp]
+    L.orbo_descriptor.restype = None
+    L.orbo_extract_many.argtypes = [C.POINTER(Params), vp, C.c_int, C.c_int, C.c_size_t, C.c_size_t,
+                                    C.c_int, C.c_int, vp]
+    L.orbo_extract_many.restype = C.c_long
+    L.orbo_match_many.argtypes = [vp, C.c_int, vp, C.c_int, C.c_int, C.c_float, C.c_int, vp, vp, vp]
+    L.orbo_match_many.restype = C.c_long
+    del u8p, i32p, f32p
+    if not native:
+        _lib = L
+    return L
+
+
+def _p(a: np.ndarray):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def _u8c(a) -> np.ndarray:
+    a = np.ascontiguousarray(a, dtype=np.uint8)
+    assert a.ndim == 2
+    return a
+
+
+# ---------------------------------------------------------------- primitives
+def resize_linear(src, dw: int, dh: int) -> np.ndarray:
+    src = _u8c(src)
+    dst = np.empty((dh, dw), np.uint8)
+    lib().orbo_resize_linear_u8(_p(src), src.shape[1], src.shape[0], src.strides[0], _p(dst), dw, dh, dw)
+    return dst
+
+
+def border_reflect101(roi, b: int = 19) -> np.ndarray:
+    roi = _u8c(roi)
+    h, w = roi.shape
+    out = np.zeros((h + 2 * b, w + 2 * b), np.uint8)
+    out[b:b + h, b:b + w] = roi
+    lib().orbo_border_reflect101(_p(out), w, h, out.strides[0], b)
+    return out
+
+
+def fast9_window(win, thr: int, nms: bool = True) -> np.ndarray:
+    win = _u8c(win)
+    h, w = win.shape
+    out = np.zeros(max(1, w * h), CAND_DTYPE)
+    n = lib().orbo_fast9_window(_p(win), w, h, win.strides[0], thr, int(nms), _p(out), out.size)
+    return out[:n].copy()
+
+
+def fast_score_map(img) -> np.ndarray:
+    img = _u8c(img)
+    h, w = img.shape
+    out = np.zeros((h, w), np.uint8)
+    lib().orbo_fast_score_map(_p(img), w, h, img.strides[0], _p(out), w)
+    return out
+
+
+def gaussian_blur7(img) -> np.ndarray:
+    img = _u8c(img)
+    h, w = img.shape
+    out = np.empty((h, w), np.uint8)
+    lib().orbo_gaussian_blur7(_p(img), w, h, img.strides[0], _p(out), w)
+    return out
+
+
+def fast_atan2(y: float, x: float) -> float:
+    return float(lib().orbo_fast_atan2(C.c_float(y), C.c_float(x)))
+
+
+def match_knn(q, t, k: int = 2, ratio: float = 0.7, threads: int = 1, native: bool = False):
+    q = np.ascontiguousarray(q, np.uint8).reshape(-1, 32)
+    t = np.ascontiguousarray(t, np.uint8).reshape(-1, 32)
+    idx = np.full((q.shape[0], 2), -1, np.int32)
+    dist = np.full((q.shape[0], 2), -1, np.int32)
+    acc = np.zeros(q.shape[0], np.uint8)
+    L = lib(native)
+    if threads <= 1:
+        L.orbo_match_knn(_p(q), q.shape[0], _p(t), t.shape[0], k, ratio, _p(idx), _p(dist), _p(acc))
+    else:
+        L.orbo_match_many(_p(q), q.shape[0], _p(t), t.shape[0], k, ratio, threads, _p(idx), _p(dist), _p(acc))
+    return idx, dist, acc.astype(bool)
+
+
+def distribute_octree(cand: np.ndarray, min_x: int, max_x: int, min_y: int, max_y: int, n: int) -> np.ndarray:
+    cand = np.ascontiguousarray(cand, CAND_DTYPE)
+    out = np.zeros(max(1, cand.size), np.int32)
+    k = lib().orbo_distribute_octree(_p(cand), cand.size, min_x, max_x, min_y, max_y, n, _p(out), out.size)
+    if k < 0:
+        raise RuntimeError(f"orbo_distribute_octree failed: {k}")
+    return out[:k].copy()
+
+
+# ---------------------------------------------------------------- extractor
+class Oracle:
+    """Upstream `ORBextractor(nfeatures, scaleFactor, nlevels, iniThFAST, minThFAST)` on the CPU."""
+
+    def __init__(self, width: int, height: int, nfeatures: int = 1000, scale_factor: float = 1.2,
+                 nlevels: int = 8, ini_th_fast: int = 20, min_th_fast: int = 7):
+        self.params = Params(nfeatures, scale_factor, nlevels, ini_th_fast, min_th_fast)
+        self.w, self.h = width, height
+        self._h = C.c_void_p()
+        rc = lib().orbo_create(C.byref(self._h), C.byref(self.params), width, height)
+        if rc:
+            raise ValueError(f"orbo_create failed: {rc}")
+        n = nlevels
+        self.lw = np.zeros(n, np.int32)
+        self.lh = np.zeros(n, np.int32)
+        self.scale = np.zeros(n, np.float32)
+        self.inv_scale = np.zeros(n, np.float32)
+        self.nfeat = np.zeros(n, np.int32)
+        lib().orbo_get_geometry(self._h, _p(self.lw), _p(self.lh), _p(self.scale), _p(self.inv_scale), _p(self.nfeat))
+        self.umax = np.zeros(16, np.int32)
+        lib().orbo_get_umax(self._h, _p(self.umax))
+        self.nlevels = n
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib().orbo_destroy(self._h)
+            self._h = None
+
+    @property
+    def max_keypoints(self) -> int:
+        return int(self.nfeat.sum()) + 16 * self.nlevels + 64
+
+    def extract(self, img):
+        img = _u8c(img)
+        assert img.shape == (self.h, self.w)
+        cap = self.max_keypoints
+        kp = np.zeros(cap, KEYPOINT_DTYPE)
+        desc = np.zeros((cap, 32), np.uint8)
+        n = lib().orbo_extract(self._h, _p(img), img.strides[0], _p(kp), _p(desc), cap)
+        if n < 0:
+            raise RuntimeError(f"orbo_extract failed: {n}")
+        return kp[:n].copy(), desc[:n].copy()
+
+    def compute_pyramid(self, img):
+        img = _u8c(img)
+        lib().orbo_compute_pyramid(self._h, _p(img), img.strides[0])
+
+    def level_padded(self, level: int) -> np.ndarray:
+        pw, ph, pitch = C.c_int(), C.c_int(), C.c_size_t()
+        ptr = lib().orbo_level_padded(self._h, level, C.byref(pw), C.byref(ph), C.byref(pitch))
+        buf = (C.c_uint8 * (pitch.value * ph.value)).from_address(ptr)
+        return np.frombuffer(buf, np.uint8).reshape(ph.value, pitch.value)[:, :pw.value].copy()
+
+    def level_roi(self, level: int) -> np.ndarray:
+        return self.level_padded(level)[19:-19, 19:-19]
+
+    def level_candidates(self, level: int) -> np.ndarray:
+        cap = int(self.lw[level]) * int(self.lh[level]) // 4 + 64
+        out = np.zeros(cap, CAND_DTYPE)
+        n = lib().orbo_level_candidates(self._h, level, _p(out), cap)
+        return out[:n].copy()
+
+    def level_blurred(self, level: int) -> np.ndarray:
+        out = np.empty((int(self.lh[level]), int(self.lw[level])), np.uint8)
+        lib().orbo_level_blurred(self._h, level, _p(out))
+        return out
+
+    def ic_angle(self, level: int, x: float, y: float) -> float:
+        return float(lib().orbo_ic_angle(self._h, level, C.c_float(x), C.c_float(y)))
+
+
+def descriptor(blurred, x: float, y: float, angle_deg: float) -> np.ndarray:
+    blurred = _u8c(blurred)
+    out = np.zeros(32, np.uint8)
+    lib().orbo_descriptor(_p(blurred), blurred.strides[0], C.c_float(x), C.c_float(y), C.c_float(angle_deg), _p(out))
+    return out
+
+
+def extract_many(frames: np.ndarray, nfeatures=1000, scale_factor=1.2, nlevels=8, ini_th=20, min_th=7,
+                 threads: int = 1, native: bool = False):
+    """CPU baseline driver: frames [n,h,w] u8 -> (total keypoints, counts[n])."""
+    frames = np.ascontiguousarray(frames, np.uint8)
+    n, h, w = frames.shape
+    p = Params(nfeatures, scale_factor, nlevels, ini_th, min_th)
+    counts = np.zeros(n, np.int32)
+    tot = lib(native).orbo_extract_many(C.byref(p), _p(frames), w, h, frames.strides[1], frames.strides[0], n,
+                                        threads, _p(counts))
+    if tot < 0:
+        raise RuntimeError(f"orbo_extract_many failed: {tot}")
+    return int(tot), counts
