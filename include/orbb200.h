@@ -1,0 +1,168 @@
+/*
+ * orbb200.h -- C ABI of the B200-native ORB front-end (liborbb200.so).
+ *
+ * Drop-in boundary for the ORB path of dsvua/jetracer-orbslam2.  Plain C: pointers, sizes and a
+ * cudaStream_t passed as void*.  No torch / OpenCV / Eigen types.  Every entry point names the
+ * reference interface (file:line under the reference tree) it replaces.
+ *
+ * Conventions:
+ *   - return 0 on success, a negative orbb_status otherwise; nothing aborts the process
+ *     (the reference's CUDA_API_CALL/checkCudaErrors exit(), src/cuda_common.h:69-95);
+ *   - the caller owns inputs and outputs; the handle owns all scratch, allocated once in
+ *     orbb_create (the reference cudaMallocs per frame, src/SlamGpuPipeline/buildStream.cpp:354-370);
+ *   - one handle per (host thread, device); all work is enqueued on the stream given, no hidden
+ *     synchronisation in the *_device entry points;
+ *   - there is NO CPU fallback: without a CUDA device orbb_create returns ORBB_ERR_NO_DEVICE.
+ */
+#ifndef ORBB200_H
+#define ORBB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ORBB_VERSION 100
+#define ORBB_MAX_LEVELS 16
+#define ORBB_EDGE_THRESHOLD 19 /* upstream EDGE_THRESHOLD; border of every padded level */
+#define ORBB_DESC_BYTES 32
+
+typedef enum {
+    ORBB_OK = 0,
+    ORBB_ERR_INVALID = -1,     /* bad argument */
+    ORBB_ERR_NO_DEVICE = -2,   /* no CUDA device / wrong arch: the product has no CPU path */
+    ORBB_ERR_CUDA = -3,        /* a CUDA runtime call failed (see orbb_last_cuda_error) */
+    ORBB_ERR_TOO_SMALL = -4,   /* a pyramid level would be < 62 px (upstream divides by nCols==0) */
+    ORBB_ERR_CAPACITY = -5,    /* batch/keypoint capacity of the handle or output exceeded */
+    ORBB_ERR_SHAPE = -6        /* image shape differs from the one the handle was created for */
+} orbb_status;
+
+/* == cv::KeyPoint (28 bytes): what ORBextractor::operator() fills.  Replaces the SoA
+ * float2 pos / float score / int level triple of src/SlamGpuPipeline/buildStream.cpp:289-296. */
+typedef struct {
+    float x, y, size, angle, response;
+    int32_t octave, class_id;
+} orbb_keypoint;
+
+/* ORBextractor(nfeatures, scaleFactor, nlevels, iniThFAST, minThFAST); replaces the compile-time
+ * knobs of src/SlamGpuPipeline/defines.h:2-9 (PYRAMID_LEVELS, FAST_EPSILON, ...). */
+typedef struct {
+    int32_t nfeatures;
+    float scale_factor;
+    int32_t nlevels, ini_th_fast, min_th_fast;
+} orbb_params;
+
+/* Level descriptor handed out by orbb_get_level; mirrors Jetracer::pyramid_t
+ * (src/cuda/pyramid.cuh:9-18) but with the 19-px reflect-101 frame and no float response map. */
+typedef struct {
+    int32_t width, height;   /* ROI size */
+    int32_t pitch;           /* bytes per row of the padded buffer */
+    int32_t roi_offset;      /* byte offset of ROI pixel (0,0) from `padded` row start + 19 rows */
+    uint8_t *padded;         /* device pointer to padded pixel (0,0): (width+38) x (height+38) */
+    uint8_t *blurred;        /* device pointer to the 7x7-blurred ROI (same pitch, ROI origin) */
+    float scale, inv_scale;  /* mvScaleFactor / mvInvScaleFactor */
+    int32_t nfeatures;       /* mnFeaturesPerLevel */
+} orbb_level;
+
+typedef struct orbb_handle orbb_handle;
+
+/* ---------------------------------------------------------------- lifetime */
+/* Replaces the buffer prologue of SlamGpuPipeline::buildStream (buildStream.cpp:208-341) and
+ * loadPattern() (src/cuda/orb.cu:218-225).  device < 0 => current device. */
+int orbb_create(orbb_handle **out, const orbb_params *params, int width, int height, int max_batch,
+                int device);
+int orbb_destroy(orbb_handle *h);
+const char *orbb_strerror(int status);
+const char *orbb_last_cuda_error(const orbb_handle *h);
+
+/* ---------------------------------------------------------------- geometry / getters
+ * ORBextractor::GetLevels/GetScaleFactors/GetInverseScaleFactors/GetScaleSigmaSquares/
+ * GetInverseScaleSigmaSquares.  Arrays must hold nlevels entries (NULL to skip). */
+int orbb_get_levels(const orbb_handle *h);
+int orbb_get_scale_factors(const orbb_handle *h, float *scale, float *inv_scale, float *sigma2,
+                           float *inv_sigma2);
+int orbb_get_features_per_level(const orbb_handle *h, int32_t *nfeat);
+int orbb_max_keypoints_per_frame(const orbb_handle *h); /* capacity to allocate per frame */
+/* mvImagePyramid[level] of frame `frame` in the last batch (device pointers into the handle) */
+int orbb_get_level(const orbb_handle *h, int frame, int level, orbb_level *out);
+
+/* ---------------------------------------------------------------- whole extractor
+ * ORBextractor::operator()(image, mask[ignored], keypoints, descriptors) over a batch of frames;
+ * replaces the stage-calling block of buildStream (buildStream.cpp:416-460).
+ *   d_images : DEVICE pointer, frame f row r at d_images + f*frame_stride + r*pitch, u8 gray
+ *   d_kp     : DEVICE [n_frames][max_kp] orbb_keypoint
+ *   d_desc   : DEVICE [n_frames][max_kp][32]
+ *   d_counts : DEVICE [n_frames] int32
+ * Keypoints of a frame are concatenated by level (0..nlevels-1); inside a level they are in
+ * quadtree Z-order (deterministic).  Asynchronous on `cuda_stream`. */
+int orbb_extract_batch_device(orbb_handle *h, const uint8_t *d_images, size_t pitch,
+                              size_t frame_stride, int n_frames, orbb_keypoint *d_kp,
+                              uint8_t *d_desc, int32_t *d_counts, int max_kp, void *cuda_stream);
+/* Same with HOST buffers (pinned or pageable): H2D of the frames, extraction, D2H of
+ * keypoints/descriptors/counts, then synchronises the stream.  This is the call a
+ * SlamGpuPipeline slot thread makes per batch (buildStream.cpp:399-406,462-466). */
+int orbb_extract_batch_host(orbb_handle *h, const uint8_t *h_images, size_t pitch,
+                            size_t frame_stride, int n_frames, orbb_keypoint *h_kp, uint8_t *h_desc,
+                            int32_t *h_counts, int max_kp, void *cuda_stream);
+
+/* ---------------------------------------------------------------- stage interface
+ * Same stage names as the reference's free functions in namespace Jetracer.  All take the batch
+ * resident in the handle (set by orbb_stage_upload or a previous stage) and are async on stream. */
+/* copy frames into level 0 (+ reflect-101 frame); precedes pyramid_create_levels */
+int orbb_stage_upload(orbb_handle *h, const uint8_t *d_images, size_t pitch, size_t frame_stride,
+                      int n_frames, void *cuda_stream);
+/* Jetracer::pyramid_create_levels (src/cuda/pyramid.cuh:20-21): levels 1..n-1, x(1/scale)
+ * bilinear 11-bit fixed point == cv::resize INTER_LINEAR, + border */
+int orbb_pyramid_create_levels(orbb_handle *h, void *cuda_stream);
+/* Jetracer::detect + grid_nms (src/cuda/fast.cuh:42-48, nms.cuh:11-15): FAST-9 score, per-cell
+ * 3x3 NMS with the ini/min threshold fallback, then DistributeOctTree selection per level */
+int orbb_detect(orbb_handle *h, void *cuda_stream);
+/* Jetracer::gaussian_blur_3x3 slot (src/cuda/orb.cuh:29-35), now 7x7 sigma=2 integer Gaussian */
+int orbb_gaussian_blur(orbb_handle *h, void *cuda_stream);
+/* Jetracer::compute_fast_angle + calc_orb (src/cuda/orb.cuh:9-27): IC_Angle (degrees) and the
+ * 256-bit steered BRIEF; writes the final keypoint/descriptor arrays */
+int orbb_compute_angle_and_orb(orbb_handle *h, orbb_keypoint *d_kp, uint8_t *d_desc,
+                               int32_t *d_counts, int max_kp, void *cuda_stream);
+
+/* ---------------------------------------------------------------- matcher
+ * Replaces Jetracer::match_keypoints (src/cuda/post_processing.cuh:40-51): brute-force Hamming
+ * k-NN over 256-bit descriptors (XOR + POPC), k in {1,2}, ties -> lowest train index, accept iff
+ * (k==1) or d1 < ratio*d2.  d_idx/d_dist are [nq][2] int32 (second column -1 when k==1 or nt<2),
+ * d_accept [nq] u8 (may be NULL), d_naccept one int32 (may be NULL).  handle may be NULL?  No:
+ * the handle supplies split-T scratch.  Async on stream. */
+int orbb_match_knn(orbb_handle *h, const uint8_t *d_query, int nq, const uint8_t *d_train, int nt,
+                   int k, float ratio, int32_t *d_idx, int32_t *d_dist, uint8_t *d_accept,
+                   int32_t *d_naccept, void *cuda_stream);
+/* Segmented form: nseg independent (query set, train set) pairs, e.g. left/right or t/t+1 frames.
+ * q_offsets/t_offsets are DEVICE int32 [nseg+1] row offsets into d_query/d_train; idx values are
+ * relative to the segment's train set. */
+int orbb_match_knn_segmented(orbb_handle *h, const uint8_t *d_query, const int32_t *d_q_offsets,
+                             const uint8_t *d_train, const int32_t *d_t_offsets, int nseg,
+                             int max_q_per_seg, int k, float ratio, int32_t *d_idx, int32_t *d_dist,
+                             uint8_t *d_accept, void *cuda_stream);
+
+/* ---------------------------------------------------------------- debug / parity access
+ * Download stage outputs of frame `frame` of the last batch to HOST memory (synchronises). */
+/* padded level, contiguous (w+38) x (h+38) */
+int orbb_debug_get_padded(orbb_handle *h, int frame, int level, uint8_t *host_out);
+/* blurred ROI, contiguous w x h */
+int orbb_debug_get_blurred(orbb_handle *h, int frame, int level, uint8_t *host_out);
+/* FAST arc score map of the ROI (w x h): m if m > min(ini,min) threshold else 0 (0 outside the
+ * tested range [19,w-19) x [19,h-19)); recomputed by the same device code as orbb_detect */
+int orbb_debug_get_scores(orbb_handle *h, int frame, int level, uint8_t *host_out);
+/* per-cell FAST candidates handed to the quadtree: triples (x,y,response), coordinates relative
+ * to (16,16) like upstream vToDistributeKeys; order unspecified. returns count (or <0) */
+int orbb_debug_get_candidates(orbb_handle *h, int frame, int level, int32_t *host_xyr, int max_n);
+/* quadtree-selected keys of a level: triples (x,y,response) relative to (16,16). returns count */
+int orbb_debug_get_selected(orbb_handle *h, int frame, int level, int32_t *host_xyr, int max_n);
+/* run only DistributeOctTree on a caller-supplied candidate list (host triples) for the geometry
+ * of `level` with quota N; returns count, writes selected triples */
+int orbb_debug_distribute(orbb_handle *h, int level, const int32_t *host_xyr, int n, int quota,
+                          int32_t *host_out_xyr, int max_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ORBB200_H */

@@ -1,0 +1,129 @@
+// k_match.cu -- brute-force Hamming k-NN (k <= 2) with ratio test over 256-bit descriptors.
+// Replaces Jetracer::match_keypoints / kernel_match_keypoints (reference
+// src/cuda/post_processing.cu:92-200, 234-341: windowed 1-NN on 32-bit squeezed descriptors with
+// per-call cudaMalloc).  Definition: SURVEY.md A.7 -- two smallest distances over all train rows,
+// ties -> lowest train index, accept iff d1 < ratio * d2 (k == 2).
+//
+// XOR + POPC only: no tensor cores (nothing here is a floating-point contraction).  Each thread
+// keeps QPT query descriptors in registers; train descriptors are staged through shared memory in
+// tiles and read with 128-bit broadcast loads, so the inner loop is 8 LOP3 + 8 POPC + adds per pair.
+// The train set may be split across blockIdx.y (split-T) so small query sets still fill 148 SMs;
+// partial (d1,i1,d2,i2) are merged in ascending split order, which preserves the tie rule.
+// Bound: POPC issue rate (16/clk/SM), see DESIGN.md.
+#include "orbb_internal.cuh"
+
+namespace orbb {
+
+#define MATCH_THREADS 128
+#define MATCH_QPT 2           // queries per thread
+#define MATCH_TILE 128        // train descriptors per shared-memory tile
+
+struct Best2 {
+    int d1, i1, d2, i2;
+};
+
+__device__ __forceinline__ void best2_update(Best2 &b, int d, int idx) {
+    if (d < b.d1) { b.d2 = b.d1; b.i2 = b.i1; b.d1 = d; b.i1 = idx; }
+    else if (d < b.d2) { b.d2 = d; b.i2 = idx; }
+}
+
+// segments: query rows [q_off[s], q_off[s+1]) are matched against train rows [t_off[s], t_off[s+1]).
+// blockIdx.x = query block inside the segment, blockIdx.y = split of the train range, blockIdx.z = segment.
+__global__ void __launch_bounds__(MATCH_THREADS)
+k_match(const uint4 *__restrict__ query, const uint4 *__restrict__ train, const int *__restrict__ q_off,
+        const int *__restrict__ t_off, int nq_one, int nt_one, int n_split, int4 *__restrict__ partial,
+        int partial_stride) {
+    __shared__ uint4 s_t[MATCH_TILE * 2];
+    const int seg = blockIdx.z;
+    const int q0 = q_off ? q_off[seg] : 0, q1 = q_off ? q_off[seg + 1] : nq_one;
+    const int t0 = t_off ? t_off[seg] : 0, t1 = t_off ? t_off[seg + 1] : nt_one;
+    const int qbase = q0 + blockIdx.x * (MATCH_THREADS * MATCH_QPT);
+    if (qbase >= q1) return;
+    const int nt = t1 - t0;
+    const int per = (nt + n_split - 1) / n_split;
+    const int ts = min(nt, (int)blockIdx.y * per), te = min(nt, ts + per);
+
+    uint4 qa[MATCH_QPT], qb[MATCH_QPT];
+    Best2 best[MATCH_QPT];
+#pragma unroll
+    for (int j = 0; j < MATCH_QPT; ++j) {
+        const int q = qbase + j * MATCH_THREADS + threadIdx.x;
+        const int qq = q < q1 ? q : q1 - 1;
+        qa[j] = query[(size_t)qq * 2];
+        qb[j] = query[(size_t)qq * 2 + 1];
+        best[j] = {257, -1, 257, -1};
+    }
+    for (int tb = ts; tb < te; tb += MATCH_TILE) {
+        const int cnt = min(MATCH_TILE, te - tb);
+        __syncthreads();
+        for (int i = threadIdx.x; i < cnt * 2; i += MATCH_THREADS) s_t[i] = train[(size_t)(t0 + tb) * 2 + i];
+        __syncthreads();
+#pragma unroll 4
+        for (int t = 0; t < cnt; ++t) {
+            const uint4 a = s_t[2 * t], b = s_t[2 * t + 1];
+#pragma unroll
+            for (int j = 0; j < MATCH_QPT; ++j) {
+                const int d = __popc(qa[j].x ^ a.x) + __popc(qa[j].y ^ a.y) + __popc(qa[j].z ^ a.z) +
+                              __popc(qa[j].w ^ a.w) + __popc(qb[j].x ^ b.x) + __popc(qb[j].y ^ b.y) +
+                              __popc(qb[j].z ^ b.z) + __popc(qb[j].w ^ b.w);
+                best2_update(best[j], d, tb + t);
+            }
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < MATCH_QPT; ++j) {
+        const int q = qbase + j * MATCH_THREADS + threadIdx.x;
+        if (q < q1)
+            partial[(size_t)blockIdx.y * partial_stride + q] = make_int4(best[j].d1, best[j].i1, best[j].d2, best[j].i2);
+    }
+}
+
+__global__ void __launch_bounds__(256)
+k_match_merge(const int4 *__restrict__ partial, int partial_stride, int n_split, int nq, int k, float ratio,
+              int *__restrict__ out_idx, int *__restrict__ out_dist, uint8_t *__restrict__ accept,
+              int *__restrict__ n_accept) {
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    bool ok = false;
+    if (q < nq) {
+        Best2 b = {257, -1, 257, -1};
+        for (int s = 0; s < n_split; ++s) {
+            const int4 p = partial[(size_t)s * partial_stride + q];
+            if (p.y >= 0) best2_update(b, p.x, p.y);
+            if (p.w >= 0) best2_update(b, p.z, p.w);
+        }
+        if (k < 2) { b.d2 = 257; b.i2 = -1; }
+        out_idx[2 * q] = b.i1;
+        out_idx[2 * q + 1] = b.i2;
+        out_dist[2 * q] = b.i1 >= 0 ? b.d1 : -1;
+        out_dist[2 * q + 1] = b.i2 >= 0 ? b.d2 : -1;
+        ok = b.i1 >= 0;
+        if (k == 2) ok = b.i2 >= 0 && (float)b.d1 < __fmul_rn(ratio, (float)b.d2);
+        if (accept) accept[q] = ok ? 1 : 0;
+    }
+    if (n_accept) {
+        const unsigned m = __ballot_sync(0xffffffffu, ok);
+        if ((threadIdx.x & 31) == 0 && m) atomicAdd(n_accept, __popc(m));
+    }
+}
+
+cudaError_t launch_match(const uint8_t *d_q, const uint8_t *d_t, const int *d_q_off, const int *d_t_off, int nseg,
+                         int nq_total, int max_q_per_seg, int nt_one, int n_split, int4 *d_partial,
+                         int partial_stride, int k, float ratio, int *d_idx, int *d_dist, uint8_t *d_accept,
+                         int *d_naccept, cudaStream_t st) {
+    if (nq_total <= 0) return cudaSuccess;
+    const int qblocks = (max_q_per_seg + MATCH_THREADS * MATCH_QPT - 1) / (MATCH_THREADS * MATCH_QPT);
+    dim3 grid(qblocks, n_split, nseg);
+    k_match<<<grid, MATCH_THREADS, 0, st>>>(reinterpret_cast<const uint4 *>(d_q), reinterpret_cast<const uint4 *>(d_t),
+                                            d_q_off, d_t_off, nq_total, nt_one, n_split, d_partial, partial_stride);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    if (d_naccept) {
+        e = cudaMemsetAsync(d_naccept, 0, sizeof(int), st);
+        if (e != cudaSuccess) return e;
+    }
+    k_match_merge<<<(nq_total + 255) / 256, 256, 0, st>>>(d_partial, partial_stride, n_split, nq_total, k, ratio, d_idx,
+                                                           d_dist, d_accept, d_naccept);
+    return cudaGetLastError();
+}
+
+}  // namespace orbb

@@ -1,0 +1,611 @@
+// orbb_api.cu -- C ABI of liborbb200.so (include/orbb200.h): handle, geometry tables, stage
+// sequencing.  Host-side mirror of the stage-calling block of SlamGpuPipeline::buildStream
+// (reference src/SlamGpuPipeline/buildStream.cpp:208-341 buffer prologue, :416-460 stage order) and
+// of upstream ORBextractor's constructor.  All device memory is allocated once here;
+// nothing on the per-batch path allocates, frees or synchronises (except the *_host / debug calls).
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include "orbb_internal.cuh"
+
+namespace orbb {
+cudaError_t launch_level0(const uint8_t *, size_t, size_t, const LevelDev &, int, cudaStream_t);
+cudaError_t launch_resize(const LevelDev *, const LevelDev &, int, int, cudaStream_t);
+cudaError_t launch_blur(const LevelDev *, const TileEntry *, int, int, cudaStream_t);
+cudaError_t launch_fast(const LevelDev *, const CellEntry *, int, int, int *, int, int, const FastSmemCfg &, int,
+                        cudaStream_t);
+cudaError_t launch_fast_dump(const LevelDev *, const CellEntry *, int, int, int, int, const FastSmemCfg &, int,
+                             uint8_t *, const long long *, cudaStream_t);
+cudaError_t launch_octree(const LevelDev *, int, const int *, int *, int, int, int, int, int, int, int, int,
+                          cudaStream_t);
+size_t octree_dyn_smem(int, int, int);
+cudaError_t launch_angle_orb(const LevelDev *, int, const int *, const int8_t *, const int *, const int *, int, int,
+                             orbb_keypoint *, uint8_t *, int *, int, cudaStream_t);
+cudaError_t launch_match(const uint8_t *, const uint8_t *, const int *, const int *, int, int, int, int, int, int4 *,
+                         int, int, float, int *, int *, uint8_t *, int *, cudaStream_t);
+}  // namespace orbb
+
+using namespace orbb;
+
+static const int8_t k_pattern_host[1024] = {
+#include "../../include/orb_pattern_31.inc"
+};
+
+struct orbb_handle {
+    orbb_params p{};
+    int w = 0, h = 0, max_batch = 0, device = 0, nlevels = 0;
+    LevelDev lv[ORBB_MAX_LEVELS]{};
+    LevelDev *d_levels = nullptr;
+    float sf[ORBB_MAX_LEVELS]{}, inv_sf[ORBB_MAX_LEVELS]{};
+    CellEntry *d_cells = nullptr;
+    int n_cells = 0;
+    TileEntry *d_tiles = nullptr;
+    int n_tiles = 0;
+    FastSmemCfg fcfg{};
+    int t_lo = 7, t_hi = 20;
+    int *d_cand_count = nullptr, *d_sel_count = nullptr;
+    int8_t *d_pattern = nullptr;
+    int *d_slot_level = nullptr, *d_slot_base = nullptr;
+    int n_slots = 0, sel_cap_max = 0, pcap = 0, pcap2 = 0, max_kp = 0;
+    int4 *d_partial = nullptr;
+    size_t partial_cap = 0;
+    uint8_t *d_in = nullptr;  // staging for the *_host entry point
+    orbb_keypoint *d_kp = nullptr;
+    uint8_t *d_desc = nullptr;
+    int *d_counts = nullptr;
+    uint8_t *d_dump = nullptr;
+    long long *d_dump_off = nullptr;
+    std::vector<long long> dump_off;
+    int n_frames_last = 0;
+    std::vector<void *> allocs;
+    char cuda_err[256] = {0};
+};
+
+#define CK(h, call)                                                                                   \
+    do {                                                                                              \
+        cudaError_t e__ = (call);                                                                     \
+        if (e__ != cudaSuccess) {                                                                     \
+            snprintf((h)->cuda_err, sizeof((h)->cuda_err), "%s:%d %s: %s", __FILE__, __LINE__, #call, \
+                     cudaGetErrorString(e__));                                                        \
+            return ORBB_ERR_CUDA;                                                                     \
+        }                                                                                             \
+    } while (0)
+
+template <typename T>
+static cudaError_t dalloc(orbb_handle *h, T **out, size_t count) {
+    void *p = nullptr;
+    cudaError_t e = cudaMalloc(&p, std::max<size_t>(count, 1) * sizeof(T));
+    if (e == cudaSuccess) {
+        h->allocs.push_back(p);
+        *out = static_cast<T *>(p);
+    }
+    return e;
+}
+
+template <typename T>
+static cudaError_t upload(orbb_handle *h, T **out, const std::vector<T> &v) {
+    cudaError_t e = dalloc(h, out, v.size());
+    if (e != cudaSuccess) return e;
+    return cudaMemcpy(*out, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice);
+}
+
+static inline int cv_round(float v) { return (int)lrintf(v); }
+static inline size_t round_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+static inline uint32_t spread_bits(uint32_t v) {  // bit i -> bit 2i
+    uint32_t r = 0;
+    for (int i = 0; i < 16; ++i) r |= ((v >> i) & 1u) << (2 * i);
+    return r;
+}
+
+extern "C" const char *orbb_strerror(int s) {
+    switch (s) {
+        case ORBB_OK: return "ok";
+        case ORBB_ERR_INVALID: return "invalid argument";
+        case ORBB_ERR_NO_DEVICE: return "no usable CUDA device (this library has no CPU path)";
+        case ORBB_ERR_CUDA: return "CUDA runtime error";
+        case ORBB_ERR_TOO_SMALL: return "image too small: a pyramid level would be under 62 px";
+        case ORBB_ERR_CAPACITY: return "capacity exceeded";
+        case ORBB_ERR_SHAPE: return "unsupported image shape";
+        default: return "unknown status";
+    }
+}
+
+extern "C" const char *orbb_last_cuda_error(const orbb_handle *h) { return h ? h->cuda_err : ""; }
+
+extern "C" int orbb_destroy(orbb_handle *h) {
+    if (!h) return ORBB_OK;
+    cudaSetDevice(h->device);
+    for (void *p : h->allocs) cudaFree(p);
+    delete h;
+    return ORBB_OK;
+}
+
+// cv::resize(INTER_LINEAR) coefficient tables, built exactly like OpenCV imgproc/resize.cpp
+static void build_resize_tables(int sw, int sh, int dw, int dh, std::vector<int> &xofs, std::vector<short2> &xalpha,
+                                std::vector<int2> &yrows, std::vector<short2> &ybeta) {
+    const double inv_x = (double)dw / sw, inv_y = (double)dh / sh;
+    const double scale_x = 1. / inv_x, scale_y = 1. / inv_y;
+    xofs.resize(dw); xalpha.resize(dw); yrows.resize(dh); ybeta.resize(dh);
+    for (int dx = 0; dx < dw; ++dx) {
+        float fx = (float)((dx + 0.5) * scale_x - 0.5);
+        int sx = (int)floorf(fx);
+        fx -= sx;
+        if (sx < 0) { fx = 0; sx = 0; }
+        if (sx >= sw - 1) { fx = 0; sx = sw - 1; }
+        xofs[dx] = sx;
+        xalpha[dx] = make_short2((short)cv_round((1.f - fx) * 2048.f), (short)cv_round(fx * 2048.f));
+    }
+    for (int dy = 0; dy < dh; ++dy) {
+        float fy = (float)((dy + 0.5) * scale_y - 0.5);
+        int sy = (int)floorf(fy);
+        fy -= sy;
+        ybeta[dy] = make_short2((short)cv_round((1.f - fy) * 2048.f), (short)cv_round(fy * 2048.f));
+        yrows[dy] = make_int2(std::min(std::max(sy, 0), sh - 1), std::min(std::max(sy + 1, 0), sh - 1));
+    }
+}
+
+extern "C" int orbb_create(orbb_handle **out, const orbb_params *params, int width, int height, int max_batch,
+                           int device) {
+    if (!out || !params) return ORBB_ERR_INVALID;
+    *out = nullptr;
+    if (params->nlevels < 1 || params->nlevels > ORBB_MAX_LEVELS || !(params->scale_factor > 1.0f) ||
+        params->nfeatures < 1 || max_batch < 1 || width < 1 || height < 1 || width > 4096 || height > 4096)
+        return ORBB_ERR_INVALID;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { cudaGetLastError(); return ORBB_ERR_NO_DEVICE; }
+    if (device < 0 && cudaGetDevice(&device) != cudaSuccess) return ORBB_ERR_NO_DEVICE;
+    if (device >= ndev || cudaSetDevice(device) != cudaSuccess) return ORBB_ERR_NO_DEVICE;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess || prop.major < 10) return ORBB_ERR_NO_DEVICE;
+
+    orbb_handle *h = new (std::nothrow) orbb_handle();
+    if (!h) return ORBB_ERR_INVALID;
+    h->p = *params; h->w = width; h->h = height; h->max_batch = max_batch; h->device = device;
+    h->nlevels = params->nlevels;
+    const int nl = h->nlevels, B = max_batch;
+    // thresholds: cv::FAST clamps to [0,255]; ini < min behaves like min := ini (K(t2) subset K(t1))
+    h->t_hi = std::min(std::max(params->ini_th_fast, 0), 255);
+    h->t_lo = std::min(std::min(std::max(params->min_th_fast, 0), 255), h->t_hi);
+
+    // ---- upstream constructor: scale chain and features per level (float32 arithmetic)
+    h->sf[0] = 1.0f;
+    for (int i = 1; i < nl; ++i) h->sf[i] = h->sf[i - 1] * params->scale_factor;
+    for (int i = 0; i < nl; ++i) h->inv_sf[i] = 1.0f / h->sf[i];
+    int nfeat[ORBB_MAX_LEVELS];
+    {
+        const float factor = 1.0f / params->scale_factor;
+        float nd = params->nfeatures * (1 - factor) / (1 - (float)pow((double)factor, (double)nl));
+        int sum = 0;
+        for (int l = 0; l < nl - 1; ++l) {
+            nfeat[l] = cv_round(nd);
+            sum += nfeat[l];
+            nd *= factor;
+        }
+        nfeat[nl - 1] = std::max(params->nfeatures - sum, 0);
+    }
+
+#define CKC(call)                                                                                          \
+    do {                                                                                                   \
+        cudaError_t e__ = (call);                                                                          \
+        if (e__ != cudaSuccess) {                                                                          \
+            fprintf(stderr, "orbb_create: %s failed: %s\n", #call, cudaGetErrorString(e__));               \
+            orbb_destroy(h);                                                                               \
+            return ORBB_ERR_CUDA;                                                                          \
+        }                                                                                                  \
+    } while (0)
+
+    std::vector<CellEntry> cells;
+    std::vector<TileEntry> tiles;
+    std::vector<int> slot_level, slot_base(nl);
+    int max_cw = 1, max_ch = 1;
+    h->dump_off.resize(nl + 1);
+    long long dump_total = 0;
+    for (int l = 0; l < nl; ++l) {
+        LevelDev &L = h->lv[l];
+        L.w = cv_round((float)width * h->inv_sf[l]);
+        L.h = cv_round((float)height * h->inv_sf[l]);
+        if (L.w - 32 < 30 || L.h - 32 < 30) { orbb_destroy(h); return ORBB_ERR_TOO_SMALL; }
+        L.pitch = (int)round_up((size_t)ORBB_ROI_X0 + L.w + ORBB_BORDER, 128);
+        L.rows = L.h + 2 * ORBB_BORDER;
+        L.frame_stride = (long long)round_up((size_t)L.pitch * L.rows, 256);
+        L.blur_stride = (long long)round_up((size_t)L.pitch * L.h, 256);
+        CKC(dalloc(h, &L.img, (size_t)L.frame_stride * B));
+        CKC(dalloc(h, &L.blur, (size_t)L.blur_stride * B));
+        CKC(cudaMemset(L.img, 0, (size_t)L.frame_stride * B));
+        L.scale = h->sf[l];
+        L.patch_size = (float)(int)(31 * h->sf[l]);
+        L.nfeat = nfeat[l];
+        h->dump_off[l] = dump_total;
+        dump_total += (long long)L.w * L.h;
+        // resize tables
+        if (l > 0) {
+            const LevelDev &S = h->lv[l - 1];
+            L.src_w = S.w; L.src_h = S.h;
+            L.area2x = (S.w == 2 * L.w && S.h == 2 * L.h) ? 1 : 0;
+            std::vector<int> xofs; std::vector<short2> xa; std::vector<int2> yr; std::vector<short2> yb;
+            build_resize_tables(S.w, S.h, L.w, L.h, xofs, xa, yr, yb);
+            int *dxofs; short2 *dxa; int2 *dyr; short2 *dyb;
+            CKC(upload(h, &dxofs, xofs)); CKC(upload(h, &dxa, xa)); CKC(upload(h, &dyr, yr)); CKC(upload(h, &dyb, yb));
+            L.xofs = dxofs; L.xalpha = dxa; L.yrows = dyr; L.ybeta = dyb;
+        }
+        // ---- per-cell FAST grid (upstream ComputeKeyPointsOctTree)
+        const int W = L.w - 32, H = L.h - 32;  // maxBorder - minBorder
+        const float fw = (float)W, fh = (float)H;
+        const int nCols = (int)(fw / 30.f), nRows = (int)(fh / 30.f);
+        L.w_cell = (int)ceilf(fw / nCols);
+        L.h_cell = (int)ceilf(fh / nRows);
+        L.n_cell_x = L.n_cell_y = 0;
+        int cap = 0;
+        for (int i = 0; i < nRows; ++i) {
+            const int y0 = ORBB_BORDER + i * L.h_cell, ch = std::min(L.h_cell, L.h - ORBB_BORDER - y0);
+            if (ch <= 0) continue;
+            L.n_cell_y = i + 1;
+            for (int j = 0; j < nCols; ++j) {
+                const int x0 = ORBB_BORDER + j * L.w_cell, cw = std::min(L.w_cell, L.w - ORBB_BORDER - x0);
+                if (cw <= 0) continue;
+                L.n_cell_x = std::max(L.n_cell_x, j + 1);
+                CellEntry c{};
+                c.level = (int16_t)l; c.x0 = (int16_t)x0; c.y0 = (int16_t)y0; c.cw = (int16_t)cw; c.ch = (int16_t)ch;
+                cells.push_back(c);
+                max_cw = std::max(max_cw, cw); max_ch = std::max(max_ch, ch);
+                cap += ((cw + 1) / 2) * ((ch + 1) / 2);  // strict 3x3 maxima: at most one per 2x2 block
+            }
+        }
+        if (L.w_cell > 63 || L.h_cell > 63) { orbb_destroy(h); return ORBB_ERR_SHAPE; }
+        L.cand_cap = (int)round_up((size_t)cap + 32, 64);
+        if (L.cand_cap >= (1 << 22)) { orbb_destroy(h); return ORBB_ERR_SHAPE; }
+        // ---- quadtree tables (upstream DistributeOctTree / DivideNode)
+        L.n_ini = (int)roundf((float)W / H);
+        if (L.n_ini < 1) { orbb_destroy(h); return ORBB_ERR_SHAPE; }
+        const float hX = (float)W / L.n_ini;
+        int root_bits = 0;
+        while ((1 << root_bits) < L.n_ini) ++root_bits;
+        int max_dim = H;
+        for (int r = 0; r < L.n_ini; ++r) max_dim = std::max(max_dim, (int)(hX * (float)(r + 1)) - (int)(hX * (float)r));
+        int D = 1;
+        while ((1 << D) < max_dim) ++D;
+        D += 1;  // one more level parts keys sitting on a root's right edge from its last column
+        L.depth = D;
+        L.key_bits = 2 * D + root_bits;
+        if (L.key_bits > 32 || D > 15) { orbb_destroy(h); return ORBB_ERR_SHAPE; }
+        std::vector<uint32_t> xkey(W), ykey(H);
+        std::vector<uint16_t> xord(W), yord(H);
+        for (int x = 0; x < W; ++x) {
+            int root = (int)((float)x / hX);
+            root = std::min(root, L.n_ini - 1);
+            int lo = (int)(hX * (float)root), hi = (int)(hX * (float)(root + 1));
+            uint32_t bits = 0;
+            for (int d = 0; d < D; ++d) {
+                const int half = (int)ceilf((float)(hi - lo) / 2);
+                const int mid = lo + half;
+                if (x < mid) { hi = mid; bits = bits << 1; }
+                else { lo = mid; bits = (bits << 1) | 1u; }
+            }
+            xkey[x] = ((uint32_t)root << (2 * D)) | spread_bits(bits);
+            const int t = std::max(x - 3, 0), j = t / L.w_cell;
+            xord[x] = (uint16_t)((j << 6) | (t - j * L.w_cell));
+        }
+        for (int y = 0; y < H; ++y) {
+            int lo = 0, hi = H;
+            uint32_t bits = 0;
+            for (int d = 0; d < D; ++d) {
+                const int half = (int)ceilf((float)(hi - lo) / 2);
+                const int mid = lo + half;
+                if (y < mid) { hi = mid; bits = bits << 1; }
+                else { lo = mid; bits = (bits << 1) | 1u; }
+            }
+            ykey[y] = spread_bits(bits) << 1;
+            const int t = std::max(y - 3, 0), i = t / L.h_cell;
+            yord[y] = (uint16_t)((i << 6) | (t - i * L.h_cell));
+        }
+        uint32_t *dxk, *dyk; uint16_t *dxo, *dyo;
+        CKC(upload(h, &dxk, xkey)); CKC(upload(h, &dyk, ykey)); CKC(upload(h, &dxo, xord)); CKC(upload(h, &dyo, yord));
+        L.xkey = dxk; L.ykey = dyk; L.xord = dxo; L.yord = dyo;
+        L.sel_cap = std::max(L.nfeat, 4 * L.n_ini) + 8;
+        const size_t cc = (size_t)L.cand_cap * B;
+        CKC(dalloc(h, &L.cand, cc)); CKC(dalloc(h, &L.key_a, cc)); CKC(dalloc(h, &L.key_b, cc));
+        CKC(dalloc(h, &L.idx_a, cc)); CKC(dalloc(h, &L.idx_b, cc)); CKC(dalloc(h, &L.sd, cc));
+        CKC(dalloc(h, &L.sel, (size_t)L.sel_cap * B));
+        slot_base[l] = (int)slot_level.size();
+        for (int s = 0; s < L.sel_cap; ++s) slot_level.push_back(l);
+        h->sel_cap_max = std::max(h->sel_cap_max, L.sel_cap);
+        // blur tiles
+        for (int ty = 0; ty < (L.h + 31) / 32; ++ty)
+            for (int tx = 0; tx < (L.w + 63) / 64; ++tx) {
+                TileEntry t{}; t.level = (int16_t)l; t.tx = (int16_t)tx; t.ty = (int16_t)ty;
+                tiles.push_back(t);
+            }
+    }
+    h->dump_off[nl] = dump_total;
+    h->n_cells = (int)cells.size(); h->n_tiles = (int)tiles.size(); h->n_slots = (int)slot_level.size();
+    h->max_kp = h->n_slots;
+    h->pcap = h->sel_cap_max; h->pcap2 = 1;
+    while (h->pcap2 < h->pcap) h->pcap2 <<= 1;
+    if (octree_dyn_smem(h->sel_cap_max, h->pcap, h->pcap2) > 200 * 1024) { orbb_destroy(h); return ORBB_ERR_CAPACITY; }
+    h->fcfg.tile_pitch = (int)round_up(max_cw + 12, 4);
+    h->fcfg.tile_rows = max_ch + 6;
+    h->fcfg.score_pitch = (int)round_up(max_cw + 2, 4);
+    h->fcfg.score_rows = max_ch + 2;
+    h->fcfg.queue_len = (int)round_up((size_t)max_cw * max_ch, 8);
+    h->fcfg.warp_bytes = (int)round_up((size_t)h->fcfg.tile_pitch * h->fcfg.tile_rows +
+                                           (size_t)h->fcfg.score_pitch * h->fcfg.score_rows + 2 * (size_t)h->fcfg.queue_len, 16);
+    CKC(upload(h, &h->d_cells, cells));
+    CKC(upload(h, &h->d_tiles, tiles));
+    CKC(upload(h, &h->d_slot_level, slot_level));
+    CKC(upload(h, &h->d_slot_base, slot_base));
+    {
+        std::vector<int8_t> pat(k_pattern_host, k_pattern_host + 1024);
+        CKC(upload(h, &h->d_pattern, pat));
+        std::vector<LevelDev> lv(h->lv, h->lv + nl);
+        CKC(upload(h, &h->d_levels, lv));
+        CKC(upload(h, &h->d_dump_off, h->dump_off));
+    }
+    CKC(dalloc(h, &h->d_cand_count, (size_t)B * nl));
+    CKC(dalloc(h, &h->d_sel_count, (size_t)B * nl));
+    CKC(cudaMemset(h->d_cand_count, 0, sizeof(int) * (size_t)B * nl));
+    CKC(cudaMemset(h->d_sel_count, 0, sizeof(int) * (size_t)B * nl));
+    CKC(dalloc(h, &h->d_in, (size_t)width * height * B));
+    CKC(dalloc(h, &h->d_kp, (size_t)h->max_kp * B));
+    CKC(dalloc(h, &h->d_desc, (size_t)h->max_kp * B * 32));
+    CKC(dalloc(h, &h->d_counts, (size_t)B));
+    CKC(dalloc(h, &h->d_dump, (size_t)dump_total));
+    CKC(cudaDeviceSynchronize());
+#undef CKC
+    *out = h;
+    return ORBB_OK;
+}
+
+// ---------------------------------------------------------------- getters
+extern "C" int orbb_get_levels(const orbb_handle *h) { return h ? h->nlevels : ORBB_ERR_INVALID; }
+
+extern "C" int orbb_get_scale_factors(const orbb_handle *h, float *scale, float *inv_scale, float *sigma2,
+                                      float *inv_sigma2) {
+    if (!h) return ORBB_ERR_INVALID;
+    for (int l = 0; l < h->nlevels; ++l) {
+        const float s2 = l == 0 ? 1.0f : h->sf[l] * h->sf[l];
+        if (scale) scale[l] = h->sf[l];
+        if (inv_scale) inv_scale[l] = h->inv_sf[l];
+        if (sigma2) sigma2[l] = s2;
+        if (inv_sigma2) inv_sigma2[l] = 1.0f / s2;
+    }
+    return ORBB_OK;
+}
+
+extern "C" int orbb_get_features_per_level(const orbb_handle *h, int32_t *nfeat) {
+    if (!h || !nfeat) return ORBB_ERR_INVALID;
+    for (int l = 0; l < h->nlevels; ++l) nfeat[l] = h->lv[l].nfeat;
+    return ORBB_OK;
+}
+
+extern "C" int orbb_max_keypoints_per_frame(const orbb_handle *h) { return h ? h->max_kp : ORBB_ERR_INVALID; }
+
+extern "C" int orbb_get_level(const orbb_handle *h, int frame, int level, orbb_level *out) {
+    if (!h || !out || level < 0 || level >= h->nlevels || frame < 0 || frame >= h->max_batch) return ORBB_ERR_INVALID;
+    const LevelDev &L = h->lv[level];
+    out->width = L.w; out->height = L.h; out->pitch = L.pitch; out->roi_offset = ORBB_BORDER;
+    out->padded = L.img + (size_t)frame * L.frame_stride + ORBB_PAD_X0;
+    out->blurred = L.blur + (size_t)frame * L.blur_stride;
+    out->scale = h->sf[level]; out->inv_scale = h->inv_sf[level]; out->nfeatures = L.nfeat;
+    return ORBB_OK;
+}
+
+// ---------------------------------------------------------------- stages
+extern "C" int orbb_stage_upload(orbb_handle *h, const uint8_t *d_images, size_t pitch, size_t frame_stride,
+                                 int n_frames, void *stream) {
+    if (!h || !d_images || n_frames < 1 || pitch < (size_t)h->w) return ORBB_ERR_INVALID;
+    if (n_frames > h->max_batch) return ORBB_ERR_CAPACITY;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    CK(h, cudaSetDevice(h->device));
+    h->n_frames_last = n_frames;
+    CK(h, cudaMemsetAsync(h->d_cand_count, 0, sizeof(int) * (size_t)n_frames * h->nlevels, st));
+    CK(h, launch_level0(d_images, pitch, frame_stride, h->lv[0], n_frames, st));
+    return ORBB_OK;
+}
+
+extern "C" int orbb_pyramid_create_levels(orbb_handle *h, void *stream) {
+    if (!h || h->n_frames_last < 1) return ORBB_ERR_INVALID;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    for (int l = 1; l < h->nlevels; ++l) CK(h, launch_resize(h->d_levels, h->lv[l], l, h->n_frames_last, st));
+    return ORBB_OK;
+}
+
+extern "C" int orbb_detect(orbb_handle *h, void *stream) {
+    if (!h || h->n_frames_last < 1) return ORBB_ERR_INVALID;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    CK(h, launch_fast(h->d_levels, h->d_cells, h->n_cells, h->nlevels, h->d_cand_count, h->t_lo, h->t_hi, h->fcfg,
+                      h->n_frames_last, st));
+    CK(h, launch_octree(h->d_levels, h->nlevels, h->d_cand_count, h->d_sel_count, 0, h->nlevels, 0, h->n_frames_last,
+                        -1, h->sel_cap_max, h->pcap, h->pcap2, st));
+    return ORBB_OK;
+}
+
+extern "C" int orbb_gaussian_blur(orbb_handle *h, void *stream) {
+    if (!h || h->n_frames_last < 1) return ORBB_ERR_INVALID;
+    CK(h, launch_blur(h->d_levels, h->d_tiles, h->n_tiles, h->n_frames_last, static_cast<cudaStream_t>(stream)));
+    return ORBB_OK;
+}
+
+extern "C" int orbb_compute_angle_and_orb(orbb_handle *h, orbb_keypoint *d_kp, uint8_t *d_desc, int32_t *d_counts,
+                                          int max_kp, void *stream) {
+    if (!h || !d_kp || !d_desc || !d_counts || max_kp < 1 || h->n_frames_last < 1) return ORBB_ERR_INVALID;
+    CK(h, launch_angle_orb(h->d_levels, h->nlevels, h->d_sel_count, h->d_pattern, h->d_slot_level, h->d_slot_base,
+                           h->n_slots, h->n_frames_last, d_kp, d_desc, d_counts, max_kp,
+                           static_cast<cudaStream_t>(stream)));
+    return ORBB_OK;
+}
+
+extern "C" int orbb_extract_batch_device(orbb_handle *h, const uint8_t *d_images, size_t pitch, size_t frame_stride,
+                                         int n_frames, orbb_keypoint *d_kp, uint8_t *d_desc, int32_t *d_counts,
+                                         int max_kp, void *stream) {
+    int rc = orbb_stage_upload(h, d_images, pitch, frame_stride, n_frames, stream);
+    if (rc) return rc;
+    if ((rc = orbb_pyramid_create_levels(h, stream))) return rc;
+    if ((rc = orbb_detect(h, stream))) return rc;
+    if ((rc = orbb_gaussian_blur(h, stream))) return rc;
+    return orbb_compute_angle_and_orb(h, d_kp, d_desc, d_counts, max_kp, stream);
+}
+
+extern "C" int orbb_extract_batch_host(orbb_handle *h, const uint8_t *h_images, size_t pitch, size_t frame_stride,
+                                       int n_frames, orbb_keypoint *h_kp, uint8_t *h_desc, int32_t *h_counts,
+                                       int max_kp, void *stream) {
+    if (!h || !h_images || !h_kp || !h_desc || !h_counts || max_kp < 1) return ORBB_ERR_INVALID;
+    if (n_frames < 1 || n_frames > h->max_batch) return ORBB_ERR_CAPACITY;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    CK(h, cudaSetDevice(h->device));
+    const size_t fw = (size_t)h->w, fsz = fw * h->h;
+    if (pitch == fw && frame_stride == fsz) {
+        CK(h, cudaMemcpyAsync(h->d_in, h_images, fsz * n_frames, cudaMemcpyHostToDevice, st));
+    } else if (frame_stride == pitch * (size_t)h->h) {
+        CK(h, cudaMemcpy2DAsync(h->d_in, fw, h_images, pitch, fw, (size_t)h->h * n_frames, cudaMemcpyHostToDevice, st));
+    } else {
+        for (int f = 0; f < n_frames; ++f)
+            CK(h, cudaMemcpy2DAsync(h->d_in + fsz * f, fw, h_images + frame_stride * f, pitch, fw, h->h,
+                                    cudaMemcpyHostToDevice, st));
+    }
+    const int mk = std::min(max_kp, h->max_kp);
+    int rc = orbb_extract_batch_device(h, h->d_in, fw, fsz, n_frames, h->d_kp, h->d_desc, h->d_counts, mk, stream);
+    if (rc) return rc;
+    CK(h, cudaMemcpyAsync(h_counts, h->d_counts, sizeof(int) * n_frames, cudaMemcpyDeviceToHost, st));
+    CK(h, cudaMemcpy2DAsync(h_kp, sizeof(orbb_keypoint) * max_kp, h->d_kp, sizeof(orbb_keypoint) * mk,
+                            sizeof(orbb_keypoint) * mk, n_frames, cudaMemcpyDeviceToHost, st));
+    CK(h, cudaMemcpy2DAsync(h_desc, 32 * (size_t)max_kp, h->d_desc, 32 * (size_t)mk, 32 * (size_t)mk, n_frames,
+                            cudaMemcpyDeviceToHost, st));
+    CK(h, cudaStreamSynchronize(st));
+    return ORBB_OK;
+}
+
+// ---------------------------------------------------------------- matcher
+static int ensure_partial(orbb_handle *h, size_t need) {
+    if (need <= h->partial_cap) return ORBB_OK;
+    int4 *p = nullptr;
+    CK(h, dalloc(h, &p, need));  // grows monotonically; old block is released in orbb_destroy
+    h->d_partial = p;
+    h->partial_cap = need;
+    return ORBB_OK;
+}
+
+static int pick_split(int qblocks_total, int nt) {
+    int want = (2 * 148 + qblocks_total - 1) / std::max(qblocks_total, 1);
+    want = std::min(want, std::max(1, nt / 256));
+    return std::max(1, std::min(want, 64));
+}
+
+extern "C" int orbb_match_knn(orbb_handle *h, const uint8_t *d_query, int nq, const uint8_t *d_train, int nt, int k,
+                              float ratio, int32_t *d_idx, int32_t *d_dist, uint8_t *d_accept, int32_t *d_naccept,
+                              void *stream) {
+    if (!h || !d_query || !d_train || !d_idx || !d_dist || nq < 0 || nt < 0 || k < 1 || k > 2) return ORBB_ERR_INVALID;
+    if ((reinterpret_cast<uintptr_t>(d_query) | reinterpret_cast<uintptr_t>(d_train)) & 15) return ORBB_ERR_INVALID;
+    if (nq == 0) return ORBB_OK;
+    const int qblocks = (nq + 255) / 256;
+    const int n_split = pick_split(qblocks, nt);
+    int rc = ensure_partial(h, (size_t)n_split * nq);
+    if (rc) return rc;
+    CK(h, launch_match(d_query, d_train, nullptr, nullptr, 1, nq, nq, nt, n_split, h->d_partial, nq, k, ratio, d_idx,
+                       d_dist, d_accept, d_naccept, static_cast<cudaStream_t>(stream)));
+    return ORBB_OK;
+}
+
+extern "C" int orbb_match_knn_segmented(orbb_handle *h, const uint8_t *d_query, const int32_t *d_q_offsets,
+                                        const uint8_t *d_train, const int32_t *d_t_offsets, int nseg,
+                                        int max_q_per_seg, int k, float ratio, int32_t *d_idx, int32_t *d_dist,
+                                        uint8_t *d_accept, void *stream) {
+    if (!h || !d_query || !d_train || !d_q_offsets || !d_t_offsets || !d_idx || !d_dist || nseg < 1 ||
+        max_q_per_seg < 1 || k < 1 || k > 2)
+        return ORBB_ERR_INVALID;
+    if ((reinterpret_cast<uintptr_t>(d_query) | reinterpret_cast<uintptr_t>(d_train)) & 15) return ORBB_ERR_INVALID;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    int nq_total = 0;  // last offset; one small D2H (the offsets are the caller's, sizes are needed for the grid)
+    CK(h, cudaMemcpyAsync(&nq_total, d_q_offsets + nseg, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CK(h, cudaStreamSynchronize(st));
+    if (nq_total <= 0) return ORBB_OK;
+    const int qblocks = (max_q_per_seg + 255) / 256 * nseg;
+    const int n_split = pick_split(qblocks, 1024);
+    int rc = ensure_partial(h, (size_t)n_split * nq_total);
+    if (rc) return rc;
+    CK(h, launch_match(d_query, d_train, d_q_offsets, d_t_offsets, nseg, nq_total, max_q_per_seg, 0, n_split,
+                       h->d_partial, nq_total, k, ratio, d_idx, d_dist, d_accept, nullptr, st));
+    return ORBB_OK;
+}
+
+// ---------------------------------------------------------------- debug / parity access
+extern "C" int orbb_debug_get_padded(orbb_handle *h, int frame, int level, uint8_t *host_out) {
+    if (!h || !host_out || level < 0 || level >= h->nlevels || frame < 0 || frame >= h->max_batch) return ORBB_ERR_INVALID;
+    const LevelDev &L = h->lv[level];
+    CK(h, cudaDeviceSynchronize());
+    CK(h, cudaMemcpy2D(host_out, L.w + 38, L.img + (size_t)frame * L.frame_stride + ORBB_PAD_X0, L.pitch, L.w + 38,
+                       L.h + 38, cudaMemcpyDeviceToHost));
+    return ORBB_OK;
+}
+
+extern "C" int orbb_debug_get_blurred(orbb_handle *h, int frame, int level, uint8_t *host_out) {
+    if (!h || !host_out || level < 0 || level >= h->nlevels || frame < 0 || frame >= h->max_batch) return ORBB_ERR_INVALID;
+    const LevelDev &L = h->lv[level];
+    CK(h, cudaDeviceSynchronize());
+    CK(h, cudaMemcpy2D(host_out, L.w, L.blur + (size_t)frame * L.blur_stride, L.pitch, L.w, L.h, cudaMemcpyDeviceToHost));
+    return ORBB_OK;
+}
+
+extern "C" int orbb_debug_get_scores(orbb_handle *h, int frame, int level, uint8_t *host_out) {
+    if (!h || !host_out || level < 0 || level >= h->nlevels || frame < 0 || frame >= h->max_batch) return ORBB_ERR_INVALID;
+    const LevelDev &L = h->lv[level];
+    CK(h, cudaMemset(h->d_dump, 0, (size_t)h->dump_off[h->nlevels]));
+    CK(h, launch_fast_dump(h->d_levels, h->d_cells, h->n_cells, h->nlevels, h->t_lo, h->t_hi, h->fcfg, frame, h->d_dump,
+                           h->d_dump_off, 0));
+    CK(h, cudaDeviceSynchronize());
+    CK(h, cudaMemcpy(host_out, h->d_dump + h->dump_off[level], (size_t)L.w * L.h, cudaMemcpyDeviceToHost));
+    return ORBB_OK;
+}
+
+static int download_packed(orbb_handle *h, const uint32_t *d_src, int n, int32_t *host_xyr, int max_n) {
+    std::vector<uint32_t> tmp((size_t)std::max(n, 1));
+    CK(h, cudaMemcpy(tmp.data(), d_src, sizeof(uint32_t) * (size_t)n, cudaMemcpyDeviceToHost));
+    for (int i = 0; i < n && i < max_n; ++i) {
+        host_xyr[3 * i] = (int)(tmp[i] & 0xfffu);
+        host_xyr[3 * i + 1] = (int)((tmp[i] >> 12) & 0xfffu);
+        host_xyr[3 * i + 2] = (int)(tmp[i] >> 24) - 1;  // response = arc score - 1
+    }
+    return n;
+}
+
+extern "C" int orbb_debug_get_candidates(orbb_handle *h, int frame, int level, int32_t *host_xyr, int max_n) {
+    if (!h || !host_xyr || level < 0 || level >= h->nlevels || frame < 0 || frame >= h->max_batch) return ORBB_ERR_INVALID;
+    const LevelDev &L = h->lv[level];
+    int n = 0;
+    CK(h, cudaDeviceSynchronize());
+    CK(h, cudaMemcpy(&n, h->d_cand_count + frame * h->nlevels + level, sizeof(int), cudaMemcpyDeviceToHost));
+    n = std::min(n, L.cand_cap);
+    return download_packed(h, L.cand + (size_t)frame * L.cand_cap, n, host_xyr, max_n);
+}
+
+extern "C" int orbb_debug_get_selected(orbb_handle *h, int frame, int level, int32_t *host_xyr, int max_n) {
+    if (!h || !host_xyr || level < 0 || level >= h->nlevels || frame < 0 || frame >= h->max_batch) return ORBB_ERR_INVALID;
+    const LevelDev &L = h->lv[level];
+    int n = 0;
+    CK(h, cudaDeviceSynchronize());
+    CK(h, cudaMemcpy(&n, h->d_sel_count + frame * h->nlevels + level, sizeof(int), cudaMemcpyDeviceToHost));
+    n = std::min(n, L.sel_cap);
+    return download_packed(h, L.sel + (size_t)frame * L.sel_cap, n, host_xyr, max_n);
+}
+
+extern "C" int orbb_debug_distribute(orbb_handle *h, int level, const int32_t *host_xyr, int n, int quota,
+                                     int32_t *host_out_xyr, int max_out) {
+    if (!h || !host_xyr || !host_out_xyr || level < 0 || level >= h->nlevels || n < 0 || quota < 0) return ORBB_ERR_INVALID;
+    const LevelDev &L = h->lv[level];
+    if (n > L.cand_cap || std::max(quota, 4 * L.n_ini) + 8 > L.sel_cap) return ORBB_ERR_CAPACITY;
+    std::vector<uint32_t> packed((size_t)std::max(n, 1));
+    for (int i = 0; i < n; ++i) {
+        const int x = host_xyr[3 * i], y = host_xyr[3 * i + 1], r = host_xyr[3 * i + 2];
+        if (x < 0 || x >= L.w - 32 || y < 0 || y >= L.h - 32 || r < 0 || r > 254) return ORBB_ERR_INVALID;
+        packed[i] = (uint32_t)x | ((uint32_t)y << 12) | ((uint32_t)(r + 1) << 24);
+    }
+    CK(h, cudaDeviceSynchronize());
+    CK(h, cudaMemcpy(L.cand, packed.data(), sizeof(uint32_t) * (size_t)n, cudaMemcpyHostToDevice));
+    CK(h, cudaMemcpy(h->d_cand_count + level, &n, sizeof(int), cudaMemcpyHostToDevice));
+    CK(h, launch_octree(h->d_levels, h->nlevels, h->d_cand_count, h->d_sel_count, level, 1, 0, 1, quota, h->sel_cap_max,
+                        h->pcap, h->pcap2, 0));
+    return orbb_debug_get_selected(h, 0, level, host_out_xyr, max_out);
+}

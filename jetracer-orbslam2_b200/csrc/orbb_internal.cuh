@@ -1,0 +1,66 @@
+// orbb_internal.cuh -- structures shared by the host API and the sm_100a kernels.
+//
+// HBM layout (one handle, batch of B frames, level l):
+//   img[l]   : B x (h_l+38) rows x pitch_l bytes.  pitch_l = roundup(32 + w_l + 19, 128).  A row is
+//              [13 unused][19 border][w_l ROI][19 border][pad]: ROI pixel 0 sits at byte 32, so ROI
+//              rows are 16-byte aligned for 128-bit vector access; the (w+38)x(h+38) "padded level"
+//              of upstream ComputePyramid is the view starting at byte 13.
+//   blur[l]  : B x h_l rows x pitch_l bytes, ROI pixel 0 at byte 0 (7x7 Gaussian of the ROI).
+//   cand[l]  : B x cand_cap_l packed u32 (x_rel:12 | y_rel:12 | m:8) written by the FAST kernel.
+//   key/idx ping-pong + sd/head scratch for the quadtree kernel, sel[l] : B x sel_cap_l packed u32.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/orbb200.h"
+
+#define ORBB_ROI_X0 32  // byte offset of ROI column 0 inside a padded row
+#define ORBB_PAD_X0 13  // byte offset of padded column 0 (= ORBB_ROI_X0 - 19)
+#define ORBB_BORDER 19
+#define ORBB_MIN_BORDER 16  // upstream minBorderX/Y = EDGE_THRESHOLD - 3
+
+namespace orbb {
+
+// Device-visible description of one pyramid level (array of nlevels lives in HBM).
+struct LevelDev {
+    int w, h, pitch, rows;       // ROI size, bytes per row, rows per frame (h + 38)
+    long long frame_stride;      // bytes between frames in img
+    long long blur_stride;       // bytes between frames in blur
+    uint8_t *img, *blur;
+    // cv::resize tables for producing THIS level from level-1 (unused for level 0)
+    const int *xofs;             // [w] source column
+    const short2 *xalpha;        // [w] (a0,a1), 11-bit fixed point
+    const int2 *yrows;           // [h] (clipped row0,row1)
+    const short2 *ybeta;         // [h] (b0,b1)
+    int src_w, src_h, area2x;
+    // per-cell FAST grid (tested range starts at ROI (19,19))
+    int w_cell, h_cell, n_cell_x, n_cell_y;
+    // quadtree
+    int nfeat, n_ini, depth, key_bits;
+    const uint32_t *xkey, *ykey; // [w-32], [h-32]: Morton-spread path bits (+root) per coordinate
+    const uint16_t *xord, *yord; // [w-32], [h-32]: (cell index << 6 | offset in cell)
+    int cand_cap, sel_cap;
+    uint32_t *cand;              // B x cand_cap
+    uint32_t *key_a, *key_b, *idx_a, *idx_b;  // B x cand_cap each (radix ping-pong)
+    uint8_t *sd;                 // B x cand_cap: split depth of adjacent sorted keys
+    uint32_t *sel;               // B x sel_cap packed selected keys
+    float scale, patch_size;     // mvScaleFactor[l], (float)(int)(31*scale)
+};
+
+struct CellEntry {  // one FAST work item = one upstream 30-px cell
+    int16_t level, x0, y0, cw, ch, pad0, pad1, pad2;  // tested-range origin (ROI coords) and size
+};
+
+struct TileEntry {  // generic 2-D tile of a level (blur kernel)
+    int16_t level, tx, ty, pad;
+};
+
+struct FastSmemCfg {
+    int tile_pitch, tile_rows;    // bytes, rows of the per-warp image tile
+    int score_pitch, score_rows;  // per-warp score tile (1-px zero frame)
+    int queue_len;                // u16 entries
+    int warp_bytes;               // total per warp (multiple of 16)
+};
+
+}  // namespace orbb

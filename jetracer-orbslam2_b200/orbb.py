@@ -1,0 +1,314 @@
+"""ctypes binding of liborbb200.so (include/orbb200.h) -- the host-side mirror, in Python, of the
+reference's ORB stage interface.
+
+Names follow the reference / upstream operator surface so parity tests read like its own would:
+  * ``ORBextractor(nfeatures, scaleFactor, nlevels, iniThFAST, minThFAST)`` with
+    ``__call__(image, mask=None) -> (keypoints, descriptors)`` and the ``GetLevels`` / ``GetScaleFactors``
+    getters (upstream ORB-SLAM2 surface named by reference src_trash1/orb_extractor.cpp:6-8);
+  * the stage functions of namespace Jetracer (reference src/cuda/{pyramid,fast,nms,orb,post_processing}.cuh):
+    ``pyramid_create_levels``, ``detect``, ``gaussian_blur``, ``compute_fast_angle_and_orb``, ``match_keypoints``.
+
+There is NO CPU fallback: if the shared library is missing or no B200 is visible, construction raises.
+PyTorch is only plumbing here (device buffers / streams for the device-resident entry points).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "liborbb200.so")
+
+KEYPOINT_DTYPE = np.dtype(
+    [("x", "<f4"), ("y", "<f4"), ("size", "<f4"), ("angle", "<f4"), ("response", "<f4"),
+     ("octave", "<i4"), ("class_id", "<i4")]
+)
+
+EXPORTS = [
+    "orbb_create", "orbb_destroy", "orbb_strerror", "orbb_last_cuda_error", "orbb_get_levels",
+    "orbb_get_scale_factors", "orbb_get_features_per_level", "orbb_max_keypoints_per_frame", "orbb_get_level",
+    "orbb_extract_batch_device", "orbb_extract_batch_host", "orbb_stage_upload", "orbb_pyramid_create_levels",
+    "orbb_detect", "orbb_gaussian_blur", "orbb_compute_angle_and_orb", "orbb_match_knn",
+    "orbb_match_knn_segmented", "orbb_debug_get_padded", "orbb_debug_get_blurred", "orbb_debug_get_scores",
+    "orbb_debug_get_candidates", "orbb_debug_get_selected", "orbb_debug_distribute",
+]
+
+
+class OrbbError(RuntimeError):
+    pass
+
+
+class Params(C.Structure):
+    _fields_ = [("nfeatures", C.c_int32), ("scale_factor", C.c_float), ("nlevels", C.c_int32),
+                ("ini_th_fast", C.c_int32), ("min_th_fast", C.c_int32)]
+
+
+class Level(C.Structure):
+    _fields_ = [("width", C.c_int32), ("height", C.c_int32), ("pitch", C.c_int32), ("roi_offset", C.c_int32),
+                ("padded", C.c_void_p), ("blurred", C.c_void_p), ("scale", C.c_float), ("inv_scale", C.c_float),
+                ("nfeatures", C.c_int32)]
+
+
+_lib = None
+
+
+def load_library():
+    """dlopen liborbb200.so and declare every prototype of include/orbb200.h.  Raises if it is missing."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise OrbbError(f"{LIB_PATH} not built: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                        "(there is no CPU fallback)")
+    L = C.CDLL(LIB_PATH)
+    vp, i32, sz, f32 = C.c_void_p, C.c_int, C.c_size_t, C.c_float
+    L.orbb_create.argtypes = [C.POINTER(vp), C.POINTER(Params), i32, i32, i32, i32]
+    L.orbb_destroy.argtypes = [vp]
+    L.orbb_strerror.argtypes = [i32]
+    L.orbb_strerror.restype = C.c_char_p
+    L.orbb_last_cuda_error.argtypes = [vp]
+    L.orbb_last_cuda_error.restype = C.c_char_p
+    L.orbb_get_levels.argtypes = [vp]
+    L.orbb_get_scale_factors.argtypes = [vp, vp, vp, vp, vp]
+    L.orbb_get_features_per_level.argtypes = [vp, vp]
+    L.orbb_max_keypoints_per_frame.argtypes = [vp]
+    L.orbb_get_level.argtypes = [vp, i32, i32, C.POINTER(Level)]
+    L.orbb_extract_batch_device.argtypes = [vp, vp, sz, sz, i32, vp, vp, vp, i32, vp]
+    L.orbb_extract_batch_host.argtypes = [vp, vp, sz, sz, i32, vp, vp, vp, i32, vp]
+    L.orbb_stage_upload.argtypes = [vp, vp, sz, sz, i32, vp]
+    L.orbb_pyramid_create_levels.argtypes = [vp, vp]
+    L.orbb_detect.argtypes = [vp, vp]
+    L.orbb_gaussian_blur.argtypes = [vp, vp]
+    L.orbb_compute_angle_and_orb.argtypes = [vp, vp, vp, vp, i32, vp]
+    L.orbb_match_knn.argtypes = [vp, vp, i32, vp, i32, i32, f32, vp, vp, vp, vp, vp]
+    L.orbb_match_knn_segmented.argtypes = [vp, vp, vp, vp, vp, i32, i32, i32, f32, vp, vp, vp, vp]
+    L.orbb_debug_get_padded.argtypes = [vp, i32, i32, vp]
+    L.orbb_debug_get_blurred.argtypes = [vp, i32, i32, vp]
+    L.orbb_debug_get_scores.argtypes = [vp, i32, i32, vp]
+    L.orbb_debug_get_candidates.argtypes = [vp, i32, i32, vp, i32]
+    L.orbb_debug_get_selected.argtypes = [vp, i32, i32, vp, i32]
+    L.orbb_debug_distribute.argtypes = [vp, i32, vp, i32, i32, vp, i32]
+    for name in EXPORTS:
+        fn = getattr(L, name)
+        if name not in ("orbb_strerror", "orbb_last_cuda_error"):
+            fn.restype = C.c_int
+    _lib = L
+    return L
+
+
+def _np_ptr(a: np.ndarray):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def _dev_ptr(t):
+    """torch CUDA tensor or raw int address -> void*"""
+    if hasattr(t, "data_ptr"):
+        if not t.is_cuda or not t.is_contiguous():
+            raise OrbbError("device entry points need contiguous CUDA tensors")
+        return C.c_void_p(t.data_ptr())
+    return C.c_void_p(int(t))
+
+
+def _stream_ptr(stream):
+    if stream is None:
+        return C.c_void_p(0)
+    if hasattr(stream, "cuda_stream"):
+        return C.c_void_p(stream.cuda_stream)
+    return C.c_void_p(int(stream))
+
+
+class ORBextractor:
+    """B200 ORB extractor for frames of one fixed size; batch capacity ``max_batch``."""
+
+    def __init__(self, nfeatures: int = 1000, scaleFactor: float = 1.2, nlevels: int = 8, iniThFAST: int = 20,
+                 minThFAST: int = 7, *, width: int, height: int, max_batch: int = 1, device: int = -1):
+        self._lib = load_library()
+        self._h = C.c_void_p()
+        self.params = Params(nfeatures, scaleFactor, nlevels, iniThFAST, minThFAST)
+        self.width, self.height, self.max_batch = width, height, max_batch
+        rc = self._lib.orbb_create(C.byref(self._h), C.byref(self.params), width, height, max_batch, device)
+        if rc != 0:
+            self._h = C.c_void_p()
+            raise OrbbError(f"orbb_create: {self._lib.orbb_strerror(rc).decode()} ({rc})")
+        self.nlevels = self._lib.orbb_get_levels(self._h)
+        self.max_kp = self._lib.orbb_max_keypoints_per_frame(self._h)
+        n = self.nlevels
+        self._scale = np.zeros(n, np.float32)
+        self._inv_scale = np.zeros(n, np.float32)
+        self._sigma2 = np.zeros(n, np.float32)
+        self._inv_sigma2 = np.zeros(n, np.float32)
+        self._check(self._lib.orbb_get_scale_factors(self._h, _np_ptr(self._scale), _np_ptr(self._inv_scale),
+                                                     _np_ptr(self._sigma2), _np_ptr(self._inv_sigma2)))
+        self.features_per_level = np.zeros(n, np.int32)
+        self._check(self._lib.orbb_get_features_per_level(self._h, _np_ptr(self.features_per_level)))
+
+    # -- lifetime ---------------------------------------------------------------------------
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            self._lib.orbb_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc: int):
+        if rc < 0:
+            msg = self._lib.orbb_strerror(rc).decode()
+            if rc == -3:
+                msg += ": " + self._lib.orbb_last_cuda_error(self._h).decode()
+            raise OrbbError(msg)
+        return rc
+
+    # -- upstream getters -------------------------------------------------------------------
+    def GetLevels(self):
+        return self.nlevels
+
+    def GetScaleFactor(self):
+        return float(self.params.scale_factor)
+
+    def GetScaleFactors(self):
+        return self._scale.copy()
+
+    def GetInverseScaleFactors(self):
+        return self._inv_scale.copy()
+
+    def GetScaleSigmaSquares(self):
+        return self._sigma2.copy()
+
+    def GetInverseScaleSigmaSquares(self):
+        return self._inv_sigma2.copy()
+
+    def level_info(self, level: int, frame: int = 0) -> Level:
+        out = Level()
+        self._check(self._lib.orbb_get_level(self._h, frame, level, C.byref(out)))
+        return out
+
+    # -- operator() -------------------------------------------------------------------------
+    def __call__(self, image: np.ndarray, mask=None):
+        """ORBextractor::operator()(image, mask[ignored]) -> (keypoints[KEYPOINT_DTYPE], descriptors[n,32])."""
+        kp, desc, counts = self.extract_batch(np.asarray(image)[None])
+        n = int(counts[0])
+        return kp[0, :n].copy(), desc[0, :n].copy()
+
+    def extract_batch(self, frames: np.ndarray, stream=None):
+        """HOST frames [n,h,w] u8 -> (kp [n,max_kp], desc [n,max_kp,32], counts [n]); H2D/D2H inside."""
+        frames = np.ascontiguousarray(frames, np.uint8)
+        if frames.ndim != 3 or frames.shape[1:] != (self.height, self.width):
+            raise OrbbError(f"expected [n,{self.height},{self.width}] u8 frames, got {frames.shape}")
+        n = frames.shape[0]
+        kp = np.zeros((n, self.max_kp), KEYPOINT_DTYPE)
+        desc = np.zeros((n, self.max_kp, 32), np.uint8)
+        counts = np.zeros(n, np.int32)
+        self._check(self._lib.orbb_extract_batch_host(self._h, _np_ptr(frames), frames.strides[1], frames.strides[0], n,
+                                                      _np_ptr(kp), _np_ptr(desc), _np_ptr(counts), self.max_kp,
+                                                      _stream_ptr(stream)))
+        return kp, desc, counts
+
+    def extract_batch_host_into(self, frames_ptr, pitch, stride, n, kp_ptr, desc_ptr, counts_ptr, stream=None):
+        """Raw-pointer form of extract_batch (pinned host buffers owned by the caller, e.g. bench.py)."""
+        self._check(self._lib.orbb_extract_batch_host(self._h, C.c_void_p(frames_ptr), pitch, stride, n,
+                                                      C.c_void_p(kp_ptr), C.c_void_p(desc_ptr),
+                                                      C.c_void_p(counts_ptr), self.max_kp, _stream_ptr(stream)))
+
+    def extract_batch_device(self, d_frames, n: int, d_kp, d_desc, d_counts, pitch=None, stride=None, stream=None):
+        """DEVICE-resident frames (torch CUDA uint8 tensor or address); async on ``stream``."""
+        pitch = self.width if pitch is None else pitch
+        stride = self.width * self.height if stride is None else stride
+        self._check(self._lib.orbb_extract_batch_device(self._h, _dev_ptr(d_frames), pitch, stride, n, _dev_ptr(d_kp),
+                                                        _dev_ptr(d_desc), _dev_ptr(d_counts), self.max_kp,
+                                                        _stream_ptr(stream)))
+
+    # -- stage interface (reference namespace Jetracer) -------------------------------------
+    def stage_upload(self, d_frames, n: int, pitch=None, stride=None, stream=None):
+        pitch = self.width if pitch is None else pitch
+        stride = self.width * self.height if stride is None else stride
+        self._check(self._lib.orbb_stage_upload(self._h, _dev_ptr(d_frames), pitch, stride, n, _stream_ptr(stream)))
+
+    def pyramid_create_levels(self, stream=None):
+        self._check(self._lib.orbb_pyramid_create_levels(self._h, _stream_ptr(stream)))
+
+    def detect(self, stream=None):
+        self._check(self._lib.orbb_detect(self._h, _stream_ptr(stream)))
+
+    def gaussian_blur(self, stream=None):
+        self._check(self._lib.orbb_gaussian_blur(self._h, _stream_ptr(stream)))
+
+    def compute_fast_angle_and_orb(self, d_kp, d_desc, d_counts, stream=None):
+        self._check(self._lib.orbb_compute_angle_and_orb(self._h, _dev_ptr(d_kp), _dev_ptr(d_desc), _dev_ptr(d_counts),
+                                                         self.max_kp, _stream_ptr(stream)))
+
+    def match_keypoints(self, d_query, nq: int, d_train, nt: int, d_idx, d_dist, d_accept=None, d_naccept=None,
+                        k: int = 2, ratio: float = 0.7, stream=None):
+        """Jetracer::match_keypoints slot: brute-force Hamming k-NN + ratio test on device descriptors."""
+        self._check(self._lib.orbb_match_knn(self._h, _dev_ptr(d_query), nq, _dev_ptr(d_train), nt, k, ratio,
+                                             _dev_ptr(d_idx), _dev_ptr(d_dist),
+                                             _dev_ptr(d_accept) if d_accept is not None else C.c_void_p(0),
+                                             _dev_ptr(d_naccept) if d_naccept is not None else C.c_void_p(0),
+                                             _stream_ptr(stream)))
+
+    def match_keypoints_segmented(self, d_query, d_q_off, d_train, d_t_off, nseg: int, max_q_per_seg: int, d_idx,
+                                  d_dist, d_accept=None, k: int = 2, ratio: float = 0.7, stream=None):
+        self._check(self._lib.orbb_match_knn_segmented(self._h, _dev_ptr(d_query), _dev_ptr(d_q_off), _dev_ptr(d_train),
+                                                       _dev_ptr(d_t_off), nseg, max_q_per_seg, k, ratio,
+                                                       _dev_ptr(d_idx), _dev_ptr(d_dist),
+                                                       _dev_ptr(d_accept) if d_accept is not None else C.c_void_p(0),
+                                                       _stream_ptr(stream)))
+
+    # -- parity / debug access --------------------------------------------------------------
+    def debug_padded(self, level: int, frame: int = 0) -> np.ndarray:
+        li = self.level_info(level)
+        out = np.zeros((li.height + 38, li.width + 38), np.uint8)
+        self._check(self._lib.orbb_debug_get_padded(self._h, frame, level, _np_ptr(out)))
+        return out
+
+    def debug_blurred(self, level: int, frame: int = 0) -> np.ndarray:
+        li = self.level_info(level)
+        out = np.zeros((li.height, li.width), np.uint8)
+        self._check(self._lib.orbb_debug_get_blurred(self._h, frame, level, _np_ptr(out)))
+        return out
+
+    def debug_scores(self, level: int, frame: int = 0) -> np.ndarray:
+        li = self.level_info(level)
+        out = np.zeros((li.height, li.width), np.uint8)
+        self._check(self._lib.orbb_debug_get_scores(self._h, frame, level, _np_ptr(out)))
+        return out
+
+    def debug_candidates(self, level: int, frame: int = 0) -> np.ndarray:
+        li = self.level_info(level)
+        cap = li.width * li.height // 4 + 64
+        out = np.zeros((cap, 3), np.int32)
+        n = self._check(self._lib.orbb_debug_get_candidates(self._h, frame, level, _np_ptr(out), cap))
+        return out[:n].copy()
+
+    def debug_selected(self, level: int, frame: int = 0) -> np.ndarray:
+        out = np.zeros((self.max_kp, 3), np.int32)
+        n = self._check(self._lib.orbb_debug_get_selected(self._h, frame, level, _np_ptr(out), self.max_kp))
+        return out[:n].copy()
+
+    def debug_distribute(self, level: int, cand_xyr: np.ndarray, quota: int) -> np.ndarray:
+        cand = np.ascontiguousarray(cand_xyr, np.int32).reshape(-1, 3)
+        out = np.zeros((self.max_kp, 3), np.int32)
+        n = self._check(self._lib.orbb_debug_distribute(self._h, level, _np_ptr(cand), cand.shape[0], quota,
+                                                        _np_ptr(out), self.max_kp))
+        return out[:n].copy()
+
+
+def match_knn_host(ex: ORBextractor, query: np.ndarray, train: np.ndarray, k: int = 2, ratio: float = 0.7):
+    """Convenience for tests: host descriptors -> device matcher -> host (idx[nq,2], dist[nq,2], accept[nq])."""
+    import torch
+    q = torch.from_numpy(np.ascontiguousarray(query, np.uint8).reshape(-1, 32)).cuda()
+    t = torch.from_numpy(np.ascontiguousarray(train, np.uint8).reshape(-1, 32)).cuda()
+    nq, nt = q.shape[0], t.shape[0]
+    idx = torch.full((max(nq, 1), 2), -7, dtype=torch.int32, device="cuda")
+    dist = torch.full((max(nq, 1), 2), -7, dtype=torch.int32, device="cuda")
+    acc = torch.zeros(max(nq, 1), dtype=torch.uint8, device="cuda")
+    nacc = torch.zeros(1, dtype=torch.int32, device="cuda")
+    ex.match_keypoints(q, nq, t, nt, idx, dist, acc, nacc, k=k, ratio=ratio,
+                       stream=torch.cuda.current_stream())
+    torch.cuda.synchronize()
+    return idx[:nq].cpu().numpy(), dist[:nq].cpu().numpy(), acc[:nq].cpu().numpy().astype(bool), int(nacc.item())

@@ -1,0 +1,282 @@
+"""GPU parity tests: the CUDA path (through the C ABI, via ctypes) against the CPU oracle and the committed
+golden vectors.  Bit-exact bar for pyramid pixels, FAST scores, candidate sets, selected keypoints
+(x, y, octave, response, size), angles and descriptor bits.  Run on the B200 box: pytest -m gpu."""
+import importlib
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN_DIR, golden_names
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def orbb():
+    import torch
+    assert torch.cuda.is_available(), "GPU tier needs a CUDA device"
+    import __graft_entry__ as g
+    g.build()
+    return importlib.import_module("jetracer-orbslam2_b200.orbb")
+
+
+def canon(kp, desc=None):
+    order = np.lexsort((kp["x"], kp["y"], kp["octave"]))
+    return (kp[order], desc[order]) if desc is not None else kp[order]
+
+
+def as_set(xyr):
+    return {tuple(int(v) for v in r) for r in np.asarray(xyr).reshape(-1, 3)}
+
+
+CONFIGS = [  # (w, h, nfeatures, scale, nlevels, generator, seed)
+    (640, 480, 1000, 1.2, 8, "textured_frame", 1000),
+    (848, 480, 1200, 1.2, 8, "textured_frame", 2000),
+    (333, 251, 400, 1.2, 6, "textured_frame", 5),
+    (320, 240, 500, 1.2, 8, "low_contrast_frame", 11),
+    (320, 240, 500, 1.2, 8, "sparse_frame", 5),
+    (400, 300, 400, 1.5, 4, "textured_frame", 9),
+    (512, 384, 600, 2.0, 3, "textured_frame", 21),
+]
+
+
+def make_frame(synth, w, h, gen, seed):
+    return getattr(synth, gen)(w, h, seed)
+
+
+@pytest.mark.parametrize("w,h,nf,sc,nl,gen,seed", CONFIGS)
+def test_pyramid_scores_candidates_selection(orbb, oracle, synth, w, h, nf, sc, nl, gen, seed):
+    img = make_frame(synth, w, h, gen, seed)
+    ex = orbb.ORBextractor(nf, sc, nl, 20, 7, width=w, height=h, max_batch=2)
+    o = oracle.Oracle(w, h, nf, sc, nl, 20, 7)
+    kp, desc = ex(img)
+    okp, odesc = o.extract(img)
+    assert np.array_equal(ex.features_per_level, o.nfeat)
+    assert np.array_equal(ex.GetScaleFactors(), o.scale)
+    for l in range(nl):
+        # ComputePyramid: every padded pixel incl. the reflect-101 frame
+        assert np.array_equal(ex.debug_padded(l), o.level_padded(l)), f"padded level {l}"
+        # 7x7 Gaussian of the ROI
+        assert np.array_equal(ex.debug_blurred(l), o.level_blurred(l)), f"blurred level {l}"
+        # FAST arc scores: m where m > 7 inside the tested range, else 0
+        m = oracle.fast_score_map(o.level_roi(l))
+        ref = np.where(m > 7, m, 0).astype(np.uint8)
+        ref[:19, :] = 0; ref[-19:, :] = 0; ref[:, :19] = 0; ref[:, -19:] = 0
+        assert np.array_equal(ex.debug_scores(l), ref), f"score map level {l}"
+        # per-cell FAST(20 -> 7) + NMS candidates (set; GPU order is unspecified)
+        oc = o.level_candidates(l)
+        got = ex.debug_candidates(l)
+        assert len(got) == len(oc)
+        assert as_set(got) == as_set(np.stack([oc["x"], oc["y"], oc["response"]], 1)) if len(oc) else len(got) == 0
+    # selected keypoints, angles, descriptors
+    kp, desc = canon(kp, desc)
+    okp, odesc = canon(okp, odesc)
+    assert len(kp) == len(okp)
+    for f in ("x", "y", "octave", "response", "size", "class_id"):
+        assert np.array_equal(kp[f], okp[f]), f
+    # north_star tolerance: angles within 1e-3 rad, descriptors <= 8 bits -- we require exact here
+    assert np.array_equal(kp["angle"], okp["angle"])
+    assert np.array_equal(desc, odesc)
+    ex.close()
+
+
+@pytest.mark.parametrize("name", golden_names())
+def test_golden_fixtures(orbb, name):
+    g = np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
+    nf, sc, nl, it, mt = g["params"]
+    img = g["image"]
+    ex = orbb.ORBextractor(int(nf), float(sc), int(nl), int(it), int(mt), width=img.shape[1], height=img.shape[0])
+    kp, desc = canon(*ex(img))
+    gkp, gdesc = canon(g["kp"], g["desc"])
+    assert len(kp) == len(gkp)
+    for f in kp.dtype.names:
+        assert np.array_equal(kp[f], gkp[f]), f
+    assert np.array_equal(desc, gdesc)
+    assert np.array_equal(ex.debug_padded(int(nl) - 1), g["pyr_last_padded"])
+    ex.close()
+
+
+def test_thresholds_other_than_default(orbb, oracle, synth):
+    img = synth.textured_frame(320, 240, 31)
+    for it, mt in ((35, 12), (12, 12), (10, 25), (60, 3)):
+        ex = orbb.ORBextractor(300, 1.2, 5, it, mt, width=320, height=240)
+        o = oracle.Oracle(320, 240, 300, 1.2, 5, it, mt)
+        kp, desc = canon(*ex(img))
+        okp, odesc = canon(*o.extract(img))
+        assert len(kp) == len(okp), (it, mt)
+        for f in ("x", "y", "octave", "response", "angle"):
+            assert np.array_equal(kp[f], okp[f]), (it, mt, f)
+        assert np.array_equal(desc, odesc)
+        ex.close()
+
+
+def _octree_case(orbb_ex, oracle, level, cand, quota):
+    li = orbb_ex.level_info(level)
+    minx, maxx, miny, maxy = 16, li.width - 16, 16, li.height - 16
+    c = np.zeros(len(cand), oracle.CAND_DTYPE)
+    c["x"], c["y"], c["response"] = cand[:, 0], cand[:, 1], cand[:, 2]
+    sel = oracle.distribute_octree(c, minx, maxx, miny, maxy, quota)
+    ref = as_set(cand[sel])
+    got = orbb_ex.debug_distribute(level, cand, quota)
+    assert len(got) == len(sel), (len(got), len(sel), quota, len(cand))
+    assert as_set(got) == ref, (quota, len(cand))
+
+
+def test_octree_stress(orbb, oracle):
+    """DistributeOctTree alone on synthetic candidate clouds: uniform, clustered, collinear, tiny; many quotas
+    so every exit (>=N after a full pass, careful phase with 1..k rounds, no growth, n < N) is hit."""
+    rng = np.random.default_rng(7)
+    for (w, h) in ((640, 480), (848, 480), (1280, 720)):
+        ex = orbb.ORBextractor(4000, 1.2, 2, 20, 7, width=w, height=h)
+        W, H = w - 32, h - 32
+        clouds = []
+        for n in (1, 2, 3, 17, 150, 1200, 6000):
+            pts = set()
+            while len(pts) < n:
+                pts.add((int(rng.integers(3, W - 3)), int(rng.integers(3, H - 3))))
+            clouds.append(np.array(sorted(pts)))
+        # clustered: gaussian blobs
+        for n in (300, 3000):
+            cx, cy = rng.integers(40, W - 40, 5), rng.integers(40, H - 40, 5)
+            pts = set()
+            while len(pts) < n:
+                k = int(rng.integers(0, 5))
+                x, y = int(rng.normal(cx[k], 12)), int(rng.normal(cy[k], 9))
+                if 3 <= x < W - 3 and 3 <= y < H - 3:
+                    pts.add((x, y))
+            clouds.append(np.array(sorted(pts)))
+        # a horizontal line, a vertical line, and the root seam columns
+        clouds.append(np.array([(x, H // 2) for x in range(3, W - 3, 2)]))
+        clouds.append(np.array([(W // 2, y) for y in range(3, H - 3)]))
+        clouds.append(np.array([(x, y) for x in range(W // 2 - 3, W // 2 + 4) for y in range(3, H - 3, 5)]))
+        for pts in clouds:
+            resp = rng.integers(7, 120, size=len(pts))  # many response ties
+            cand = np.concatenate([pts, resp[:, None]], 1).astype(np.int32)
+            cand = cand[rng.permutation(len(cand))]
+            for quota in (1, 5, 60, 217, 434, 1000, 2000):
+                _octree_case(ex, oracle, 0, cand, quota)
+        ex.close()
+
+
+def test_batch_equals_single_and_is_deterministic(orbb, synth):
+    frames = np.stack([synth.textured_frame(424, 240, 100 + i) for i in range(5)] +
+                      [synth.flat_frame(424, 240), synth.checkerboard_frame(424, 240)])
+    ex = orbb.ORBextractor(600, 1.2, 6, 20, 7, width=424, height=240, max_batch=8)
+    kp, desc, counts = ex.extract_batch(frames)
+    kp2, desc2, counts2 = ex.extract_batch(frames)
+    assert np.array_equal(counts, counts2)
+    assert counts[5] == 0  # flat frame: no corners
+    one = orbb.ORBextractor(600, 1.2, 6, 20, 7, width=424, height=240, max_batch=1)
+    for f in range(len(frames)):
+        n = counts[f]
+        assert kp[f, :n].tobytes() == kp2[f, :n].tobytes() and desc[f, :n].tobytes() == desc2[f, :n].tobytes()
+        k1, d1 = one(frames[f])
+        assert len(k1) == n and k1.tobytes() == kp[f, :n].tobytes() and d1.tobytes() == desc[f, :n].tobytes()
+    ex.close(); one.close()
+
+
+def test_stage_interface_matches_operator(orbb, synth):
+    """pyramid_create_levels -> detect -> gaussian_blur -> compute_fast_angle_and_orb == operator()."""
+    import torch
+    img = synth.textured_frame(640, 480, 77)
+    ex = orbb.ORBextractor(1000, 1.2, 8, 20, 7, width=640, height=480, max_batch=1)
+    ref_kp, ref_desc = ex(img)
+    d_img = torch.from_numpy(img).cuda()
+    d_kp = torch.zeros(ex.max_kp * 28, dtype=torch.uint8, device="cuda")
+    d_desc = torch.zeros(ex.max_kp * 32, dtype=torch.uint8, device="cuda")
+    d_cnt = torch.zeros(1, dtype=torch.int32, device="cuda")
+    st = torch.cuda.current_stream()
+    ex.stage_upload(d_img, 1, stream=st)
+    ex.pyramid_create_levels(stream=st)
+    ex.detect(stream=st)
+    ex.gaussian_blur(stream=st)
+    ex.compute_fast_angle_and_orb(d_kp, d_desc, d_cnt, stream=st)
+    torch.cuda.synchronize()
+    n = int(d_cnt.item())
+    kp = np.frombuffer(d_kp.cpu().numpy().tobytes(), orbb.KEYPOINT_DTYPE)[:n]
+    desc = d_desc.cpu().numpy().reshape(-1, 32)[:n]
+    assert n == len(ref_kp) and kp.tobytes() == ref_kp.tobytes() and np.array_equal(desc, ref_desc)
+    ex.close()
+
+
+def test_matcher_vs_oracle(orbb, oracle):
+    rng = np.random.default_rng(3)
+    ex = orbb.ORBextractor(500, 1.2, 4, 20, 7, width=320, height=240)
+    for nq, nt in ((1, 1), (1, 2), (7, 300), (1000, 1000), (257, 5000), (3000, 129), (33, 50000)):
+        t = rng.integers(0, 256, size=(nt, 32), dtype=np.uint8)
+        q = t[rng.integers(0, nt, size=nq)].copy()
+        q ^= (rng.integers(0, 256, size=q.shape, dtype=np.uint8) & rng.integers(0, 256, size=q.shape, dtype=np.uint8)
+              & rng.integers(0, 256, size=q.shape, dtype=np.uint8))
+        if nt > 10:
+            t[5] = t[3]  # exact duplicates: tie -> lowest train index
+        for k in (1, 2):
+            idx, dist, acc, nacc = orbb.match_knn_host(ex, q, t, k=k, ratio=0.7)
+            oidx, odist, oacc = oracle.match_knn(q, t, k=k, ratio=0.7)
+            if k == 1:
+                oidx[:, 1] = -1; odist[:, 1] = -1
+            assert np.array_equal(idx, oidx), (nq, nt, k)
+            assert np.array_equal(dist, odist), (nq, nt, k)
+            assert np.array_equal(acc, oacc) and nacc == int(oacc.sum())
+    ex.close()
+
+
+def test_matcher_segmented(orbb, oracle):
+    import torch
+    rng = np.random.default_rng(4)
+    ex = orbb.ORBextractor(500, 1.2, 4, 20, 7, width=320, height=240)
+    nqs, nts = [100, 0, 257, 31], [90, 50, 400, 1]
+    q = rng.integers(0, 256, size=(sum(nqs), 32), dtype=np.uint8)
+    t = rng.integers(0, 256, size=(sum(nts), 32), dtype=np.uint8)
+    qo = np.concatenate([[0], np.cumsum(nqs)]).astype(np.int32)
+    to = np.concatenate([[0], np.cumsum(nts)]).astype(np.int32)
+    dq, dt = torch.from_numpy(q).cuda(), torch.from_numpy(t).cuda()
+    dqo, dto = torch.from_numpy(qo).cuda(), torch.from_numpy(to).cuda()
+    idx = torch.zeros((len(q), 2), dtype=torch.int32, device="cuda")
+    dist = torch.zeros((len(q), 2), dtype=torch.int32, device="cuda")
+    acc = torch.zeros(len(q), dtype=torch.uint8, device="cuda")
+    ex.match_keypoints_segmented(dq, dqo, dt, dto, 4, max(nqs), idx, dist, acc, k=2, ratio=0.8,
+                                 stream=torch.cuda.current_stream())
+    torch.cuda.synchronize()
+    idx, dist, acc = idx.cpu().numpy(), dist.cpu().numpy(), acc.cpu().numpy().astype(bool)
+    for s in range(4):
+        if nqs[s] == 0:
+            continue
+        oi, od, oa = oracle.match_knn(q[qo[s]:qo[s + 1]], t[to[s]:to[s + 1]], k=2, ratio=0.8)
+        assert np.array_equal(idx[qo[s]:qo[s + 1]], oi) and np.array_equal(dist[qo[s]:qo[s + 1]], od)
+        assert np.array_equal(acc[qo[s]:qo[s + 1]], oa)
+    ex.close()
+
+
+def test_errors_are_codes_not_aborts(orbb):
+    with pytest.raises(orbb.OrbbError):
+        orbb.ORBextractor(1000, 1.2, 8, 20, 7, width=120, height=100)  # level 7 under 62 px
+    with pytest.raises(orbb.OrbbError):
+        orbb.ORBextractor(1000, 1.0, 8, 20, 7, width=640, height=480)  # scale factor must be > 1
+    ex = orbb.ORBextractor(100, 1.2, 2, 20, 7, width=200, height=150, max_batch=1)
+    with pytest.raises(orbb.OrbbError):
+        ex.extract_batch(np.zeros((2, 150, 200), np.uint8))  # over batch capacity
+    with pytest.raises(orbb.OrbbError):
+        ex(np.zeros((100, 100), np.uint8))  # wrong shape
+    ex.close()
+
+
+def test_full_size_properties(orbb, synth):
+    """BASELINE config sizes where the oracle is too slow to run per frame: size-independent properties --
+    batch determinism, per-level quotas respected, keypoints inside the image, descriptor self-match."""
+    base = np.stack([synth.textured_frame(848, 480, 2000 + i) for i in range(4)])
+    frames = np.concatenate([base] * 16)  # 64 frames
+    ex = orbb.ORBextractor(1200, 1.2, 8, 20, 7, width=848, height=480, max_batch=64)
+    kp, desc, counts = ex.extract_batch(frames)
+    assert (counts >= 1200).all() and (counts <= 1200 + 2 * 8 + 8).all()
+    for f in range(4, 64):  # repeated inputs -> identical outputs regardless of batch slot
+        n = counts[f]
+        assert n == counts[f % 4] and kp[f, :n].tobytes() == kp[f % 4, :n].tobytes()
+        assert desc[f, :n].tobytes() == desc[f % 4, :n].tobytes()
+    k0 = kp[0, :counts[0]]
+    assert (k0["x"] >= 19).all() and (k0["x"] < 848).all() and (k0["y"] >= 19).all() and (k0["y"] < 480).all()
+    per_level = np.bincount(k0["octave"], minlength=8)
+    assert (per_level <= ex.features_per_level + 2).all()
+    idx, dist, acc, _ = orbb.match_knn_host(ex, desc[0, :counts[0]], desc[4, :counts[4]], k=1)
+    assert (dist[:, 0] == 0).all()
+    ex.close()
