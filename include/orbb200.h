@@ -119,6 +119,10 @@ int orbb_pyramid_create_levels(orbb_handle *h, void *cuda_stream);
 /* Jetracer::detect + grid_nms (src/cuda/fast.cuh:42-48, nms.cuh:11-15): FAST-9 score, per-cell
  * 3x3 NMS with the ini/min threshold fallback, then DistributeOctTree selection per level */
 int orbb_detect(orbb_handle *h, void *cuda_stream);
+/* the two halves of orbb_detect, exposed so a host stage (or bench.py) can time/overlap them:
+ * FAST score + cell NMS + threshold fallback -> candidate lists; then quadtree selection */
+int orbb_detect_fast(orbb_handle *h, void *cuda_stream);
+int orbb_detect_distribute(orbb_handle *h, void *cuda_stream);
 /* Jetracer::gaussian_blur_3x3 slot (src/cuda/orb.cuh:29-35), now 7x7 sigma=2 integer Gaussian */
 int orbb_gaussian_blur(orbb_handle *h, void *cuda_stream);
 /* Jetracer::compute_fast_angle + calc_orb (src/cuda/orb.cuh:9-27): IC_Angle (degrees) and the

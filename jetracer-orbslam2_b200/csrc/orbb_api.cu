@@ -413,14 +413,23 @@ extern "C" int orbb_pyramid_create_levels(orbb_handle *h, void *stream) {
     return ORBB_OK;
 }
 
-extern "C" int orbb_detect(orbb_handle *h, void *stream) {
+extern "C" int orbb_detect_fast(orbb_handle *h, void *stream) {
     if (!h || h->n_frames_last < 1) return ORBB_ERR_INVALID;
-    cudaStream_t st = static_cast<cudaStream_t>(stream);
     CK(h, launch_fast(h->d_levels, h->d_cells, h->n_cells, h->nlevels, h->d_cand_count, h->t_lo, h->t_hi, h->fcfg,
-                      h->n_frames_last, st));
-    CK(h, launch_octree(h->d_levels, h->nlevels, h->d_cand_count, h->d_sel_count, 0, h->nlevels, 0, h->n_frames_last,
-                        -1, h->sel_cap_max, h->pcap, h->pcap2, st));
+                      h->n_frames_last, static_cast<cudaStream_t>(stream)));
     return ORBB_OK;
+}
+
+extern "C" int orbb_detect_distribute(orbb_handle *h, void *stream) {
+    if (!h || h->n_frames_last < 1) return ORBB_ERR_INVALID;
+    CK(h, launch_octree(h->d_levels, h->nlevels, h->d_cand_count, h->d_sel_count, 0, h->nlevels, 0, h->n_frames_last,
+                        -1, h->sel_cap_max, h->pcap, h->pcap2, static_cast<cudaStream_t>(stream)));
+    return ORBB_OK;
+}
+
+extern "C" int orbb_detect(orbb_handle *h, void *stream) {
+    const int rc = orbb_detect_fast(h, stream);
+    return rc ? rc : orbb_detect_distribute(h, stream);
 }
 
 extern "C" int orbb_gaussian_blur(orbb_handle *h, void *stream) {

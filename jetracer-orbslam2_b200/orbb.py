@@ -30,7 +30,7 @@ EXPORTS = [
     "orbb_create", "orbb_destroy", "orbb_strerror", "orbb_last_cuda_error", "orbb_get_levels",
     "orbb_get_scale_factors", "orbb_get_features_per_level", "orbb_max_keypoints_per_frame", "orbb_get_level",
     "orbb_extract_batch_device", "orbb_extract_batch_host", "orbb_stage_upload", "orbb_pyramid_create_levels",
-    "orbb_detect", "orbb_gaussian_blur", "orbb_compute_angle_and_orb", "orbb_match_knn",
+    "orbb_detect", "orbb_detect_fast", "orbb_detect_distribute", "orbb_gaussian_blur", "orbb_compute_angle_and_orb", "orbb_match_knn",
     "orbb_match_knn_segmented", "orbb_debug_get_padded", "orbb_debug_get_blurred", "orbb_debug_get_scores",
     "orbb_debug_get_candidates", "orbb_debug_get_selected", "orbb_debug_distribute",
 ]
@@ -80,6 +80,8 @@ def load_library():
     L.orbb_stage_upload.argtypes = [vp, vp, sz, sz, i32, vp]
     L.orbb_pyramid_create_levels.argtypes = [vp, vp]
     L.orbb_detect.argtypes = [vp, vp]
+    L.orbb_detect_fast.argtypes = [vp, vp]
+    L.orbb_detect_distribute.argtypes = [vp, vp]
     L.orbb_gaussian_blur.argtypes = [vp, vp]
     L.orbb_compute_angle_and_orb.argtypes = [vp, vp, vp, vp, i32, vp]
     L.orbb_match_knn.argtypes = [vp, vp, i32, vp, i32, i32, f32, vp, vp, vp, vp, vp]
@@ -234,6 +236,12 @@ class ORBextractor:
 
     def detect(self, stream=None):
         self._check(self._lib.orbb_detect(self._h, _stream_ptr(stream)))
+
+    def detect_fast(self, stream=None):
+        self._check(self._lib.orbb_detect_fast(self._h, _stream_ptr(stream)))
+
+    def detect_distribute(self, stream=None):
+        self._check(self._lib.orbb_detect_distribute(self._h, _stream_ptr(stream)))
 
     def gaussian_blur(self, stream=None):
         self._check(self._lib.orbb_gaussian_blur(self._h, _stream_ptr(stream)))
