@@ -11,9 +11,9 @@
 //            VIMNMX3), corners (m > t_lo) written to a score tile and re-compacted,
 //   phase 3  3x3 strict NMS inside the cell (the score tile has a zero frame: neighbours outside the
 //            cell's tested range count as 0, exactly like cv::FAST on the cell window),
-//   phase 4  per-cell decision: if any survivor has m > t_hi emit those, else emit all survivors
-//            (K_hi = K_lo intersect {m > t_hi}, so one NMS pass serves both thresholds),
-//            appended to the (frame, level) candidate list with one atomicAdd per 32 survivors.
+//   phase 4  survivors are appended to the (frame, level) candidate list, one atomicAdd per 32.
+// Phases 1-3 run at the high threshold first and are repeated at the low threshold only when the
+// cell came out empty -- upstream's FAST(iniTh) -> FAST(minTh) fallback, decided after NMS.
 // No score map ever goes to HBM (the DUMP instantiation exists only for the parity tests).
 // Bound: SM issue slots / shared-memory bandwidth, not HBM.
 #include "orbb_internal.cuh"
@@ -91,78 +91,84 @@ k_fast_cells(const LevelDev *__restrict__ levels, const CellEntry *__restrict__ 
     const unsigned inv_cw = (1u << 20) / (unsigned)cw + 1u;  // exact floor(idx/cw) for idx*cw < 2^20
     const unsigned lt_mask = (1u << lane) - 1u;
 
-    // ---- phase 1: antipodal-pair precheck (any 9-arc holds one pixel of every antipodal pair)
-    int qn = 0;
-    for (int base = 0; base < npix; base += 32) {
-        const int idx = base + lane;
-        bool pass = false;
-        if (idx < npix) {
-            const int y = (int)(((unsigned)idx * inv_cw) >> 20), x = idx - y * cw;
-            const uint8_t *p = tile + (y + 3) * tp + x + 3 + off;
-            const int v = p[0], lo = v - t_lo, hi = v + t_lo;
-            const int r0 = p[3 * tp], r8 = p[-3 * tp], r4 = p[3], r12 = p[-3];
-            const bool dark = ((r0 < lo) | (r8 < lo)) & ((r4 < lo) | (r12 < lo));
-            const bool bright = ((r0 > hi) | (r8 > hi)) & ((r4 > hi) | (r12 > hi));
-            pass = dark | bright;
-        }
-        const unsigned m = __ballot_sync(0xffffffffu, pass);
-        if (pass) queue[qn + __popc(m & lt_mask)] = (uint16_t)idx;
-        qn += __popc(m);
-    }
-    __syncwarp();
-
-    // ---- phase 2: exact arc score; corners (m > t_lo) go to the score tile and stay queued
-    int cn = 0;
-    for (int base = 0; base < qn; base += 32) {
-        const int i = base + lane;
-        int idx = 0, m = 0;
-        if (i < qn) {
-            idx = queue[i];
-            const int y = (int)(((unsigned)idx * inv_cw) >> 20), x = idx - y * cw;
-            m = arc_score(tile + (y + 3) * tp + x + 3 + off, tp);
-            m = m > t_lo ? m : 0;
-            if (m) score[(y + 1) * sp + x + 1] = (uint8_t)min(m, 255);
-        }
-        __syncwarp();
-        const unsigned bm = __ballot_sync(0xffffffffu, m != 0);
-        if (m) queue[cn + __popc(bm & lt_mask)] = (uint16_t)idx;
-        cn += __popc(bm);
-        __syncwarp();
-    }
-
-    if (DUMP) {
-        uint8_t *out = dump + dump_off[c.level];
-        for (int idx = lane; idx < npix; idx += 32) {
-            const int y = idx / cw, x = idx - y * cw;
-            out[(size_t)(c.y0 + y) * L.w + c.x0 + x] = score[(y + 1) * sp + x + 1];
-        }
-        return;  // parity dump only: no candidates are emitted
-    }
-
-    // ---- phase 3: strict 3x3 NMS inside the cell
+    // Upstream order: FAST(ini) on the cell; only if that leaves nothing, FAST(min).  Running the high
+    // threshold first rejects most pixels in the precheck (the low-threshold pass is rare on textured input).
     int kn = 0;
-    bool any_hi = false;
-    for (int base = 0; base < cn; base += 32) {
-        const int i = base + lane;
-        int idx = 0;
-        bool keep = false, strong = false;
-        if (i < cn) {
-            idx = queue[i];
-            const int y = (int)(((unsigned)idx * inv_cw) >> 20), x = idx - y * cw;
-            const uint8_t *s = score + (y + 1) * sp + x + 1;
-            const int v = s[0];
-            const int n0 = max3(s[-sp - 1], s[-sp], s[-sp + 1]);
-            const int n1 = max3(s[-1], s[1], s[sp - 1]);
-            const int n2 = max3(s[sp], s[sp + 1], n0);
-            keep = v > max(n1, n2);
-            strong = keep && v > t_hi;
+    for (int pass = DUMP ? 1 : 0; pass < 2; ++pass) {
+        const int thr = pass == 0 ? t_hi : t_lo;
+        if (pass == 1 && !DUMP && t_lo == t_hi) break;
+        // ---- phase 1: antipodal-pair precheck (any 9-arc holds one pixel of every antipodal pair)
+        int qn = 0;
+        for (int base = 0; base < npix; base += 32) {
+            const int idx = base + lane;
+            bool ok = false;
+            if (idx < npix) {
+                const int y = (int)(((unsigned)idx * inv_cw) >> 20), x = idx - y * cw;
+                const uint8_t *p = tile + (y + 3) * tp + x + 3 + off;
+                const int v = p[0], lo = v - thr, hi = v + thr;
+                const int r0 = p[3 * tp], r8 = p[-3 * tp], r4 = p[3], r12 = p[-3];
+                const bool dark = ((r0 < lo) | (r8 < lo)) & ((r4 < lo) | (r12 < lo));
+                const bool bright = ((r0 > hi) | (r8 > hi)) & ((r4 > hi) | (r12 > hi));
+                ok = dark | bright;
+            }
+            const unsigned m = __ballot_sync(0xffffffffu, ok);
+            if (ok) queue[qn + __popc(m & lt_mask)] = (uint16_t)idx;
+            qn += __popc(m);
         }
         __syncwarp();
-        const unsigned bm = __ballot_sync(0xffffffffu, keep);
-        any_hi |= __any_sync(0xffffffffu, strong);
-        if (keep) queue[kn + __popc(bm & lt_mask)] = (uint16_t)idx;
-        kn += __popc(bm);
-        __syncwarp();
+
+        // ---- phase 2: exact arc score; corners (m > thr) go to the score tile and stay queued
+        int cn = 0;
+        for (int base = 0; base < qn; base += 32) {
+            const int i = base + lane;
+            int idx = 0, m = 0;
+            if (i < qn) {
+                idx = queue[i];
+                const int y = (int)(((unsigned)idx * inv_cw) >> 20), x = idx - y * cw;
+                m = arc_score(tile + (y + 3) * tp + x + 3 + off, tp);
+                m = m > thr ? m : 0;
+                if (m) score[(y + 1) * sp + x + 1] = (uint8_t)min(m, 255);
+            }
+            __syncwarp();
+            const unsigned bm = __ballot_sync(0xffffffffu, m != 0);
+            if (m) queue[cn + __popc(bm & lt_mask)] = (uint16_t)idx;
+            cn += __popc(bm);
+            __syncwarp();
+        }
+
+        if (DUMP) {
+            uint8_t *out = dump + dump_off[c.level];
+            for (int idx = lane; idx < npix; idx += 32) {
+                const int y = idx / cw, x = idx - y * cw;
+                out[(size_t)(c.y0 + y) * L.w + c.x0 + x] = score[(y + 1) * sp + x + 1];
+            }
+            return;  // parity dump only: no candidates are emitted
+        }
+
+        // ---- phase 3: strict 3x3 NMS inside the cell (scores written by an earlier pass stay valid:
+        // the arc score does not depend on the threshold)
+        kn = 0;
+        for (int base = 0; base < cn; base += 32) {
+            const int i = base + lane;
+            int idx = 0;
+            bool keep = false;
+            if (i < cn) {
+                idx = queue[i];
+                const int y = (int)(((unsigned)idx * inv_cw) >> 20), x = idx - y * cw;
+                const uint8_t *s = score + (y + 1) * sp + x + 1;
+                const int v = s[0];
+                const int n0 = max3(s[-sp - 1], s[-sp], s[-sp + 1]);
+                const int n1 = max3(s[-1], s[1], s[sp - 1]);
+                const int n2 = max3(s[sp], s[sp + 1], n0);
+                keep = v > max(n1, n2);
+            }
+            __syncwarp();
+            const unsigned bm = __ballot_sync(0xffffffffu, keep);
+            if (keep) queue[kn + __popc(bm & lt_mask)] = (uint16_t)idx;
+            kn += __popc(bm);
+            __syncwarp();
+        }
+        if (kn > 0) break;  // cv::FAST(ini) found keypoints: no fallback for this cell
     }
 
     // ---- phase 4: per-cell threshold decision + append to the (frame, level) candidate list
@@ -176,7 +182,7 @@ k_fast_cells(const LevelDev *__restrict__ levels, const CellEntry *__restrict__ 
             const int idx = queue[i];
             const int y = (int)(((unsigned)idx * inv_cw) >> 20), x = idx - y * cw;
             const int m = score[(y + 1) * sp + x + 1];
-            emit = !any_hi || m > t_hi;
+            emit = true;
             // coordinates relative to (minBorderX, minBorderY) = (16,16), as upstream's vToDistributeKeys
             packed = (uint32_t)(c.x0 + x - ORBB_MIN_BORDER) | ((uint32_t)(c.y0 + y - ORBB_MIN_BORDER) << 12) |
                      ((uint32_t)m << 24);

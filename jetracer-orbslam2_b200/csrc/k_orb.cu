@@ -34,14 +34,23 @@ __device__ __forceinline__ float fast_atan2_deg(float y, float x) {
 }
 
 #define ORB_WARPS 8
+#define PATCH_R 19                      // rotated pattern reach: |(13,13)| = 18.4 -> 19
+#define PATCH_ROWS (2 * PATCH_R + 1)    // 39
+#define PATCH_PITCH 44                  // 11 aligned words cover 39 columns at any byte phase
+
+// umax[|v|] of upstream's circular patch, as a compile-time function of the unrolled row
+__device__ __forceinline__ constexpr int umax_of(int av) {
+    return (int)((0x3689ABCDDEEEFFFFull >> (4 * av)) & 15ull);
+}
 
 __global__ void __launch_bounds__(ORB_WARPS * 32)
 k_angle_orb(const LevelDev *__restrict__ levels, int n_levels, const int *__restrict__ sel_count,
             const int8_t *__restrict__ pattern, const int *__restrict__ slot_level, const int *__restrict__ slot_base,
             int n_slots, orbb_keypoint *__restrict__ out_kp, uint8_t *__restrict__ out_desc,
             int *__restrict__ out_counts, int max_kp) {
-    const int lane = threadIdx.x & 31;
-    const int gslot = blockIdx.x * ORB_WARPS + (threadIdx.x >> 5);
+    __shared__ __align__(16) uint8_t s_patch[ORB_WARPS][PATCH_ROWS * PATCH_PITCH];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int gslot = blockIdx.x * ORB_WARPS + warp;
     const int frame = blockIdx.y;
     if (gslot >= n_slots) return;
     const int level = slot_level[gslot], slot = gslot - slot_base[level];
@@ -61,22 +70,33 @@ k_angle_orb(const LevelDev *__restrict__ levels, int n_levels, const int *__rest
     const int x = (int)(c & 0xfffu) + ORBB_MIN_BORDER, y = (int)((c >> 12) & 0xfffu) + ORBB_MIN_BORDER;
     const int resp = (int)(c >> 24) - 1;  // cv::FAST response = arc score - 1
 
-    // ---- IC_Angle: lane r handles disc row v = r - 15
-    const uint8_t *center = L.img + (size_t)frame * L.frame_stride + (size_t)(y + ORBB_BORDER) * L.pitch + ORBB_ROI_X0 + x;
-    int m10 = 0, m01 = 0;
-    if (lane < 31) {
-        const int v = lane - 15, av = v < 0 ? -v : v;
-        const int d = (int)((0x3689ABCDDEEEFFFFull >> (4 * av)) & 15ull);  // umax[|v|]
-        const uint8_t *row = center + (ptrdiff_t)v * L.pitch;
-        int s = 0, sx = 0;
-        for (int u = -d; u <= d; ++u) {
-            const int val = row[u];
-            s += val;
-            sx += u * val;
+    // ---- stage the 39x39 blurred patch with aligned 32-bit loads
+    uint8_t *patch = s_patch[warp];
+    const int xa = (x - PATCH_R) & ~3, poff = (x - PATCH_R) - xa;
+    {
+        const uint8_t *src = L.blur + (size_t)frame * L.blur_stride + (size_t)(y - PATCH_R) * L.pitch + xa;
+        const int lr = lane >> 4, lw = lane & 15;  // 2 rows per warp instruction, 11 of 16 lanes active
+        if (lw < 11) {
+#pragma unroll
+            for (int r = 0; r < PATCH_ROWS + 1; r += 2)
+                if (r + lr < PATCH_ROWS)
+                    reinterpret_cast<uint32_t *>(patch + (r + lr) * PATCH_PITCH)[lw] =
+                        *reinterpret_cast<const uint32_t *>(src + (size_t)(r + lr) * L.pitch + 4 * lw);
         }
-        m10 = sx;
-        m01 = v * s;
     }
+
+    // ---- IC_Angle: lane = column u (coalesced row reads), rows unrolled with their compile-time umax
+    const uint8_t *center = L.img + (size_t)frame * L.frame_stride + (size_t)(y + ORBB_BORDER) * L.pitch + ORBB_ROI_X0 + x;
+    const int u = lane - 15, au = u < 0 ? -u : u;
+    int colsum = 0, m01 = 0;
+#pragma unroll
+    for (int v = -15; v <= 15; ++v) {
+        const int d = umax_of(v < 0 ? -v : v);
+        const int val = (au <= d) ? (int)center[(ptrdiff_t)v * L.pitch + u] : 0;  // lane 31 has au = 16 > d
+        colsum += val;
+        m01 += v * val;
+    }
+    int m10 = u * colsum;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
         m10 += __shfl_xor_sync(0xffffffffu, m10, o);
@@ -84,14 +104,17 @@ k_angle_orb(const LevelDev *__restrict__ levels, int n_levels, const int *__rest
     }
     const float angle = fast_atan2_deg((float)m01, (float)m10);
 
-    // ---- steered BRIEF on the blurred level
+    // ---- steered BRIEF on the staged patch
     const float factor_pi = (float)(3.14159265358979323846 / 180.0);  // == (float)(CV_PI/180.f)
     const float rad = __fmul_rn(angle, factor_pi);
-    const float a = (float)cos((double)rad), b = (float)sin((double)rad);
-    const uint8_t *bc = L.blur + (size_t)frame * L.blur_stride + (size_t)y * L.pitch + x;
+    double sd, cd;
+    sincos((double)rad, &sd, &cd);
+    const float a = (float)cd, b = (float)sd;
     const int8_t *pat = pattern + lane * 32;
     const int4 q0 = *reinterpret_cast<const int4 *>(pat), q1 = *reinterpret_cast<const int4 *>(pat + 16);
     const int w[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
+    __syncwarp();
+    const uint8_t *pc = patch + PATCH_R * PATCH_PITCH + PATCH_R + poff;
     int val = 0;
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
@@ -101,21 +124,23 @@ k_angle_orb(const LevelDev *__restrict__ levels, int n_levels, const int *__rest
         const int rx0 = __float2int_rn(__fsub_rn(__fmul_rn(x0, a), __fmul_rn(y0, b)));
         const int ry1 = __float2int_rn(__fadd_rn(__fmul_rn(x1, b), __fmul_rn(y1, a)));
         const int rx1 = __float2int_rn(__fsub_rn(__fmul_rn(x1, a), __fmul_rn(y1, b)));
-        const int t0 = bc[(ptrdiff_t)ry0 * L.pitch + rx0], t1 = bc[(ptrdiff_t)ry1 * L.pitch + rx1];
+        const int t0 = pc[ry0 * PATCH_PITCH + rx0], t1 = pc[ry1 * PATCH_PITCH + rx1];
         val |= (t0 < t1) << k;
     }
     const size_t o = (size_t)frame * max_kp + off + slot;
     out_desc[o * 32 + lane] = (uint8_t)val;
-    if (lane == 0) {
-        orbb_keypoint kp;
-        kp.x = level ? __fmul_rn((float)x, L.scale) : (float)x;
-        kp.y = level ? __fmul_rn((float)y, L.scale) : (float)y;
-        kp.size = L.patch_size;
-        kp.angle = angle;
-        kp.response = (float)resp;
-        kp.octave = level;
-        kp.class_id = -1;
-        out_kp[o] = kp;
+    if (lane < 7) {  // 28-byte cv::KeyPoint written as 7 coalesced words
+        float f;
+        switch (lane) {
+            case 0: f = level ? __fmul_rn((float)x, L.scale) : (float)x; break;
+            case 1: f = level ? __fmul_rn((float)y, L.scale) : (float)y; break;
+            case 2: f = L.patch_size; break;
+            case 3: f = angle; break;
+            case 4: f = (float)resp; break;
+            case 5: f = __int_as_float(level); break;
+            default: f = __int_as_float(-1); break;
+        }
+        reinterpret_cast<float *>(out_kp + o)[lane] = f;
     }
 }
 

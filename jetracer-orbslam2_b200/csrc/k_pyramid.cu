@@ -7,9 +7,8 @@
 // 19-px BORDER_REFLECT_101 border.  The weight/offset tables are built once on the host exactly
 // like OpenCV builds them (float32/double mix), so device arithmetic is integer only.
 //
-// Roofline: HBM-bound.  One thread produces 4 adjacent bytes of a padded row (one 32-bit
-// coalesced store); the border is produced by the same kernel by reflecting the output coordinate
-// and recomputing the pixel (no second pass over the ROI).
+// Roofline: HBM-bound by design (every level is written once and read once); see DESIGN.md for the
+// measured distance to it.
 #include "orbb_internal.cuh"
 
 namespace orbb {
@@ -44,96 +43,161 @@ __global__ void __launch_bounds__(128) k_level0(const uint8_t *__restrict__ in, 
     *reinterpret_cast<uint32_t *>(L.img + (size_t)frame * L.frame_stride + (size_t)py * L.pitch + b0) = out;
 }
 
-// ---- level l from level l-1
-__global__ void __launch_bounds__(128) k_resize(const LevelDev *__restrict__ levels, int l) {
+// ---- level l from level l-1: tiled two-phase bilinear resize (cv::resize INTER_LINEAR, 8U).
+// A CTA produces a 64-byte x 32-row tile of the PADDED output row layout (aligned 32-bit stores; the
+// reflect-101 frame is produced in the same pass by reflecting the output coordinate).  The source
+// window is staged in shared memory with coalesced 32-bit loads, then
+//   H phase: T[src_row][dst_col] = (S[sx]*a0 + S[sx+1]*a1) >> 4   (u16, thread = dst column, the
+//            column's (sx,a0,a1) lives in registers for all source rows)
+//   V phase: dst = (((b0*T0)>>16) + ((b1*T1)>>16) + 2) >> 2        (thread = 4 columns x 4 rows)
+// Exact 2x shrinks take OpenCV's INTER_AREA route: (a+b+c+d+2)>>2, same two phases with unit weights.
+#define RS_TW 64
+#define RS_TH 32
+#define RS_THREADS 128
+
+__global__ void __launch_bounds__(RS_THREADS) k_resize(const LevelDev *__restrict__ levels, int l, int src_pitch,
+                                                       int src_rows_max) {
+    extern __shared__ __align__(16) uint8_t rs_smem[];
+    __shared__ int s_red[8];
     const LevelDev &L = levels[l];
     const LevelDev &S = levels[l - 1];
-    const int word = blockIdx.x * blockDim.x + threadIdx.x;
-    const int py = blockIdx.y, frame = blockIdx.z;
-    if (word * 4 >= L.pitch) return;
-    const int y = reflect101(py - ORBB_BORDER, L.h);
-    const uint8_t *sroi = S.img + (size_t)frame * S.frame_stride + (size_t)ORBB_BORDER * S.pitch + ORBB_ROI_X0;
-    const int b0 = word * 4;
-    uint32_t out = 0;
-    if (L.area2x) {
-        const uint8_t *r0 = sroi + (size_t)(2 * y) * S.pitch, *r1 = r0 + S.pitch;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const int px = b0 + k - ORBB_PAD_X0;
-            if (px >= 0 && px < L.w + 2 * ORBB_BORDER) {
-                const int x = reflect101(px - ORBB_BORDER, L.w);
-                const int v = (r0[2 * x] + r0[2 * x + 1] + r1[2 * x] + r1[2 * x + 1] + 2) >> 2;
-                out |= (uint32_t)v << (8 * k);
-            }
-        }
-    } else {
-        const int2 yr = __ldg(&L.yrows[y]);
-        const short2 bw = __ldg(&L.ybeta[y]);
-        const uint8_t *r0 = sroi + (size_t)yr.x * S.pitch, *r1 = sroi + (size_t)yr.y * S.pitch;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const int px = b0 + k - ORBB_PAD_X0;
-            if (px >= 0 && px < L.w + 2 * ORBB_BORDER) {
-                const int x = reflect101(px - ORBB_BORDER, L.w);
-                const int sx = __ldg(&L.xofs[x]);
-                const int sx1 = min(sx + 1, S.w - 1);
-                const short2 a = __ldg(&L.xalpha[x]);
-                const int t0 = r0[sx] * a.x + r0[sx1] * a.y;
-                const int t1 = r1[sx] * a.x + r1[sx1] * a.y;
-                const int v = ((((int)bw.x * (t0 >> 4)) >> 16) + (((int)bw.y * (t1 >> 4)) >> 16) + 2) >> 2;
-                out |= (uint32_t)v << (8 * k);
-            }
-        }
+    uint8_t *s_src = rs_smem;                                                         // [src_rows_max][src_pitch]
+    uint16_t *s_t = reinterpret_cast<uint16_t *>(rs_smem + (((size_t)src_rows_max * src_pitch + 15) & ~(size_t)15));  // [src_rows_max][RS_TW]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int bx0 = blockIdx.x * RS_TW, py0 = blockIdx.y * RS_TH, frame = blockIdx.z;
+    const int pw = L.w + 2 * ORBB_BORDER, ph = L.h + 2 * ORBB_BORDER;
+    const bool area = L.area2x != 0;
+
+    // per-column coefficients (thread = dst column c)
+    const int c = tid & (RS_TW - 1);
+    int px = bx0 + c - ORBB_PAD_X0;
+    px = min(max(px, 0), pw - 1);
+    const int rx = reflect101(px - ORBB_BORDER, L.w);
+    int sx, sx1, a0, a1;
+    if (area) { sx = 2 * rx; sx1 = sx + 1; a0 = 1; a1 = 1; }
+    else {
+        sx = __ldg(&L.xofs[rx]);
+        sx1 = min(sx + 1, S.w - 1);
+        const short2 a = __ldg(&L.xalpha[rx]);
+        a0 = a.x; a1 = a.y;
     }
-    *reinterpret_cast<uint32_t *>(L.img + (size_t)frame * L.frame_stride + (size_t)py * L.pitch + b0) = out;
+    // per-row source rows (threads 0..RS_TH-1 each own one dst row of the tile)
+    int r0 = 0x7fffffff, r1 = -1;
+    if (tid < RS_TH && py0 + tid < ph) {
+        const int ry = reflect101(py0 + tid - ORBB_BORDER, L.h);
+        if (area) { r0 = 2 * ry; r1 = r0 + 1; }
+        else { const int2 yr = __ldg(&L.yrows[ry]); r0 = yr.x; r1 = yr.y; }
+    }
+    // block-wide extents of the source window
+    int cmin = __reduce_min_sync(0xffffffffu, sx), cmax = __reduce_max_sync(0xffffffffu, sx1);
+    int rmin = __reduce_min_sync(0xffffffffu, r0), rmax = __reduce_max_sync(0xffffffffu, r1);
+    if (lane == 0) { s_red[warp] = cmin; s_red[4 + warp] = cmax; }
+    __syncthreads();
+    cmin = min(min(s_red[0], s_red[1]), min(s_red[2], s_red[3]));
+    cmax = max(max(s_red[4], s_red[5]), max(s_red[6], s_red[7]));
+    __syncthreads();
+    if (warp == 0 && lane == 0) { s_red[0] = rmin; s_red[1] = rmax; }  // rows live in warp 0 (RS_TH == 32)
+    __syncthreads();
+    rmin = s_red[0]; rmax = s_red[1];
+    const int sa = cmin & ~3;
+    const int nwords = (cmax - sa + 4) >> 2, nrows = rmax - rmin + 1;
+
+    // stage the source window
+    const uint8_t *sroi = S.img + (size_t)frame * S.frame_stride + (size_t)ORBB_BORDER * S.pitch + ORBB_ROI_X0;
+    for (int i = tid; i < nrows * nwords; i += RS_THREADS) {
+        const int r = i / nwords, wd = i - r * nwords;
+        reinterpret_cast<uint32_t *>(s_src + (size_t)r * src_pitch)[wd] =
+            *reinterpret_cast<const uint32_t *>(sroi + (size_t)(rmin + r) * S.pitch + sa + 4 * wd);
+    }
+    __syncthreads();
+    // H phase
+    const int o0 = sx - sa, o1 = sx1 - sa;
+    for (int r = tid >> 6; r < nrows; r += RS_THREADS / RS_TW) {
+        const uint8_t *row = s_src + (size_t)r * src_pitch;
+        const int t = row[o0] * a0 + row[o1] * a1;
+        s_t[r * RS_TW + c] = (uint16_t)(area ? t : (t >> 4));
+    }
+    __syncthreads();
+    // V phase: thread = (quad q of 4 columns, row group g)
+    const int q = tid & 15, g = tid >> 4;
+    uint8_t *drow = L.img + (size_t)frame * L.frame_stride + bx0 + 4 * q;
+    if (bx0 + 4 * q >= L.pitch) return;
+#pragma unroll
+    for (int k = 0; k < RS_TH / 8; ++k) {
+        const int py = py0 + g + 8 * k;
+        if (py >= ph) break;
+        const int ry = reflect101(py - ORBB_BORDER, L.h);
+        int y0, y1, b0, b1;
+        if (area) { y0 = 2 * ry; y1 = y0 + 1; b0 = b1 = 0; }
+        else {
+            const int2 yr = __ldg(&L.yrows[ry]);
+            const short2 bw = __ldg(&L.ybeta[ry]);
+            y0 = yr.x; y1 = yr.y; b0 = bw.x; b1 = bw.y;
+        }
+        const uint2 ta = *reinterpret_cast<const uint2 *>(s_t + (y0 - rmin) * RS_TW + 4 * q);
+        const uint2 tb = *reinterpret_cast<const uint2 *>(s_t + (y1 - rmin) * RS_TW + 4 * q);
+        const int t0[4] = {(int)(ta.x & 0xffff), (int)(ta.x >> 16), (int)(ta.y & 0xffff), (int)(ta.y >> 16)};
+        const int t1[4] = {(int)(tb.x & 0xffff), (int)(tb.x >> 16), (int)(tb.y & 0xffff), (int)(tb.y >> 16)};
+        uint32_t out = 0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int v = area ? ((t0[j] + t1[j] + 2) >> 2)
+                               : ((((b0 * t0[j]) >> 16) + ((b1 * t1[j]) >> 16) + 2) >> 2);
+            out |= (uint32_t)v << (8 * j);
+        }
+        *reinterpret_cast<uint32_t *>(drow + (size_t)py * L.pitch) = out;
+    }
 }
 
 // ---- 7x7 sigma=2 Gaussian of the ROI, OpenCV 4.13 fixed point: k = [18,34,48,56,48,34,18]/256 per
 // pass, dst = (V + 32768) >> 16.  Reads the padded level, so REFLECT_101 at the ROI
-// edge is already materialised by the border.  Tile: 64 x 32 outputs per CTA of 256 threads.
-#define BLUR_TW 64
-#define BLUR_TH 32
-__global__ void __launch_bounds__(256) k_blur(const LevelDev *__restrict__ levels, const TileEntry *__restrict__ tiles) {
-    __shared__ __align__(16) uint8_t s_in[(BLUR_TH + 6) * 80];          // cols -8..71 (aligned), rows -3..34
-    __shared__ __align__(16) uint16_t s_h[(BLUR_TH + 6) * BLUR_TW];     // horizontal pass, 8.8 fixed point
-    const TileEntry t = tiles[blockIdx.x];
-    const LevelDev &L = levels[t.level];
+// edge is already materialised by the border.
+// One thread owns 4 adjacent columns and walks BLUR_R output rows down the image.  Per input row it
+// issues three aligned, coalesced 32-bit loads (ROI rows are 16-byte aligned by layout), forms the
+// byte windows with funnel shifts and does the horizontal pass with IDP.4A (2 per pixel); the vertical
+// pass runs on a 7-deep register window, so no shared memory and no intermediate image exist.
+#define BLUR_R 16
+struct BlurIndex { int first[ORBB_MAX_LEVELS + 1]; };  // per-frame work-item prefix over levels
+
+__global__ void __launch_bounds__(128) k_blur(const LevelDev *__restrict__ levels, int n_levels, BlurIndex bi) {
+    const int item = blockIdx.x * blockDim.x + threadIdx.x;
+    if (item >= bi.first[n_levels]) return;
+    int l = 0;
+    while (item >= bi.first[l + 1]) ++l;
+    const LevelDev &L = levels[l];
     const int frame = blockIdx.y;
-    const int x0 = t.tx * BLUR_TW, y0 = t.ty * BLUR_TH;
+    const int wpr = (L.w + 3) >> 2;
+    const int local = item - bi.first[l];
+    const int strip = local / wpr, word = local - strip * wpr;
+    const int y0 = strip * BLUR_R, x = word * 4;
     const uint8_t *roi = L.img + (size_t)frame * L.frame_stride + (size_t)ORBB_BORDER * L.pitch + ORBB_ROI_X0;
-    // load rows y0-3 .. y0+34, cols x0-8 .. x0+71 as 20 words per row; clamp rows to the padded range
-    for (int i = threadIdx.x; i < (BLUR_TH + 6) * 20; i += 256) {
-        const int r = i / 20, wd = i - r * 20;
-        int yy = y0 - 3 + r;
-        yy = min(yy, L.h + ORBB_BORDER - 1);
-        int xx = x0 - 8 + wd * 4;
-        uint32_t v = 0;
-        if (xx + 3 < L.pitch - ORBB_ROI_X0)  // stay inside the row allocation
-            v = *reinterpret_cast<const uint32_t *>(roi + (ptrdiff_t)yy * L.pitch + xx);
-        reinterpret_cast<uint32_t *>(s_in)[r * 20 + wd] = v;
-    }
-    __syncthreads();
-    for (int i = threadIdx.x; i < (BLUR_TH + 6) * BLUR_TW; i += 256) {
-        const int r = i / BLUR_TW, c = i - r * BLUR_TW;
-        const uint8_t *p = s_in + r * 80 + c + 8 - 3;
-        const int s = 18 * (p[0] + p[6]) + 34 * (p[1] + p[5]) + 48 * (p[2] + p[4]) + 56 * p[3];
-        s_h[i] = (uint16_t)s;
-    }
-    __syncthreads();
-    // vertical pass: each thread makes 4 adjacent outputs of one row -> one 32-bit store
-    for (int i = threadIdx.x; i < BLUR_TH * (BLUR_TW / 4); i += 256) {
-        const int r = i / (BLUR_TW / 4), c4 = (i - r * (BLUR_TW / 4)) * 4;
-        const int y = y0 + r, x = x0 + c4;
-        if (y >= L.h || x >= L.w) continue;
-        uint32_t out = 0;
+    uint8_t *dst = L.blur + (size_t)frame * L.blur_stride + x;
+    const unsigned W1 = 18u | (34u << 8) | (48u << 16) | (56u << 24), W2 = 48u | (34u << 8) | (18u << 16);
+    const int ymax = L.h + ORBB_BORDER - 1;
+    unsigned h0[7], h1[7], h2[7], h3[7];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const uint16_t *q = s_h + r * BLUR_TW + c4 + k;
-            const uint32_t v = 18u * (q[0] + q[6 * BLUR_TW]) + 34u * (q[BLUR_TW] + q[5 * BLUR_TW]) +
-                               48u * (q[2 * BLUR_TW] + q[4 * BLUR_TW]) + 56u * q[3 * BLUR_TW];
-            out |= ((v + 32768u) >> 16) << (8 * k);
+    for (int r = 0; r < BLUR_R + 6; ++r) {
+        const int yy = min(y0 - 3 + r, ymax);
+        const uint32_t *p = reinterpret_cast<const uint32_t *>(roi + (ptrdiff_t)yy * L.pitch + x - 4);
+        const unsigned A = __ldg(p), B = __ldg(p + 1), C = __ldg(p + 2);
+        const unsigned n0 = __dp4a(__funnelshift_r(A, B, 8), W1, __dp4a(__funnelshift_r(B, C, 8), W2, 0u));
+        const unsigned n1 = __dp4a(__funnelshift_r(A, B, 16), W1, __dp4a(__funnelshift_r(B, C, 16), W2, 0u));
+        const unsigned n2 = __dp4a(__funnelshift_r(A, B, 24), W1, __dp4a(__funnelshift_r(B, C, 24), W2, 0u));
+        const unsigned n3 = __dp4a(B, W1, __dp4a(C, W2, 0u));
+#pragma unroll
+        for (int k = 0; k < 6; ++k) { h0[k] = h0[k + 1]; h1[k] = h1[k + 1]; h2[k] = h2[k + 1]; h3[k] = h3[k + 1]; }
+        h0[6] = n0; h1[6] = n1; h2[6] = n2; h3[6] = n3;
+        if (r >= 6) {
+            const int y = y0 + r - 6;
+            if (y < L.h) {
+                const unsigned v0 = 32768u + 18u * (h0[0] + h0[6]) + 34u * (h0[1] + h0[5]) + 48u * (h0[2] + h0[4]) + 56u * h0[3];
+                const unsigned v1 = 32768u + 18u * (h1[0] + h1[6]) + 34u * (h1[1] + h1[5]) + 48u * (h1[2] + h1[4]) + 56u * h1[3];
+                const unsigned v2 = 32768u + 18u * (h2[0] + h2[6]) + 34u * (h2[1] + h2[5]) + 48u * (h2[2] + h2[4]) + 56u * h2[3];
+                const unsigned v3 = 32768u + 18u * (h3[0] + h3[6]) + 34u * (h3[1] + h3[5]) + 48u * (h3[2] + h3[4]) + 56u * h3[3];
+                const unsigned lo = __byte_perm(v0, v1, 0x0062), hi = __byte_perm(v2, v3, 0x0062);
+                *reinterpret_cast<uint32_t *>(dst + (size_t)y * L.pitch) = __byte_perm(lo, hi, 0x5410);
+            }
         }
-        *reinterpret_cast<uint32_t *>(L.blur + (size_t)frame * L.blur_stride + (size_t)y * L.pitch + x) = out;
     }
 }
 
@@ -147,17 +211,31 @@ cudaError_t launch_level0(const uint8_t *d_in, size_t pitch, size_t stride, cons
     return cudaGetLastError();
 }
 
-cudaError_t launch_resize(const LevelDev *d_levels, const LevelDev &Lh, int l, int n_frames, cudaStream_t st) {
-    const int words = Lh.pitch / 4;
-    dim3 grid((words + 127) / 128, Lh.rows, n_frames);
-    k_resize<<<grid, 128, 0, st>>>(d_levels, l);
+cudaError_t launch_resize(const LevelDev *d_levels, const LevelDev *h_levels, int l, int n_frames, cudaStream_t st) {
+    const LevelDev &Lh = h_levels[l], &Sh = h_levels[l - 1];
+    // worst-case source window of one tile (+ slack for clamping/alignment)
+    const int src_cols = (int)((double)RS_TW * Sh.w / Lh.w) + 8;
+    const int src_pitch = ((src_cols + 3) / 4 + 1) * 4;
+    const int src_rows = (int)((double)RS_TH * Sh.h / Lh.h) + 5;
+    const size_t smem = (((size_t)src_rows * src_pitch + 15) & ~(size_t)15) + (size_t)src_rows * RS_TW * 2;
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(k_resize, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+    }
+    dim3 grid((Lh.pitch + RS_TW - 1) / RS_TW, (Lh.rows + RS_TH - 1) / RS_TH, n_frames);
+    k_resize<<<grid, RS_THREADS, smem, st>>>(d_levels, l, src_pitch, src_rows);
     return cudaGetLastError();
 }
 
-cudaError_t launch_blur(const LevelDev *d_levels, const TileEntry *d_tiles, int n_tiles, int n_frames,
+cudaError_t launch_blur(const LevelDev *d_levels, const LevelDev *h_levels, int n_levels, int n_frames,
                         cudaStream_t st) {
-    dim3 grid(n_tiles, n_frames);
-    k_blur<<<grid, 256, 0, st>>>(d_levels, d_tiles);
+    BlurIndex bi;
+    bi.first[0] = 0;
+    for (int l = 0; l < n_levels; ++l)
+        bi.first[l + 1] = bi.first[l] + ((h_levels[l].h + BLUR_R - 1) / BLUR_R) * ((h_levels[l].w + 3) >> 2);
+    for (int l = n_levels + 1; l <= ORBB_MAX_LEVELS; ++l) bi.first[l] = bi.first[n_levels];
+    dim3 grid((bi.first[n_levels] + 127) / 128, n_frames);
+    k_blur<<<grid, 128, 0, st>>>(d_levels, n_levels, bi);
     return cudaGetLastError();
 }
 

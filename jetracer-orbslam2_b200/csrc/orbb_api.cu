@@ -14,8 +14,8 @@
 
 namespace orbb {
 cudaError_t launch_level0(const uint8_t *, size_t, size_t, const LevelDev &, int, cudaStream_t);
-cudaError_t launch_resize(const LevelDev *, const LevelDev &, int, int, cudaStream_t);
-cudaError_t launch_blur(const LevelDev *, const TileEntry *, int, int, cudaStream_t);
+cudaError_t launch_resize(const LevelDev *, const LevelDev *, int, int, cudaStream_t);
+cudaError_t launch_blur(const LevelDev *, const LevelDev *, int, int, cudaStream_t);
 cudaError_t launch_fast(const LevelDev *, const CellEntry *, int, int, int *, int, int, const FastSmemCfg &, int,
                         cudaStream_t);
 cudaError_t launch_fast_dump(const LevelDev *, const CellEntry *, int, int, int, int, const FastSmemCfg &, int,
@@ -409,7 +409,7 @@ extern "C" int orbb_stage_upload(orbb_handle *h, const uint8_t *d_images, size_t
 extern "C" int orbb_pyramid_create_levels(orbb_handle *h, void *stream) {
     if (!h || h->n_frames_last < 1) return ORBB_ERR_INVALID;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    for (int l = 1; l < h->nlevels; ++l) CK(h, launch_resize(h->d_levels, h->lv[l], l, h->n_frames_last, st));
+    for (int l = 1; l < h->nlevels; ++l) CK(h, launch_resize(h->d_levels, h->lv, l, h->n_frames_last, st));
     return ORBB_OK;
 }
 
@@ -434,7 +434,7 @@ extern "C" int orbb_detect(orbb_handle *h, void *stream) {
 
 extern "C" int orbb_gaussian_blur(orbb_handle *h, void *stream) {
     if (!h || h->n_frames_last < 1) return ORBB_ERR_INVALID;
-    CK(h, launch_blur(h->d_levels, h->d_tiles, h->n_tiles, h->n_frames_last, static_cast<cudaStream_t>(stream)));
+    CK(h, launch_blur(h->d_levels, h->lv, h->nlevels, h->n_frames_last, static_cast<cudaStream_t>(stream)));
     return ORBB_OK;
 }
 
