@@ -298,13 +298,21 @@ def main():
     match_ms = m0.elapsed_time(m1) / m_iters
     gpairs = nq * MAP_SIZE / (match_ms * 1e-3) / 1e9
 
-    # ---- reduce over ranks: max time, sum of keypoints (the only collective: counts, after the timed region)
-    t = torch.tensor([total_ms, e2e_ms, match_ms], dtype=torch.float64, device=dev)
-    kp_total = torch.tensor([float(counts.sum())], dtype=torch.float64, device=dev)
+    # ---- the only collectives (after the timed region): gather per-frame counts and match records to rank 0
+    sharding = importlib.import_module(PKG + ".sharding")
+    g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    g0.record(st)
+    all_counts = sharding.gather_counts(d_cnt, B * world)
+    records = torch.stack([torch.arange(nq, dtype=torch.int32, device=dev), m_idx[:, 0], m_dist[:, 0]], 1)
+    gathered, _ = sharding.gather_ragged_to_rank0(records)
+    g1.record(st)
+    torch.cuda.synchronize()
+    gather_ms = g0.elapsed_time(g1)
+    t = torch.tensor([total_ms, e2e_ms, match_ms, gather_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dist.all_reduce(kp_total, op=dist.ReduceOp.SUM)
-    total_ms, e2e_ms, match_ms_max = [float(v) for v in t.tolist()]
+    total_ms, e2e_ms, match_ms_max, gather_ms = [float(v) for v in t.tolist()]
+    kp_total = all_counts.sum().to(torch.float64).reshape(1)
 
     if rank == 0:
         hbm_peak, peak_kind, sm_max = measured_peaks()
@@ -332,6 +340,9 @@ def main():
                               "frac_of_hbm": BYTES_PER_FRAME * fps / world / 1e9 / hbm_peak},
             "stages_ms": dict(zip(stage_names, stage_ms)),
             "keypoints_per_frame": float(kp_total.item()) / (B * world),
+            "gather": {"ms": gather_ms, "what": "all_gather of per-frame counts + ragged gather of {q,t,dist} match "
+                                               "records to rank 0 (NCCL), after the timed region",
+                       "records_on_rank0": int(gathered.shape[0]) if gathered is not None else 0},
             "matcher": {"value": gpairs * world * (match_ms / match_ms_max), "unit": "Gpairs/s", "nq_per_gpu": nq,
                         "nt": MAP_SIZE, "k": 1, "ms": match_ms_max, "popc_roof_gpairs_per_gpu": popc_roof,
                         "frac_of_popc_roof": gpairs / popc_roof},

@@ -1,0 +1,151 @@
+// orbb200.hpp -- header-only C++ host mirror over the C ABI (include/orbb200.h).
+//
+// The reference's host code is C++ (SlamGpuPipeline::buildStream, reference
+// src/SlamGpuPipeline/buildStream.cpp:190-680), so this is what a maintainer includes:
+//   * orbb200::ORBextractor -- the upstream ORB-SLAM2 surface the reference names in
+//     src_trash1/orb_extractor.cpp:6-8: ctor(nfeatures, scaleFactor, nlevels, iniThFAST, minThFAST),
+//     operator()(image, mask, keypoints, descriptors), GetLevels/GetScaleFactors/... getters.
+//     OpenCV headers are optional (define ORBB_WITH_OPENCV to get the cv::InputArray overload).
+//   * namespace Jetracer -- the stage functions with the reference's names
+//     (src/cuda/pyramid.cuh:20-21, fast.cuh:42-48, nms.cuh:11-15, orb.cuh:9-37, post_processing.cuh:40-51),
+//     taking the handle (which owns what the reference passed as std::vector<pyramid_t> + raw buffers).
+// Errors become std::runtime_error (the reference aborts the process, src/cuda_common.h:69-95).
+#ifndef ORBB200_HPP
+#define ORBB200_HPP
+
+#include <cstdint>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "orbb200.h"
+
+#ifdef ORBB_WITH_OPENCV
+#include <opencv2/core.hpp>
+#endif
+
+namespace orbb200 {
+
+using KeyPoint = orbb_keypoint;  // layout-identical to cv::KeyPoint (28 bytes)
+
+inline void check(int rc, const orbb_handle *h, const char *what) {
+    if (rc >= 0) return;
+    std::string msg = std::string(what) + ": " + orbb_strerror(rc);
+    if (rc == ORBB_ERR_CUDA && h) msg += std::string(" (") + orbb_last_cuda_error(h) + ")";
+    throw std::runtime_error(msg);
+}
+
+class ORBextractor {
+public:
+    ORBextractor(int nfeatures, float scaleFactor, int nlevels, int iniThFAST, int minThFAST, int width, int height,
+                 int max_batch = 1, int device = -1)
+        : width_(width), height_(height), max_batch_(max_batch) {
+        orbb_params p{nfeatures, scaleFactor, nlevels, iniThFAST, minThFAST};
+        check(orbb_create(&h_, &p, width, height, max_batch, device), nullptr, "orbb_create");
+        nlevels_ = orbb_get_levels(h_);
+        scale_factor_ = scaleFactor;
+        max_kp_ = orbb_max_keypoints_per_frame(h_);
+        mvScaleFactor.resize(nlevels_); mvInvScaleFactor.resize(nlevels_);
+        mvLevelSigma2.resize(nlevels_); mvInvLevelSigma2.resize(nlevels_);
+        check(orbb_get_scale_factors(h_, mvScaleFactor.data(), mvInvScaleFactor.data(), mvLevelSigma2.data(),
+                                     mvInvLevelSigma2.data()), h_, "orbb_get_scale_factors");
+        kp_.resize((size_t)max_kp_ * max_batch_);
+        desc_.resize((size_t)max_kp_ * max_batch_ * ORBB_DESC_BYTES);
+        counts_.resize(max_batch_);
+    }
+    ~ORBextractor() { orbb_destroy(h_); }
+    ORBextractor(const ORBextractor &) = delete;
+    ORBextractor &operator=(const ORBextractor &) = delete;
+
+    // ORBextractor::operator()(image, mask, keypoints, descriptors); mask is ignored (as upstream).
+    // descriptors: keypoints.size() x 32 bytes, row-major.
+    void operator()(const uint8_t *image, size_t pitch, const uint8_t * /*mask*/, std::vector<KeyPoint> &keypoints,
+                    std::vector<uint8_t> &descriptors, void *cuda_stream = nullptr) {
+        check(orbb_extract_batch_host(h_, image, pitch, pitch * (size_t)height_, 1, kp_.data(), desc_.data(),
+                                      counts_.data(), max_kp_, cuda_stream), h_, "orbb_extract_batch_host");
+        const int n = counts_[0];
+        keypoints.assign(kp_.begin(), kp_.begin() + n);
+        descriptors.assign(desc_.begin(), desc_.begin() + (size_t)n * ORBB_DESC_BYTES);
+    }
+    // batch form: frames [n][height][pitch]; outputs per frame
+    void extract(const uint8_t *frames, size_t pitch, size_t frame_stride, int n,
+                 std::vector<std::vector<KeyPoint>> &keypoints, std::vector<std::vector<uint8_t>> &descriptors,
+                 void *cuda_stream = nullptr) {
+        check(orbb_extract_batch_host(h_, frames, pitch, frame_stride, n, kp_.data(), desc_.data(), counts_.data(),
+                                      max_kp_, cuda_stream), h_, "orbb_extract_batch_host");
+        keypoints.resize(n); descriptors.resize(n);
+        for (int f = 0; f < n; ++f) {
+            const size_t o = (size_t)f * max_kp_;
+            keypoints[f].assign(kp_.begin() + o, kp_.begin() + o + counts_[f]);
+            descriptors[f].assign(desc_.begin() + o * 32, desc_.begin() + (o + counts_[f]) * 32);
+        }
+    }
+#ifdef ORBB_WITH_OPENCV
+    void operator()(cv::InputArray image, cv::InputArray mask, std::vector<cv::KeyPoint> &keypoints,
+                    cv::OutputArray descriptors) {
+        (void)mask;
+        cv::Mat im = image.getMat();
+        if (im.empty()) return;
+        CV_Assert(im.type() == CV_8UC1 && im.cols == width_ && im.rows == height_);
+        std::vector<KeyPoint> kp; std::vector<uint8_t> d;
+        (*this)(im.data, im.step, nullptr, kp, d);
+        keypoints.resize(kp.size());
+        for (size_t i = 0; i < kp.size(); ++i)
+            keypoints[i] = cv::KeyPoint(kp[i].x, kp[i].y, kp[i].size, kp[i].angle, kp[i].response, kp[i].octave, kp[i].class_id);
+        if (kp.empty()) { descriptors.release(); return; }
+        descriptors.create((int)kp.size(), 32, CV_8U);
+        std::memcpy(descriptors.getMat().data, d.data(), d.size());
+    }
+#endif
+    int GetLevels() const { return nlevels_; }
+    float GetScaleFactor() const { return scale_factor_; }
+    std::vector<float> GetScaleFactors() const { return mvScaleFactor; }
+    std::vector<float> GetInverseScaleFactors() const { return mvInvScaleFactor; }
+    std::vector<float> GetScaleSigmaSquares() const { return mvLevelSigma2; }
+    std::vector<float> GetInverseScaleSigmaSquares() const { return mvInvLevelSigma2; }
+    // mvImagePyramid[level] of the last batch (device memory, padded layout)
+    orbb_level ImagePyramidLevel(int level, int frame = 0) const {
+        orbb_level l{};
+        check(orbb_get_level(h_, frame, level, &l), h_, "orbb_get_level");
+        return l;
+    }
+    orbb_handle *handle() const { return h_; }
+    int max_keypoints() const { return max_kp_; }
+
+private:
+    orbb_handle *h_ = nullptr;
+    int width_, height_, max_batch_, nlevels_ = 0, max_kp_ = 0;
+    float scale_factor_ = 1.2f;
+    std::vector<float> mvScaleFactor, mvInvScaleFactor, mvLevelSigma2, mvInvLevelSigma2;
+    std::vector<KeyPoint> kp_;
+    std::vector<uint8_t> desc_;
+    std::vector<int32_t> counts_;
+};
+
+}  // namespace orbb200
+
+// ---- the reference's stage names (namespace Jetracer), async on the given stream -------------------------
+namespace Jetracer {
+inline void upload_frames(orbb_handle *h, const uint8_t *d_images, size_t pitch, size_t frame_stride, int n_frames,
+                          void *stream) {
+    orbb200::check(orbb_stage_upload(h, d_images, pitch, frame_stride, n_frames, stream), h, "upload_frames");
+}
+inline void pyramid_create_levels(orbb_handle *h, void *stream) {
+    orbb200::check(orbb_pyramid_create_levels(h, stream), h, "pyramid_create_levels");
+}
+inline void detect(orbb_handle *h, void *stream) { orbb200::check(orbb_detect(h, stream), h, "detect"); }
+inline void gaussian_blur(orbb_handle *h, void *stream) { orbb200::check(orbb_gaussian_blur(h, stream), h, "gaussian_blur"); }
+// compute_fast_angle + calc_orb fused: angles (degrees) and 256-bit descriptors into caller-owned device arrays
+inline void compute_fast_angle_and_calc_orb(orbb_handle *h, orbb_keypoint *d_kp, uint8_t *d_desc, int32_t *d_counts,
+                                            int max_kp, void *stream) {
+    orbb200::check(orbb_compute_angle_and_orb(h, d_kp, d_desc, d_counts, max_kp, stream), h, "calc_orb");
+}
+inline void match_keypoints(orbb_handle *h, const uint8_t *d_query, int nq, const uint8_t *d_train, int nt, int k,
+                            float ratio, int32_t *d_idx, int32_t *d_dist, uint8_t *d_accept, int32_t *d_naccept,
+                            void *stream) {
+    orbb200::check(orbb_match_knn(h, d_query, nq, d_train, nt, k, ratio, d_idx, d_dist, d_accept, d_naccept, stream), h,
+                   "match_keypoints");
+}
+}  // namespace Jetracer
+
+#endif  // ORBB200_HPP

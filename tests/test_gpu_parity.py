@@ -288,3 +288,25 @@ def test_full_size_properties(orbb, synth):
     idx, dist, acc, _ = orbb.match_knn_host(ex, desc[0, :counts[0]], desc[4, :counts[4]], k=1)
     assert (dist[:, 0] == 0).all()
     ex.close()
+
+
+def test_cpp_host_mirror(orbb, oracle, synth, tmp_path):
+    """include/orbb200.hpp (the C++ mirror a reference maintainer would include) gives the same bytes."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = tmp_path / "host_mirror"
+    libdir = os.path.join(root, "jetracer-orbslam2_b200")
+    subprocess.run(["g++", "-std=c++17", "-O2", "-I" + os.path.join(root, "include"),
+                    os.path.join(root, "tests", "cpp", "host_mirror_main.cpp"), "-o", str(exe), "-L" + libdir,
+                    "-lorbb200", "-Wl,-rpath," + libdir], check=True)
+    img = synth.textured_frame(640, 480, 4242)
+    raw, out = tmp_path / "frame.raw", tmp_path / "out.bin"
+    raw.write_bytes(img.tobytes())
+    subprocess.run([str(exe), str(raw), "640", "480", str(out)], check=True)
+    blob = out.read_bytes()
+    n = int(np.frombuffer(blob[:4], np.int32)[0])
+    kp = np.frombuffer(blob[4:4 + 28 * n], orbb.KEYPOINT_DTYPE)
+    desc = np.frombuffer(blob[4 + 28 * n:], np.uint8).reshape(n, 32)
+    okp, odesc = canon(*oracle.Oracle(640, 480).extract(img))
+    kp, desc = canon(kp, desc)
+    assert n == len(okp) and kp.tobytes() == okp.tobytes() and np.array_equal(desc, odesc)
