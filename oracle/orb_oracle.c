@@ -159,34 +159,43 @@ int orbo_fast9_window(const uint8_t *win, int cw, int ch, size_t pitch, int thr,
                       orbo_candidate *out, int max_out) {
     if (cw < 7 || ch < 7) return 0;
     thr = thr < 0 ? 0 : (thr > 255 ? 255 : thr);
-    uint8_t *sc = (uint8_t *)calloc((size_t)cw * ch, 1);
-    uint8_t *is = (uint8_t *)calloc((size_t)cw * ch, 1);
-    for (int y = 3; y < ch - 3; ++y)
+    /* score rows with a zero frame; 0 = "not a corner at this threshold" (a corner scores >= thr, and a
+     * corner with thr == 0 and score 0 cannot beat anything in the strict NMS either) */
+    const int sp = cw + 2;
+    uint8_t stack_buf[80 * 80];
+    uint8_t *sc = (size_t)sp * (ch + 2) <= sizeof(stack_buf) ? stack_buf : (uint8_t *)malloc((size_t)sp * (ch + 2));
+    uint8_t *is = NULL;
+    memset(sc, 0, (size_t)sp * (ch + 2));
+    if (thr == 0 || !nms) is = (uint8_t *)calloc((size_t)cw * ch, 1);
+    for (int y = 3; y < ch - 3; ++y) {
+        const uint8_t *row = win + (size_t)y * pitch;
         for (int x = 3; x < cw - 3; ++x) {
-            const uint8_t *p = win + (size_t)y * pitch + x;
-            if (is_corner9(p, pitch, thr)) {
-                is[y * cw + x] = 1;
-                sc[y * cw + x] = (uint8_t)corner_score16(p, pitch, thr);
-            }
+            const uint8_t *p = row + x;
+            const int v = p[0], lo = v - thr, hi = v + thr;
+            /* any 9-arc contains one pixel of every antipodal pair (same prune as cv::FAST) */
+            const int r0 = p[3 * (ptrdiff_t)pitch], r8 = p[-3 * (ptrdiff_t)pitch], r4 = p[3], r12 = p[-3];
+            const int dark = ((r0 < lo) | (r8 < lo)) & ((r4 < lo) | (r12 < lo));
+            const int bright = ((r0 > hi) | (r8 > hi)) & ((r4 > hi) | (r12 > hi));
+            if (!(dark | bright)) continue;
+            if (!is_corner9(p, pitch, thr)) continue;
+            sc[(y + 1) * sp + x + 1] = (uint8_t)corner_score16(p, pitch, thr);
+            if (is) is[y * cw + x] = 1;
         }
+    }
     int n = 0;
     for (int y = 3; y < ch - 3; ++y)
         for (int x = 3; x < cw - 3; ++x) {
-            if (!is[y * cw + x]) continue;
-            int s = sc[y * cw + x], keep = 1;
-            if (nms) {
-                for (int dy = -1; dy <= 1 && keep; ++dy)
-                    for (int dx = -1; dx <= 1; ++dx) {
-                        if (!dx && !dy) continue;
-                        if (!(s > sc[(y + dy) * cw + x + dx])) { keep = 0; break; }
-                    }
-            }
-            if (keep) {
-                if (n < max_out) { out[n].x = x; out[n].y = y; out[n].response = s; }
-                ++n;
-            }
+            const uint8_t *q = sc + (y + 1) * sp + x + 1;
+            const int s = q[0];
+            if (is ? !is[y * cw + x] : s == 0) continue;
+            if (nms && !(s > q[-1] && s > q[1] && s > q[-sp - 1] && s > q[-sp] && s > q[-sp + 1] &&
+                         s > q[sp - 1] && s > q[sp] && s > q[sp + 1]))
+                continue;
+            if (n < max_out) { out[n].x = x; out[n].y = y; out[n].response = s; }
+            ++n;
         }
-    free(sc); free(is);
+    if (sc != stack_buf) free(sc);
+    free(is);
     return n;
 }
 
@@ -203,21 +212,35 @@ void orbo_fast_score_map(const uint8_t *img, int w, int h, size_t pitch, uint8_t
 /* ---------- cv::GaussianBlur(7x7, 2, 2, REFLECT_101) on 8U, OpenCV 4.13 -- A.6 ----------
  * fixed-point separable kernel [18,34,48,56,48,34,18]/256, dst = (V + 32768) >> 16 */
 void orbo_gaussian_blur7(const uint8_t *src, int w, int h, size_t sp, uint8_t *dst, size_t dp) {
-    static const int k[7] = {18, 34, 48, 56, 48, 34, 18};
-    uint32_t *hbuf = (uint32_t *)malloc(sizeof(uint32_t) * (size_t)w * h);
-    for (int y = 0; y < h; ++y)
+    static const uint32_t k[7] = {18, 34, 48, 56, 48, 34, 18};
+    uint16_t *hbuf = (uint16_t *)malloc(sizeof(uint16_t) * (size_t)w * h);
+    int *xi = (int *)malloc(sizeof(int) * (size_t)(w + 6));
+    for (int x = -3; x < w + 3; ++x) xi[x + 3] = reflect101(x, w);
+    for (int y = 0; y < h; ++y) {
+        const uint8_t *r = src + (size_t)y * sp;
+        uint16_t *o = hbuf + (size_t)y * w;
         for (int x = 0; x < w; ++x) {
-            uint32_t s = 0;
-            for (int i = 0; i < 7; ++i) s += (uint32_t)k[i] * src[(size_t)y * sp + reflect101(x + i - 3, w)];
-            hbuf[(size_t)y * w + x] = s;
+            if (x >= 3 && x < w - 3) {
+                const uint8_t *p = r + x - 3;
+                o[x] = (uint16_t)(18 * (p[0] + p[6]) + 34 * (p[1] + p[5]) + 48 * (p[2] + p[4]) + 56 * p[3]);
+            } else {
+                uint32_t s = 0;
+                for (int i = 0; i < 7; ++i) s += k[i] * r[xi[x + i]];
+                o[x] = (uint16_t)s;
+            }
         }
-    for (int y = 0; y < h; ++y)
+    }
+    for (int y = 0; y < h; ++y) {
+        const uint16_t *rr[7];
+        for (int i = 0; i < 7; ++i) rr[i] = hbuf + (size_t)reflect101(y + i - 3, h) * w;
+        uint8_t *o = dst + (size_t)y * dp;
         for (int x = 0; x < w; ++x) {
-            uint32_t s = 0;
-            for (int i = 0; i < 7; ++i) s += (uint32_t)k[i] * hbuf[(size_t)reflect101(y + i - 3, h) * w + x];
-            dst[(size_t)y * dp + x] = (uint8_t)((s + 32768u) >> 16);
+            const uint32_t s = 18u * ((uint32_t)rr[0][x] + rr[6][x]) + 34u * ((uint32_t)rr[1][x] + rr[5][x]) +
+                               48u * ((uint32_t)rr[2][x] + rr[4][x]) + 56u * rr[3][x];
+            o[x] = (uint8_t)((s + 32768u) >> 16);
         }
-    free(hbuf);
+    }
+    free(hbuf); free(xi);
 }
 
 /* cv::fastAtan2 (degrees), float32, no FMA -- A.5 */
