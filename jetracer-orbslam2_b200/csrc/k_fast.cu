@@ -201,8 +201,8 @@ k_fast_cells(const LevelDev *__restrict__ levels, const CellEntry *__restrict__ 
 }
 
 cudaError_t launch_fast(const LevelDev *d_levels, const CellEntry *d_cells, int n_cells, int n_levels,
-                        int *d_cand_count, int t_lo, int t_hi, const FastSmemCfg &cfg, int n_frames,
-                        cudaStream_t st) {
+                        int *d_cand_count, int t_lo, int t_hi, const FastSmemCfg &cfg, int frame_base,
+                        int n_frames, cudaStream_t st) {
     dim3 grid((n_cells + FAST_WARPS - 1) / FAST_WARPS, n_frames);
     const size_t smem = (size_t)cfg.warp_bytes * FAST_WARPS;
     if (smem > 48 * 1024) {
@@ -210,7 +210,7 @@ cudaError_t launch_fast(const LevelDev *d_levels, const CellEntry *d_cells, int 
         if (e != cudaSuccess) return e;
     }
     k_fast_cells<false><<<grid, FAST_WARPS * 32, smem, st>>>(d_levels, d_cells, n_cells, n_levels, d_cand_count,
-                                                            t_lo, t_hi, cfg, 0, nullptr, nullptr);
+                                                            t_lo, t_hi, cfg, frame_base, nullptr, nullptr);
     return cudaGetLastError();
 }
 

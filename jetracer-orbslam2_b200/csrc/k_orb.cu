@@ -47,11 +47,11 @@ __global__ void __launch_bounds__(ORB_WARPS * 32)
 k_angle_orb(const LevelDev *__restrict__ levels, int n_levels, const int *__restrict__ sel_count,
             const int8_t *__restrict__ pattern, const int *__restrict__ slot_level, const int *__restrict__ slot_base,
             int n_slots, orbb_keypoint *__restrict__ out_kp, uint8_t *__restrict__ out_desc,
-            int *__restrict__ out_counts, int max_kp) {
+            int *__restrict__ out_counts, int max_kp, int frame_base) {
     __shared__ __align__(16) uint8_t s_patch[ORB_WARPS][PATCH_ROWS * PATCH_PITCH];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int gslot = blockIdx.x * ORB_WARPS + warp;
-    const int frame = blockIdx.y;
+    const int frame = blockIdx.y + frame_base;
     if (gslot >= n_slots) return;
     const int level = slot_level[gslot], slot = gslot - slot_base[level];
     const int *cnt = sel_count + frame * n_levels;
@@ -145,11 +145,11 @@ k_angle_orb(const LevelDev *__restrict__ levels, int n_levels, const int *__rest
 }
 
 cudaError_t launch_angle_orb(const LevelDev *d_levels, int n_levels, const int *d_sel_count, const int8_t *d_pattern,
-                             const int *d_slot_level, const int *d_slot_base, int n_slots, int n_frames,
-                             orbb_keypoint *d_kp, uint8_t *d_desc, int *d_counts, int max_kp, cudaStream_t st) {
+                             const int *d_slot_level, const int *d_slot_base, int n_slots, int frame_base,
+                             int n_frames, orbb_keypoint *d_kp, uint8_t *d_desc, int *d_counts, int max_kp, cudaStream_t st) {
     dim3 grid((n_slots + ORB_WARPS - 1) / ORB_WARPS, n_frames);
     k_angle_orb<<<grid, ORB_WARPS * 32, 0, st>>>(d_levels, n_levels, d_sel_count, d_pattern, d_slot_level, d_slot_base,
-                                                 n_slots, d_kp, d_desc, d_counts, max_kp);
+                                                 n_slots, d_kp, d_desc, d_counts, max_kp, frame_base);
     return cudaGetLastError();
 }
 

@@ -21,12 +21,12 @@ __device__ __forceinline__ int reflect101(int p, int len) {
 
 // ---- level 0: copy the caller's frames into the padded layout + border
 __global__ void __launch_bounds__(128) k_level0(const uint8_t *__restrict__ in, size_t in_pitch,
-                                                size_t in_stride, LevelDev L, int aligned4) {
+                                                size_t in_stride, LevelDev L, int aligned4, int frame_base) {
     const int word = blockIdx.x * blockDim.x + threadIdx.x;
-    const int py = blockIdx.y, frame = blockIdx.z;
+    const int py = blockIdx.y, frame = blockIdx.z + frame_base;
     if (word * 4 >= L.pitch) return;
     const int y = reflect101(py - ORBB_BORDER, L.h);
-    const uint8_t *src = in + (size_t)frame * in_stride + (size_t)y * in_pitch;
+    const uint8_t *src = in + (size_t)blockIdx.z * in_stride + (size_t)y * in_pitch;
     const int b0 = word * 4;
     uint32_t out = 0;
     const int x0 = b0 - ORBB_ROI_X0;
@@ -56,7 +56,7 @@ __global__ void __launch_bounds__(128) k_level0(const uint8_t *__restrict__ in, 
 #define RS_THREADS 128
 
 __global__ void __launch_bounds__(RS_THREADS) k_resize(const LevelDev *__restrict__ levels, int l, int src_pitch,
-                                                       int src_rows_max) {
+                                                       int src_rows_max, int frame_base) {
     extern __shared__ __align__(16) uint8_t rs_smem[];
     __shared__ int s_red[8];
     const LevelDev &L = levels[l];
@@ -64,7 +64,7 @@ __global__ void __launch_bounds__(RS_THREADS) k_resize(const LevelDev *__restric
     uint8_t *s_src = rs_smem;                                                         // [src_rows_max][src_pitch]
     uint16_t *s_t = reinterpret_cast<uint16_t *>(rs_smem + (((size_t)src_rows_max * src_pitch + 15) & ~(size_t)15));  // [src_rows_max][RS_TW]
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int bx0 = blockIdx.x * RS_TW, py0 = blockIdx.y * RS_TH, frame = blockIdx.z;
+    const int bx0 = blockIdx.x * RS_TW, py0 = blockIdx.y * RS_TH, frame = blockIdx.z + frame_base;
     const int pw = L.w + 2 * ORBB_BORDER, ph = L.h + 2 * ORBB_BORDER;
     const bool area = L.area2x != 0;
 
@@ -159,13 +159,14 @@ __global__ void __launch_bounds__(RS_THREADS) k_resize(const LevelDev *__restric
 #define BLUR_R 16
 struct BlurIndex { int first[ORBB_MAX_LEVELS + 1]; };  // per-frame work-item prefix over levels
 
-__global__ void __launch_bounds__(128) k_blur(const LevelDev *__restrict__ levels, int n_levels, BlurIndex bi) {
+__global__ void __launch_bounds__(128) k_blur(const LevelDev *__restrict__ levels, int n_levels, BlurIndex bi,
+                                              int frame_base) {
     const int item = blockIdx.x * blockDim.x + threadIdx.x;
     if (item >= bi.first[n_levels]) return;
     int l = 0;
     while (item >= bi.first[l + 1]) ++l;
     const LevelDev &L = levels[l];
-    const int frame = blockIdx.y;
+    const int frame = blockIdx.y + frame_base;
     const int wpr = (L.w + 3) >> 2;
     const int local = item - bi.first[l];
     const int strip = local / wpr, word = local - strip * wpr;
@@ -202,16 +203,17 @@ __global__ void __launch_bounds__(128) k_blur(const LevelDev *__restrict__ level
 }
 
 // ---------------------------------------------------------------- host launchers
-cudaError_t launch_level0(const uint8_t *d_in, size_t pitch, size_t stride, const LevelDev &L0, int n_frames,
-                          cudaStream_t st) {
+cudaError_t launch_level0(const uint8_t *d_in, size_t pitch, size_t stride, const LevelDev &L0, int frame_base,
+                          int n_frames, cudaStream_t st) {
     const int words = L0.pitch / 4;
     dim3 grid((words + 127) / 128, L0.rows, n_frames);
     const int aligned4 = ((reinterpret_cast<uintptr_t>(d_in) | pitch | stride) & 3) == 0;
-    k_level0<<<grid, 128, 0, st>>>(d_in, pitch, stride, L0, aligned4);
+    k_level0<<<grid, 128, 0, st>>>(d_in, pitch, stride, L0, aligned4, frame_base);
     return cudaGetLastError();
 }
 
-cudaError_t launch_resize(const LevelDev *d_levels, const LevelDev *h_levels, int l, int n_frames, cudaStream_t st) {
+cudaError_t launch_resize(const LevelDev *d_levels, const LevelDev *h_levels, int l, int frame_base, int n_frames,
+                          cudaStream_t st) {
     const LevelDev &Lh = h_levels[l], &Sh = h_levels[l - 1];
     // worst-case source window of one tile (+ slack for clamping/alignment)
     const int src_cols = (int)((double)RS_TW * Sh.w / Lh.w) + 8;
@@ -223,19 +225,19 @@ cudaError_t launch_resize(const LevelDev *d_levels, const LevelDev *h_levels, in
         if (e != cudaSuccess) return e;
     }
     dim3 grid((Lh.pitch + RS_TW - 1) / RS_TW, (Lh.rows + RS_TH - 1) / RS_TH, n_frames);
-    k_resize<<<grid, RS_THREADS, smem, st>>>(d_levels, l, src_pitch, src_rows);
+    k_resize<<<grid, RS_THREADS, smem, st>>>(d_levels, l, src_pitch, src_rows, frame_base);
     return cudaGetLastError();
 }
 
-cudaError_t launch_blur(const LevelDev *d_levels, const LevelDev *h_levels, int n_levels, int n_frames,
-                        cudaStream_t st) {
+cudaError_t launch_blur(const LevelDev *d_levels, const LevelDev *h_levels, int n_levels, int frame_base,
+                        int n_frames, cudaStream_t st) {
     BlurIndex bi;
     bi.first[0] = 0;
     for (int l = 0; l < n_levels; ++l)
         bi.first[l + 1] = bi.first[l] + ((h_levels[l].h + BLUR_R - 1) / BLUR_R) * ((h_levels[l].w + 3) >> 2);
     for (int l = n_levels + 1; l <= ORBB_MAX_LEVELS; ++l) bi.first[l] = bi.first[n_levels];
     dim3 grid((bi.first[n_levels] + 127) / 128, n_frames);
-    k_blur<<<grid, 128, 0, st>>>(d_levels, n_levels, bi);
+    k_blur<<<grid, 128, 0, st>>>(d_levels, n_levels, bi, frame_base);
     return cudaGetLastError();
 }
 

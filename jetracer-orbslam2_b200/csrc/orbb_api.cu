@@ -13,23 +13,25 @@
 #include "orbb_internal.cuh"
 
 namespace orbb {
-cudaError_t launch_level0(const uint8_t *, size_t, size_t, const LevelDev &, int, cudaStream_t);
-cudaError_t launch_resize(const LevelDev *, const LevelDev *, int, int, cudaStream_t);
-cudaError_t launch_blur(const LevelDev *, const LevelDev *, int, int, cudaStream_t);
-cudaError_t launch_fast(const LevelDev *, const CellEntry *, int, int, int *, int, int, const FastSmemCfg &, int,
+cudaError_t launch_level0(const uint8_t *, size_t, size_t, const LevelDev &, int, int, cudaStream_t);
+cudaError_t launch_resize(const LevelDev *, const LevelDev *, int, int, int, cudaStream_t);
+cudaError_t launch_blur(const LevelDev *, const LevelDev *, int, int, int, cudaStream_t);
+cudaError_t launch_fast(const LevelDev *, const CellEntry *, int, int, int *, int, int, const FastSmemCfg &, int, int,
                         cudaStream_t);
 cudaError_t launch_fast_dump(const LevelDev *, const CellEntry *, int, int, int, int, const FastSmemCfg &, int,
                              uint8_t *, const long long *, cudaStream_t);
 cudaError_t launch_octree(const LevelDev *, int, const int *, int *, int, int, int, int, int, int, int, int,
                           cudaStream_t);
 size_t octree_dyn_smem(int, int, int);
-cudaError_t launch_angle_orb(const LevelDev *, int, const int *, const int8_t *, const int *, const int *, int, int,
+cudaError_t launch_angle_orb(const LevelDev *, int, const int *, const int8_t *, const int *, const int *, int, int, int,
                              orbb_keypoint *, uint8_t *, int *, int, cudaStream_t);
 cudaError_t launch_match(const uint8_t *, const uint8_t *, const int *, const int *, int, int, int, int, int, int4 *,
                          int, int, float, int *, int *, uint8_t *, int *, cudaStream_t);
 }  // namespace orbb
 
 using namespace orbb;
+
+#define ORBB_MAX_CHUNKS 16  // pipeline depth of orbb_extract_batch_host
 
 static const int8_t k_pattern_host[1024] = {
 #include "../../include/orb_pattern_31.inc"
@@ -61,6 +63,10 @@ struct orbb_handle {
     long long *d_dump_off = nullptr;
     std::vector<long long> dump_off;
     int n_frames_last = 0;
+    cudaStream_t s_in = nullptr, s_out = nullptr;  // copy streams of the pipelined *_host entry point
+    cudaStream_t s_comp[2] = {nullptr, nullptr};   // alternating compute streams (chunk tails overlap)
+    cudaEvent_t ev_fence = nullptr, ev_done[2] = {nullptr, nullptr};
+    std::vector<cudaEvent_t> ev_in, ev_comp;
     std::vector<void *> allocs;
     char cuda_err[256] = {0};
 };
@@ -120,6 +126,15 @@ extern "C" int orbb_destroy(orbb_handle *h) {
     if (!h) return ORBB_OK;
     cudaSetDevice(h->device);
     for (void *p : h->allocs) cudaFree(p);
+    for (cudaEvent_t e : h->ev_in) cudaEventDestroy(e);
+    for (cudaEvent_t e : h->ev_comp) cudaEventDestroy(e);
+    if (h->s_in) cudaStreamDestroy(h->s_in);
+    if (h->s_out) cudaStreamDestroy(h->s_out);
+    for (int i = 0; i < 2; ++i) {
+        if (h->s_comp[i]) cudaStreamDestroy(h->s_comp[i]);
+        if (h->ev_done[i]) cudaEventDestroy(h->ev_done[i]);
+    }
+    if (h->ev_fence) cudaEventDestroy(h->ev_fence);
     delete h;
     return ORBB_OK;
 }
@@ -353,6 +368,18 @@ extern "C" int orbb_create(orbb_handle **out, const orbb_params *params, int wid
     CKC(dalloc(h, &h->d_desc, (size_t)h->max_kp * B * 32));
     CKC(dalloc(h, &h->d_counts, (size_t)B));
     CKC(dalloc(h, &h->d_dump, (size_t)dump_total));
+    CKC(cudaStreamCreateWithFlags(&h->s_in, cudaStreamNonBlocking));
+    CKC(cudaStreamCreateWithFlags(&h->s_out, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; ++i) {
+        CKC(cudaStreamCreateWithFlags(&h->s_comp[i], cudaStreamNonBlocking));
+        CKC(cudaEventCreateWithFlags(&h->ev_done[i], cudaEventDisableTiming));
+    }
+    CKC(cudaEventCreateWithFlags(&h->ev_fence, cudaEventDisableTiming));
+    h->ev_in.resize(ORBB_MAX_CHUNKS); h->ev_comp.resize(ORBB_MAX_CHUNKS);
+    for (int i = 0; i < ORBB_MAX_CHUNKS; ++i) {
+        CKC(cudaEventCreateWithFlags(&h->ev_in[i], cudaEventDisableTiming));
+        CKC(cudaEventCreateWithFlags(&h->ev_comp[i], cudaEventDisableTiming));
+    }
     CKC(cudaDeviceSynchronize());
 #undef CKC
     *out = h;
@@ -394,37 +421,69 @@ extern "C" int orbb_get_level(const orbb_handle *h, int frame, int level, orbb_l
 }
 
 // ---------------------------------------------------------------- stages
+// Every stage works on a frame range [f0, f0+n) of the resident batch so that the host entry point can
+// pipeline chunks; the public stage calls use the whole batch of the last upload.
+static int run_upload(orbb_handle *h, const uint8_t *d_images, size_t pitch, size_t stride, int f0, int n, cudaStream_t st) {
+    CK(h, cudaMemsetAsync(h->d_cand_count + (size_t)f0 * h->nlevels, 0, sizeof(int) * (size_t)n * h->nlevels, st));
+    CK(h, launch_level0(d_images, pitch, stride, h->lv[0], f0, n, st));
+    return ORBB_OK;
+}
+static int run_pyramid(orbb_handle *h, int f0, int n, cudaStream_t st) {
+    for (int l = 1; l < h->nlevels; ++l) CK(h, launch_resize(h->d_levels, h->lv, l, f0, n, st));
+    return ORBB_OK;
+}
+static int run_fast(orbb_handle *h, int f0, int n, cudaStream_t st) {
+    CK(h, launch_fast(h->d_levels, h->d_cells, h->n_cells, h->nlevels, h->d_cand_count, h->t_lo, h->t_hi, h->fcfg, f0, n, st));
+    return ORBB_OK;
+}
+static int run_distribute(orbb_handle *h, int f0, int n, cudaStream_t st) {
+    CK(h, launch_octree(h->d_levels, h->nlevels, h->d_cand_count, h->d_sel_count, 0, h->nlevels, f0, n, -1,
+                        h->sel_cap_max, h->pcap, h->pcap2, st));
+    return ORBB_OK;
+}
+static int run_blur(orbb_handle *h, int f0, int n, cudaStream_t st) {
+    CK(h, launch_blur(h->d_levels, h->lv, h->nlevels, f0, n, st));
+    return ORBB_OK;
+}
+static int run_angle_orb(orbb_handle *h, int f0, int n, orbb_keypoint *d_kp, uint8_t *d_desc, int32_t *d_counts, int max_kp,
+                         cudaStream_t st) {
+    CK(h, launch_angle_orb(h->d_levels, h->nlevels, h->d_sel_count, h->d_pattern, h->d_slot_level, h->d_slot_base,
+                           h->n_slots, f0, n, d_kp, d_desc, d_counts, max_kp, st));
+    return ORBB_OK;
+}
+static int run_all(orbb_handle *h, const uint8_t *d_images, size_t pitch, size_t stride, int f0, int n, orbb_keypoint *d_kp,
+                   uint8_t *d_desc, int32_t *d_counts, int max_kp, cudaStream_t st) {
+    int rc;
+    if ((rc = run_upload(h, d_images, pitch, stride, f0, n, st))) return rc;
+    if ((rc = run_pyramid(h, f0, n, st))) return rc;
+    if ((rc = run_fast(h, f0, n, st))) return rc;
+    if ((rc = run_distribute(h, f0, n, st))) return rc;
+    if ((rc = run_blur(h, f0, n, st))) return rc;
+    return run_angle_orb(h, f0, n, d_kp, d_desc, d_counts, max_kp, st);
+}
+
 extern "C" int orbb_stage_upload(orbb_handle *h, const uint8_t *d_images, size_t pitch, size_t frame_stride,
                                  int n_frames, void *stream) {
     if (!h || !d_images || n_frames < 1 || pitch < (size_t)h->w) return ORBB_ERR_INVALID;
     if (n_frames > h->max_batch) return ORBB_ERR_CAPACITY;
-    cudaStream_t st = static_cast<cudaStream_t>(stream);
     CK(h, cudaSetDevice(h->device));
     h->n_frames_last = n_frames;
-    CK(h, cudaMemsetAsync(h->d_cand_count, 0, sizeof(int) * (size_t)n_frames * h->nlevels, st));
-    CK(h, launch_level0(d_images, pitch, frame_stride, h->lv[0], n_frames, st));
-    return ORBB_OK;
+    return run_upload(h, d_images, pitch, frame_stride, 0, n_frames, static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int orbb_pyramid_create_levels(orbb_handle *h, void *stream) {
     if (!h || h->n_frames_last < 1) return ORBB_ERR_INVALID;
-    cudaStream_t st = static_cast<cudaStream_t>(stream);
-    for (int l = 1; l < h->nlevels; ++l) CK(h, launch_resize(h->d_levels, h->lv, l, h->n_frames_last, st));
-    return ORBB_OK;
+    return run_pyramid(h, 0, h->n_frames_last, static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int orbb_detect_fast(orbb_handle *h, void *stream) {
     if (!h || h->n_frames_last < 1) return ORBB_ERR_INVALID;
-    CK(h, launch_fast(h->d_levels, h->d_cells, h->n_cells, h->nlevels, h->d_cand_count, h->t_lo, h->t_hi, h->fcfg,
-                      h->n_frames_last, static_cast<cudaStream_t>(stream)));
-    return ORBB_OK;
+    return run_fast(h, 0, h->n_frames_last, static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int orbb_detect_distribute(orbb_handle *h, void *stream) {
     if (!h || h->n_frames_last < 1) return ORBB_ERR_INVALID;
-    CK(h, launch_octree(h->d_levels, h->nlevels, h->d_cand_count, h->d_sel_count, 0, h->nlevels, 0, h->n_frames_last,
-                        -1, h->sel_cap_max, h->pcap, h->pcap2, static_cast<cudaStream_t>(stream)));
-    return ORBB_OK;
+    return run_distribute(h, 0, h->n_frames_last, static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int orbb_detect(orbb_handle *h, void *stream) {
@@ -434,56 +493,79 @@ extern "C" int orbb_detect(orbb_handle *h, void *stream) {
 
 extern "C" int orbb_gaussian_blur(orbb_handle *h, void *stream) {
     if (!h || h->n_frames_last < 1) return ORBB_ERR_INVALID;
-    CK(h, launch_blur(h->d_levels, h->lv, h->nlevels, h->n_frames_last, static_cast<cudaStream_t>(stream)));
-    return ORBB_OK;
+    return run_blur(h, 0, h->n_frames_last, static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int orbb_compute_angle_and_orb(orbb_handle *h, orbb_keypoint *d_kp, uint8_t *d_desc, int32_t *d_counts,
                                           int max_kp, void *stream) {
     if (!h || !d_kp || !d_desc || !d_counts || max_kp < 1 || h->n_frames_last < 1) return ORBB_ERR_INVALID;
-    CK(h, launch_angle_orb(h->d_levels, h->nlevels, h->d_sel_count, h->d_pattern, h->d_slot_level, h->d_slot_base,
-                           h->n_slots, h->n_frames_last, d_kp, d_desc, d_counts, max_kp,
-                           static_cast<cudaStream_t>(stream)));
-    return ORBB_OK;
+    return run_angle_orb(h, 0, h->n_frames_last, d_kp, d_desc, d_counts, max_kp, static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int orbb_extract_batch_device(orbb_handle *h, const uint8_t *d_images, size_t pitch, size_t frame_stride,
                                          int n_frames, orbb_keypoint *d_kp, uint8_t *d_desc, int32_t *d_counts,
                                          int max_kp, void *stream) {
-    int rc = orbb_stage_upload(h, d_images, pitch, frame_stride, n_frames, stream);
-    if (rc) return rc;
-    if ((rc = orbb_pyramid_create_levels(h, stream))) return rc;
-    if ((rc = orbb_detect(h, stream))) return rc;
-    if ((rc = orbb_gaussian_blur(h, stream))) return rc;
-    return orbb_compute_angle_and_orb(h, d_kp, d_desc, d_counts, max_kp, stream);
+    if (!h || !d_images || !d_kp || !d_desc || !d_counts || max_kp < 1 || n_frames < 1 || pitch < (size_t)h->w)
+        return ORBB_ERR_INVALID;
+    if (n_frames > h->max_batch) return ORBB_ERR_CAPACITY;
+    CK(h, cudaSetDevice(h->device));
+    h->n_frames_last = n_frames;
+    return run_all(h, d_images, pitch, frame_stride, 0, n_frames, d_kp, d_desc, d_counts, max_kp,
+                   static_cast<cudaStream_t>(stream));
 }
 
+// Host entry point: chunks of the batch flow through three streams (H2D copy stream -> caller's compute stream
+// -> D2H copy stream) linked by events, so PCIe transfers of chunk c+1 / c-1 overlap the kernels of chunk c.
 extern "C" int orbb_extract_batch_host(orbb_handle *h, const uint8_t *h_images, size_t pitch, size_t frame_stride,
                                        int n_frames, orbb_keypoint *h_kp, uint8_t *h_desc, int32_t *h_counts,
                                        int max_kp, void *stream) {
-    if (!h || !h_images || !h_kp || !h_desc || !h_counts || max_kp < 1) return ORBB_ERR_INVALID;
+    if (!h || !h_images || !h_kp || !h_desc || !h_counts || max_kp < 1 || pitch < (size_t)h->w) return ORBB_ERR_INVALID;
     if (n_frames < 1 || n_frames > h->max_batch) return ORBB_ERR_CAPACITY;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     CK(h, cudaSetDevice(h->device));
+    h->n_frames_last = n_frames;
     const size_t fw = (size_t)h->w, fsz = fw * h->h;
-    if (pitch == fw && frame_stride == fsz) {
-        CK(h, cudaMemcpyAsync(h->d_in, h_images, fsz * n_frames, cudaMemcpyHostToDevice, st));
-    } else if (frame_stride == pitch * (size_t)h->h) {
-        CK(h, cudaMemcpy2DAsync(h->d_in, fw, h_images, pitch, fw, (size_t)h->h * n_frames, cudaMemcpyHostToDevice, st));
-    } else {
-        for (int f = 0; f < n_frames; ++f)
-            CK(h, cudaMemcpy2DAsync(h->d_in + fsz * f, fw, h_images + frame_stride * f, pitch, fw, h->h,
-                                    cudaMemcpyHostToDevice, st));
-    }
     const int mk = std::min(max_kp, h->max_kp);
-    int rc = orbb_extract_batch_device(h, h->d_in, fw, fsz, n_frames, h->d_kp, h->d_desc, h->d_counts, mk, stream);
-    if (rc) return rc;
-    CK(h, cudaMemcpyAsync(h_counts, h->d_counts, sizeof(int) * n_frames, cudaMemcpyDeviceToHost, st));
-    CK(h, cudaMemcpy2DAsync(h_kp, sizeof(orbb_keypoint) * max_kp, h->d_kp, sizeof(orbb_keypoint) * mk,
-                            sizeof(orbb_keypoint) * mk, n_frames, cudaMemcpyDeviceToHost, st));
-    CK(h, cudaMemcpy2DAsync(h_desc, 32 * (size_t)max_kp, h->d_desc, 32 * (size_t)mk, 32 * (size_t)mk, n_frames,
-                            cudaMemcpyDeviceToHost, st));
-    CK(h, cudaStreamSynchronize(st));
+    // everything already queued on the caller's stream happens-before the pipeline
+    CK(h, cudaEventRecord(h->ev_fence, st));
+    CK(h, cudaStreamWaitEvent(h->s_in, h->ev_fence, 0));
+    CK(h, cudaStreamWaitEvent(h->s_comp[0], h->ev_fence, 0));
+    CK(h, cudaStreamWaitEvent(h->s_comp[1], h->ev_fence, 0));
+    // chunk sizes grow 16, 32, 64, 64, ...: the first H2D (which nothing can hide) stays short
+    int per = n_frames <= 32 ? n_frames : 16;
+    for (int c = 0, f0 = 0; f0 < n_frames; ++c) {
+        int n = std::min(per, n_frames - f0);
+        if (c == ORBB_MAX_CHUNKS - 1) n = n_frames - f0;
+        cudaStream_t sc = h->s_comp[c & 1];
+        uint8_t *din = h->d_in + fsz * f0;
+        const uint8_t *src = h_images + frame_stride * f0;
+        if (pitch == fw && frame_stride == fsz) {
+            CK(h, cudaMemcpyAsync(din, src, fsz * n, cudaMemcpyHostToDevice, h->s_in));
+        } else if (frame_stride == pitch * (size_t)h->h) {
+            CK(h, cudaMemcpy2DAsync(din, fw, src, pitch, fw, (size_t)h->h * n, cudaMemcpyHostToDevice, h->s_in));
+        } else {
+            for (int f = 0; f < n; ++f)
+                CK(h, cudaMemcpy2DAsync(din + fsz * f, fw, src + frame_stride * f, pitch, fw, h->h, cudaMemcpyHostToDevice,
+                                        h->s_in));
+        }
+        CK(h, cudaEventRecord(h->ev_in[c], h->s_in));
+        CK(h, cudaStreamWaitEvent(sc, h->ev_in[c], 0));
+        int rc = run_all(h, din, fw, fsz, f0, n, h->d_kp, h->d_desc, h->d_counts, mk, sc);
+        if (rc) return rc;
+        CK(h, cudaEventRecord(h->ev_comp[c], sc));
+        CK(h, cudaStreamWaitEvent(h->s_out, h->ev_comp[c], 0));
+        CK(h, cudaMemcpyAsync(h_counts + f0, h->d_counts + f0, sizeof(int) * n, cudaMemcpyDeviceToHost, h->s_out));
+        CK(h, cudaMemcpy2DAsync(h_kp + (size_t)f0 * max_kp, sizeof(orbb_keypoint) * max_kp, h->d_kp + (size_t)f0 * mk,
+                                sizeof(orbb_keypoint) * mk, sizeof(orbb_keypoint) * mk, n, cudaMemcpyDeviceToHost, h->s_out));
+        CK(h, cudaMemcpy2DAsync(h_desc + 32 * (size_t)f0 * max_kp, 32 * (size_t)max_kp, h->d_desc + 32 * (size_t)f0 * mk,
+                                32 * (size_t)mk, 32 * (size_t)mk, n, cudaMemcpyDeviceToHost, h->s_out));
+        f0 += n;
+        per = std::min(per * 2, 64);
+    }
+    // the caller's stream observes completion too (later work queued on it is ordered after the batch)
+    CK(h, cudaEventRecord(h->ev_done[0], h->s_out));
+    CK(h, cudaStreamWaitEvent(st, h->ev_done[0], 0));
+    CK(h, cudaStreamSynchronize(h->s_out));
     return ORBB_OK;
 }
 
