@@ -6,9 +6,11 @@
 // Work item = one upstream 30-px cell, processed by ONE WARP with warp-synchronous code only (no
 // block barriers): the cell's (cw+6)x(ch+6) window is staged in shared memory with aligned 32-bit
 // loads, then
-//   phase 1  antipodal-pair precheck at the low threshold, ballot-compacted into a queue,
-//   phase 2  exact threshold-free arc score m = max over 9-arcs of min|d| (3-input min/max network,
-//            VIMNMX3), corners (m > t_lo) written to a score tile and re-compacted,
+//   phase 1  packed antipodal-pair precheck (4 pixels per lane, VABSDIFF4 + SWAR compare), ballot-compacted
+//            into a queue of pixel indices,
+//   phase 2  exact threshold-free arc score m = max over 9-arcs of min|d|: both polarities packed in
+//            s16x2 (one IMAD per ring pixel), 3-input min/max network (VIMNMX3.U16x2); corners (m > thr)
+//            written to a score tile and re-compacted,
 //   phase 3  3x3 strict NMS inside the cell (the score tile has a zero frame: neighbours outside the
 //            cell's tested range count as 0, exactly like cv::FAST on the cell window),
 //   phase 4  survivors are appended to the (frame, level) candidate list, one atomicAdd per 32.
@@ -26,30 +28,31 @@ __device__ __forceinline__ int min3(int a, int b, int c) { return __vimin3_s32(a
 __device__ __forceinline__ int max3(int a, int b, int c) { return __vimax3_s32(a, b, c); }
 
 // m = max(A, B), A = max over the 16 9-arcs of min(v - ring), B = same for (ring - v).
+// Both chains run at once in packed s16x2: P_k = (v - r_k + 256) | ((r_k - v + 256) << 16), which is a single
+// IMAD per ring pixel, P_k = base + r_k * 0xFFFF with base = (v + 256) | ((256 - v) << 16): both halves stay in
+// [1, 511], so no borrow crosses the halves.  Then min over 9 = two layers of 3-input min (VIMNMX3.U16x2) and
+// the max over the 16 arcs is a 3-input max tree: 40 min/max instructions for both polarities.
 __device__ __forceinline__ int arc_score(const uint8_t *p, int tp) {
-    const int v = p[0];
-    int d[16];
-    d[0] = v - p[3 * tp];       d[1] = v - p[3 * tp + 1];   d[2] = v - p[2 * tp + 2];   d[3] = v - p[tp + 3];
-    d[4] = v - p[3];            d[5] = v - p[-tp + 3];      d[6] = v - p[-2 * tp + 2];  d[7] = v - p[-3 * tp + 1];
-    d[8] = v - p[-3 * tp];      d[9] = v - p[-3 * tp - 1];  d[10] = v - p[-2 * tp - 2]; d[11] = v - p[-tp - 3];
-    d[12] = v - p[-3];          d[13] = v - p[tp - 3];      d[14] = v - p[2 * tp - 2];  d[15] = v - p[3 * tp - 1];
-    int lo3[16], hi3[16];
+    const unsigned v = p[0];
+    const unsigned base = (v + 256u) | ((256u - v) << 16);
+    unsigned d[16];
+#define RING(k, off) d[k] = base + (unsigned)p[off] * 0xFFFFu
+    RING(0, 3 * tp);       RING(1, 3 * tp + 1);   RING(2, 2 * tp + 2);    RING(3, tp + 3);
+    RING(4, 3);            RING(5, -tp + 3);      RING(6, -2 * tp + 2);   RING(7, -3 * tp + 1);
+    RING(8, -3 * tp);      RING(9, -3 * tp - 1);  RING(10, -2 * tp - 2);  RING(11, -tp - 3);
+    RING(12, -3);          RING(13, tp - 3);      RING(14, 2 * tp - 2);   RING(15, 3 * tp - 1);
+#undef RING
+    unsigned lo3[16];
 #pragma unroll
-    for (int k = 0; k < 16; ++k) {
-        lo3[k] = min3(d[k], d[(k + 1) & 15], d[(k + 2) & 15]);
-        hi3[k] = max3(d[k], d[(k + 1) & 15], d[(k + 2) & 15]);
-    }
-    int a = -256, b = 256;
+    for (int k = 0; k < 16; ++k) lo3[k] = __vimin3_u16x2(d[k], d[(k + 1) & 15], d[(k + 2) & 15]);
+    unsigned best = 0;
 #pragma unroll
     for (int k = 0; k < 16; k += 2) {
-        const int l0 = min3(lo3[k], lo3[(k + 3) & 15], lo3[(k + 6) & 15]);
-        const int l1 = min3(lo3[k + 1], lo3[(k + 4) & 15], lo3[(k + 7) & 15]);
-        a = max3(a, l0, l1);
-        const int h0 = max3(hi3[k], hi3[(k + 3) & 15], hi3[(k + 6) & 15]);
-        const int h1 = max3(hi3[k + 1], hi3[(k + 4) & 15], hi3[(k + 7) & 15]);
-        b = min3(b, h0, h1);
+        const unsigned l0 = __vimin3_u16x2(lo3[k], lo3[(k + 3) & 15], lo3[(k + 6) & 15]);
+        const unsigned l1 = __vimin3_u16x2(lo3[k + 1], lo3[(k + 4) & 15], lo3[(k + 7) & 15]);
+        best = __vimax3_u16x2(best, l0, l1);
     }
-    return max(a, -b);
+    return (int)max(best & 0xffffu, best >> 16) - 256;
 }
 
 template <bool DUMP>
@@ -68,21 +71,38 @@ k_fast_cells(const LevelDev *__restrict__ levels, const CellEntry *__restrict__ 
     uint8_t *tile = smem + (size_t)warp * cfg.warp_bytes;
     uint8_t *score = tile + cfg.tile_pitch * cfg.tile_rows;
     uint16_t *queue = reinterpret_cast<uint16_t *>(score + cfg.score_pitch * cfg.score_rows);
-    const int tp = cfg.tile_pitch, sp = cfg.score_pitch;
+    const int tp = cfg.tile_pitch, sp = cfg.score_pitch, tpw = tp >> 2;
     const int cw = c.cw, ch = c.ch;
+    const uint32_t *tile32 = reinterpret_cast<const uint32_t *>(tile);
 
-    // ---- stage the window: rows y0-3 .. y0+ch+2, columns from the 4-aligned address at/below x0-3
-    const int xa = (c.x0 - 3) & ~3, off = (c.x0 - 3) - xa;
-    const int nwords = (off + cw + 6 + 3) >> 2;
+    // ---- stage the window, RE-ALIGNED: shared-memory byte column k <-> image column x0 - 4 + k, so the
+    // cell's first tested pixel sits at byte 4 of each row and groups of 4 pixels are whole 32-bit words.
+    // Global loads stay aligned (ROI rows are 16-byte aligned); a funnel shift moves the bytes into place.
+    const int off = 4;  // tested pixel x lives at tile byte column x + off
     {
+        const int gx = c.x0 - 4, xa = gx & ~3, sh = (gx - xa) * 8;
+        const int nwords = (cw + 7 + 3) >> 2;
         const uint8_t *roi = L.img + (size_t)frame * L.frame_stride + (size_t)ORBB_BORDER * L.pitch + ORBB_ROI_X0;
         const int rpi = 32 / nwords;  // rows per iteration (nwords <= 32 guaranteed by the host)
         const int lr = lane / nwords, lw = lane - lr * nwords;
         const uint8_t *src = roi + (ptrdiff_t)(c.y0 - 3) * L.pitch + xa + 4 * lw;
-        for (int r = lr; r < ch + 6; r += rpi)
-            if (lr < rpi)
-                reinterpret_cast<uint32_t *>(tile + r * tp)[lw] =
-                    *reinterpret_cast<const uint32_t *>(src + (ptrdiff_t)r * L.pitch);
+        if (lr < rpi) {
+            const int nrows = ch + 6;
+            for (int r0 = lr; r0 < nrows; r0 += 4 * rpi) {  // 4 rows (8 loads) in flight per lane
+                uint32_t ga[4], gb[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const int r = min(r0 + k * rpi, nrows - 1);
+                    const uint32_t *g = reinterpret_cast<const uint32_t *>(src + (ptrdiff_t)r * L.pitch);
+                    ga[k] = g[0]; gb[k] = g[1];
+                }
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const int r = r0 + k * rpi;
+                    if (r < nrows) reinterpret_cast<uint32_t *>(tile + r * tp)[lw] = __funnelshift_r(ga[k], gb[k], sh);
+                }
+            }
+        }
         for (int i = lane; i < (sp * cfg.score_rows) >> 2; i += 32) reinterpret_cast<uint32_t *>(score)[i] = 0;
     }
     __syncwarp();
@@ -90,6 +110,8 @@ k_fast_cells(const LevelDev *__restrict__ levels, const CellEntry *__restrict__ 
     const int npix = cw * ch;
     const unsigned inv_cw = (1u << 20) / (unsigned)cw + 1u;  // exact floor(idx/cw) for idx*cw < 2^20
     const unsigned lt_mask = (1u << lane) - 1u;
+    const int nux = (cw + 3) >> 2, nunits = nux * ch;        // 4-pixel units per row / per cell
+    const unsigned inv_nux = (1u << 20) / (unsigned)nux + 1u;
 
     // Upstream order: FAST(ini) on the cell; only if that leaves nothing, FAST(min).  Running the high
     // threshold first rejects most pixels in the precheck (the low-threshold pass is rare on textured input).
@@ -97,23 +119,36 @@ k_fast_cells(const LevelDev *__restrict__ levels, const CellEntry *__restrict__ 
     for (int pass = DUMP ? 1 : 0; pass < 2; ++pass) {
         const int thr = pass == 0 ? t_hi : t_lo;
         if (pass == 1 && !DUMP && t_lo == t_hi) break;
-        // ---- phase 1: antipodal-pair precheck (any 9-arc holds one pixel of every antipodal pair)
+        // ---- phase 1: packed precheck, 4 pixels per lane.  Necessary condition for a 9-arc: every antipodal
+        // pair holds a pixel with |d| > thr; tested on the pairs (0,8) and (4,12) with VABSDIFF4 and a
+        // carry-free SWAR compare on |d|>>1 (a superset of |d| > thr -- exactness comes from phase 2).
+        const unsigned kadd = (unsigned)(128 - ((thr + 1) >> 1)) * 0x01010101u;
         int qn = 0;
-        for (int base = 0; base < npix; base += 32) {
-            const int idx = base + lane;
-            bool ok = false;
-            if (idx < npix) {
-                const int y = (int)(((unsigned)idx * inv_cw) >> 20), x = idx - y * cw;
-                const uint8_t *p = tile + (y + 3) * tp + x + 3 + off;
-                const int v = p[0], lo = v - thr, hi = v + thr;
-                const int r0 = p[3 * tp], r8 = p[-3 * tp], r4 = p[3], r12 = p[-3];
-                const bool dark = ((r0 < lo) | (r8 < lo)) & ((r4 < lo) | (r12 < lo));
-                const bool bright = ((r0 > hi) | (r8 > hi)) & ((r4 > hi) | (r12 > hi));
-                ok = dark | bright;
+        for (int base = 0; base < nunits; base += 32) {
+            const int u = base + lane;
+            unsigned flags = 0;
+            int pix0 = 0;
+            if (u < nunits) {
+                const int y = (int)(((unsigned)u * inv_nux) >> 20), j = u - y * nux;
+                const uint32_t *row = tile32 + (y + 3) * tpw + j;  // row[0]=left word, row[1]=centre, row[2]=right
+                const unsigned cc = row[1];
+                const unsigned a0 = __vabsdiffu4(row[1 + 3 * tpw], cc), a8 = __vabsdiffu4(row[1 - 3 * tpw], cc);
+                const unsigned a4 = __vabsdiffu4(__funnelshift_r(cc, row[2], 24), cc);
+                const unsigned a12 = __vabsdiffu4(__funnelshift_r(row[0], cc, 8), cc);
+                const unsigned x0 = ((a0 >> 1) & 0x7f7f7f7fu) + kadd, x8 = ((a8 >> 1) & 0x7f7f7f7fu) + kadd;
+                const unsigned x4 = ((a4 >> 1) & 0x7f7f7f7fu) + kadd, x12 = ((a12 >> 1) & 0x7f7f7f7fu) + kadd;
+                const int nvalid = cw - 4 * j;
+                const unsigned vmask = nvalid >= 4 ? 0x80808080u : (0x80808080u >> (8 * (4 - nvalid)));
+                flags = (x0 | x8) & (x4 | x12) & vmask;
+                pix0 = y * cw + 4 * j;
             }
-            const unsigned m = __ballot_sync(0xffffffffu, ok);
-            if (ok) queue[qn + __popc(m & lt_mask)] = (uint16_t)idx;
-            qn += __popc(m);
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+                const bool ok = (flags >> (8 * b + 7)) & 1u;
+                const unsigned m = __ballot_sync(0xffffffffu, ok);
+                if (ok) queue[qn + __popc(m & lt_mask)] = (uint16_t)(pix0 + b);
+                qn += __popc(m);
+            }
         }
         __syncwarp();
 
@@ -125,7 +160,7 @@ k_fast_cells(const LevelDev *__restrict__ levels, const CellEntry *__restrict__ 
             if (i < qn) {
                 idx = queue[i];
                 const int y = (int)(((unsigned)idx * inv_cw) >> 20), x = idx - y * cw;
-                m = arc_score(tile + (y + 3) * tp + x + 3 + off, tp);
+                m = arc_score(tile + (y + 3) * tp + x + off, tp);
                 m = m > thr ? m : 0;
                 if (m) score[(y + 1) * sp + x + 1] = (uint8_t)min(m, 255);
             }
