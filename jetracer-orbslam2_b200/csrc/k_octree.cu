@@ -48,13 +48,16 @@ __device__ __forceinline__ uint32_t block_excl_scan(uint32_t v, uint32_t *warp_t
     __syncthreads();  // protect warp_tot reuse
     if (lane == 31) warp_tot[warp] = inc;
     __syncthreads();
-    uint32_t base = 0, tot = 0;
+    // every warp scans the 16 warp totals with shuffles (lanes >= 16 carry zeros)
+    const uint32_t wt = lane < OCT_WARPS ? warp_tot[lane] : 0u;
+    uint32_t winc = wt;
 #pragma unroll
-    for (int w = 0; w < OCT_WARPS; ++w) {
-        const uint32_t t = warp_tot[w];
-        if (w < warp) base += t;
-        tot += t;
+    for (int o = 1; o < OCT_WARPS; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(FULL, winc, o);
+        if (lane >= o) winc += t;
     }
+    const uint32_t tot = __shfl_sync(FULL, winc, OCT_WARPS - 1);
+    const uint32_t base = __shfl_sync(FULL, winc - wt, warp);
     *total = tot;
     return base + inc - v;
 }

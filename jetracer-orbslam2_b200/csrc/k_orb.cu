@@ -77,22 +77,28 @@ k_angle_orb(const LevelDev *__restrict__ levels, int n_levels, const int *__rest
         const uint8_t *src = L.blur + (size_t)frame * L.blur_stride + (size_t)(y - PATCH_R) * L.pitch + xa;
         const int lr = lane >> 4, lw = lane & 15;  // 2 rows per warp instruction, 11 of 16 lanes active
         if (lw < 11) {
+            const uint8_t *g = src + (size_t)lr * L.pitch + 4 * lw;
+            const size_t step = 2 * (size_t)L.pitch;
+            uint32_t v[(PATCH_ROWS + 1) / 2];
 #pragma unroll
-            for (int r = 0; r < PATCH_ROWS + 1; r += 2)
-                if (r + lr < PATCH_ROWS)
-                    reinterpret_cast<uint32_t *>(patch + (r + lr) * PATCH_PITCH)[lw] =
-                        *reinterpret_cast<const uint32_t *>(src + (size_t)(r + lr) * L.pitch + 4 * lw);
+            for (int r = 0; r < (PATCH_ROWS + 1) / 2; ++r)  // all 20 loads in flight before the first store
+                v[r] = (2 * r + lr < PATCH_ROWS) ? *reinterpret_cast<const uint32_t *>(g + r * step) : 0u;
+#pragma unroll
+            for (int r = 0; r < (PATCH_ROWS + 1) / 2; ++r)
+                if (2 * r + lr < PATCH_ROWS) reinterpret_cast<uint32_t *>(patch + (2 * r + lr) * PATCH_PITCH)[lw] = v[r];
         }
     }
 
     // ---- IC_Angle: lane = column u (coalesced row reads), rows unrolled with their compile-time umax
-    const uint8_t *center = L.img + (size_t)frame * L.frame_stride + (size_t)(y + ORBB_BORDER) * L.pitch + ORBB_ROI_X0 + x;
     const int u = lane - 15, au = u < 0 ? -u : u;
+    const int pitch = L.pitch;
+    const uint8_t *rowp = L.img + (size_t)frame * L.frame_stride + (size_t)(y + ORBB_BORDER - 15) * pitch + ORBB_ROI_X0 + x + u;
     int colsum = 0, m01 = 0;
 #pragma unroll
     for (int v = -15; v <= 15; ++v) {
         const int d = umax_of(v < 0 ? -v : v);
-        const int val = (au <= d) ? (int)center[(ptrdiff_t)v * L.pitch + u] : 0;  // lane 31 has au = 16 > d
+        const int val = (au <= d) ? (int)*rowp : 0;  // lane 31 has au = 16 > d
+        rowp += pitch;
         colsum += val;
         m01 += v * val;
     }

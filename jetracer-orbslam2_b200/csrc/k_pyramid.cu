@@ -19,28 +19,33 @@ __device__ __forceinline__ int reflect101(int p, int len) {
     return p >= len ? 2 * len - 2 - p : p;
 }
 
-// ---- level 0: copy the caller's frames into the padded layout + border
-__global__ void __launch_bounds__(128) k_level0(const uint8_t *__restrict__ in, size_t in_pitch,
-                                                size_t in_stride, LevelDev L, int aligned4, int frame_base) {
-    const int word = blockIdx.x * blockDim.x + threadIdx.x;
-    const int py = blockIdx.y, frame = blockIdx.z + frame_base;
-    if (word * 4 >= L.pitch) return;
+// ---- level 0: copy the caller's frames into the padded layout + border.
+// thread = one 16-byte chunk of a padded row (ROI rows are 16-byte aligned by layout): interior chunks are one
+// 128-bit load + one 128-bit store, edge chunks are assembled bytewise through the reflect-101 map.
+__global__ void __launch_bounds__(256) k_level0(const uint8_t *__restrict__ in, size_t in_pitch, size_t in_stride,
+                                                LevelDev L, int aligned16, int frame_base) {
+    const int cpr = L.pitch >> 4;  // 16-byte chunks per row (pitch is a multiple of 128)
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= cpr * L.rows) return;
+    const int py = i / cpr, chunk = i - py * cpr;
+    const int frame = blockIdx.y + frame_base;
     const int y = reflect101(py - ORBB_BORDER, L.h);
-    const uint8_t *src = in + (size_t)blockIdx.z * in_stride + (size_t)y * in_pitch;
-    const int b0 = word * 4;
-    uint32_t out = 0;
-    const int x0 = b0 - ORBB_ROI_X0;
-    if (aligned4 && x0 >= 0 && x0 + 3 < L.w) {
-        out = *reinterpret_cast<const uint32_t *>(src + x0);
+    const uint8_t *src = in + (size_t)blockIdx.y * in_stride + (size_t)y * in_pitch;
+    const int b0 = chunk * 16, x0 = b0 - ORBB_ROI_X0;
+    uint4 out;
+    if (aligned16 && x0 >= 0 && x0 + 15 < L.w) {
+        out = *reinterpret_cast<const uint4 *>(src + x0);
     } else {
+        uint32_t wv[4] = {0, 0, 0, 0};
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
+        for (int k = 0; k < 16; ++k) {
             const int px = b0 + k - ORBB_PAD_X0;
             if (px >= 0 && px < L.w + 2 * ORBB_BORDER)
-                out |= (uint32_t)src[reflect101(px - ORBB_BORDER, L.w)] << (8 * k);
+                wv[k >> 2] |= (uint32_t)src[reflect101(px - ORBB_BORDER, L.w)] << (8 * (k & 3));
         }
+        out = make_uint4(wv[0], wv[1], wv[2], wv[3]);
     }
-    *reinterpret_cast<uint32_t *>(L.img + (size_t)frame * L.frame_stride + (size_t)py * L.pitch + b0) = out;
+    *reinterpret_cast<uint4 *>(L.img + (size_t)frame * L.frame_stride + (size_t)py * L.pitch + b0) = out;
 }
 
 // ---- level l from level l-1: tiled two-phase bilinear resize (cv::resize INTER_LINEAR, 8U).
@@ -59,6 +64,7 @@ __global__ void __launch_bounds__(RS_THREADS) k_resize(const LevelDev *__restric
                                                        int src_rows_max, int frame_base) {
     extern __shared__ __align__(16) uint8_t rs_smem[];
     __shared__ int s_red[8];
+    __shared__ int4 s_rowtab[RS_TH];  // per dst row of the tile: (src row0, src row1, b0, b1)
     const LevelDev &L = levels[l];
     const LevelDev &S = levels[l - 1];
     uint8_t *s_src = rs_smem;                                                         // [src_rows_max][src_pitch]
@@ -83,10 +89,19 @@ __global__ void __launch_bounds__(RS_THREADS) k_resize(const LevelDev *__restric
     }
     // per-row source rows (threads 0..RS_TH-1 each own one dst row of the tile)
     int r0 = 0x7fffffff, r1 = -1;
-    if (tid < RS_TH && py0 + tid < ph) {
-        const int ry = reflect101(py0 + tid - ORBB_BORDER, L.h);
-        if (area) { r0 = 2 * ry; r1 = r0 + 1; }
-        else { const int2 yr = __ldg(&L.yrows[ry]); r0 = yr.x; r1 = yr.y; }
+    if (tid < RS_TH) {
+        int4 rt = make_int4(0, 0, 0, 0);
+        if (py0 + tid < ph) {
+            const int ry = reflect101(py0 + tid - ORBB_BORDER, L.h);
+            if (area) { r0 = 2 * ry; r1 = r0 + 1; }
+            else {
+                const int2 yr = __ldg(&L.yrows[ry]);
+                const short2 bw = __ldg(&L.ybeta[ry]);
+                r0 = yr.x; r1 = yr.y; rt.z = bw.x; rt.w = bw.y;
+            }
+            rt.x = r0; rt.y = r1;
+        }
+        s_rowtab[tid] = rt;
     }
     // block-wide extents of the source window
     int cmin = __reduce_min_sync(0xffffffffu, sx), cmax = __reduce_max_sync(0xffffffffu, sx1);
@@ -104,18 +119,27 @@ __global__ void __launch_bounds__(RS_THREADS) k_resize(const LevelDev *__restric
 
     // stage the source window
     const uint8_t *sroi = S.img + (size_t)frame * S.frame_stride + (size_t)ORBB_BORDER * S.pitch + ORBB_ROI_X0;
-    for (int i = tid; i < nrows * nwords; i += RS_THREADS) {
-        const int r = i / nwords, wd = i - r * nwords;
-        reinterpret_cast<uint32_t *>(s_src + (size_t)r * src_pitch)[wd] =
-            *reinterpret_cast<const uint32_t *>(sroi + (size_t)(rmin + r) * S.pitch + sa + 4 * wd);
+    {
+        const unsigned inv_nw = (1u << 20) / (unsigned)nwords + 1u;  // exact i / nwords for i * nwords < 2^20
+        for (int i = tid; i < nrows * nwords; i += RS_THREADS) {
+            const int r = (int)(((unsigned)i * inv_nw) >> 20), wd = i - r * nwords;
+            reinterpret_cast<uint32_t *>(s_src + (size_t)r * src_pitch)[wd] =
+                *reinterpret_cast<const uint32_t *>(sroi + (size_t)(rmin + r) * S.pitch + sa + 4 * wd);
+        }
     }
     __syncthreads();
     // H phase
-    const int o0 = sx - sa, o1 = sx1 - sa;
-    for (int r = tid >> 6; r < nrows; r += RS_THREADS / RS_TW) {
-        const uint8_t *row = s_src + (size_t)r * src_pitch;
-        const int t = row[o0] * a0 + row[o1] * a1;
-        s_t[r * RS_TW + c] = (uint16_t)(area ? t : (t >> 4));
+    {
+        const uint8_t *p0 = s_src + (size_t)(tid >> 6) * src_pitch + (sx - sa);
+        const int d1 = sx1 - sx, step = (RS_THREADS / RS_TW) * src_pitch;
+        uint16_t *t = s_t + (tid >> 6) * RS_TW + c;
+        const int sh = area ? 0 : 4;
+#pragma unroll 4
+        for (int r = tid >> 6; r < nrows; r += RS_THREADS / RS_TW) {
+            *t = (uint16_t)((p0[0] * a0 + p0[d1] * a1) >> sh);
+            p0 += step;
+            t += (RS_THREADS / RS_TW) * RS_TW;
+        }
     }
     __syncthreads();
     // V phase: thread = (quad q of 4 columns, row group g)
@@ -126,14 +150,8 @@ __global__ void __launch_bounds__(RS_THREADS) k_resize(const LevelDev *__restric
     for (int k = 0; k < RS_TH / 8; ++k) {
         const int py = py0 + g + 8 * k;
         if (py >= ph) break;
-        const int ry = reflect101(py - ORBB_BORDER, L.h);
-        int y0, y1, b0, b1;
-        if (area) { y0 = 2 * ry; y1 = y0 + 1; b0 = b1 = 0; }
-        else {
-            const int2 yr = __ldg(&L.yrows[ry]);
-            const short2 bw = __ldg(&L.ybeta[ry]);
-            y0 = yr.x; y1 = yr.y; b0 = bw.x; b1 = bw.y;
-        }
+        const int4 rt = s_rowtab[g + 8 * k];
+        const int y0 = rt.x, y1 = rt.y, b0 = rt.z, b1 = rt.w;
         const uint2 ta = *reinterpret_cast<const uint2 *>(s_t + (y0 - rmin) * RS_TW + 4 * q);
         const uint2 tb = *reinterpret_cast<const uint2 *>(s_t + (y1 - rmin) * RS_TW + 4 * q);
         const int t0[4] = {(int)(ta.x & 0xffff), (int)(ta.x >> 16), (int)(ta.y & 0xffff), (int)(ta.y >> 16)};
@@ -205,10 +223,10 @@ __global__ void __launch_bounds__(128) k_blur(const LevelDev *__restrict__ level
 // ---------------------------------------------------------------- host launchers
 cudaError_t launch_level0(const uint8_t *d_in, size_t pitch, size_t stride, const LevelDev &L0, int frame_base,
                           int n_frames, cudaStream_t st) {
-    const int words = L0.pitch / 4;
-    dim3 grid((words + 127) / 128, L0.rows, n_frames);
-    const int aligned4 = ((reinterpret_cast<uintptr_t>(d_in) | pitch | stride) & 3) == 0;
-    k_level0<<<grid, 128, 0, st>>>(d_in, pitch, stride, L0, aligned4, frame_base);
+    const int items = (L0.pitch >> 4) * L0.rows;
+    dim3 grid((items + 255) / 256, n_frames);
+    const int aligned16 = ((reinterpret_cast<uintptr_t>(d_in) | pitch | stride) & 15) == 0;
+    k_level0<<<grid, 256, 0, st>>>(d_in, pitch, stride, L0, aligned16, frame_base);
     return cudaGetLastError();
 }
 
