@@ -38,6 +38,8 @@ CONFIGS = [  # (w, h, nfeatures, scale, nlevels, generator, seed)
     (320, 240, 500, 1.2, 8, "sparse_frame", 5),
     (400, 300, 400, 1.5, 4, "textured_frame", 9),
     (512, 384, 600, 2.0, 3, "textured_frame", 21),
+    (848, 800, 1000, 1.2, 8, "textured_frame", 3000),   # cfg 3 geometry (T265-sized)
+    (1280, 720, 2000, 1.2, 8, "textured_frame", 4000),  # cfg 4 geometry
 ]
 
 
@@ -310,3 +312,42 @@ def test_cpp_host_mirror(orbb, oracle, synth, tmp_path):
     okp, odesc = canon(*oracle.Oracle(640, 480).extract(img))
     kp, desc = canon(kp, desc)
     assert n == len(okp) and kp.tobytes() == okp.tobytes() and np.array_equal(desc, odesc)
+
+
+def test_cfg3_stereo_and_temporal_matching(orbb, oracle, synth):
+    """cfg 3: left/right (horizontal disparity) and t/t+1 (translation) pairs, 2-NN + 0.7 ratio test through the
+    segmented matcher; extraction and matches must equal the oracle's."""
+    import torch
+    w, h = 848, 800
+    left = synth.textured_frame(w, h, 3100)
+    right = synth.shifted_frame(left, -24, 0, 3101)
+    nxt = synth.shifted_frame(left, 3, 1, 3102)
+    frames = np.stack([left, right, nxt])
+    ex = orbb.ORBextractor(1000, 1.2, 8, 20, 7, width=w, height=h, max_batch=3)
+    kp, desc, counts = ex.extract_batch(frames)
+    o = oracle.Oracle(w, h, 1000)
+    odesc = []
+    for f in range(3):
+        okp, od = canon(*o.extract(frames[f]))
+        gk, gd = canon(kp[f, :counts[f]], desc[f, :counts[f]])
+        assert len(okp) == counts[f] and gk.tobytes() == okp.tobytes() and np.array_equal(gd, od)
+        odesc.append(desc[f, :counts[f]].copy())  # GPU order == what the matcher sees
+    # segments: (left -> right), (left -> next)
+    q = np.concatenate([odesc[0], odesc[0]])
+    t = np.concatenate([odesc[1], odesc[2]])
+    qo = np.array([0, len(odesc[0]), 2 * len(odesc[0])], np.int32)
+    to = np.array([0, len(odesc[1]), len(odesc[1]) + len(odesc[2])], np.int32)
+    dq, dt = torch.from_numpy(q).cuda(), torch.from_numpy(t).cuda()
+    idx = torch.zeros((len(q), 2), dtype=torch.int32, device="cuda")
+    dist = torch.zeros((len(q), 2), dtype=torch.int32, device="cuda")
+    acc = torch.zeros(len(q), dtype=torch.uint8, device="cuda")
+    ex.match_keypoints_segmented(dq, torch.from_numpy(qo).cuda(), dt, torch.from_numpy(to).cuda(), 2, len(odesc[0]),
+                                 idx, dist, acc, k=2, ratio=0.7, stream=torch.cuda.current_stream())
+    torch.cuda.synchronize()
+    idx, dist, acc = idx.cpu().numpy(), dist.cpu().numpy(), acc.cpu().numpy().astype(bool)
+    for s_ in range(2):
+        oi, od, oa = oracle.match_knn(q[qo[s_]:qo[s_ + 1]], t[to[s_]:to[s_ + 1]], k=2, ratio=0.7)
+        assert np.array_equal(idx[qo[s_]:qo[s_ + 1]], oi) and np.array_equal(dist[qo[s_]:qo[s_ + 1]], od)
+        assert np.array_equal(acc[qo[s_]:qo[s_ + 1]], oa)
+        assert oa.sum() > 50  # the synthetic pair really has correspondences
+    ex.close()
