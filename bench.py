@@ -252,23 +252,63 @@ def main():
                 for j in range(len(stage_names))]
     counts = d_cnt.cpu().numpy()
 
-    # ---- end-to-end through the host C-ABI call (pinned host in, H2D + extract + D2H inside the timed region)
-    def e2e_step(i):
+    # ---- end-to-end through the host C-ABI (pinned host in, H2D + extract + D2H inside the timed region).
+    # e2e      : the double-buffered submit/wait form (orbb_extract_batch_host_async + orbb_wait) a capture loop
+    #            uses: batch i+1 is submitted before batch i is waited for, every batch's result is read on the host.
+    # e2e_sync : one blocking orbb_extract_batch_host call per step.
+    pin_out = [(torch.zeros(B * ex.max_kp * 28, dtype=torch.uint8).pin_memory(),
+                torch.zeros(B * ex.max_kp * 32, dtype=torch.uint8).pin_memory(),
+                torch.zeros(B, dtype=torch.int32).pin_memory()) for _ in range(2)]
+
+    def e2e_sync_step(i):
         ex.extract_batch_host_into(pin_frames[i % N_INPUT_SETS].data_ptr(), W, W * H, B, pin_kp.data_ptr(),
                                    pin_desc.data_ptr(), pin_cnt.data_ptr(), stream=st)
 
+    def e2e_async_run(nsteps):
+        seen, prev = 0, None
+        for i in range(nsteps):
+            k, d, c = pin_out[i % 2]
+            t = ex.extract_batch_host_async(pin_frames[i % N_INPUT_SETS].data_ptr(), W, W * H, B, k.data_ptr(),
+                                            d.data_ptr(), c.data_ptr(), stream=st)
+            if prev is not None:
+                ex.wait(prev[0])
+                seen += int(prev[1].sum())  # the host really reads the step's result
+            prev = (t, c)
+        ex.wait(prev[0])
+        return seen + int(prev[1].sum())
+
     for i in range(min(args.warmup, 3)):
-        e2e_step(i)
+        e2e_sync_step(i)
     sync_all()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(st)
     for i in range(args.steps):
-        e2e_step(i)
+        e2e_sync_step(i)
     e1.record(st)
     sync_all()
-    e2e_ms = e0.elapsed_time(e1)
+    e2e_sync_ms = e0.elapsed_time(e1)
+    e2e_async_run(min(args.warmup, 3))
+    sync_all()
+    t0 = time.perf_counter()
+    e0.record(st)
+    kp_seen = e2e_async_run(args.steps)
+    e1.record(st)
+    torch.cuda.synchronize()
+    e2e_wall_ms = (time.perf_counter() - t0) * 1e3
+    e2e_ms = max(e0.elapsed_time(e1), e2e_wall_ms)  # host-blocking API: take the larger of event and wall time
+    sync_all()
     h2d = B * W * H
     d2h = B * ex.max_kp * 60 + 4 * B
+    # PCIe H2D rate of this box for the same pinned buffer (explains the e2e ceiling)
+    p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    d_sets[0].copy_(pin_frames[0], non_blocking=True)
+    torch.cuda.synchronize()
+    p0.record(st)
+    for _ in range(3):
+        d_sets[0].copy_(pin_frames[0], non_blocking=True)
+    p1.record(st)
+    torch.cuda.synchronize()
+    h2d_gbs = 3 * h2d / (p0.elapsed_time(p1) * 1e-3) / 1e9
 
     # ---- matcher: this rank's batch descriptors (1-NN) against a 50k map (cfg 5)
     nq = int(counts.sum())
@@ -308,10 +348,10 @@ def main():
     g1.record(st)
     torch.cuda.synchronize()
     gather_ms = g0.elapsed_time(g1)
-    t = torch.tensor([total_ms, e2e_ms, match_ms, gather_ms], dtype=torch.float64, device=dev)
+    t = torch.tensor([total_ms, e2e_ms, match_ms, gather_ms, e2e_sync_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    total_ms, e2e_ms, match_ms_max, gather_ms = [float(v) for v in t.tolist()]
+    total_ms, e2e_ms, match_ms_max, gather_ms, e2e_sync_ms = [float(v) for v in t.tolist()]
     kp_total = all_counts.sum().to(torch.float64).reshape(1)
 
     if rank == 0:
@@ -331,7 +371,10 @@ def main():
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
             "config": workload_config(B),
             "clocks": clocks,
-            "e2e": {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "e2e": {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "api": "orbb_extract_batch_host_async + orbb_wait, double-buffered (2 batches in flight)",
+                    "sync_api_value": frames_total / (e2e_sync_ms * 1e-3), "pcie_h2d_gbs": h2d_gbs,
+                    "h2d_bound_fps": world * h2d_gbs * 1e9 / (W * H)},
             "gpu_launches": KERNELS_PER_STEP * args.steps,
             "roofline": {"bound": "hbm", "kernel": "k_fast_cells", "achieved": achieved, "peak": hbm_peak,
                          "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": None, "peak_kind": peak_kind,

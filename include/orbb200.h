@@ -107,6 +107,17 @@ int orbb_extract_batch_host(orbb_handle *h, const uint8_t *h_images, size_t pitc
                             size_t frame_stride, int n_frames, orbb_keypoint *h_kp, uint8_t *h_desc,
                             int32_t *h_counts, int max_kp, void *cuda_stream);
 
+/* Asynchronous form of orbb_extract_batch_host for double-buffered capture loops: enqueues the whole
+ * pipeline (chunked H2D -> kernels -> D2H on the handle's internal streams) and returns a ticket (>= 0)
+ * without waiting; orbb_wait(ticket) blocks until that batch's outputs are in the host buffers.  At most
+ * two batches are in flight per handle (the call blocks on ticket-2); input and output host buffers of a
+ * batch must stay untouched until its ticket has been waited for.  Pinned host memory is needed for the
+ * copies to overlap (pageable memory works but serialises). */
+int orbb_extract_batch_host_async(orbb_handle *h, const uint8_t *h_images, size_t pitch,
+                                  size_t frame_stride, int n_frames, orbb_keypoint *h_kp,
+                                  uint8_t *h_desc, int32_t *h_counts, int max_kp, void *cuda_stream);
+int orbb_wait(orbb_handle *h, int ticket);
+
 /* ---------------------------------------------------------------- stage interface
  * Same stage names as the reference's free functions in namespace Jetracer.  All take the batch
  * resident in the handle (set by orbb_stage_upload or a previous stage) and are async on stream. */

@@ -55,10 +55,13 @@ struct orbb_handle {
     int n_slots = 0, sel_cap_max = 0, pcap = 0, pcap2 = 0, max_kp = 0;
     int4 *d_partial = nullptr;
     size_t partial_cap = 0;
-    uint8_t *d_in = nullptr;  // staging for the *_host entry point
-    orbb_keypoint *d_kp = nullptr;
-    uint8_t *d_desc = nullptr;
-    int *d_counts = nullptr;
+    // staging of the *_host entry points, double-buffered so consecutive batches overlap
+    uint8_t *d_in2[2] = {nullptr, nullptr};
+    orbb_keypoint *d_kp2[2] = {nullptr, nullptr};
+    uint8_t *d_desc2[2] = {nullptr, nullptr};
+    int *d_counts2[2] = {nullptr, nullptr};
+    cudaEvent_t ev_ticket[2] = {nullptr, nullptr}, ev_tail[2] = {nullptr, nullptr};
+    long long n_submitted = 0;
     uint8_t *d_dump = nullptr;
     long long *d_dump_off = nullptr;
     std::vector<long long> dump_off;
@@ -135,6 +138,10 @@ extern "C" int orbb_destroy(orbb_handle *h) {
         if (h->ev_done[i]) cudaEventDestroy(h->ev_done[i]);
     }
     if (h->ev_fence) cudaEventDestroy(h->ev_fence);
+    for (int i = 0; i < 2; ++i) {
+        if (h->ev_ticket[i]) cudaEventDestroy(h->ev_ticket[i]);
+        if (h->ev_tail[i]) cudaEventDestroy(h->ev_tail[i]);
+    }
     delete h;
     return ORBB_OK;
 }
@@ -363,10 +370,14 @@ extern "C" int orbb_create(orbb_handle **out, const orbb_params *params, int wid
     CKC(dalloc(h, &h->d_sel_count, (size_t)B * nl));
     CKC(cudaMemset(h->d_cand_count, 0, sizeof(int) * (size_t)B * nl));
     CKC(cudaMemset(h->d_sel_count, 0, sizeof(int) * (size_t)B * nl));
-    CKC(dalloc(h, &h->d_in, (size_t)width * height * B));
-    CKC(dalloc(h, &h->d_kp, (size_t)h->max_kp * B));
-    CKC(dalloc(h, &h->d_desc, (size_t)h->max_kp * B * 32));
-    CKC(dalloc(h, &h->d_counts, (size_t)B));
+    for (int i = 0; i < 2; ++i) {
+        CKC(dalloc(h, &h->d_in2[i], (size_t)width * height * B));
+        CKC(dalloc(h, &h->d_kp2[i], (size_t)h->max_kp * B));
+        CKC(dalloc(h, &h->d_desc2[i], (size_t)h->max_kp * B * 32));
+        CKC(dalloc(h, &h->d_counts2[i], (size_t)B));
+        CKC(cudaEventCreateWithFlags(&h->ev_ticket[i], cudaEventDisableTiming));
+        CKC(cudaEventCreateWithFlags(&h->ev_tail[i], cudaEventDisableTiming));
+    }
     CKC(dalloc(h, &h->d_dump, (size_t)dump_total));
     CKC(cudaStreamCreateWithFlags(&h->s_in, cudaStreamNonBlocking));
     CKC(cudaStreamCreateWithFlags(&h->s_out, cudaStreamNonBlocking));
@@ -514,30 +525,47 @@ extern "C" int orbb_extract_batch_device(orbb_handle *h, const uint8_t *d_images
                    static_cast<cudaStream_t>(stream));
 }
 
-// Host entry point: chunks of the batch flow through three streams (H2D copy stream -> caller's compute stream
-// -> D2H copy stream) linked by events, so PCIe transfers of chunk c+1 / c-1 overlap the kernels of chunk c.
-extern "C" int orbb_extract_batch_host(orbb_handle *h, const uint8_t *h_images, size_t pitch, size_t frame_stride,
-                                       int n_frames, orbb_keypoint *h_kp, uint8_t *h_desc, int32_t *h_counts,
-                                       int max_kp, void *stream) {
+// Host entry points: chunks of the batch flow through the handle's streams (H2D copy stream -> two alternating
+// compute streams -> D2H copy stream) linked by events, so PCIe transfers overlap the kernels; staging buffers
+// are double-buffered by ticket parity so the next batch's H2D runs under the current batch's kernels.
+extern "C" int orbb_wait(orbb_handle *h, int ticket) {
+    if (!h || ticket < 0 || ticket >= h->n_submitted) return ORBB_ERR_INVALID;
+    if (ticket < h->n_submitted - 2) return ORBB_OK;  // older than the ring: already waited for at submit time
+    CK(h, cudaEventSynchronize(h->ev_ticket[ticket & 1]));
+    return ORBB_OK;
+}
+
+extern "C" int orbb_extract_batch_host_async(orbb_handle *h, const uint8_t *h_images, size_t pitch, size_t frame_stride,
+                                             int n_frames, orbb_keypoint *h_kp, uint8_t *h_desc, int32_t *h_counts,
+                                             int max_kp, void *stream) {
     if (!h || !h_images || !h_kp || !h_desc || !h_counts || max_kp < 1 || pitch < (size_t)h->w) return ORBB_ERR_INVALID;
     if (n_frames < 1 || n_frames > h->max_batch) return ORBB_ERR_CAPACITY;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     CK(h, cudaSetDevice(h->device));
+    const int ticket = (int)h->n_submitted, par = ticket & 1;
+    if (ticket >= 2) CK(h, cudaEventSynchronize(h->ev_ticket[par]));  // batch ticket-2 owned this parity's buffers
     h->n_frames_last = n_frames;
     const size_t fw = (size_t)h->w, fsz = fw * h->h;
     const int mk = std::min(max_kp, h->max_kp);
-    // everything already queued on the caller's stream happens-before the pipeline
+    uint8_t *d_in = h->d_in2[par];
+    orbb_keypoint *d_kp = h->d_kp2[par];
+    uint8_t *d_desc = h->d_desc2[par];
+    int *d_counts = h->d_counts2[par];
+    // everything already queued on the caller's stream happens-before the pipeline; the level/scratch buffers
+    // are shared by consecutive batches, so each compute stream also waits for the other one's previous tail
     CK(h, cudaEventRecord(h->ev_fence, st));
     CK(h, cudaStreamWaitEvent(h->s_in, h->ev_fence, 0));
-    CK(h, cudaStreamWaitEvent(h->s_comp[0], h->ev_fence, 0));
-    CK(h, cudaStreamWaitEvent(h->s_comp[1], h->ev_fence, 0));
-    // chunk sizes grow 16, 32, 64, 64, ...: the first H2D (which nothing can hide) stays short
+    for (int i = 0; i < 2; ++i) {
+        CK(h, cudaStreamWaitEvent(h->s_comp[i], h->ev_fence, 0));
+        if (ticket >= 1) CK(h, cudaStreamWaitEvent(h->s_comp[i], h->ev_tail[i ^ 1], 0));
+    }
+    // chunk sizes grow 16, 32, 64, 64, ...: the first H2D (which nothing in this batch can hide) stays short
     int per = n_frames <= 32 ? n_frames : 16;
     for (int c = 0, f0 = 0; f0 < n_frames; ++c) {
         int n = std::min(per, n_frames - f0);
         if (c == ORBB_MAX_CHUNKS - 1) n = n_frames - f0;
         cudaStream_t sc = h->s_comp[c & 1];
-        uint8_t *din = h->d_in + fsz * f0;
+        uint8_t *din = d_in + fsz * f0;
         const uint8_t *src = h_images + frame_stride * f0;
         if (pitch == fw && frame_stride == fsz) {
             CK(h, cudaMemcpyAsync(din, src, fsz * n, cudaMemcpyHostToDevice, h->s_in));
@@ -550,23 +578,34 @@ extern "C" int orbb_extract_batch_host(orbb_handle *h, const uint8_t *h_images, 
         }
         CK(h, cudaEventRecord(h->ev_in[c], h->s_in));
         CK(h, cudaStreamWaitEvent(sc, h->ev_in[c], 0));
-        int rc = run_all(h, din, fw, fsz, f0, n, h->d_kp, h->d_desc, h->d_counts, mk, sc);
+        int rc = run_all(h, din, fw, fsz, f0, n, d_kp, d_desc, d_counts, mk, sc);
         if (rc) return rc;
         CK(h, cudaEventRecord(h->ev_comp[c], sc));
         CK(h, cudaStreamWaitEvent(h->s_out, h->ev_comp[c], 0));
-        CK(h, cudaMemcpyAsync(h_counts + f0, h->d_counts + f0, sizeof(int) * n, cudaMemcpyDeviceToHost, h->s_out));
-        CK(h, cudaMemcpy2DAsync(h_kp + (size_t)f0 * max_kp, sizeof(orbb_keypoint) * max_kp, h->d_kp + (size_t)f0 * mk,
+        CK(h, cudaMemcpyAsync(h_counts + f0, d_counts + f0, sizeof(int) * n, cudaMemcpyDeviceToHost, h->s_out));
+        CK(h, cudaMemcpy2DAsync(h_kp + (size_t)f0 * max_kp, sizeof(orbb_keypoint) * max_kp, d_kp + (size_t)f0 * mk,
                                 sizeof(orbb_keypoint) * mk, sizeof(orbb_keypoint) * mk, n, cudaMemcpyDeviceToHost, h->s_out));
-        CK(h, cudaMemcpy2DAsync(h_desc + 32 * (size_t)f0 * max_kp, 32 * (size_t)max_kp, h->d_desc + 32 * (size_t)f0 * mk,
+        CK(h, cudaMemcpy2DAsync(h_desc + 32 * (size_t)f0 * max_kp, 32 * (size_t)max_kp, d_desc + 32 * (size_t)f0 * mk,
                                 32 * (size_t)mk, 32 * (size_t)mk, n, cudaMemcpyDeviceToHost, h->s_out));
         f0 += n;
         per = std::min(per * 2, 64);
     }
-    // the caller's stream observes completion too (later work queued on it is ordered after the batch)
-    CK(h, cudaEventRecord(h->ev_done[0], h->s_out));
-    CK(h, cudaStreamWaitEvent(st, h->ev_done[0], 0));
-    CK(h, cudaStreamSynchronize(h->s_out));
-    return ORBB_OK;
+    CK(h, cudaEventRecord(h->ev_tail[0], h->s_comp[0]));
+    CK(h, cudaEventRecord(h->ev_tail[1], h->s_comp[1]));
+    // completion is observed through orbb_wait (the caller's stream is NOT made to wait: that would serialise
+    // consecutive batches through the fence above)
+    CK(h, cudaEventRecord(h->ev_ticket[par], h->s_out));
+    h->n_submitted++;
+    return ticket;
+}
+
+extern "C" int orbb_extract_batch_host(orbb_handle *h, const uint8_t *h_images, size_t pitch, size_t frame_stride,
+                                       int n_frames, orbb_keypoint *h_kp, uint8_t *h_desc, int32_t *h_counts,
+                                       int max_kp, void *stream) {
+    const int ticket = orbb_extract_batch_host_async(h, h_images, pitch, frame_stride, n_frames, h_kp, h_desc, h_counts,
+                                                     max_kp, stream);
+    if (ticket < 0) return ticket;
+    return orbb_wait(h, ticket);
 }
 
 // ---------------------------------------------------------------- matcher

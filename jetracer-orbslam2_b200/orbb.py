@@ -29,7 +29,8 @@ KEYPOINT_DTYPE = np.dtype(
 EXPORTS = [
     "orbb_create", "orbb_destroy", "orbb_strerror", "orbb_last_cuda_error", "orbb_get_levels",
     "orbb_get_scale_factors", "orbb_get_features_per_level", "orbb_max_keypoints_per_frame", "orbb_get_level",
-    "orbb_extract_batch_device", "orbb_extract_batch_host", "orbb_stage_upload", "orbb_pyramid_create_levels",
+    "orbb_extract_batch_device", "orbb_extract_batch_host", "orbb_extract_batch_host_async", "orbb_wait",
+    "orbb_stage_upload", "orbb_pyramid_create_levels",
     "orbb_detect", "orbb_detect_fast", "orbb_detect_distribute", "orbb_gaussian_blur", "orbb_compute_angle_and_orb", "orbb_match_knn",
     "orbb_match_knn_segmented", "orbb_debug_get_padded", "orbb_debug_get_blurred", "orbb_debug_get_scores",
     "orbb_debug_get_candidates", "orbb_debug_get_selected", "orbb_debug_distribute",
@@ -77,6 +78,8 @@ def load_library():
     L.orbb_get_level.argtypes = [vp, i32, i32, C.POINTER(Level)]
     L.orbb_extract_batch_device.argtypes = [vp, vp, sz, sz, i32, vp, vp, vp, i32, vp]
     L.orbb_extract_batch_host.argtypes = [vp, vp, sz, sz, i32, vp, vp, vp, i32, vp]
+    L.orbb_extract_batch_host_async.argtypes = [vp, vp, sz, sz, i32, vp, vp, vp, i32, vp]
+    L.orbb_wait.argtypes = [vp, i32]
     L.orbb_stage_upload.argtypes = [vp, vp, sz, sz, i32, vp]
     L.orbb_pyramid_create_levels.argtypes = [vp, vp]
     L.orbb_detect.argtypes = [vp, vp]
@@ -216,6 +219,15 @@ class ORBextractor:
         self._check(self._lib.orbb_extract_batch_host(self._h, C.c_void_p(frames_ptr), pitch, stride, n,
                                                       C.c_void_p(kp_ptr), C.c_void_p(desc_ptr),
                                                       C.c_void_p(counts_ptr), self.max_kp, _stream_ptr(stream)))
+
+    def extract_batch_host_async(self, frames_ptr, pitch, stride, n, kp_ptr, desc_ptr, counts_ptr, stream=None) -> int:
+        """Submit a batch (pinned host buffers) without waiting; returns a ticket for ``wait``."""
+        return self._check(self._lib.orbb_extract_batch_host_async(
+            self._h, C.c_void_p(frames_ptr), pitch, stride, n, C.c_void_p(kp_ptr), C.c_void_p(desc_ptr),
+            C.c_void_p(counts_ptr), self.max_kp, _stream_ptr(stream)))
+
+    def wait(self, ticket: int):
+        self._check(self._lib.orbb_wait(self._h, ticket))
 
     def extract_batch_device(self, d_frames, n: int, d_kp, d_desc, d_counts, pitch=None, stride=None, stream=None):
         """DEVICE-resident frames (torch CUDA uint8 tensor or address); async on ``stream``."""

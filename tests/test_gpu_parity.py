@@ -351,3 +351,35 @@ def test_cfg3_stereo_and_temporal_matching(orbb, oracle, synth):
         assert np.array_equal(acc[qo[s_]:qo[s_ + 1]], oa)
         assert oa.sum() > 50  # the synthetic pair really has correspondences
     ex.close()
+
+
+def test_async_host_api_matches_sync(orbb, synth):
+    """orbb_extract_batch_host_async/orbb_wait with two batches in flight == the blocking call."""
+    import torch
+    frames = [np.stack([synth.textured_frame(424, 240, 700 + 10 * b + i) for i in range(40)]) for b in range(3)]
+    ex = orbb.ORBextractor(600, 1.2, 6, 20, 7, width=424, height=240, max_batch=40)
+    ref = [ex.extract_batch(f) for f in frames]
+    pins = [torch.from_numpy(f).pin_memory() for f in frames]
+    outs = [(torch.zeros(40 * ex.max_kp * 28, dtype=torch.uint8).pin_memory(),
+             torch.zeros(40 * ex.max_kp * 32, dtype=torch.uint8).pin_memory(),
+             torch.zeros(40, dtype=torch.int32).pin_memory()) for _ in range(3)]
+    tickets = []
+    for rep in range(2):  # 6 submissions: the ticket ring wraps
+        for b in range(3):
+            k, d, c = outs[b]
+            tickets.append(ex.extract_batch_host_async(pins[b].data_ptr(), 424, 424 * 240, 40, k.data_ptr(), d.data_ptr(),
+                                                       c.data_ptr()))
+            if len(tickets) >= 2:
+                ex.wait(tickets[-2])
+    ex.wait(tickets[-1])
+    assert tickets == list(range(tickets[0], tickets[0] + 6))  # earlier blocking calls consumed tickets too
+    for b in range(3):
+        k, d, c = outs[b]
+        rk, rd, rc = ref[b]
+        assert np.array_equal(c.numpy(), rc)
+        kk = np.frombuffer(k.numpy().tobytes(), orbb.KEYPOINT_DTYPE).reshape(40, ex.max_kp)
+        dd = d.numpy().reshape(40, ex.max_kp, 32)
+        for f in range(40):
+            n = rc[f]
+            assert kk[f, :n].tobytes() == rk[f, :n].tobytes() and dd[f, :n].tobytes() == rd[f, :n].tobytes()
+    ex.close()
