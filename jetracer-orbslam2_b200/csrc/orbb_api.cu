@@ -68,6 +68,8 @@ struct orbb_handle {
     int n_frames_last = 0;
     cudaStream_t s_in = nullptr, s_out = nullptr;  // copy streams of the pipelined *_host entry point
     cudaStream_t s_comp[2] = {nullptr, nullptr};   // alternating compute streams (chunk tails overlap)
+    cudaStream_t s_side = nullptr;                 // side stream of the device entry point (blur under FAST/quadtree)
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     cudaEvent_t ev_fence = nullptr, ev_done[2] = {nullptr, nullptr};
     std::vector<cudaEvent_t> ev_in, ev_comp;
     std::vector<void *> allocs;
@@ -138,6 +140,9 @@ extern "C" int orbb_destroy(orbb_handle *h) {
         if (h->ev_done[i]) cudaEventDestroy(h->ev_done[i]);
     }
     if (h->ev_fence) cudaEventDestroy(h->ev_fence);
+    if (h->s_side) cudaStreamDestroy(h->s_side);
+    if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+    if (h->ev_join) cudaEventDestroy(h->ev_join);
     for (int i = 0; i < 2; ++i) {
         if (h->ev_ticket[i]) cudaEventDestroy(h->ev_ticket[i]);
         if (h->ev_tail[i]) cudaEventDestroy(h->ev_tail[i]);
@@ -386,6 +391,9 @@ extern "C" int orbb_create(orbb_handle **out, const orbb_params *params, int wid
         CKC(cudaEventCreateWithFlags(&h->ev_done[i], cudaEventDisableTiming));
     }
     CKC(cudaEventCreateWithFlags(&h->ev_fence, cudaEventDisableTiming));
+    CKC(cudaStreamCreateWithFlags(&h->s_side, cudaStreamNonBlocking));
+    CKC(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+    CKC(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
     h->ev_in.resize(ORBB_MAX_CHUNKS); h->ev_comp.resize(ORBB_MAX_CHUNKS);
     for (int i = 0; i < ORBB_MAX_CHUNKS; ++i) {
         CKC(cudaEventCreateWithFlags(&h->ev_in[i], cudaEventDisableTiming));
@@ -463,13 +471,23 @@ static int run_angle_orb(orbb_handle *h, int f0, int n, orbb_keypoint *d_kp, uin
     return ORBB_OK;
 }
 static int run_all(orbb_handle *h, const uint8_t *d_images, size_t pitch, size_t stride, int f0, int n, orbb_keypoint *d_kp,
-                   uint8_t *d_desc, int32_t *d_counts, int max_kp, cudaStream_t st) {
+                   uint8_t *d_desc, int32_t *d_counts, int max_kp, cudaStream_t st, cudaStream_t side = nullptr,
+                   cudaEvent_t ev_fork = nullptr, cudaEvent_t ev_join = nullptr) {
     int rc;
     if ((rc = run_upload(h, d_images, pitch, stride, f0, n, st))) return rc;
     if ((rc = run_pyramid(h, f0, n, st))) return rc;
     if ((rc = run_fast(h, f0, n, st))) return rc;
+    // The blur depends only on the pyramid.  FAST saturates the issue slots, the quadtree kernel does not
+    // (barrier/latency bound), so with a side stream the blur is forked to run under the quadtree.
+    if (side) {
+        CK(h, cudaEventRecord(ev_fork, st));
+        CK(h, cudaStreamWaitEvent(side, ev_fork, 0));
+        if ((rc = run_blur(h, f0, n, side))) return rc;
+        CK(h, cudaEventRecord(ev_join, side));
+    }
     if ((rc = run_distribute(h, f0, n, st))) return rc;
-    if ((rc = run_blur(h, f0, n, st))) return rc;
+    if (side) CK(h, cudaStreamWaitEvent(st, ev_join, 0));
+    else if ((rc = run_blur(h, f0, n, st))) return rc;
     return run_angle_orb(h, f0, n, d_kp, d_desc, d_counts, max_kp, st);
 }
 
@@ -522,7 +540,7 @@ extern "C" int orbb_extract_batch_device(orbb_handle *h, const uint8_t *d_images
     CK(h, cudaSetDevice(h->device));
     h->n_frames_last = n_frames;
     return run_all(h, d_images, pitch, frame_stride, 0, n_frames, d_kp, d_desc, d_counts, max_kp,
-                   static_cast<cudaStream_t>(stream));
+                   static_cast<cudaStream_t>(stream), h->s_side, h->ev_fork, h->ev_join);
 }
 
 // Host entry points: chunks of the batch flow through the handle's streams (H2D copy stream -> two alternating
