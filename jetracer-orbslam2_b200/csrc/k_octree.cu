@@ -76,8 +76,7 @@ __device__ __forceinline__ void radix_pass(const uint32_t *__restrict__ kin, con
         const bool valid = i < s1;
         const unsigned d = valid ? ((kin[i] >> shift) & 255u) : (0x1000u + lane);
         const unsigned peers = __match_any_sync(FULL, d);
-        if (valid && (peers & lt) == 0) S.whist[warp][d] += __popc(peers);
-        __syncwarp();
+        if (valid && (peers & lt) == 0) atomicAdd(&S.whist[warp][d], (uint32_t)__popc(peers));  // no return: RED
     }
     __syncthreads();
     uint32_t tot = 0;
@@ -100,18 +99,48 @@ __device__ __forceinline__ void radix_pass(const uint32_t *__restrict__ kin, con
         if (valid) { k = kin[i]; id = iin[i]; }
         const unsigned d = valid ? ((k >> shift) & 255u) : (0x1000u + lane);
         const unsigned peers = __match_any_sync(FULL, d);
-        uint32_t pos = 0;
-        if (valid) pos = S.digit_base[d] + S.whist[warp][d] + __popc(peers & lt);
-        __syncwarp();
-        if (valid && (peers & lt) == 0) S.whist[warp][d] += __popc(peers);
-        __syncwarp();
+        // the group leader reserves the group's slots in the warp-private running offset and broadcasts the base
+        uint32_t old = 0;
+        if (valid && (peers & lt) == 0) old = atomicAdd(&S.whist[warp][d], (uint32_t)__popc(peers));
+        old = __shfl_sync(FULL, old, __ffs(peers) - 1);
+        const uint32_t pos = valid ? S.digit_base[d] + old + __popc(peers & lt) : 0u;
         if (valid) { kout[pos] = k; iout[pos] = id; }
     }
     __syncthreads();
 }
 
-// shared-memory bitonic sort, DESCENDING by key, m = power of two
+// bitonic sort, DESCENDING by key, m = power of two.  m <= OCT_THREADS: one element per thread in registers,
+// strides < 32 with warp shuffles and only the wide strides through shared memory; larger m: all in smem.
 __device__ __forceinline__ void bitonic_desc(unsigned long long *key, uint32_t *val, int m) {
+    if (m <= OCT_THREADS) {
+        const int i = threadIdx.x;
+        unsigned long long a = i < m ? key[i] : 0ull;
+        uint32_t v = i < m ? val[i] : 0u;
+        for (int k = 2; k <= m; k <<= 1) {
+            for (int j = k >> 1; j > 0; j >>= 1) {
+                unsigned long long b;
+                uint32_t w;
+                if (j >= 32) {
+                    __syncthreads();
+                    if (i < m) { key[i] = a; val[i] = v; }
+                    __syncthreads();
+                    b = i < m ? key[i ^ j] : 0ull;
+                    w = i < m ? val[i ^ j] : 0u;
+                } else {
+                    b = __shfl_xor_sync(FULL, a, j);
+                    w = __shfl_xor_sync(FULL, v, j);
+                }
+                const bool lower = (i & j) == 0, desc = (i & k) == 0;
+                // the lower index of a pair keeps the larger key in a descending run
+                const bool take = (lower == desc) ? (a < b) : (a > b);
+                if (take) { a = b; v = w; }
+            }
+        }
+        __syncthreads();
+        if (i < m) { key[i] = a; val[i] = v; }
+        __syncthreads();
+        return;
+    }
     for (int k = 2; k <= m; k <<= 1) {
         for (int j = k >> 1; j > 0; j >>= 1) {
             for (int i = threadIdx.x; i < m; i += OCT_THREADS) {
@@ -130,7 +159,7 @@ __device__ __forceinline__ void bitonic_desc(unsigned long long *key, uint32_t *
     }
 }
 
-__global__ void __launch_bounds__(OCT_THREADS)
+__global__ void __launch_bounds__(OCT_THREADS, 3)
 k_octree(const LevelDev *__restrict__ levels, int n_levels, const int *__restrict__ cand_count,
          int *__restrict__ sel_count, int level_base, int frame_base, int quota_override, int pcap, int pcap2) {
     __shared__ OctStatic S;
@@ -150,10 +179,12 @@ k_octree(const LevelDev *__restrict__ levels, int n_levels, const int *__restric
     unsigned long long *best = reinterpret_cast<unsigned long long *>(dyn);          // [sel_cap]
     unsigned long long *skey = best + L.sel_cap;                                       // [pcap2]
     uint32_t *sval = reinterpret_cast<uint32_t *>(skey + pcap2);                       // [pcap2]
-    uint32_t *p_start = sval + pcap2, *p_cnt = p_start + pcap, *p_seq = p_cnt + pcap;  // [pcap] each
-    uint32_t *p_gain = p_seq + pcap;
-    uint32_t *q_start = p_gain + pcap, *q_cnt = q_start + pcap, *q_seq = q_cnt + pcap;
-    uint32_t *node_start = q_seq + pcap;                                               // [pcap + 1]
+    // per-node arrays, [pcap + 1] each: start (two generations), creation sequence (two generations,
+    // 0xffffffff = not expandable this round), gain, processing rank (-1 = not split)
+    uint32_t *nst_a = sval + pcap2, *nst_b = nst_a + (pcap + 1);
+    uint32_t *seq_a = nst_b + (pcap + 1), *seq_b = seq_a + (pcap + 1);
+    uint32_t *gain = seq_b + (pcap + 1);
+    int *rank_of = reinterpret_cast<int *>(gain + (pcap + 1));
 
     const size_t fo = (size_t)frame * L.cand_cap;
     const uint32_t *cand = L.cand + fo;
@@ -174,7 +205,8 @@ k_octree(const LevelDev *__restrict__ levels, int n_levels, const int *__restric
         uint32_t *t = ka; ka = kb; kb = t;
         t = ia; ia = ib; ib = t;
     }
-    uint32_t *seg = kb;                                  // free ping-pong buffers become scratch
+    // free ping-pong buffers become scratch: two generations of u16 segment ids, and the head flags
+    uint16_t *seg_a = reinterpret_cast<uint16_t *>(kb), *seg_b = seg_a + L.cand_cap;
     uint8_t *head = reinterpret_cast<uint8_t *>(ib);
 
     // ---- 3. split depths + histograms
@@ -223,58 +255,63 @@ k_octree(const LevelDev *__restrict__ levels, int n_levels, const int *__restric
     __syncthreads();
 
     if (mode == 1) {
-        // ---- 5. careful phase.  nodes at depth k0 -> node_start[]
-        const int nseg = S.ctl[C_SIZE];  // < N <= pcap
-        uint32_t carry = 0;
-        for (int base = 0; base < n; base += OCT_THREADS) {
-            const int i = base + tid;
-            const uint32_t h = i < n ? head[i] : 0u;
-            uint32_t tot;
-            const uint32_t ex = block_excl_scan(h, S.warp_tot, &tot) + carry;
-            if (h) node_start[ex] = (uint32_t)i;
-            carry += tot;
-        }
-        if (tid == 0) node_start[nseg] = (uint32_t)n;
-        __syncthreads();
-        // expandable nodes with their closed-form creation sequence
-        const uint32_t digit_mask = 0xCCCCCCCCu & ((k0 >= 16) ? 0xffffffffu : ((1u << (2 * k0)) - 1u));
-        const uint32_t root_mask = (k0 & 1) ? 0u : (((1u << (L.key_bits - 2 * D)) - 1u) << (2 * k0));
-        for (int s = tid; s < nseg; s += OCT_THREADS) {
-            const uint32_t st = node_start[s], cnt = node_start[s + 1] - st;
-            if (cnt > 1) {
-                const int p = atomicAdd(&S.ctl[C_PN], 1);
-                p_start[p] = st; p_cnt[p] = cnt;
-                p_seq[p] = (ka[st] >> (2 * (D - k0))) ^ digit_mask ^ root_mask;
+        // ---- 5. careful phase, key-parallel.  A round works on the current head-delimited nodes: nst[] start of
+        // every node, seq[] creation sequence of the nodes created by the previous round that hold > 1 key
+        // (upstream's vSizeAndPointerToNode), seg[] node id of every key.
+        int nseg = S.ctl[C_SIZE];  // < N <= pcap
+        uint32_t *nst = nst_a, *nst2 = nst_b, *seq = seq_a, *seq2 = seq_b;
+        uint16_t *seg = seg_a, *seg2 = seg_b;
+        {
+            uint32_t carry = 0;
+            for (int base = 0; base < n; base += OCT_THREADS) {
+                const int i = base + tid;
+                const uint32_t h = i < n ? head[i] : 0u;
+                uint32_t tot;
+                const uint32_t inc = block_excl_scan(h, S.warp_tot, &tot) + carry + h;
+                if (i < n) { seg[i] = (uint16_t)(inc - 1); if (h) nst[inc - 1] = (uint32_t)i; }
+                carry += tot;
+            }
+            if (tid == 0) nst[nseg] = (uint32_t)n;
+            __syncthreads();
+            // closed-form creation sequence of the breadth-first pass that made the depth-k0 nodes
+            const uint32_t digit_mask = 0xCCCCCCCCu & ((1u << (2 * k0)) - 1u);
+            const uint32_t root_mask = (k0 & 1) ? 0u : (((1u << (L.key_bits - 2 * D)) - 1u) << (2 * k0));
+            for (int sidx = tid; sidx < nseg; sidx += OCT_THREADS) {
+                const uint32_t st = nst[sidx], cnt = nst[sidx + 1] - st;
+                seq[sidx] = cnt > 1 ? (((ka[st] >> (2 * (D - k0))) ^ digit_mask ^ root_mask) & 0x7fffffffu) : 0xffffffffu;
             }
         }
-        __syncthreads();
         int d = k0;
-        uint32_t *ps = p_start, *pc = p_cnt, *pq = p_seq, *qs = q_start, *qc = q_cnt, *qq = q_seq;
         while (true) {
-            const int pn = S.ctl[C_PN], size = S.ctl[C_SIZE];
+            const int size = S.ctl[C_SIZE];
+            for (int sidx = tid; sidx < nseg; sidx += OCT_THREADS) { gain[sidx] = 0; rank_of[sidx] = -1; }
+            if (tid == 0) { S.ctl[C_PN] = 0; S.ctl[C_CUT] = 0x7fffffff; }
+            __syncthreads();
+            // gains: children - 1 = number of depth-(d+1) partings inside the node
+            for (int i = tid; i < n - 1; i += OCT_THREADS)
+                if (sd[i] == d + 1) {
+                    const int sidx = seg[i];
+                    if (seq[sidx] != 0xffffffffu) atomicAdd(&gain[sidx], 1u);
+                }
+            // expandable nodes -> sort list keyed by (count, creation sequence)
+            for (int sidx = tid; sidx < nseg; sidx += OCT_THREADS)
+                if (seq[sidx] != 0xffffffffu) {
+                    const int p = atomicAdd(&S.ctl[C_PN], 1);
+                    skey[p] = ((unsigned long long)(nst[sidx + 1] - nst[sidx]) << 32) | seq[sidx];
+                    sval[p] = (uint32_t)sidx;
+                }
+            __syncthreads();
+            const int pn = S.ctl[C_PN];
             int m = 1;
             while (m < pn) m <<= 1;
-            // gains + sort keys
-            for (int p = tid; p < m; p += OCT_THREADS) {
-                if (p < pn) {
-                    const uint32_t st = ps[p], cnt = pc[p];
-                    uint32_t g = 0;
-                    for (uint32_t i = st; i + 1 < st + cnt; ++i) g += (sd[i] == d + 1);
-                    p_gain[p] = g;
-                    skey[p] = ((unsigned long long)cnt << 32) | pq[p];
-                } else {
-                    skey[p] = 0ull;
-                }
-                sval[p] = (uint32_t)p;
-            }
-            if (tid == 0) { S.ctl[C_CUT] = 0x7fffffff; S.ctl[C_QN] = 0; }
+            for (int p = pn + tid; p < m; p += OCT_THREADS) { skey[p] = 0ull; sval[p] = 0xffffffffu; }
             __syncthreads();
             bitonic_desc(skey, sval, m);
-            // prefix sums of gains in processing order; first rank where size reaches N
+            // prefix sums of the gains in processing order; first rank at which the node count reaches N
             uint32_t carry2 = 0;
             for (int base = 0; base < pn; base += OCT_THREADS) {
                 const int r = base + tid;
-                const uint32_t g = r < pn ? p_gain[sval[r]] : 0u;
+                const uint32_t g = r < pn ? gain[sval[r]] : 0u;
                 uint32_t tot;
                 const uint32_t inc = block_excl_scan(g, S.warp_tot, &tot) + carry2 + g;
                 if (r < pn) {
@@ -288,34 +325,38 @@ k_octree(const LevelDev *__restrict__ levels, int n_levels, const int *__restric
             const bool found = cut != 0x7fffffff;
             const int nsplit = found ? cut + 1 : pn;
             const uint32_t total = nsplit > 0 ? (uint32_t)skey[nsplit - 1] : 0u;
-            // split the first nsplit nodes: new heads, and (if we go on) their expandable children
-            for (int r = tid; r < nsplit; r += OCT_THREADS) {
-                const int p = (int)sval[r];
-                const uint32_t st = ps[p], en = st + pc[p];
-                uint32_t cs = st;
-                for (uint32_t i = st; i < en; ++i) {
-                    const bool last = (i + 1 == en);
-                    if (last || sd[i] == d + 1) {
-                        if (!last) head[i + 1] = 1;
-                        const uint32_t len = i + 1 - cs;
-                        if (!found && len > 1) {
-                            const int q = atomicAdd(&S.ctl[C_QN], 1);
-                            qs[q] = cs; qc[q] = len;
-                            qq[q] = (uint32_t)r * 4u + ((ka[cs] >> (2 * (D - d - 1))) & 3u);
-                        }
-                        cs = i + 1;
-                    }
-                }
-            }
+            for (int r = tid; r < nsplit; r += OCT_THREADS) rank_of[sval[r]] = r;
+            __syncthreads();
+            // split: every depth-(d+1) parting inside a split node starts a new node
+            for (int i = tid; i < n - 1; i += OCT_THREADS)
+                if (sd[i] == d + 1 && rank_of[seg[i]] >= 0) head[i + 1] = 1;
             __syncthreads();
             if (found || total == 0) break;
-            if (tid == 0) { S.ctl[C_SIZE] = size + (int)total; S.ctl[C_PN] = S.ctl[C_QN]; }
-            uint32_t *t;
-            t = ps; ps = qs; qs = t;
-            t = pc; pc = qc; qc = t;
-            t = pq; pq = qq; qq = t;
-            ++d;
+            // next round: renumber the nodes; the new expandable ones are the children (> 1 key) of split nodes,
+            // created in processing order of their parents, n1..n4 inside a parent
+            const int nseg2 = size + (int)total;
+            uint32_t carry = 0;
+            for (int base = 0; base < n; base += OCT_THREADS) {
+                const int i = base + tid;
+                const uint32_t h = i < n ? head[i] : 0u;
+                uint32_t tot;
+                const uint32_t inc = block_excl_scan(h, S.warp_tot, &tot) + carry + h;
+                if (i < n) { seg2[i] = (uint16_t)(inc - 1); if (h) nst2[inc - 1] = (uint32_t)i; }
+                carry += tot;
+            }
+            if (tid == 0) nst2[nseg2] = (uint32_t)n;
             __syncthreads();
+            for (int s2 = tid; s2 < nseg2; s2 += OCT_THREADS) {
+                const uint32_t st = nst2[s2], cnt = nst2[s2 + 1] - st;
+                const int pr = rank_of[seg[st]];
+                seq2[s2] = (pr >= 0 && cnt > 1) ? ((uint32_t)pr * 4u + ((ka[st] >> (2 * (D - d - 1))) & 3u)) : 0xffffffffu;
+            }
+            if (tid == 0) S.ctl[C_SIZE] = nseg2;
+            __syncthreads();
+            { uint32_t *t = nst; nst = nst2; nst2 = t; t = seq; seq = seq2; seq2 = t; }
+            { uint16_t *t = seg; seg = seg2; seg2 = t; }
+            nseg = nseg2;
+            ++d;
         }
     }
 
@@ -326,31 +367,31 @@ k_octree(const LevelDev *__restrict__ levels, int n_levels, const int *__restric
         const uint32_t h = i < n ? head[i] : 0u;
         uint32_t tot;
         const uint32_t inc = block_excl_scan(h, S.warp_tot, &tot) + carry + h;
-        if (i < n) seg[i] = inc - 1;
+        if (i < n) seg_a[i] = (uint16_t)min(inc - 1, 0xffffu);
         carry += tot;
     }
     const int nfinal = min((int)carry, L.sel_cap);
-    for (int s = tid; s < nfinal; s += OCT_THREADS) best[s] = 0ull;
+    for (int sidx = tid; sidx < nfinal; sidx += OCT_THREADS) best[sidx] = 0ull;
     __syncthreads();
     for (int i = tid; i < n; i += OCT_THREADS) {
-        const uint32_t s = seg[i];
-        if (s < (uint32_t)nfinal) {
+        const uint32_t sidx = seg_a[i];
+        if (sidx < (uint32_t)nfinal) {
             const uint32_t id = ia[i], c = cand[id];
             const uint32_t xo = __ldg(&L.xord[c & 0xfffu]), yo = __ldg(&L.yord[(c >> 12) & 0xfffu]);
             const uint32_t ord = ((yo >> 6) << 19) | ((xo >> 6) << 12) | ((yo & 63u) << 6) | (xo & 63u);
             const unsigned long long v = ((unsigned long long)(c >> 24) << 48) |
                                          ((unsigned long long)(0x3ffffffu - ord) << 22) | id;
-            atomicMax(&best[s], v);
+            atomicMax(&best[sidx], v);
         }
     }
     __syncthreads();
     uint32_t *sel = L.sel + (size_t)frame * L.sel_cap;
-    for (int s = tid; s < nfinal; s += OCT_THREADS) sel[s] = cand[(uint32_t)(best[s] & 0x3fffffull)];
+    for (int sidx = tid; sidx < nfinal; sidx += OCT_THREADS) sel[sidx] = cand[(uint32_t)(best[sidx] & 0x3fffffull)];
     if (tid == 0) *out_count = nfinal;
 }
 
 size_t octree_dyn_smem(int sel_cap_max, int pcap, int pcap2) {
-    return (size_t)sel_cap_max * 8 + (size_t)pcap2 * 12 + (size_t)pcap * 4 * 7 + (size_t)(pcap + 1) * 4 + 16;
+    return (size_t)sel_cap_max * 8 + (size_t)pcap2 * 12 + (size_t)(pcap + 1) * 4 * 6 + 16;
 }
 
 cudaError_t launch_octree(const LevelDev *d_levels, int n_levels, const int *d_cand_count, int *d_sel_count,
