@@ -19,6 +19,9 @@
 //  * each final node keeps its max-response key, first in upstream candidate order on ties
 //    (64-bit shared-memory atomicMax over (response, ~order, index)).
 // Bound: latency/issue (tiny per-CTA working sets, L2 resident); not HBM.
+#include <algorithm>
+#include <cstdlib>
+
 #include "orbb_internal.cuh"
 
 namespace orbb {
@@ -159,7 +162,7 @@ __device__ __forceinline__ void bitonic_desc(unsigned long long *key, uint32_t *
     }
 }
 
-__global__ void __launch_bounds__(OCT_THREADS, 3)
+__global__ void __launch_bounds__(OCT_THREADS, 4)
 k_octree(const LevelDev *__restrict__ levels, int n_levels, const int *__restrict__ cand_count,
          int *__restrict__ sel_count, int level_base, int frame_base, int quota_override, int pcap, int pcap2) {
     __shared__ OctStatic S;
@@ -397,7 +400,8 @@ size_t octree_dyn_smem(int sel_cap_max, int pcap, int pcap2) {
 cudaError_t launch_octree(const LevelDev *d_levels, int n_levels, const int *d_cand_count, int *d_sel_count,
                           int level_base, int n_launch_levels, int frame_base, int n_frames, int quota_override,
                           int sel_cap_max, int pcap, int pcap2, cudaStream_t st) {
-    const size_t smem = octree_dyn_smem(sel_cap_max, pcap, pcap2);
+    size_t smem = octree_dyn_smem(sel_cap_max, pcap, pcap2);
+    if (getenv("ORBB_OCT_PAD")) smem = std::max(smem, (size_t)atoi(getenv("ORBB_OCT_PAD")));
     static size_t configured = 0;
     if (smem > 32 * 1024 && smem > configured) {
         cudaError_t e = cudaFuncSetAttribute(k_octree, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

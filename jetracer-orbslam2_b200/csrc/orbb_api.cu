@@ -539,8 +539,22 @@ extern "C" int orbb_extract_batch_device(orbb_handle *h, const uint8_t *d_images
     if (n_frames > h->max_batch) return ORBB_ERR_CAPACITY;
     CK(h, cudaSetDevice(h->device));
     h->n_frames_last = n_frames;
-    return run_all(h, d_images, pitch, frame_stride, 0, n_frames, d_kp, d_desc, d_counts, max_kp,
-                   static_cast<cudaStream_t>(stream), h->s_side, h->ev_fork, h->ev_join);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (n_frames < 64)
+        return run_all(h, d_images, pitch, frame_stride, 0, n_frames, d_kp, d_desc, d_counts, max_kp, st, h->s_side,
+                       h->ev_fork, h->ev_join);
+    // Large batches: two halves on two streams.  FAST saturates the issue slots while the quadtree kernel is
+    // latency bound, so the halves interleave (one half's quadtree runs under the other half's FAST).
+    const int na = n_frames / 2, nb = n_frames - na;
+    CK(h, cudaEventRecord(h->ev_fence, st));
+    CK(h, cudaStreamWaitEvent(h->s_comp[0], h->ev_fence, 0));
+    int rc = run_all(h, d_images, pitch, frame_stride, 0, na, d_kp, d_desc, d_counts, max_kp, st);
+    if (rc) return rc;
+    rc = run_all(h, d_images + frame_stride * na, pitch, frame_stride, na, nb, d_kp, d_desc, d_counts, max_kp, h->s_comp[0]);
+    if (rc) return rc;
+    CK(h, cudaEventRecord(h->ev_join, h->s_comp[0]));
+    CK(h, cudaStreamWaitEvent(st, h->ev_join, 0));
+    return ORBB_OK;
 }
 
 // Host entry points: chunks of the batch flow through the handle's streams (H2D copy stream -> two alternating
