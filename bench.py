@@ -38,7 +38,9 @@ N_INPUT_SETS = 2          # rotate over 2 resident batches: 2 x 78.6 MB of input
 MAP_SIZE = 50_000
 LEVEL_PIXELS = 950_532    # sum_l w_l*h_l for 640x480, 8 levels, 1.2
 BYTES_PER_FRAME = W * H + 2 * LEVEL_PIXELS + 60 * NFEAT  # 2,268,264 B
-KERNELS_PER_STEP = 12     # level0, 7 x resize, fast, octree, blur, angle_orb
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE k_fast_cells launch over 256 frames, from the committed
+# ncu --set full capture profiles/r01_k_fast_cells_full.txt (270.7 MB + 19.0 MB)
+FAST_DRAM_TRAFFIC_256 = 289.7e6
 
 
 def measured_peaks():
@@ -137,7 +139,7 @@ def run_reference(args):
         native = True
     except Exception:
         O.build()
-    per_step = max(cores, 8)
+    per_step = max(4 * cores, 16)
     frames = make_frames(per_step, 5000)
     for _ in range(args.warmup):
         O.extract_many(frames, NFEAT, SCALE, NLEVELS, INI_TH, MIN_TH, threads=cores, native=native)
@@ -245,10 +247,12 @@ def main():
     sampler = ClockSampler(local_rank)
     sampler.start()
     v0, v1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    launches0 = ex.launch_count()
     v0.record(st)
     for i in range(args.steps):
         dev_step(i)
     v1.record(st)
+    gpu_launches = ex.launch_count() - launches0
     sync_all()
     sampler.stop_flag = True
     sampler.join()
@@ -386,9 +390,11 @@ def main():
                     "api": "orbb_extract_batch_host_async + orbb_wait, double-buffered (2 batches in flight)",
                     "sync_api_value": frames_total / (e2e_sync_ms * 1e-3), "pcie_h2d_gbs": h2d_gbs,
                     "h2d_bound_fps": world * h2d_gbs * 1e9 / (W * H)},
-            "gpu_launches": KERNELS_PER_STEP * args.steps,
+            "gpu_launches": gpu_launches,
             "roofline": {"bound": "hbm", "kernel": "k_fast_cells", "achieved": achieved, "peak": hbm_peak,
-                         "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": None, "peak_kind": peak_kind,
+                         "unit": "GB/s", "frac": achieved / hbm_peak,
+                         "traffic": FAST_DRAM_TRAFFIC_256 * B / 256.0, "algorithmic_bytes": fast_bytes,
+                         "peak_kind": peak_kind,
                          "note": "issue/shared-memory bound integer kernel; HBM fraction reported honestly"},
             "step_roofline": {"bytes_per_frame": BYTES_PER_FRAME, "achieved_gbs": BYTES_PER_FRAME * fps / world / 1e9,
                               "frac_of_hbm": BYTES_PER_FRAME * fps / world / 1e9 / hbm_peak},

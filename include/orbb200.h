@@ -85,6 +85,8 @@ int orbb_get_scale_factors(const orbb_handle *h, float *scale, float *inv_scale,
                            float *inv_sigma2);
 int orbb_get_features_per_level(const orbb_handle *h, int32_t *nfeat);
 int orbb_max_keypoints_per_frame(const orbb_handle *h); /* capacity to allocate per frame */
+/* number of CUDA kernels this handle has launched so far (bench.py reports it as gpu_launches) */
+long long orbb_get_launch_count(const orbb_handle *h);
 /* mvImagePyramid[level] of frame `frame` in the last batch (device pointers into the handle) */
 int orbb_get_level(const orbb_handle *h, int frame, int level, orbb_level *out);
 

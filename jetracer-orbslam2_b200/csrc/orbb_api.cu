@@ -62,6 +62,7 @@ struct orbb_handle {
     int *d_counts2[2] = {nullptr, nullptr};
     cudaEvent_t ev_ticket[2] = {nullptr, nullptr}, ev_tail[2] = {nullptr, nullptr};
     long long n_submitted = 0;
+    long long n_launches = 0;  // kernels launched (not memsets/copies)
     uint8_t *d_dump = nullptr;
     long long *d_dump_off = nullptr;
     std::vector<long long> dump_off;
@@ -429,6 +430,8 @@ extern "C" int orbb_get_features_per_level(const orbb_handle *h, int32_t *nfeat)
 
 extern "C" int orbb_max_keypoints_per_frame(const orbb_handle *h) { return h ? h->max_kp : ORBB_ERR_INVALID; }
 
+extern "C" long long orbb_get_launch_count(const orbb_handle *h) { return h ? h->n_launches : -1; }
+
 extern "C" int orbb_get_level(const orbb_handle *h, int frame, int level, orbb_level *out) {
     if (!h || !out || level < 0 || level >= h->nlevels || frame < 0 || frame >= h->max_batch) return ORBB_ERR_INVALID;
     const LevelDev &L = h->lv[level];
@@ -445,29 +448,35 @@ extern "C" int orbb_get_level(const orbb_handle *h, int frame, int level, orbb_l
 static int run_upload(orbb_handle *h, const uint8_t *d_images, size_t pitch, size_t stride, int f0, int n, cudaStream_t st) {
     CK(h, cudaMemsetAsync(h->d_cand_count + (size_t)f0 * h->nlevels, 0, sizeof(int) * (size_t)n * h->nlevels, st));
     CK(h, launch_level0(d_images, pitch, stride, h->lv[0], f0, n, st));
+    h->n_launches += 1;
     return ORBB_OK;
 }
 static int run_pyramid(orbb_handle *h, int f0, int n, cudaStream_t st) {
     for (int l = 1; l < h->nlevels; ++l) CK(h, launch_resize(h->d_levels, h->lv, l, f0, n, st));
+    h->n_launches += h->nlevels - 1;
     return ORBB_OK;
 }
 static int run_fast(orbb_handle *h, int f0, int n, cudaStream_t st) {
     CK(h, launch_fast(h->d_levels, h->d_cells, h->n_cells, h->nlevels, h->d_cand_count, h->t_lo, h->t_hi, h->fcfg, f0, n, st));
+    h->n_launches += 1;
     return ORBB_OK;
 }
 static int run_distribute(orbb_handle *h, int f0, int n, cudaStream_t st) {
     CK(h, launch_octree(h->d_levels, h->nlevels, h->d_cand_count, h->d_sel_count, 0, h->nlevels, f0, n, -1,
                         h->sel_cap_max, h->pcap, h->pcap2, st));
+    h->n_launches += 1;
     return ORBB_OK;
 }
 static int run_blur(orbb_handle *h, int f0, int n, cudaStream_t st) {
     CK(h, launch_blur(h->d_levels, h->lv, h->nlevels, f0, n, st));
+    h->n_launches += 1;
     return ORBB_OK;
 }
 static int run_angle_orb(orbb_handle *h, int f0, int n, orbb_keypoint *d_kp, uint8_t *d_desc, int32_t *d_counts, int max_kp,
                          cudaStream_t st) {
     CK(h, launch_angle_orb(h->d_levels, h->nlevels, h->d_sel_count, h->d_pattern, h->d_slot_level, h->d_slot_base,
                            h->n_slots, f0, n, d_kp, d_desc, d_counts, max_kp, st));
+    h->n_launches += 1;
     return ORBB_OK;
 }
 static int run_all(orbb_handle *h, const uint8_t *d_images, size_t pitch, size_t stride, int f0, int n, orbb_keypoint *d_kp,
@@ -668,6 +677,7 @@ extern "C" int orbb_match_knn(orbb_handle *h, const uint8_t *d_query, int nq, co
     if (rc) return rc;
     CK(h, launch_match(d_query, d_train, nullptr, nullptr, 1, nq, nq, nt, n_split, h->d_partial, nq, k, ratio, d_idx,
                        d_dist, d_accept, d_naccept, static_cast<cudaStream_t>(stream)));
+    h->n_launches += 2;
     return ORBB_OK;
 }
 
@@ -690,6 +700,7 @@ extern "C" int orbb_match_knn_segmented(orbb_handle *h, const uint8_t *d_query, 
     if (rc) return rc;
     CK(h, launch_match(d_query, d_train, d_q_offsets, d_t_offsets, nseg, nq_total, max_q_per_seg, 0, n_split,
                        h->d_partial, nq_total, k, ratio, d_idx, d_dist, d_accept, nullptr, st));
+    h->n_launches += 2;
     return ORBB_OK;
 }
 

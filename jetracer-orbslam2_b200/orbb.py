@@ -28,7 +28,8 @@ KEYPOINT_DTYPE = np.dtype(
 
 EXPORTS = [
     "orbb_create", "orbb_destroy", "orbb_strerror", "orbb_last_cuda_error", "orbb_get_levels",
-    "orbb_get_scale_factors", "orbb_get_features_per_level", "orbb_max_keypoints_per_frame", "orbb_get_level",
+    "orbb_get_scale_factors", "orbb_get_features_per_level", "orbb_max_keypoints_per_frame",
+    "orbb_get_launch_count", "orbb_get_level",
     "orbb_extract_batch_device", "orbb_extract_batch_host", "orbb_extract_batch_host_async", "orbb_wait",
     "orbb_stage_upload", "orbb_pyramid_create_levels",
     "orbb_detect", "orbb_detect_fast", "orbb_detect_distribute", "orbb_gaussian_blur", "orbb_compute_angle_and_orb", "orbb_match_knn",
@@ -75,6 +76,7 @@ def load_library():
     L.orbb_get_scale_factors.argtypes = [vp, vp, vp, vp, vp]
     L.orbb_get_features_per_level.argtypes = [vp, vp]
     L.orbb_max_keypoints_per_frame.argtypes = [vp]
+    L.orbb_get_launch_count.argtypes = [vp]
     L.orbb_get_level.argtypes = [vp, i32, i32, C.POINTER(Level)]
     L.orbb_extract_batch_device.argtypes = [vp, vp, sz, sz, i32, vp, vp, vp, i32, vp]
     L.orbb_extract_batch_host.argtypes = [vp, vp, sz, sz, i32, vp, vp, vp, i32, vp]
@@ -97,8 +99,9 @@ def load_library():
     L.orbb_debug_distribute.argtypes = [vp, i32, vp, i32, i32, vp, i32]
     for name in EXPORTS:
         fn = getattr(L, name)
-        if name not in ("orbb_strerror", "orbb_last_cuda_error"):
+        if name not in ("orbb_strerror", "orbb_last_cuda_error", "orbb_get_launch_count"):
             fn.restype = C.c_int
+    L.orbb_get_launch_count.restype = C.c_longlong
     _lib = L
     return L
 
@@ -187,6 +190,9 @@ class ORBextractor:
 
     def GetInverseScaleSigmaSquares(self):
         return self._inv_sigma2.copy()
+
+    def launch_count(self) -> int:
+        return int(self._lib.orbb_get_launch_count(self._h))
 
     def level_info(self, level: int, frame: int = 0) -> Level:
         out = Level()
