@@ -18,11 +18,17 @@
 // cell came out empty -- upstream's FAST(iniTh) -> FAST(minTh) fallback, decided after NMS.
 // No score map ever goes to HBM (the DUMP instantiation exists only for the parity tests).
 // Bound: SM issue slots / shared-memory bandwidth, not HBM.
+#include <cuda.h>
+
 #include "orbb_internal.cuh"
 
 namespace orbb {
 
 #define FAST_WARPS 4
+
+// one tensor map per pyramid level (array in device global memory): 3-D u8 tensor (row bytes, rows, frames),
+// box = one cell window
+struct TmaMaps { CUtensorMap m[ORBB_MAX_LEVELS]; };
 
 __device__ __forceinline__ int min3(int a, int b, int c) { return __vimin3_s32(a, b, c); }
 __device__ __forceinline__ int max3(int a, int b, int c) { return __vimax3_s32(a, b, c); }
@@ -55,12 +61,12 @@ __device__ __forceinline__ int arc_score(const uint8_t *p, int tp) {
     return (int)max(best & 0xffffu, best >> 16) - 256;
 }
 
-template <bool DUMP>
+template <bool DUMP, bool TMA>
 __global__ void __launch_bounds__(FAST_WARPS * 32)
-k_fast_cells(const LevelDev *__restrict__ levels, const CellEntry *__restrict__ cells, int n_cells, int n_levels,
+k_fast_cells(const CUtensorMap *__restrict__ maps, const LevelDev *__restrict__ levels, const CellEntry *__restrict__ cells, int n_cells, int n_levels,
              int *__restrict__ cand_count, int t_lo, int t_hi, FastSmemCfg cfg, int frame_base,
              uint8_t *__restrict__ dump, const long long *__restrict__ dump_off) {
-    extern __shared__ __align__(16) uint8_t smem[];
+    extern __shared__ __align__(128) uint8_t smem[];  // 128-byte aligned: TMA destination
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int cell_id = blockIdx.x * FAST_WARPS + warp;
     if (cell_id >= n_cells) return;
@@ -69,17 +75,44 @@ k_fast_cells(const LevelDev *__restrict__ levels, const CellEntry *__restrict__ 
     const LevelDev &L = levels[c.level];
 
     uint8_t *tile = smem + (size_t)warp * cfg.warp_bytes;
-    uint8_t *score = tile + cfg.tile_pitch * cfg.tile_rows;
+    uint8_t *score = tile + max(cfg.tile_pitch, cfg.tma_pitch) * cfg.tile_rows;
     uint16_t *queue = reinterpret_cast<uint16_t *>(score + cfg.score_pitch * cfg.score_rows);
-    const int tp = cfg.tile_pitch, sp = cfg.score_pitch, tpw = tp >> 2;
+    const int tp = TMA ? cfg.tma_pitch : cfg.tile_pitch, sp = cfg.score_pitch, tpw = tp >> 2;
     const int cw = c.cw, ch = c.ch;
     const uint32_t *tile32 = reinterpret_cast<const uint32_t *>(tile);
 
     // ---- stage the window, RE-ALIGNED: shared-memory byte column k <-> image column x0 - 4 + k, so the
     // cell's first tested pixel sits at byte 4 of each row and groups of 4 pixels are whole 32-bit words.
     // Global loads stay aligned (ROI rows are 16-byte aligned); a funnel shift moves the bytes into place.
-    const int off = 4;  // tested pixel x lives at tile byte column x + off
-    {
+    // tested pixel x lives at tile byte column x + off.  Manual staging re-aligns (off = 4); the TMA box must
+    // start on a 16-byte boundary, so its rows keep a byte phase of (x0 - 4) & 15 that phase 1 absorbs.
+    const int off = TMA ? 4 + ((c.x0 - 4) & 15) : 4;
+    if (TMA) {
+        // One bulk-tensor copy per cell: the TMA unit fetches the (box_w x box_h) window at byte column
+        // ROI_X0 + x0 - 4 of padded row BORDER + y0 - 3 straight into shared memory (no registers, no per-lane
+        // address math, arbitrary byte phase), and signals the warp's mbarrier with the byte count.
+        __shared__ __align__(8) unsigned long long s_bar[FAST_WARPS];
+        const unsigned bar = (unsigned)__cvta_generic_to_shared(&s_bar[warp]);
+        const unsigned dst = (unsigned)__cvta_generic_to_shared(tile);
+        if (lane == 0) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            // the tensor maps live in global memory and were written by the host (cudaMemcpy): acquire them for
+            // the tensormap proxy before the first use in this warp
+            asm volatile("fence.proxy.tensormap::generic.acquire.sys [%0], 128;" ::"l"(maps + c.level) : "memory");
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(tp * cfg.tile_rows) : "memory");
+            asm volatile(
+                "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                ::"r"(dst), "l"(maps + c.level), "r"((ORBB_ROI_X0 + c.x0 - 4) & ~15), "r"(ORBB_BORDER + c.y0 - 3), "r"(frame), "r"(bar)
+                : "memory");
+        }
+        for (int i = lane; i < (sp * cfg.score_rows) >> 2; i += 32) reinterpret_cast<uint32_t *>(score)[i] = 0;
+        __syncwarp();
+        unsigned done = 0;
+        while (!done)
+            asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0; selp.u32 %0, 1, 0, p; }"
+                         : "=r"(done) : "r"(bar) : "memory");
+    } else {
         const int gx = c.x0 - 4, xa = gx & ~3, sh = (gx - xa) * 8;
         const int nwords = (cw + 7 + 3) >> 2;
         const uint8_t *roi = L.img + (size_t)frame * L.frame_stride + (size_t)ORBB_BORDER * L.pitch + ORBB_ROI_X0;
@@ -130,11 +163,26 @@ k_fast_cells(const LevelDev *__restrict__ levels, const CellEntry *__restrict__ 
             int pix0 = 0;
             if (u < nunits) {
                 const int y = (int)(((unsigned)u * inv_nux) >> 20), j = u - y * nux;
-                const uint32_t *row = tile32 + (y + 3) * tpw + j;  // row[0]=left word, row[1]=centre, row[2]=right
-                const unsigned cc = row[1];
-                const unsigned a0 = __vabsdiffu4(row[1 + 3 * tpw], cc), a8 = __vabsdiffu4(row[1 - 3 * tpw], cc);
-                const unsigned a4 = __vabsdiffu4(__funnelshift_r(cc, row[2], 24), cc);
-                const unsigned a12 = __vabsdiffu4(__funnelshift_r(row[0], cc, 8), cc);
+                unsigned cc, up, dn, lf, rt;
+                if (TMA) {  // arbitrary byte phase: every 4-pixel window is a funnel shift of two words
+                    const int bc = off + 4 * j;  // byte column of the unit's first pixel
+                    const uint32_t *r0 = tile32 + (y + 3) * tpw;
+                    const int wc = bc >> 2, sc = (bc & 3) * 8;
+                    cc = __funnelshift_r(r0[wc], r0[wc + 1], sc);
+                    up = __funnelshift_r(r0[wc - 3 * tpw], r0[wc + 1 - 3 * tpw], sc);
+                    dn = __funnelshift_r(r0[wc + 3 * tpw], r0[wc + 1 + 3 * tpw], sc);
+                    const int bl = bc - 3, br = bc + 3;
+                    lf = __funnelshift_r(r0[bl >> 2], r0[(bl >> 2) + 1], (bl & 3) * 8);
+                    rt = __funnelshift_r(r0[br >> 2], r0[(br >> 2) + 1], (br & 3) * 8);
+                } else {
+                    const uint32_t *row = tile32 + (y + 3) * tpw + j;  // row[0]=left word, row[1]=centre, row[2]=right
+                    cc = row[1];
+                    dn = row[1 + 3 * tpw]; up = row[1 - 3 * tpw];
+                    rt = __funnelshift_r(cc, row[2], 24);
+                    lf = __funnelshift_r(row[0], cc, 8);
+                }
+                const unsigned a0 = __vabsdiffu4(dn, cc), a8 = __vabsdiffu4(up, cc);
+                const unsigned a4 = __vabsdiffu4(rt, cc), a12 = __vabsdiffu4(lf, cc);
                 const unsigned x0 = ((a0 >> 1) & 0x7f7f7f7fu) + kadd, x8 = ((a8 >> 1) & 0x7f7f7f7fu) + kadd;
                 const unsigned x4 = ((a4 >> 1) & 0x7f7f7f7fu) + kadd, x12 = ((a12 >> 1) & 0x7f7f7f7fu) + kadd;
                 const int nvalid = cw - 4 * j;
@@ -235,33 +283,71 @@ k_fast_cells(const LevelDev *__restrict__ levels, const CellEntry *__restrict__ 
     }
 }
 
-cudaError_t launch_fast(const LevelDev *d_levels, const CellEntry *d_cells, int n_cells, int n_levels,
-                        int *d_cand_count, int t_lo, int t_hi, const FastSmemCfg &cfg, int frame_base,
-                        int n_frames, cudaStream_t st) {
+template <bool DUMP, bool TMA>
+static cudaError_t launch_fast_t(const CUtensorMap *maps, const LevelDev *d_levels, const CellEntry *d_cells, int n_cells,
+                                 int n_levels, int *d_cand_count, int t_lo, int t_hi, const FastSmemCfg &cfg,
+                                 int frame_base, int n_frames, uint8_t *d_dump, const long long *d_dump_off,
+                                 cudaStream_t st) {
     dim3 grid((n_cells + FAST_WARPS - 1) / FAST_WARPS, n_frames);
     const size_t smem = (size_t)cfg.warp_bytes * FAST_WARPS;
     if (smem > 48 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(k_fast_cells<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(k_fast_cells<DUMP, TMA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
     }
-    k_fast_cells<false><<<grid, FAST_WARPS * 32, smem, st>>>(d_levels, d_cells, n_cells, n_levels, d_cand_count,
-                                                            t_lo, t_hi, cfg, frame_base, nullptr, nullptr);
+    k_fast_cells<DUMP, TMA><<<grid, FAST_WARPS * 32, smem, st>>>(maps, d_levels, d_cells, n_cells, n_levels, d_cand_count,
+                                                                  t_lo, t_hi, cfg, frame_base, d_dump, d_dump_off);
     return cudaGetLastError();
 }
 
-// parity-test variant: one frame, dumps the per-pixel score (m > t_lo ? m : 0) of every cell
-cudaError_t launch_fast_dump(const LevelDev *d_levels, const CellEntry *d_cells, int n_cells, int n_levels, int t_lo,
-                             int t_hi, const FastSmemCfg &cfg, int frame, uint8_t *d_dump,
-                             const long long *d_dump_off, cudaStream_t st) {
-    dim3 grid((n_cells + FAST_WARPS - 1) / FAST_WARPS, 1);
-    const size_t smem = (size_t)cfg.warp_bytes * FAST_WARPS;
-    if (smem > 48 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(k_fast_cells<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-    }
-    k_fast_cells<true><<<grid, FAST_WARPS * 32, smem, st>>>(d_levels, d_cells, n_cells, n_levels, nullptr, t_lo, t_hi,
-                                                           cfg, frame, d_dump, d_dump_off);
-    return cudaGetLastError();
+cudaError_t launch_fast(const void *tma_maps, const LevelDev *d_levels, const CellEntry *d_cells, int n_cells,
+                        int n_levels, int *d_cand_count, int t_lo, int t_hi, const FastSmemCfg &cfg, int frame_base,
+                        int n_frames, cudaStream_t st) {
+    if (tma_maps)
+        return launch_fast_t<false, true>(static_cast<const CUtensorMap *>(tma_maps), d_levels, d_cells, n_cells, n_levels,
+                                          d_cand_count, t_lo, t_hi, cfg, frame_base, n_frames, nullptr, nullptr, st);
+    return launch_fast_t<false, false>(nullptr, d_levels, d_cells, n_cells, n_levels, d_cand_count, t_lo, t_hi, cfg,
+                                       frame_base, n_frames, nullptr, nullptr, st);
 }
+
+// parity-test variant: one frame, dumps the per-pixel score (m > t_lo ? m : 0) of every cell
+cudaError_t launch_fast_dump(const void *tma_maps, const LevelDev *d_levels, const CellEntry *d_cells, int n_cells,
+                             int n_levels, int t_lo, int t_hi, const FastSmemCfg &cfg, int frame, uint8_t *d_dump,
+                             const long long *d_dump_off, cudaStream_t st) {
+    if (tma_maps)
+        return launch_fast_t<true, true>(static_cast<const CUtensorMap *>(tma_maps), d_levels, d_cells, n_cells, n_levels,
+                                         nullptr, t_lo, t_hi, cfg, frame, 1, d_dump, d_dump_off, st);
+    return launch_fast_t<true, false>(nullptr, d_levels, d_cells, n_cells, n_levels, nullptr, t_lo, t_hi, cfg, frame, 1,
+                                      d_dump, d_dump_off, st);
+}
+
+// Build the per-level tensor maps (driver entry point fetched through the runtime: no -lcuda needed).
+// Returns false when the driver cannot encode them; the caller then uses the manual staging path.
+bool build_fast_tma_maps(void *out_maps, const LevelDev *h_levels, int n_levels, int max_batch, const FastSmemCfg &cfg) {
+    typedef CUresult (*EncodeFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                 const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                 CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    void *fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn ||
+        qres != cudaDriverEntryPointSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    TmaMaps *maps = static_cast<TmaMaps *>(out_maps);
+    for (int l = 0; l < n_levels; ++l) {
+        const LevelDev &L = h_levels[l];
+        const cuuint64_t dims[3] = {(cuuint64_t)L.pitch, (cuuint64_t)L.rows, (cuuint64_t)max_batch};
+        const cuuint64_t strides[2] = {(cuuint64_t)L.pitch, (cuuint64_t)L.frame_stride};
+        const cuuint32_t box[3] = {(cuuint32_t)cfg.tma_pitch, (cuuint32_t)cfg.tile_rows, 1u};
+        const cuuint32_t estr[3] = {1u, 1u, 1u};
+        const CUresult r = reinterpret_cast<EncodeFn>(fn)(&maps->m[l], CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, L.img, dims, strides,
+                                                           box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                                           CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return false;
+    }
+    return true;
+}
+
+size_t fast_tma_maps_bytes() { return sizeof(TmaMaps); }
 
 }  // namespace orbb

@@ -6,6 +6,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <vector>
@@ -16,9 +17,11 @@ namespace orbb {
 cudaError_t launch_level0(const uint8_t *, size_t, size_t, const LevelDev &, int, int, cudaStream_t);
 cudaError_t launch_resize(const LevelDev *, const LevelDev *, int, int, int, cudaStream_t);
 cudaError_t launch_blur(const LevelDev *, const LevelDev *, int, int, int, cudaStream_t);
-cudaError_t launch_fast(const LevelDev *, const CellEntry *, int, int, int *, int, int, const FastSmemCfg &, int, int,
-                        cudaStream_t);
-cudaError_t launch_fast_dump(const LevelDev *, const CellEntry *, int, int, int, int, const FastSmemCfg &, int,
+cudaError_t launch_fast(const void *, const LevelDev *, const CellEntry *, int, int, int *, int, int, const FastSmemCfg &,
+                        int, int, cudaStream_t);
+bool build_fast_tma_maps(void *, const LevelDev *, int, int, const FastSmemCfg &);
+size_t fast_tma_maps_bytes();
+cudaError_t launch_fast_dump(const void *, const LevelDev *, const CellEntry *, int, int, int, int, const FastSmemCfg &, int,
                              uint8_t *, const long long *, cudaStream_t);
 cudaError_t launch_octree(const LevelDev *, int, const int *, int *, int, int, int, int, int, int, int, int,
                           cudaStream_t);
@@ -48,6 +51,7 @@ struct orbb_handle {
     TileEntry *d_tiles = nullptr;
     int n_tiles = 0;
     FastSmemCfg fcfg{};
+    void *tma_maps = nullptr;  // DEVICE array of CUtensorMap, one per level (nullptr: FAST stages manually)
     int t_lo = 7, t_hi = 20;
     int *d_cand_count = nullptr, *d_sel_count = nullptr;
     int8_t *d_pattern = nullptr;
@@ -355,12 +359,28 @@ extern "C" int orbb_create(orbb_handle **out, const orbb_params *params, int wid
     while (h->pcap2 < h->pcap) h->pcap2 <<= 1;
     if (octree_dyn_smem(h->sel_cap_max, h->pcap, h->pcap2) > 200 * 1024) { orbb_destroy(h); return ORBB_ERR_CAPACITY; }
     h->fcfg.tile_pitch = (int)round_up(max_cw + 12, 4);
+    h->fcfg.tma_pitch = (int)round_up(max_cw + 10 + 15 + 4, 16);  // 16-byte aligned box start: up to 15 bytes of phase
     h->fcfg.tile_rows = max_ch + 6;
     h->fcfg.score_pitch = (int)round_up(max_cw + 2, 4);
     h->fcfg.score_rows = max_ch + 2;
     h->fcfg.queue_len = (int)round_up((size_t)max_cw * max_ch, 8);
-    h->fcfg.warp_bytes = (int)round_up((size_t)h->fcfg.tile_pitch * h->fcfg.tile_rows +
-                                           (size_t)h->fcfg.score_pitch * h->fcfg.score_rows + 2 * (size_t)h->fcfg.queue_len, 16);
+    // TMA staging of the FAST windows is opt-in (ORBB_FAST_TMA=1): measured on B200 it is not faster than the
+    // manual aligned-load + funnel-shift staging (0.70 vs 0.66 ms per 256 frames; the 16-byte aligned box costs
+    // 1.4 KB more shared memory per warp), see DESIGN.md.
+    const bool want_tma = getenv("ORBB_FAST_TMA") && atoi(getenv("ORBB_FAST_TMA")) != 0;
+    if (!want_tma) h->fcfg.tma_pitch = 0;
+    h->fcfg.warp_bytes = (int)round_up((size_t)std::max(h->fcfg.tile_pitch, h->fcfg.tma_pitch) * h->fcfg.tile_rows +
+                                           (size_t)h->fcfg.score_pitch * h->fcfg.score_rows + 2 * (size_t)h->fcfg.queue_len, 128);  // 128-byte aligned TMA destination per warp
+    if (want_tma && h->fcfg.tma_pitch <= 256 && h->fcfg.tile_rows <= 256) {
+        std::vector<unsigned char> store(fast_tma_maps_bytes() + 128);
+        void *hm = reinterpret_cast<void *>((reinterpret_cast<uintptr_t>(store.data()) + 63) & ~(uintptr_t)63);
+        if (build_fast_tma_maps(hm, h->lv, nl, B, h->fcfg)) {
+            unsigned char *dm = nullptr;
+            CKC(dalloc(h, &dm, fast_tma_maps_bytes()));
+            CKC(cudaMemcpy(dm, hm, fast_tma_maps_bytes(), cudaMemcpyHostToDevice));
+            h->tma_maps = dm;
+        }
+    }
     CKC(upload(h, &h->d_cells, cells));
     CKC(upload(h, &h->d_tiles, tiles));
     CKC(upload(h, &h->d_slot_level, slot_level));
@@ -457,7 +477,7 @@ static int run_pyramid(orbb_handle *h, int f0, int n, cudaStream_t st) {
     return ORBB_OK;
 }
 static int run_fast(orbb_handle *h, int f0, int n, cudaStream_t st) {
-    CK(h, launch_fast(h->d_levels, h->d_cells, h->n_cells, h->nlevels, h->d_cand_count, h->t_lo, h->t_hi, h->fcfg, f0, n, st));
+    CK(h, launch_fast(h->tma_maps, h->d_levels, h->d_cells, h->n_cells, h->nlevels, h->d_cand_count, h->t_lo, h->t_hi, h->fcfg, f0, n, st));
     h->n_launches += 1;
     return ORBB_OK;
 }
@@ -726,7 +746,7 @@ extern "C" int orbb_debug_get_scores(orbb_handle *h, int frame, int level, uint8
     if (!h || !host_out || level < 0 || level >= h->nlevels || frame < 0 || frame >= h->max_batch) return ORBB_ERR_INVALID;
     const LevelDev &L = h->lv[level];
     CK(h, cudaMemset(h->d_dump, 0, (size_t)h->dump_off[h->nlevels]));
-    CK(h, launch_fast_dump(h->d_levels, h->d_cells, h->n_cells, h->nlevels, h->t_lo, h->t_hi, h->fcfg, frame, h->d_dump,
+    CK(h, launch_fast_dump(h->tma_maps, h->d_levels, h->d_cells, h->n_cells, h->nlevels, h->t_lo, h->t_hi, h->fcfg, frame, h->d_dump,
                            h->d_dump_off, 0));
     CK(h, cudaDeviceSynchronize());
     CK(h, cudaMemcpy(host_out, h->d_dump + h->dump_off[level], (size_t)L.w * L.h, cudaMemcpyDeviceToHost));

@@ -57,7 +57,8 @@ struct TileEntry {  // generic 2-D tile of a level (blur kernel)
 };
 
 struct FastSmemCfg {
-    int tile_pitch, tile_rows;    // bytes, rows of the per-warp image tile
+    int tile_pitch, tile_rows;    // bytes, rows of the per-warp image tile (manual staging)
+    int tma_pitch;                // row bytes of the TMA box (16-byte aligned start => up to 15 bytes of phase)
     int score_pitch, score_rows;  // per-warp score tile (1-px zero frame)
     int queue_len;                // u16 entries
     int warp_bytes;               // total per warp (multiple of 16)
