@@ -596,9 +596,12 @@ extern "C" int orbb_wait(orbb_handle *h, int ticket) {
     return ORBB_OK;
 }
 
-extern "C" int orbb_extract_batch_host_async(orbb_handle *h, const uint8_t *h_images, size_t pitch, size_t frame_stride,
-                                             int n_frames, orbb_keypoint *h_kp, uint8_t *h_desc, int32_t *h_counts,
-                                             int max_kp, void *stream) {
+// latency_mode: chunk sizes grow 16, 32, 64, 64, ... so the first H2D (which nothing in a lone batch can hide)
+// stays short.  Throughput mode (async API, batches back to back): two half-batch chunks -- the next batch's H2D
+// already runs under this batch's kernels, and large chunks keep every kernel's grid full.
+static int submit_host(orbb_handle *h, const uint8_t *h_images, size_t pitch, size_t frame_stride, int n_frames,
+                       orbb_keypoint *h_kp, uint8_t *h_desc, int32_t *h_counts, int max_kp, void *stream,
+                       bool latency_mode) {
     if (!h || !h_images || !h_kp || !h_desc || !h_counts || max_kp < 1 || pitch < (size_t)h->w) return ORBB_ERR_INVALID;
     if (n_frames < 1 || n_frames > h->max_batch) return ORBB_ERR_CAPACITY;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -620,8 +623,7 @@ extern "C" int orbb_extract_batch_host_async(orbb_handle *h, const uint8_t *h_im
         CK(h, cudaStreamWaitEvent(h->s_comp[i], h->ev_fence, 0));
         if (ticket >= 1) CK(h, cudaStreamWaitEvent(h->s_comp[i], h->ev_tail[i ^ 1], 0));
     }
-    // chunk sizes grow 16, 32, 64, 64, ...: the first H2D (which nothing in this batch can hide) stays short
-    int per = n_frames <= 32 ? n_frames : 16;
+    int per = n_frames <= 32 ? n_frames : (latency_mode ? 16 : (n_frames + 1) / 2);
     for (int c = 0, f0 = 0; f0 < n_frames; ++c) {
         int n = std::min(per, n_frames - f0);
         if (c == ORBB_MAX_CHUNKS - 1) n = n_frames - f0;
@@ -649,7 +651,7 @@ extern "C" int orbb_extract_batch_host_async(orbb_handle *h, const uint8_t *h_im
         CK(h, cudaMemcpy2DAsync(h_desc + 32 * (size_t)f0 * max_kp, 32 * (size_t)max_kp, d_desc + 32 * (size_t)f0 * mk,
                                 32 * (size_t)mk, 32 * (size_t)mk, n, cudaMemcpyDeviceToHost, h->s_out));
         f0 += n;
-        per = std::min(per * 2, 64);
+        if (latency_mode) per = std::min(per * 2, 64);
     }
     CK(h, cudaEventRecord(h->ev_tail[0], h->s_comp[0]));
     CK(h, cudaEventRecord(h->ev_tail[1], h->s_comp[1]));
@@ -660,11 +662,16 @@ extern "C" int orbb_extract_batch_host_async(orbb_handle *h, const uint8_t *h_im
     return ticket;
 }
 
+extern "C" int orbb_extract_batch_host_async(orbb_handle *h, const uint8_t *h_images, size_t pitch, size_t frame_stride,
+                                             int n_frames, orbb_keypoint *h_kp, uint8_t *h_desc, int32_t *h_counts,
+                                             int max_kp, void *stream) {
+    return submit_host(h, h_images, pitch, frame_stride, n_frames, h_kp, h_desc, h_counts, max_kp, stream, false);
+}
+
 extern "C" int orbb_extract_batch_host(orbb_handle *h, const uint8_t *h_images, size_t pitch, size_t frame_stride,
                                        int n_frames, orbb_keypoint *h_kp, uint8_t *h_desc, int32_t *h_counts,
                                        int max_kp, void *stream) {
-    const int ticket = orbb_extract_batch_host_async(h, h_images, pitch, frame_stride, n_frames, h_kp, h_desc, h_counts,
-                                                     max_kp, stream);
+    const int ticket = submit_host(h, h_images, pitch, frame_stride, n_frames, h_kp, h_desc, h_counts, max_kp, stream, true);
     if (ticket < 0) return ticket;
     return orbb_wait(h, ticket);
 }
