@@ -38,9 +38,9 @@ N_INPUT_SETS = 2          # rotate over 2 resident batches: 2 x 78.6 MB of input
 MAP_SIZE = 50_000
 LEVEL_PIXELS = 950_532    # sum_l w_l*h_l for 640x480, 8 levels, 1.2
 BYTES_PER_FRAME = W * H + 2 * LEVEL_PIXELS + 60 * NFEAT  # 2,268,264 B
-# dram__bytes_read.sum + dram__bytes_write.sum of ONE k_fast_cells launch over 256 frames, from the committed
-# ncu --set full capture profiles/r01_k_fast_cells_full.txt (270.7 MB + 19.0 MB)
-FAST_DRAM_TRAFFIC_256 = 289.7e6
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE k_fast_cells launch, per frame, from the committed
+# ncu --set full capture profiles/r01_all_kernels_full.txt (135.4 MB + 8.43 MB for a 128-frame launch)
+FAST_DRAM_TRAFFIC_PER_FRAME = (135.4e6 + 8.432e6) / 128
 
 
 def measured_peaks():
@@ -393,7 +393,7 @@ def main():
             "gpu_launches": gpu_launches,
             "roofline": {"bound": "hbm", "kernel": "k_fast_cells", "achieved": achieved, "peak": hbm_peak,
                          "unit": "GB/s", "frac": achieved / hbm_peak,
-                         "traffic": FAST_DRAM_TRAFFIC_256 * B / 256.0, "algorithmic_bytes": fast_bytes,
+                         "traffic": FAST_DRAM_TRAFFIC_PER_FRAME * B, "algorithmic_bytes": fast_bytes,
                          "peak_kind": peak_kind,
                          "note": "issue/shared-memory bound integer kernel; HBM fraction reported honestly"},
             "step_roofline": {"bytes_per_frame": BYTES_PER_FRAME, "achieved_gbs": BYTES_PER_FRAME * fps / world / 1e9,
