@@ -482,6 +482,14 @@ static int run_fast(orbb_handle *h, int f0, int n, cudaStream_t st) {
     return ORBB_OK;
 }
 static int run_distribute(orbb_handle *h, int f0, int n, cudaStream_t st) {
+    static const bool split = getenv("ORBB_OCT_SPLIT") != nullptr;  // diagnostics: one launch per level
+    if (split) {
+        for (int l = 0; l < h->nlevels; ++l)
+            CK(h, launch_octree(h->d_levels, h->nlevels, h->d_cand_count, h->d_sel_count, l, 1, f0, n, -1, h->sel_cap_max,
+                                h->pcap, h->pcap2, st));
+        h->n_launches += h->nlevels;
+        return ORBB_OK;
+    }
     CK(h, launch_octree(h->d_levels, h->nlevels, h->d_cand_count, h->d_sel_count, 0, h->nlevels, f0, n, -1,
                         h->sel_cap_max, h->pcap, h->pcap2, st));
     h->n_launches += 1;
