@@ -160,6 +160,19 @@ int orbb_match_knn_segmented(orbb_handle *h, const uint8_t *d_query, const int32
                              int max_q_per_seg, int k, float ratio, int32_t *d_idx, int32_t *d_dist,
                              uint8_t *d_accept, void *cuda_stream);
 
+/* Windowed (guided) matcher with the reference's own match_keypoints semantics
+ * (src/cuda/post_processing.cu:92-200, call site src/SlamGpuPipeline/buildStream.cpp:545-548): for every
+ * query keypoint, among the train keypoints with |dx| <= max_px and |dy| <= max_px (float compare), the one
+ * with the smallest Hamming distance, accepted iff distance < max_hamming; ties -> lowest train index (the
+ * reference's rotated scan order makes its tie-break thread dependent; ours is fixed).  Here on the full
+ * 256-bit descriptors.  Positions are read as two consecutive floats (x, y) every `xy_stride` bytes, so an
+ * orbb_keypoint array (stride 28) or a packed float2 array (stride 8) can be passed directly.
+ * d_idx/d_dist: [nq] int32 (-1 when unmatched); d_nmatched: one int32 (may be NULL).  Async on stream. */
+int orbb_match_windowed(orbb_handle *h, const uint8_t *d_query, const void *d_query_xy, int q_xy_stride, int nq,
+                        const uint8_t *d_train, const void *d_train_xy, int t_xy_stride, int nt, float max_px,
+                        int max_hamming, int32_t *d_idx, int32_t *d_dist, int32_t *d_nmatched,
+                        void *cuda_stream);
+
 /* ---------------------------------------------------------------- debug / parity access
  * Download stage outputs of frame `frame` of the last batch to HOST memory (synchronises). */
 /* padded level, contiguous (w+38) x (h+38) */

@@ -146,6 +146,17 @@ inline void match_keypoints(orbb_handle *h, const uint8_t *d_query, int nq, cons
     orbb200::check(orbb_match_knn(h, d_query, nq, d_train, nt, k, ratio, d_idx, d_dist, d_accept, d_naccept, stream), h,
                    "match_keypoints");
 }
+// the reference's own gate (post_processing.cuh:40-51: max_pixel_distance, max_hamming_distance): keypoint arrays
+// are passed as they are (positions are the first two floats of every orbb_keypoint)
+inline void match_keypoints(orbb_handle *h, const uint8_t *d_desc_prev, const orbb_keypoint *d_kp_prev, int n_prev,
+                            const uint8_t *d_desc_curr, const orbb_keypoint *d_kp_curr, int n_curr,
+                            int max_pixel_distance, int max_hamming_distance, int32_t *d_idx, int32_t *d_dist,
+                            int32_t *d_keypoints_num_matched, void *stream) {
+    orbb200::check(orbb_match_windowed(h, d_desc_prev, d_kp_prev, (int)sizeof(orbb_keypoint), n_prev, d_desc_curr,
+                                       d_kp_curr, (int)sizeof(orbb_keypoint), n_curr, (float)max_pixel_distance,
+                                       max_hamming_distance, d_idx, d_dist, d_keypoints_num_matched, stream),
+                   h, "match_keypoints (windowed)");
+}
 }  // namespace Jetracer
 
 #endif  // ORBB200_HPP

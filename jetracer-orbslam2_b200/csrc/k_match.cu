@@ -106,6 +106,65 @@ k_match_merge(const int4 *__restrict__ partial, int partial_stride, int n_split,
     }
 }
 
+// ---- windowed 1-NN with a Hamming cutoff: the reference's match_keypoints semantics on 256-bit descriptors.
+// thread = one query; train positions + descriptors go through shared memory in tiles; the position gate runs
+// first, XOR/POPC only for the few candidates inside the window.
+#define WIN_THREADS 128
+#define WIN_TILE 128
+__global__ void __launch_bounds__(WIN_THREADS)
+k_match_windowed(const uint4 *__restrict__ query, const uint8_t *__restrict__ q_xy, int q_stride, int nq,
+                 const uint4 *__restrict__ train, const uint8_t *__restrict__ t_xy, int t_stride, int nt, float max_px,
+                 int max_hamming, int *__restrict__ out_idx, int *__restrict__ out_dist, int *__restrict__ n_matched) {
+    __shared__ uint4 s_d[WIN_TILE * 2];
+    __shared__ float2 s_xy[WIN_TILE];
+    const int q = blockIdx.x * WIN_THREADS + threadIdx.x;
+    const int qq = min(q, nq - 1);
+    const uint4 qa = query[(size_t)qq * 2], qb = query[(size_t)qq * 2 + 1];
+    const float qx = *reinterpret_cast<const float *>(q_xy + (size_t)qq * q_stride);
+    const float qy = *reinterpret_cast<const float *>(q_xy + (size_t)qq * q_stride + 4);
+    int best_d = max_hamming, best_i = -1;  // accept only d < max_hamming; strict '<' keeps the lowest index on ties
+    for (int tb = 0; tb < nt; tb += WIN_TILE) {
+        const int cnt = min(WIN_TILE, nt - tb);
+        __syncthreads();
+        for (int i = threadIdx.x; i < cnt * 2; i += WIN_THREADS) s_d[i] = train[(size_t)tb * 2 + i];
+        for (int i = threadIdx.x; i < cnt; i += WIN_THREADS) {
+            const uint8_t *p = t_xy + (size_t)(tb + i) * t_stride;
+            s_xy[i] = make_float2(*reinterpret_cast<const float *>(p), *reinterpret_cast<const float *>(p + 4));
+        }
+        __syncthreads();
+        for (int t = 0; t < cnt; ++t) {
+            const float2 p = s_xy[t];
+            if (fabsf(__fsub_rn(qx, p.x)) <= max_px && fabsf(__fsub_rn(qy, p.y)) <= max_px) {
+                const uint4 a = s_d[2 * t], b = s_d[2 * t + 1];
+                const int d = __popc(qa.x ^ a.x) + __popc(qa.y ^ a.y) + __popc(qa.z ^ a.z) + __popc(qa.w ^ a.w) +
+                              __popc(qb.x ^ b.x) + __popc(qb.y ^ b.y) + __popc(qb.z ^ b.z) + __popc(qb.w ^ b.w);
+                if (d < best_d) { best_d = d; best_i = tb + t; }
+            }
+        }
+    }
+    const bool ok = q < nq && best_i >= 0;
+    if (q < nq) { out_idx[q] = best_i; out_dist[q] = best_i >= 0 ? best_d : -1; }
+    if (n_matched) {
+        const unsigned m = __ballot_sync(0xffffffffu, ok);
+        if ((threadIdx.x & 31) == 0 && m) atomicAdd(n_matched, __popc(m));
+    }
+}
+
+cudaError_t launch_match_windowed(const uint8_t *d_q, const void *d_q_xy, int q_stride, int nq, const uint8_t *d_t,
+                                  const void *d_t_xy, int t_stride, int nt, float max_px, int max_hamming, int *d_idx,
+                                  int *d_dist, int *d_nmatched, cudaStream_t st) {
+    if (nq <= 0) return cudaSuccess;
+    if (d_nmatched) {
+        cudaError_t e = cudaMemsetAsync(d_nmatched, 0, sizeof(int), st);
+        if (e != cudaSuccess) return e;
+    }
+    k_match_windowed<<<(nq + WIN_THREADS - 1) / WIN_THREADS, WIN_THREADS, 0, st>>>(
+        reinterpret_cast<const uint4 *>(d_q), static_cast<const uint8_t *>(d_q_xy), q_stride, nq,
+        reinterpret_cast<const uint4 *>(d_t), static_cast<const uint8_t *>(d_t_xy), t_stride, nt, max_px, max_hamming, d_idx,
+        d_dist, d_nmatched);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_match(const uint8_t *d_q, const uint8_t *d_t, const int *d_q_off, const int *d_t_off, int nseg,
                          int nq_total, int max_q_per_seg, int nt_one, int n_split, int4 *d_partial,
                          int partial_stride, int k, float ratio, int *d_idx, int *d_dist, uint8_t *d_accept,

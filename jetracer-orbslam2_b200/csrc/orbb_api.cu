@@ -26,6 +26,8 @@ cudaError_t launch_fast_dump(const void *, const LevelDev *, const CellEntry *, 
 cudaError_t launch_octree(const LevelDev *, int, const int *, int *, int, int, int, int, int, int, int, int,
                           cudaStream_t);
 size_t octree_dyn_smem(int, int, int);
+cudaError_t launch_match_windowed(const uint8_t *, const void *, int, int, const uint8_t *, const void *, int, int, float, int,
+                                  int *, int *, int *, cudaStream_t);
 cudaError_t launch_angle_orb(const LevelDev *, int, const int *, const int8_t *, const int *, const int *, int, int, int,
                              orbb_keypoint *, uint8_t *, int *, int, cudaStream_t);
 cudaError_t launch_match(const uint8_t *, const uint8_t *, const int *, const int *, int, int, int, int, int, int4 *,
@@ -736,6 +738,21 @@ extern "C" int orbb_match_knn_segmented(orbb_handle *h, const uint8_t *d_query, 
     CK(h, launch_match(d_query, d_train, d_q_offsets, d_t_offsets, nseg, nq_total, max_q_per_seg, 0, n_split,
                        h->d_partial, nq_total, k, ratio, d_idx, d_dist, d_accept, nullptr, st));
     h->n_launches += 2;
+    return ORBB_OK;
+}
+
+extern "C" int orbb_match_windowed(orbb_handle *h, const uint8_t *d_query, const void *d_query_xy, int q_xy_stride, int nq,
+                                   const uint8_t *d_train, const void *d_train_xy, int t_xy_stride, int nt, float max_px,
+                                   int max_hamming, int32_t *d_idx, int32_t *d_dist, int32_t *d_nmatched, void *stream) {
+    if (!h || !d_query || !d_query_xy || !d_train || !d_train_xy || !d_idx || !d_dist || nq < 0 || nt < 0 ||
+        q_xy_stride < 8 || t_xy_stride < 8 || (q_xy_stride & 3) || (t_xy_stride & 3) || max_hamming < 0)
+        return ORBB_ERR_INVALID;
+    if ((reinterpret_cast<uintptr_t>(d_query) | reinterpret_cast<uintptr_t>(d_train)) & 15) return ORBB_ERR_INVALID;
+    if ((reinterpret_cast<uintptr_t>(d_query_xy) | reinterpret_cast<uintptr_t>(d_train_xy)) & 3) return ORBB_ERR_INVALID;
+    if (nq == 0) return ORBB_OK;
+    CK(h, launch_match_windowed(d_query, d_query_xy, q_xy_stride, nq, d_train, d_train_xy, t_xy_stride, nt, max_px,
+                                std::min(max_hamming, 257), d_idx, d_dist, d_nmatched, static_cast<cudaStream_t>(stream)));
+    h->n_launches += 1;
     return ORBB_OK;
 }
 

@@ -33,7 +33,7 @@ EXPORTS = [
     "orbb_extract_batch_device", "orbb_extract_batch_host", "orbb_extract_batch_host_async", "orbb_wait",
     "orbb_stage_upload", "orbb_pyramid_create_levels",
     "orbb_detect", "orbb_detect_fast", "orbb_detect_distribute", "orbb_gaussian_blur", "orbb_compute_angle_and_orb", "orbb_match_knn",
-    "orbb_match_knn_segmented", "orbb_debug_get_padded", "orbb_debug_get_blurred", "orbb_debug_get_scores",
+    "orbb_match_knn_segmented", "orbb_match_windowed", "orbb_debug_get_padded", "orbb_debug_get_blurred", "orbb_debug_get_scores",
     "orbb_debug_get_candidates", "orbb_debug_get_selected", "orbb_debug_distribute",
 ]
 
@@ -91,6 +91,7 @@ def load_library():
     L.orbb_compute_angle_and_orb.argtypes = [vp, vp, vp, vp, i32, vp]
     L.orbb_match_knn.argtypes = [vp, vp, i32, vp, i32, i32, f32, vp, vp, vp, vp, vp]
     L.orbb_match_knn_segmented.argtypes = [vp, vp, vp, vp, vp, i32, i32, i32, f32, vp, vp, vp, vp]
+    L.orbb_match_windowed.argtypes = [vp, vp, vp, i32, i32, vp, vp, i32, i32, f32, i32, vp, vp, vp, vp]
     L.orbb_debug_get_padded.argtypes = [vp, i32, i32, vp]
     L.orbb_debug_get_blurred.argtypes = [vp, i32, i32, vp]
     L.orbb_debug_get_scores.argtypes = [vp, i32, i32, vp]
@@ -284,6 +285,16 @@ class ORBextractor:
                                                        _dev_ptr(d_idx), _dev_ptr(d_dist),
                                                        _dev_ptr(d_accept) if d_accept is not None else C.c_void_p(0),
                                                        _stream_ptr(stream)))
+
+    def match_keypoints_windowed(self, d_query, d_query_xy, q_xy_stride: int, nq: int, d_train, d_train_xy,
+                                 t_xy_stride: int, nt: int, max_pixel_distance: float, max_hamming_distance: int,
+                                 d_idx, d_dist, d_nmatched=None, stream=None):
+        """The reference's match_keypoints(current, previous, max_pixel_distance, max_hamming_distance, ...) gate:
+        position window first, then best Hamming distance below the cutoff."""
+        self._check(self._lib.orbb_match_windowed(
+            self._h, _dev_ptr(d_query), _dev_ptr(d_query_xy), q_xy_stride, nq, _dev_ptr(d_train), _dev_ptr(d_train_xy),
+            t_xy_stride, nt, max_pixel_distance, max_hamming_distance, _dev_ptr(d_idx), _dev_ptr(d_dist),
+            _dev_ptr(d_nmatched) if d_nmatched is not None else C.c_void_p(0), _stream_ptr(stream)))
 
     # -- parity / debug access --------------------------------------------------------------
     def debug_padded(self, level: int, frame: int = 0) -> np.ndarray:

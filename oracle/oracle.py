@@ -59,6 +59,8 @@ def lib(native: bool = False):
     L.orbo_fast_atan2.restype = C.c_float
     L.orbo_match_knn.argtypes = [vp, C.c_int, vp, C.c_int, C.c_int, C.c_float, vp, vp, vp]
     L.orbo_match_knn.restype = C.c_int
+    L.orbo_match_windowed.argtypes = [vp, vp, C.c_int, vp, vp, C.c_int, C.c_float, C.c_int, vp, vp]
+    L.orbo_match_windowed.restype = C.c_int
     L.orbo_create.argtypes = [C.POINTER(vp), C.POINTER(Params), C.c_int, C.c_int]
     L.orbo_create.restype = C.c_int
     L.orbo_destroy.argtypes = [vp]
@@ -163,6 +165,18 @@ def match_knn(q, t, k: int = 2, ratio: float = 0.7, threads: int = 1, native: bo
     else:
         L.orbo_match_many(_p(q), q.shape[0], _p(t), t.shape[0], k, ratio, threads, _p(idx), _p(dist), _p(acc))
     return idx, dist, acc.astype(bool)
+
+
+def match_windowed(q, q_xy, t, t_xy, max_px: float, max_hamming: int):
+    q = np.ascontiguousarray(q, np.uint8).reshape(-1, 32)
+    t = np.ascontiguousarray(t, np.uint8).reshape(-1, 32)
+    q_xy = np.ascontiguousarray(q_xy, np.float32).reshape(-1, 2)
+    t_xy = np.ascontiguousarray(t_xy, np.float32).reshape(-1, 2)
+    idx = np.full(q.shape[0], -1, np.int32)
+    dist = np.full(q.shape[0], -1, np.int32)
+    n = lib().orbo_match_windowed(_p(q), _p(q_xy), q.shape[0], _p(t), _p(t_xy), t.shape[0], max_px, max_hamming,
+                                  _p(idx), _p(dist))
+    return idx, dist, int(n)
 
 
 def distribute_octree(cand: np.ndarray, min_x: int, max_x: int, min_y: int, max_y: int, n: int) -> np.ndarray:

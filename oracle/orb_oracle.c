@@ -291,6 +291,25 @@ int orbo_match_knn(const uint8_t *q, int nq, const uint8_t *t, int nt, int k, fl
     return nacc;
 }
 
+/* reference kernel_match_keypoints semantics (src/cuda/post_processing.cu:156-171) on 256-bit descriptors */
+int orbo_match_windowed(const uint8_t *q, const float *q_xy, int nq, const uint8_t *t, const float *t_xy, int nt,
+                        float max_px, int max_hamming, int32_t *out_idx, int32_t *out_dist) {
+    int nm = 0;
+    for (int i = 0; i < nq; ++i) {
+        int best = -1, bd = max_hamming;
+        for (int j = 0; j < nt; ++j) {
+            if (fabsf(q_xy[2 * i] - t_xy[2 * j]) <= max_px && fabsf(q_xy[2 * i + 1] - t_xy[2 * j + 1]) <= max_px) {
+                const int d = hamming256(q + (size_t)i * 32, t + (size_t)j * 32);
+                if (d < bd) { bd = d; best = j; }
+            }
+        }
+        out_idx[i] = best;
+        out_dist[i] = best >= 0 ? bd : -1;
+        nm += best >= 0;
+    }
+    return nm;
+}
+
 /* ---------- extractor context ---------- */
 struct orbo_ctx {
     orbo_params p;

@@ -76,6 +76,11 @@ float orbo_fast_atan2(float y, float x);
 int orbo_match_knn(const uint8_t *q, int nq, const uint8_t *t, int nt, int k, float ratio,
                    int32_t *out_idx, int32_t *out_dist, uint8_t *accept);
 
+/* windowed 1-NN with Hamming cutoff (reference src/cuda/post_processing.cu:92-200 semantics, ties -> lowest
+ * train index): out_idx/out_dist [nq], -1 when unmatched. returns #matched */
+int orbo_match_windowed(const uint8_t *q, const float *q_xy, int nq, const uint8_t *t, const float *t_xy, int nt,
+                        float max_px, int max_hamming, int32_t *out_idx, int32_t *out_dist);
+
 /* ---- extractor context (upstream ORBextractor object) ---- */
 int orbo_create(orbo_ctx **out, const orbo_params *p, int width, int height);
 void orbo_destroy(orbo_ctx *c);

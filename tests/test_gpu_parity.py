@@ -383,3 +383,49 @@ def test_async_host_api_matches_sync(orbb, synth):
             n = rc[f]
             assert kk[f, :n].tobytes() == rk[f, :n].tobytes() and dd[f, :n].tobytes() == rd[f, :n].tobytes()
     ex.close()
+
+
+def test_windowed_matcher_reference_semantics(orbb, oracle, synth):
+    """orbb_match_windowed (the reference's match_keypoints gate: +-max_px window, best Hamming < cutoff) vs oracle,
+    on real keypoints of frame t / t+1 (keypoint array passed directly, stride 28) and on random data."""
+    import torch
+    w, h = 640, 480
+    f0 = synth.textured_frame(w, h, 5100)
+    f1 = synth.shifted_frame(f0, 3, 1, 5101)
+    ex = orbb.ORBextractor(1000, 1.2, 8, 20, 7, width=w, height=h, max_batch=2)
+    kp, desc, counts = ex.extract_batch(np.stack([f0, f1]))
+    n0, n1 = int(counts[0]), int(counts[1])
+    st = torch.cuda.current_stream()
+    for max_px, max_ham in ((2.0, 4), (6.0, 64), (40.0, 257), (0.0, 30)):
+        dq = torch.from_numpy(desc[0, :n0].copy()).cuda()
+        dt = torch.from_numpy(desc[1, :n1].copy()).cuda()
+        kq = torch.from_numpy(np.frombuffer(kp[0, :n0].tobytes(), np.uint8).copy()).cuda()   # orbb_keypoint[], stride 28
+        kt = torch.from_numpy(np.frombuffer(kp[1, :n1].tobytes(), np.uint8).copy()).cuda()
+        idx = torch.zeros(n0, dtype=torch.int32, device="cuda")
+        dist = torch.zeros(n0, dtype=torch.int32, device="cuda")
+        nm = torch.zeros(1, dtype=torch.int32, device="cuda")
+        ex.match_keypoints_windowed(dq, kq, 28, n0, dt, kt, 28, n1, max_px, max_ham, idx, dist, nm, stream=st)
+        torch.cuda.synchronize()
+        qxy = np.stack([kp[0, :n0]["x"], kp[0, :n0]["y"]], 1)
+        txy = np.stack([kp[1, :n1]["x"], kp[1, :n1]["y"]], 1)
+        oi, od, on = oracle.match_windowed(desc[0, :n0], qxy, desc[1, :n1], txy, max_px, max_ham)
+        assert np.array_equal(idx.cpu().numpy(), oi) and np.array_equal(dist.cpu().numpy(), od)
+        assert int(nm.item()) == on
+        if max_px == 6.0:
+            assert on > 200  # the (3,1) shift really produces windowed matches
+    rng = np.random.default_rng(9)
+    nq, nt = 777, 1301
+    q = rng.integers(0, 256, size=(nq, 32), dtype=np.uint8)
+    t = rng.integers(0, 256, size=(nt, 32), dtype=np.uint8)
+    t[:300] = q[:300] ^ (rng.integers(0, 256, size=(300, 32), dtype=np.uint8) & 0x11)
+    qxy = rng.uniform(0, 200, size=(nq, 2)).astype(np.float32)
+    txy = rng.uniform(0, 200, size=(nt, 2)).astype(np.float32)
+    txy[:300] = qxy[:300] + rng.integers(-3, 4, size=(300, 2)).astype(np.float32)
+    idx = torch.zeros(nq, dtype=torch.int32, device="cuda")
+    dist = torch.zeros(nq, dtype=torch.int32, device="cuda")
+    ex.match_keypoints_windowed(torch.from_numpy(q).cuda(), torch.from_numpy(qxy).cuda(), 8, nq, torch.from_numpy(t).cuda(),
+                                torch.from_numpy(txy).cuda(), 8, nt, 3.0, 100, idx, dist, stream=st)
+    torch.cuda.synchronize()
+    oi, od, _ = oracle.match_windowed(q, qxy, t, txy, 3.0, 100)
+    assert np.array_equal(idx.cpu().numpy(), oi) and np.array_equal(dist.cpu().numpy(), od)
+    ex.close()
