@@ -50,8 +50,6 @@ struct orbb_handle {
     float sf[ORBB_MAX_LEVELS]{}, inv_sf[ORBB_MAX_LEVELS]{};
     CellEntry *d_cells = nullptr;
     int n_cells = 0;
-    TileEntry *d_tiles = nullptr;
-    int n_tiles = 0;
     FastSmemCfg fcfg{};
     void *tma_maps = nullptr;  // DEVICE array of CUtensorMap, one per level (nullptr: FAST stages manually)
     int t_lo = 7, t_hi = 20;
@@ -233,7 +231,6 @@ extern "C" int orbb_create(orbb_handle **out, const orbb_params *params, int wid
     } while (0)
 
     std::vector<CellEntry> cells;
-    std::vector<TileEntry> tiles;
     std::vector<int> slot_level, slot_base(nl);
     int max_cw = 1, max_ch = 1;
     h->dump_off.resize(nl + 1);
@@ -347,15 +344,9 @@ extern "C" int orbb_create(orbb_handle **out, const orbb_params *params, int wid
         slot_base[l] = (int)slot_level.size();
         for (int s = 0; s < L.sel_cap; ++s) slot_level.push_back(l);
         h->sel_cap_max = std::max(h->sel_cap_max, L.sel_cap);
-        // blur tiles
-        for (int ty = 0; ty < (L.h + 31) / 32; ++ty)
-            for (int tx = 0; tx < (L.w + 63) / 64; ++tx) {
-                TileEntry t{}; t.level = (int16_t)l; t.tx = (int16_t)tx; t.ty = (int16_t)ty;
-                tiles.push_back(t);
-            }
     }
     h->dump_off[nl] = dump_total;
-    h->n_cells = (int)cells.size(); h->n_tiles = (int)tiles.size(); h->n_slots = (int)slot_level.size();
+    h->n_cells = (int)cells.size(); h->n_slots = (int)slot_level.size();
     h->max_kp = h->n_slots;
     h->pcap = h->sel_cap_max; h->pcap2 = 1;
     while (h->pcap2 < h->pcap) h->pcap2 <<= 1;
@@ -384,7 +375,6 @@ extern "C" int orbb_create(orbb_handle **out, const orbb_params *params, int wid
         }
     }
     CKC(upload(h, &h->d_cells, cells));
-    CKC(upload(h, &h->d_tiles, tiles));
     CKC(upload(h, &h->d_slot_level, slot_level));
     CKC(upload(h, &h->d_slot_base, slot_base));
     {

@@ -52,10 +52,6 @@ struct CellEntry {  // one FAST work item = one upstream 30-px cell
     int16_t level, x0, y0, cw, ch, pad0, pad1, pad2;  // tested-range origin (ROI coords) and size
 };
 
-struct TileEntry {  // generic 2-D tile of a level (blur kernel)
-    int16_t level, tx, ty, pad;
-};
-
 struct FastSmemCfg {
     int tile_pitch, tile_rows;    // bytes, rows of the per-warp image tile (manual staging)
     int tma_pitch;                // row bytes of the TMA box (16-byte aligned start => up to 15 bytes of phase)
