@@ -429,3 +429,53 @@ def test_windowed_matcher_reference_semantics(orbb, oracle, synth):
     oi, od, _ = oracle.match_windowed(q, qxy, t, txy, 3.0, 100)
     assert np.array_equal(idx.cpu().numpy(), oi) and np.array_equal(dist.cpu().numpy(), od)
     ex.close()
+
+
+def test_degenerate_inputs(orbb, oracle):
+    """Inputs that stress capacities and tie handling: uniform noise (maximal candidate density -> tens of
+    thousands of candidates per level, quadtree on the global-scratch path), salt & pepper, smooth gradients
+    (threshold-7 fallback everywhere), 2-px and 3-px checkerboards (massive NMS ties), constant frames."""
+    rng = np.random.default_rng(2025)
+    w, h = 640, 480
+    yy, xx = np.mgrid[0:h, 0:w]
+    sp = np.full((h, w), 128, np.uint8)
+    m = rng.random((h, w))
+    sp[m < 0.02] = 0
+    sp[m > 0.98] = 255
+    frames = np.stack([
+        rng.integers(0, 256, size=(h, w), dtype=np.uint8),                       # uniform noise
+        sp,                                                                        # salt & pepper
+        ((xx * 255) // (w - 1)).astype(np.uint8),                                  # horizontal ramp
+        ((xx + 2 * yy) % 256).astype(np.uint8),                                    # diagonal saw-tooth
+        np.where(((yy // 2) + (xx // 2)) % 2 == 0, 40, 215).astype(np.uint8),      # 2-px checkerboard
+        np.where(((yy // 3) + (xx // 3)) % 2 == 0, 90, 160).astype(np.uint8),      # 3-px checkerboard
+        np.zeros((h, w), np.uint8), np.full((h, w), 255, np.uint8),                # constant
+    ])
+    ex = orbb.ORBextractor(1000, 1.2, 8, 20, 7, width=w, height=h, max_batch=len(frames))
+    kp, desc, counts = ex.extract_batch(frames)
+    o = oracle.Oracle(w, h, 1000)
+    for f in range(len(frames)):
+        okp, odesc = canon(*o.extract(frames[f]))
+        gk, gd = canon(kp[f, :counts[f]], desc[f, :counts[f]])
+        assert len(okp) == counts[f], (f, len(okp), counts[f])
+        assert gk.tobytes() == okp.tobytes(), f
+        assert np.array_equal(gd, odesc), f
+    # candidate sets of the densest frame, level 0 and last level
+    o.compute_pyramid(frames[0])
+    for l in (0, 7):
+        oc = o.level_candidates(l)
+        assert as_set(ex.debug_candidates(l, frame=0)) == as_set(np.stack([oc["x"], oc["y"], oc["response"]], 1))
+    ex.close()
+
+
+def test_noise_1280x720_over_64k_candidates(orbb, oracle):
+    """Level 0 of a 1280x720 noise frame yields > 65535 candidates: exercises 32-bit indices in the quadtree sort."""
+    rng = np.random.default_rng(77)
+    img = rng.integers(0, 256, size=(720, 1280), dtype=np.uint8)
+    ex = orbb.ORBextractor(2000, 1.2, 8, 20, 7, width=1280, height=720)
+    o = oracle.Oracle(1280, 720, 2000)
+    gk, gd = canon(*ex(img))
+    okp, od = canon(*o.extract(img))
+    assert len(ex.debug_candidates(0)) == len(o.level_candidates(0)) > 65535
+    assert len(gk) == len(okp) and gk.tobytes() == okp.tobytes() and np.array_equal(gd, od)
+    ex.close()
