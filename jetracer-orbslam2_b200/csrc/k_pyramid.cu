@@ -20,32 +20,38 @@ __device__ __forceinline__ int reflect101(int p, int len) {
 }
 
 // ---- level 0: copy the caller's frames into the padded layout + border.
-// thread = one 16-byte chunk of a padded row (ROI rows are 16-byte aligned by layout): interior chunks are one
-// 128-bit load + one 128-bit store, edge chunks are assembled bytewise through the reflect-101 map.
+// Work items of a frame are ordered so that warps do not diverge: first every 16-byte chunk that lies entirely
+// inside the ROI (one 128-bit load + one 128-bit store; ROI rows are 16-byte aligned by layout), then the 32-bit
+// words that touch the reflect-101 frame or the ragged right end, assembled bytewise through the reflect map.
+// With an unaligned source (pointer, pitch or stride not a multiple of 16) n_int == 0 and every word takes the
+// bytewise route.
 __global__ void __launch_bounds__(256) k_level0(const uint8_t *__restrict__ in, size_t in_pitch, size_t in_stride,
-                                                LevelDev L, int aligned16, int frame_base) {
-    const int cpr = L.pitch >> 4;  // 16-byte chunks per row (pitch is a multiple of 128)
+                                                LevelDev L, int n_int, int n_edge, int frame_base) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= cpr * L.rows) return;
-    const int py = i / cpr, chunk = i - py * cpr;
     const int frame = blockIdx.y + frame_base;
-    const int y = reflect101(py - ORBB_BORDER, L.h);
-    const uint8_t *src = in + (size_t)blockIdx.y * in_stride + (size_t)y * in_pitch;
-    const int b0 = chunk * 16, x0 = b0 - ORBB_ROI_X0;
-    uint4 out;
-    if (aligned16 && x0 >= 0 && x0 + 15 < L.w) {
-        out = *reinterpret_cast<const uint4 *>(src + x0);
-    } else {
-        uint32_t wv[4] = {0, 0, 0, 0};
-#pragma unroll
-        for (int k = 0; k < 16; ++k) {
-            const int px = b0 + k - ORBB_PAD_X0;
-            if (px >= 0 && px < L.w + 2 * ORBB_BORDER)
-                wv[k >> 2] |= (uint32_t)src[reflect101(px - ORBB_BORDER, L.w)] << (8 * (k & 3));
-        }
-        out = make_uint4(wv[0], wv[1], wv[2], wv[3]);
+    const uint8_t *fsrc = in + (size_t)blockIdx.y * in_stride;
+    uint8_t *fdst = L.img + (size_t)frame * L.frame_stride;
+    const int n_interior = n_int * L.rows;
+    if (i < n_interior) {
+        const int py = i / n_int, c = i - py * n_int;
+        const int y = reflect101(py - ORBB_BORDER, L.h);
+        const uint4 v = __ldg(reinterpret_cast<const uint4 *>(fsrc + (size_t)y * in_pitch + 16 * c));
+        *reinterpret_cast<uint4 *>(fdst + (size_t)py * L.pitch + ORBB_ROI_X0 + 16 * c) = v;
+        return;
     }
-    *reinterpret_cast<uint4 *>(L.img + (size_t)frame * L.frame_stride + (size_t)py * L.pitch + b0) = out;
+    const int e = i - n_interior;
+    if (e >= n_edge * L.rows) return;
+    const int py = e / n_edge, k = e - py * n_edge;
+    // words 3..7 hold the left frame (bytes 12..31); the rest continue after the last interior chunk
+    const int wd = k < 5 ? 3 + k : 8 + 4 * n_int + (k - 5);
+    const uint8_t *src = fsrc + (size_t)reflect101(py - ORBB_BORDER, L.h) * in_pitch;
+    uint32_t out = 0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int px = min(max(4 * wd + j - ORBB_PAD_X0, 0), L.w + 2 * ORBB_BORDER - 1);
+        out |= (uint32_t)__ldg(src + reflect101(px - ORBB_BORDER, L.w)) << (8 * j);
+    }
+    *reinterpret_cast<uint32_t *>(fdst + (size_t)py * L.pitch + 4 * wd) = out;
 }
 
 // ---- level l from level l-1: tiled two-phase bilinear resize (cv::resize INTER_LINEAR, 8U).
@@ -167,6 +173,75 @@ __global__ void __launch_bounds__(RS_THREADS) k_resize(const LevelDev *__restric
     }
 }
 
+// ---- level l from level l-1, table-driven form (the default; k_resize above is the fallback for scale steps
+// whose 2-pixel source span does not fit an 8-byte window, i.e. scale factors > 2).
+// thread = one aligned 4-byte group of one PADDED output row; a CTA covers 128 bytes x RS_ROWS consecutive rows so
+// that the source rows shared by neighbouring output rows hit in L1.  No shared memory, no barriers, no dependent
+// chains: every per-column and per-row quantity is precomputed on the host (rs_h / rs_v, with the reflect-101
+// frame folded in), so a thread issues its 8 aligned 32-bit loads (two 8-byte windows on each of the two source
+// rows) up front, gathers [S[sx],S[sx+1]] of two pixels with one PRMT, does the horizontal pass with IDP.2A
+// against (a0 | a1<<16) and the vertical pass with IMAD.HI against b<<16.
+#define RS_ROWS 8
+struct ResizeArgs {  // by value: lives in the constant bank, no dependent global loads before the tables
+    const uint8_t *src;  // source level, frame 0, padded row ORBB_BORDER (= ROI row 0), byte 0
+    uint8_t *dst;        // destination level, frame 0, padded row 0, byte 12 (first group)
+    long long src_stride, dst_stride;
+    const uint4 *rs_h;
+    const int4 *rs_v;
+    int src_pitch, dst_pitch, nq, rows;
+};
+
+template <bool AREA>
+__global__ void __launch_bounds__(32 * RS_ROWS) k_resize_rows(const ResizeArgs A, int frame_base) {
+    const int q = blockIdx.x * 32 + threadIdx.x;
+    const int py0 = blockIdx.y * (2 * RS_ROWS) + threadIdx.y;
+    if (q >= A.nq || py0 >= A.rows) return;
+    const int frame = blockIdx.z + frame_base;
+    const uint4 hx = __ldg(A.rs_h + 2 * q), hw = __ldg(A.rs_h + 2 * q + 1);
+    const uint8_t *sbase = A.src + (size_t)frame * A.src_stride;
+    uint8_t *dbase = A.dst + (size_t)frame * A.dst_stride + 4 * q;
+    constexpr int SH = AREA ? 0 : 4;
+    // two output rows per thread (py0 and py0 + RS_ROWS): 16 independent loads in flight
+    const int py1 = min(py0 + RS_ROWS, A.rows - 1);
+    int4 v[2] = {__ldg(A.rs_v + py0), __ldg(A.rs_v + py1)};
+    unsigned w[2][8];
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+        const uint8_t *p0 = sbase + (size_t)v[r].x * A.src_pitch, *p1 = sbase + (size_t)v[r].y * A.src_pitch;
+        w[r][0] = __ldg(reinterpret_cast<const unsigned *>(p0 + hx.x));
+        w[r][1] = __ldg(reinterpret_cast<const unsigned *>(p0 + hx.x + 4));
+        w[r][2] = __ldg(reinterpret_cast<const unsigned *>(p0 + hx.z));
+        w[r][3] = __ldg(reinterpret_cast<const unsigned *>(p0 + hx.z + 4));
+        w[r][4] = __ldg(reinterpret_cast<const unsigned *>(p1 + hx.x));
+        w[r][5] = __ldg(reinterpret_cast<const unsigned *>(p1 + hx.x + 4));
+        w[r][6] = __ldg(reinterpret_cast<const unsigned *>(p1 + hx.z));
+        w[r][7] = __ldg(reinterpret_cast<const unsigned *>(p1 + hx.z + 4));
+    }
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+        unsigned ta[4], tb[4];
+        {
+            const unsigned pa = __byte_perm(w[r][0], w[r][1], hx.y), pb = __byte_perm(w[r][2], w[r][3], hx.w);
+            ta[0] = __dp2a_lo(hw.x, pa, 0u) >> SH; ta[1] = __dp2a_hi(hw.y, pa, 0u) >> SH;
+            ta[2] = __dp2a_lo(hw.z, pb, 0u) >> SH; ta[3] = __dp2a_hi(hw.w, pb, 0u) >> SH;
+        }
+        {
+            const unsigned pa = __byte_perm(w[r][4], w[r][5], hx.y), pb = __byte_perm(w[r][6], w[r][7], hx.w);
+            tb[0] = __dp2a_lo(hw.x, pa, 0u) >> SH; tb[1] = __dp2a_hi(hw.y, pa, 0u) >> SH;
+            tb[2] = __dp2a_lo(hw.z, pb, 0u) >> SH; tb[3] = __dp2a_hi(hw.w, pb, 0u) >> SH;
+        }
+        unsigned s[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            s[j] = AREA ? ta[j] + tb[j] + 2u
+                        : __umulhi((unsigned)v[r].z, ta[j]) + __umulhi((unsigned)v[r].w, tb[j]) + 2u;
+        // s < 1024: pack pairs in 16-bit halves, shift both at once, gather bytes 0 and 2
+        const unsigned lo = (s[0] | (s[1] << 16)) >> 2, hi = (s[2] | (s[3] << 16)) >> 2;
+        const int py = r == 0 ? py0 : py0 + RS_ROWS;
+        if (py < A.rows) *reinterpret_cast<unsigned *>(dbase + (size_t)py * A.dst_pitch) = __byte_perm(lo, hi, 0x6420);
+    }
+}
+
 // ---- 7x7 sigma=2 Gaussian of the ROI, OpenCV 4.13 fixed point: k = [18,34,48,56,48,34,18]/256 per
 // pass, dst = (V + 32768) >> 16.  Reads the padded level, so REFLECT_101 at the ROI
 // edge is already materialised by the border.
@@ -223,16 +298,31 @@ __global__ void __launch_bounds__(128) k_blur(const LevelDev *__restrict__ level
 // ---------------------------------------------------------------- host launchers
 cudaError_t launch_level0(const uint8_t *d_in, size_t pitch, size_t stride, const LevelDev &L0, int frame_base,
                           int n_frames, cudaStream_t st) {
-    const int items = (L0.pitch >> 4) * L0.rows;
-    dim3 grid((items + 255) / 256, n_frames);
     const int aligned16 = ((reinterpret_cast<uintptr_t>(d_in) | pitch | stride) & 15) == 0;
-    k_level0<<<grid, 256, 0, st>>>(d_in, pitch, stride, L0, aligned16, frame_base);
+    const int n_int = aligned16 ? L0.w / 16 : 0;
+    const int last_word = (ORBB_ROI_X0 + L0.w + ORBB_BORDER + 3) / 4;  // one past the last word holding a padded pixel
+    const int n_edge = 5 + last_word - (8 + 4 * n_int);
+    const int items = (n_int + n_edge) * L0.rows;
+    dim3 grid((items + 255) / 256, n_frames);
+    k_level0<<<grid, 256, 0, st>>>(d_in, pitch, stride, L0, n_int, n_edge, frame_base);
     return cudaGetLastError();
 }
 
 cudaError_t launch_resize(const LevelDev *d_levels, const LevelDev *h_levels, int l, int frame_base, int n_frames,
                           cudaStream_t st) {
     const LevelDev &Lh = h_levels[l], &Sh = h_levels[l - 1];
+    if (Lh.rs_ok) {
+        ResizeArgs A;
+        A.src = Sh.img + (size_t)ORBB_BORDER * Sh.pitch;
+        A.dst = Lh.img + 12;
+        A.src_stride = Sh.frame_stride; A.dst_stride = Lh.frame_stride;
+        A.rs_h = Lh.rs_h; A.rs_v = Lh.rs_v;
+        A.src_pitch = Sh.pitch; A.dst_pitch = Lh.pitch; A.nq = Lh.rs_nq; A.rows = Lh.rows;
+        dim3 grid((Lh.rs_nq + 31) / 32, (Lh.rows + 2 * RS_ROWS - 1) / (2 * RS_ROWS), n_frames), block(32, RS_ROWS);
+        if (Lh.area2x) k_resize_rows<true><<<grid, block, 0, st>>>(A, frame_base);
+        else k_resize_rows<false><<<grid, block, 0, st>>>(A, frame_base);
+        return cudaGetLastError();
+    }
     // worst-case source window of one tile (+ slack for clamping/alignment)
     const int src_cols = (int)((double)RS_TW * Sh.w / Lh.w) + 8;
     const int src_pitch = ((src_cols + 3) / 4 + 1) * 4;

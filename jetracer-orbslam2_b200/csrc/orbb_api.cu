@@ -262,6 +262,43 @@ extern "C" int orbb_create(orbb_handle **out, const orbb_params *params, int wid
             int *dxofs; short2 *dxa; int2 *dyr; short2 *dyb;
             CKC(upload(h, &dxofs, xofs)); CKC(upload(h, &dxa, xa)); CKC(upload(h, &dyr, yr)); CKC(upload(h, &dyb, yb));
             L.xofs = dxofs; L.xalpha = dxa; L.yrows = dyr; L.ybeta = dyb;
+            // tables of the row-walking resize kernel: one entry per aligned 4-byte group of the padded row
+            // (first group = byte 12, which holds padded columns -1..2) and one per padded row
+            auto refl = [](int p, int len) { p = p < 0 ? -p : p; return p >= len ? 2 * len - 2 - p : p; };
+            const int pw = L.w + 2 * ORBB_BORDER, ph = L.h + 2 * ORBB_BORDER;
+            const int nq = (ORBB_ROI_X0 + L.w + ORBB_BORDER - 12 + 3) / 4;
+            std::vector<uint4> rsh(2 * (size_t)nq);
+            bool ok = true;
+            for (int q = 0; q < nq; ++q) {
+                int sxj[4]; unsigned wj[4];
+                for (int j = 0; j < 4; ++j) {
+                    const int px = std::min(std::max(12 + 4 * q + j - ORBB_PAD_X0, 0), pw - 1);
+                    const int rx = refl(px - ORBB_BORDER, L.w);
+                    if (L.area2x) { sxj[j] = 2 * rx; wj[j] = 1u | (1u << 16); }
+                    else { sxj[j] = xofs[rx]; wj[j] = (unsigned)(uint16_t)xa[rx].x | ((unsigned)(uint16_t)xa[rx].y << 16); }
+                }
+                unsigned off[2], sel[2];
+                for (int pr = 0; pr < 2; ++pr) {
+                    const int s0 = sxj[2 * pr], s1 = sxj[2 * pr + 1];
+                    const int base = std::min(s0, s1) & ~3;
+                    const int n[4] = {s0 - base, s0 + 1 - base, s1 - base, s1 + 1 - base};
+                    sel[pr] = 0;
+                    for (int k = 0; k < 4; ++k) { if (n[k] > 7) ok = false; sel[pr] |= (unsigned)(n[k] & 7) << (4 * k); }
+                    off[pr] = (unsigned)(ORBB_ROI_X0 + base);
+                }
+                rsh[2 * q] = make_uint4(off[0], sel[0], off[1], sel[1]);
+                rsh[2 * q + 1] = make_uint4(wj[0], wj[1], wj[2], wj[3]);
+            }
+            std::vector<int4> rsv((size_t)ph);
+            for (int py = 0; py < ph; ++py) {
+                const int ry = refl(py - ORBB_BORDER, L.h);
+                if (L.area2x) rsv[py] = make_int4(2 * ry, 2 * ry + 1, 0, 0);
+                else rsv[py] = make_int4(yr[ry].x, yr[ry].y, (int)yb[ry].x << 16, (int)yb[ry].y << 16);
+            }
+            uint4 *drsh; int4 *drsv;
+            CKC(upload(h, &drsh, rsh)); CKC(upload(h, &drsv, rsv));
+            L.rs_h = drsh; L.rs_v = drsv; L.rs_nq = nq;
+            L.rs_ok = (ok && !getenv("ORBB_RESIZE_TILED")) ? 1 : 0;
         }
         // ---- per-cell FAST grid (upstream ComputeKeyPointsOctTree)
         const int W = L.w - 32, H = L.h - 32;  // maxBorder - minBorder

@@ -34,6 +34,10 @@ struct LevelDev {
     const int2 *yrows;           // [h] (clipped row0,row1)
     const short2 *ybeta;         // [h] (b0,b1)
     int src_w, src_h, area2x;
+    // table-driven resize (k_resize_rows): per 4-byte group of the padded output row and per padded output row
+    const uint4 *rs_h;           // [2*rs_nq]: {byte offset A, PRMT selector A, byte offset B, selector B}, {4 x (a0 | a1<<16)}
+    const int4 *rs_v;            // [h+38]: {src row0, src row1, b0<<16, b1<<16} (reflect-101 already applied)
+    int rs_nq, rs_ok;            // groups per row (first group = padded byte 12); 0 => fall back to k_resize
     // per-cell FAST grid (tested range starts at ROI (19,19))
     int w_cell, h_cell, n_cell_x, n_cell_y;
     // quadtree
