@@ -33,7 +33,8 @@ __device__ __forceinline__ float fast_atan2_deg(float y, float x) {
     return a;
 }
 
-#define ORB_WARPS 8
+#define ORB_WARPS 4
+#define ORB_KPW 8                       // keypoint slots per warp: the per-keypoint scalar math runs one slot per lane
 #define PATCH_R 19                      // rotated pattern reach: |(13,13)| = 18.4 -> 19
 #define PATCH_ROWS (2 * PATCH_R + 1)    // 39
 #define PATCH_PITCH 44                  // 11 aligned words cover 39 columns at any byte phase
@@ -43,117 +44,155 @@ __device__ __forceinline__ constexpr int umax_of(int av) {
     return (int)((0x3689ABCDDEEEFFFFull >> (4 * av)) & 15ull);
 }
 
-__global__ void __launch_bounds__(ORB_WARPS * 32)
+// warp = ORB_KPW consecutive keypoint slots, warp-synchronous (no block barriers):
+//   phase 0  lanes 0..7: slot -> (level, x, y, response, output index), kept in registers and broadcast by shuffle
+//   phase A  per slot: IC_Angle moments, lane = patch column (coalesced row reads of the un-blurred level)
+//   phase S  lanes 0..7: fastAtan2, sincos(double) and the cv::KeyPoint record -- the scalar chain that a
+//            warp-per-keypoint kernel would execute 32x redundantly now runs once per 8 keypoints
+//   phase B  per slot: stage the 39x39 blurred patch, lane i builds descriptor byte i (its 16 pattern points sit in
+//            registers as floats, converted once per warp)
+__global__ void __launch_bounds__(ORB_WARPS * 32, 8)
 k_angle_orb(const LevelDev *__restrict__ levels, int n_levels, const int *__restrict__ sel_count,
             const int8_t *__restrict__ pattern, const int *__restrict__ slot_level, const int *__restrict__ slot_base,
             int n_slots, orbb_keypoint *__restrict__ out_kp, uint8_t *__restrict__ out_desc,
             int *__restrict__ out_counts, int max_kp, int frame_base) {
     __shared__ __align__(16) uint8_t s_patch[ORB_WARPS][PATCH_ROWS * PATCH_PITCH];
+    const unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int gslot = blockIdx.x * ORB_WARPS + warp;
     const int frame = blockIdx.y + frame_base;
-    if (gslot >= n_slots) return;
-    const int level = slot_level[gslot], slot = gslot - slot_base[level];
     const int *cnt = sel_count + frame * n_levels;
-    const LevelDev &L = levels[level];
-    const int my_cnt = min(cnt[level], L.sel_cap);
-    int off = 0;
-    for (int l = 0; l < level; ++l) off += min(cnt[l], levels[l].sel_cap);
-    if (level == 0 && slot == 0 && lane == 0) {
-        int total = my_cnt;
-        for (int l = 1; l < n_levels; ++l) total += min(cnt[l], levels[l].sel_cap);
-        out_counts[frame] = min(total, max_kp);
-    }
-    if (slot >= my_cnt || off + slot >= max_kp) return;
 
-    const uint32_t c = L.sel[(size_t)frame * L.sel_cap + slot];
-    const int x = (int)(c & 0xfffu) + ORBB_MIN_BORDER, y = (int)((c >> 12) & 0xfffu) + ORBB_MIN_BORDER;
-    const int resp = (int)(c >> 24) - 1;  // cv::FAST response = arc score - 1
-
-    // ---- stage the 39x39 blurred patch with aligned 32-bit loads
-    uint8_t *patch = s_patch[warp];
-    const int xa = (x - PATCH_R) & ~3, poff = (x - PATCH_R) - xa;
+    // ---- phase 0
+    int my_o = -1, my_x = 0, my_y = 0, my_level = 0, my_resp = 0;
     {
-        const uint8_t *src = L.blur + (size_t)frame * L.blur_stride + (size_t)(y - PATCH_R) * L.pitch + xa;
-        const int lr = lane >> 4, lw = lane & 15;  // 2 rows per warp instruction, 11 of 16 lanes active
-        if (lw < 11) {
-            const uint8_t *g = src + (size_t)lr * L.pitch + 4 * lw;
-            const size_t step = 2 * (size_t)L.pitch;
-            uint32_t v[(PATCH_ROWS + 1) / 2];
-#pragma unroll
-            for (int r = 0; r < (PATCH_ROWS + 1) / 2; ++r)  // all 20 loads in flight before the first store
-                v[r] = (2 * r + lr < PATCH_ROWS) ? *reinterpret_cast<const uint32_t *>(g + r * step) : 0u;
-#pragma unroll
-            for (int r = 0; r < (PATCH_ROWS + 1) / 2; ++r)
-                if (2 * r + lr < PATCH_ROWS) reinterpret_cast<uint32_t *>(patch + (2 * r + lr) * PATCH_PITCH)[lw] = v[r];
+        const int gslot = (blockIdx.x * ORB_WARPS + warp) * ORB_KPW + lane;
+        if (lane < ORB_KPW && gslot < n_slots) {
+            my_level = slot_level[gslot];
+            const int slot = gslot - slot_base[my_level];
+            const LevelDev &L = levels[my_level];
+            const int my_cnt = min(cnt[my_level], L.sel_cap);
+            int off = 0;
+            for (int l = 0; l < my_level; ++l) off += min(cnt[l], levels[l].sel_cap);
+            if (gslot == 0) {
+                int total = my_cnt;
+                for (int l = 1; l < n_levels; ++l) total += min(cnt[l], levels[l].sel_cap);
+                out_counts[frame] = min(total, max_kp);
+            }
+            if (slot < my_cnt && off + slot < max_kp) {
+                const uint32_t c = L.sel[(size_t)frame * L.sel_cap + slot];
+                my_x = (int)(c & 0xfffu) + ORBB_MIN_BORDER;
+                my_y = (int)((c >> 12) & 0xfffu) + ORBB_MIN_BORDER;
+                my_resp = (int)(c >> 24) - 1;  // cv::FAST response = arc score - 1
+                my_o = off + slot;
+            }
         }
     }
+    const unsigned live = __ballot_sync(FULL, my_o >= 0);
+    if (live == 0) return;
 
-    // ---- IC_Angle: lane = column u (coalesced row reads), rows unrolled with their compile-time umax
+    // ---- phase A: IC_Angle moments; rows unrolled with their compile-time umax
     const int u = lane - 15, au = u < 0 ? -u : u;
-    const int pitch = L.pitch;
-    const uint8_t *rowp = L.img + (size_t)frame * L.frame_stride + (size_t)(y + ORBB_BORDER - 15) * pitch + ORBB_ROI_X0 + x + u;
-    int colsum = 0, m01 = 0;
+    int my_m01 = 0, my_m10 = 0;
+#pragma unroll 1
+    for (int i = 0; i < ORB_KPW; ++i) {
+        if (!((live >> i) & 1u)) continue;
+        const LevelDev &L = levels[__shfl_sync(FULL, my_level, i)];
+        const int pitch = L.pitch;
+        const uint8_t *rowp = L.img + (size_t)frame * L.frame_stride +
+                              (size_t)(__shfl_sync(FULL, my_y, i) + ORBB_BORDER - 15) * pitch + ORBB_ROI_X0 +
+                              __shfl_sync(FULL, my_x, i) + u;
+        int colsum = 0, m01 = 0;
 #pragma unroll
-    for (int v = -15; v <= 15; ++v) {
-        const int d = umax_of(v < 0 ? -v : v);
-        const int val = (au <= d) ? (int)*rowp : 0;  // lane 31 has au = 16 > d
-        rowp += pitch;
-        colsum += val;
-        m01 += v * val;
-    }
-    int m10 = u * colsum;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        m10 += __shfl_xor_sync(0xffffffffu, m10, o);
-        m01 += __shfl_xor_sync(0xffffffffu, m01, o);
-    }
-    const float angle = fast_atan2_deg((float)m01, (float)m10);
-
-    // ---- steered BRIEF on the staged patch
-    const float factor_pi = (float)(3.14159265358979323846 / 180.0);  // == (float)(CV_PI/180.f)
-    const float rad = __fmul_rn(angle, factor_pi);
-    double sd, cd;
-    sincos((double)rad, &sd, &cd);
-    const float a = (float)cd, b = (float)sd;
-    const int8_t *pat = pattern + lane * 32;
-    const int4 q0 = *reinterpret_cast<const int4 *>(pat), q1 = *reinterpret_cast<const int4 *>(pat + 16);
-    const int w[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
-    __syncwarp();
-    const uint8_t *pc = patch + PATCH_R * PATCH_PITCH + PATCH_R + poff;
-    int val = 0;
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-        const float x0 = (float)(int8_t)(w[k] & 0xff), y0 = (float)(int8_t)((w[k] >> 8) & 0xff);
-        const float x1 = (float)(int8_t)((w[k] >> 16) & 0xff), y1 = (float)(int8_t)((w[k] >> 24) & 0xff);
-        const int ry0 = __float2int_rn(__fadd_rn(__fmul_rn(x0, b), __fmul_rn(y0, a)));
-        const int rx0 = __float2int_rn(__fsub_rn(__fmul_rn(x0, a), __fmul_rn(y0, b)));
-        const int ry1 = __float2int_rn(__fadd_rn(__fmul_rn(x1, b), __fmul_rn(y1, a)));
-        const int rx1 = __float2int_rn(__fsub_rn(__fmul_rn(x1, a), __fmul_rn(y1, b)));
-        const int t0 = pc[ry0 * PATCH_PITCH + rx0], t1 = pc[ry1 * PATCH_PITCH + rx1];
-        val |= (t0 < t1) << k;
-    }
-    const size_t o = (size_t)frame * max_kp + off + slot;
-    out_desc[o * 32 + lane] = (uint8_t)val;
-    if (lane < 7) {  // 28-byte cv::KeyPoint written as 7 coalesced words
-        float f;
-        switch (lane) {
-            case 0: f = level ? __fmul_rn((float)x, L.scale) : (float)x; break;
-            case 1: f = level ? __fmul_rn((float)y, L.scale) : (float)y; break;
-            case 2: f = L.patch_size; break;
-            case 3: f = angle; break;
-            case 4: f = (float)resp; break;
-            case 5: f = __int_as_float(level); break;
-            default: f = __int_as_float(-1); break;
+        for (int v = -15; v <= 15; ++v) {
+            const int d = umax_of(v < 0 ? -v : v);
+            const int val = (au <= d) ? (int)*rowp : 0;  // lane 31 has au = 16 > d
+            rowp += pitch;
+            colsum += val;
+            m01 += v * val;
         }
-        reinterpret_cast<float *>(out_kp + o)[lane] = f;
+        const int m10 = __reduce_add_sync(FULL, u * colsum);
+        m01 = __reduce_add_sync(FULL, m01);
+        if (lane == i) { my_m01 = m01; my_m10 = m10; }
+    }
+
+    // ---- phase S
+    float my_a = 0.f, my_b = 0.f;
+    if (my_o >= 0) {
+        const float angle = fast_atan2_deg((float)my_m01, (float)my_m10);
+        const float factor_pi = (float)(3.14159265358979323846 / 180.0);  // == (float)(CV_PI/180.f)
+        const float rad = __fmul_rn(angle, factor_pi);
+        double sd, cd;
+        sincos((double)rad, &sd, &cd);
+        my_a = (float)cd; my_b = (float)sd;
+        const LevelDev &L = levels[my_level];
+        float *kp = reinterpret_cast<float *>(out_kp + (size_t)frame * max_kp + my_o);
+        kp[0] = my_level ? __fmul_rn((float)my_x, L.scale) : (float)my_x;
+        kp[1] = my_level ? __fmul_rn((float)my_y, L.scale) : (float)my_y;
+        kp[2] = L.patch_size;
+        kp[3] = angle;
+        kp[4] = (float)my_resp;
+        kp[5] = __int_as_float(my_level);
+        kp[6] = __int_as_float(-1);
+    }
+    // pattern points of this lane's descriptor byte, as floats
+    float px0[8], py0[8], px1[8], py1[8];
+    {
+        const int8_t *pat = pattern + lane * 32;
+        const int4 q0 = *reinterpret_cast<const int4 *>(pat), q1 = *reinterpret_cast<const int4 *>(pat + 16);
+        const int w[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            px0[k] = (float)(int8_t)(w[k] & 0xff); py0[k] = (float)(int8_t)((w[k] >> 8) & 0xff);
+            px1[k] = (float)(int8_t)((w[k] >> 16) & 0xff); py1[k] = (float)(int8_t)((w[k] >> 24) & 0xff);
+        }
+    }
+
+    // ---- phase B: steered BRIEF on the staged blurred patch
+    uint8_t *patch = s_patch[warp];
+#pragma unroll 1
+    for (int i = 0; i < ORB_KPW; ++i) {
+        if (!((live >> i) & 1u)) continue;
+        const LevelDev &L = levels[__shfl_sync(FULL, my_level, i)];
+        const int x = __shfl_sync(FULL, my_x, i), y = __shfl_sync(FULL, my_y, i), o = __shfl_sync(FULL, my_o, i);
+        const float a = __shfl_sync(FULL, my_a, i), b = __shfl_sync(FULL, my_b, i);
+        const int xa = (x - PATCH_R) & ~3, poff = (x - PATCH_R) - xa;
+        __syncwarp();  // the previous slot's reads of the patch are done
+        {
+            const uint8_t *src = L.blur + (size_t)frame * L.blur_stride + (size_t)(y - PATCH_R) * L.pitch + xa;
+            const int lr = lane >> 4, lw = lane & 15;  // 2 rows per warp instruction, 11 of 16 lanes active
+            if (lw < 11) {
+                const uint8_t *g = src + (size_t)lr * L.pitch + 4 * lw;
+                const size_t step = 2 * (size_t)L.pitch;
+                uint32_t v[(PATCH_ROWS + 1) / 2];
+#pragma unroll
+                for (int r = 0; r < (PATCH_ROWS + 1) / 2; ++r)  // all 20 loads in flight before the first store
+                    v[r] = (2 * r + lr < PATCH_ROWS) ? *reinterpret_cast<const uint32_t *>(g + r * step) : 0u;
+#pragma unroll
+                for (int r = 0; r < (PATCH_ROWS + 1) / 2; ++r)
+                    if (2 * r + lr < PATCH_ROWS) reinterpret_cast<uint32_t *>(patch + (2 * r + lr) * PATCH_PITCH)[lw] = v[r];
+            }
+        }
+        __syncwarp();
+        const uint8_t *pc = patch + PATCH_R * PATCH_PITCH + PATCH_R + poff;
+        int val = 0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const int ry0 = __float2int_rn(__fadd_rn(__fmul_rn(px0[k], b), __fmul_rn(py0[k], a)));
+            const int rx0 = __float2int_rn(__fsub_rn(__fmul_rn(px0[k], a), __fmul_rn(py0[k], b)));
+            const int ry1 = __float2int_rn(__fadd_rn(__fmul_rn(px1[k], b), __fmul_rn(py1[k], a)));
+            const int rx1 = __float2int_rn(__fsub_rn(__fmul_rn(px1[k], a), __fmul_rn(py1[k], b)));
+            const int t0 = pc[ry0 * PATCH_PITCH + rx0], t1 = pc[ry1 * PATCH_PITCH + rx1];
+            val |= (t0 < t1) << k;
+        }
+        out_desc[((size_t)frame * max_kp + o) * 32 + lane] = (uint8_t)val;
     }
 }
 
 cudaError_t launch_angle_orb(const LevelDev *d_levels, int n_levels, const int *d_sel_count, const int8_t *d_pattern,
                              const int *d_slot_level, const int *d_slot_base, int n_slots, int frame_base,
                              int n_frames, orbb_keypoint *d_kp, uint8_t *d_desc, int *d_counts, int max_kp, cudaStream_t st) {
-    dim3 grid((n_slots + ORB_WARPS - 1) / ORB_WARPS, n_frames);
+    const int per_cta = ORB_WARPS * ORB_KPW;
+    dim3 grid((n_slots + per_cta - 1) / per_cta, n_frames);
     k_angle_orb<<<grid, ORB_WARPS * 32, 0, st>>>(d_levels, n_levels, d_sel_count, d_pattern, d_slot_level, d_slot_base,
                                                  n_slots, d_kp, d_desc, d_counts, max_kp, frame_base);
     return cudaGetLastError();

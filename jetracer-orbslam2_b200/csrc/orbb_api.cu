@@ -75,6 +75,9 @@ struct orbb_handle {
     cudaStream_t s_comp[2] = {nullptr, nullptr};   // alternating compute streams (chunk tails overlap)
     cudaStream_t s_side = nullptr;                 // side stream of the device entry point (blur under FAST/quadtree)
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    cudaStream_t s_dev[7] = {};                    // extra streams of the device entry point (batch split in parts)
+    cudaEvent_t ev_dev[7] = {};
+    int dev_split = 2;
     cudaEvent_t ev_fence = nullptr, ev_done[2] = {nullptr, nullptr};
     std::vector<cudaEvent_t> ev_in, ev_comp;
     std::vector<void *> allocs;
@@ -146,6 +149,10 @@ extern "C" int orbb_destroy(orbb_handle *h) {
     }
     if (h->ev_fence) cudaEventDestroy(h->ev_fence);
     if (h->s_side) cudaStreamDestroy(h->s_side);
+    for (int i = 0; i < 7; ++i) {
+        if (h->s_dev[i]) cudaStreamDestroy(h->s_dev[i]);
+        if (h->ev_dev[i]) cudaEventDestroy(h->ev_dev[i]);
+    }
     if (h->ev_fork) cudaEventDestroy(h->ev_fork);
     if (h->ev_join) cudaEventDestroy(h->ev_join);
     for (int i = 0; i < 2; ++i) {
@@ -442,6 +449,11 @@ extern "C" int orbb_create(orbb_handle **out, const orbb_params *params, int wid
     }
     CKC(cudaEventCreateWithFlags(&h->ev_fence, cudaEventDisableTiming));
     CKC(cudaStreamCreateWithFlags(&h->s_side, cudaStreamNonBlocking));
+    for (int i = 0; i < 7; ++i) {
+        CKC(cudaStreamCreateWithFlags(&h->s_dev[i], cudaStreamNonBlocking));
+        CKC(cudaEventCreateWithFlags(&h->ev_dev[i], cudaEventDisableTiming));
+    }
+    if (const char *e = getenv("ORBB_DEV_SPLIT")) h->dev_split = std::min(std::max(atoi(e), 1), 8);
     CKC(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
     CKC(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
     h->ev_in.resize(ORBB_MAX_CHUNKS); h->ev_comp.resize(ORBB_MAX_CHUNKS);
@@ -609,17 +621,22 @@ extern "C" int orbb_extract_batch_device(orbb_handle *h, const uint8_t *d_images
     if (n_frames < 64)
         return run_all(h, d_images, pitch, frame_stride, 0, n_frames, d_kp, d_desc, d_counts, max_kp, st, h->s_side,
                        h->ev_fork, h->ev_join);
-    // Large batches: two halves on two streams.  FAST saturates the issue slots while the quadtree kernel is
-    // latency bound, so the halves interleave (one half's quadtree runs under the other half's FAST).
-    const int na = n_frames / 2, nb = n_frames - na;
+    // Large batches: parts of the batch on separate streams.  FAST saturates the issue slots while the quadtree
+    // kernel is latency bound, so the parts interleave (one part's quadtree runs under another part's FAST).
+    const int parts = std::max(1, std::min(h->dev_split, n_frames / 32));
     CK(h, cudaEventRecord(h->ev_fence, st));
-    CK(h, cudaStreamWaitEvent(h->s_comp[0], h->ev_fence, 0));
-    int rc = run_all(h, d_images, pitch, frame_stride, 0, na, d_kp, d_desc, d_counts, max_kp, st);
-    if (rc) return rc;
-    rc = run_all(h, d_images + frame_stride * na, pitch, frame_stride, na, nb, d_kp, d_desc, d_counts, max_kp, h->s_comp[0]);
-    if (rc) return rc;
-    CK(h, cudaEventRecord(h->ev_join, h->s_comp[0]));
-    CK(h, cudaStreamWaitEvent(st, h->ev_join, 0));
+    for (int k = 0, f0 = 0; k < parts; ++k) {
+        const int n = (n_frames - f0) / (parts - k);
+        cudaStream_t sk = k == 0 ? st : h->s_dev[k - 1];
+        if (k) CK(h, cudaStreamWaitEvent(sk, h->ev_fence, 0));
+        const int rc = run_all(h, d_images + frame_stride * f0, pitch, frame_stride, f0, n, d_kp, d_desc, d_counts, max_kp, sk);
+        if (rc) return rc;
+        if (k) {
+            CK(h, cudaEventRecord(h->ev_dev[k - 1], sk));
+            CK(h, cudaStreamWaitEvent(st, h->ev_dev[k - 1], 0));
+        }
+        f0 += n;
+    }
     return ORBB_OK;
 }
 
