@@ -173,6 +173,76 @@ int orbb_match_windowed(orbb_handle *h, const uint8_t *d_query, const void *d_qu
                         int max_hamming, int32_t *d_idx, int32_t *d_dist, int32_t *d_nmatched,
                         void *cuda_stream);
 
+/* ---------------------------------------------------------------- RGB-D association
+ * The step right after descriptors in SlamGpuPipeline::buildStream (buildStream.cpp:376-394, 468-487, 523-556):
+ * depth aligned to the image the keypoints live in, keypoints lifted to 3-D, previous-frame points reprojected
+ * and matched inside a pixel window, matched 3-D pairs compacted for the pose solver.  Arithmetic follows the
+ * reference kernels (a CUDA copy of librealsense's rsutil.h) with un-fused IEEE float32/float64 operations. */
+
+/* == rs2_intrinsics / rs2_extrinsics of librealsense2 (rs_types.h), bit-compatible, so the structs the reference
+ * uploads in SlamGpuPipeline::upload_intristics (SlamGpuPipeline.cpp:60-91) can be passed as they are. */
+typedef enum {
+    ORBB_DISTORTION_NONE = 0,
+    ORBB_DISTORTION_MODIFIED_BROWN_CONRADY = 1,
+    ORBB_DISTORTION_INVERSE_BROWN_CONRADY = 2,
+    ORBB_DISTORTION_FTHETA = 3, /* not supported (atan/tan chain is not reproducible bit-exactly): ORBB_ERR_INVALID */
+    ORBB_DISTORTION_BROWN_CONRADY = 4,
+    ORBB_DISTORTION_KANNALA_BRANDT4 = 5
+} orbb_distortion;
+typedef struct {
+    int32_t width, height;
+    float ppx, ppy, fx, fy;
+    int32_t model; /* orbb_distortion */
+    float coeffs[5];
+} orbb_intrinsics;
+typedef struct {
+    float rotation[9]; /* column-major 3x3 */
+    float translation[3];
+} orbb_extrinsics;
+
+/* Jetracer::align_depth_to_other (src/cuda/cuda-align.cuh:41-50, kernels cuda-align.cu:122-286, launcher :366-399):
+ * every depth pixel with a non-zero value is deprojected at its top-left (-0.5) and bottom-right (+0.5) corner,
+ * transformed, projected into the other image; the rectangle between the two rounded corners receives
+ * min(raw depth); pixels nothing maps to are 0.  One fused scatter kernel (no int2 pixel map in HBM) + a vectorised
+ * sentinel->0 pass.  d_depth: DEVICE [n_frames][depth.height][depth.width] u16; d_aligned_out: DEVICE
+ * [n_frames][other.height][other.width] u32.  Intrinsics/extrinsics are HOST structs (passed by value to the
+ * kernel).  Async on stream. */
+int orbb_align_depth_to_other(orbb_handle *h, const uint16_t *d_depth, int n_frames, float depth_scale,
+                              const orbb_intrinsics *depth_intrin, const orbb_intrinsics *other_intrin,
+                              const orbb_extrinsics *depth_to_other, uint32_t *d_aligned_out, void *cuda_stream);
+
+/* Jetracer::keypoint_pixel_to_point (src/cuda/cuda-align.cuh:52-65, kernel cuda-align.cu:282-364, launcher :401-443):
+ * keep the keypoints with aligned depth > 1 and response > 1, lift them to 3-D (float64, raw depth units) and
+ * compact keypoints, descriptors and points.  Differences from the reference, both deliberate: the depth is read at
+ * (int(x+0.5), int(y+0.5)) -- the reference indexes the column with pos.y (cuda-align.cu:332) -- and
+ * the compaction keeps input order (the reference's atomicAdd order is nondeterministic).
+ * Inputs are the outputs of orbb_extract_batch_device ([n_frames][max_kp] keypoints, [..][32] descriptors,
+ * [n_frames] counts); outputs have the same strides; d_points is [n_frames][max_kp][3] float64;
+ * d_valid_counts [n_frames].  In-place (out == in) is NOT allowed.  Async on stream. */
+int orbb_keypoint_pixel_to_point(orbb_handle *h, const uint32_t *d_aligned_depth, const orbb_intrinsics *other_intrin,
+                                 int n_frames, const orbb_keypoint *d_kp_in, const uint8_t *d_desc_in,
+                                 const int32_t *d_counts_in, int max_kp, orbb_keypoint *d_kp_out, uint8_t *d_desc_out,
+                                 double *d_points, int32_t *d_valid_counts, void *cuda_stream);
+
+/* kernel_reproject_prev_points (src/cuda/post_processing.cu:72-90): pos = project(T * [p;1]) with T a column-major
+ * 4x4 float64 (Eigen::Matrix4d layout).  d_T: DEVICE [n_frames][16] or NULL for identity.  d_pos_out:
+ * [n_frames][max_kp] float2.  Async on stream. */
+int orbb_reproject_points(orbb_handle *h, const double *d_points, const int32_t *d_counts, int n_frames, int max_kp,
+                          const double *d_T, const orbb_intrinsics *intrin, float *d_pos_out, void *cuda_stream);
+
+/* kernel_match_keypoints over a batch of frame pairs (src/cuda/post_processing.cu:92-200): frame f's query set
+ * (descriptors d_query[f][..], positions d_query_xy, q_counts[f] rows) against its train set; same gate and tie rule as
+ * orbb_match_windowed.  Then the matched 3-D pairs are compacted in query order (the reference's atomicAdd order is
+ * nondeterministic): d_prev_matched/d_curr_matched [n_frames][max_kp][3] float64 gathered from d_query_points /
+ * d_train_points, d_xy_u16 [n_frames][2][max_kp] (x row then y row, uint16_t(train pos), as :193-194),
+ * d_nmatched [n_frames].  Point/xy outputs may be NULL.  d_idx/d_dist: [n_frames][max_kp].  Async on stream. */
+int orbb_match_windowed_batch(orbb_handle *h, const uint8_t *d_query, const float *d_query_xy, const int32_t *d_q_counts,
+                              const uint8_t *d_train, const void *d_train_xy, int t_xy_stride,
+                              const int32_t *d_t_counts, int n_frames, int max_kp, float max_px, int max_hamming,
+                              int32_t *d_idx, int32_t *d_dist, const double *d_query_points,
+                              const double *d_train_points, double *d_prev_matched, double *d_curr_matched,
+                              uint16_t *d_xy_u16, int32_t *d_nmatched, void *cuda_stream);
+
 /* ---------------------------------------------------------------- debug / parity access
  * Download stage outputs of frame `frame` of the last batch to HOST memory (synchronises). */
 /* padded level, contiguous (w+38) x (h+38) */

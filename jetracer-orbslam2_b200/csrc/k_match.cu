@@ -111,12 +111,24 @@ k_match_merge(const int4 *__restrict__ partial, int partial_stride, int n_split,
 // first, XOR/POPC only for the few candidates inside the window.
 #define WIN_THREADS 128
 #define WIN_TILE 128
+// Batched form (q_counts != nullptr): blockIdx.y = frame pair, rows of frame f start at f * max_kp in every array and
+// the set sizes come from the device-side count arrays.
 __global__ void __launch_bounds__(WIN_THREADS)
 k_match_windowed(const uint4 *__restrict__ query, const uint8_t *__restrict__ q_xy, int q_stride, int nq,
                  const uint4 *__restrict__ train, const uint8_t *__restrict__ t_xy, int t_stride, int nt, float max_px,
-                 int max_hamming, int *__restrict__ out_idx, int *__restrict__ out_dist, int *__restrict__ n_matched) {
+                 int max_hamming, int *__restrict__ out_idx, int *__restrict__ out_dist, int *__restrict__ n_matched,
+                 const int *__restrict__ q_counts, const int *__restrict__ t_counts, int max_kp) {
     __shared__ uint4 s_d[WIN_TILE * 2];
     __shared__ float2 s_xy[WIN_TILE];
+    if (q_counts) {
+        const size_t f = blockIdx.y, row0 = f * max_kp;
+        nq = min(q_counts[f], max_kp); nt = min(t_counts[f], max_kp);
+        if ((int)(blockIdx.x * WIN_THREADS) >= nq) return;
+        query += 2 * row0; train += 2 * row0;
+        q_xy += row0 * q_stride; t_xy += row0 * t_stride;
+        out_idx += row0; out_dist += row0;
+        n_matched = nullptr;
+    }
     const int q = blockIdx.x * WIN_THREADS + threadIdx.x;
     const int qq = min(q, nq - 1);
     const uint4 qa = query[(size_t)qq * 2], qb = query[(size_t)qq * 2 + 1];
@@ -161,7 +173,7 @@ cudaError_t launch_match_windowed(const uint8_t *d_q, const void *d_q_xy, int q_
     k_match_windowed<<<(nq + WIN_THREADS - 1) / WIN_THREADS, WIN_THREADS, 0, st>>>(
         reinterpret_cast<const uint4 *>(d_q), static_cast<const uint8_t *>(d_q_xy), q_stride, nq,
         reinterpret_cast<const uint4 *>(d_t), static_cast<const uint8_t *>(d_t_xy), t_stride, nt, max_px, max_hamming, d_idx,
-        d_dist, d_nmatched);
+        d_dist, d_nmatched, nullptr, nullptr, 0);
     return cudaGetLastError();
 }
 
@@ -182,6 +194,18 @@ cudaError_t launch_match(const uint8_t *d_q, const uint8_t *d_t, const int *d_q_
     }
     k_match_merge<<<(nq_total + 255) / 256, 256, 0, st>>>(d_partial, partial_stride, n_split, nq_total, k, ratio, d_idx,
                                                            d_dist, d_accept, d_naccept);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_match_windowed_batch(const uint8_t *d_q, const void *d_q_xy, int q_stride, const int *d_q_counts,
+                                        const uint8_t *d_t, const void *d_t_xy, int t_stride, const int *d_t_counts,
+                                        int n_frames, int max_kp, float max_px, int max_hamming, int *d_idx, int *d_dist,
+                                        cudaStream_t st) {
+    dim3 grid((max_kp + WIN_THREADS - 1) / WIN_THREADS, n_frames);
+    k_match_windowed<<<grid, WIN_THREADS, 0, st>>>(
+        reinterpret_cast<const uint4 *>(d_q), static_cast<const uint8_t *>(d_q_xy), q_stride, 0,
+        reinterpret_cast<const uint4 *>(d_t), static_cast<const uint8_t *>(d_t_xy), t_stride, 0, max_px, max_hamming, d_idx,
+        d_dist, nullptr, d_q_counts, d_t_counts, max_kp);
     return cudaGetLastError();
 }
 

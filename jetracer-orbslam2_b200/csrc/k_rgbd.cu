@@ -1,0 +1,269 @@
+// k_rgbd.cu -- RGB-D association: the stages that follow the descriptors in SlamGpuPipeline::buildStream
+// (reference src/SlamGpuPipeline/buildStream.cpp:376-394, 468-487, 523-556).
+//   k_align_scatter / k_align_finish  replace Jetracer::align_depth_to_other (src/cuda/cuda-align.cu:122-286,
+//                                     launcher :366-399): four kernels and a 16 B/pixel int2 map in the reference,
+//                                     here one scatter kernel that maps both corners of a depth pixel in registers
+//                                     and issues the RED.MIN itself, plus a 128-bit sentinel->0 pass;
+//   k_kp_to_point                     replaces kernel_keypoint_pixel_to_point (cuda-align.cu:282-364): depth gate,
+//                                     float64 deprojection, order-preserving block compaction;
+//   k_reproject                       replaces kernel_reproject_prev_points (src/cuda/post_processing.cu:72-90);
+//   k_compact_pairs                   the compaction tail of kernel_match_keypoints (post_processing.cu:176-197).
+// Arithmetic = the reference's rsutil.h copies (cuda-align.cu:26-120, post_processing.cu:10-43), every float32 and
+// float64 operation rounded on its own (_rn intrinsics: the library is built with -fmad=false, the intrinsics make
+// the intent explicit), so that a plain C restatement (oracle/rgbd_oracle.c, -ffp-contract=off) reproduces it bit
+// for bit.  Bound: the scatter is L2-atomic / HBM bound (2 B read + ~4 RED per depth pixel), everything else is
+// launch-latency sized (about 1000 keypoints per frame).
+#include "orbb_internal.cuh"
+
+namespace orbb {
+
+struct AlignArgs {
+    orbb_intrinsics d, o;
+    orbb_extrinsics e;
+    float depth_scale;
+};
+
+__device__ __forceinline__ float fmul(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ float fadd(float a, float b) { return __fadd_rn(a, b); }
+__device__ __forceinline__ double dmul(double a, double b) { return __dmul_rn(a, b); }
+__device__ __forceinline__ double dadd(double a, double b) { return __dadd_rn(a, b); }
+
+// radial factor 1 + c0 r2 + c1 r2 r2 + c4 r2 r2 r2, left to right as the reference writes it
+__device__ __forceinline__ float radial_f(const float *c, float r2) {
+    return fadd(fadd(fadd(1.0f, fmul(c[0], r2)), fmul(fmul(c[1], r2), r2)), fmul(fmul(fmul(c[4], r2), r2), r2));
+}
+
+// rs2_deproject_pixel_to_point (cuda-align.cu:58-83)
+__device__ __forceinline__ void deproject(float pt[3], const orbb_intrinsics &in, float px, float py, float depth) {
+    float x = __fdiv_rn(__fsub_rn(px, in.ppx), in.fx);
+    float y = __fdiv_rn(__fsub_rn(py, in.ppy), in.fy);
+    if (in.model == ORBB_DISTORTION_INVERSE_BROWN_CONRADY) {
+        const float r2 = fadd(fmul(x, x), fmul(y, y));
+        const float f = radial_f(in.coeffs, r2);
+        const float ux = fadd(fadd(fmul(x, f), fmul(fmul(fmul(2.0f, in.coeffs[2]), x), y)),
+                              fmul(in.coeffs[3], fadd(r2, fmul(fmul(2.0f, x), x))));
+        const float uy = fadd(fadd(fmul(y, f), fmul(fmul(fmul(2.0f, in.coeffs[3]), x), y)),
+                              fmul(in.coeffs[2], fadd(r2, fmul(fmul(2.0f, y), y))));
+        x = ux; y = uy;
+    }
+    pt[0] = fmul(depth, x); pt[1] = fmul(depth, y); pt[2] = depth;
+}
+
+// the distortion + pinhole tail shared by rs2_project_point_to_pixel (cuda-align.cu:26-56) and its double-input
+// twin (post_processing.cu:10-43)
+__device__ __forceinline__ void project_xy(float pix[2], const orbb_intrinsics &in, float x, float y) {
+    if (in.model == ORBB_DISTORTION_MODIFIED_BROWN_CONRADY) {
+        const float r2 = fadd(fmul(x, x), fmul(y, y));
+        const float f = radial_f(in.coeffs, r2);
+        x = fmul(x, f); y = fmul(y, f);
+        const float dx = fadd(fadd(x, fmul(fmul(fmul(2.0f, in.coeffs[2]), x), y)),
+                              fmul(in.coeffs[3], fadd(r2, fmul(fmul(2.0f, x), x))));
+        const float dy = fadd(fadd(y, fmul(fmul(fmul(2.0f, in.coeffs[3]), x), y)),
+                              fmul(in.coeffs[2], fadd(r2, fmul(fmul(2.0f, y), y))));
+        x = dx; y = dy;
+    }
+    pix[0] = fadd(fmul(x, in.fx), in.ppx);
+    pix[1] = fadd(fmul(y, in.fy), in.ppy);
+}
+
+// ---- depth -> other image.  thread = one depth pixel of one frame.
+__global__ void __launch_bounds__(256) k_align_scatter(const uint16_t *__restrict__ depth, uint32_t *__restrict__ out,
+                                                       const AlignArgs A) {
+    const int x = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * 8 + threadIdx.y;
+    if (x >= A.d.width || y >= A.d.height) return;
+    const size_t f = blockIdx.z;
+    const unsigned raw = depth[(f * A.d.height + y) * A.d.width + x];
+    const float dv = fmul((float)(int)raw, A.depth_scale);
+    if (dv == 0.0f) return;  // no depth data: nothing is written (cuda-align.cu:139-141)
+    int cx[2], cy[2];
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {  // top-left (-0.5) and bottom-right (+0.5) corner of the depth pixel
+        const float shift = c ? 0.5f : -0.5f;
+        float p[3], q[3], pix[2];
+        deproject(p, A.d, fadd((float)x, shift), fadd((float)y, shift), dv);
+        const float *R = A.e.rotation, *T = A.e.translation;
+        q[0] = fadd(fadd(fadd(fmul(R[0], p[0]), fmul(R[3], p[1])), fmul(R[6], p[2])), T[0]);
+        q[1] = fadd(fadd(fadd(fmul(R[1], p[0]), fmul(R[4], p[1])), fmul(R[7], p[2])), T[1]);
+        q[2] = fadd(fadd(fadd(fmul(R[2], p[0]), fmul(R[5], p[1])), fmul(R[8], p[2])), T[2]);
+        project_xy(pix, A.o, __fdiv_rn(q[0], q[2]), __fdiv_rn(q[1], q[2]));
+        cx[c] = (int)fadd(pix[0], 0.5f);  // cvt.rzi: truncation, saturating, NaN -> 0
+        cy[c] = (int)fadd(pix[1], 0.5f);
+    }
+    if (cx[0] < 0 || cy[0] < 0 || cx[1] >= A.o.width || cy[1] >= A.o.height) return;
+    uint32_t *o = out + f * A.o.width * A.o.height;
+    for (int yy = cy[0]; yy <= cy[1]; ++yy)
+        for (int xx = cx[0]; xx <= cx[1]; ++xx) atomicMin(o + (size_t)yy * A.o.width + xx, raw);
+}
+
+// pixels nothing mapped to still hold the 0xFFFFFFFF the buffer was initialised with: they become 0
+__global__ void __launch_bounds__(256) k_align_finish(uint32_t *__restrict__ out, size_t n) {
+    const size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (i + 3 < n) {
+        uint4 v = *reinterpret_cast<uint4 *>(out + i);
+        if (v.x == 0xFFFFFFFFu || v.y == 0xFFFFFFFFu || v.z == 0xFFFFFFFFu || v.w == 0xFFFFFFFFu) {
+            v.x = v.x == 0xFFFFFFFFu ? 0u : v.x; v.y = v.y == 0xFFFFFFFFu ? 0u : v.y;
+            v.z = v.z == 0xFFFFFFFFu ? 0u : v.z; v.w = v.w == 0xFFFFFFFFu ? 0u : v.w;
+            *reinterpret_cast<uint4 *>(out + i) = v;
+        }
+    } else {
+        for (size_t k = i; k < n; ++k)
+            if (out[k] == 0xFFFFFFFFu) out[k] = 0u;
+    }
+}
+
+// ---- order-preserving compaction helper: CTA-wide exclusive rank of `keep` within a chunk of blockDim.x items
+__device__ __forceinline__ int block_rank(bool keep, int *s_warp, int *chunk_total) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    const unsigned m = __ballot_sync(0xffffffffu, keep);
+    __syncthreads();  // s_warp is reused between chunks
+    if (lane == 0) s_warp[warp] = __popc(m);
+    __syncthreads();
+    int before = 0, total = 0;
+    for (int w = 0; w < nw; ++w) {
+        const int c = s_warp[w];
+        before += w < warp ? c : 0;
+        total += c;
+    }
+    *chunk_total = total;
+    return before + __popc(m & ((1u << lane) - 1u));
+}
+
+// ---- keypoints -> 3-D points.  CTA = one frame.
+#define KP_THREADS 256
+__global__ void __launch_bounds__(KP_THREADS)
+k_kp_to_point(const uint32_t *__restrict__ aligned, const orbb_intrinsics in, const orbb_keypoint *__restrict__ kp_in,
+              const uint4 *__restrict__ desc_in, const int *__restrict__ counts_in, int max_kp,
+              orbb_keypoint *__restrict__ kp_out, uint4 *__restrict__ desc_out, double *__restrict__ points,
+              int *__restrict__ valid_counts) {
+    __shared__ int s_warp[KP_THREADS / 32];
+    const size_t f = blockIdx.x;
+    const int n = min(counts_in[f], max_kp);
+    const uint32_t *dimg = aligned + f * in.width * in.height;
+    int base = 0;
+    for (int i0 = 0; i0 < n; i0 += KP_THREADS) {
+        const int i = i0 + threadIdx.x;
+        bool keep = false;
+        orbb_keypoint k{};
+        int depth = 0;
+        if (i < n) {
+            k = kp_in[f * max_kp + i];
+            const int xi = (int)((double)k.x + 0.5), yi = (int)((double)k.y + 0.5);
+            if (xi >= 0 && yi >= 0 && xi < in.width && yi < in.height) depth = (int)dimg[(size_t)yi * in.width + xi];
+            keep = depth > 1 && k.response > 1.0f;
+        }
+        int total;
+        const int r = base + block_rank(keep, s_warp, &total);
+        if (keep) {
+            const size_t o = f * max_kp + r;
+            kp_out[o] = k;
+            desc_out[2 * o] = desc_in[2 * (f * max_kp + i)];
+            desc_out[2 * o + 1] = desc_in[2 * (f * max_kp + i) + 1];
+            // deproject_pixel_to_point_double (cuda-align.cu:85-110): float32 normalisation, float64 afterwards
+            double x = (double)__fdiv_rn(__fsub_rn(k.x, in.ppx), in.fx);
+            double y = (double)__fdiv_rn(__fsub_rn(k.y, in.ppy), in.fy);
+            if (in.model == ORBB_DISTORTION_INVERSE_BROWN_CONRADY) {
+                const double c0 = in.coeffs[0], c1 = in.coeffs[1], c2 = in.coeffs[2], c3 = in.coeffs[3], c4 = in.coeffs[4];
+                const double r2 = dadd(dmul(x, x), dmul(y, y));
+                const double fr = dadd(dadd(dadd(1.0, dmul(c0, r2)), dmul(dmul(c1, r2), r2)), dmul(dmul(dmul(c4, r2), r2), r2));
+                const double ux = dadd(dadd(dmul(x, fr), dmul(dmul(dmul(2.0, c2), x), y)), dmul(c3, dadd(r2, dmul(dmul(2.0, x), x))));
+                const double uy = dadd(dadd(dmul(y, fr), dmul(dmul(dmul(2.0, c3), x), y)), dmul(c2, dadd(r2, dmul(dmul(2.0, y), y))));
+                x = ux; y = uy;
+            }
+            const double dd = (double)(float)depth;
+            points[3 * o] = dmul(dd, x); points[3 * o + 1] = dmul(dd, y); points[3 * o + 2] = dd;
+        }
+        base += total;
+    }
+    if (threadIdx.x == 0) valid_counts[f] = base;
+}
+
+// ---- reprojection of the previous frame's points.  thread = one point.
+__global__ void __launch_bounds__(128)
+k_reproject(const double *__restrict__ points, const int *__restrict__ counts, int max_kp, const double *__restrict__ T,
+            const orbb_intrinsics in, float2 *__restrict__ pos_out) {
+    const size_t f = blockIdx.y;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= min(counts[f], max_kp)) return;
+    const double *p = points + 3 * (f * max_kp + i);
+    double e[3] = {p[0], p[1], p[2]};
+    if (T) {
+        // Eigen::Matrix4d * Vector4d, column-major; a fixed-size row.dot(v) reduces pairwise: (a0 + a1) + (a2 + a3)
+        const double *M = T + 16 * f;
+#pragma unroll
+        for (int r = 0; r < 3; ++r)
+            e[r] = dadd(dadd(dmul(M[r], p[0]), dmul(M[4 + r], p[1])), dadd(dmul(M[8 + r], p[2]), M[12 + r]));
+    }
+    float pix[2];
+    project_xy(pix, in, (float)__ddiv_rn(e[0], e[2]), (float)__ddiv_rn(e[1], e[2]));
+    pos_out[f * max_kp + i] = make_float2(pix[0], pix[1]);
+}
+
+// ---- matched 3-D pairs, compacted in query order.  CTA = one frame pair.
+__global__ void __launch_bounds__(KP_THREADS)
+k_compact_pairs(const int *__restrict__ idx, const int *__restrict__ q_counts, int max_kp,
+                const double *__restrict__ q_points, const double *__restrict__ t_points,
+                const uint8_t *__restrict__ t_xy, int t_stride, double *__restrict__ prev_out,
+                double *__restrict__ curr_out, uint16_t *__restrict__ xy_out, int *__restrict__ n_matched) {
+    __shared__ int s_warp[KP_THREADS / 32];
+    const size_t f = blockIdx.x;
+    const int n = min(q_counts[f], max_kp);
+    int base = 0;
+    for (int i0 = 0; i0 < n; i0 += KP_THREADS) {
+        const int i = i0 + threadIdx.x;
+        const int t = i < n ? idx[f * max_kp + i] : -1;
+        int total;
+        const int r = base + block_rank(t >= 0, s_warp, &total);
+        if (t >= 0) {
+            const size_t o = f * max_kp + r, q = f * max_kp + i, tt = f * max_kp + t;
+            if (prev_out && q_points) { prev_out[3 * o] = q_points[3 * q]; prev_out[3 * o + 1] = q_points[3 * q + 1]; prev_out[3 * o + 2] = q_points[3 * q + 2]; }
+            if (curr_out && t_points) { curr_out[3 * o] = t_points[3 * tt]; curr_out[3 * o + 1] = t_points[3 * tt + 1]; curr_out[3 * o + 2] = t_points[3 * tt + 2]; }
+            if (xy_out) {
+                const float *p = reinterpret_cast<const float *>(t_xy + tt * t_stride);
+                xy_out[(2 * f) * max_kp + r] = (uint16_t)p[0];
+                xy_out[(2 * f + 1) * max_kp + r] = (uint16_t)p[1];
+            }
+        }
+        base += total;
+    }
+    if (threadIdx.x == 0 && n_matched) n_matched[f] = base;
+}
+
+// ---------------------------------------------------------------- host launchers
+cudaError_t launch_align(const uint16_t *d_depth, int n_frames, float depth_scale, const orbb_intrinsics &di,
+                         const orbb_intrinsics &oi, const orbb_extrinsics &ex, uint32_t *d_out, cudaStream_t st) {
+    const size_t n = (size_t)n_frames * oi.width * oi.height;
+    cudaError_t e = cudaMemsetAsync(d_out, 0xFF, n * sizeof(uint32_t), st);
+    if (e != cudaSuccess) return e;
+    AlignArgs A;
+    A.d = di; A.o = oi; A.e = ex; A.depth_scale = depth_scale;
+    dim3 grid((di.width + 31) / 32, (di.height + 7) / 8, n_frames), block(32, 8);
+    k_align_scatter<<<grid, block, 0, st>>>(d_depth, d_out, A);
+    k_align_finish<<<(unsigned)((n / 4 + 256) / 256), 256, 0, st>>>(d_out, n);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_kp_to_point(const uint32_t *d_aligned, const orbb_intrinsics &in, int n_frames, const orbb_keypoint *kp_in,
+                               const uint8_t *desc_in, const int *counts_in, int max_kp, orbb_keypoint *kp_out,
+                               uint8_t *desc_out, double *points, int *valid, cudaStream_t st) {
+    k_kp_to_point<<<n_frames, KP_THREADS, 0, st>>>(d_aligned, in, kp_in, reinterpret_cast<const uint4 *>(desc_in), counts_in,
+                                                   max_kp, kp_out, reinterpret_cast<uint4 *>(desc_out), points, valid);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_reproject(const double *points, const int *counts, int n_frames, int max_kp, const double *T,
+                             const orbb_intrinsics &in, float *pos_out, cudaStream_t st) {
+    dim3 grid((max_kp + 127) / 128, n_frames);
+    k_reproject<<<grid, 128, 0, st>>>(points, counts, max_kp, T, in, reinterpret_cast<float2 *>(pos_out));
+    return cudaGetLastError();
+}
+
+cudaError_t launch_compact_pairs(const int *idx, const int *q_counts, int n_frames, int max_kp, const double *q_points,
+                                 const double *t_points, const void *t_xy, int t_stride, double *prev_out,
+                                 double *curr_out, uint16_t *xy_out, int *n_matched, cudaStream_t st) {
+    k_compact_pairs<<<n_frames, KP_THREADS, 0, st>>>(idx, q_counts, max_kp, q_points, t_points,
+                                                     static_cast<const uint8_t *>(t_xy), t_stride, prev_out, curr_out, xy_out,
+                                                     n_matched);
+    return cudaGetLastError();
+}
+
+}  // namespace orbb

@@ -32,6 +32,16 @@ cudaError_t launch_angle_orb(const LevelDev *, int, const int *, const int8_t *,
                              orbb_keypoint *, uint8_t *, int *, int, cudaStream_t);
 cudaError_t launch_match(const uint8_t *, const uint8_t *, const int *, const int *, int, int, int, int, int, int4 *,
                          int, int, float, int *, int *, uint8_t *, int *, cudaStream_t);
+cudaError_t launch_align(const uint16_t *, int, float, const orbb_intrinsics &, const orbb_intrinsics &, const orbb_extrinsics &,
+                         uint32_t *, cudaStream_t);
+cudaError_t launch_kp_to_point(const uint32_t *, const orbb_intrinsics &, int, const orbb_keypoint *, const uint8_t *,
+                               const int *, int, orbb_keypoint *, uint8_t *, double *, int *, cudaStream_t);
+cudaError_t launch_reproject(const double *, const int *, int, int, const double *, const orbb_intrinsics &, float *,
+                             cudaStream_t);
+cudaError_t launch_compact_pairs(const int *, const int *, int, int, const double *, const double *, const void *, int,
+                                 double *, double *, uint16_t *, int *, cudaStream_t);
+cudaError_t launch_match_windowed_batch(const uint8_t *, const void *, int, const int *, const uint8_t *, const void *, int,
+                                        const int *, int, int, float, int, int *, int *, cudaStream_t);
 }  // namespace orbb
 
 using namespace orbb;
@@ -797,6 +807,82 @@ extern "C" int orbb_match_windowed(orbb_handle *h, const uint8_t *d_query, const
     CK(h, launch_match_windowed(d_query, d_query_xy, q_xy_stride, nq, d_train, d_train_xy, t_xy_stride, nt, max_px,
                                 std::min(max_hamming, 257), d_idx, d_dist, d_nmatched, static_cast<cudaStream_t>(stream)));
     h->n_launches += 1;
+    return ORBB_OK;
+}
+
+// ---------------------------------------------------------------- RGB-D association
+static bool intrin_ok(const orbb_intrinsics *in) {
+    if (!in || in->width < 1 || in->height < 1 || in->width > 16384 || in->height > 16384) return false;
+    // FTHETA / KANNALA_BRANDT4 need atan/tan chains (or are ignored by the reference's copy of rsutil.h): refused
+    return in->model == ORBB_DISTORTION_NONE || in->model == ORBB_DISTORTION_MODIFIED_BROWN_CONRADY ||
+           in->model == ORBB_DISTORTION_INVERSE_BROWN_CONRADY || in->model == ORBB_DISTORTION_BROWN_CONRADY;
+}
+
+extern "C" int orbb_align_depth_to_other(orbb_handle *h, const uint16_t *d_depth, int n_frames, float depth_scale,
+                                         const orbb_intrinsics *depth_intrin, const orbb_intrinsics *other_intrin,
+                                         const orbb_extrinsics *depth_to_other, uint32_t *d_aligned_out, void *stream) {
+    if (!h || !d_depth || !d_aligned_out || !depth_to_other || n_frames < 1 || !intrin_ok(depth_intrin) ||
+        !intrin_ok(other_intrin))
+        return ORBB_ERR_INVALID;
+    // the reference asserts these out (cuda-align.cu:63-64): a forward-distorted image cannot be deprojected
+    if (depth_intrin->model == ORBB_DISTORTION_MODIFIED_BROWN_CONRADY) return ORBB_ERR_INVALID;
+    if (reinterpret_cast<uintptr_t>(d_aligned_out) & 15) return ORBB_ERR_INVALID;
+    CK(h, cudaSetDevice(h->device));
+    CK(h, launch_align(d_depth, n_frames, depth_scale, *depth_intrin, *other_intrin, *depth_to_other, d_aligned_out,
+                       static_cast<cudaStream_t>(stream)));
+    h->n_launches += 2;
+    return ORBB_OK;
+}
+
+extern "C" int orbb_keypoint_pixel_to_point(orbb_handle *h, const uint32_t *d_aligned_depth, const orbb_intrinsics *other_intrin,
+                                            int n_frames, const orbb_keypoint *d_kp_in, const uint8_t *d_desc_in,
+                                            const int32_t *d_counts_in, int max_kp, orbb_keypoint *d_kp_out,
+                                            uint8_t *d_desc_out, double *d_points, int32_t *d_valid_counts, void *stream) {
+    if (!h || !d_aligned_depth || !d_kp_in || !d_desc_in || !d_counts_in || !d_kp_out || !d_desc_out || !d_points ||
+        !d_valid_counts || n_frames < 1 || max_kp < 1 || !intrin_ok(other_intrin))
+        return ORBB_ERR_INVALID;
+    if (other_intrin->model == ORBB_DISTORTION_MODIFIED_BROWN_CONRADY) return ORBB_ERR_INVALID;  // cuda-align.cu:90-91
+    if (d_kp_in == d_kp_out || d_desc_in == d_desc_out) return ORBB_ERR_INVALID;
+    if ((reinterpret_cast<uintptr_t>(d_desc_in) | reinterpret_cast<uintptr_t>(d_desc_out)) & 15) return ORBB_ERR_INVALID;
+    CK(h, cudaSetDevice(h->device));
+    CK(h, launch_kp_to_point(d_aligned_depth, *other_intrin, n_frames, d_kp_in, d_desc_in, d_counts_in, max_kp, d_kp_out,
+                             d_desc_out, d_points, d_valid_counts, static_cast<cudaStream_t>(stream)));
+    h->n_launches += 1;
+    return ORBB_OK;
+}
+
+extern "C" int orbb_reproject_points(orbb_handle *h, const double *d_points, const int32_t *d_counts, int n_frames,
+                                     int max_kp, const double *d_T, const orbb_intrinsics *intrin, float *d_pos_out,
+                                     void *stream) {
+    if (!h || !d_points || !d_counts || !d_pos_out || n_frames < 1 || max_kp < 1 || !intrin_ok(intrin)) return ORBB_ERR_INVALID;
+    if (reinterpret_cast<uintptr_t>(d_pos_out) & 7) return ORBB_ERR_INVALID;
+    CK(h, cudaSetDevice(h->device));
+    CK(h, launch_reproject(d_points, d_counts, n_frames, max_kp, d_T, *intrin, d_pos_out, static_cast<cudaStream_t>(stream)));
+    h->n_launches += 1;
+    return ORBB_OK;
+}
+
+extern "C" int orbb_match_windowed_batch(orbb_handle *h, const uint8_t *d_query, const float *d_query_xy,
+                                         const int32_t *d_q_counts, const uint8_t *d_train, const void *d_train_xy,
+                                         int t_xy_stride, const int32_t *d_t_counts, int n_frames, int max_kp, float max_px,
+                                         int max_hamming, int32_t *d_idx, int32_t *d_dist, const double *d_query_points,
+                                         const double *d_train_points, double *d_prev_matched, double *d_curr_matched,
+                                         uint16_t *d_xy_u16, int32_t *d_nmatched, void *stream) {
+    if (!h || !d_query || !d_query_xy || !d_q_counts || !d_train || !d_train_xy || !d_t_counts || !d_idx || !d_dist ||
+        n_frames < 1 || max_kp < 1 || t_xy_stride < 8 || (t_xy_stride & 3) || max_hamming < 0)
+        return ORBB_ERR_INVALID;
+    if ((reinterpret_cast<uintptr_t>(d_query) | reinterpret_cast<uintptr_t>(d_train)) & 15) return ORBB_ERR_INVALID;
+    if ((reinterpret_cast<uintptr_t>(d_query_xy) | reinterpret_cast<uintptr_t>(d_train_xy)) & 3) return ORBB_ERR_INVALID;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    CK(h, cudaSetDevice(h->device));
+    CK(h, launch_match_windowed_batch(d_query, d_query_xy, 8, d_q_counts, d_train, d_train_xy, t_xy_stride, d_t_counts,
+                                      n_frames, max_kp, max_px, std::min(max_hamming, 257), d_idx, d_dist, st));
+    h->n_launches += 1;
+    if (d_nmatched || d_prev_matched || d_curr_matched || d_xy_u16) {
+        CK(h, launch_compact_pairs(d_idx, d_q_counts, n_frames, max_kp, d_query_points, d_train_points, d_train_xy,
+                                   t_xy_stride, d_prev_matched, d_curr_matched, d_xy_u16, d_nmatched, st));
+        h->n_launches += 1;
+    }
     return ORBB_OK;
 }
 

@@ -35,6 +35,7 @@ EXPORTS = [
     "orbb_detect", "orbb_detect_fast", "orbb_detect_distribute", "orbb_gaussian_blur", "orbb_compute_angle_and_orb", "orbb_match_knn",
     "orbb_match_knn_segmented", "orbb_match_windowed", "orbb_debug_get_padded", "orbb_debug_get_blurred", "orbb_debug_get_scores",
     "orbb_debug_get_candidates", "orbb_debug_get_selected", "orbb_debug_distribute",
+    "orbb_align_depth_to_other", "orbb_keypoint_pixel_to_point", "orbb_reproject_points", "orbb_match_windowed_batch",
 ]
 
 
@@ -51,6 +52,29 @@ class Level(C.Structure):
     _fields_ = [("width", C.c_int32), ("height", C.c_int32), ("pitch", C.c_int32), ("roi_offset", C.c_int32),
                 ("padded", C.c_void_p), ("blurred", C.c_void_p), ("scale", C.c_float), ("inv_scale", C.c_float),
                 ("nfeatures", C.c_int32)]
+
+
+class Intrinsics(C.Structure):
+    """== rs2_intrinsics (librealsense2 rs_types.h)"""
+    _fields_ = [("width", C.c_int32), ("height", C.c_int32), ("ppx", C.c_float), ("ppy", C.c_float),
+                ("fx", C.c_float), ("fy", C.c_float), ("model", C.c_int32), ("coeffs", C.c_float * 5)]
+
+
+class Extrinsics(C.Structure):
+    """== rs2_extrinsics: column-major rotation, translation"""
+    _fields_ = [("rotation", C.c_float * 9), ("translation", C.c_float * 3)]
+
+
+DISTORTION_NONE, DISTORTION_MODIFIED_BROWN_CONRADY, DISTORTION_INVERSE_BROWN_CONRADY = 0, 1, 2
+DISTORTION_FTHETA, DISTORTION_BROWN_CONRADY, DISTORTION_KANNALA_BRANDT4 = 3, 4, 5
+
+
+def make_intrinsics(width, height, ppx, ppy, fx, fy, model=DISTORTION_NONE, coeffs=(0, 0, 0, 0, 0)) -> Intrinsics:
+    return Intrinsics(width, height, ppx, ppy, fx, fy, model, (C.c_float * 5)(*coeffs))
+
+
+def make_extrinsics(rotation=(1, 0, 0, 0, 1, 0, 0, 0, 1), translation=(0, 0, 0)) -> Extrinsics:
+    return Extrinsics((C.c_float * 9)(*rotation), (C.c_float * 3)(*translation))
 
 
 _lib = None
@@ -98,6 +122,12 @@ def load_library():
     L.orbb_debug_get_candidates.argtypes = [vp, i32, i32, vp, i32]
     L.orbb_debug_get_selected.argtypes = [vp, i32, i32, vp, i32]
     L.orbb_debug_distribute.argtypes = [vp, i32, vp, i32, i32, vp, i32]
+    L.orbb_align_depth_to_other.argtypes = [vp, vp, i32, f32, C.POINTER(Intrinsics), C.POINTER(Intrinsics),
+                                            C.POINTER(Extrinsics), vp, vp]
+    L.orbb_keypoint_pixel_to_point.argtypes = [vp, vp, C.POINTER(Intrinsics), i32, vp, vp, vp, i32, vp, vp, vp, vp, vp]
+    L.orbb_reproject_points.argtypes = [vp, vp, vp, i32, i32, vp, C.POINTER(Intrinsics), vp, vp]
+    L.orbb_match_windowed_batch.argtypes = [vp, vp, vp, vp, vp, vp, i32, vp, i32, i32, f32, i32, vp, vp, vp, vp, vp, vp,
+                                            vp, vp, vp]
     for name in EXPORTS:
         fn = getattr(L, name)
         if name not in ("orbb_strerror", "orbb_last_cuda_error", "orbb_get_launch_count"):
@@ -295,6 +325,37 @@ class ORBextractor:
             self._h, _dev_ptr(d_query), _dev_ptr(d_query_xy), q_xy_stride, nq, _dev_ptr(d_train), _dev_ptr(d_train_xy),
             t_xy_stride, nt, max_pixel_distance, max_hamming_distance, _dev_ptr(d_idx), _dev_ptr(d_dist),
             _dev_ptr(d_nmatched) if d_nmatched is not None else C.c_void_p(0), _stream_ptr(stream)))
+
+    # -- RGB-D association (reference src/cuda/cuda-align.cuh, post_processing.cuh) -----------
+    def align_depth_to_other(self, d_depth, n: int, depth_scale: float, depth_intrin: Intrinsics,
+                             other_intrin: Intrinsics, depth_to_other: Extrinsics, d_aligned_out, stream=None):
+        self._check(self._lib.orbb_align_depth_to_other(self._h, _dev_ptr(d_depth), n, depth_scale, C.byref(depth_intrin),
+                                                        C.byref(other_intrin), C.byref(depth_to_other),
+                                                        _dev_ptr(d_aligned_out), _stream_ptr(stream)))
+
+    def keypoint_pixel_to_point(self, d_aligned, other_intrin: Intrinsics, n: int, d_kp_in, d_desc_in, d_counts_in,
+                                d_kp_out, d_desc_out, d_points, d_valid_counts, stream=None):
+        self._check(self._lib.orbb_keypoint_pixel_to_point(
+            self._h, _dev_ptr(d_aligned), C.byref(other_intrin), n, _dev_ptr(d_kp_in), _dev_ptr(d_desc_in),
+            _dev_ptr(d_counts_in), self.max_kp, _dev_ptr(d_kp_out), _dev_ptr(d_desc_out), _dev_ptr(d_points),
+            _dev_ptr(d_valid_counts), _stream_ptr(stream)))
+
+    def reproject_points(self, d_points, d_counts, n: int, d_T, intrin: Intrinsics, d_pos_out, stream=None):
+        self._check(self._lib.orbb_reproject_points(
+            self._h, _dev_ptr(d_points), _dev_ptr(d_counts), n, self.max_kp,
+            _dev_ptr(d_T) if d_T is not None else C.c_void_p(0), C.byref(intrin), _dev_ptr(d_pos_out),
+            _stream_ptr(stream)))
+
+    def match_keypoints_windowed_batch(self, d_query, d_query_xy, d_q_counts, d_train, d_train_xy, t_xy_stride: int,
+                                       d_t_counts, n: int, max_pixel_distance: float, max_hamming_distance: int,
+                                       d_idx, d_dist, d_query_points=None, d_train_points=None, d_prev_matched=None,
+                                       d_curr_matched=None, d_xy_u16=None, d_nmatched=None, stream=None):
+        opt = lambda t: _dev_ptr(t) if t is not None else C.c_void_p(0)  # noqa: E731
+        self._check(self._lib.orbb_match_windowed_batch(
+            self._h, _dev_ptr(d_query), _dev_ptr(d_query_xy), _dev_ptr(d_q_counts), _dev_ptr(d_train),
+            _dev_ptr(d_train_xy), t_xy_stride, _dev_ptr(d_t_counts), n, self.max_kp, max_pixel_distance,
+            max_hamming_distance, _dev_ptr(d_idx), _dev_ptr(d_dist), opt(d_query_points), opt(d_train_points),
+            opt(d_prev_matched), opt(d_curr_matched), opt(d_xy_u16), opt(d_nmatched), _stream_ptr(stream)))
 
     # -- parity / debug access --------------------------------------------------------------
     def debug_padded(self, level: int, frame: int = 0) -> np.ndarray:

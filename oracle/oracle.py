@@ -25,6 +25,23 @@ class Params(C.Structure):
                 ("ini_th_fast", C.c_int32), ("min_th_fast", C.c_int32)]
 
 
+class Intrinsics(C.Structure):
+    _fields_ = [("width", C.c_int32), ("height", C.c_int32), ("ppx", C.c_float), ("ppy", C.c_float),
+                ("fx", C.c_float), ("fy", C.c_float), ("model", C.c_int32), ("coeffs", C.c_float * 5)]
+
+
+class Extrinsics(C.Structure):
+    _fields_ = [("rotation", C.c_float * 9), ("translation", C.c_float * 3)]
+
+
+def make_intrinsics(width, height, ppx, ppy, fx, fy, model=0, coeffs=(0, 0, 0, 0, 0)) -> Intrinsics:
+    return Intrinsics(width, height, ppx, ppy, fx, fy, model, (C.c_float * 5)(*coeffs))
+
+
+def make_extrinsics(rotation=(1, 0, 0, 0, 1, 0, 0, 0, 1), translation=(0, 0, 0)) -> Extrinsics:
+    return Extrinsics((C.c_float * 9)(*rotation), (C.c_float * 3)(*translation))
+
+
 def build(native: bool = False) -> str:
     """Compile the oracle with its Makefile (gcc only) and return the .so path."""
     target = "native" if native else "all"
@@ -92,6 +109,15 @@ def lib(native: bool = False):
     L.orbo_extract_many.restype = C.c_long
     L.orbo_match_many.argtypes = [vp, C.c_int, vp, C.c_int, C.c_int, C.c_float, C.c_int, vp, vp, vp]
     L.orbo_match_many.restype = C.c_long
+    L.orbo_align_depth_to_other.argtypes = [vp, C.c_float, C.POINTER(Intrinsics), C.POINTER(Intrinsics),
+                                            C.POINTER(Extrinsics), vp]
+    L.orbo_align_depth_to_other.restype = None
+    L.orbo_keypoint_pixel_to_point.argtypes = [vp, C.POINTER(Intrinsics), vp, vp, C.c_int, vp, vp, vp]
+    L.orbo_keypoint_pixel_to_point.restype = C.c_int
+    L.orbo_reproject_points.argtypes = [vp, C.c_int, vp, C.POINTER(Intrinsics), vp]
+    L.orbo_reproject_points.restype = None
+    L.orbo_compact_pairs.argtypes = [vp, C.c_int, vp, vp, vp, C.c_int, vp, vp, vp, vp]
+    L.orbo_compact_pairs.restype = C.c_int
     del u8p, i32p, f32p
     if not native:
         _lib = L
@@ -278,3 +304,46 @@ def extract_many(frames: np.ndarray, nfeatures=1000, scale_factor=1.2, nlevels=8
     if tot < 0:
         raise RuntimeError(f"orbo_extract_many failed: {tot}")
     return int(tot), counts
+
+
+# ---------------------------------------------------------------- RGB-D association (rgbd_oracle.c)
+def align_depth_to_other(depth: np.ndarray, depth_scale: float, di: Intrinsics, oi: Intrinsics, ex: Extrinsics):
+    depth = np.ascontiguousarray(depth, np.uint16)
+    assert depth.shape == (di.height, di.width)
+    out = np.empty((oi.height, oi.width), np.uint32)
+    lib().orbo_align_depth_to_other(_p(depth), depth_scale, C.byref(di), C.byref(oi), C.byref(ex), _p(out))
+    return out
+
+
+def keypoint_pixel_to_point(aligned: np.ndarray, oi: Intrinsics, kp: np.ndarray, desc: np.ndarray):
+    aligned = np.ascontiguousarray(aligned, np.uint32)
+    kp = np.ascontiguousarray(kp, KEYPOINT_DTYPE)
+    desc = np.ascontiguousarray(desc, np.uint8).reshape(-1, 32)
+    n = kp.shape[0]
+    kp_out = np.zeros(max(n, 1), KEYPOINT_DTYPE)
+    desc_out = np.zeros((max(n, 1), 32), np.uint8)
+    pts = np.zeros((max(n, 1), 3), np.float64)
+    m = lib().orbo_keypoint_pixel_to_point(_p(aligned), C.byref(oi), _p(kp), _p(desc), n, _p(kp_out), _p(desc_out), _p(pts))
+    return kp_out[:m].copy(), desc_out[:m].copy(), pts[:m].copy()
+
+
+def reproject_points(points: np.ndarray, T, intrin: Intrinsics) -> np.ndarray:
+    points = np.ascontiguousarray(points, np.float64).reshape(-1, 3)
+    out = np.zeros((max(points.shape[0], 1), 2), np.float32)
+    Tc = None if T is None else np.ascontiguousarray(np.asarray(T, np.float64).reshape(4, 4).T)  # -> column-major
+    lib().orbo_reproject_points(_p(points), points.shape[0], _p(Tc) if Tc is not None else None, C.byref(intrin), _p(out))
+    return out[:points.shape[0]].copy()
+
+
+def compact_pairs(idx: np.ndarray, q_points: np.ndarray, t_points: np.ndarray, t_xy: np.ndarray):
+    idx = np.ascontiguousarray(idx, np.int32)
+    q_points = np.ascontiguousarray(q_points, np.float64).reshape(-1, 3)
+    t_points = np.ascontiguousarray(t_points, np.float64).reshape(-1, 3)
+    t_xy = np.ascontiguousarray(t_xy, np.float32).reshape(-1, 2)
+    n = idx.shape[0]
+    prev = np.zeros((max(n, 1), 3), np.float64)
+    curr = np.zeros((max(n, 1), 3), np.float64)
+    xs = np.zeros(max(n, 1), np.uint16)
+    ys = np.zeros(max(n, 1), np.uint16)
+    m = lib().orbo_compact_pairs(_p(idx), n, _p(q_points), _p(t_points), _p(t_xy), 2, _p(prev), _p(curr), _p(xs), _p(ys))
+    return prev[:m].copy(), curr[:m].copy(), xs[:m].copy(), ys[:m].copy()

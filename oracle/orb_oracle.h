@@ -118,6 +118,25 @@ long orbo_extract_many(const orbo_params *p, const uint8_t *frames, int w, int h
 long orbo_match_many(const uint8_t *q, int nq, const uint8_t *t, int nt, int k, float ratio,
                      int n_threads, int32_t *out_idx, int32_t *out_dist, uint8_t *accept);
 
+/* ---- RGB-D association stages (rgbd_oracle.c; reference src/cuda/cuda-align.cu, post_processing.cu) ---- */
+typedef struct {
+    int32_t width, height;
+    float ppx, ppy, fx, fy;
+    int32_t model;
+    float coeffs[5];
+} orbo_intrinsics; /* == rs2_intrinsics */
+typedef struct {
+    float rotation[9];
+    float translation[3];
+} orbo_extrinsics; /* == rs2_extrinsics */
+void orbo_align_depth_to_other(const uint16_t *depth, float depth_scale, const orbo_intrinsics *di,
+                               const orbo_intrinsics *oi, const orbo_extrinsics *ex, uint32_t *out);
+int orbo_keypoint_pixel_to_point(const uint32_t *aligned, const orbo_intrinsics *oi, const orbo_keypoint *kp,
+                                 const uint8_t *desc, int n, orbo_keypoint *kp_out, uint8_t *desc_out, double *points);
+void orbo_reproject_points(const double *points, int n, const double *T, const orbo_intrinsics *intrin, float *pos_out);
+int orbo_compact_pairs(const int32_t *idx, int nq, const double *q_points, const double *t_points, const float *t_xy,
+                       int t_xy_stride_floats, double *prev_out, double *curr_out, uint16_t *x_out, uint16_t *y_out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,189 @@
+"""GPU parity, RGB-D association stages: align_depth_to_other, keypoint_pixel_to_point,
+reprojection and the batched windowed matcher with pair compaction, through the C ABI, bit-exact against
+oracle/rgbd_oracle.c (integers, float32 and float64 alike: every operation is rounded on its own on both sides)."""
+import importlib
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def orbb():
+    import torch
+    assert torch.cuda.is_available(), "GPU tier needs a CUDA device"
+    import __graft_entry__ as g
+    g.build()
+    return importlib.import_module("jetracer-orbslam2_b200.orbb")
+
+
+def synth_depth(w, h, seed):
+    """Smooth surface 0.4-4 m in 1 mm units + steps + speckle + holes (zeros), like a D435 depth frame."""
+    rng = np.random.default_rng(seed)
+    yy, xx = np.mgrid[0:h, 0:w].astype(np.float32)
+    z = 1500 + 900 * np.sin(xx / 97.0 + seed) * np.cos(yy / 61.0) + 3.0 * xx
+    for _ in range(12):
+        x0, y0 = rng.integers(0, w - 40), rng.integers(0, h - 40)
+        z[y0:y0 + rng.integers(10, 120), x0:x0 + rng.integers(10, 160)] = rng.integers(400, 4000)
+    z += rng.integers(-8, 9, (h, w))
+    d = np.clip(z, 0, 65535).astype(np.uint16)
+    d[rng.random((h, w)) < 0.08] = 0
+    d[:, :6] = 0
+    return d
+
+
+def d435_pair(orbb_or_oracle, w, h, distorted):
+    mk_i, mk_e = orbb_or_oracle.make_intrinsics, orbb_or_oracle.make_extrinsics
+    di = mk_i(w, h, w * 0.5 + 3.7, h * 0.5 - 2.2, 0.502 * w, 0.502 * w, 4)  # BROWN_CONRADY, zero coeffs (D435 depth)
+    if distorted:
+        oi = mk_i(w, h, w * 0.5 - 5.1, h * 0.5 + 4.3, 0.72 * w, 0.725 * w, 1, (0.12, -0.25, 0.0007, -0.0004, 0.09))
+    else:
+        oi = mk_i(w, h, w * 0.5 - 5.1, h * 0.5 + 4.3, 0.72 * w, 0.725 * w, 2, (0, 0, 0, 0, 0))
+    a, b = 0.004, -0.003  # small rotation about x and y, column-major
+    R = (1, a * b, -b, 0, 1, a, b, -a, 1)
+    ex = mk_e(R, (0.0148, 0.0002, 0.0003))
+    return di, oi, ex
+
+
+@pytest.mark.parametrize("w,h,distorted", [(848, 480, False), (848, 480, True), (640, 480, True), (333, 251, True)])
+def test_align_depth_to_other(orbb, oracle, w, h, distorted):
+    import torch
+    n = 3
+    depth = np.stack([synth_depth(w, h, 10 + i) for i in range(n)])
+    ex = orbb.ORBextractor(100, 1.2, 2, 20, 7, width=w, height=h, max_batch=1)
+    di, oi, e = d435_pair(orbb, w, h, distorted)
+    odi, ooi, oe = d435_pair(oracle, w, h, distorted)
+    d_depth = torch.from_numpy(depth.view(np.int16)).cuda()
+    d_out = torch.zeros((n, h, w), dtype=torch.int32, device="cuda")
+    ex.align_depth_to_other(d_depth, n, 0.001, di, oi, e, d_out, stream=torch.cuda.current_stream())
+    torch.cuda.synchronize()
+    got = d_out.cpu().numpy().view(np.uint32)
+    for i in range(n):
+        ref = oracle.align_depth_to_other(depth[i], 0.001, odi, ooi, oe)
+        assert (ref > 0).mean() > 0.3
+        assert np.array_equal(got[i], ref), f"frame {i}: {(got[i] != ref).sum()} pixels differ"
+
+
+def test_align_different_sizes_and_empty(orbb, oracle):
+    """depth 424x240 onto a 640x480 image (rectangles of ~2x3 pixels), plus an all-zero frame."""
+    import torch
+    dw, dh, ow, oh = 424, 240, 640, 480
+    depth = np.stack([synth_depth(dw, dh, 77), np.zeros((dh, dw), np.uint16)])
+    di = orbb.make_intrinsics(dw, dh, 212.3, 119.1, 213.0, 213.0, 4)
+    oi = orbb.make_intrinsics(ow, oh, 322.0, 241.5, 460.0, 461.0, 1, (0.1, -0.2, 0.001, 0.0005, 0.05))
+    e = orbb.make_extrinsics((1, 0, 0, 0, 1, 0, 0, 0, 1), (0.015, 0, 0))
+    odi = oracle.make_intrinsics(dw, dh, 212.3, 119.1, 213.0, 213.0, 4)
+    ooi = oracle.make_intrinsics(ow, oh, 322.0, 241.5, 460.0, 461.0, 1, (0.1, -0.2, 0.001, 0.0005, 0.05))
+    oe = oracle.make_extrinsics((1, 0, 0, 0, 1, 0, 0, 0, 1), (0.015, 0, 0))
+    ex = orbb.ORBextractor(100, 1.2, 2, 20, 7, width=ow, height=oh, max_batch=1)
+    d_depth = torch.from_numpy(depth.view(np.int16)).cuda()
+    d_out = torch.full((2, oh, ow), 5, dtype=torch.int32, device="cuda")
+    ex.align_depth_to_other(d_depth, 2, 0.001, di, oi, e, d_out, stream=torch.cuda.current_stream())
+    torch.cuda.synchronize()
+    got = d_out.cpu().numpy().view(np.uint32)
+    assert np.array_equal(got[0], oracle.align_depth_to_other(depth[0], 0.001, odi, ooi, oe))
+    assert not got[1].any()
+    # unsupported models are refused loudly, not approximated
+    bad = orbb.make_intrinsics(ow, oh, 322.0, 241.5, 460.0, 461.0, orbb.DISTORTION_FTHETA)
+    with pytest.raises(orbb.OrbbError):
+        ex.align_depth_to_other(d_depth, 2, 0.001, di, bad, e, d_out)
+
+
+def _frame_pipeline(orbb, oracle, synth, w, h, n, nfeat, distorted, seed):
+    """extract -> align -> keypoint_pixel_to_point on the GPU; returns host copies + the oracle's inputs."""
+    import torch
+    frames = np.stack([synth.textured_frame(w, h, seed + i) for i in range(n)])
+    depth = np.stack([synth_depth(w, h, seed + 50 + i) for i in range(n)])
+    ex = orbb.ORBextractor(nfeat, 1.2, 8, 20, 7, width=w, height=h, max_batch=n)
+    mk = ex.max_kp
+    st = torch.cuda.current_stream()
+    d_frames = torch.from_numpy(frames).cuda()
+    d_kp = torch.zeros((n, mk, 7), dtype=torch.float32, device="cuda")
+    d_desc = torch.zeros((n, mk, 32), dtype=torch.uint8, device="cuda")
+    d_counts = torch.zeros(n, dtype=torch.int32, device="cuda")
+    ex.extract_batch_device(d_frames, n, d_kp, d_desc, d_counts, stream=st)
+    di, oi, e = d435_pair(orbb, w, h, distorted)
+    if distorted:  # the keypoint image must be deprojectable: inverse model on the colour side
+        oi = orbb.make_intrinsics(w, h, oi.ppx, oi.ppy, oi.fx, oi.fy, 2, (0.12, -0.25, 0.0007, -0.0004, 0.09))
+    d_depth = torch.from_numpy(depth.view(np.int16)).cuda()
+    d_al = torch.zeros((n, h, w), dtype=torch.int32, device="cuda")
+    ex.align_depth_to_other(d_depth, n, 0.001, di, oi, e, d_al, stream=st)
+    d_kp2 = torch.zeros_like(d_kp); d_desc2 = torch.zeros_like(d_desc)
+    d_pts = torch.zeros((n, mk, 3), dtype=torch.float64, device="cuda")
+    d_valid = torch.zeros(n, dtype=torch.int32, device="cuda")
+    ex.keypoint_pixel_to_point(d_al, oi, n, d_kp, d_desc, d_counts, d_kp2, d_desc2, d_pts, d_valid, stream=st)
+    torch.cuda.synchronize()
+    ooi = oracle.make_intrinsics(w, h, oi.ppx, oi.ppy, oi.fx, oi.fy, oi.model, tuple(oi.coeffs))
+    dev = dict(ex=ex, d_kp2=d_kp2, d_desc2=d_desc2, d_pts=d_pts, d_valid=d_valid, oi=oi)
+    host = dict(kp=d_kp.cpu().numpy().view(orbb.KEYPOINT_DTYPE).reshape(n, mk), desc=d_desc.cpu().numpy(),
+                counts=d_counts.cpu().numpy(), aligned=d_al.cpu().numpy().view(np.uint32),
+                kp2=d_kp2.cpu().numpy().view(orbb.KEYPOINT_DTYPE).reshape(n, mk), desc2=d_desc2.cpu().numpy(),
+                pts=d_pts.cpu().numpy(), valid=d_valid.cpu().numpy(), ooi=ooi)
+    return dev, host
+
+
+@pytest.mark.parametrize("distorted", [False, True])
+def test_keypoint_pixel_to_point(orbb, oracle, synth, distorted):
+    n = 4
+    dev, hst = _frame_pipeline(orbb, oracle, synth, 640, 480, n, 1000, distorted, 9100)
+    for f in range(n):
+        c = int(hst["counts"][f])
+        okp, odesc, opts = oracle.keypoint_pixel_to_point(hst["aligned"][f], hst["ooi"], hst["kp"][f, :c], hst["desc"][f, :c])
+        m = int(hst["valid"][f])
+        assert m == len(okp) and 0.5 * c < m < c  # holes in the depth drop some keypoints, not all
+        assert np.array_equal(hst["kp2"][f, :m].view(np.uint8), okp.view(np.uint8))
+        assert np.array_equal(hst["desc2"][f, :m], odesc)
+        assert np.array_equal(hst["pts"][f, :m].view(np.uint64), opts.view(np.uint64)), "float64 points differ"
+
+
+@pytest.mark.parametrize("with_T", [False, True])
+def test_reproject_match_compact(orbb, oracle, synth, with_T):
+    """Frame f is matched against frame f+1 of a slowly translating sequence: previous points reprojected with T,
+    windowed match (reference gate arguments), matched 3-D pairs compacted in query order."""
+    import torch
+    n, w, h = 4, 640, 480
+    dev, hst = _frame_pipeline(orbb, oracle, synth, w, h, n, 800, False, 9300)
+    ex, mk = dev["ex"], dev["ex"].max_kp
+    st = torch.cuda.current_stream()
+    # previous frame = frame f, current = frame (f+1) % n (different random textures: matches are rare, so loosen the
+    # gates enough to get a few hundred candidates through the descriptor compare)
+    perm = [(f + 1) % n for f in range(n)]
+    cur_kp = dev["d_kp2"][perm].contiguous(); cur_desc = dev["d_desc2"][perm].contiguous()
+    cur_pts = dev["d_pts"][perm].contiguous(); cur_valid = dev["d_valid"][perm].contiguous()
+    T = None
+    if with_T:
+        rng = np.random.default_rng(5)
+        Ts = []
+        for f in range(n):
+            a = rng.normal(0, 0.01, 3)
+            R = np.array([[1, -a[2], a[1]], [a[2], 1, -a[0]], [-a[1], a[0], 1]])
+            M = np.eye(4); M[:3, :3] = R; M[:3, 3] = rng.normal(0, 8.0, 3)
+            Ts.append(M)
+        T = torch.from_numpy(np.stack([M.T.copy() for M in Ts])).cuda()  # column-major per frame
+    d_pos = torch.zeros((n, mk, 2), dtype=torch.float32, device="cuda")
+    ex.reproject_points(dev["d_pts"], dev["d_valid"], n, T, dev["oi"], d_pos, stream=st)
+    d_idx = torch.full((n, mk), -9, dtype=torch.int32, device="cuda"); d_dist = torch.full_like(d_idx, -9)
+    d_prev = torch.zeros((n, mk, 3), dtype=torch.float64, device="cuda"); d_curr = torch.zeros_like(d_prev)
+    d_xy = torch.zeros((n, 2, mk), dtype=torch.int16, device="cuda")
+    d_nm = torch.zeros(n, dtype=torch.int32, device="cuda")
+    ex.match_keypoints_windowed_batch(dev["d_desc2"], d_pos, dev["d_valid"], cur_desc, cur_kp, 28, cur_valid, n, 40.0, 90,
+                                      d_idx, d_dist, dev["d_pts"], cur_pts, d_prev, d_curr, d_xy, d_nm, stream=st)
+    torch.cuda.synchronize()
+    pos = d_pos.cpu().numpy(); idx = d_idx.cpu().numpy(); dist = d_dist.cpu().numpy()
+    prev = d_prev.cpu().numpy(); curr = d_curr.cpu().numpy(); xy = d_xy.cpu().numpy().view(np.uint16); nm = d_nm.cpu().numpy()
+    total = 0
+    for f in range(n):
+        m, g = int(hst["valid"][f]), perm[f]
+        mc = int(hst["valid"][g])
+        opos = oracle.reproject_points(hst["pts"][f, :m], Ts[f] if with_T else None, hst["ooi"])
+        assert np.array_equal(pos[f, :m].view(np.uint32), opos.view(np.uint32)), "reprojected positions differ"
+        txy = np.stack([hst["kp2"][g, :mc]["x"], hst["kp2"][g, :mc]["y"]], 1)
+        oidx, odist, onm = oracle.match_windowed(hst["desc2"][f, :m], opos, hst["desc2"][g, :mc], txy, 40.0, 90)
+        assert np.array_equal(idx[f, :m], oidx) and np.array_equal(dist[f, :m], odist)
+        oprev, ocurr, oxs, oys = oracle.compact_pairs(oidx, hst["pts"][f, :m], hst["pts"][g, :mc], txy)
+        assert int(nm[f]) == onm == len(oprev)
+        assert np.array_equal(prev[f, :onm], oprev) and np.array_equal(curr[f, :onm], ocurr)
+        assert np.array_equal(xy[f, 0, :onm], oxs) and np.array_equal(xy[f, 1, :onm], oys)
+        total += onm
+    assert total > 50, "test too weak: hardly any match went through"

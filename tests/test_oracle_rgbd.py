@@ -1,0 +1,116 @@
+"""CPU tier: the RGB-D association oracle (oracle/rgbd_oracle.c) against independent known answers.
+
+The reference has no test for these stages, so the oracle is pinned here against closed-form
+cases derived by hand: with identical power-of-two intrinsics and identity extrinsics every float operation of
+the deproject -> transform -> project chain is exact, so the aligned depth has a closed form."""
+import numpy as np
+import pytest
+
+
+def _closed_form_identity(depth):
+    """depth pixel (x, y) covers [x, x+1] x [y, y+1] of the other image; pixels whose rectangle leaves the image
+    are skipped whole (reference src/cuda/cuda-align.cu:236-237); min over non-zero contributors, else 0."""
+    h, w = depth.shape
+    out = np.full((h, w), 0xFFFFFFFF, np.uint64)
+    for y in range(h - 1):
+        for x in range(w - 1):
+            d = int(depth[y, x])
+            if d == 0:
+                continue
+            out[y:y + 2, x:x + 2] = np.minimum(out[y:y + 2, x:x + 2], d)
+    out[out == 0xFFFFFFFF] = 0
+    return out.astype(np.uint32)
+
+
+def test_align_identity_closed_form(oracle):
+    rng = np.random.default_rng(7)
+    w, h = 64, 48
+    depth = rng.integers(300, 4000, (h, w)).astype(np.uint16)
+    depth[rng.random((h, w)) < 0.2] = 0
+    intr = oracle.make_intrinsics(w, h, 32.0, 24.0, 64.0, 64.0)
+    got = oracle.align_depth_to_other(depth, 2.0 ** -10, intr, intr, oracle.make_extrinsics())
+    assert np.array_equal(got, _closed_form_identity(depth))
+
+
+def test_align_translation_shifts_by_disparity(oracle):
+    """A pure x translation t at constant depth Z moves everything by fx*t/Z pixels: pick numbers where that is an
+    exact integer (fx=64, t=0.5, Z=4 -> 8 px)."""
+    w, h = 96, 32
+    depth = np.zeros((h, w), np.uint16)
+    depth[8:20, 10:40] = 4096  # * 2^-10 = 4.0
+    intr = oracle.make_intrinsics(w, h, 48.0, 16.0, 64.0, 64.0)
+    ex = oracle.make_extrinsics(translation=(0.5, 0, 0))
+    got = oracle.align_depth_to_other(depth, 2.0 ** -10, intr, intr, ex)
+    ref = np.zeros((h, w), np.uint32)
+    ref[8:21, 18:49] = 4096  # rectangle grows by one row/column (both corners are rounded outwards)
+    assert np.array_equal(got, ref)
+
+
+def test_align_all_zero_and_out_of_view(oracle):
+    w, h = 40, 30
+    intr = oracle.make_intrinsics(w, h, 20.0, 15.0, 32.0, 32.0)
+    assert not oracle.align_depth_to_other(np.zeros((h, w), np.uint16), 0.001, intr, intr, oracle.make_extrinsics()).any()
+    far = oracle.make_extrinsics(translation=(1000.0, 0, 0))  # everything projects right of the image
+    d = np.full((h, w), 1000, np.uint16)
+    assert not oracle.align_depth_to_other(d, 0.001, intr, intr, far).any()
+
+
+def test_keypoint_pixel_to_point_gate_order_and_values(oracle):
+    w, h = 64, 48
+    intr = oracle.make_intrinsics(w, h, 32.0, 24.0, 64.0, 64.0)
+    aligned = np.zeros((h, w), np.uint32)
+    aligned[10, 20] = 2048; aligned[11, 21] = 1; aligned[30, 40] = 512
+    kp = np.zeros(5, oracle.KEYPOINT_DTYPE)
+    kp["x"] = [20.4, 21.0, 40.0, 5.0, 19.5]
+    kp["y"] = [9.6, 11.0, 30.0, 5.0, 10.49]
+    kp["response"] = [30, 30, 30, 30, 1.0]
+    desc = np.arange(5 * 32, dtype=np.uint8).reshape(5, 32)
+    k2, d2, pts = oracle.keypoint_pixel_to_point(aligned, intr, kp, desc)
+    # kp0 -> (20,10) depth 2048 kept; kp1 depth 1 (not > 1) dropped; kp2 kept; kp3 no depth; kp4 response 1.0 dropped
+    assert np.array_equal(k2["x"], kp["x"][[0, 2]]) and np.array_equal(d2, desc[[0, 2]])
+    x0 = np.float64((np.float32(20.4) - np.float32(32)) / np.float32(64))
+    y0 = np.float64((np.float32(9.6) - np.float32(24)) / np.float32(64))
+    assert np.array_equal(pts[0], [2048.0 * x0, 2048.0 * y0, 2048.0])
+    assert np.array_equal(pts[1], [512.0 * 0.125, 512.0 * 0.09375, 512.0])
+
+
+def test_reproject_identity_and_transform(oracle):
+    intr = oracle.make_intrinsics(640, 480, 320.0, 240.0, 512.0, 512.0)
+    pts = np.array([[0.25, -0.5, 2.0], [1.0, 1.0, 4.0], [0.0, 0.0, 1.0]])
+    pos = oracle.reproject_points(pts, None, intr)
+    assert np.array_equal(pos, np.array([[384, 112], [448, 368], [320, 240]], np.float32))
+    T = np.eye(4); T[0, 3] = 0.5; T[2, 3] = 1.0  # x += 0.5, z += 1
+    pos = oracle.reproject_points(pts, T, intr)
+    ref = np.stack([(pts[:, 0] + 0.5) / (pts[:, 2] + 1) * 512 + 320, pts[:, 1] / (pts[:, 2] + 1) * 512 + 240], 1)
+    assert np.allclose(pos, ref, rtol=0, atol=1e-3)
+
+
+def test_distortion_round_trip(oracle):
+    """project(MODIFIED_BROWN_CONRADY) of deproject(INVERSE_BROWN_CONRADY) with the same coefficients is the identity
+    up to the model's approximation error: aligned depth through a distorted pair stays within a pixel of the
+    undistorted result."""
+    rng = np.random.default_rng(3)
+    w, h = 80, 60
+    depth = rng.integers(800, 1200, (h, w)).astype(np.uint16)
+    plain = oracle.make_intrinsics(w, h, 40.0, 30.0, 70.0, 70.0)
+    c = (0.05, -0.02, 0.001, -0.001, 0.003)
+    di = oracle.make_intrinsics(w, h, 40.0, 30.0, 70.0, 70.0, 2, c)
+    oi = oracle.make_intrinsics(w, h, 40.0, 30.0, 70.0, 70.0, 1, c)
+    a = oracle.align_depth_to_other(depth, 0.001, plain, plain, oracle.make_extrinsics())
+    b = oracle.align_depth_to_other(depth, 0.001, di, oi, oracle.make_extrinsics())
+    inner = (slice(8, h - 8), slice(8, w - 8))
+    assert (b[inner] > 0).all()
+    # each output is a min over a 2x2 neighbourhood; a sub-pixel model error moves at most one contributor
+    lo = np.minimum.reduce([np.roll(np.roll(depth, dy, 0), dx, 1) for dy in (-1, 0, 1, 2) for dx in (-1, 0, 1, 2)])
+    hi = np.maximum.reduce([np.roll(np.roll(depth, dy, 0), dx, 1) for dy in (-1, 0, 1, 2) for dx in (-1, 0, 1, 2)])
+    assert (b[inner] >= lo[inner]).all() and (b[inner] <= hi[inner]).all() and (a[inner] >= lo[inner]).all()
+
+
+def test_compact_pairs(oracle):
+    idx = np.array([2, -1, 0, -1, 1], np.int32)
+    qp = np.arange(15, dtype=np.float64).reshape(5, 3)
+    tp = 100 + np.arange(9, dtype=np.float64).reshape(3, 3)
+    txy = np.array([[10.9, 20.1], [30.5, 40.5], [65535.0, 0.2]], np.float32)
+    prev, curr, xs, ys = oracle.compact_pairs(idx, qp, tp, txy)
+    assert np.array_equal(prev, qp[[0, 2, 4]]) and np.array_equal(curr, tp[[2, 0, 1]])
+    assert xs.tolist() == [65535, 10, 30] and ys.tolist() == [0, 20, 40]
