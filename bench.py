@@ -170,6 +170,72 @@ def workload_config(frames_per_gpu):
             "parallelism": "frames sharded across GPUs, no data-path collective"}
 
 
+def bench_rgbd_stage(orbb, torch, device_index, steps, warmup):
+    """Frames/s through orbb_rgbd_stage_submit/wait (two batches in flight) at the cfg 2 geometry, plus the
+    alignment kernels timed alone against the HBM roofline (2 B depth read + 4 B aligned write per pixel)."""
+    synth = importlib.import_module(PKG + ".synth")
+    w, h, nb = 848, 480, 64
+    rng = np.random.default_rng(99)
+    base = [synth.textured_frame(w, h, 2000 + i) for i in range(8)]
+    gray = np.stack([np.roll(base[i % 8], (3 * (i // 8), 2 * (i // 8)), axis=(0, 1)) for i in range(nb)])
+    yy, xx = np.mgrid[0:h, 0:w].astype(np.float32)
+    depth = np.stack([np.clip(1500 + 900 * np.sin(xx / 97.0 + i) * np.cos(yy / 61.0) + rng.integers(-8, 9, (h, w)), 1, 65535)
+                      .astype(np.uint16) for i in range(4)])
+    depth[:, rng.random((h, w)) < 0.08] = 0
+    depth = depth[np.arange(nb) % 4]
+    di = orbb.make_intrinsics(w, h, w * 0.5 + 3.7, h * 0.5 - 2.2, 0.502 * w, 0.502 * w, 4)
+    oi = orbb.make_intrinsics(w, h, w * 0.5 - 5.1, h * 0.5 + 4.3, 0.72 * w, 0.725 * w, 2)
+    ex_ = orbb.make_extrinsics((1, 0, 0, 0, 1, 0, 0, 0, 1), (0.0148, 0.0002, 0.0003))
+    stage = orbb.RgbdFrameStage(orbb.Params(1200, SCALE, NLEVELS, INI_TH, MIN_TH), di, oi, ex_, 0.001, 2.0, 64,
+                                max_batch=nb, device=device_index)
+    pg = [torch.from_numpy(gray).pin_memory(), torch.from_numpy(np.roll(gray, 1, axis=0).copy()).pin_memory()]
+    pd = [torch.from_numpy(depth.view(np.int16)).pin_memory() for _ in range(2)]
+
+    def run(k):
+        prev, seen = None, 0
+        for i in range(k):
+            t = stage.submit_ptr(pg[i % 2].data_ptr(), pd[i % 2].data_ptr(), nb)
+            if prev is not None:
+                seen += int(stage.wait(prev)["valid_keypoints_num"].sum())
+            prev = t
+        return seen + int(stage.wait(prev)["valid_keypoints_num"].sum())
+
+    run(max(warmup, 2))
+    torch.cuda.synchronize()
+    l0 = stage.launch_count()
+    t0 = time.perf_counter()
+    seen = run(steps)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    launches = stage.launch_count() - l0
+    # alignment alone, device-resident
+    st = torch.cuda.current_stream()
+    ex = orbb.ORBextractor(100, SCALE, 2, INI_TH, MIN_TH, width=w, height=h, max_batch=1, device=device_index)
+    d_depth = torch.from_numpy(depth.view(np.int16)).cuda()
+    d_al = torch.zeros((nb, h, w), dtype=torch.int32, device="cuda")
+    for _ in range(3):
+        ex.align_depth_to_other(d_depth, nb, 0.001, di, oi, ex_, d_al, stream=st)
+    a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a0.record(st)
+    for _ in range(10):
+        ex.align_depth_to_other(d_depth, nb, 0.001, di, oi, ex_, d_al, stream=st)
+    a1.record(st)
+    torch.cuda.synchronize()
+    align_ms = a0.elapsed_time(a1) / 10
+    hbm_peak, peak_kind, _ = measured_peaks()
+    align_bytes = nb * w * h * 6
+    ex.close()
+    stage.close()
+    return {"value": nb * steps / dt, "unit": "frames/s", "workload": "cfg2-geometry: 848x480 gray + 848x480 u16 depth, "
+            "1200 kp, batches of 64 consecutive frames, window 2 px / Hamming < 64", "steps": steps,
+            "api": "orbb_rgbd_stage_submit + orbb_rgbd_stage_wait (2 batches in flight), wall clock",
+            "h2d_bytes_per_step": nb * w * h * 3, "d2h_bytes_per_step": nb * stage.max_kp * 136 + 12 * nb,
+            "valid_keypoints_per_frame": seen / (nb * steps), "gpu_launches": launches,
+            "align": {"ms_per_64_frames": align_ms, "algorithmic_bytes": align_bytes,
+                      "achieved_gbs": align_bytes / (align_ms * 1e-3) / 1e9,
+                      "frac_of_hbm": align_bytes / (align_ms * 1e-3) / 1e9 / hbm_peak, "peak_kind": peak_kind}}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -178,6 +244,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--frames", type=int, default=FRAMES_PER_GPU)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-rgbd", action="store_true", help="skip the RGB-D frame-stage leg (cfg 2 geometry)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -353,6 +420,12 @@ def main():
     match_ms = m0.elapsed_time(m1) / m_iters
     gpairs = nq * MAP_SIZE / (match_ms * 1e-3) / 1e9
 
+    # ---- RGB-D frame stage (BASELINE cfg 2 geometry: 848x480, 1200 kp, batches of 64 frames):
+    # pinned gray + depth in, align + extract + depth gate + reproject + windowed match + compaction, results D2H.
+    rgbd = None
+    if rank == 0 and world == 1 and not args.no_rgbd:
+        rgbd = bench_rgbd_stage(orbb, torch, local_rank, min(args.steps, 10), min(args.warmup, 3))
+
     # ---- the only collectives (after the timed region): gather per-frame counts and match records to rank 0
     sharding = importlib.import_module(PKG + ".sharding")
     g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -407,6 +480,8 @@ def main():
                         "nt": MAP_SIZE, "k": 1, "ms": match_ms_max, "popc_roof_gpairs_per_gpu": popc_roof,
                         "frac_of_popc_roof": gpairs / popc_roof},
         }
+        if rgbd is not None:
+            line["rgbd_stage"] = rgbd
         if world == 1 and not args.no_cpu:
             cores = os.cpu_count() or 1
             cfps, nsample, native = cpu_oracle_fps(host_sets[0], cores)

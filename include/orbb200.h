@@ -243,6 +243,53 @@ int orbb_match_windowed_batch(orbb_handle *h, const uint8_t *d_query, const floa
                               const double *d_train_points, double *d_prev_matched, double *d_curr_matched,
                               uint16_t *d_xy_u16, int32_t *d_nmatched, void *cuda_stream);
 
+/* ---------------------------------------------------------------- RGB-D frame stage
+ * The per-frame body of SlamGpuPipeline::buildStream (src/SlamGpuPipeline/buildStream.cpp:345-660) rewritten around
+ * the handle, for batches of consecutive frames of one camera stream: pinned H2D, depth alignment on its own stream
+ * next to the extraction (as :376-394 / :399-460), depth gate + 3-D lift (:468-487), reprojection + windowed match
+ * against the previous frame + pair compaction (:523-556), results D2H into stage-owned pinned memory.  Nothing is
+ * allocated per frame and nothing synchronises except orbb_rgbd_stage_wait (the reference cudaMallocs 3+5 buffers
+ * and synchronises four times per frame).  Frame f of a batch is matched against frame f-1; frame 0 against the last
+ * frame of the previous batch (kept on the device), or against nothing after create/reset.  JPEG preview, overlay and
+ * the (disabled) pose maths of the reference are out of scope. */
+typedef struct orbb_rgbd_stage orbb_rgbd_stage;
+typedef struct {
+    orbb_params orb;
+    int32_t max_batch;
+    orbb_intrinsics depth_intrin;   /* depth frames are depth_intrin.width x height, u16 */
+    orbb_intrinsics image_intrin;   /* gray frames are image_intrin.width x height, u8; keypoints live here */
+    orbb_extrinsics depth_to_image;
+    float depth_scale;              /* rs2 depth units -> metres; only "is it zero" matters (cuda-align.cu:139) */
+    float max_pixel_distance;       /* match_keypoints gate, 2 in the reference (buildStream.cpp:545-548) */
+    int32_t max_hamming_distance;   /* 4 of 32 bits in the reference; here out of 256 */
+} orbb_rgbd_config;
+/* == the per-frame fields of slam_frame_t (src/SlamGpuPipeline/types.h:25-65) for a batch; HOST pointers into
+ * stage-owned pinned memory, valid until the second-next submit. Row stride of every per-keypoint array: max_kp. */
+typedef struct {
+    int32_t n_frames, max_kp;
+    const int32_t *keypoints_count;       /* [n] extracted keypoints (slam_frame_t::keypoints_count) */
+    const int32_t *valid_keypoints_num;   /* [n] after the depth gate (h_valid_keypoints_num) */
+    const int32_t *matched_keypoints_num; /* [n] matched against the previous frame (h_matched_keypoints_num) */
+    const orbb_keypoint *keypoints;       /* [n][max_kp] depth-gated keypoints (d_pos + score + level) */
+    const uint8_t *descriptors;           /* [n][max_kp][32] (256-bit, not the reference's 32-bit squeeze) */
+    const double *points;                 /* [n][max_kp][3] (h_points) */
+    const double *previous_matched_points, *current_matched_points; /* [n][max_kp][3] */
+    const uint16_t *matched_xy;           /* [n][2][max_kp]: keypoints_x row, keypoints_y row */
+} orbb_slam_frames;
+int orbb_rgbd_stage_create(orbb_rgbd_stage **out, const orbb_rgbd_config *cfg, int device);
+int orbb_rgbd_stage_destroy(orbb_rgbd_stage *s);
+/* forget the previous frame (start of a new sequence) */
+int orbb_rgbd_stage_reset(orbb_rgbd_stage *s);
+/* the extractor handle inside the stage (getters, launch count, last CUDA error) */
+orbb_handle *orbb_rgbd_stage_handle(orbb_rgbd_stage *s);
+/* Enqueue n_frames consecutive frames: HOST gray [n][h][w] u8, HOST depth [n][dh][dw] u16 (pinned memory lets the
+ * copies overlap the previous batch's kernels), h_T = per-frame T_w2c_prev_curr, [n][16] column-major float64
+ * (Eigen::Matrix4d) or NULL for identity (the reference forces identity, buildStream.cpp:538).  Returns a ticket.
+ * At most two batches are in flight; input buffers must stay untouched until the ticket has been waited for. */
+int orbb_rgbd_stage_submit(orbb_rgbd_stage *s, const uint8_t *h_gray, const uint16_t *h_depth, int n_frames,
+                           const double *h_T);
+int orbb_rgbd_stage_wait(orbb_rgbd_stage *s, int ticket, orbb_slam_frames *out);
+
 /* ---------------------------------------------------------------- debug / parity access
  * Download stage outputs of frame `frame` of the last batch to HOST memory (synchronises). */
 /* padded level, contiguous (w+38) x (h+38) */

@@ -122,6 +122,35 @@ private:
     std::vector<int32_t> counts_;
 };
 
+// The SlamGpuPipeline slot body (reference src/SlamGpuPipeline/buildStream.cpp:345-660) as an object: what the slot
+// thread owns instead of its hand-allocated buffers, streams and the per-frame slam_frame_t mallocs.
+class RgbdFrameStage {
+public:
+    RgbdFrameStage(const orbb_rgbd_config &cfg, int device = -1) {
+        check(orbb_rgbd_stage_create(&s_, &cfg, device), nullptr, "orbb_rgbd_stage_create");
+    }
+    ~RgbdFrameStage() { orbb_rgbd_stage_destroy(s_); }
+    RgbdFrameStage(const RgbdFrameStage &) = delete;
+    RgbdFrameStage &operator=(const RgbdFrameStage &) = delete;
+    // enqueue a batch of consecutive frames (pinned host memory); returns a ticket
+    int submit(const uint8_t *gray, const uint16_t *depth, int n_frames, const double *T_w2c_prev_curr = nullptr) {
+        const int t = orbb_rgbd_stage_submit(s_, gray, depth, n_frames, T_w2c_prev_curr);
+        check(t, orbb_rgbd_stage_handle(s_), "orbb_rgbd_stage_submit");
+        return t;
+    }
+    // blocks until the batch is in host memory; the views stay valid until the second-next submit
+    orbb_slam_frames wait(int ticket) {
+        orbb_slam_frames f{};
+        check(orbb_rgbd_stage_wait(s_, ticket, &f), orbb_rgbd_stage_handle(s_), "orbb_rgbd_stage_wait");
+        return f;
+    }
+    void reset() { check(orbb_rgbd_stage_reset(s_), orbb_rgbd_stage_handle(s_), "orbb_rgbd_stage_reset"); }
+    orbb_handle *handle() const { return orbb_rgbd_stage_handle(s_); }
+
+private:
+    orbb_rgbd_stage *s_ = nullptr;
+};
+
 }  // namespace orbb200
 
 // ---- the reference's stage names (namespace Jetracer), async on the given stream -------------------------
@@ -156,6 +185,23 @@ inline void match_keypoints(orbb_handle *h, const uint8_t *d_desc_prev, const or
                                        d_kp_curr, (int)sizeof(orbb_keypoint), n_curr, (float)max_pixel_distance,
                                        max_hamming_distance, d_idx, d_dist, d_keypoints_num_matched, stream),
                    h, "match_keypoints (windowed)");
+}
+// src/cuda/cuda-align.cuh:41-50: the int2 pixel map and the device copies of the intrinsics are gone
+inline void align_depth_to_other(orbb_handle *h, uint32_t *d_aligned_out, const uint16_t *d_depth_in, float depth_scale,
+                                 const orbb_intrinsics &depth_intrin, const orbb_intrinsics &other_intrin,
+                                 const orbb_extrinsics &depth_to_other, int n_frames, void *stream) {
+    orbb200::check(orbb_align_depth_to_other(h, d_depth_in, n_frames, depth_scale, &depth_intrin, &other_intrin,
+                                             &depth_to_other, d_aligned_out, stream), h, "align_depth_to_other");
+}
+// src/cuda/cuda-align.cuh:52-65: counts stay on the device (the reference round-trips h_valid_keypoints_num)
+inline void keypoint_pixel_to_point(orbb_handle *h, const uint32_t *d_aligned_depth, const orbb_intrinsics &rgb_intrin,
+                                    int n_frames, const orbb_keypoint *d_kp_in, const uint8_t *d_descriptors_in,
+                                    const int32_t *d_keypoints_num, int max_kp, orbb_keypoint *d_kp_out,
+                                    uint8_t *d_descriptors_out, double *d_points, int32_t *d_valid_keypoints_num,
+                                    void *stream) {
+    orbb200::check(orbb_keypoint_pixel_to_point(h, d_aligned_depth, &rgb_intrin, n_frames, d_kp_in, d_descriptors_in,
+                                                d_keypoints_num, max_kp, d_kp_out, d_descriptors_out, d_points,
+                                                d_valid_keypoints_num, stream), h, "keypoint_pixel_to_point");
 }
 }  // namespace Jetracer
 

@@ -1,0 +1,244 @@
+// orbb_stage.cu -- the SlamGpuPipeline slot body rewritten around the handle: host-side mirror of
+// reference src/SlamGpuPipeline/buildStream.cpp:345-660 for batches of consecutive RGB-D frames.
+//
+// Streams (the reference uses stream / align_stream / nvjpeg_stream with four cudaStreamSynchronize per frame):
+//   s_in     H2D of gray, depth and the T matrices of batch k (double-buffered device staging)
+//   s_align  align_depth_to_other of batch k                      -- runs next to the extraction, as :376-394
+//   s_main   extraction -> depth gate / 3-D lift -> reprojection -> windowed match + compaction -> carry row
+//   s_out    D2H of the batch's results into pinned host memory (double-buffered)
+// linked by events only; the host blocks in orbb_rgbd_stage_wait and, with two batches already in flight, in
+// submit.  Device rows: every per-keypoint array has max_batch + 1 frame rows; row 0 carries the last frame of the
+// previous batch, so "previous frame of frame f" is simply row f and "current" is row f + 1.
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include "orbb_internal.cuh"
+
+struct orbb_rgbd_stage {
+    orbb_rgbd_config cfg{};
+    orbb_handle *h = nullptr;
+    int device = 0, B = 0, max_kp = 0;
+    size_t gray_bytes = 0, depth_px = 0, img_px = 0;
+    cudaStream_t s_in = nullptr, s_align = nullptr, s_main = nullptr, s_out = nullptr;
+    cudaEvent_t ev_in[2] = {}, ev_out[2] = {}, ev_main[2] = {}, ev_align = nullptr, ev_gate = nullptr;
+    // device
+    uint8_t *d_gray[2] = {};
+    uint16_t *d_depth[2] = {};
+    double *d_T[2] = {};
+    uint32_t *d_aligned = nullptr;
+    orbb_keypoint *d_kp_raw = nullptr, *d_kp = nullptr;
+    uint8_t *d_desc_raw = nullptr, *d_desc = nullptr;
+    int *d_counts_raw = nullptr, *d_valid = nullptr, *d_idx = nullptr, *d_dist = nullptr, *d_nm = nullptr;
+    double *d_pts = nullptr, *d_prev_m = nullptr, *d_curr_m = nullptr;
+    float *d_pos = nullptr;
+    uint16_t *d_xy = nullptr;
+    // pinned host results, by ticket parity
+    struct Host {
+        int *counts, *valid, *matched;
+        orbb_keypoint *kp;
+        uint8_t *desc;
+        double *pts, *prev_m, *curr_m, *T;
+        uint16_t *xy;
+        int n_frames;
+    } host[2] = {};
+    std::vector<void *> dev_allocs, host_allocs;
+    long long n_submitted = 0;
+    bool gate_recorded = false;
+};
+
+#define SCK(s, call)                                                                                       \
+    do {                                                                                                   \
+        cudaError_t e__ = (call);                                                                          \
+        if (e__ != cudaSuccess) {                                                                          \
+            fprintf(stderr, "orbb_rgbd_stage: %s:%d %s: %s\n", __FILE__, __LINE__, #call, cudaGetErrorString(e__)); \
+            return ORBB_ERR_CUDA;                                                                          \
+        }                                                                                                  \
+    } while (0)
+#define SRC(call)                 \
+    do {                          \
+        const int rc__ = (call);  \
+        if (rc__ < 0) return rc__; \
+    } while (0)
+
+template <typename T>
+static cudaError_t sdev(orbb_rgbd_stage *s, T **out, size_t count) {
+    void *p = nullptr;
+    cudaError_t e = cudaMalloc(&p, std::max<size_t>(count, 1) * sizeof(T));
+    if (e == cudaSuccess) { s->dev_allocs.push_back(p); *out = static_cast<T *>(p); }
+    return e;
+}
+template <typename T>
+static cudaError_t shost(orbb_rgbd_stage *s, T **out, size_t count) {
+    void *p = nullptr;
+    cudaError_t e = cudaHostAlloc(&p, std::max<size_t>(count, 1) * sizeof(T), cudaHostAllocDefault);
+    if (e == cudaSuccess) { s->host_allocs.push_back(p); *out = static_cast<T *>(p); }
+    return e;
+}
+
+extern "C" int orbb_rgbd_stage_destroy(orbb_rgbd_stage *s) {
+    if (!s) return ORBB_OK;
+    cudaSetDevice(s->device);
+    cudaDeviceSynchronize();
+    for (void *p : s->dev_allocs) cudaFree(p);
+    for (void *p : s->host_allocs) cudaFreeHost(p);
+    for (int i = 0; i < 2; ++i) {
+        if (s->ev_in[i]) cudaEventDestroy(s->ev_in[i]);
+        if (s->ev_out[i]) cudaEventDestroy(s->ev_out[i]);
+        if (s->ev_main[i]) cudaEventDestroy(s->ev_main[i]);
+    }
+    if (s->ev_align) cudaEventDestroy(s->ev_align);
+    if (s->ev_gate) cudaEventDestroy(s->ev_gate);
+    for (cudaStream_t st : {s->s_in, s->s_align, s->s_main, s->s_out})
+        if (st) cudaStreamDestroy(st);
+    orbb_destroy(s->h);
+    delete s;
+    return ORBB_OK;
+}
+
+extern "C" int orbb_rgbd_stage_create(orbb_rgbd_stage **out, const orbb_rgbd_config *cfg, int device) {
+    if (!out || !cfg || cfg->max_batch < 1 || cfg->max_hamming_distance < 0) return ORBB_ERR_INVALID;
+    *out = nullptr;
+    orbb_rgbd_stage *s = new (std::nothrow) orbb_rgbd_stage();
+    if (!s) return ORBB_ERR_INVALID;
+    s->cfg = *cfg;
+    s->B = cfg->max_batch;
+    int rc = orbb_create(&s->h, &cfg->orb, cfg->image_intrin.width, cfg->image_intrin.height, cfg->max_batch, device);
+    if (rc) { delete s; return rc; }
+    cudaGetDevice(&s->device);
+    s->max_kp = orbb_max_keypoints_per_frame(s->h);
+    s->img_px = (size_t)cfg->image_intrin.width * cfg->image_intrin.height;
+    s->gray_bytes = s->img_px;
+    s->depth_px = (size_t)cfg->depth_intrin.width * cfg->depth_intrin.height;
+    const size_t B = s->B, mk = s->max_kp, R = B + 1;
+#define SCKC(call)                                                        \
+    do {                                                                  \
+        if ((call) != cudaSuccess) {                                      \
+            fprintf(stderr, "orbb_rgbd_stage_create: %s failed: %s\n", #call, cudaGetErrorString(cudaGetLastError())); \
+            orbb_rgbd_stage_destroy(s);                                   \
+            return ORBB_ERR_CUDA;                                         \
+        }                                                                 \
+    } while (0)
+    if (cfg->depth_intrin.width < 1 || cfg->depth_intrin.height < 1) { orbb_rgbd_stage_destroy(s); return ORBB_ERR_INVALID; }
+    for (int i = 0; i < 2; ++i) {
+        SCKC(sdev(s, &s->d_gray[i], s->gray_bytes * B));
+        SCKC(sdev(s, &s->d_depth[i], s->depth_px * B));
+        SCKC(sdev(s, &s->d_T[i], 16 * B));
+        SCKC(cudaEventCreateWithFlags(&s->ev_in[i], cudaEventDisableTiming));
+        SCKC(cudaEventCreateWithFlags(&s->ev_out[i], cudaEventDisableTiming));
+        SCKC(cudaEventCreateWithFlags(&s->ev_main[i], cudaEventDisableTiming));
+        orbb_rgbd_stage::Host &H = s->host[i];
+        SCKC(shost(s, &H.counts, B)); SCKC(shost(s, &H.valid, B)); SCKC(shost(s, &H.matched, B));
+        SCKC(shost(s, &H.kp, B * mk)); SCKC(shost(s, &H.desc, B * mk * 32));
+        SCKC(shost(s, &H.pts, B * mk * 3)); SCKC(shost(s, &H.prev_m, B * mk * 3)); SCKC(shost(s, &H.curr_m, B * mk * 3));
+        SCKC(shost(s, &H.xy, B * mk * 2)); SCKC(shost(s, &H.T, B * 16));
+    }
+    SCKC(cudaEventCreateWithFlags(&s->ev_align, cudaEventDisableTiming));
+    SCKC(cudaEventCreateWithFlags(&s->ev_gate, cudaEventDisableTiming));
+    SCKC(sdev(s, &s->d_aligned, s->img_px * B));
+    SCKC(sdev(s, &s->d_kp_raw, B * mk)); SCKC(sdev(s, &s->d_desc_raw, B * mk * 32)); SCKC(sdev(s, &s->d_counts_raw, B));
+    SCKC(sdev(s, &s->d_kp, R * mk)); SCKC(sdev(s, &s->d_desc, R * mk * 32)); SCKC(sdev(s, &s->d_pts, R * mk * 3));
+    SCKC(sdev(s, &s->d_valid, R));
+    SCKC(sdev(s, &s->d_pos, B * mk * 2)); SCKC(sdev(s, &s->d_idx, B * mk)); SCKC(sdev(s, &s->d_dist, B * mk));
+    SCKC(sdev(s, &s->d_prev_m, B * mk * 3)); SCKC(sdev(s, &s->d_curr_m, B * mk * 3)); SCKC(sdev(s, &s->d_xy, B * mk * 2));
+    SCKC(sdev(s, &s->d_nm, B));
+    SCKC(cudaMemset(s->d_valid, 0, sizeof(int) * R));
+    for (cudaStream_t *st : {&s->s_in, &s->s_align, &s->s_main, &s->s_out})
+        SCKC(cudaStreamCreateWithFlags(st, cudaStreamNonBlocking));
+    SCKC(cudaDeviceSynchronize());
+#undef SCKC
+    *out = s;
+    return ORBB_OK;
+}
+
+extern "C" orbb_handle *orbb_rgbd_stage_handle(orbb_rgbd_stage *s) { return s ? s->h : nullptr; }
+
+extern "C" int orbb_rgbd_stage_reset(orbb_rgbd_stage *s) {
+    if (!s) return ORBB_ERR_INVALID;
+    SCK(s, cudaSetDevice(s->device));
+    SCK(s, cudaMemsetAsync(s->d_valid, 0, sizeof(int), s->s_main));  // row 0 = "no previous frame"
+    return ORBB_OK;
+}
+
+extern "C" int orbb_rgbd_stage_submit(orbb_rgbd_stage *s, const uint8_t *h_gray, const uint16_t *h_depth, int n_frames,
+                                      const double *h_T) {
+    if (!s || !h_gray || !h_depth) return ORBB_ERR_INVALID;
+    if (n_frames < 1 || n_frames > s->B) return ORBB_ERR_CAPACITY;
+    SCK(s, cudaSetDevice(s->device));
+    const int ticket = (int)s->n_submitted, p = ticket & 1;
+    const size_t n = n_frames, mk = s->max_kp;
+    orbb_rgbd_stage::Host &H = s->host[p];
+    if (ticket >= 2) SCK(s, cudaEventSynchronize(s->ev_out[p]));  // batch ticket-2 owned this parity's buffers
+    // ---- inputs
+    SCK(s, cudaMemcpyAsync(s->d_gray[p], h_gray, s->gray_bytes * n, cudaMemcpyHostToDevice, s->s_in));
+    SCK(s, cudaMemcpyAsync(s->d_depth[p], h_depth, s->depth_px * n * sizeof(uint16_t), cudaMemcpyHostToDevice, s->s_in));
+    if (h_T) {
+        std::memcpy(H.T, h_T, sizeof(double) * 16 * n);
+        SCK(s, cudaMemcpyAsync(s->d_T[p], H.T, sizeof(double) * 16 * n, cudaMemcpyHostToDevice, s->s_in));
+    }
+    SCK(s, cudaEventRecord(s->ev_in[p], s->s_in));
+    // ---- depth alignment on its own stream; the aligned buffer is free once the previous batch's gate has read it
+    SCK(s, cudaStreamWaitEvent(s->s_align, s->ev_in[p], 0));
+    if (s->gate_recorded) SCK(s, cudaStreamWaitEvent(s->s_align, s->ev_gate, 0));
+    SRC(orbb_align_depth_to_other(s->h, s->d_depth[p], n_frames, s->cfg.depth_scale, &s->cfg.depth_intrin,
+                                  &s->cfg.image_intrin, &s->cfg.depth_to_image, s->d_aligned, s->s_align));
+    SCK(s, cudaEventRecord(s->ev_align, s->s_align));
+    // ---- extraction
+    SCK(s, cudaStreamWaitEvent(s->s_main, s->ev_in[p], 0));
+    SRC(orbb_extract_batch_device(s->h, s->d_gray[p], (size_t)s->cfg.image_intrin.width, s->gray_bytes, n_frames,
+                                  s->d_kp_raw, s->d_desc_raw, s->d_counts_raw, s->max_kp, s->s_main));
+    // ---- depth gate + 3-D lift into rows 1..n (the previous batch's D2H must have drained them)
+    SCK(s, cudaStreamWaitEvent(s->s_main, s->ev_align, 0));
+    if (ticket >= 1) SCK(s, cudaStreamWaitEvent(s->s_main, s->ev_out[p ^ 1], 0));
+    SRC(orbb_keypoint_pixel_to_point(s->h, s->d_aligned, &s->cfg.image_intrin, n_frames, s->d_kp_raw, s->d_desc_raw,
+                                     s->d_counts_raw, s->max_kp, s->d_kp + mk, s->d_desc + 32 * mk, s->d_pts + 3 * mk,
+                                     s->d_valid + 1, s->s_main));
+    SCK(s, cudaEventRecord(s->ev_gate, s->s_main));
+    s->gate_recorded = true;
+    // ---- previous (rows 0..n-1) -> current (rows 1..n): reproject, windowed match, compact the 3-D pairs
+    SRC(orbb_reproject_points(s->h, s->d_pts, s->d_valid, n_frames, s->max_kp, h_T ? s->d_T[p] : nullptr,
+                              &s->cfg.image_intrin, s->d_pos, s->s_main));
+    SRC(orbb_match_windowed_batch(s->h, s->d_desc, s->d_pos, s->d_valid, s->d_desc + 32 * mk, s->d_kp + mk,
+                                  (int)sizeof(orbb_keypoint), s->d_valid + 1, n_frames, s->max_kp, s->cfg.max_pixel_distance,
+                                  s->cfg.max_hamming_distance, s->d_idx, s->d_dist, s->d_pts, s->d_pts + 3 * mk,
+                                  s->d_prev_m, s->d_curr_m, s->d_xy, s->d_nm, s->s_main));
+    SCK(s, cudaEventRecord(s->ev_main[p], s->s_main));
+    // ---- results to the host
+    SCK(s, cudaStreamWaitEvent(s->s_out, s->ev_main[p], 0));
+    SCK(s, cudaMemcpyAsync(H.counts, s->d_counts_raw, sizeof(int) * n, cudaMemcpyDeviceToHost, s->s_out));
+    SCK(s, cudaMemcpyAsync(H.valid, s->d_valid + 1, sizeof(int) * n, cudaMemcpyDeviceToHost, s->s_out));
+    SCK(s, cudaMemcpyAsync(H.matched, s->d_nm, sizeof(int) * n, cudaMemcpyDeviceToHost, s->s_out));
+    SCK(s, cudaMemcpyAsync(H.kp, s->d_kp + mk, sizeof(orbb_keypoint) * n * mk, cudaMemcpyDeviceToHost, s->s_out));
+    SCK(s, cudaMemcpyAsync(H.desc, s->d_desc + 32 * mk, 32 * n * mk, cudaMemcpyDeviceToHost, s->s_out));
+    SCK(s, cudaMemcpyAsync(H.pts, s->d_pts + 3 * mk, sizeof(double) * 3 * n * mk, cudaMemcpyDeviceToHost, s->s_out));
+    SCK(s, cudaMemcpyAsync(H.prev_m, s->d_prev_m, sizeof(double) * 3 * n * mk, cudaMemcpyDeviceToHost, s->s_out));
+    SCK(s, cudaMemcpyAsync(H.curr_m, s->d_curr_m, sizeof(double) * 3 * n * mk, cudaMemcpyDeviceToHost, s->s_out));
+    SCK(s, cudaMemcpyAsync(H.xy, s->d_xy, sizeof(uint16_t) * 2 * n * mk, cudaMemcpyDeviceToHost, s->s_out));
+    SCK(s, cudaEventRecord(s->ev_out[p], s->s_out));
+    H.n_frames = n_frames;
+    // ---- carry: the batch's last frame becomes row 0 (read by the next batch's reprojection / match only)
+    SCK(s, cudaMemcpyAsync(s->d_kp, s->d_kp + n * mk, sizeof(orbb_keypoint) * mk, cudaMemcpyDeviceToDevice, s->s_main));
+    SCK(s, cudaMemcpyAsync(s->d_desc, s->d_desc + 32 * n * mk, 32 * mk, cudaMemcpyDeviceToDevice, s->s_main));
+    SCK(s, cudaMemcpyAsync(s->d_pts, s->d_pts + 3 * n * mk, sizeof(double) * 3 * mk, cudaMemcpyDeviceToDevice, s->s_main));
+    SCK(s, cudaMemcpyAsync(s->d_valid, s->d_valid + n, sizeof(int), cudaMemcpyDeviceToDevice, s->s_main));
+    s->n_submitted++;
+    return ticket;
+}
+
+extern "C" int orbb_rgbd_stage_wait(orbb_rgbd_stage *s, int ticket, orbb_slam_frames *out) {
+    if (!s || ticket < 0 || ticket >= s->n_submitted) return ORBB_ERR_INVALID;
+    if (ticket < s->n_submitted - 2) return ORBB_ERR_INVALID;  // its buffers have been reused
+    SCK(s, cudaSetDevice(s->device));
+    const int p = ticket & 1;
+    SCK(s, cudaEventSynchronize(s->ev_out[p]));
+    if (out) {
+        const orbb_rgbd_stage::Host &H = s->host[p];
+        out->n_frames = H.n_frames; out->max_kp = s->max_kp;
+        out->keypoints_count = H.counts; out->valid_keypoints_num = H.valid; out->matched_keypoints_num = H.matched;
+        out->keypoints = H.kp; out->descriptors = H.desc; out->points = H.pts;
+        out->previous_matched_points = H.prev_m; out->current_matched_points = H.curr_m; out->matched_xy = H.xy;
+    }
+    return ORBB_OK;
+}

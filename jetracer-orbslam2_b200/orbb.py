@@ -36,6 +36,8 @@ EXPORTS = [
     "orbb_match_knn_segmented", "orbb_match_windowed", "orbb_debug_get_padded", "orbb_debug_get_blurred", "orbb_debug_get_scores",
     "orbb_debug_get_candidates", "orbb_debug_get_selected", "orbb_debug_distribute",
     "orbb_align_depth_to_other", "orbb_keypoint_pixel_to_point", "orbb_reproject_points", "orbb_match_windowed_batch",
+    "orbb_rgbd_stage_create", "orbb_rgbd_stage_destroy", "orbb_rgbd_stage_reset", "orbb_rgbd_stage_handle",
+    "orbb_rgbd_stage_submit", "orbb_rgbd_stage_wait",
 ]
 
 
@@ -63,6 +65,20 @@ class Intrinsics(C.Structure):
 class Extrinsics(C.Structure):
     """== rs2_extrinsics: column-major rotation, translation"""
     _fields_ = [("rotation", C.c_float * 9), ("translation", C.c_float * 3)]
+
+
+class RgbdConfig(C.Structure):
+    _fields_ = [("orb", Params), ("max_batch", C.c_int32), ("depth_intrin", Intrinsics), ("image_intrin", Intrinsics),
+                ("depth_to_image", Extrinsics), ("depth_scale", C.c_float), ("max_pixel_distance", C.c_float),
+                ("max_hamming_distance", C.c_int32)]
+
+
+class SlamFrames(C.Structure):
+    """== orbb_slam_frames: host pointers into the stage's pinned result buffers"""
+    _fields_ = [("n_frames", C.c_int32), ("max_kp", C.c_int32), ("keypoints_count", C.c_void_p),
+                ("valid_keypoints_num", C.c_void_p), ("matched_keypoints_num", C.c_void_p), ("keypoints", C.c_void_p),
+                ("descriptors", C.c_void_p), ("points", C.c_void_p), ("previous_matched_points", C.c_void_p),
+                ("current_matched_points", C.c_void_p), ("matched_xy", C.c_void_p)]
 
 
 DISTORTION_NONE, DISTORTION_MODIFIED_BROWN_CONRADY, DISTORTION_INVERSE_BROWN_CONRADY = 0, 1, 2
@@ -128,10 +144,17 @@ def load_library():
     L.orbb_reproject_points.argtypes = [vp, vp, vp, i32, i32, vp, C.POINTER(Intrinsics), vp, vp]
     L.orbb_match_windowed_batch.argtypes = [vp, vp, vp, vp, vp, vp, i32, vp, i32, i32, f32, i32, vp, vp, vp, vp, vp, vp,
                                             vp, vp, vp]
+    L.orbb_rgbd_stage_create.argtypes = [C.POINTER(vp), C.POINTER(RgbdConfig), i32]
+    L.orbb_rgbd_stage_destroy.argtypes = [vp]
+    L.orbb_rgbd_stage_reset.argtypes = [vp]
+    L.orbb_rgbd_stage_handle.argtypes = [vp]
+    L.orbb_rgbd_stage_submit.argtypes = [vp, vp, vp, i32, vp]
+    L.orbb_rgbd_stage_wait.argtypes = [vp, i32, C.POINTER(SlamFrames)]
     for name in EXPORTS:
         fn = getattr(L, name)
-        if name not in ("orbb_strerror", "orbb_last_cuda_error", "orbb_get_launch_count"):
+        if name not in ("orbb_strerror", "orbb_last_cuda_error", "orbb_get_launch_count", "orbb_rgbd_stage_handle"):
             fn.restype = C.c_int
+    L.orbb_rgbd_stage_handle.restype = vp
     L.orbb_get_launch_count.restype = C.c_longlong
     _lib = L
     return L
@@ -394,6 +417,87 @@ class ORBextractor:
         n = self._check(self._lib.orbb_debug_distribute(self._h, level, _np_ptr(cand), cand.shape[0], quota,
                                                         _np_ptr(out), self.max_kp))
         return out[:n].copy()
+
+
+class RgbdFrameStage:
+    """The SlamGpuPipeline slot (reference src/SlamGpuPipeline/buildStream.cpp:345-660) around the B200 handle:
+    ``submit(gray, depth[, T])`` enqueues a batch of consecutive RGB-D frames, ``wait(ticket)`` returns the
+    per-frame ``slam_frame_t`` fields as numpy views of the stage's pinned buffers."""
+
+    def __init__(self, orb_params: Params, depth_intrin: Intrinsics, image_intrin: Intrinsics,
+                 depth_to_image: Extrinsics, depth_scale: float = 0.001, max_pixel_distance: float = 2.0,
+                 max_hamming_distance: int = 64, max_batch: int = 1, device: int = -1):
+        self._lib = load_library()
+        self.cfg = RgbdConfig(orb_params, max_batch, depth_intrin, image_intrin, depth_to_image, depth_scale,
+                              max_pixel_distance, max_hamming_distance)
+        self._s = C.c_void_p()
+        rc = self._lib.orbb_rgbd_stage_create(C.byref(self._s), C.byref(self.cfg), device)
+        if rc != 0:
+            self._s = C.c_void_p()
+            raise OrbbError(f"orbb_rgbd_stage_create: {self._lib.orbb_strerror(rc).decode()} ({rc})")
+        self._h = C.c_void_p(self._lib.orbb_rgbd_stage_handle(self._s))
+        self.max_kp = self._lib.orbb_max_keypoints_per_frame(self._h)
+        self._keep = {}
+
+    def close(self):
+        if getattr(self, "_s", None) and self._s.value:
+            self._lib.orbb_rgbd_stage_destroy(self._s)
+            self._s = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc: int):
+        if rc < 0:
+            raise OrbbError(f"{self._lib.orbb_strerror(rc).decode()} ({rc})")
+        return rc
+
+    def launch_count(self) -> int:
+        return int(self._lib.orbb_get_launch_count(self._h))
+
+    def reset(self):
+        self._check(self._lib.orbb_rgbd_stage_reset(self._s))
+
+    def submit(self, gray: np.ndarray, depth: np.ndarray, T=None) -> int:
+        """gray [n,h,w] u8, depth [n,dh,dw] u16 (numpy, ideally views of pinned memory), T [n,4,4] float64 row-major."""
+        gray = np.ascontiguousarray(gray, np.uint8)
+        depth = np.ascontiguousarray(depth, np.uint16)
+        n = gray.shape[0]
+        Tc = None
+        if T is not None:
+            Tc = np.ascontiguousarray(np.asarray(T, np.float64).reshape(n, 4, 4).transpose(0, 2, 1))  # column-major
+        t = self._check(self._lib.orbb_rgbd_stage_submit(self._s, _np_ptr(gray), _np_ptr(depth), n,
+                                                         _np_ptr(Tc) if Tc is not None else C.c_void_p(0)))
+        self._keep[t & 1] = (gray, depth, Tc)  # inputs must outlive the copies
+        return t
+
+    def submit_ptr(self, gray_ptr: int, depth_ptr: int, n: int) -> int:
+        return self._check(self._lib.orbb_rgbd_stage_submit(self._s, C.c_void_p(gray_ptr), C.c_void_p(depth_ptr), n,
+                                                            C.c_void_p(0)))
+
+    def wait(self, ticket: int) -> dict:
+        out = SlamFrames()
+        self._check(self._lib.orbb_rgbd_stage_wait(self._s, ticket, C.byref(out)))
+        n, mk = out.n_frames, out.max_kp
+
+        def view(ptr, dtype, shape):
+            count = int(np.prod(shape))
+            buf = (C.c_uint8 * (count * np.dtype(dtype).itemsize)).from_address(ptr)
+            return np.frombuffer(buf, dtype, count).reshape(shape)
+
+        return dict(n_frames=n, max_kp=mk,
+                    keypoints_count=view(out.keypoints_count, np.int32, (n,)),
+                    valid_keypoints_num=view(out.valid_keypoints_num, np.int32, (n,)),
+                    matched_keypoints_num=view(out.matched_keypoints_num, np.int32, (n,)),
+                    keypoints=view(out.keypoints, KEYPOINT_DTYPE, (n, mk)),
+                    descriptors=view(out.descriptors, np.uint8, (n, mk, 32)),
+                    points=view(out.points, np.float64, (n, mk, 3)),
+                    previous_matched_points=view(out.previous_matched_points, np.float64, (n, mk, 3)),
+                    current_matched_points=view(out.current_matched_points, np.float64, (n, mk, 3)),
+                    matched_xy=view(out.matched_xy, np.uint16, (n, 2, mk)))
 
 
 def match_knn_host(ex: ORBextractor, query: np.ndarray, train: np.ndarray, k: int = 2, ratio: float = 0.7):

@@ -45,3 +45,23 @@ def test_strerror_and_no_device_is_loud(built):
     if not torch.cuda.is_available():
         with pytest.raises(built.OrbbError):
             built.ORBextractor(1000, 1.2, 8, 20, 7, width=640, height=480)  # must not fall back to a CPU path
+
+
+def test_cpp_host_mirror_compiles_and_links(built, tmp_path):
+    """include/orbb200.hpp (what a reference maintainer includes) compiles as C++17 and links against the library;
+    also pins the layouts the stage structs share with librealsense (rs2_intrinsics 48 B, rs2_extrinsics 48 B)."""
+    import subprocess
+    src = tmp_path / "mirror.cpp"
+    src.write_text('#include "orbb200.hpp"\n'
+                   'static_assert(sizeof(orbb_intrinsics) == 48 && sizeof(orbb_extrinsics) == 48, "rs2 layout");\n'
+                   'static_assert(sizeof(orbb_keypoint) == 28, "cv::KeyPoint layout");\n'
+                   'int main(int argc, char **) {\n'
+                   '  if (argc > 100) { orbb_rgbd_config c{}; orbb200::RgbdFrameStage s(c); s.reset();\n'
+                   '    orbb200::ORBextractor e(1000, 1.2f, 8, 20, 7, 640, 480); (void)e.GetLevels(); }\n'
+                   '  return 0; }\n')
+    libdir = os.path.dirname(built.LIB_PATH)
+    exe = tmp_path / "mirror"
+    subprocess.run(["g++", "-std=c++17", "-Wall", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe),
+                    "-L", libdir, "-lorbb200", "-Wl,-rpath," + libdir], check=True)
+    assert subprocess.run([str(exe)]).returncode == 0
+    assert ctypes.sizeof(built.Intrinsics) == 48 and ctypes.sizeof(built.Extrinsics) == 48

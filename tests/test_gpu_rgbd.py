@@ -187,3 +187,68 @@ def test_reproject_match_compact(orbb, oracle, synth, with_T):
         assert np.array_equal(xy[f, 0, :onm], oxs) and np.array_equal(xy[f, 1, :onm], oys)
         total += onm
     assert total > 50, "test too weak: hardly any match went through"
+
+
+def test_rgbd_frame_stage_sequence(orbb, oracle, synth):
+    """The host stage over a moving sequence fed as batches of 3 + 1 + 4 frames (two in flight):
+    every frame's gated keypoints / descriptors / 3-D points and its matches against the previous frame -- across
+    batch boundaries -- equal the oracle chain run frame by frame on the GPU extractor's raw output."""
+    import torch
+    w, h, nfeat = 640, 480, 600
+    base = synth.textured_frame(w, h, 4242)
+    gray = [base]
+    for i in range(7):
+        gray.append(synth.shifted_frame(gray[-1], 2, 1, 100 + i))
+    gray = np.stack(gray)
+    depth = np.stack([synth_depth(w, h, 300 + i // 3) for i in range(8)])
+    di, oi, e = d435_pair(orbb, w, h, False)
+    odi, ooi, oe = d435_pair(oracle, w, h, False)
+    params = orbb.Params(nfeat, 1.2, 8, 20, 7)
+    stage = orbb.RgbdFrameStage(params, di, oi, e, depth_scale=0.001, max_pixel_distance=6.0, max_hamming_distance=60,
+                                max_batch=4)
+    rng = np.random.default_rng(11)
+    T = np.tile(np.eye(4), (8, 1, 1))
+    T[:, :3, 3] = rng.normal(0, 1.5, (8, 3))  # millimetres: depth units are raw
+    t0 = stage.submit(gray[0:3], depth[0:3], T[0:3])
+    t1 = stage.submit(gray[3:4], depth[3:4], T[3:4])
+    r0 = {k: (v.copy() if isinstance(v, np.ndarray) else v) for k, v in stage.wait(t0).items()}
+    t2 = stage.submit(gray[4:8], depth[4:8], T[4:8])
+    r1 = {k: (v.copy() if isinstance(v, np.ndarray) else v) for k, v in stage.wait(t1).items()}
+    r2 = {k: (v.copy() if isinstance(v, np.ndarray) else v) for k, v in stage.wait(t2).items()}
+    got = {k: np.concatenate([r[k] for r in (r0, r1, r2)]) for k in r0 if isinstance(r0[k], np.ndarray)}
+
+    ex = orbb.ORBextractor(nfeat, 1.2, 8, 20, 7, width=w, height=h, max_batch=8)
+    kp, desc, counts = ex.extract_batch(gray)  # raw GPU output, GPU order (deterministic)
+    assert np.array_equal(got["keypoints_count"], counts)
+    prev = None
+    total_matched = 0
+    for f in range(8):
+        c = int(counts[f])
+        aligned = oracle.align_depth_to_other(depth[f], 0.001, odi, ooi, oe)
+        okp, odesc, opts = oracle.keypoint_pixel_to_point(aligned, ooi, kp[f, :c], desc[f, :c])
+        m = len(okp)
+        assert int(got["valid_keypoints_num"][f]) == m
+        assert np.array_equal(got["keypoints"][f, :m].view(np.uint8), okp.view(np.uint8))
+        assert np.array_equal(got["descriptors"][f, :m], odesc)
+        assert np.array_equal(got["points"][f, :m], opts)
+        if prev is None:
+            assert int(got["matched_keypoints_num"][f]) == 0
+        else:
+            pkp, pdesc, ppts = prev
+            pos = oracle.reproject_points(ppts, T[f], ooi)
+            txy = np.stack([okp["x"], okp["y"]], 1)
+            oidx, odist, onm = oracle.match_windowed(pdesc, pos, odesc, txy, 6.0, 60)
+            oprev, ocurr, oxs, oys = oracle.compact_pairs(oidx, ppts, opts, txy)
+            assert int(got["matched_keypoints_num"][f]) == onm, f"frame {f}"
+            assert np.array_equal(got["previous_matched_points"][f, :onm], oprev)
+            assert np.array_equal(got["current_matched_points"][f, :onm], ocurr)
+            assert np.array_equal(got["matched_xy"][f, 0, :onm], oxs) and np.array_equal(got["matched_xy"][f, 1, :onm], oys)
+            total_matched += onm
+        prev = (okp, odesc, opts)
+    assert total_matched > 300, f"sequence too weak: {total_matched} matches"
+    # reset drops the carried frame
+    stage.reset()
+    r = stage.wait(stage.submit(gray[0:1], depth[0:1]))
+    assert int(r["matched_keypoints_num"][0]) == 0
+    with pytest.raises(orbb.OrbbError):
+        stage.submit(gray[0:5], depth[0:5])  # over the stage's batch capacity
