@@ -243,6 +243,14 @@ int orbb_match_windowed_batch(orbb_handle *h, const uint8_t *d_query, const floa
                               const double *d_train_points, double *d_prev_matched, double *d_curr_matched,
                               uint16_t *d_xy_u16, int32_t *d_nmatched, void *cuda_stream);
 
+/* Jetracer::rgb_to_grayscale (src/cuda/cuda_RGB_to_Grayscale.cuh, kernel cuda_RGB_to_Grayscale.cu:10-24, call site
+ * buildStream.cpp:416-422) for a batch: gray = floor((B*0.07 + G*0.72 + R*0.21) + 0.5) in float64, every operation
+ * rounded on its own, interleaved RGB8 in.  DEVICE pointers; rgb_pitch must be a multiple of 4.  Async on stream.
+ * The output can be fed to orbb_extract_batch_device / orbb_stage_upload. */
+int orbb_rgb_to_grayscale(orbb_handle *h, const uint8_t *d_rgb, size_t rgb_pitch, size_t rgb_frame_stride, int width,
+                          int height, int n_frames, uint8_t *d_gray, size_t gray_pitch, size_t gray_frame_stride,
+                          void *cuda_stream);
+
 /* ---------------------------------------------------------------- RGB-D frame stage
  * The per-frame body of SlamGpuPipeline::buildStream (src/SlamGpuPipeline/buildStream.cpp:345-660) rewritten around
  * the handle, for batches of consecutive frames of one camera stream: pinned H2D, depth alignment on its own stream

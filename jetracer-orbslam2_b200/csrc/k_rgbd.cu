@@ -228,6 +228,39 @@ k_compact_pairs(const int *__restrict__ idx, const int *__restrict__ q_counts, i
     if (threadIdx.x == 0 && n_matched) n_matched[f] = base;
 }
 
+// ---- RGB8 -> gray (reference cuda_RGB_to_Grayscale.cu:10-24).  thread = 4 pixels: three aligned 32-bit loads, one
+// 32-bit store (the reference: 3 byte loads + 1 byte store per thread).  float64 like the reference's expression.
+__global__ void __launch_bounds__(256) k_rgb_to_gray(const uint8_t *__restrict__ rgb, size_t rgb_pitch, size_t rgb_stride,
+                                                     int width, int height, uint8_t *__restrict__ gray, size_t gray_pitch,
+                                                     size_t gray_stride, int aligned) {
+    const int q = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * 8 + threadIdx.y;
+    const int x = 4 * q;
+    if (x >= width || y >= height) return;
+    const uint8_t *src = rgb + blockIdx.z * rgb_stride + (size_t)y * rgb_pitch + 3 * (size_t)x;
+    uint8_t *dst = gray + blockIdx.z * gray_stride + (size_t)y * gray_pitch + x;
+    uint8_t px[12];
+    const int n = min(4, width - x);
+    if (aligned && n == 4) {
+        const uint32_t *s32 = reinterpret_cast<const uint32_t *>(src);
+        const uint32_t a = __ldg(s32), b = __ldg(s32 + 1), c = __ldg(s32 + 2);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { px[k] = (a >> (8 * k)) & 255u; px[4 + k] = (b >> (8 * k)) & 255u; px[8 + k] = (c >> (8 * k)) & 255u; }
+    } else {
+#pragma unroll
+        for (int k = 0; k < 12; ++k) px[k] = k < 3 * n ? src[k] : 0;
+    }
+    uint32_t out = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const double R = (double)(float)px[3 * k], G = (double)(float)px[3 * k + 1], B = (double)(float)px[3 * k + 2];
+        const double v = dadd(dadd(dadd(dmul(B, 0.07), dmul(G, 0.72)), dmul(R, 0.21)), 0.5);
+        out |= (uint32_t)(uint8_t)(int)floor(v) << (8 * k);
+    }
+    if (aligned && n == 4) *reinterpret_cast<uint32_t *>(dst) = out;
+    else
+        for (int k = 0; k < n; ++k) dst[k] = (uint8_t)(out >> (8 * k));
+}
+
 // ---------------------------------------------------------------- host launchers
 cudaError_t launch_align(const uint16_t *d_depth, int n_frames, float depth_scale, const orbb_intrinsics &di,
                          const orbb_intrinsics &oi, const orbb_extrinsics &ex, uint32_t *d_out, cudaStream_t st) {
@@ -263,6 +296,15 @@ cudaError_t launch_compact_pairs(const int *idx, const int *q_counts, int n_fram
     k_compact_pairs<<<n_frames, KP_THREADS, 0, st>>>(idx, q_counts, max_kp, q_points, t_points,
                                                      static_cast<const uint8_t *>(t_xy), t_stride, prev_out, curr_out, xy_out,
                                                      n_matched);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_rgb_to_gray(const uint8_t *d_rgb, size_t rgb_pitch, size_t rgb_stride, int w, int h, int n_frames,
+                               uint8_t *d_gray, size_t gray_pitch, size_t gray_stride, cudaStream_t st) {
+    const int aligned = ((reinterpret_cast<uintptr_t>(d_rgb) | rgb_pitch | rgb_stride | reinterpret_cast<uintptr_t>(d_gray) |
+                          gray_pitch | gray_stride) & 3) == 0;
+    dim3 grid(((w + 3) / 4 + 31) / 32, (h + 7) / 8, n_frames), block(32, 8);
+    k_rgb_to_gray<<<grid, block, 0, st>>>(d_rgb, rgb_pitch, rgb_stride, w, h, d_gray, gray_pitch, gray_stride, aligned);
     return cudaGetLastError();
 }
 

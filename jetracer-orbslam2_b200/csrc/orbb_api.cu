@@ -40,6 +40,7 @@ cudaError_t launch_reproject(const double *, const int *, int, int, const double
                              cudaStream_t);
 cudaError_t launch_compact_pairs(const int *, const int *, int, int, const double *, const double *, const void *, int,
                                  double *, double *, uint16_t *, int *, cudaStream_t);
+cudaError_t launch_rgb_to_gray(const uint8_t *, size_t, size_t, int, int, int, uint8_t *, size_t, size_t, cudaStream_t);
 cudaError_t launch_match_windowed_batch(const uint8_t *, const void *, int, const int *, const uint8_t *, const void *, int,
                                         const int *, int, int, float, int, int *, int *, cudaStream_t);
 }  // namespace orbb
@@ -883,6 +884,19 @@ extern "C" int orbb_match_windowed_batch(orbb_handle *h, const uint8_t *d_query,
                                    t_xy_stride, d_prev_matched, d_curr_matched, d_xy_u16, d_nmatched, st));
         h->n_launches += 1;
     }
+    return ORBB_OK;
+}
+
+extern "C" int orbb_rgb_to_grayscale(orbb_handle *h, const uint8_t *d_rgb, size_t rgb_pitch, size_t rgb_frame_stride, int width,
+                                     int height, int n_frames, uint8_t *d_gray, size_t gray_pitch, size_t gray_frame_stride,
+                                     void *stream) {
+    if (!h || !d_rgb || !d_gray || width < 1 || height < 1 || n_frames < 1 || rgb_pitch < 3 * (size_t)width ||
+        gray_pitch < (size_t)width)
+        return ORBB_ERR_INVALID;
+    CK(h, cudaSetDevice(h->device));
+    CK(h, launch_rgb_to_gray(d_rgb, rgb_pitch, rgb_frame_stride, width, height, n_frames, d_gray, gray_pitch,
+                             gray_frame_stride, static_cast<cudaStream_t>(stream)));
+    h->n_launches += 1;
     return ORBB_OK;
 }
 

@@ -36,6 +36,7 @@ EXPORTS = [
     "orbb_match_knn_segmented", "orbb_match_windowed", "orbb_debug_get_padded", "orbb_debug_get_blurred", "orbb_debug_get_scores",
     "orbb_debug_get_candidates", "orbb_debug_get_selected", "orbb_debug_distribute",
     "orbb_align_depth_to_other", "orbb_keypoint_pixel_to_point", "orbb_reproject_points", "orbb_match_windowed_batch",
+    "orbb_rgb_to_grayscale",
     "orbb_rgbd_stage_create", "orbb_rgbd_stage_destroy", "orbb_rgbd_stage_reset", "orbb_rgbd_stage_handle",
     "orbb_rgbd_stage_submit", "orbb_rgbd_stage_wait",
 ]
@@ -144,6 +145,7 @@ def load_library():
     L.orbb_reproject_points.argtypes = [vp, vp, vp, i32, i32, vp, C.POINTER(Intrinsics), vp, vp]
     L.orbb_match_windowed_batch.argtypes = [vp, vp, vp, vp, vp, vp, i32, vp, i32, i32, f32, i32, vp, vp, vp, vp, vp, vp,
                                             vp, vp, vp]
+    L.orbb_rgb_to_grayscale.argtypes = [vp, vp, sz, sz, i32, i32, i32, vp, sz, sz, vp]
     L.orbb_rgbd_stage_create.argtypes = [C.POINTER(vp), C.POINTER(RgbdConfig), i32]
     L.orbb_rgbd_stage_destroy.argtypes = [vp]
     L.orbb_rgbd_stage_reset.argtypes = [vp]
@@ -350,6 +352,13 @@ class ORBextractor:
             _dev_ptr(d_nmatched) if d_nmatched is not None else C.c_void_p(0), _stream_ptr(stream)))
 
     # -- RGB-D association (reference src/cuda/cuda-align.cuh, post_processing.cuh) -----------
+    def rgb_to_grayscale(self, d_rgb, n: int, d_gray, width=None, height=None, stream=None):
+        """Jetracer::rgb_to_grayscale on [n,h,w,3] interleaved RGB8 -> [n,h,w] gray (contiguous device tensors)."""
+        w = self.width if width is None else width
+        hh = self.height if height is None else height
+        self._check(self._lib.orbb_rgb_to_grayscale(self._h, _dev_ptr(d_rgb), 3 * w, 3 * w * hh, w, hh, n, _dev_ptr(d_gray),
+                                                    w, w * hh, _stream_ptr(stream)))
+
     def align_depth_to_other(self, d_depth, n: int, depth_scale: float, depth_intrin: Intrinsics,
                              other_intrin: Intrinsics, depth_to_other: Extrinsics, d_aligned_out, stream=None):
         self._check(self._lib.orbb_align_depth_to_other(self._h, _dev_ptr(d_depth), n, depth_scale, C.byref(depth_intrin),

@@ -118,6 +118,8 @@ def lib(native: bool = False):
     L.orbo_reproject_points.restype = None
     L.orbo_compact_pairs.argtypes = [vp, C.c_int, vp, vp, vp, C.c_int, vp, vp, vp, vp]
     L.orbo_compact_pairs.restype = C.c_int
+    L.orbo_rgb_to_grayscale.argtypes = [vp, C.c_size_t, C.c_int, C.c_int, vp, C.c_size_t]
+    L.orbo_rgb_to_grayscale.restype = None
     del u8p, i32p, f32p
     if not native:
         _lib = L
@@ -347,3 +349,11 @@ def compact_pairs(idx: np.ndarray, q_points: np.ndarray, t_points: np.ndarray, t
     ys = np.zeros(max(n, 1), np.uint16)
     m = lib().orbo_compact_pairs(_p(idx), n, _p(q_points), _p(t_points), _p(t_xy), 2, _p(prev), _p(curr), _p(xs), _p(ys))
     return prev[:m].copy(), curr[:m].copy(), xs[:m].copy(), ys[:m].copy()
+
+
+def rgb_to_grayscale(rgb: np.ndarray) -> np.ndarray:
+    rgb = np.ascontiguousarray(rgb, np.uint8)
+    h, w, _ = rgb.shape
+    out = np.empty((h, w), np.uint8)
+    lib().orbo_rgb_to_grayscale(_p(rgb), rgb.strides[0], w, h, _p(out), w)
+    return out

@@ -176,3 +176,15 @@ int orbo_compact_pairs(const int32_t *idx, int nq, const double *q_points, const
     }
     return m;
 }
+
+/* kernel_rgb_to_grayscale (reference src/cuda/cuda_RGB_to_Grayscale.cu:10-24), the expression as written there */
+void orbo_rgb_to_grayscale(const uint8_t *src, size_t src_pitch, int cols, int rows, uint8_t *dst, size_t dst_pitch) {
+    for (int y = 0; y < rows; ++y)
+        for (int x = 0; x < cols; ++x) {
+            float R, G, B;
+            R = (float)(src[y * src_pitch + x * 3 + 0]);
+            G = (float)(src[y * src_pitch + x * 3 + 1]);
+            B = (float)(src[y * src_pitch + x * 3 + 2]);
+            dst[y * dst_pitch + x] = (uint8_t)floor((B * 0.07 + G * 0.72 + R * 0.21) + 0.5);
+        }
+}

@@ -252,3 +252,22 @@ def test_rgbd_frame_stage_sequence(orbb, oracle, synth):
     assert int(r["matched_keypoints_num"][0]) == 0
     with pytest.raises(orbb.OrbbError):
         stage.submit(gray[0:5], depth[0:5])  # over the stage's batch capacity
+
+
+@pytest.mark.parametrize("w,h", [(848, 480), (333, 251), (5, 3)])
+def test_rgb_to_grayscale(orbb, oracle, w, h):
+    import torch
+    rng = np.random.default_rng(w)
+    n = 3
+    rgb = rng.integers(0, 256, (n, h, w, 3)).astype(np.uint8)
+    tie = [(r, g, b) for r in range(0, 256, 3) for g in range(0, 256, 5) for b in range(256)
+           if (7 * b + 72 * g + 21 * r) % 100 == 50][:w * h // 2]
+    rgb[0].reshape(-1, 3)[:len(tie)] = np.array(tie, np.uint8)
+    ex = orbb.ORBextractor(100, 1.2, 2, 20, 7, width=640, height=480, max_batch=1)
+    d_rgb = torch.from_numpy(rgb).cuda()
+    d_gray = torch.zeros((n, h, w), dtype=torch.uint8, device="cuda")
+    ex.rgb_to_grayscale(d_rgb, n, d_gray, width=w, height=h, stream=torch.cuda.current_stream())
+    torch.cuda.synchronize()
+    got = d_gray.cpu().numpy()
+    for i in range(n):
+        assert np.array_equal(got[i], oracle.rgb_to_grayscale(rgb[i])), f"frame {i}"

@@ -114,3 +114,17 @@ def test_compact_pairs(oracle):
     prev, curr, xs, ys = oracle.compact_pairs(idx, qp, tp, txy)
     assert np.array_equal(prev, qp[[0, 2, 4]]) and np.array_equal(curr, tp[[2, 0, 1]])
     assert xs.tolist() == [65535, 10, 30] and ys.tolist() == [0, 20, 40]
+
+
+def test_rgb_to_grayscale_matches_float64_formula(oracle):
+    """Independent restatement with numpy float64 (IEEE, un-fused): floor((B*0.07 + G*0.72 + R*0.21) + 0.5), over a
+    frame that contains every boundary case 7B + 72G + 21R = 50 (mod 100)."""
+    rng = np.random.default_rng(1)
+    rgb = rng.integers(0, 256, (64, 96, 3)).astype(np.uint8)
+    tie = [(r, g, b) for r in range(0, 256, 5) for g in range(0, 256, 7) for b in range(256)
+           if (7 * b + 72 * g + 21 * r) % 100 == 50][:64 * 96 // 2]
+    rgb.reshape(-1, 3)[:len(tie)] = np.array(tie, np.uint8)
+    R, G, B = (rgb[..., i].astype(np.float32).astype(np.float64) for i in range(3))
+    ref = np.floor((B * 0.07 + G * 0.72 + R * 0.21) + 0.5).astype(np.uint8)
+    assert np.array_equal(oracle.rgb_to_grayscale(rgb), ref)
+    assert oracle.rgb_to_grayscale(np.full((4, 4, 3), 255, np.uint8)).max() == 255
