@@ -66,10 +66,22 @@ __device__ __forceinline__ void project_xy(float pix[2], const orbb_intrinsics &
     pix[1] = fadd(fmul(y, in.fy), in.ppy);
 }
 
-// ---- depth -> other image.  thread = one depth pixel of one frame.
+// ---- depth -> other image.  thread = one depth pixel of one frame, CTA = 32 x 8 pixels.
+// Without a distortion model on the depth side the normalised corner coordinates (c -+ 0.5 - pp) / f depend only on
+// the column (row): the CTA computes its 33 + 9 distinct values once (42 IEEE divisions instead of 1024) and the
+// pixels read them from shared memory -- the same operations on the same operands, so the result is unchanged.
 __global__ void __launch_bounds__(256) k_align_scatter(const uint16_t *__restrict__ depth, uint32_t *__restrict__ out,
                                                        const AlignArgs A) {
+    __shared__ float s_nx[33], s_ny[9];
     const int x = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * 8 + threadIdx.y;
+    const bool plain = A.d.model != ORBB_DISTORTION_INVERSE_BROWN_CONRADY;
+    if (plain) {
+        const int t = threadIdx.y * 32 + threadIdx.x;
+        // corner k of the tile: pixel (x0 + k) - 0.5, which is also pixel (x0 + k - 1) + 0.5 (both sums are exact)
+        if (t < 33) s_nx[t] = __fdiv_rn(__fsub_rn(fadd((float)(blockIdx.x * 32 + t), -0.5f), A.d.ppx), A.d.fx);
+        else if (t < 42) s_ny[t - 33] = __fdiv_rn(__fsub_rn(fadd((float)(blockIdx.y * 8 + t - 33), -0.5f), A.d.ppy), A.d.fy);
+        __syncthreads();
+    }
     if (x >= A.d.width || y >= A.d.height) return;
     const size_t f = blockIdx.z;
     const unsigned raw = depth[(f * A.d.height + y) * A.d.width + x];
@@ -78,9 +90,13 @@ __global__ void __launch_bounds__(256) k_align_scatter(const uint16_t *__restric
     int cx[2], cy[2];
 #pragma unroll
     for (int c = 0; c < 2; ++c) {  // top-left (-0.5) and bottom-right (+0.5) corner of the depth pixel
-        const float shift = c ? 0.5f : -0.5f;
         float p[3], q[3], pix[2];
-        deproject(p, A.d, fadd((float)x, shift), fadd((float)y, shift), dv);
+        if (plain) {
+            p[0] = fmul(dv, s_nx[threadIdx.x + c]); p[1] = fmul(dv, s_ny[threadIdx.y + c]); p[2] = dv;
+        } else {
+            const float shift = c ? 0.5f : -0.5f;
+            deproject(p, A.d, fadd((float)x, shift), fadd((float)y, shift), dv);
+        }
         const float *R = A.e.rotation, *T = A.e.translation;
         q[0] = fadd(fadd(fadd(fmul(R[0], p[0]), fmul(R[3], p[1])), fmul(R[6], p[2])), T[0]);
         q[1] = fadd(fadd(fadd(fmul(R[1], p[0]), fmul(R[4], p[1])), fmul(R[7], p[2])), T[1]);
