@@ -479,3 +479,34 @@ def test_noise_1280x720_over_64k_candidates(orbb, oracle):
     assert len(ex.debug_candidates(0)) == len(o.level_candidates(0)) > 65535
     assert len(gk) == len(okp) and gk.tobytes() == okp.tobytes() and np.array_equal(gd, od)
     ex.close()
+
+
+def test_cuda_graph_replay_opt_in(orbb, oracle, synth, monkeypatch):
+    """ORBB_GRAPH=1: the small-batch device entry point replays a captured CUDA graph; results stay bit-exact across
+    replays, across alternating buffer sets (graph cache) and after an eviction (5 distinct argument sets > 4 slots)."""
+    import torch
+    monkeypatch.setenv("ORBB_GRAPH", "1")
+    w, h = 320, 240
+    ex = orbb.ORBextractor(400, 1.2, 6, 20, 7, width=w, height=h, max_batch=2)
+    monkeypatch.delenv("ORBB_GRAPH")
+    st = torch.cuda.current_stream()
+    o = oracle.Oracle(w, h, 400, 1.2, 6, 20, 7)
+    sets = []
+    for k in range(5):
+        frames = np.stack([synth.textured_frame(w, h, 600 + 2 * k), synth.textured_frame(w, h, 601 + 2 * k)])
+        sets.append((frames, torch.from_numpy(frames).cuda(), torch.zeros((2, ex.max_kp, 7), dtype=torch.float32, device="cuda"),
+                     torch.zeros((2, ex.max_kp, 32), dtype=torch.uint8, device="cuda"), torch.zeros(2, dtype=torch.int32, device="cuda")))
+    l0 = ex.launch_count()
+    for rep in range(3):
+        for frames, d_in, d_kp, d_desc, d_cnt in sets:
+            d_kp.zero_(); d_desc.zero_(); d_cnt.zero_()
+            ex.extract_batch_device(d_in, 2, d_kp, d_desc, d_cnt, stream=st)
+            torch.cuda.synchronize()
+            kp = d_kp.cpu().numpy().view(orbb.KEYPOINT_DTYPE).reshape(2, ex.max_kp)
+            desc = d_desc.cpu().numpy(); cnt = d_cnt.cpu().numpy()
+            for f in range(2):
+                okp, odesc = canon(*o.extract(frames[f]))
+                gkp, gdesc = canon(kp[f, :cnt[f]], desc[f, :cnt[f]])
+                assert len(gkp) == len(okp)
+                assert np.array_equal(gkp.view(np.uint8), okp.view(np.uint8)) and np.array_equal(gdesc, odesc)
+    assert ex.launch_count() - l0 == 15 * 10  # replays are counted like direct launches: level0 + 5 resizes + 4
