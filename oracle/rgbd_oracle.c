@@ -32,63 +32,77 @@ static int f2i_cuda(float v) {
     return (int)v;
 }
 
-/* cuda-align.cu:26-56 */
-static void project_point_to_pixel(float pixel[2], const orbo_intrinsics *intrin, const float point[3]) {
-    float x = point[0] / point[2], y = point[1] / point[2];
-    if (intrin->model == MODEL_MODIFIED_BC) {
-        float r2 = x * x + y * y;
-        float f = 1 + intrin->coeffs[0] * r2 + intrin->coeffs[1] * r2 * r2 + intrin->coeffs[4] * r2 * r2 * r2;
+/* ---- camera model pieces.  The evaluation order of every sum and product below is the one C gives the
+ * reference's expressions (left to right, integer constants promoted to the floating type of the expression);
+ * compiled with -ffp-contract=off nothing is fused. */
+
+/* radial polynomial 1 + k1 r2 + k2 r2^2 + k3 r2^3 (k3 is coeffs[4]) -- cuda-align.cu:39, :74 */
+static float radial_f32(const float *k, float r2) { return 1 + k[0] * r2 + k[1] * r2 * r2 + k[4] * r2 * r2 * r2; }
+static double radial_f64(const float *k, double r2) { return 1 + k[0] * r2 + k[1] * r2 * r2 + k[4] * r2 * r2 * r2; }
+
+/* tangential terms added to a coordinate that has (forward model) or has not (inverse model) been scaled by the
+ * radial factor; p1 = coeffs[2], p2 = coeffs[3] -- cuda-align.cu:42-43, :75-76 */
+static float tangential_x32(const float *k, float base, float x, float y, float r2) {
+    return base + 2 * k[2] * x * y + k[3] * (r2 + 2 * x * x);
+}
+static float tangential_y32(const float *k, float base, float x, float y, float r2) {
+    return base + 2 * k[3] * x * y + k[2] * (r2 + 2 * y * y);
+}
+
+/* normalised image coordinates -> pixel, with the forward (MODIFIED_BROWN_CONRADY) distortion -- cuda-align.cu:26-56 */
+static void normalized_to_pixel(const orbo_intrinsics *cam, float x, float y, float *u, float *v) {
+    if (cam->model == MODEL_MODIFIED_BC) {
+        const float r2 = x * x + y * y;
+        const float f = radial_f32(cam->coeffs, r2);
         x *= f;
         y *= f;
-        float dx = x + 2 * intrin->coeffs[2] * x * y + intrin->coeffs[3] * (r2 + 2 * x * x);
-        float dy = y + 2 * intrin->coeffs[3] * x * y + intrin->coeffs[2] * (r2 + 2 * y * y);
-        x = dx;
-        y = dy;
+        const float xd = tangential_x32(cam->coeffs, x, x, y, r2), yd = tangential_y32(cam->coeffs, y, x, y, r2);
+        x = xd;
+        y = yd;
     }
-    pixel[0] = x * intrin->fx + intrin->ppx;
-    pixel[1] = y * intrin->fy + intrin->ppy;
+    *u = x * cam->fx + cam->ppx;
+    *v = y * cam->fy + cam->ppy;
 }
 
-/* cuda-align.cu:58-83 */
-static void deproject_pixel_to_point(float point[3], const orbo_intrinsics *intrin, const float pixel[2], float depth) {
-    float x = (pixel[0] - intrin->ppx) / intrin->fx;
-    float y = (pixel[1] - intrin->ppy) / intrin->fy;
-    if (intrin->model == MODEL_INVERSE_BC) {
-        float r2 = x * x + y * y;
-        float f = 1 + intrin->coeffs[0] * r2 + intrin->coeffs[1] * r2 * r2 + intrin->coeffs[4] * r2 * r2 * r2;
-        float ux = x * f + 2 * intrin->coeffs[2] * x * y + intrin->coeffs[3] * (r2 + 2 * x * x);
-        float uy = y * f + 2 * intrin->coeffs[3] * x * y + intrin->coeffs[2] * (r2 + 2 * y * y);
-        x = ux;
-        y = uy;
+/* pixel + depth -> 3-D point, with the INVERSE_BROWN_CONRADY undistortion -- cuda-align.cu:58-83 */
+static void pixel_to_point_f32(const orbo_intrinsics *cam, float u, float v, float depth, float out[3]) {
+    float x = (u - cam->ppx) / cam->fx;
+    float y = (v - cam->ppy) / cam->fy;
+    if (cam->model == MODEL_INVERSE_BC) {
+        const float r2 = x * x + y * y;
+        const float f = radial_f32(cam->coeffs, r2);
+        const float xu = tangential_x32(cam->coeffs, x * f, x, y, r2), yu = tangential_y32(cam->coeffs, y * f, x, y, r2);
+        x = xu;
+        y = yu;
     }
-    point[0] = depth * x;
-    point[1] = depth * y;
-    point[2] = depth;
+    out[0] = depth * x;
+    out[1] = depth * y;
+    out[2] = depth;
 }
 
-/* cuda-align.cu:85-110 */
-static void deproject_pixel_to_point_double(double *point, const orbo_intrinsics *intrin, const float pixel[2], float depth) {
-    double x = (pixel[0] - intrin->ppx) / intrin->fx;
-    double y = (pixel[1] - intrin->ppy) / intrin->fy;
-    if (intrin->model == MODEL_INVERSE_BC) {
-        double r2 = x * x + y * y;
-        double f = 1 + intrin->coeffs[0] * r2 + intrin->coeffs[1] * r2 * r2 + intrin->coeffs[4] * r2 * r2 * r2;
-        double ux = x * f + 2 * intrin->coeffs[2] * x * y + intrin->coeffs[3] * (r2 + 2 * x * x);
-        double uy = y * f + 2 * intrin->coeffs[3] * x * y + intrin->coeffs[2] * (r2 + 2 * y * y);
-        x = ux;
-        y = uy;
+/* the float64 twin used for the keypoints (float32 normalisation, float64 afterwards) -- cuda-align.cu:85-110 */
+static void pixel_to_point_f64(const orbo_intrinsics *cam, float u, float v, float depth, double out[3]) {
+    double x = (u - cam->ppx) / cam->fx;
+    double y = (v - cam->ppy) / cam->fy;
+    if (cam->model == MODEL_INVERSE_BC) {
+        const float *k = cam->coeffs;
+        const double r2 = x * x + y * y;
+        const double f = radial_f64(k, r2);
+        const double xu = x * f + 2 * k[2] * x * y + k[3] * (r2 + 2 * x * x);
+        const double yu = y * f + 2 * k[3] * x * y + k[2] * (r2 + 2 * y * y);
+        x = xu;
+        y = yu;
     }
-    double depth_d = (double)depth;
-    point[0] = depth_d * x;
-    point[1] = depth_d * y;
-    point[2] = depth_d;
+    const double z = (double)depth;
+    out[0] = z * x;
+    out[1] = z * y;
+    out[2] = z;
 }
 
-/* cuda-align.cu:112-120 */
-static void transform_point_to_point(float to_point[3], const orbo_extrinsics *extrin, const float from_point[3]) {
-    to_point[0] = extrin->rotation[0] * from_point[0] + extrin->rotation[3] * from_point[1] + extrin->rotation[6] * from_point[2] + extrin->translation[0];
-    to_point[1] = extrin->rotation[1] * from_point[0] + extrin->rotation[4] * from_point[1] + extrin->rotation[7] * from_point[2] + extrin->translation[1];
-    to_point[2] = extrin->rotation[2] * from_point[0] + extrin->rotation[5] * from_point[1] + extrin->rotation[8] * from_point[2] + extrin->translation[2];
+/* rigid transform, column-major rotation -- cuda-align.cu:112-120 */
+static void rigid_transform(const orbo_extrinsics *e, const float p[3], float q[3]) {
+    for (int r = 0; r < 3; ++r)
+        q[r] = e->rotation[r] * p[0] + e->rotation[3 + r] * p[1] + e->rotation[6 + r] * p[2] + e->translation[r];
 }
 
 /* kernel_map_depth_to_other + kernel_reset_to_max + kernel_depth_to_other + kernel_reset_to_zero
@@ -96,32 +110,32 @@ static void transform_point_to_point(float to_point[3], const orbo_extrinsics *e
 void orbo_align_depth_to_other(const uint16_t *depth, float depth_scale, const orbo_intrinsics *di,
                                const orbo_intrinsics *oi, const orbo_extrinsics *ex, uint32_t *out) {
     const size_t n_out = (size_t)oi->width * oi->height;
-    for (size_t i = 0; i < n_out; ++i) out[i] = 9999999u;
-    for (int depth_y = 0; depth_y < di->height; ++depth_y)
-        for (int depth_x = 0; depth_x < di->width; ++depth_x) {
-            const uint16_t raw = depth[(size_t)depth_y * di->width + depth_x];
-            float depth_val = raw * depth_scale;
-            int p[2][2] = {{-1, -1}, {-1, -1}};
-            for (int block_index = 0; block_index < 2; ++block_index) {
-                float shift = block_index ? 0.5 : -0.5;
-                if (depth_val != 0) {
-                    float depth_pixel[2] = {depth_x + shift, depth_y + shift}, depth_point[3], other_point[3], other_pixel[2];
-                    deproject_pixel_to_point(depth_point, di, depth_pixel, depth_val);
-                    transform_point_to_point(other_point, ex, depth_point);
-                    project_point_to_pixel(other_pixel, oi, other_point);
-                    p[block_index][0] = f2i_cuda(other_pixel[0] + 0.5f);
-                    p[block_index][1] = f2i_cuda(other_pixel[1] + 0.5f);
-                }
+    const uint32_t UNSET = 9999999u; /* kernel_reset_to_max, cuda-align.cu:254-265 */
+    for (size_t i = 0; i < n_out; ++i) out[i] = UNSET;
+    for (int dy = 0; dy < di->height; ++dy)
+        for (int dx = 0; dx < di->width; ++dx) {
+            const uint16_t raw = depth[(size_t)dy * di->width + dx];
+            const float metres = raw * depth_scale;
+            if (metres == 0) continue; /* no depth: mapped pixel stays (-1,-1) and is rejected below (:139-141) */
+            int corner[2][2];
+            for (int c = 0; c < 2; ++c) { /* c = blockIdx.z of kernel_map_depth_to_other: top-left, bottom-right */
+                const float shift = c ? 0.5 : -0.5;
+                float p[3], q[3], u, v;
+                pixel_to_point_f32(di, dx + shift, dy + shift, metres, p);
+                rigid_transform(ex, p, q);
+                normalized_to_pixel(oi, q[0] / q[2], q[1] / q[2], &u, &v);
+                corner[c][0] = f2i_cuda(u + 0.5f);
+                corner[c][1] = f2i_cuda(v + 0.5f);
             }
-            if (p[0][0] < 0 || p[0][1] < 0 || p[1][0] >= oi->width || p[1][1] >= oi->height) continue;
-            for (int y = p[0][1]; y <= p[1][1]; ++y)
-                for (int x = p[0][0]; x <= p[1][0]; ++x) {
+            if (corner[0][0] < 0 || corner[0][1] < 0 || corner[1][0] >= oi->width || corner[1][1] >= oi->height) continue;
+            for (int y = corner[0][1]; y <= corner[1][1]; ++y)
+                for (int x = corner[0][0]; x <= corner[1][0]; ++x) {
                     uint32_t *o = &out[(size_t)y * oi->width + x];
-                    if (raw < *o) *o = raw;
+                    if (raw < *o) *o = raw; /* atomicMin, :246 */
                 }
         }
-    for (size_t i = 0; i < n_out; ++i)
-        if (out[i] == 9999999u) out[i] = 0;
+    for (size_t i = 0; i < n_out; ++i) /* kernel_reset_to_zero, :267-279 */
+        if (out[i] == UNSET) out[i] = 0;
 }
 
 /* kernel_keypoint_pixel_to_point (cuda-align.cu:282-364) with the (x, y) lookup and input-order compaction */
@@ -135,7 +149,7 @@ int orbo_keypoint_pixel_to_point(const uint32_t *aligned, const orbo_intrinsics 
         if (xi >= 0 && yi >= 0 && xi < oi->width && yi < oi->height) depth = (int)aligned[(size_t)yi * oi->width + xi];
         const float score = kp[idx].response;
         if (depth > 1 && score > 1.0f) {
-            deproject_pixel_to_point_double(points + 3 * (size_t)m, oi, pos, (float)depth);
+            pixel_to_point_f64(oi, pos[0], pos[1], (float)depth, points + 3 * (size_t)m);
             memcpy(desc_out + 32 * (size_t)m, desc + 32 * (size_t)idx, 32);
             kp_out[m] = kp[idx];
             ++m;
@@ -153,9 +167,9 @@ void orbo_reproject_points(const double *points, int n, const double *T, const o
         double e[3] = {p[0], p[1], p[2]};
         if (T)
             for (int r = 0; r < 3; ++r) e[r] = (T[r] * p[0] + T[4 + r] * p[1]) + (T[8 + r] * p[2] + T[12 + r] * 1.0);
-        float x = e[0] / e[2], y = e[1] / e[2];
-        float pt[3] = {x, y, 1.0f}, pixel[2];
-        project_point_to_pixel(pixel, intrin, pt); /* x / 1.0f == x exactly */
+        const float x = e[0] / e[2], y = e[1] / e[2]; /* float64 division, then narrowed (post_processing.cu:16) */
+        float pixel[2];
+        normalized_to_pixel(intrin, x, y, &pixel[0], &pixel[1]);
         pos_out[2 * idx] = pixel[0];
         pos_out[2 * idx + 1] = pixel[1];
     }
