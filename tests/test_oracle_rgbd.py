@@ -128,3 +128,117 @@ def test_rgb_to_grayscale_matches_float64_formula(oracle):
     ref = np.floor((B * 0.07 + G * 0.72 + R * 0.21) + 0.5).astype(np.uint8)
     assert np.array_equal(oracle.rgb_to_grayscale(rgb), ref)
     assert oracle.rgb_to_grayscale(np.full((4, 4, 3), 255, np.uint8)).max() == 255
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Independent restatement in vectorised numpy: every np.float32 / np.float64 ufunc is one IEEE operation, so numpy
+# reproduces "each operation rounded on its own" without sharing a line of code with the C oracle.
+def _np_radial(k, r2, one):
+    return one + k[0] * r2 + k[1] * r2 * r2 + k[4] * r2 * r2 * r2
+
+
+def _np_align(depth, scale, di, oi, ex):
+    f32 = np.float32
+    h, w = depth.shape
+    raw = depth.astype(np.int64)
+    metres = depth.astype(np.int32).astype(f32) * f32(scale)
+    R = [f32(v) for v in ex.rotation]
+    T = [f32(v) for v in ex.translation]
+    kd = [f32(v) for v in di.coeffs]
+    ko = [f32(v) for v in oi.coeffs]
+    xs, ys = np.meshgrid(np.arange(w), np.arange(h))
+    corners = []
+    for shift in (f32(-0.5), f32(0.5)):
+        x = ((xs.astype(f32) + shift) - f32(di.ppx)) / f32(di.fx)
+        y = ((ys.astype(f32) + shift) - f32(di.ppy)) / f32(di.fy)
+        if di.model == 2:
+            r2 = x * x + y * y
+            f = _np_radial(kd, r2, f32(1))
+            ux = x * f + f32(2) * kd[2] * x * y + kd[3] * (r2 + f32(2) * x * x)
+            uy = y * f + f32(2) * kd[3] * x * y + kd[2] * (r2 + f32(2) * y * y)
+            x, y = ux, uy
+        p = (metres * x, metres * y, metres)
+        q = [R[r] * p[0] + R[3 + r] * p[1] + R[6 + r] * p[2] + T[r] for r in range(3)]
+        with np.errstate(divide="ignore", invalid="ignore"):
+            a, b = q[0] / q[2], q[1] / q[2]
+        if oi.model == 1:
+            r2 = a * a + b * b
+            f = _np_radial(ko, r2, f32(1))
+            a = a * f
+            b = b * f
+            da = a + f32(2) * ko[2] * a * b + ko[3] * (r2 + f32(2) * a * a)
+            db = b + f32(2) * ko[3] * a * b + ko[2] * (r2 + f32(2) * b * b)
+            a, b = da, db
+        u = a * f32(oi.fx) + f32(oi.ppx) + f32(0.5)
+        v = b * f32(oi.fy) + f32(oi.ppy) + f32(0.5)
+        with np.errstate(invalid="ignore"):
+            corners.append((np.trunc(np.nan_to_num(u, nan=0.0)).astype(np.int64), np.trunc(np.nan_to_num(v, nan=0.0)).astype(np.int64)))
+    (x0, y0), (x1, y1) = corners
+    ok = (metres != 0) & (x0 >= 0) & (y0 >= 0) & (x1 < oi.width) & (y1 < oi.height)
+    out = np.full(oi.width * oi.height, 2 ** 32 - 1, np.int64)
+    span_x, span_y = int((x1 - x0)[ok].max(initial=-1)), int((y1 - y0)[ok].max(initial=-1))
+    for oy in range(span_y + 1):
+        for ox in range(span_x + 1):
+            m = ok & (x0 + ox <= x1) & (y0 + oy <= y1)
+            np.minimum.at(out, ((y0 + oy) * oi.width + (x0 + ox))[m], raw[m])
+    out[out == 2 ** 32 - 1] = 0
+    return out.reshape(oi.height, oi.width).astype(np.uint32)
+
+
+@pytest.mark.parametrize("dist_depth,dist_other", [(False, False), (False, True), (True, True)])
+def test_align_matches_numpy_float32(oracle, dist_depth, dist_other):
+    rng = np.random.default_rng(21)
+    w, h = 160, 120
+    yy, xx = np.mgrid[0:h, 0:w]
+    depth = (900 + 400 * np.sin(xx / 23.0) * np.cos(yy / 17.0) + rng.integers(-9, 10, (h, w))).astype(np.uint16)
+    depth[rng.random((h, w)) < 0.1] = 0
+    c = (0.11, -0.23, 0.0009, -0.0006, 0.07)
+    di = oracle.make_intrinsics(w, h, 81.3, 58.9, 95.7, 96.1, 2 if dist_depth else 4, c if dist_depth else (0,) * 5)
+    oi = oracle.make_intrinsics(w, h, 78.2, 61.4, 131.5, 132.25, 1 if dist_other else 0, c if dist_other else (0,) * 5)
+    a, b = 0.01, -0.007
+    ex = oracle.make_extrinsics((1, a * b, -b, 0, 1, a, b, -a, 1), (0.0148, -0.0003, 0.0011))
+    got = oracle.align_depth_to_other(depth, 0.001, di, oi, ex)
+    ref = _np_align(depth, 0.001, di, oi, ex)
+    assert (ref > 0).mean() > 0.3
+    assert np.array_equal(got, ref), f"{(got != ref).sum()} pixels differ"
+
+
+def test_points_and_reprojection_match_numpy(oracle):
+    rng = np.random.default_rng(8)
+    w, h, n = 320, 240, 400
+    c = (0.09, -0.2, 0.0011, -0.0004, 0.05)
+    intr = oracle.make_intrinsics(w, h, 158.3, 121.7, 211.5, 212.75, 2, c)
+    aligned = rng.integers(0, 3000, (h, w)).astype(np.uint32)
+    kp = np.zeros(n, oracle.KEYPOINT_DTYPE)
+    kp["x"] = rng.uniform(0, w - 1, n).astype(np.float32); kp["y"] = rng.uniform(0, h - 1, n).astype(np.float32)
+    kp["response"] = rng.integers(0, 60, n)
+    desc = rng.integers(0, 256, (n, 32)).astype(np.uint8)
+    k2, d2, pts = oracle.keypoint_pixel_to_point(aligned, intr, kp, desc)
+    xi = (kp["x"].astype(np.float64) + 0.5).astype(np.int64); yi = (kp["y"].astype(np.float64) + 0.5).astype(np.int64)
+    dep = aligned[yi, xi].astype(np.int64)
+    keep = (dep > 1) & (kp["response"] > 1.0)
+    assert np.array_equal(k2["x"], kp["x"][keep]) and np.array_equal(d2, desc[keep])
+    f32, f64 = np.float32, np.float64
+    kc = [f64(f32(v)) for v in c]
+    x = ((kp["x"][keep] - f32(intr.ppx)) / f32(intr.fx)).astype(f64)
+    y = ((kp["y"][keep] - f32(intr.ppy)) / f32(intr.fy)).astype(f64)
+    r2 = x * x + y * y
+    f = _np_radial(kc, r2, f64(1))
+    ux = x * f + 2 * kc[2] * x * y + kc[3] * (r2 + 2 * x * x)
+    uy = y * f + 2 * kc[3] * x * y + kc[2] * (r2 + 2 * y * y)
+    z = dep[keep].astype(f32).astype(f64)
+    assert np.array_equal(pts, np.stack([z * ux, z * uy, z], 1))
+    # reprojection through a forward-distorted camera with a rigid transform
+    cam = oracle.make_intrinsics(w, h, 158.3, 121.7, 211.5, 212.75, 1, c)
+    T = np.eye(4); T[:3, :3] = [[1, -0.01, 0.02], [0.01, 1, -0.015], [-0.02, 0.015, 1]]; T[:3, 3] = [4.0, -2.5, 7.0]
+    pos = oracle.reproject_points(pts, T, cam)
+    e = [(T[r, 0] * pts[:, 0] + T[r, 1] * pts[:, 1]) + (T[r, 2] * pts[:, 2] + T[r, 3] * 1.0) for r in range(3)]
+    a = (e[0] / e[2]).astype(f32); b = (e[1] / e[2]).astype(f32)
+    k32 = [f32(v) for v in c]
+    r2 = a * a + b * b
+    f = _np_radial(k32, r2, f32(1))
+    a = a * f; b = b * f
+    da = a + f32(2) * k32[2] * a * b + k32[3] * (r2 + f32(2) * a * a)
+    db = b + f32(2) * k32[3] * a * b + k32[2] * (r2 + f32(2) * b * b)
+    ref = np.stack([da * f32(cam.fx) + f32(cam.ppx), db * f32(cam.fy) + f32(cam.ppy)], 1)
+    assert np.array_equal(pos.view(np.uint32), ref.astype(f32).view(np.uint32))
