@@ -65,21 +65,30 @@ __device__ __forceinline__ uint32_t block_excl_scan(uint32_t v, uint32_t *warp_t
     return base + inc - v;
 }
 
-__device__ __forceinline__ void radix_pass(const uint32_t *__restrict__ kin, const uint32_t *__restrict__ iin,
-                                           uint32_t *__restrict__ kout, uint32_t *__restrict__ iout, int n,
-                                           int shift, OctStatic &S) {
+// One LSD pass.  Every warp owns a contiguous slice of the keys (stability).  Loads are issued OCT_RB at a time before
+// the dependent match/atomic chain consumes them.  OCT_RB = 4 cuts the L2 round trips a lone CTA waits for (small
+// batches: 217 -> 158 us for a 4-frame call); with every SM full of CTAs the other CTAs hide them anyway and the
+// extra registers only cost occupancy, so large batches use OCT_RB = 1.
+template <int OCT_RB>
+__device__ __forceinline__ void radix_pass(const uint2 *__restrict__ kvin, uint2 *__restrict__ kvout, int n, int shift,
+                                           OctStatic &S) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const unsigned lt = (1u << lane) - 1u;
     for (int i = tid; i < OCT_WARPS * 256; i += OCT_THREADS) (&S.whist[0][0])[i] = 0;
     __syncthreads();
     const int seglen = ((n + OCT_THREADS - 1) / OCT_THREADS) * 32;  // per-warp contiguous slice
     const int s0 = min(n, warp * seglen), s1 = min(n, s0 + seglen);
-    for (int base = s0; base < s1; base += 32) {
-        const int i = base + lane;
-        const bool valid = i < s1;
-        const unsigned d = valid ? ((kin[i] >> shift) & 255u) : (0x1000u + lane);
-        const unsigned peers = __match_any_sync(FULL, d);
-        if (valid && (peers & lt) == 0) atomicAdd(&S.whist[warp][d], (uint32_t)__popc(peers));  // no return: RED
+    // digit histogram: warp-private counters, plain RED.ADD per lane (order is irrelevant for counts)
+    for (int base = s0; base < s1; base += 32 * OCT_RB) {
+        uint32_t kk[OCT_RB];
+#pragma unroll
+        for (int j = 0; j < OCT_RB; ++j) {
+            const int i = base + 32 * j + lane;
+            kk[j] = i < s1 ? kvin[i].x : 0u;
+        }
+#pragma unroll
+        for (int j = 0; j < OCT_RB; ++j)
+            if (base + 32 * j + lane < s1) atomicAdd(&S.whist[warp][(kk[j] >> shift) & 255u], 1u);
     }
     __syncthreads();
     uint32_t tot = 0;
@@ -95,19 +104,28 @@ __device__ __forceinline__ void radix_pass(const uint32_t *__restrict__ kin, con
     const uint32_t ex = block_excl_scan(tid < 256 ? tot : 0u, S.warp_tot, &dummy);
     if (tid < 256) S.digit_base[tid] = ex;
     __syncthreads();
-    for (int base = s0; base < s1; base += 32) {
-        const int i = base + lane;
-        const bool valid = i < s1;
-        uint32_t k = 0, id = 0;
-        if (valid) { k = kin[i]; id = iin[i]; }
-        const unsigned d = valid ? ((k >> shift) & 255u) : (0x1000u + lane);
-        const unsigned peers = __match_any_sync(FULL, d);
-        // the group leader reserves the group's slots in the warp-private running offset and broadcasts the base
-        uint32_t old = 0;
-        if (valid && (peers & lt) == 0) old = atomicAdd(&S.whist[warp][d], (uint32_t)__popc(peers));
-        old = __shfl_sync(FULL, old, __ffs(peers) - 1);
-        const uint32_t pos = valid ? S.digit_base[d] + old + __popc(peers & lt) : 0u;
-        if (valid) { kout[pos] = k; iout[pos] = id; }
+    // stable scatter: rank inside the warp step by MATCH.ANY, running offset per (warp, digit) in shared memory
+    for (int base = s0; base < s1; base += 32 * OCT_RB) {
+        uint2 kv[OCT_RB];
+#pragma unroll
+        for (int j = 0; j < OCT_RB; ++j) {
+            const int i = base + 32 * j + lane;
+            kv[j] = i < s1 ? kvin[i] : make_uint2(0u, 0u);
+        }
+#pragma unroll
+        for (int j = 0; j < OCT_RB; ++j) {
+            if (base + 32 * j >= s1) break;  // warp-uniform
+            const bool valid = base + 32 * j + lane < s1;
+            const unsigned d = valid ? ((kv[j].x >> shift) & 255u) : (0x1000u + lane);
+            const unsigned peers = __match_any_sync(FULL, d);
+            // every lane of the group reads the digit's running offset, the group leader advances it: one writer
+            // per digit and step, steps are warp-synchronous, so no atomic and no broadcast are needed
+            const uint32_t old = valid ? S.whist[warp][d] : 0u;
+            __syncwarp();
+            if (valid && (peers & lt) == 0) S.whist[warp][d] = old + (uint32_t)__popc(peers);
+            __syncwarp();
+            if (valid) kvout[S.digit_base[d] + old + __popc(peers & lt)] = kv[j];  // one 8-byte store per key
+        }
     }
     __syncthreads();
 }
@@ -162,7 +180,8 @@ __device__ __forceinline__ void bitonic_desc(unsigned long long *key, uint32_t *
     }
 }
 
-__global__ void __launch_bounds__(OCT_THREADS, 4)
+template <int OCT_RB, int MIN_CTAS>
+__global__ void __launch_bounds__(OCT_THREADS, MIN_CTAS)
 k_octree(const LevelDev *__restrict__ levels, int n_levels, const int *__restrict__ cand_count,
          int *__restrict__ sel_count, int level_base, int frame_base, int quota_override, int pcap, int pcap2) {
     __shared__ OctStatic S;
@@ -191,26 +210,33 @@ k_octree(const LevelDev *__restrict__ levels, int n_levels, const int *__restric
 
     const size_t fo = (size_t)frame * L.cand_cap;
     const uint32_t *cand = L.cand + fo;
-    uint32_t *ka = L.key_a + fo, *kb = L.key_b + fo, *ia = L.idx_a + fo, *ib = L.idx_b + fo;
+    uint2 *kva = L.kv_a + fo, *kvb = L.kv_b + fo;  // (path key, candidate index) pairs, radix ping-pong
     uint8_t *sd = L.sd + fo;
     const int D = L.depth;
 
     // ---- 1. path keys
-    for (int i = tid; i < n; i += OCT_THREADS) {
-        const uint32_t c = cand[i];
-        ka[i] = __ldg(&L.xkey[c & 0xfffu]) | __ldg(&L.ykey[(c >> 12) & 0xfffu]);
-        ia[i] = (uint32_t)i;
+    for (int base = tid; base < n; base += OCT_RB * OCT_THREADS) {
+        uint32_t c[OCT_RB], kx[OCT_RB], ky[OCT_RB];
+#pragma unroll
+        for (int j = 0; j < OCT_RB; ++j) c[j] = base + j * OCT_THREADS < n ? cand[base + j * OCT_THREADS] : 0u;
+#pragma unroll
+        for (int j = 0; j < OCT_RB; ++j) { kx[j] = __ldg(&L.xkey[c[j] & 0xfffu]); ky[j] = __ldg(&L.ykey[(c[j] >> 12) & 0xfffu]); }
+#pragma unroll
+        for (int j = 0; j < OCT_RB; ++j) {
+            const int i = base + j * OCT_THREADS;
+            if (i < n) kva[i] = make_uint2(kx[j] | ky[j], (uint32_t)i);
+        }
     }
     __syncthreads();
     // ---- 2. LSD radix sort by path
     for (int shift = 0; shift < L.key_bits; shift += 8) {
-        radix_pass(ka, ia, kb, ib, n, shift, S);
-        uint32_t *t = ka; ka = kb; kb = t;
-        t = ia; ia = ib; ib = t;
+        radix_pass<OCT_RB>(kva, kvb, n, shift, S);
+        uint2 *t = kva; kva = kvb; kvb = t;
     }
+    const uint2 *kv = kva;  // sorted
     // free ping-pong buffers become scratch: two generations of u16 segment ids, and the head flags
-    uint16_t *seg_a = reinterpret_cast<uint16_t *>(kb), *seg_b = seg_a + L.cand_cap;
-    uint8_t *head = reinterpret_cast<uint8_t *>(ib);
+    uint16_t *seg_a = reinterpret_cast<uint16_t *>(kvb), *seg_b = seg_a + L.cand_cap;
+    uint8_t *head = reinterpret_cast<uint8_t *>(seg_b + L.cand_cap);
 
     // ---- 3. split depths + histograms
     if (tid < 40) { S.hist_sd[tid] = 0; S.hist_g[tid] = 0; }
@@ -219,7 +245,7 @@ k_octree(const LevelDev *__restrict__ levels, int n_levels, const int *__restric
         const int i = base + tid;
         unsigned s = 0x100u + lane;
         if (i < n - 1) {
-            const int hb = 31 - __clz(ka[i] ^ ka[i + 1]);
+            const int hb = 31 - __clz(kv[i].x ^ kv[i + 1].x);
             s = hb >= 2 * D ? 0u : (unsigned)(D - (hb >> 1));
             sd[i] = (uint8_t)s;
         }
@@ -281,7 +307,7 @@ k_octree(const LevelDev *__restrict__ levels, int n_levels, const int *__restric
             const uint32_t root_mask = (k0 & 1) ? 0u : (((1u << (L.key_bits - 2 * D)) - 1u) << (2 * k0));
             for (int sidx = tid; sidx < nseg; sidx += OCT_THREADS) {
                 const uint32_t st = nst[sidx], cnt = nst[sidx + 1] - st;
-                seq[sidx] = cnt > 1 ? (((ka[st] >> (2 * (D - k0))) ^ digit_mask ^ root_mask) & 0x7fffffffu) : 0xffffffffu;
+                seq[sidx] = cnt > 1 ? (((kv[st].x >> (2 * (D - k0))) ^ digit_mask ^ root_mask) & 0x7fffffffu) : 0xffffffffu;
             }
         }
         int d = k0;
@@ -352,7 +378,7 @@ k_octree(const LevelDev *__restrict__ levels, int n_levels, const int *__restric
             for (int s2 = tid; s2 < nseg2; s2 += OCT_THREADS) {
                 const uint32_t st = nst2[s2], cnt = nst2[s2 + 1] - st;
                 const int pr = rank_of[seg[st]];
-                seq2[s2] = (pr >= 0 && cnt > 1) ? ((uint32_t)pr * 4u + ((ka[st] >> (2 * (D - d - 1))) & 3u)) : 0xffffffffu;
+                seq2[s2] = (pr >= 0 && cnt > 1) ? ((uint32_t)pr * 4u + ((kv[st].x >> (2 * (D - d - 1))) & 3u)) : 0xffffffffu;
             }
             if (tid == 0) S.ctl[C_SIZE] = nseg2;
             __syncthreads();
@@ -376,16 +402,26 @@ k_octree(const LevelDev *__restrict__ levels, int n_levels, const int *__restric
     const int nfinal = min((int)carry, L.sel_cap);
     for (int sidx = tid; sidx < nfinal; sidx += OCT_THREADS) best[sidx] = 0ull;
     __syncthreads();
-    for (int i = tid; i < n; i += OCT_THREADS) {
-        const uint32_t sidx = seg_a[i];
-        if (sidx < (uint32_t)nfinal) {
-            const uint32_t id = ia[i], c = cand[id];
-            const uint32_t xo = __ldg(&L.xord[c & 0xfffu]), yo = __ldg(&L.yord[(c >> 12) & 0xfffu]);
-            const uint32_t ord = ((yo >> 6) << 19) | ((xo >> 6) << 12) | ((yo & 63u) << 6) | (xo & 63u);
-            const unsigned long long v = ((unsigned long long)(c >> 24) << 48) |
-                                         ((unsigned long long)(0x3ffffffu - ord) << 22) | id;
-            atomicMax(&best[sidx], v);
+    for (int base = tid; base < n; base += OCT_RB * OCT_THREADS) {
+        uint32_t sidx[OCT_RB], id[OCT_RB], c[OCT_RB], xo[OCT_RB], yo[OCT_RB];
+#pragma unroll
+        for (int j = 0; j < OCT_RB; ++j) {
+            const int i = base + j * OCT_THREADS;
+            sidx[j] = i < n ? (uint32_t)seg_a[i] : 0xffffffffu;
+            id[j] = i < n ? kv[i].y : 0u;
         }
+#pragma unroll
+        for (int j = 0; j < OCT_RB; ++j) c[j] = sidx[j] < (uint32_t)nfinal ? cand[id[j]] : 0u;
+#pragma unroll
+        for (int j = 0; j < OCT_RB; ++j) { xo[j] = __ldg(&L.xord[c[j] & 0xfffu]); yo[j] = __ldg(&L.yord[(c[j] >> 12) & 0xfffu]); }
+#pragma unroll
+        for (int j = 0; j < OCT_RB; ++j)
+            if (sidx[j] < (uint32_t)nfinal) {
+                const uint32_t ord = ((yo[j] >> 6) << 19) | ((xo[j] >> 6) << 12) | ((yo[j] & 63u) << 6) | (xo[j] & 63u);
+                const unsigned long long v = ((unsigned long long)(c[j] >> 24) << 48) |
+                                             ((unsigned long long)(0x3ffffffu - ord) << 22) | id[j];
+                atomicMax(&best[sidx[j]], v);
+            }
     }
     __syncthreads();
     uint32_t *sel = L.sel + (size_t)frame * L.sel_cap;
@@ -397,21 +433,33 @@ size_t octree_dyn_smem(int sel_cap_max, int pcap, int pcap2) {
     return (size_t)sel_cap_max * 8 + (size_t)pcap2 * 12 + (size_t)(pcap + 1) * 4 * 6 + 16;
 }
 
+template <int OCT_RB, int MIN_CTAS>
+static cudaError_t launch_octree_t(const LevelDev *d_levels, int n_levels, const int *d_cand_count, int *d_sel_count,
+                                   int level_base, int n_launch_levels, int frame_base, int n_frames, int quota_override,
+                                   size_t smem, int pcap, int pcap2, cudaStream_t st) {
+    static size_t configured = 0;
+    if (smem > 32 * 1024 && smem > configured) {
+        cudaError_t e = cudaFuncSetAttribute(k_octree<OCT_RB, MIN_CTAS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        configured = smem;
+    }
+    dim3 grid(n_launch_levels, n_frames);
+    k_octree<OCT_RB, MIN_CTAS><<<grid, OCT_THREADS, smem, st>>>(d_levels, n_levels, d_cand_count, d_sel_count, level_base,
+                                                                frame_base, quota_override, pcap, pcap2);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_octree(const LevelDev *d_levels, int n_levels, const int *d_cand_count, int *d_sel_count,
                           int level_base, int n_launch_levels, int frame_base, int n_frames, int quota_override,
                           int sel_cap_max, int pcap, int pcap2, cudaStream_t st) {
     size_t smem = octree_dyn_smem(sel_cap_max, pcap, pcap2);
     if (getenv("ORBB_OCT_PAD")) smem = std::max(smem, (size_t)atoi(getenv("ORBB_OCT_PAD")));
-    static size_t configured = 0;
-    if (smem > 32 * 1024 && smem > configured) {
-        cudaError_t e = cudaFuncSetAttribute(k_octree, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        configured = smem;
-    }
-    dim3 grid(n_launch_levels, n_frames);
-    k_octree<<<grid, OCT_THREADS, smem, st>>>(d_levels, n_levels, d_cand_count, d_sel_count, level_base, frame_base,
-                                              quota_override, pcap, pcap2);
-    return cudaGetLastError();
+    // fewer CTAs than the GPU can hold at once: every CTA's own latency is the kernel's duration
+    if ((long long)n_launch_levels * n_frames <= 148 * 3)
+        return launch_octree_t<4, 3>(d_levels, n_levels, d_cand_count, d_sel_count, level_base, n_launch_levels, frame_base,
+                                     n_frames, quota_override, smem, pcap, pcap2, st);
+    return launch_octree_t<1, 4>(d_levels, n_levels, d_cand_count, d_sel_count, level_base, n_launch_levels, frame_base,
+                                 n_frames, quota_override, smem, pcap, pcap2, st);
 }
 
 }  // namespace orbb

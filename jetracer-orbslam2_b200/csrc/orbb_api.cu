@@ -402,8 +402,8 @@ extern "C" int orbb_create(orbb_handle **out, const orbb_params *params, int wid
         L.xkey = dxk; L.ykey = dyk; L.xord = dxo; L.yord = dyo;
         L.sel_cap = std::max(L.nfeat, 4 * L.n_ini) + 8;
         const size_t cc = (size_t)L.cand_cap * B;
-        CKC(dalloc(h, &L.cand, cc)); CKC(dalloc(h, &L.key_a, cc)); CKC(dalloc(h, &L.key_b, cc));
-        CKC(dalloc(h, &L.idx_a, cc)); CKC(dalloc(h, &L.idx_b, cc)); CKC(dalloc(h, &L.sd, cc));
+        CKC(dalloc(h, &L.cand, cc)); CKC(dalloc(h, &L.kv_a, cc)); CKC(dalloc(h, &L.kv_b, cc));
+        CKC(dalloc(h, &L.sd, cc));
         CKC(dalloc(h, &L.sel, (size_t)L.sel_cap * B));
         slot_base[l] = (int)slot_level.size();
         for (int s = 0; s < L.sel_cap; ++s) slot_level.push_back(l);

@@ -46,7 +46,7 @@ struct LevelDev {
     const uint16_t *xord, *yord; // [w-32], [h-32]: (cell index << 6 | offset in cell)
     int cand_cap, sel_cap;
     uint32_t *cand;              // B x cand_cap
-    uint32_t *key_a, *key_b, *idx_a, *idx_b;  // B x cand_cap each (radix ping-pong)
+    uint2 *kv_a, *kv_b;          // B x cand_cap each: (path key, candidate index) pairs, radix ping-pong
     uint8_t *sd;                 // B x cand_cap: split depth of adjacent sorted keys
     uint32_t *sel;               // B x sel_cap packed selected keys
     float scale, patch_size;     // mvScaleFactor[l], (float)(int)(31*scale)
