@@ -130,6 +130,43 @@ __device__ __forceinline__ void radix_pass(const uint2 *__restrict__ kvin, uint2
     __syncthreads();
 }
 
+// Node numbering from the head flags (1 = this key starts a node).  Every warp owns a contiguous slice of the keys;
+// inside a slice the rank of a key is a ballot prefix, across slices one scan of the 16 slice totals.  emit(i, node,
+// is_head) is called once per key with the 0-based node index.  Returns the number of nodes.  Two block barriers per
+// call (the chunked block scan it replaces needed two per 512 keys).
+template <typename F>
+__device__ __forceinline__ uint32_t head_scan(const uint8_t *__restrict__ head, int n, OctStatic &S, F emit) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const unsigned lt = (1u << lane) - 1u;
+    const int seglen = ((n + OCT_THREADS - 1) / OCT_THREADS) * 32;
+    const int s0 = min(n, warp * seglen), s1 = min(n, s0 + seglen);
+    uint32_t cnt = 0;
+    for (int base = s0; base < s1; base += 32) {
+        const int i = base + lane;
+        cnt += __popc(__ballot_sync(FULL, i < s1 && head[i] != 0));
+    }
+    __syncthreads();  // protect warp_tot reuse
+    if (lane == 0) S.warp_tot[warp] = cnt;
+    __syncthreads();
+    const uint32_t wt = lane < OCT_WARPS ? S.warp_tot[lane] : 0u;
+    uint32_t winc = wt;
+#pragma unroll
+    for (int o = 1; o < OCT_WARPS; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(FULL, winc, o);
+        if (lane >= o) winc += t;
+    }
+    const uint32_t total = __shfl_sync(FULL, winc, OCT_WARPS - 1);
+    uint32_t run = __shfl_sync(FULL, winc - wt, warp);  // heads before this warp's slice
+    for (int base = s0; base < s1; base += 32) {
+        const int i = base + lane;
+        const bool h = i < s1 && head[i] != 0;
+        const unsigned bal = __ballot_sync(FULL, h);
+        if (i < s1) emit(i, run + __popc(bal & lt) + (h ? 1u : 0u) - 1u, h);
+        run += __popc(bal);
+    }
+    return total;
+}
+
 // bitonic sort, DESCENDING by key, m = power of two.  m <= OCT_THREADS: one element per thread in registers,
 // strides < 32 with warp shuffles and only the wide strides through shared memory; larger m: all in smem.
 __device__ __forceinline__ void bitonic_desc(unsigned long long *key, uint32_t *val, int m) {
@@ -210,7 +247,7 @@ k_octree(const LevelDev *__restrict__ levels, int n_levels, const int *__restric
 
     const size_t fo = (size_t)frame * L.cand_cap;
     const uint32_t *cand = L.cand + fo;
-    uint2 *kva = L.kv_a + fo, *kvb = L.kv_b + fo;  // (path key, candidate index) pairs, radix ping-pong
+    uint2 *kva = L.kv_a + fo, *kvb = L.kv_b + fo;  // (path key, packed candidate) pairs, radix ping-pong
     uint8_t *sd = L.sd + fo;
     const int D = L.depth;
 
@@ -224,7 +261,7 @@ k_octree(const LevelDev *__restrict__ levels, int n_levels, const int *__restric
 #pragma unroll
         for (int j = 0; j < OCT_RB; ++j) {
             const int i = base + j * OCT_THREADS;
-            if (i < n) kva[i] = make_uint2(kx[j] | ky[j], (uint32_t)i);
+            if (i < n) kva[i] = make_uint2(kx[j] | ky[j], c[j]);  // the candidate travels with its key: no gathers later
         }
     }
     __syncthreads();
@@ -243,25 +280,27 @@ k_octree(const LevelDev *__restrict__ levels, int n_levels, const int *__restric
     __syncthreads();
     for (int base = 0; base < n; base += OCT_THREADS) {
         const int i = base + tid;
-        unsigned s = 0x100u + lane;
-        if (i < n - 1) {
-            const int hb = 31 - __clz(kv[i].x ^ kv[i + 1].x);
-            s = hb >= 2 * D ? 0u : (unsigned)(D - (hb >> 1));
-            sd[i] = (uint8_t)s;
-        }
-        const unsigned peers = __match_any_sync(FULL, s);
-        if (i < n - 1 && (peers & ((1u << lane) - 1u)) == 0) atomicAdd(&S.hist_sd[s], __popc(peers));
-    }
-    __syncthreads();
-    for (int base = 0; base < n; base += OCT_THREADS) {
-        const int i = base + tid;
-        unsigned g = 0x100u + lane;
+        unsigned s = 0x100u + lane, g = 0x100u + lane;
         if (i < n) {
-            const unsigned l = i > 0 ? sd[i - 1] : 0u, r = i < n - 1 ? sd[i] : 0u;
+            const uint32_t kc = kv[i].x;
+            unsigned l = 0, r = 0;
+            if (i > 0) {
+                const int hb = 31 - __clz(kv[i - 1].x ^ kc);
+                l = hb >= 2 * D ? 0u : (unsigned)(D - (hb >> 1));
+            }
+            if (i < n - 1) {
+                const int hb = 31 - __clz(kc ^ kv[i + 1].x);
+                r = hb >= 2 * D ? 0u : (unsigned)(D - (hb >> 1));
+                sd[i] = (uint8_t)r;
+                s = r;
+            }
             g = max(l, r);
         }
-        const unsigned peers = __match_any_sync(FULL, g);
-        if (i < n && (peers & ((1u << lane) - 1u)) == 0) atomicAdd(&S.hist_g[g], __popc(peers));
+        const unsigned lt = (1u << lane) - 1u;
+        const unsigned ps = __match_any_sync(FULL, s);
+        if (i < n - 1 && (ps & lt) == 0) atomicAdd(&S.hist_sd[s], __popc(ps));
+        const unsigned pg = __match_any_sync(FULL, g);
+        if (i < n && (pg & lt) == 0) atomicAdd(&S.hist_g[g], __popc(pg));
     }
     __syncthreads();
     // ---- 4. replay the breadth-first passes on the histograms
@@ -291,15 +330,10 @@ k_octree(const LevelDev *__restrict__ levels, int n_levels, const int *__restric
         uint32_t *nst = nst_a, *nst2 = nst_b, *seq = seq_a, *seq2 = seq_b;
         uint16_t *seg = seg_a, *seg2 = seg_b;
         {
-            uint32_t carry = 0;
-            for (int base = 0; base < n; base += OCT_THREADS) {
-                const int i = base + tid;
-                const uint32_t h = i < n ? head[i] : 0u;
-                uint32_t tot;
-                const uint32_t inc = block_excl_scan(h, S.warp_tot, &tot) + carry + h;
-                if (i < n) { seg[i] = (uint16_t)(inc - 1); if (h) nst[inc - 1] = (uint32_t)i; }
-                carry += tot;
-            }
+            head_scan(head, n, S, [&](int i, uint32_t node, bool h) {
+                seg[i] = (uint16_t)node;
+                if (h) nst[node] = (uint32_t)i;
+            });
             if (tid == 0) nst[nseg] = (uint32_t)n;
             __syncthreads();
             // closed-form creation sequence of the breadth-first pass that made the depth-k0 nodes
@@ -364,15 +398,10 @@ k_octree(const LevelDev *__restrict__ levels, int n_levels, const int *__restric
             // next round: renumber the nodes; the new expandable ones are the children (> 1 key) of split nodes,
             // created in processing order of their parents, n1..n4 inside a parent
             const int nseg2 = size + (int)total;
-            uint32_t carry = 0;
-            for (int base = 0; base < n; base += OCT_THREADS) {
-                const int i = base + tid;
-                const uint32_t h = i < n ? head[i] : 0u;
-                uint32_t tot;
-                const uint32_t inc = block_excl_scan(h, S.warp_tot, &tot) + carry + h;
-                if (i < n) { seg2[i] = (uint16_t)(inc - 1); if (h) nst2[inc - 1] = (uint32_t)i; }
-                carry += tot;
-            }
+            head_scan(head, n, S, [&](int i, uint32_t node, bool h) {
+                seg2[i] = (uint16_t)node;
+                if (h) nst2[node] = (uint32_t)i;
+            });
             if (tid == 0) nst2[nseg2] = (uint32_t)n;
             __syncthreads();
             for (int s2 = tid; s2 < nseg2; s2 += OCT_THREADS) {
@@ -390,42 +419,37 @@ k_octree(const LevelDev *__restrict__ levels, int n_levels, const int *__restric
     }
 
     // ---- 6. final nodes = head-delimited segments; keep the best key of each
-    uint32_t carry = 0;
-    for (int base = 0; base < n; base += OCT_THREADS) {
-        const int i = base + tid;
-        const uint32_t h = i < n ? head[i] : 0u;
-        uint32_t tot;
-        const uint32_t inc = block_excl_scan(h, S.warp_tot, &tot) + carry + h;
-        if (i < n) seg_a[i] = (uint16_t)min(inc - 1, 0xffffu);
-        carry += tot;
-    }
-    const int nfinal = min((int)carry, L.sel_cap);
+    const uint32_t n_nodes = head_scan(head, n, S, [&](int i, uint32_t node, bool) { seg_a[i] = (uint16_t)min(node, 0xffffu); });
+    const int nfinal = min((int)n_nodes, L.sel_cap);
     for (int sidx = tid; sidx < nfinal; sidx += OCT_THREADS) best[sidx] = 0ull;
     __syncthreads();
     for (int base = tid; base < n; base += OCT_RB * OCT_THREADS) {
-        uint32_t sidx[OCT_RB], id[OCT_RB], c[OCT_RB], xo[OCT_RB], yo[OCT_RB];
+        uint32_t sidx[OCT_RB], c[OCT_RB], xo[OCT_RB], yo[OCT_RB];
 #pragma unroll
         for (int j = 0; j < OCT_RB; ++j) {
             const int i = base + j * OCT_THREADS;
             sidx[j] = i < n ? (uint32_t)seg_a[i] : 0xffffffffu;
-            id[j] = i < n ? kv[i].y : 0u;
+            c[j] = i < n ? kv[i].y : 0u;
         }
-#pragma unroll
-        for (int j = 0; j < OCT_RB; ++j) c[j] = sidx[j] < (uint32_t)nfinal ? cand[id[j]] : 0u;
 #pragma unroll
         for (int j = 0; j < OCT_RB; ++j) { xo[j] = __ldg(&L.xord[c[j] & 0xfffu]); yo[j] = __ldg(&L.yord[(c[j] >> 12) & 0xfffu]); }
 #pragma unroll
         for (int j = 0; j < OCT_RB; ++j)
             if (sidx[j] < (uint32_t)nfinal) {
+                // (response, earliest upstream candidate order) decides; ord is unique per pixel, so the low 24 bits
+                // (x | y << 12 of the winner) never take part in the comparison
                 const uint32_t ord = ((yo[j] >> 6) << 19) | ((xo[j] >> 6) << 12) | ((yo[j] & 63u) << 6) | (xo[j] & 63u);
-                const unsigned long long v = ((unsigned long long)(c[j] >> 24) << 48) |
-                                             ((unsigned long long)(0x3ffffffu - ord) << 22) | id[j];
+                const unsigned long long v = ((unsigned long long)(c[j] >> 24) << 56) |
+                                             ((unsigned long long)(0x3ffffffu - ord) << 24) | (c[j] & 0xffffffu);
                 atomicMax(&best[sidx[j]], v);
             }
     }
     __syncthreads();
     uint32_t *sel = L.sel + (size_t)frame * L.sel_cap;
-    for (int sidx = tid; sidx < nfinal; sidx += OCT_THREADS) sel[sidx] = cand[(uint32_t)(best[sidx] & 0x3fffffull)];
+    for (int sidx = tid; sidx < nfinal; sidx += OCT_THREADS) {
+        const unsigned long long b = best[sidx];
+        sel[sidx] = (uint32_t)(b & 0xffffffull) | ((uint32_t)(b >> 56) << 24);
+    }
     if (tid == 0) *out_count = nfinal;
 }
 
