@@ -220,7 +220,8 @@ __device__ __forceinline__ void bitonic_desc(unsigned long long *key, uint32_t *
 template <int OCT_RB, int MIN_CTAS>
 __global__ void __launch_bounds__(OCT_THREADS, MIN_CTAS)
 k_octree(const LevelDev *__restrict__ levels, int n_levels, const int *__restrict__ cand_count,
-         int *__restrict__ sel_count, int level_base, int frame_base, int quota_override, int pcap, int pcap2) {
+         int *__restrict__ sel_count, int level_base, int frame_base, int quota_override, int pcap, int pcap2,
+         int sort_off, int sort_bytes) {
     __shared__ OctStatic S;
     extern __shared__ __align__(16) uint8_t dyn[];
     const int tid = threadIdx.x, lane = tid & 31;
@@ -247,8 +248,14 @@ k_octree(const LevelDev *__restrict__ levels, int n_levels, const int *__restric
 
     const size_t fo = (size_t)frame * L.cand_cap;
     const uint32_t *cand = L.cand + fo;
-    uint2 *kva = L.kv_a + fo, *kvb = L.kv_b + fo;  // (path key, packed candidate) pairs, radix ping-pong
-    uint8_t *sd = L.sd + fo;
+    // (path key, packed candidate) pairs, radix ping-pong.  When the launch could afford the shared memory (small
+    // grids: one or two CTAs per SM) and this level's candidates fit, every per-key array lives in shared memory:
+    // the scattered 8-byte stores of the sort and the strided passes over the keys then never leave the SM.
+    const int n_pad = (n + 15) & ~15;
+    const bool in_smem = (size_t)n_pad * 16 <= (size_t)sort_bytes;
+    uint2 *kva = in_smem ? reinterpret_cast<uint2 *>(dyn + sort_off) : L.kv_a + fo;
+    uint2 *kvb = in_smem ? kva + n_pad : L.kv_b + fo;
+    const int key_stride = in_smem ? n_pad : L.cand_cap;  // elements between the scratch arrays carved from kvb
     const int D = L.depth;
 
     // ---- 1. path keys
@@ -272,8 +279,9 @@ k_octree(const LevelDev *__restrict__ levels, int n_levels, const int *__restric
     }
     const uint2 *kv = kva;  // sorted
     // free ping-pong buffers become scratch: two generations of u16 segment ids, and the head flags
-    uint16_t *seg_a = reinterpret_cast<uint16_t *>(kvb), *seg_b = seg_a + L.cand_cap;
-    uint8_t *head = reinterpret_cast<uint8_t *>(seg_b + L.cand_cap);
+    uint16_t *seg_a = reinterpret_cast<uint16_t *>(kvb), *seg_b = seg_a + key_stride;
+    uint8_t *head = reinterpret_cast<uint8_t *>(seg_b + key_stride);
+    uint8_t *sd = in_smem ? head + key_stride : L.sd + fo;  // 2 + 2 + 1 + 1 bytes per key fit the free 8-byte half
 
     // ---- 3. split depths + histograms
     if (tid < 40) { S.hist_sd[tid] = 0; S.hist_g[tid] = 0; }
@@ -460,16 +468,18 @@ size_t octree_dyn_smem(int sel_cap_max, int pcap, int pcap2) {
 template <int OCT_RB, int MIN_CTAS>
 static cudaError_t launch_octree_t(const LevelDev *d_levels, int n_levels, const int *d_cand_count, int *d_sel_count,
                                    int level_base, int n_launch_levels, int frame_base, int n_frames, int quota_override,
-                                   size_t smem, int pcap, int pcap2, cudaStream_t st) {
+                                   size_t smem, int sort_bytes, int pcap, int pcap2, cudaStream_t st) {
     static size_t configured = 0;
-    if (smem > 32 * 1024 && smem > configured) {
-        cudaError_t e = cudaFuncSetAttribute(k_octree<OCT_RB, MIN_CTAS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const int sort_off = (int)((smem + 15) & ~(size_t)15);
+    const size_t total = (size_t)sort_off + (size_t)sort_bytes;
+    if (total > 32 * 1024 && total > configured) {
+        cudaError_t e = cudaFuncSetAttribute(k_octree<OCT_RB, MIN_CTAS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)total);
         if (e != cudaSuccess) return e;
-        configured = smem;
+        configured = total;
     }
     dim3 grid(n_launch_levels, n_frames);
-    k_octree<OCT_RB, MIN_CTAS><<<grid, OCT_THREADS, smem, st>>>(d_levels, n_levels, d_cand_count, d_sel_count, level_base,
-                                                                frame_base, quota_override, pcap, pcap2);
+    k_octree<OCT_RB, MIN_CTAS><<<grid, OCT_THREADS, total, st>>>(d_levels, n_levels, d_cand_count, d_sel_count, level_base,
+                                                                 frame_base, quota_override, pcap, pcap2, sort_off, sort_bytes);
     return cudaGetLastError();
 }
 
@@ -479,11 +489,18 @@ cudaError_t launch_octree(const LevelDev *d_levels, int n_levels, const int *d_c
     size_t smem = octree_dyn_smem(sel_cap_max, pcap, pcap2);
     if (getenv("ORBB_OCT_PAD")) smem = std::max(smem, (size_t)atoi(getenv("ORBB_OCT_PAD")));
     // fewer CTAs than the GPU can hold at once: every CTA's own latency is the kernel's duration
-    if ((long long)n_launch_levels * n_frames <= 148 * 3)
+    const long long ctas = (long long)n_launch_levels * n_frames;
+    if (ctas <= 148 * 3) {
+        // shared memory left per CTA when the grid is spread over the 148 SMs (227 KB each, 18 KB static per CTA)
+        const int per_sm = (int)((ctas + 147) / 148);
+        long long spare = (227 * 1024) / per_sm - 18 * 1024 - (long long)smem - 1024;
+        static const bool no_smem_sort = getenv("ORBB_OCT_NOSMEM") != nullptr;
+        const int sort_bytes = (no_smem_sort || spare < 32 * 1024) ? 0 : (int)std::min<long long>(spare, 176 * 1024) & ~15;
         return launch_octree_t<4, 3>(d_levels, n_levels, d_cand_count, d_sel_count, level_base, n_launch_levels, frame_base,
-                                     n_frames, quota_override, smem, pcap, pcap2, st);
+                                     n_frames, quota_override, smem, sort_bytes, pcap, pcap2, st);
+    }
     return launch_octree_t<1, 4>(d_levels, n_levels, d_cand_count, d_sel_count, level_base, n_launch_levels, frame_base,
-                                 n_frames, quota_override, smem, pcap, pcap2, st);
+                                 n_frames, quota_override, smem, 0, pcap, pcap2, st);
 }
 
 }  // namespace orbb
