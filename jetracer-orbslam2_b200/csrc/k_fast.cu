@@ -113,27 +113,41 @@ k_fast_cells(const CUtensorMap *__restrict__ maps, const LevelDev *__restrict__ 
             asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0; selp.u32 %0, 1, 0, p; }"
                          : "=r"(done) : "r"(bar) : "memory");
     } else {
-        const int gx = c.x0 - 4, xa = gx & ~3, sh = (gx - xa) * 8;
-        const int nwords = (cw + 7 + 3) >> 2;
-        const uint8_t *roi = L.img + (size_t)frame * L.frame_stride + (size_t)ORBB_BORDER * L.pitch + ORBB_ROI_X0;
-        const int rpi = 32 / nwords;  // rows per iteration (nwords <= 32 guaranteed by the host)
-        const int lr = lane / nwords, lw = lane - lr * nwords;
-        const uint8_t *src = roi + (ptrdiff_t)(c.y0 - 3) * L.pitch + xa + 4 * lw;
-        if (lr < rpi) {
-            const int nrows = ch + 6;
-            for (int r0 = lr; r0 < nrows; r0 += 4 * rpi) {  // 4 rows (8 loads) in flight per lane
-                uint32_t ga[4], gb[4];
+        // 128-bit staging WITH re-alignment: a lane loads the two aligned 16-byte chunks around four output words
+        // (ROI rows are 128-byte aligned by layout), forms the words with funnel shifts -- the word offset of the
+        // window inside its first chunk is uniform per cell, so the four variants are a uniform switch -- and writes
+        // them with one 128-bit shared store.  7 instructions per 16 pixels instead of 16.
+        const int gx = c.x0 - 4, xa16 = gx & ~15, wo = (gx - xa16) >> 2, sh = (gx & 3) * 8;
+        const int nwords = (cw + 7 + 3) >> 2, ng = (nwords + 3) >> 2;  // output words per row, 4-word groups per row
+        const int nrows = ch + 6, nitems = nrows * ng;
+        const uint8_t *src = L.img + (size_t)frame * L.frame_stride + (size_t)(ORBB_BORDER + c.y0 - 3) * L.pitch + ORBB_ROI_X0 + xa16;
+        const int row_left = L.pitch - (ORBB_ROI_X0 + xa16);          // bytes from the first chunk to the end of the padded row
+        const unsigned inv_ng = (1u << 16) / (unsigned)ng + 1u;       // exact i / ng for i < 2^10, ng <= 5
+        for (int i0 = 0; i0 < nitems; i0 += 64) {                     // two items (four 128-bit loads) in flight per lane
+            uint4 a[2], b[2];
+            int r[2], g[2];
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    const int r = min(r0 + k * rpi, nrows - 1);
-                    const uint32_t *g = reinterpret_cast<const uint32_t *>(src + (ptrdiff_t)r * L.pitch);
-                    ga[k] = g[0]; gb[k] = g[1];
-                }
+            for (int u = 0; u < 2; ++u) {
+                const int i = min(i0 + 32 * u + lane, nitems - 1);
+                r[u] = (int)(((unsigned)i * inv_ng) >> 16); g[u] = i - r[u] * ng;
+                const uint4 *p = reinterpret_cast<const uint4 *>(src + (size_t)r[u] * L.pitch + 16 * g[u]);
+                a[u] = __ldg(p);
+                b[u] = 16 * g[u] + 32 <= row_left ? __ldg(p + 1) : make_uint4(0u, 0u, 0u, 0u);  // never past the row
+            }
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    const int r = r0 + k * rpi;
-                    if (r < nrows) reinterpret_cast<uint32_t *>(tile + r * tp)[lw] = __funnelshift_r(ga[k], gb[k], sh);
+            for (int u = 0; u < 2; ++u) {
+                uint4 o;
+                switch (wo) {  // uniform per cell
+                    case 0: o = make_uint4(__funnelshift_r(a[u].x, a[u].y, sh), __funnelshift_r(a[u].y, a[u].z, sh),
+                                           __funnelshift_r(a[u].z, a[u].w, sh), __funnelshift_r(a[u].w, b[u].x, sh)); break;
+                    case 1: o = make_uint4(__funnelshift_r(a[u].y, a[u].z, sh), __funnelshift_r(a[u].z, a[u].w, sh),
+                                           __funnelshift_r(a[u].w, b[u].x, sh), __funnelshift_r(b[u].x, b[u].y, sh)); break;
+                    case 2: o = make_uint4(__funnelshift_r(a[u].z, a[u].w, sh), __funnelshift_r(a[u].w, b[u].x, sh),
+                                           __funnelshift_r(b[u].x, b[u].y, sh), __funnelshift_r(b[u].y, b[u].z, sh)); break;
+                    default: o = make_uint4(__funnelshift_r(a[u].w, b[u].x, sh), __funnelshift_r(b[u].x, b[u].y, sh),
+                                            __funnelshift_r(b[u].y, b[u].z, sh), __funnelshift_r(b[u].z, b[u].w, sh)); break;
                 }
+                if (i0 + 32 * u + lane < nitems) *reinterpret_cast<uint4 *>(tile + r[u] * tp + 16 * g[u]) = o;
             }
         }
         for (int i = lane; i < (sp * cfg.score_rows) >> 2; i += 32) reinterpret_cast<uint32_t *>(score)[i] = 0;
