@@ -116,7 +116,7 @@ k_fast_cells(const CUtensorMap *__restrict__ maps, const LevelDev *__restrict__ 
         // 128-bit staging WITH re-alignment: a lane loads the two aligned 16-byte chunks around four output words
         // (ROI rows are 128-byte aligned by layout), forms the words with funnel shifts -- the word offset of the
         // window inside its first chunk is uniform per cell, so the four variants are a uniform switch -- and writes
-        // them with one 128-bit shared store.  7 instructions per 16 pixels instead of 16.
+        // them to the tile.  10 instructions per 16 pixels instead of 16.
         const int gx = c.x0 - 4, xa16 = gx & ~15, wo = (gx - xa16) >> 2, sh = (gx & 3) * 8;
         const int nwords = (cw + 7 + 3) >> 2, ng = (nwords + 3) >> 2;  // output words per row, 4-word groups per row
         const int nrows = ch + 6, nitems = nrows * ng;
@@ -147,7 +147,17 @@ k_fast_cells(const CUtensorMap *__restrict__ maps, const LevelDev *__restrict__ 
                     default: o = make_uint4(__funnelshift_r(a[u].w, b[u].x, sh), __funnelshift_r(b[u].x, b[u].y, sh),
                                             __funnelshift_r(b[u].y, b[u].z, sh), __funnelshift_r(b[u].z, b[u].w, sh)); break;
                 }
-                if (i0 + 32 * u + lane < nitems) *reinterpret_cast<uint4 *>(tile + r[u] * tp + 16 * g[u]) = o;
+                // four 32-bit stores: the tile keeps an odd word pitch, so the byte loads of the arc score (pixels
+                // of many rows in one warp instruction) spread over all banks; a 16-byte pitch would fold rows 8
+                // apart onto the same banks
+                if (i0 + 32 * u + lane < nitems) {
+                    uint32_t *t = reinterpret_cast<uint32_t *>(tile + r[u] * tp) + 4 * g[u];
+                    const int left = tpw - 4 * g[u];
+                    t[0] = o.x;
+                    if (left > 1) t[1] = o.y;
+                    if (left > 2) t[2] = o.z;
+                    if (left > 3) t[3] = o.w;
+                }
             }
         }
         for (int i = lane; i < (sp * cfg.score_rows) >> 2; i += 32) reinterpret_cast<uint32_t *>(score)[i] = 0;

@@ -415,7 +415,7 @@ extern "C" int orbb_create(orbb_handle **out, const orbb_params *params, int wid
     h->pcap = h->sel_cap_max; h->pcap2 = 1;
     while (h->pcap2 < h->pcap) h->pcap2 <<= 1;
     if (octree_dyn_smem(h->sel_cap_max, h->pcap, h->pcap2) > 200 * 1024) { orbb_destroy(h); return ORBB_ERR_CAPACITY; }
-    h->fcfg.tile_pitch = (int)round_up(max_cw + 12, 16);  // whole 16-byte groups (128-bit shared stores)
+    h->fcfg.tile_pitch = (int)round_up(max_cw + 12, 4) | 4;  // odd number of words: rows never share a bank pattern
     h->fcfg.tma_pitch = (int)round_up(max_cw + 10 + 15 + 4, 16);  // 16-byte aligned box start: up to 15 bytes of phase
     h->fcfg.tile_rows = max_ch + 6;
     h->fcfg.score_pitch = (int)round_up(max_cw + 2, 4);
