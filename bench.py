@@ -39,8 +39,8 @@ MAP_SIZE = 50_000
 LEVEL_PIXELS = 950_532    # sum_l w_l*h_l for 640x480, 8 levels, 1.2
 BYTES_PER_FRAME = W * H + 2 * LEVEL_PIXELS + 60 * NFEAT  # 2,268,264 B
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE k_fast_cells launch, per frame, from the committed
-# ncu --set full capture profiles/r01_all_kernels_full.txt (135.4 MB + 8.43 MB for a 128-frame launch)
-FAST_DRAM_TRAFFIC_PER_FRAME = (135.4e6 + 8.432e6) / 128
+# ncu --set full capture profiles/r01j_all_kernels_full.txt (135.4 MB + 8.56 MB for a 128-frame launch)
+FAST_DRAM_TRAFFIC_PER_FRAME = (135.4e6 + 8.563e6) / 128
 
 
 def measured_peaks():
