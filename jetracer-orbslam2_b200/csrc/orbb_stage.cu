@@ -35,6 +35,10 @@ struct orbb_rgbd_stage {
     double *d_pts = nullptr, *d_prev_m = nullptr, *d_curr_m = nullptr;
     float *d_pos = nullptr;
     uint16_t *d_xy = nullptr;
+    // every result array is a slice of ONE device block, mirrored by one pinned host block per parity, so that a
+    // full batch comes back with a single D2H copy (nine separate copies cost ~8 us of latency each)
+    uint8_t *d_block = nullptr, *h_block[2] = {nullptr, nullptr};
+    size_t block_bytes = 0;
     // pinned host results, by ticket parity
     struct Host {
         int *counts, *valid, *matched;
@@ -130,20 +134,39 @@ extern "C" int orbb_rgbd_stage_create(orbb_rgbd_stage **out, const orbb_rgbd_con
         SCKC(cudaEventCreateWithFlags(&s->ev_out[i], cudaEventDisableTiming));
         SCKC(cudaEventCreateWithFlags(&s->ev_main[i], cudaEventDisableTiming));
         orbb_rgbd_stage::Host &H = s->host[i];
-        SCKC(shost(s, &H.counts, B)); SCKC(shost(s, &H.valid, B)); SCKC(shost(s, &H.matched, B));
-        SCKC(shost(s, &H.kp, B * mk)); SCKC(shost(s, &H.desc, B * mk * 32));
-        SCKC(shost(s, &H.pts, B * mk * 3)); SCKC(shost(s, &H.prev_m, B * mk * 3)); SCKC(shost(s, &H.curr_m, B * mk * 3));
-        SCKC(shost(s, &H.xy, B * mk * 2)); SCKC(shost(s, &H.T, B * 16));
+        SCKC(shost(s, &H.T, B * 16));
     }
     SCKC(cudaEventCreateWithFlags(&s->ev_align, cudaEventDisableTiming));
     SCKC(cudaEventCreateWithFlags(&s->ev_gate, cudaEventDisableTiming));
     SCKC(sdev(s, &s->d_aligned, s->img_px * B));
-    SCKC(sdev(s, &s->d_kp_raw, B * mk)); SCKC(sdev(s, &s->d_desc_raw, B * mk * 32)); SCKC(sdev(s, &s->d_counts_raw, B));
-    SCKC(sdev(s, &s->d_kp, R * mk)); SCKC(sdev(s, &s->d_desc, R * mk * 32)); SCKC(sdev(s, &s->d_pts, R * mk * 3));
-    SCKC(sdev(s, &s->d_valid, R));
+    SCKC(sdev(s, &s->d_kp_raw, B * mk)); SCKC(sdev(s, &s->d_desc_raw, B * mk * 32));
     SCKC(sdev(s, &s->d_pos, B * mk * 2)); SCKC(sdev(s, &s->d_idx, B * mk)); SCKC(sdev(s, &s->d_dist, B * mk));
-    SCKC(sdev(s, &s->d_prev_m, B * mk * 3)); SCKC(sdev(s, &s->d_curr_m, B * mk * 3)); SCKC(sdev(s, &s->d_xy, B * mk * 2));
-    SCKC(sdev(s, &s->d_nm, B));
+    {
+        // result block layout (256-byte aligned slices); rows 0 of kp/desc/pts/valid carry the previous batch's last frame
+        size_t off = 0;
+        auto slice = [&](size_t bytes) { const size_t o = off; off = (off + bytes + 255) & ~(size_t)255; return o; };
+        const size_t o_kp = slice(sizeof(orbb_keypoint) * R * mk), o_desc = slice(32 * R * mk), o_pts = slice(sizeof(double) * 3 * R * mk);
+        const size_t o_prev = slice(sizeof(double) * 3 * B * mk), o_curr = slice(sizeof(double) * 3 * B * mk);
+        const size_t o_xy = slice(sizeof(uint16_t) * 2 * B * mk), o_cnt = slice(sizeof(int) * B), o_valid = slice(sizeof(int) * R);
+        const size_t o_nm = slice(sizeof(int) * B);
+        s->block_bytes = off;
+        SCKC(sdev(s, &s->d_block, off));
+        uint8_t *d = s->d_block;
+        s->d_kp = reinterpret_cast<orbb_keypoint *>(d + o_kp); s->d_desc = d + o_desc; s->d_pts = reinterpret_cast<double *>(d + o_pts);
+        s->d_prev_m = reinterpret_cast<double *>(d + o_prev); s->d_curr_m = reinterpret_cast<double *>(d + o_curr);
+        s->d_xy = reinterpret_cast<uint16_t *>(d + o_xy); s->d_counts_raw = reinterpret_cast<int *>(d + o_cnt);
+        s->d_valid = reinterpret_cast<int *>(d + o_valid); s->d_nm = reinterpret_cast<int *>(d + o_nm);
+        for (int i = 0; i < 2; ++i) {
+            SCKC(shost(s, &s->h_block[i], off));
+            uint8_t *hb = s->h_block[i];
+            orbb_rgbd_stage::Host &H = s->host[i];
+            H.kp = reinterpret_cast<orbb_keypoint *>(hb + o_kp) + mk; H.desc = hb + o_desc + 32 * mk;
+            H.pts = reinterpret_cast<double *>(hb + o_pts) + 3 * mk;
+            H.prev_m = reinterpret_cast<double *>(hb + o_prev); H.curr_m = reinterpret_cast<double *>(hb + o_curr);
+            H.xy = reinterpret_cast<uint16_t *>(hb + o_xy); H.counts = reinterpret_cast<int *>(hb + o_cnt);
+            H.valid = reinterpret_cast<int *>(hb + o_valid) + 1; H.matched = reinterpret_cast<int *>(hb + o_nm);
+        }
+    }
     SCKC(cudaMemset(s->d_valid, 0, sizeof(int) * R));
     for (cudaStream_t *st : {&s->s_in, &s->s_align, &s->s_main, &s->s_out})
         SCKC(cudaStreamCreateWithFlags(st, cudaStreamNonBlocking));
@@ -207,15 +230,19 @@ extern "C" int orbb_rgbd_stage_submit(orbb_rgbd_stage *s, const uint8_t *h_gray,
     SCK(s, cudaEventRecord(s->ev_main[p], s->s_main));
     // ---- results to the host
     SCK(s, cudaStreamWaitEvent(s->s_out, s->ev_main[p], 0));
-    SCK(s, cudaMemcpyAsync(H.counts, s->d_counts_raw, sizeof(int) * n, cudaMemcpyDeviceToHost, s->s_out));
-    SCK(s, cudaMemcpyAsync(H.valid, s->d_valid + 1, sizeof(int) * n, cudaMemcpyDeviceToHost, s->s_out));
-    SCK(s, cudaMemcpyAsync(H.matched, s->d_nm, sizeof(int) * n, cudaMemcpyDeviceToHost, s->s_out));
-    SCK(s, cudaMemcpyAsync(H.kp, s->d_kp + mk, sizeof(orbb_keypoint) * n * mk, cudaMemcpyDeviceToHost, s->s_out));
-    SCK(s, cudaMemcpyAsync(H.desc, s->d_desc + 32 * mk, 32 * n * mk, cudaMemcpyDeviceToHost, s->s_out));
-    SCK(s, cudaMemcpyAsync(H.pts, s->d_pts + 3 * mk, sizeof(double) * 3 * n * mk, cudaMemcpyDeviceToHost, s->s_out));
-    SCK(s, cudaMemcpyAsync(H.prev_m, s->d_prev_m, sizeof(double) * 3 * n * mk, cudaMemcpyDeviceToHost, s->s_out));
-    SCK(s, cudaMemcpyAsync(H.curr_m, s->d_curr_m, sizeof(double) * 3 * n * mk, cudaMemcpyDeviceToHost, s->s_out));
-    SCK(s, cudaMemcpyAsync(H.xy, s->d_xy, sizeof(uint16_t) * 2 * n * mk, cudaMemcpyDeviceToHost, s->s_out));
+    if (n_frames == s->B) {
+        SCK(s, cudaMemcpyAsync(s->h_block[p], s->d_block, s->block_bytes, cudaMemcpyDeviceToHost, s->s_out));
+    } else {  // partial batch: only the rows in use
+        SCK(s, cudaMemcpyAsync(H.counts, s->d_counts_raw, sizeof(int) * n, cudaMemcpyDeviceToHost, s->s_out));
+        SCK(s, cudaMemcpyAsync(H.valid, s->d_valid + 1, sizeof(int) * n, cudaMemcpyDeviceToHost, s->s_out));
+        SCK(s, cudaMemcpyAsync(H.matched, s->d_nm, sizeof(int) * n, cudaMemcpyDeviceToHost, s->s_out));
+        SCK(s, cudaMemcpyAsync(H.kp, s->d_kp + mk, sizeof(orbb_keypoint) * n * mk, cudaMemcpyDeviceToHost, s->s_out));
+        SCK(s, cudaMemcpyAsync(H.desc, s->d_desc + 32 * mk, 32 * n * mk, cudaMemcpyDeviceToHost, s->s_out));
+        SCK(s, cudaMemcpyAsync(H.pts, s->d_pts + 3 * mk, sizeof(double) * 3 * n * mk, cudaMemcpyDeviceToHost, s->s_out));
+        SCK(s, cudaMemcpyAsync(H.prev_m, s->d_prev_m, sizeof(double) * 3 * n * mk, cudaMemcpyDeviceToHost, s->s_out));
+        SCK(s, cudaMemcpyAsync(H.curr_m, s->d_curr_m, sizeof(double) * 3 * n * mk, cudaMemcpyDeviceToHost, s->s_out));
+        SCK(s, cudaMemcpyAsync(H.xy, s->d_xy, sizeof(uint16_t) * 2 * n * mk, cudaMemcpyDeviceToHost, s->s_out));
+    }
     SCK(s, cudaEventRecord(s->ev_out[p], s->s_out));
     H.n_frames = n_frames;
     // ---- carry: the batch's last frame becomes row 0 (read by the next batch's reprojection / match only)

@@ -1,0 +1,29 @@
+#!/usr/bin/env python3
+"""Latency of one RGB-D frame through orbb_rgbd_stage_submit + wait (max_batch = 1, the reference's per-wake-up
+use), 848x480 gray + depth from pinned memory, median over 200 frames.  usage (GPU box): python tools/stage_latency_probe.py"""
+import importlib, os, sys, time
+import numpy as np
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+orbb = importlib.import_module("jetracer-orbslam2_b200.orbb")
+synth = importlib.import_module("jetracer-orbslam2_b200.synth")
+for (w, h, nf) in ((848, 480, 1200), (640, 480, 1000)):
+    gray = torch.from_numpy(np.stack([synth.textured_frame(w, h, 50 + i) for i in range(4)])).pin_memory()
+    yy, xx = np.mgrid[0:h, 0:w].astype(np.float32)
+    depth = np.clip(1500 + 900 * np.sin(xx / 97.0) * np.cos(yy / 61.0), 1, 65535).astype(np.uint16)
+    pd = torch.from_numpy(np.stack([depth] * 4).view(np.int16)).pin_memory()
+    di = orbb.make_intrinsics(w, h, w * 0.5 + 3.7, h * 0.5 - 2.2, 0.502 * w, 0.502 * w, 4)
+    oi = orbb.make_intrinsics(w, h, w * 0.5 - 5.1, h * 0.5 + 4.3, 0.72 * w, 0.725 * w, 2)
+    ex = orbb.make_extrinsics((1, 0, 0, 0, 1, 0, 0, 0, 1), (0.0148, 0.0002, 0.0003))
+    stage = orbb.RgbdFrameStage(orbb.Params(nf, 1.2, 8, 20, 7), di, oi, ex, 0.001, 2.0, 64, max_batch=1)
+    fb, db = w * h, 2 * w * h
+    for i in range(10):
+        stage.wait(stage.submit_ptr(gray.data_ptr() + (i % 4) * fb, pd.data_ptr() + (i % 4) * db, 1))
+    ts = []
+    for i in range(200):
+        t = time.perf_counter()
+        r = stage.wait(stage.submit_ptr(gray.data_ptr() + (i % 4) * fb, pd.data_ptr() + (i % 4) * db, 1))
+        ts.append(time.perf_counter() - t)
+    print(f"{w}x{h} {nf} kp: one RGB-D frame submit+wait median {1e6 * float(np.median(ts)):.1f} us, "
+          f"valid {int(r['valid_keypoints_num'][0])}, matched {int(r['matched_keypoints_num'][0])}", flush=True)
+    stage.close()
