@@ -40,6 +40,9 @@ CONFIGS = [  # (w, h, nfeatures, scale, nlevels, generator, seed)
     (512, 384, 600, 2.0, 3, "textured_frame", 21),
     (848, 800, 1000, 1.2, 8, "textured_frame", 3000),   # cfg 3 geometry (T265-sized)
     (1280, 720, 2000, 1.2, 8, "textured_frame", 4000),  # cfg 4 geometry
+    (1920, 1080, 3000, 1.2, 8, "textured_frame", 4100),  # full HD: widest tables, two quadtree roots
+    (97, 83, 120, 1.2, 2, "textured_frame", 33),        # smallest useful frame: one or two cells per level
+    (752, 480, 1000, 1.3, 6, "textured_frame", 77),     # EuRoC-sized, non-default scale (cells up to 37 px wide)
 ]
 
 
