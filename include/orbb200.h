@@ -243,6 +243,24 @@ int orbb_match_windowed_batch(orbb_handle *h, const uint8_t *d_query, const floa
                               const double *d_train_points, double *d_prev_matched, double *d_curr_matched,
                               uint16_t *d_xy_u16, int32_t *d_nmatched, void *cuda_stream);
 
+/* Guided matcher with ORB-SLAM2's SearchByProjection gates (upstream raulmur/ORB_SLAM2
+ * src/ORBmatcher.cc SearchByProjection(Frame&, const Frame&, th, bMono) + ComputeThreeMaxima, un-vendored, no pin in
+ * the reference): for every query keypoint of frame f, projected to (u, v) in the train image (orbb_reproject_points),
+ *   radius = th * mvScaleFactors[query octave]; candidates = train keypoints with |u - x| < radius, |v - y| < radius
+ *   (strict, as Frame::GetFeaturesInArea) and query octave - 1 <= train octave <= query octave + 1;
+ *   best = smallest 256-bit Hamming distance (ties -> lowest train index; upstream: grid-cell traversal order);
+ *   accepted iff best <= th_high (ORBmatcher::TH_HIGH = 100);
+ *   check_orientation != 0: rot = query angle - train angle (+360 if negative), bin = round(rot / 30) (30 -> 0), only
+ *   matches in the three most populated bins survive (second/third bin dropped below 10 % of the first).
+ * Not modelled (SLAM state, not front-end): the "train keypoint already has a map point" skip, the stereo uRight check
+ * and the forward/backward octave modes.  Arrays as in orbb_match_windowed_batch; d_nmatched [n_frames] counts the
+ * survivors.  Async on stream. */
+int orbb_match_projection_batch(orbb_handle *h, const uint8_t *d_query_desc, const float *d_query_uv,
+                                const orbb_keypoint *d_query_kp, const int32_t *d_q_counts, const uint8_t *d_train_desc,
+                                const orbb_keypoint *d_train_kp, const int32_t *d_t_counts, int n_frames, int max_kp,
+                                float th, int th_high, int check_orientation, int32_t *d_idx, int32_t *d_dist,
+                                int32_t *d_nmatched, void *cuda_stream);
+
 /* Jetracer::rgb_to_grayscale (src/cuda/cuda_RGB_to_Grayscale.cuh, kernel cuda_RGB_to_Grayscale.cu:10-24, call site
  * buildStream.cpp:416-422) for a batch: gray = floor((B*0.07 + G*0.72 + R*0.21) + 0.5) in float64, every operation
  * rounded on its own, interleaved RGB8 in.  DEVICE pointers; rgb_pitch must be a multiple of 4.  Async on stream.

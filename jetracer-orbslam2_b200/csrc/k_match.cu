@@ -209,4 +209,118 @@ cudaError_t launch_match_windowed_batch(const uint8_t *d_q, const void *d_q_xy, 
     return cudaGetLastError();
 }
 
+// ---- ORB-SLAM2 SearchByProjection gates (upstream ORBmatcher.cc): per-query radius from the octave, octave band,
+// best distance <= th_high.  thread = one query of one frame pair, train keypoints (descriptor, position, octave) go
+// through shared memory in tiles.  Same structure as k_match_windowed.
+struct ScaleTable { float sf[ORBB_MAX_LEVELS]; };
+
+__global__ void __launch_bounds__(WIN_THREADS)
+k_match_projection(const uint4 *__restrict__ query, const float2 *__restrict__ q_uv, const orbb_keypoint *__restrict__ q_kp,
+                   const int *__restrict__ q_counts, const uint4 *__restrict__ train, const orbb_keypoint *__restrict__ t_kp,
+                   const int *__restrict__ t_counts, int max_kp, float th, int th_high, const ScaleTable scales, int n_levels,
+                   int *__restrict__ out_idx, int *__restrict__ out_dist) {
+    __shared__ uint4 s_d[WIN_TILE * 2];
+    __shared__ float2 s_xy[WIN_TILE];
+    __shared__ int s_oct[WIN_TILE];
+    const size_t f = blockIdx.y, row0 = f * max_kp;
+    const int nq = min(q_counts[f], max_kp), nt = min(t_counts[f], max_kp);
+    if ((int)(blockIdx.x * WIN_THREADS) >= nq) return;
+    const int q = blockIdx.x * WIN_THREADS + threadIdx.x;
+    const size_t qq = row0 + min(q, nq - 1);
+    const uint4 qa = query[qq * 2], qb = query[qq * 2 + 1];
+    const float2 uv = q_uv[qq];
+    const int oq = min(max(q_kp[qq].octave, 0), n_levels - 1);
+    const float radius = __fmul_rn(th, scales.sf[oq]);
+    int best_d = 256, best_i = -1;
+    for (int tb = 0; tb < nt; tb += WIN_TILE) {
+        const int cnt = min(WIN_TILE, nt - tb);
+        __syncthreads();
+        for (int i = threadIdx.x; i < cnt * 2; i += WIN_THREADS) s_d[i] = train[(row0 + tb) * 2 + i];
+        for (int i = threadIdx.x; i < cnt; i += WIN_THREADS) {
+            const orbb_keypoint &k = t_kp[row0 + tb + i];
+            s_xy[i] = make_float2(k.x, k.y);
+            s_oct[i] = k.octave;
+        }
+        __syncthreads();
+        for (int t = 0; t < cnt; ++t) {
+            const float2 p = s_xy[t];
+            const int ot = s_oct[t];
+            if (fabsf(__fsub_rn(p.x, uv.x)) < radius && fabsf(__fsub_rn(p.y, uv.y)) < radius && ot >= oq - 1 && ot <= oq + 1) {
+                const uint4 a = s_d[2 * t], b = s_d[2 * t + 1];
+                const int d = __popc(qa.x ^ a.x) + __popc(qa.y ^ a.y) + __popc(qa.z ^ a.z) + __popc(qa.w ^ a.w) +
+                              __popc(qb.x ^ b.x) + __popc(qb.y ^ b.y) + __popc(qb.z ^ b.z) + __popc(qb.w ^ b.w);
+                if (d < best_d) { best_d = d; best_i = tb + t; }
+            }
+        }
+    }
+    if (q < nq) {
+        const bool ok = best_i >= 0 && best_d <= th_high;
+        out_idx[row0 + q] = ok ? best_i : -1;
+        out_dist[row0 + q] = ok ? best_d : -1;
+    }
+}
+
+// rotation-consistency filter (ORBmatcher::ComputeThreeMaxima) + survivor count.  CTA = one frame pair.
+__global__ void __launch_bounds__(256)
+k_rotation_filter(const orbb_keypoint *__restrict__ q_kp, const orbb_keypoint *__restrict__ t_kp,
+                  const int *__restrict__ q_counts, int max_kp, int check, int *__restrict__ idx, int *__restrict__ dist,
+                  int *__restrict__ n_matched) {
+    __shared__ int s_hist[30], s_keep[30], s_n;
+    const size_t f = blockIdx.x, row0 = f * max_kp;
+    const int nq = min(q_counts[f], max_kp);
+    if (threadIdx.x < 30) { s_hist[threadIdx.x] = 0; s_keep[threadIdx.x] = 1; }
+    if (threadIdx.x == 0) s_n = 0;
+    __syncthreads();
+    auto bin_of = [&](int q, int t) {
+        float rot = __fsub_rn(q_kp[row0 + q].angle, t_kp[row0 + t].angle);
+        if (rot < 0.0f) rot = __fadd_rn(rot, 360.0f);
+        int bin = (int)roundf(__fmul_rn(rot, 1.0f / 30));  // upstream: factor = 1.0f/HISTO_LENGTH, bin = round(rot*factor)
+        return bin == 30 ? 0 : bin;
+    };
+    if (check) {
+        for (int q = threadIdx.x; q < nq; q += blockDim.x) {
+            const int t = idx[row0 + q];
+            if (t >= 0) atomicAdd(&s_hist[bin_of(q, t)], 1);
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            int max1 = 0, max2 = 0, max3 = 0, ind1 = -1, ind2 = -1, ind3 = -1;
+            for (int i = 0; i < 30; ++i) {
+                const int s = s_hist[i];
+                if (s > max1) { max3 = max2; max2 = max1; max1 = s; ind3 = ind2; ind2 = ind1; ind1 = i; }
+                else if (s > max2) { max3 = max2; max2 = s; ind3 = ind2; ind2 = i; }
+                else if (s > max3) { max3 = s; ind3 = i; }
+            }
+            if ((float)max2 < __fmul_rn(0.1f, (float)max1)) { ind2 = -1; ind3 = -1; }
+            else if ((float)max3 < __fmul_rn(0.1f, (float)max1)) ind3 = -1;
+            for (int i = 0; i < 30; ++i) s_keep[i] = (i == ind1 || i == ind2 || i == ind3) ? 1 : 0;
+        }
+        __syncthreads();
+    }
+    int mine = 0;
+    for (int q = threadIdx.x; q < nq; q += blockDim.x) {
+        const int t = idx[row0 + q];
+        if (t < 0) continue;
+        if (check && !s_keep[bin_of(q, t)]) { idx[row0 + q] = -1; dist[row0 + q] = -1; }
+        else ++mine;
+    }
+    atomicAdd(&s_n, mine);
+    __syncthreads();
+    if (threadIdx.x == 0 && n_matched) n_matched[f] = s_n;
+}
+
+cudaError_t launch_match_projection(const uint8_t *d_q, const float *d_q_uv, const orbb_keypoint *d_q_kp, const int *d_q_counts,
+                                    const uint8_t *d_t, const orbb_keypoint *d_t_kp, const int *d_t_counts, int n_frames,
+                                    int max_kp, float th, int th_high, int check, const float *sf, int n_levels, int *d_idx,
+                                    int *d_dist, int *d_nmatched, cudaStream_t st) {
+    ScaleTable tab{};
+    for (int l = 0; l < n_levels && l < ORBB_MAX_LEVELS; ++l) tab.sf[l] = sf[l];
+    dim3 grid((max_kp + WIN_THREADS - 1) / WIN_THREADS, n_frames);
+    k_match_projection<<<grid, WIN_THREADS, 0, st>>>(reinterpret_cast<const uint4 *>(d_q), reinterpret_cast<const float2 *>(d_q_uv),
+                                                     d_q_kp, d_q_counts, reinterpret_cast<const uint4 *>(d_t), d_t_kp, d_t_counts,
+                                                     max_kp, th, th_high, tab, n_levels, d_idx, d_dist);
+    k_rotation_filter<<<n_frames, 256, 0, st>>>(d_q_kp, d_t_kp, d_q_counts, max_kp, check, d_idx, d_dist, d_nmatched);
+    return cudaGetLastError();
+}
+
 }  // namespace orbb

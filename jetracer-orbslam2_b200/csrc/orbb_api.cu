@@ -40,6 +40,9 @@ cudaError_t launch_reproject(const double *, const int *, int, int, const double
                              cudaStream_t);
 cudaError_t launch_compact_pairs(const int *, const int *, int, int, const double *, const double *, const void *, int,
                                  double *, double *, uint16_t *, int *, cudaStream_t);
+cudaError_t launch_match_projection(const uint8_t *, const float *, const orbb_keypoint *, const int *, const uint8_t *,
+                                    const orbb_keypoint *, const int *, int, int, float, int, int, const float *, int, int *, int *,
+                                    int *, cudaStream_t);
 cudaError_t launch_rgb_to_gray(const uint8_t *, size_t, size_t, int, int, int, uint8_t *, size_t, size_t, cudaStream_t);
 cudaError_t launch_match_windowed_batch(const uint8_t *, const void *, int, const int *, const uint8_t *, const void *, int,
                                         const int *, int, int, float, int, int *, int *, cudaStream_t);
@@ -934,6 +937,25 @@ extern "C" int orbb_match_windowed_batch(orbb_handle *h, const uint8_t *d_query,
                                    t_xy_stride, d_prev_matched, d_curr_matched, d_xy_u16, d_nmatched, st));
         h->n_launches += 1;
     }
+    return ORBB_OK;
+}
+
+extern "C" int orbb_match_projection_batch(orbb_handle *h, const uint8_t *d_query_desc, const float *d_query_uv,
+                                           const orbb_keypoint *d_query_kp, const int32_t *d_q_counts,
+                                           const uint8_t *d_train_desc, const orbb_keypoint *d_train_kp,
+                                           const int32_t *d_t_counts, int n_frames, int max_kp, float th, int th_high,
+                                           int check_orientation, int32_t *d_idx, int32_t *d_dist, int32_t *d_nmatched,
+                                           void *stream) {
+    if (!h || !d_query_desc || !d_query_uv || !d_query_kp || !d_q_counts || !d_train_desc || !d_train_kp || !d_t_counts ||
+        !d_idx || !d_dist || n_frames < 1 || max_kp < 1 || !(th > 0.0f) || th_high < 0)
+        return ORBB_ERR_INVALID;
+    if ((reinterpret_cast<uintptr_t>(d_query_desc) | reinterpret_cast<uintptr_t>(d_train_desc)) & 15) return ORBB_ERR_INVALID;
+    if (reinterpret_cast<uintptr_t>(d_query_uv) & 7) return ORBB_ERR_INVALID;
+    CK(h, cudaSetDevice(h->device));
+    CK(h, launch_match_projection(d_query_desc, d_query_uv, d_query_kp, d_q_counts, d_train_desc, d_train_kp, d_t_counts,
+                                  n_frames, max_kp, th, std::min(th_high, 256), check_orientation, h->sf, h->nlevels, d_idx,
+                                  d_dist, d_nmatched, static_cast<cudaStream_t>(stream)));
+    h->n_launches += 2;
     return ORBB_OK;
 }
 

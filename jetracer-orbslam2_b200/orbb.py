@@ -36,7 +36,7 @@ EXPORTS = [
     "orbb_match_knn_segmented", "orbb_match_windowed", "orbb_debug_get_padded", "orbb_debug_get_blurred", "orbb_debug_get_scores",
     "orbb_debug_get_candidates", "orbb_debug_get_selected", "orbb_debug_distribute",
     "orbb_align_depth_to_other", "orbb_keypoint_pixel_to_point", "orbb_reproject_points", "orbb_match_windowed_batch",
-    "orbb_rgb_to_grayscale",
+    "orbb_rgb_to_grayscale", "orbb_match_projection_batch",
     "orbb_rgbd_stage_create", "orbb_rgbd_stage_destroy", "orbb_rgbd_stage_reset", "orbb_rgbd_stage_handle",
     "orbb_rgbd_stage_submit", "orbb_rgbd_stage_wait",
 ]
@@ -145,6 +145,7 @@ def load_library():
     L.orbb_reproject_points.argtypes = [vp, vp, vp, i32, i32, vp, C.POINTER(Intrinsics), vp, vp]
     L.orbb_match_windowed_batch.argtypes = [vp, vp, vp, vp, vp, vp, i32, vp, i32, i32, f32, i32, vp, vp, vp, vp, vp, vp,
                                             vp, vp, vp]
+    L.orbb_match_projection_batch.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, f32, i32, i32, vp, vp, vp, vp]
     L.orbb_rgb_to_grayscale.argtypes = [vp, vp, sz, sz, i32, i32, i32, vp, sz, sz, vp]
     L.orbb_rgbd_stage_create.argtypes = [C.POINTER(vp), C.POINTER(RgbdConfig), i32]
     L.orbb_rgbd_stage_destroy.argtypes = [vp]
@@ -388,6 +389,16 @@ class ORBextractor:
             _dev_ptr(d_train_xy), t_xy_stride, _dev_ptr(d_t_counts), n, self.max_kp, max_pixel_distance,
             max_hamming_distance, _dev_ptr(d_idx), _dev_ptr(d_dist), opt(d_query_points), opt(d_train_points),
             opt(d_prev_matched), opt(d_curr_matched), opt(d_xy_u16), opt(d_nmatched), _stream_ptr(stream)))
+
+    def match_keypoints_projection_batch(self, d_query_desc, d_query_uv, d_query_kp, d_q_counts, d_train_desc,
+                                         d_train_kp, d_t_counts, n: int, th: float, th_high: int, check_orientation: bool,
+                                         d_idx, d_dist, d_nmatched=None, stream=None):
+        """ORB-SLAM2 SearchByProjection gates (radius th * scale^octave, octave band, <= TH_HIGH, rotation bins)."""
+        self._check(self._lib.orbb_match_projection_batch(
+            self._h, _dev_ptr(d_query_desc), _dev_ptr(d_query_uv), _dev_ptr(d_query_kp), _dev_ptr(d_q_counts),
+            _dev_ptr(d_train_desc), _dev_ptr(d_train_kp), _dev_ptr(d_t_counts), n, self.max_kp, th, th_high,
+            int(check_orientation), _dev_ptr(d_idx), _dev_ptr(d_dist),
+            _dev_ptr(d_nmatched) if d_nmatched is not None else C.c_void_p(0), _stream_ptr(stream)))
 
     # -- parity / debug access --------------------------------------------------------------
     def debug_padded(self, level: int, frame: int = 0) -> np.ndarray:

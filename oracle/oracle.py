@@ -118,6 +118,8 @@ def lib(native: bool = False):
     L.orbo_reproject_points.restype = None
     L.orbo_compact_pairs.argtypes = [vp, C.c_int, vp, vp, vp, C.c_int, vp, vp, vp, vp]
     L.orbo_compact_pairs.restype = C.c_int
+    L.orbo_search_by_projection.argtypes = [vp, vp, vp, C.c_int, vp, vp, C.c_int, vp, C.c_int, C.c_float, C.c_int, C.c_int, vp, vp]
+    L.orbo_search_by_projection.restype = C.c_int
     L.orbo_rgb_to_grayscale.argtypes = [vp, C.c_size_t, C.c_int, C.c_int, vp, C.c_size_t]
     L.orbo_rgb_to_grayscale.restype = None
     del u8p, i32p, f32p
@@ -357,3 +359,19 @@ def rgb_to_grayscale(rgb: np.ndarray) -> np.ndarray:
     out = np.empty((h, w), np.uint8)
     lib().orbo_rgb_to_grayscale(_p(rgb), rgb.strides[0], w, h, _p(out), w)
     return out
+
+
+def search_by_projection(q_desc, q_uv, q_kp, t_desc, t_kp, scale_factors, th: float, th_high: int = 100,
+                         check_orientation: bool = True):
+    q_desc = np.ascontiguousarray(q_desc, np.uint8).reshape(-1, 32)
+    t_desc = np.ascontiguousarray(t_desc, np.uint8).reshape(-1, 32)
+    q_uv = np.ascontiguousarray(q_uv, np.float32).reshape(-1, 2)
+    q_kp = np.ascontiguousarray(q_kp, KEYPOINT_DTYPE)
+    t_kp = np.ascontiguousarray(t_kp, KEYPOINT_DTYPE)
+    sf = np.ascontiguousarray(scale_factors, np.float32)
+    nq = q_desc.shape[0]
+    idx = np.full(max(nq, 1), -1, np.int32)
+    dist = np.full(max(nq, 1), -1, np.int32)
+    n = lib().orbo_search_by_projection(_p(q_desc), _p(q_uv), _p(q_kp), nq, _p(t_desc), _p(t_kp), t_desc.shape[0], _p(sf),
+                                        sf.shape[0], th, th_high, int(check_orientation), _p(idx), _p(dist))
+    return idx[:nq].copy(), dist[:nq].copy(), int(n)

@@ -134,6 +134,10 @@ void orbo_align_depth_to_other(const uint16_t *depth, float depth_scale, const o
 int orbo_keypoint_pixel_to_point(const uint32_t *aligned, const orbo_intrinsics *oi, const orbo_keypoint *kp,
                                  const uint8_t *desc, int n, orbo_keypoint *kp_out, uint8_t *desc_out, double *points);
 void orbo_reproject_points(const double *points, int n, const double *T, const orbo_intrinsics *intrin, float *pos_out);
+int orbo_search_by_projection(const uint8_t *q_desc, const float *q_uv, const orbo_keypoint *q_kp, int nq,
+                              const uint8_t *t_desc, const orbo_keypoint *t_kp, int nt, const float *scale_factors,
+                              int n_levels, float th, int th_high, int check_orientation, int32_t *out_idx,
+                              int32_t *out_dist);
 void orbo_rgb_to_grayscale(const uint8_t *src, size_t src_pitch, int cols, int rows, uint8_t *dst, size_t dst_pitch);
 int orbo_compact_pairs(const int32_t *idx, int nq, const double *q_points, const double *t_points, const float *t_xy,
                        int t_xy_stride_floats, double *prev_out, double *curr_out, uint16_t *x_out, uint16_t *y_out);

@@ -18,6 +18,7 @@
  */
 #include <math.h>
 #include <stdint.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "orb_oracle.h"
@@ -201,4 +202,77 @@ void orbo_rgb_to_grayscale(const uint8_t *src, size_t src_pitch, int cols, int r
             B = (float)(src[y * src_pitch + x * 3 + 2]);
             dst[y * dst_pitch + x] = (uint8_t)floor((B * 0.07 + G * 0.72 + R * 0.21) + 0.5);
         }
+}
+
+/* ORB-SLAM2 ORBmatcher::SearchByProjection(CurrentFrame, LastFrame, th) gates + ComputeThreeMaxima (upstream
+ * raulmur/ORB_SLAM2 src/ORBmatcher.cc, not vendored by the reference, no version pin): restated from the published
+ * algorithm.  Front-end part only: no map-point bookkeeping, no stereo check, symmetric octave band.  Ties -> lowest
+ * train index (upstream: grid traversal order of Frame::GetFeaturesInArea).  Returns the number of surviving matches. */
+static int hamming256(const uint8_t *a, const uint8_t *b) {
+    int d = 0;
+    for (int i = 0; i < 32; ++i) d += __builtin_popcount((unsigned)(a[i] ^ b[i]));
+    return d;
+}
+
+int orbo_search_by_projection(const uint8_t *q_desc, const float *q_uv, const orbo_keypoint *q_kp, int nq,
+                              const uint8_t *t_desc, const orbo_keypoint *t_kp, int nt, const float *scale_factors,
+                              int n_levels, float th, int th_high, int check_orientation, int32_t *out_idx,
+                              int32_t *out_dist) {
+    enum { HISTO_LENGTH = 30 };
+    int hist[HISTO_LENGTH] = {0};
+    const float factor = 1.0f / HISTO_LENGTH;
+    for (int i = 0; i < nq; ++i) {
+        out_idx[i] = -1;
+        out_dist[i] = -1;
+        int oct = q_kp[i].octave;
+        if (oct < 0) oct = 0;
+        if (oct > n_levels - 1) oct = n_levels - 1;
+        const float radius = th * scale_factors[oct];
+        const int min_level = oct - 1, max_level = oct + 1;
+        int best_dist = 256, best_idx = -1;
+        for (int j = 0; j < nt; ++j) {
+            const float distx = t_kp[j].x - q_uv[2 * i], disty = t_kp[j].y - q_uv[2 * i + 1];
+            if (!(fabsf(distx) < radius && fabsf(disty) < radius)) continue;
+            if (t_kp[j].octave < min_level || t_kp[j].octave > max_level) continue;
+            const int dist = hamming256(q_desc + 32 * (size_t)i, t_desc + 32 * (size_t)j);
+            if (dist < best_dist) { best_dist = dist; best_idx = j; }
+        }
+        if (best_idx >= 0 && best_dist <= th_high) {
+            out_idx[i] = best_idx;
+            out_dist[i] = best_dist;
+        }
+    }
+    int n = 0;
+    int keep[HISTO_LENGTH];
+    for (int b = 0; b < HISTO_LENGTH; ++b) keep[b] = 1;
+    int *bins = 0;
+    if (check_orientation) {
+        bins = (int *)malloc(sizeof(int) * (size_t)(nq > 0 ? nq : 1));
+        for (int i = 0; i < nq; ++i) {
+            if (out_idx[i] < 0) continue;
+            float rot = q_kp[i].angle - t_kp[out_idx[i]].angle;
+            if (rot < 0.0) rot += 360.0f;
+            int bin = (int)round(rot * factor);
+            if (bin == HISTO_LENGTH) bin = 0;
+            bins[i] = bin;
+            hist[bin]++;
+        }
+        int max1 = 0, max2 = 0, max3 = 0, ind1 = -1, ind2 = -1, ind3 = -1;
+        for (int b = 0; b < HISTO_LENGTH; ++b) {
+            const int s = hist[b];
+            if (s > max1) { max3 = max2; max2 = max1; max1 = s; ind3 = ind2; ind2 = ind1; ind1 = b; }
+            else if (s > max2) { max3 = max2; max2 = s; ind3 = ind2; ind2 = b; }
+            else if (s > max3) { max3 = s; ind3 = b; }
+        }
+        if (max2 < 0.1f * (float)max1) { ind2 = -1; ind3 = -1; }
+        else if (max3 < 0.1f * (float)max1) { ind3 = -1; }
+        for (int b = 0; b < HISTO_LENGTH; ++b) keep[b] = (b == ind1 || b == ind2 || b == ind3);
+    }
+    for (int i = 0; i < nq; ++i) {
+        if (out_idx[i] < 0) continue;
+        if (check_orientation && !keep[bins[i]]) { out_idx[i] = -1; out_dist[i] = -1; }
+        else ++n;
+    }
+    free(bins);
+    return n;
 }

@@ -271,3 +271,50 @@ def test_rgb_to_grayscale(orbb, oracle, w, h):
     got = d_gray.cpu().numpy()
     for i in range(n):
         assert np.array_equal(got[i], oracle.rgb_to_grayscale(rgb[i])), f"frame {i}"
+
+
+@pytest.mark.parametrize("check", [False, True])
+def test_match_projection_batch(orbb, oracle, synth, check):
+    """ORB-SLAM2 SearchByProjection gates on real keypoints of a translating sequence: frame f -> frame f+1, projected
+    positions = reprojected 3-D points; per-frame results equal the oracle (idx, dist, survivor count)."""
+    import torch
+    n, w, h = 4, 640, 480
+    base = synth.textured_frame(w, h, 777)
+    gray = [base]
+    for i in range(n):
+        gray.append(synth.shifted_frame(gray[-1], 3, 2, 900 + i))
+    gray = np.stack(gray)
+    ex = orbb.ORBextractor(800, 1.2, 8, 20, 7, width=w, height=h, max_batch=n + 1)
+    mk = ex.max_kp
+    st = torch.cuda.current_stream()
+    d_frames = torch.from_numpy(gray).cuda()
+    d_kp = torch.zeros((n + 1, mk, 7), dtype=torch.float32, device="cuda")
+    d_desc = torch.zeros((n + 1, mk, 32), dtype=torch.uint8, device="cuda")
+    d_cnt = torch.zeros(n + 1, dtype=torch.int32, device="cuda")
+    ex.extract_batch_device(d_frames, n + 1, d_kp, d_desc, d_cnt, stream=st)
+    # projected positions: the previous keypoint moved by the known shift + a little noise (stands in for the
+    # reprojection of its 3-D point)
+    torch.cuda.synchronize()
+    kp = d_kp.cpu().numpy().view(orbb.KEYPOINT_DTYPE).reshape(n + 1, mk)
+    desc = d_desc.cpu().numpy(); cnt = d_cnt.cpu().numpy()
+    rng = np.random.default_rng(3)
+    uv = np.zeros((n, mk, 2), np.float32)
+    uv[..., 0] = kp[:n]["x"] + 3 + rng.normal(0, 1.5, (n, mk)); uv[..., 1] = kp[:n]["y"] + 2 + rng.normal(0, 1.5, (n, mk))
+    d_uv = torch.from_numpy(uv).cuda()
+    q_kp, q_desc, q_cnt = d_kp[:n].contiguous(), d_desc[:n].contiguous(), d_cnt[:n].contiguous()
+    t_kp, t_desc, t_cnt = d_kp[1:].contiguous(), d_desc[1:].contiguous(), d_cnt[1:].contiguous()
+    d_idx = torch.full((n, mk), -9, dtype=torch.int32, device="cuda"); d_dist = torch.full_like(d_idx, -9)
+    d_nm = torch.zeros(n, dtype=torch.int32, device="cuda")
+    ex.match_keypoints_projection_batch(q_desc, d_uv, q_kp, q_cnt, t_desc, t_kp, t_cnt, n, 7.0, 100, check, d_idx, d_dist,
+                                        d_nm, stream=st)
+    torch.cuda.synchronize()
+    idx, dist, nm = d_idx.cpu().numpy(), d_dist.cpu().numpy(), d_nm.cpu().numpy()
+    sf = ex.GetScaleFactors()
+    total = 0
+    for f in range(n):
+        a, b = int(cnt[f]), int(cnt[f + 1])
+        oidx, odist, onm = oracle.search_by_projection(desc[f, :a], uv[f, :a], kp[f, :a], desc[f + 1, :b], kp[f + 1, :b], sf,
+                                                       7.0, 100, check)
+        assert np.array_equal(idx[f, :a], oidx) and np.array_equal(dist[f, :a], odist) and int(nm[f]) == onm, f"frame {f}"
+        total += onm
+    assert total > 400, f"test too weak: {total} matches"

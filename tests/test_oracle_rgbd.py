@@ -242,3 +242,65 @@ def test_points_and_reprojection_match_numpy(oracle):
     db = b + f32(2) * k32[3] * a * b + k32[2] * (r2 + f32(2) * b * b)
     ref = np.stack([da * f32(cam.fx) + f32(cam.ppx), db * f32(cam.fy) + f32(cam.ppy)], 1)
     assert np.array_equal(pos.view(np.uint32), ref.astype(f32).view(np.uint32))
+
+
+def _np_search_by_projection(q_desc, q_uv, q_kp, t_desc, t_kp, sf, th, th_high, check):
+    """Vectorised numpy restatement of ORBmatcher::SearchByProjection's front-end gates + ComputeThreeMaxima."""
+    nq = len(q_desc)
+    lut = np.array([bin(i).count("1") for i in range(256)], np.int32)
+    dist = lut[q_desc[:, None, :] ^ t_desc[None, :, :]].sum(2)
+    radius = (np.float32(th) * sf[np.clip(q_kp["octave"], 0, len(sf) - 1)]).astype(np.float32)
+    dx = np.abs(t_kp["x"][None, :] - q_uv[:, 0:1]); dy = np.abs(t_kp["y"][None, :] - q_uv[:, 1:2])
+    oq = np.clip(q_kp["octave"], 0, len(sf) - 1)[:, None]; ot = t_kp["octave"][None, :]
+    ok = (dx < radius[:, None]) & (dy < radius[:, None]) & (ot >= oq - 1) & (ot <= oq + 1)
+    d = np.where(ok, dist, 10 ** 6)
+    idx = d.argmin(1).astype(np.int32)  # first minimum = lowest train index
+    best = d[np.arange(nq), idx]
+    good = best <= th_high
+    idx = np.where(good, idx, -1).astype(np.int32); best = np.where(good, best, -1).astype(np.int32)
+    if check:
+        rot = (q_kp["angle"] - t_kp["angle"][np.maximum(idx, 0)]).astype(np.float32)
+        rot = np.where(rot < 0, rot + np.float32(360), rot).astype(np.float32)
+        x = (rot * np.float32(1.0 / 30)).astype(np.float64)
+        bins = (np.sign(x) * np.floor(np.abs(x) + 0.5)).astype(np.int64)  # C round(): half away from zero
+        bins[bins == 30] = 0
+        hist = np.bincount(bins[idx >= 0], minlength=30)
+        m = [0, 0, 0]; ind = [-1, -1, -1]
+        for b in range(30):
+            s = int(hist[b])
+            if s > m[0]:
+                m = [s, m[0], m[1]]; ind = [b, ind[0], ind[1]]
+            elif s > m[1]:
+                m = [m[0], s, m[1]]; ind = [ind[0], b, ind[1]]
+            elif s > m[2]:
+                m[2] = s; ind[2] = b
+        if np.float32(m[1]) < np.float32(0.1) * np.float32(m[0]):
+            ind[1] = ind[2] = -1
+        elif np.float32(m[2]) < np.float32(0.1) * np.float32(m[0]):
+            ind[2] = -1
+        drop = (idx >= 0) & ~np.isin(bins, [i for i in ind if i >= 0])
+        idx[drop] = -1; best[drop] = -1
+    return idx, best, int((idx >= 0).sum())
+
+
+@pytest.mark.parametrize("check", [False, True])
+def test_search_by_projection_matches_numpy(oracle, check):
+    rng = np.random.default_rng(17)
+    nq, nt, nl = 300, 350, 8
+    sf = (np.float32(1.2) ** np.arange(nl)).astype(np.float32)
+    t_kp = np.zeros(nt, oracle.KEYPOINT_DTYPE)
+    t_kp["x"] = rng.uniform(20, 620, nt).astype(np.float32); t_kp["y"] = rng.uniform(20, 460, nt).astype(np.float32)
+    t_kp["octave"] = rng.integers(0, nl, nt); t_kp["angle"] = rng.uniform(0, 360, nt).astype(np.float32)
+    t_desc = rng.integers(0, 256, (nt, 32)).astype(np.uint8)
+    src = rng.integers(0, nt, nq)  # every query is a noisy copy of some train keypoint
+    q_kp = t_kp[src].copy()
+    q_kp["octave"] = np.clip(q_kp["octave"] + rng.integers(-2, 3, nq), 0, nl - 1)
+    q_kp["angle"] = np.mod(q_kp["angle"] + np.where(rng.random(nq) < 0.7, 12.0, rng.uniform(0, 360, nq)), 360).astype(np.float32)
+    q_uv = np.stack([t_kp["x"][src] + rng.normal(0, 6, nq), t_kp["y"][src] + rng.normal(0, 6, nq)], 1).astype(np.float32)
+    q_desc = t_desc[src] ^ (rng.random((nq, 32)) < 0.25).astype(np.uint8) * rng.integers(0, 256, (nq, 32)).astype(np.uint8)
+    got = oracle.search_by_projection(q_desc, q_uv, q_kp, t_desc, t_kp, sf, 7.0, 100, check)
+    ref = _np_search_by_projection(q_desc, q_uv, q_kp, t_desc, t_kp, sf, 7.0, 100, check)
+    assert np.array_equal(got[0], ref[0]) and np.array_equal(got[1], ref[1]) and got[2] == ref[2]
+    assert 40 < got[2] < nq
+    if check:
+        assert got[2] < oracle.search_by_projection(q_desc, q_uv, q_kp, t_desc, t_kp, sf, 7.0, 100, False)[2]
