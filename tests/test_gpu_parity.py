@@ -513,3 +513,29 @@ def test_cuda_graph_replay_opt_in(orbb, oracle, synth, monkeypatch):
                 assert len(gkp) == len(okp)
                 assert np.array_equal(gkp.view(np.uint8), okp.view(np.uint8)) and np.array_equal(gdesc, odesc)
     assert ex.launch_count() - l0 == 15 * 10  # replays are counted like direct launches: level0 + 5 resizes + 4
+
+
+@pytest.mark.parametrize("nb", [64, 71, 130])
+def test_large_batch_paths_equal_single_frame(orbb, synth, nb):
+    """Batches >= 64 frames take the multi-stream split with the throughput variants of the kernels (large-grid
+    quadtree kernel, two batch parts); a single frame takes the small-grid variants (shared-memory per-key arrays,
+    batched loads).  Both must give the same bytes, in the same order."""
+    import torch
+    w, h = 320, 240
+    base = [synth.textured_frame(w, h, 300 + i) for i in range(6)] + [synth.sparse_frame(w, h, 9), synth.low_contrast_frame(w, h, 4)]
+    frames = np.stack([np.roll(base[i % 8], (3 * (i // 8), 5 * (i // 8)), axis=(0, 1)) for i in range(nb)])
+    ex = orbb.ORBextractor(500, 1.2, 8, 20, 7, width=w, height=h, max_batch=nb)
+    st = torch.cuda.current_stream()
+    d_in = torch.from_numpy(frames).cuda()
+    d_kp = torch.zeros((nb, ex.max_kp, 7), dtype=torch.float32, device="cuda")
+    d_desc = torch.zeros((nb, ex.max_kp, 32), dtype=torch.uint8, device="cuda")
+    d_cnt = torch.zeros(nb, dtype=torch.int32, device="cuda")
+    ex.extract_batch_device(d_in, nb, d_kp, d_desc, d_cnt, stream=st)
+    torch.cuda.synchronize()
+    kp = d_kp.cpu().numpy().view(orbb.KEYPOINT_DTYPE).reshape(nb, ex.max_kp); desc = d_desc.cpu().numpy(); cnt = d_cnt.cpu().numpy()
+    one = orbb.ORBextractor(500, 1.2, 8, 20, 7, width=w, height=h, max_batch=1)
+    for f in list(range(0, nb, 9)) + [nb - 1]:
+        k1, d1 = one(frames[f])
+        n = int(cnt[f])
+        assert len(k1) == n and k1.tobytes() == kp[f, :n].tobytes() and d1.tobytes() == desc[f, :n].tobytes(), f"frame {f}"
+    ex.close(); one.close()
