@@ -261,6 +261,17 @@ int orbb_match_projection_batch(orbb_handle *h, const uint8_t *d_query_desc, con
                                 float th, int th_high, int check_orientation, int32_t *d_idx, int32_t *d_dist,
                                 int32_t *d_nmatched, void *cuda_stream);
 
+/* Stereo association of rectified pairs with ORB-SLAM2 Frame::ComputeStereoMatches semantics (SURVEY.md 8f-3;
+ * upstream raulmur/ORB_SLAM2 src/Frame.cc, un-vendored; the reference has no stereo path).  The pairs are the frames
+ * (2p, 2p+1) = (left, right) of the batch last extracted with this handle -- their pyramids must still be resident --
+ * and d_kp / d_desc / d_counts are that extraction's outputs.  Per LEFT keypoint: d_uright and d_depth
+ * ([n_pairs][max_kp] float, -1 when there is no stereo match; depth = bf / disparity), d_nstereo [n_pairs] matches
+ * surviving the median-SAD filter.  bf = fx * baseline (upstream mbf).  Row band, octave band, TH_HIGH / thOrbDist,
+ * 11x11 SAD sub-pixel search and parabola fit as upstream.  Async on stream. */
+int orbb_compute_stereo_matches(orbb_handle *h, const orbb_keypoint *d_kp, const uint8_t *d_desc, const int32_t *d_counts,
+                                int max_kp, int n_pairs, float bf, float fx, float *d_uright, float *d_depth,
+                                int32_t *d_nstereo, void *cuda_stream);
+
 /* Jetracer::rgb_to_grayscale (src/cuda/cuda_RGB_to_Grayscale.cuh, kernel cuda_RGB_to_Grayscale.cu:10-24, call site
  * buildStream.cpp:416-422) for a batch: gray = floor((B*0.07 + G*0.72 + R*0.21) + 0.5) in float64, every operation
  * rounded on its own, interleaved RGB8 in.  DEVICE pointers; rgb_pitch must be a multiple of 4.  Async on stream.

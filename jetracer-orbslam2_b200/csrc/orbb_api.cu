@@ -43,6 +43,8 @@ cudaError_t launch_compact_pairs(const int *, const int *, int, int, const doubl
 cudaError_t launch_match_projection(const uint8_t *, const float *, const orbb_keypoint *, const int *, const uint8_t *,
                                     const orbb_keypoint *, const int *, int, int, float, int, int, const float *, int, int *, int *,
                                     int *, cudaStream_t);
+cudaError_t launch_stereo(const LevelDev *, const float *, const float *, int, const orbb_keypoint *, const uint8_t *, const int *,
+                          int, int, float, float, float *, float *, int *, int *, cudaStream_t);
 cudaError_t launch_rgb_to_gray(const uint8_t *, size_t, size_t, int, int, int, uint8_t *, size_t, size_t, cudaStream_t);
 cudaError_t launch_match_windowed_batch(const uint8_t *, const void *, int, const int *, const uint8_t *, const void *, int,
                                         const int *, int, int, float, int, int *, int *, cudaStream_t);
@@ -73,6 +75,8 @@ struct orbb_handle {
     int n_slots = 0, sel_cap_max = 0, pcap = 0, pcap2 = 0, max_kp = 0;
     int4 *d_partial = nullptr;
     size_t partial_cap = 0;
+    int *d_stereo_sad = nullptr;  // SAD cost per left keypoint (stereo matcher scratch), grows on demand
+    size_t stereo_cap = 0;
     // staging of the *_host entry points, double-buffered so consecutive batches overlap
     uint8_t *d_in2[2] = {nullptr, nullptr};
     orbb_keypoint *d_kp2[2] = {nullptr, nullptr};
@@ -955,6 +959,28 @@ extern "C" int orbb_match_projection_batch(orbb_handle *h, const uint8_t *d_quer
     CK(h, launch_match_projection(d_query_desc, d_query_uv, d_query_kp, d_q_counts, d_train_desc, d_train_kp, d_t_counts,
                                   n_frames, max_kp, th, std::min(th_high, 256), check_orientation, h->sf, h->nlevels, d_idx,
                                   d_dist, d_nmatched, static_cast<cudaStream_t>(stream)));
+    h->n_launches += 2;
+    return ORBB_OK;
+}
+
+extern "C" int orbb_compute_stereo_matches(orbb_handle *h, const orbb_keypoint *d_kp, const uint8_t *d_desc,
+                                           const int32_t *d_counts, int max_kp, int n_pairs, float bf, float fx,
+                                           float *d_uright, float *d_depth, int32_t *d_nstereo, void *stream) {
+    if (!h || !d_kp || !d_desc || !d_counts || !d_uright || !d_depth || max_kp < 1 || n_pairs < 1 || !(bf > 0.0f) ||
+        !(fx > 0.0f))
+        return ORBB_ERR_INVALID;
+    if (2 * n_pairs > h->n_frames_last) return ORBB_ERR_CAPACITY;  // the pairs' pyramids must be resident
+    if (reinterpret_cast<uintptr_t>(d_desc) & 15) return ORBB_ERR_INVALID;
+    CK(h, cudaSetDevice(h->device));
+    const size_t need = (size_t)n_pairs * max_kp;
+    if (need > h->stereo_cap) {
+        int *p = nullptr;
+        CK(h, dalloc(h, &p, need));  // grows monotonically; released in orbb_destroy
+        h->d_stereo_sad = p;
+        h->stereo_cap = need;
+    }
+    CK(h, launch_stereo(h->d_levels, h->sf, h->inv_sf, h->nlevels, d_kp, d_desc, d_counts, max_kp, n_pairs, bf, fx, d_uright,
+                        d_depth, h->d_stereo_sad, d_nstereo, static_cast<cudaStream_t>(stream)));
     h->n_launches += 2;
     return ORBB_OK;
 }

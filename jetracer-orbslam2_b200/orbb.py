@@ -36,7 +36,7 @@ EXPORTS = [
     "orbb_match_knn_segmented", "orbb_match_windowed", "orbb_debug_get_padded", "orbb_debug_get_blurred", "orbb_debug_get_scores",
     "orbb_debug_get_candidates", "orbb_debug_get_selected", "orbb_debug_distribute",
     "orbb_align_depth_to_other", "orbb_keypoint_pixel_to_point", "orbb_reproject_points", "orbb_match_windowed_batch",
-    "orbb_rgb_to_grayscale", "orbb_match_projection_batch",
+    "orbb_rgb_to_grayscale", "orbb_match_projection_batch", "orbb_compute_stereo_matches",
     "orbb_rgbd_stage_create", "orbb_rgbd_stage_destroy", "orbb_rgbd_stage_reset", "orbb_rgbd_stage_handle",
     "orbb_rgbd_stage_submit", "orbb_rgbd_stage_wait",
 ]
@@ -146,6 +146,7 @@ def load_library():
     L.orbb_match_windowed_batch.argtypes = [vp, vp, vp, vp, vp, vp, i32, vp, i32, i32, f32, i32, vp, vp, vp, vp, vp, vp,
                                             vp, vp, vp]
     L.orbb_match_projection_batch.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, f32, i32, i32, vp, vp, vp, vp]
+    L.orbb_compute_stereo_matches.argtypes = [vp, vp, vp, vp, i32, i32, f32, f32, vp, vp, vp, vp]
     L.orbb_rgb_to_grayscale.argtypes = [vp, vp, sz, sz, i32, i32, i32, vp, sz, sz, vp]
     L.orbb_rgbd_stage_create.argtypes = [C.POINTER(vp), C.POINTER(RgbdConfig), i32]
     L.orbb_rgbd_stage_destroy.argtypes = [vp]
@@ -399,6 +400,13 @@ class ORBextractor:
             _dev_ptr(d_train_desc), _dev_ptr(d_train_kp), _dev_ptr(d_t_counts), n, self.max_kp, th, th_high,
             int(check_orientation), _dev_ptr(d_idx), _dev_ptr(d_dist),
             _dev_ptr(d_nmatched) if d_nmatched is not None else C.c_void_p(0), _stream_ptr(stream)))
+
+    def compute_stereo_matches(self, d_kp, d_desc, d_counts, n_pairs: int, bf: float, fx: float, d_uright, d_depth,
+                               d_nstereo=None, stream=None):
+        """ORB-SLAM2 Frame::ComputeStereoMatches on the (2p, 2p+1) frames of the batch extracted last."""
+        self._check(self._lib.orbb_compute_stereo_matches(
+            self._h, _dev_ptr(d_kp), _dev_ptr(d_desc), _dev_ptr(d_counts), self.max_kp, n_pairs, bf, fx, _dev_ptr(d_uright),
+            _dev_ptr(d_depth), _dev_ptr(d_nstereo) if d_nstereo is not None else C.c_void_p(0), _stream_ptr(stream)))
 
     # -- parity / debug access --------------------------------------------------------------
     def debug_padded(self, level: int, frame: int = 0) -> np.ndarray:

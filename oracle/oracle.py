@@ -120,6 +120,8 @@ def lib(native: bool = False):
     L.orbo_compact_pairs.restype = C.c_int
     L.orbo_search_by_projection.argtypes = [vp, vp, vp, C.c_int, vp, vp, C.c_int, vp, C.c_int, C.c_float, C.c_int, C.c_int, vp, vp]
     L.orbo_search_by_projection.restype = C.c_int
+    L.orbo_compute_stereo_matches.argtypes = [vp, vp, vp, vp, C.c_int, vp, vp, C.c_int, C.c_float, C.c_float, vp, vp]
+    L.orbo_compute_stereo_matches.restype = C.c_int
     L.orbo_rgb_to_grayscale.argtypes = [vp, C.c_size_t, C.c_int, C.c_int, vp, C.c_size_t]
     L.orbo_rgb_to_grayscale.restype = None
     del u8p, i32p, f32p
@@ -375,3 +377,13 @@ def search_by_projection(q_desc, q_uv, q_kp, t_desc, t_kp, scale_factors, th: fl
     n = lib().orbo_search_by_projection(_p(q_desc), _p(q_uv), _p(q_kp), nq, _p(t_desc), _p(t_kp), t_desc.shape[0], _p(sf),
                                         sf.shape[0], th, th_high, int(check_orientation), _p(idx), _p(dist))
     return idx[:nq].copy(), dist[:nq].copy(), int(n)
+
+
+def compute_stereo_matches(left: "Oracle", right: "Oracle", kl, dl, kr, dr, bf: float, fx: float):
+    """Frame::ComputeStereoMatches on two Oracle objects whose pyramids hold the rectified pair."""
+    kl = np.ascontiguousarray(kl, KEYPOINT_DTYPE); kr = np.ascontiguousarray(kr, KEYPOINT_DTYPE)
+    dl = np.ascontiguousarray(dl, np.uint8).reshape(-1, 32); dr = np.ascontiguousarray(dr, np.uint8).reshape(-1, 32)
+    ur = np.full(max(len(kl), 1), -1, np.float32)
+    z = np.full(max(len(kl), 1), -1, np.float32)
+    n = lib().orbo_compute_stereo_matches(left._h, right._h, _p(kl), _p(dl), len(kl), _p(kr), _p(dr), len(kr), bf, fx, _p(ur), _p(z))
+    return ur[:len(kl)].copy(), z[:len(kl)].copy(), int(n)

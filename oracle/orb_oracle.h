@@ -138,6 +138,9 @@ int orbo_search_by_projection(const uint8_t *q_desc, const float *q_uv, const or
                               const uint8_t *t_desc, const orbo_keypoint *t_kp, int nt, const float *scale_factors,
                               int n_levels, float th, int th_high, int check_orientation, int32_t *out_idx,
                               int32_t *out_dist);
+int orbo_compute_stereo_matches(orbo_ctx *left, orbo_ctx *right, const orbo_keypoint *kl, const uint8_t *dl, int n_left,
+                                const orbo_keypoint *kr, const uint8_t *dr, int n_right, float mbf, float fx, float *uright,
+                                float *depth);
 void orbo_rgb_to_grayscale(const uint8_t *src, size_t src_pitch, int cols, int rows, uint8_t *dst, size_t dst_pitch);
 int orbo_compact_pairs(const int32_t *idx, int nq, const double *q_points, const double *t_points, const float *t_xy,
                        int t_xy_stride_floats, double *prev_out, double *curr_out, uint16_t *x_out, uint16_t *y_out);

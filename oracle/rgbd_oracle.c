@@ -276,3 +276,119 @@ int orbo_search_by_projection(const uint8_t *q_desc, const float *q_uv, const or
     free(bins);
     return n;
 }
+
+/* ORB-SLAM2 Frame::ComputeStereoMatches (upstream raulmur/ORB_SLAM2 src/Frame.cc, not vendored by the reference, no
+ * version pin): restated from the published algorithm.  left / right are oracle contexts whose pyramids hold the two
+ * rectified images (orbo_extract or orbo_compute_pyramid was called on them); the keypoints / descriptors are passed
+ * explicitly so that any ordering can be checked.  uright / depth: one float per left keypoint, -1 = no match.
+ * Returns the number of matches left after the median-SAD filter. */
+typedef struct { int dist, idx; } sad_idx;
+static int cmp_sad_idx(const void *a, const void *b) {
+    const sad_idx *x = (const sad_idx *)a, *y = (const sad_idx *)b;
+    if (x->dist != y->dist) return x->dist < y->dist ? -1 : 1;
+    return x->idx < y->idx ? -1 : (x->idx > y->idx);
+}
+
+int orbo_compute_stereo_matches(orbo_ctx *left, orbo_ctx *right, const orbo_keypoint *kl, const uint8_t *dl, int n_left,
+                                const orbo_keypoint *kr, const uint8_t *dr, int n_right, float mbf, float fx, float *uright,
+                                float *depth) {
+    enum { TH_HIGH = 100, TH_LOW = 50 };
+    const int nlev = orbo_nlevels(left);
+    int32_t lw[ORBO_MAX_LEVELS], lh[ORBO_MAX_LEVELS], nf[ORBO_MAX_LEVELS];
+    float sf[ORBO_MAX_LEVELS], isf[ORBO_MAX_LEVELS];
+    orbo_get_geometry(left, lw, lh, sf, isf, nf);
+    const int thOrbDist = (TH_HIGH + TH_LOW) / 2;
+    const float mb = mbf / fx;
+    const float minZ = mb, minD = 0, maxD = mbf / minZ;
+    int *minr = (int *)malloc(sizeof(int) * (size_t)(n_right > 0 ? n_right : 1));
+    int *maxr = (int *)malloc(sizeof(int) * (size_t)(n_right > 0 ? n_right : 1));
+    for (int iR = 0; iR < n_right; ++iR) {
+        const float kpY = kr[iR].y;
+        const float r = 2.0f * sf[kr[iR].octave];
+        maxr[iR] = (int)ceil(kpY + r);
+        minr[iR] = (int)floor(kpY - r);
+    }
+    sad_idx *vDistIdx = (sad_idx *)malloc(sizeof(sad_idx) * (size_t)(n_left > 0 ? n_left : 1));
+    int nmatch = 0;
+    for (int iL = 0; iL < n_left; ++iL) {
+        uright[iL] = -1.0f;
+        depth[iL] = -1.0f;
+        const int levelL = kl[iL].octave;
+        const float vL = kl[iL].y, uL = kl[iL].x;
+        const int row = (int)vL;
+        const float minU = uL - maxD, maxU = uL - minD;
+        if (maxU < 0) continue;
+        int bestDist = TH_HIGH, bestIdxR = -1;
+        for (int iR = 0; iR < n_right; ++iR) {
+            if (row < minr[iR] || row > maxr[iR]) continue; /* vRowIndices[vL] membership */
+            if (kr[iR].octave < levelL - 1 || kr[iR].octave > levelL + 1) continue;
+            const float uR = kr[iR].x;
+            if (uR >= minU && uR <= maxU) {
+                const int dist = hamming256(dl + 32 * (size_t)iL, dr + 32 * (size_t)iR);
+                if (dist < bestDist) { bestDist = dist; bestIdxR = iR; }
+            }
+        }
+        if (bestIdxR < 0 || !(bestDist < thOrbDist)) continue;
+        const float uR0 = kr[bestIdxR].x;
+        const float scaleFactor = isf[levelL];
+        const float scaleduL = round(kl[iL].x * scaleFactor);
+        const float scaledvL = round(kl[iL].y * scaleFactor);
+        const float scaleduR0 = round(uR0 * scaleFactor);
+        const int w = 5, L = 5;
+        int pw, ph;
+        size_t pl, pr;
+        const uint8_t *imL = orbo_level_padded(left, levelL, &pw, &ph, &pl) + (size_t)ORBO_EDGE_THRESHOLD * pl + ORBO_EDGE_THRESHOLD;
+        const uint8_t *imR = orbo_level_padded(right, levelL, &pw, &ph, &pr) + (size_t)ORBO_EDGE_THRESHOLD * pr + ORBO_EDGE_THRESHOLD;
+        const int cols = lw[levelL];
+        int bestSad = INT32_MAX, bestincR = 0;
+        float vDists[11];
+        const float iniu = scaleduR0 + L - w, endu = scaleduR0 + L + w + 1;
+        if (iniu < 0 || endu >= cols) continue;
+        const int xl = (int)scaleduL, yl = (int)scaledvL, xr = (int)scaleduR0;
+        const float centerL = imL[(ptrdiff_t)yl * (ptrdiff_t)pl + xl];
+        for (int incR = -L; incR <= +L; ++incR) {
+            const float centerR = imR[(ptrdiff_t)yl * (ptrdiff_t)pr + xr + incR];
+            float dist = 0; /* cv::norm(IL, IR, NORM_L1) of the centre-subtracted float patches: exact integers */
+            for (int dy = -w; dy <= w; ++dy)
+                for (int dx = -w; dx <= w; ++dx) {
+                    const float a = (float)imL[(ptrdiff_t)(yl + dy) * (ptrdiff_t)pl + xl + dx] - centerL;
+                    const float b = (float)imR[(ptrdiff_t)(yl + dy) * (ptrdiff_t)pr + xr + incR + dx] - centerR;
+                    dist += fabsf(a - b);
+                }
+            if (dist < bestSad) { bestSad = (int)dist; bestincR = incR; }
+            vDists[L + incR] = dist;
+        }
+        if (bestincR == -L || bestincR == L) continue;
+        const float dist1 = vDists[L + bestincR - 1], dist2 = vDists[L + bestincR], dist3 = vDists[L + bestincR + 1];
+        const float deltaR = (dist1 - dist3) / (2.0f * (dist1 + dist3 - 2.0f * dist2));
+        if (deltaR < -1 || deltaR > 1) continue;
+        float bestuR = sf[levelL] * ((float)scaleduR0 + (float)bestincR + deltaR);
+        float disparity = (uL - bestuR);
+        if (disparity >= minD && disparity < maxD) {
+            if (disparity <= 0) {
+                disparity = 0.01;
+                bestuR = uL - 0.01;
+            }
+            depth[iL] = mbf / disparity;
+            uright[iL] = bestuR;
+            vDistIdx[nmatch].dist = bestSad;
+            vDistIdx[nmatch].idx = iL;
+            ++nmatch;
+        }
+    }
+    int kept = nmatch;
+    if (nmatch > 0) {
+        qsort(vDistIdx, (size_t)nmatch, sizeof(sad_idx), cmp_sad_idx);
+        const float median = vDistIdx[nmatch / 2].dist;
+        const float thDist = 1.5f * 1.4f * median;
+        for (int i = nmatch - 1; i >= 0; --i) {
+            if (vDistIdx[i].dist < thDist) break;
+            uright[vDistIdx[i].idx] = -1;
+            depth[vDistIdx[i].idx] = -1;
+            --kept;
+        }
+    }
+    free(minr); free(maxr); free(vDistIdx);
+    (void)nlev; (void)lh; (void)nf;
+    return kept;
+}

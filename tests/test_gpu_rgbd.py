@@ -318,3 +318,42 @@ def test_match_projection_batch(orbb, oracle, synth, check):
         assert np.array_equal(idx[f, :a], oidx) and np.array_equal(dist[f, :a], odist) and int(nm[f]) == onm, f"frame {f}"
         total += onm
     assert total > 400, f"test too weak: {total} matches"
+
+
+def test_compute_stereo_matches(orbb, oracle, synth):
+    """Frame::ComputeStereoMatches over a batch of rectified pairs (left = frame 2p, right = 2p+1): uRight, depth and
+    the surviving-match count are bit-exact against the oracle fed with the GPU extractor's own keypoint order."""
+    import torch
+    w, h, npairs = 640, 480, 3
+    frames = []
+    for p in range(npairs):
+        left = synth.textured_frame(w, h, 40 + p)
+        frames += [left, synth.shifted_frame(left, -(7 + 5 * p), 0, 60 + p)]
+    frames = np.stack(frames)
+    ex = orbb.ORBextractor(1000, 1.2, 8, 20, 7, width=w, height=h, max_batch=2 * npairs)
+    mk = ex.max_kp
+    st = torch.cuda.current_stream()
+    d_in = torch.from_numpy(frames).cuda()
+    d_kp = torch.zeros((2 * npairs, mk, 7), dtype=torch.float32, device="cuda")
+    d_desc = torch.zeros((2 * npairs, mk, 32), dtype=torch.uint8, device="cuda")
+    d_cnt = torch.zeros(2 * npairs, dtype=torch.int32, device="cuda")
+    ex.extract_batch_device(d_in, 2 * npairs, d_kp, d_desc, d_cnt, stream=st)
+    d_ur = torch.full((npairs, mk), -7.0, dtype=torch.float32, device="cuda"); d_z = torch.full_like(d_ur, -7.0)
+    d_ns = torch.zeros(npairs, dtype=torch.int32, device="cuda")
+    bf, fx = 40.0, 400.0
+    ex.compute_stereo_matches(d_kp, d_desc, d_cnt, npairs, bf, fx, d_ur, d_z, d_ns, stream=st)
+    torch.cuda.synchronize()
+    kp = d_kp.cpu().numpy().view(orbb.KEYPOINT_DTYPE).reshape(2 * npairs, mk); desc = d_desc.cpu().numpy(); cnt = d_cnt.cpu().numpy()
+    ur, z, ns = d_ur.cpu().numpy(), d_z.cpu().numpy(), d_ns.cpu().numpy()
+    for p in range(npairs):
+        ol, orr = oracle.Oracle(w, h, 1000), oracle.Oracle(w, h, 1000)
+        ol.compute_pyramid(frames[2 * p]); orr.compute_pyramid(frames[2 * p + 1])
+        a, b = int(cnt[2 * p]), int(cnt[2 * p + 1])
+        our, oz, on = oracle.compute_stereo_matches(ol, orr, kp[2 * p, :a], desc[2 * p, :a], kp[2 * p + 1, :b], desc[2 * p + 1, :b], bf, fx)
+        assert int(ns[p]) == on and on > 300, (p, int(ns[p]), on)
+        assert np.array_equal(ur[p, :a].view(np.uint32), our.view(np.uint32)), f"pair {p}: uRight"
+        assert np.array_equal(z[p, :a].view(np.uint32), oz.view(np.uint32)), f"pair {p}: depth"
+        m = our >= 0
+        assert abs(np.median(kp[2 * p, :a]["x"][m] - our[m]) - (7 + 5 * p)) < 0.15
+    with pytest.raises(orbb.OrbbError):
+        ex.compute_stereo_matches(d_kp, d_desc, d_cnt, npairs + 1, bf, fx, d_ur, d_z)  # more pairs than resident frames

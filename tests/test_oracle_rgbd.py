@@ -304,3 +304,82 @@ def test_search_by_projection_matches_numpy(oracle, check):
     assert 40 < got[2] < nq
     if check:
         assert got[2] < oracle.search_by_projection(q_desc, q_uv, q_kp, t_desc, t_kp, sf, 7.0, 100, False)[2]
+
+
+def _py_stereo(ol, orr, kl, dl, kr, dr, mbf, fx):
+    """Frame::ComputeStereoMatches restated with numpy float32 scalars / vector ops, independent of the C oracle
+    (which only supplies the two image pyramids)."""
+    f32 = np.float32
+    sf, isf = ol.scale, ol.inv_scale
+    lut = np.array([bin(i).count("1") for i in range(256)], np.int32)
+    mb = f32(mbf) / f32(fx); maxD = f32(mbf) / mb; minD = f32(0)
+    r = (f32(2.0) * sf[kr["octave"]]).astype(f32)
+    maxr = np.ceil((kr["y"] + r).astype(f32)).astype(np.int64); minr = np.floor((kr["y"] - r).astype(f32)).astype(np.int64)
+    ur = np.full(len(kl), -1, f32); z = np.full(len(kl), -1, f32)
+    found = []
+    for iL in range(len(kl)):
+        uL, vL, lev = kl["x"][iL], kl["y"][iL], int(kl["octave"][iL])
+        row = int(vL)
+        minU, maxU = f32(uL - maxD), f32(uL - minD)
+        if maxU < 0:
+            continue
+        cand = np.nonzero((minr <= row) & (row <= maxr) & (kr["octave"] >= lev - 1) & (kr["octave"] <= lev + 1) &
+                          (kr["x"] >= minU) & (kr["x"] <= maxU))[0]
+        if len(cand) == 0:
+            continue
+        d = lut[dl[iL][None, :] ^ dr[cand]].sum(1)
+        j = int(d.argmin())
+        if not (d[j] < 100 and d[j] < 75):
+            continue
+        uR0 = kr["x"][cand[j]]
+        su, sv, sr = (f32(np.sign(v) * np.floor(np.abs(np.float64(f32(a * isf[lev]))) + 0.5)) for v, a in
+                      ((uL, uL), (vL, vL), (uR0, uR0)))  # C round(): half away from zero
+        imL = ol.level_padded(lev).astype(np.int64); imR = orr.level_padded(lev).astype(np.int64)
+        cols = int(ol.lw[lev])
+        if sr + 5 - 5 < 0 or sr + 5 + 5 + 1 >= cols:
+            continue
+        xl, yl, xr = int(su) + 19, int(sv) + 19, int(sr) + 19
+        IL = imL[yl - 5:yl + 6, xl - 5:xl + 6] - imL[yl, xl]
+        dists = []
+        for inc in range(-5, 6):
+            IR = imR[yl - 5:yl + 6, xr + inc - 5:xr + inc + 6] - imR[yl, xr + inc]
+            dists.append(int(np.abs(IL - IR).sum()))
+        b = int(np.argmin(dists))  # first minimum, like the strict '<' scan
+        if b == 0 or b == 10:
+            continue
+        d1, d2, d3 = f32(dists[b - 1]), f32(dists[b]), f32(dists[b + 1])
+        with np.errstate(divide="ignore", invalid="ignore"):
+            delta = f32(f32(d1 - d3) / f32(f32(2.0) * f32(f32(d1 + d3) - f32(f32(2.0) * d2))))
+        if delta < -1 or delta > 1:
+            continue
+        best_u = f32(sf[lev] * f32(f32(sr + f32(b - 5)) + delta))
+        disp = f32(uL - best_u)
+        if disp >= minD and disp < maxD:
+            if disp <= 0:
+                disp = f32(0.01); best_u = f32(np.float64(uL) - 0.01)
+            z[iL] = f32(f32(mbf) / disp); ur[iL] = best_u
+            found.append((dists[b], iL))
+    if found:
+        found.sort()
+        th = f32(f32(f32(1.5) * f32(1.4)) * f32(found[len(found) // 2][0]))
+        for dist, iL in found:
+            if not (f32(dist) < th):
+                ur[iL] = -1; z[iL] = -1
+    return ur, z, int((ur >= 0).sum() if not found else sum(1 for dist, _ in found if f32(dist) < th))
+
+
+def test_stereo_matches_numpy_restatement_and_known_disparity(oracle, synth):
+    w, h = 320, 240
+    left = synth.textured_frame(w, h, 21)
+    right = synth.shifted_frame(left, -9, 0, 5)  # every scene point appears 9 px further left in the right image
+    ol, orr = oracle.Oracle(w, h, 400, 1.2, 6), oracle.Oracle(w, h, 400, 1.2, 6)
+    kl, dl = ol.extract(left); kr, dr = orr.extract(right)
+    bf, fx = 18.0, 200.0
+    ur, z, n = oracle.compute_stereo_matches(ol, orr, kl, dl, kr, dr, bf, fx)
+    rur, rz, rn = _py_stereo(ol, orr, kl, dl, kr, dr, bf, fx)
+    assert n == rn and np.array_equal(ur.view(np.uint32), rur.view(np.uint32)) and np.array_equal(z.view(np.uint32), rz.view(np.uint32))
+    m = ur >= 0
+    assert m.sum() == n and n > 100
+    disp = kl["x"][m] - ur[m]
+    assert np.abs(np.median(disp) - 9.0) < 0.1 and (np.abs(disp - 9.0) < 1.5).mean() > 0.9
+    assert np.allclose(z[m], bf / disp, rtol=1e-6)
