@@ -469,13 +469,11 @@ template <int OCT_RB, int MIN_CTAS>
 static cudaError_t launch_octree_t(const LevelDev *d_levels, int n_levels, const int *d_cand_count, int *d_sel_count,
                                    int level_base, int n_launch_levels, int frame_base, int n_frames, int quota_override,
                                    size_t smem, int sort_bytes, int pcap, int pcap2, cudaStream_t st) {
-    static size_t configured = 0;
     const int sort_off = (int)((smem + 15) & ~(size_t)15);
     const size_t total = (size_t)sort_off + (size_t)sort_bytes;
-    if (total > 32 * 1024 && total > configured) {
+    if (total > 30 * 1024) {  // 48 KB default limit minus the 18 KB of static shared memory; the attribute is per device
         cudaError_t e = cudaFuncSetAttribute(k_octree<OCT_RB, MIN_CTAS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)total);
         if (e != cudaSuccess) return e;
-        configured = total;
     }
     dim3 grid(n_launch_levels, n_frames);
     k_octree<OCT_RB, MIN_CTAS><<<grid, OCT_THREADS, total, st>>>(d_levels, n_levels, d_cand_count, d_sel_count, level_base,
