@@ -327,6 +327,17 @@ int orbb_rgbd_stage_submit(orbb_rgbd_stage *s, const uint8_t *h_gray, const uint
                            const double *h_T);
 int orbb_rgbd_stage_wait(orbb_rgbd_stage *s, int ticket, orbb_slam_frames *out);
 
+/* ---------------------------------------------------------------- wire format
+ * The BSON document the reference sends per processed frame (src/WebSocket/WebSocketCom.cpp:164-184, writer
+ * src/WebSocket/bson.cpp:46-130): int32 ax, ay, az, width, height, channels; binary (subtype 0x80) keypoints_x,
+ * keypoints_y (uint16 each, n_matched of them: orbb_slam_frames::matched_xy rows) and image (the caller's JPEG bytes,
+ * may be empty).  Host-only; byte-identical to the reference's Bson class.  orbb_slam_frame_bson_size gives the
+ * exact message size; orbb_slam_frame_to_bson returns the bytes written or a negative orbb_status. */
+size_t orbb_slam_frame_bson_size(int n_matched, size_t image_bytes);
+long long orbb_slam_frame_to_bson(int32_t ax, int32_t ay, int32_t az, int32_t width, int32_t height, int32_t channels,
+                                  const uint16_t *keypoints_x, const uint16_t *keypoints_y, int n_matched,
+                                  const uint8_t *image, size_t image_bytes, uint8_t *out, size_t out_capacity);
+
 /* ---------------------------------------------------------------- debug / parity access
  * Download stage outputs of frame `frame` of the last batch to HOST memory (synchronises). */
 /* padded level, contiguous (w+38) x (h+38) */

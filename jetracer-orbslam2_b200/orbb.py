@@ -37,6 +37,7 @@ EXPORTS = [
     "orbb_debug_get_candidates", "orbb_debug_get_selected", "orbb_debug_distribute",
     "orbb_align_depth_to_other", "orbb_keypoint_pixel_to_point", "orbb_reproject_points", "orbb_match_windowed_batch",
     "orbb_rgb_to_grayscale", "orbb_match_projection_batch", "orbb_compute_stereo_matches",
+    "orbb_slam_frame_bson_size", "orbb_slam_frame_to_bson",
     "orbb_rgbd_stage_create", "orbb_rgbd_stage_destroy", "orbb_rgbd_stage_reset", "orbb_rgbd_stage_handle",
     "orbb_rgbd_stage_submit", "orbb_rgbd_stage_wait",
 ]
@@ -148,6 +149,8 @@ def load_library():
     L.orbb_match_projection_batch.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, f32, i32, i32, vp, vp, vp, vp]
     L.orbb_compute_stereo_matches.argtypes = [vp, vp, vp, vp, i32, i32, f32, f32, vp, vp, vp, vp]
     L.orbb_rgb_to_grayscale.argtypes = [vp, vp, sz, sz, i32, i32, i32, vp, sz, sz, vp]
+    L.orbb_slam_frame_bson_size.argtypes = [i32, sz]
+    L.orbb_slam_frame_to_bson.argtypes = [i32, i32, i32, i32, i32, i32, vp, vp, i32, vp, sz, vp, sz]
     L.orbb_rgbd_stage_create.argtypes = [C.POINTER(vp), C.POINTER(RgbdConfig), i32]
     L.orbb_rgbd_stage_destroy.argtypes = [vp]
     L.orbb_rgbd_stage_reset.argtypes = [vp]
@@ -156,8 +159,11 @@ def load_library():
     L.orbb_rgbd_stage_wait.argtypes = [vp, i32, C.POINTER(SlamFrames)]
     for name in EXPORTS:
         fn = getattr(L, name)
-        if name not in ("orbb_strerror", "orbb_last_cuda_error", "orbb_get_launch_count", "orbb_rgbd_stage_handle"):
+        if name not in ("orbb_strerror", "orbb_last_cuda_error", "orbb_get_launch_count", "orbb_rgbd_stage_handle",
+                        "orbb_slam_frame_bson_size", "orbb_slam_frame_to_bson"):
             fn.restype = C.c_int
+    L.orbb_slam_frame_bson_size.restype = C.c_size_t
+    L.orbb_slam_frame_to_bson.restype = C.c_longlong
     L.orbb_rgbd_stage_handle.restype = vp
     L.orbb_get_launch_count.restype = C.c_longlong
     _lib = L
@@ -526,6 +532,24 @@ class RgbdFrameStage:
                     previous_matched_points=view(out.previous_matched_points, np.float64, (n, mk, 3)),
                     current_matched_points=view(out.current_matched_points, np.float64, (n, mk, 3)),
                     matched_xy=view(out.matched_xy, np.uint16, (n, 2, mk)))
+
+
+def slam_frame_to_bson(ax: int, ay: int, az: int, width: int, height: int, keypoints_x, keypoints_y, image=b"",
+                       channels: int = 1) -> bytes:
+    """The reference's per-frame WebSocket message (WebSocketCom.cpp:164-184) as bytes."""
+    L = load_library()
+    kx = np.ascontiguousarray(keypoints_x, np.uint16)
+    ky = np.ascontiguousarray(keypoints_y, np.uint16)
+    if kx.shape != ky.shape or kx.ndim != 1:
+        raise OrbbError("keypoints_x / keypoints_y must be 1-D arrays of the same length")
+    img = np.frombuffer(bytes(image), np.uint8)
+    n = int(L.orbb_slam_frame_bson_size(kx.shape[0], img.shape[0]))
+    out = np.empty(n, np.uint8)
+    rc = L.orbb_slam_frame_to_bson(ax, ay, az, width, height, channels, _np_ptr(kx), _np_ptr(ky), kx.shape[0],
+                                   _np_ptr(img) if img.shape[0] else C.c_void_p(0), img.shape[0], _np_ptr(out), n)
+    if rc != n:
+        raise OrbbError(f"orbb_slam_frame_to_bson: {rc}")
+    return out.tobytes()
 
 
 def match_knn_host(ex: ORBextractor, query: np.ndarray, train: np.ndarray, k: int = 2, ratio: float = 0.7):
