@@ -41,6 +41,10 @@ BYTES_PER_FRAME = W * H + 2 * LEVEL_PIXELS + 60 * NFEAT  # 2,268,264 B (SURVEY 8
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE k_fast_cells launch, per frame, from the committed
 # ncu --set full capture profiles/r01j_all_kernels_full.txt (135.4 MB + 8.56 MB for a 128-frame launch)
 FAST_DRAM_TRAFFIC_PER_FRAME = (135.4e6 + 8.563e6) / 128
+# thread instructions executed per frame by the six extraction kernels (thread_inst_executed of the same capture:
+# level0 0.286 G + resize x7 2.309 G + FAST 8.698 G + quadtree 2.016 G + blur 2.473 G + angle/rBRIEF 2.425 G per 128
+# frames) -- the path is issue bound, so the step is also reported against the SM issue roofline
+THREAD_INST_PER_FRAME = (0.2857e9 + 2.3089e9 + 8.698e9 + 2.016e9 + 2.473e9 + 2.425e9) / 128
 
 
 def measured_peaks():
@@ -470,7 +474,12 @@ def main():
                          "peak_kind": peak_kind,
                          "note": "issue/shared-memory bound integer kernel; HBM fraction reported honestly"},
             "step_roofline": {"bytes_per_frame": BYTES_PER_FRAME, "achieved_gbs": BYTES_PER_FRAME * fps / world / 1e9,
-                              "frac_of_hbm": BYTES_PER_FRAME * fps / world / 1e9 / hbm_peak},
+                              "frac_of_hbm": BYTES_PER_FRAME * fps / world / 1e9 / hbm_peak,
+                              "thread_inst_per_frame": THREAD_INST_PER_FRAME,
+                              "issue_peak_tinst_s": 148 * 4 * 32 * f_mhz * 1e6 / 1e12,
+                              "frac_of_issue": THREAD_INST_PER_FRAME * fps / world / (148 * 4 * 32 * f_mhz * 1e6),
+                              "note": "integer-issue bound path: 148 SMs x 4 schedulers x 32 lanes x SM clock; "
+                                      "instruction counts from profiles/r01j_all_kernels_full.txt"},
             "stages_ms": dict(zip(stage_names, stage_ms)),
             "keypoints_per_frame": float(kp_total.item()) / (B * world),
             "gather": {"ms": gather_ms, "what": "all_gather of per-frame counts + ragged gather of {q,t,dist} match "
