@@ -27,8 +27,38 @@ __device__ __forceinline__ void best2_update(Best2 &b, int d, int idx) {
     else if (d < b.d2) { b.d2 = d; b.i2 = idx; }
 }
 
+// 256-bit Hamming distance with three carry-save adders in front of the population counts: POPC issues at a quarter
+// of the integer rate (16 lanes/clk/SM), so 8 POPC per pair bound the plain form.  x0..x6 are folded by
+// (sum, carry) = (a^b^c, maj(a,b,c)) -- one LOP3 each -- into two weight-1 words and three weight-2 words:
+// 5 POPC + 6 LOP3 instead of 8 POPC, which balances the POPC pipe against the integer pipe.
+__device__ __forceinline__ int hamming256(const uint4 &qa, const uint4 &qb, const uint4 &a, const uint4 &b) {
+    const unsigned x0 = qa.x ^ a.x, x1 = qa.y ^ a.y, x2 = qa.z ^ a.z, x3 = qa.w ^ a.w;
+    const unsigned x4 = qb.x ^ b.x, x5 = qb.y ^ b.y, x6 = qb.z ^ b.z, x7 = qb.w ^ b.w;
+    unsigned sa, ca, sb, cb, sc, cc;  // explicit LOP3s: 0x96 = a^b^c, 0xE8 = majority(a,b,c)
+    asm("lop3.b32 %0, %1, %2, %3, 0x96;" : "=r"(sa) : "r"(x0), "r"(x1), "r"(x2));
+    asm("lop3.b32 %0, %1, %2, %3, 0xE8;" : "=r"(ca) : "r"(x0), "r"(x1), "r"(x2));
+    asm("lop3.b32 %0, %1, %2, %3, 0x96;" : "=r"(sb) : "r"(x3), "r"(x4), "r"(x5));
+    asm("lop3.b32 %0, %1, %2, %3, 0xE8;" : "=r"(cb) : "r"(x3), "r"(x4), "r"(x5));
+    asm("lop3.b32 %0, %1, %2, %3, 0x96;" : "=r"(sc) : "r"(sa), "r"(sb), "r"(x6));
+    asm("lop3.b32 %0, %1, %2, %3, 0xE8;" : "=r"(cc) : "r"(sa), "r"(sb), "r"(x6));
+    return __popc(sc) + __popc(x7) + 2 * (__popc(ca) + __popc(cb) + __popc(cc));
+}
+
+// running two smallest (distance, index) pairs as packed keys (distance << 22 | index relative to the split's first
+// train row): three min/max instead of a compare-and-shuffle chain; equal distances order by index, which is the
+// "first seen wins" rule of the strict '<' scan.
+struct Best2K {
+    unsigned k1, k2;
+};
+__device__ __forceinline__ void best2k_update(Best2K &b, unsigned key) {
+    const unsigned hi = max(key, b.k1);
+    b.k1 = min(key, b.k1);
+    b.k2 = min(b.k2, hi);
+}
+
 // segments: query rows [q_off[s], q_off[s+1]) are matched against train rows [t_off[s], t_off[s+1]).
 // blockIdx.x = query block inside the segment, blockIdx.y = split of the train range, blockIdx.z = segment.
+template <int K>  // K = 1: only the nearest neighbour is tracked (one min per pair instead of three min/max)
 __global__ void __launch_bounds__(MATCH_THREADS)
 k_match(const uint4 *__restrict__ query, const uint4 *__restrict__ train, const int *__restrict__ q_off,
         const int *__restrict__ t_off, int nq_one, int nt_one, int n_split, int4 *__restrict__ partial,
@@ -44,14 +74,14 @@ k_match(const uint4 *__restrict__ query, const uint4 *__restrict__ train, const 
     const int ts = min(nt, (int)blockIdx.y * per), te = min(nt, ts + per);
 
     uint4 qa[MATCH_QPT], qb[MATCH_QPT];
-    Best2 best[MATCH_QPT];
+    Best2K best[MATCH_QPT];
 #pragma unroll
     for (int j = 0; j < MATCH_QPT; ++j) {
         const int q = qbase + j * MATCH_THREADS + threadIdx.x;
         const int qq = q < q1 ? q : q1 - 1;
         qa[j] = query[(size_t)qq * 2];
         qb[j] = query[(size_t)qq * 2 + 1];
-        best[j] = {257, -1, 257, -1};
+        best[j] = {0xffffffffu, 0xffffffffu};
     }
     for (int tb = ts; tb < te; tb += MATCH_TILE) {
         const int cnt = min(MATCH_TILE, te - tb);
@@ -62,19 +92,23 @@ k_match(const uint4 *__restrict__ query, const uint4 *__restrict__ train, const 
         for (int t = 0; t < cnt; ++t) {
             const uint4 a = s_t[2 * t], b = s_t[2 * t + 1];
 #pragma unroll
+            const unsigned rel = (unsigned)(tb + t - ts);  // < 2^22: the host picks n_split accordingly
             for (int j = 0; j < MATCH_QPT; ++j) {
-                const int d = __popc(qa[j].x ^ a.x) + __popc(qa[j].y ^ a.y) + __popc(qa[j].z ^ a.z) +
-                              __popc(qa[j].w ^ a.w) + __popc(qb[j].x ^ b.x) + __popc(qb[j].y ^ b.y) +
-                              __popc(qb[j].z ^ b.z) + __popc(qb[j].w ^ b.w);
-                best2_update(best[j], d, tb + t);
+                const unsigned key = ((unsigned)hamming256(qa[j], qb[j], a, b) << 22) | rel;
+                if (K == 1) best[j].k1 = min(best[j].k1, key);
+                else best2k_update(best[j], key);
             }
         }
     }
 #pragma unroll
     for (int j = 0; j < MATCH_QPT; ++j) {
         const int q = qbase + j * MATCH_THREADS + threadIdx.x;
-        if (q < q1)
-            partial[(size_t)blockIdx.y * partial_stride + q] = make_int4(best[j].d1, best[j].i1, best[j].d2, best[j].i2);
+        if (q < q1) {
+            const unsigned k1 = best[j].k1, k2 = best[j].k2;
+            partial[(size_t)blockIdx.y * partial_stride + q] =
+                make_int4(k1 == 0xffffffffu ? 257 : (int)(k1 >> 22), k1 == 0xffffffffu ? -1 : ts + (int)(k1 & 0x3fffffu),
+                          k2 == 0xffffffffu ? 257 : (int)(k2 >> 22), k2 == 0xffffffffu ? -1 : ts + (int)(k2 & 0x3fffffu));
+        }
     }
 }
 
@@ -148,8 +182,7 @@ k_match_windowed(const uint4 *__restrict__ query, const uint8_t *__restrict__ q_
             const float2 p = s_xy[t];
             if (fabsf(__fsub_rn(qx, p.x)) <= max_px && fabsf(__fsub_rn(qy, p.y)) <= max_px) {
                 const uint4 a = s_d[2 * t], b = s_d[2 * t + 1];
-                const int d = __popc(qa.x ^ a.x) + __popc(qa.y ^ a.y) + __popc(qa.z ^ a.z) + __popc(qa.w ^ a.w) +
-                              __popc(qb.x ^ b.x) + __popc(qb.y ^ b.y) + __popc(qb.z ^ b.z) + __popc(qb.w ^ b.w);
+                const int d = hamming256(qa, qb, a, b);
                 if (d < best_d) { best_d = d; best_i = tb + t; }
             }
         }
@@ -184,8 +217,12 @@ cudaError_t launch_match(const uint8_t *d_q, const uint8_t *d_t, const int *d_q_
     if (nq_total <= 0) return cudaSuccess;
     const int qblocks = (max_q_per_seg + MATCH_THREADS * MATCH_QPT - 1) / (MATCH_THREADS * MATCH_QPT);
     dim3 grid(qblocks, n_split, nseg);
-    k_match<<<grid, MATCH_THREADS, 0, st>>>(reinterpret_cast<const uint4 *>(d_q), reinterpret_cast<const uint4 *>(d_t),
-                                            d_q_off, d_t_off, nq_total, nt_one, n_split, d_partial, partial_stride);
+    if (k == 1)
+        k_match<1><<<grid, MATCH_THREADS, 0, st>>>(reinterpret_cast<const uint4 *>(d_q), reinterpret_cast<const uint4 *>(d_t),
+                                                   d_q_off, d_t_off, nq_total, nt_one, n_split, d_partial, partial_stride);
+    else
+        k_match<2><<<grid, MATCH_THREADS, 0, st>>>(reinterpret_cast<const uint4 *>(d_q), reinterpret_cast<const uint4 *>(d_t),
+                                                   d_q_off, d_t_off, nq_total, nt_one, n_split, d_partial, partial_stride);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     if (d_naccept) {
@@ -247,8 +284,7 @@ k_match_projection(const uint4 *__restrict__ query, const float2 *__restrict__ q
             const int ot = s_oct[t];
             if (fabsf(__fsub_rn(p.x, uv.x)) < radius && fabsf(__fsub_rn(p.y, uv.y)) < radius && ot >= oq - 1 && ot <= oq + 1) {
                 const uint4 a = s_d[2 * t], b = s_d[2 * t + 1];
-                const int d = __popc(qa.x ^ a.x) + __popc(qa.y ^ a.y) + __popc(qa.z ^ a.z) + __popc(qa.w ^ a.w) +
-                              __popc(qb.x ^ b.x) + __popc(qb.y ^ b.y) + __popc(qb.z ^ b.z) + __popc(qb.w ^ b.w);
+                const int d = hamming256(qa, qb, a, b);
                 if (d < best_d) { best_d = d; best_i = tb + t; }
             }
         }

@@ -811,6 +811,7 @@ static int ensure_partial(orbb_handle *h, size_t need) {
 static int pick_split(int qblocks_total, int nt) {
     int want = (2 * 148 + qblocks_total - 1) / std::max(qblocks_total, 1);
     want = std::min(want, std::max(1, nt / 256));
+    want = std::max(want, (int)(((long long)nt + (1 << 22) - 1) >> 22));  // packed keys hold 22 index bits per split
     return std::max(1, std::min(want, 64));
 }
 
@@ -820,6 +821,7 @@ extern "C" int orbb_match_knn(orbb_handle *h, const uint8_t *d_query, int nq, co
     if (!h || !d_query || !d_train || !d_idx || !d_dist || nq < 0 || nt < 0 || k < 1 || k > 2) return ORBB_ERR_INVALID;
     if ((reinterpret_cast<uintptr_t>(d_query) | reinterpret_cast<uintptr_t>(d_train)) & 15) return ORBB_ERR_INVALID;
     if (nq == 0) return ORBB_OK;
+    if (nt > 64 * (1 << 22)) return ORBB_ERR_CAPACITY;  // 268 M train rows per call
     const int qblocks = (nq + 255) / 256;
     const int n_split = pick_split(qblocks, nt);
     int rc = ensure_partial(h, (size_t)n_split * nq);
