@@ -240,6 +240,73 @@ def bench_rgbd_stage(orbb, torch, device_index, steps, warmup):
                       "frac_of_hbm": align_bytes / (align_ms * 1e-3) / 1e9 / hbm_peak, "peak_kind": peak_kind}}
 
 
+def bench_reference_gpu_kernels(orbb, torch, device_index):
+    """The reference's OWN front-end kernels recompiled for sm_100a (oracle/_ref/ref_gpu_bench, built by
+    `make -C oracle ref_gpu` from the sources under /root/reference; its stage sequence of buildStream.cpp:424-466)
+    timed on this GPU in a separate process, next to the product on the same 848x480 frame (reference Context.h:16-17).
+    DIFFERENT ALGORITHM (FAST-12 float score on one blurred level, one keypoint per 32x32 cell, 32-bit hash):
+    timing baseline only, not a parity check.  Returns None when the binary did not travel with the snapshot."""
+    import subprocess
+    import tempfile
+    exe = os.path.join(ROOT, "oracle", "_ref", "ref_gpu_bench")
+    if not os.path.exists(exe):
+        return None
+    synth = importlib.import_module(PKG + ".synth")
+    w, h = 848, 480
+    frame = synth.textured_frame(w, h, 2000)
+    with tempfile.NamedTemporaryFile(suffix=".raw", delete=False) as f:
+        frame.tofile(f)
+        path = f.name
+    try:
+        r = subprocess.run([exe, path, str(w), str(h), "200"], capture_output=True, text=True, timeout=90)
+        ref = json.loads(r.stdout.strip().splitlines()[-1]) if r.returncode == 0 and r.stdout.strip() else None
+    except Exception as e:  # a baseline that fails to run is reported, never fatal
+        ref = {"error": repr(e)[:200]}
+    finally:
+        os.unlink(path)
+    if ref is None:
+        ref = {"error": (r.stderr or "no output")[-200:]}
+    st = torch.cuda.current_stream()
+
+    def ours(nfeat, nlevels, batch, iters):
+        ex = orbb.ORBextractor(nfeat, SCALE, nlevels, INI_TH, MIN_TH, width=w, height=h, max_batch=batch, device=device_index)
+        frames = np.stack([synth.textured_frame(w, h, 2000 + i) for i in range(min(batch, 8))])
+        frames = np.concatenate([frames] * ((batch + len(frames) - 1) // len(frames)))[:batch]
+        d_in = torch.from_numpy(frames).cuda()
+        d_kp = torch.zeros(batch * ex.max_kp * 28, dtype=torch.uint8, device="cuda")
+        d_desc = torch.zeros(batch * ex.max_kp * 32, dtype=torch.uint8, device="cuda")
+        d_cnt = torch.zeros(batch, dtype=torch.int32, device="cuda")
+        for _ in range(5):
+            ex.extract_batch_device(d_in, batch, d_kp, d_desc, d_cnt, stream=st)
+        torch.cuda.synchronize()
+        lat = []
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        for _ in range(iters):  # one call at a time, synchronised: same protocol as the reference binary's latency
+            e0.record(st)
+            ex.extract_batch_device(d_in, batch, d_kp, d_desc, d_cnt, stream=st)
+            e1.record(st)
+            torch.cuda.synchronize()
+            lat.append(e0.elapsed_time(e1))
+        e0.record(st)
+        for _ in range(iters):  # back to back
+            ex.extract_batch_device(d_in, batch, d_kp, d_desc, d_cnt, stream=st)
+        e1.record(st)
+        torch.cuda.synchronize()
+        b2b = e0.elapsed_time(e1) / iters
+        nkp = float(d_cnt.sum().item()) / batch
+        ex.close()
+        return {"nfeatures": nfeat, "levels": nlevels, "batch": batch, "keypoints_per_frame": nkp,
+                "call_latency_us": 1e3 * float(np.median(lat)), "back_to_back_us_per_frame": 1e3 * b2b / batch,
+                "frames_per_s": batch / (b2b * 1e-3)}
+
+    return {"what": "reference src/cuda kernels recompiled for sm_100a vs the product, one 848x480 frame "
+                    "(different algorithms: timing only)",
+            "reference": ref,
+            "ours_same_shape_1_level_405_kp": ours(405, 1, 1, 200),
+            "ours_orbslam2_8_levels_1200_kp": ours(1200, NLEVELS, 1, 200),
+            "ours_orbslam2_8_levels_1200_kp_batch_64": ours(1200, NLEVELS, 64, 20)}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -249,6 +316,7 @@ def main():
     ap.add_argument("--frames", type=int, default=FRAMES_PER_GPU)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-rgbd", action="store_true", help="skip the RGB-D frame-stage leg (cfg 2 geometry)")
+    ap.add_argument("--no-refgpu", action="store_true", help="skip the leg that times the reference's own kernels")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -430,6 +498,10 @@ def main():
     if rank == 0 and world == 1 and not args.no_rgbd:
         rgbd = bench_rgbd_stage(orbb, torch, local_rank, min(args.steps, 10), min(args.warmup, 3))
 
+    refgpu = None
+    if rank == 0 and world == 1 and not args.no_refgpu:
+        refgpu = bench_reference_gpu_kernels(orbb, torch, local_rank)
+
     # ---- the only collectives (after the timed region): gather per-frame counts and match records to rank 0
     sharding = importlib.import_module(PKG + ".sharding")
     g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -494,6 +566,8 @@ def main():
         }
         if rgbd is not None:
             line["rgbd_stage"] = rgbd
+        if refgpu is not None:
+            line["reference_gpu_kernels"] = refgpu
         if world == 1 and not args.no_cpu:
             cores = os.cpu_count() or 1
             cfps, nsample, native = cpu_oracle_fps(host_sets[0], cores)

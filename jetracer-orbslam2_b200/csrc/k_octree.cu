@@ -20,24 +20,38 @@
 //    (64-bit shared-memory atomicMax over (response, ~order, index)).
 // Bound: latency/issue (tiny per-CTA working sets, L2 resident); not HBM.
 #include <algorithm>
+#include <cstdio>
 #include <cstdlib>
 
 #include "orbb_internal.cuh"
 
 namespace orbb {
 
+#ifdef ORBB_OCT_PROF  // diagnostics build only (make EXTRA=-DORBB_OCT_PROF): phase timestamps of CTA (0,0)
+__device__ long long g_oct_prof[64];
+#define OCT_T(k) do { if (threadIdx.x == 0 && blockIdx.x == 0 && blockIdx.y == 0) prof_t[k] = clock64(); } while (0)
+#define OCT_A(k, t0) do { if (threadIdx.x == 0 && blockIdx.x == 0 && blockIdx.y == 0) g_oct_prof[k] += clock64() - (t0); } while (0)
+#define OCT_NOW() clock64()
+#else
+#define OCT_T(k) do { } while (0)
+#define OCT_A(k, t0) do { } while (0)
+#define OCT_NOW() 0
+#endif
+
 #define OCT_THREADS 512
 #define OCT_WARPS (OCT_THREADS / 32)
 #define FULL 0xffffffffu
+#define OCT_TBL_STATIC 2048  // cells of the static cell table: 8 B x 2048 = the 16 KB of whist (OCT_WARPS x 256 x 4)
 
 struct OctStatic {
     uint32_t whist[OCT_WARPS][256];
     uint32_t digit_base[256];
     int hist_sd[40], hist_g[40];
     uint32_t warp_tot[OCT_WARPS];
+    uint32_t tcnt[OCT_TBL_STATIC / 2];  // cell-table key counts (2 x u16 per word); the cells' best keys alias whist
     int ctl[16];
 };
-enum { C_MODE = 0, C_DEPTH, C_SIZE, C_PN, C_QN, C_CUT, C_TOTAL, C_NFINAL };
+enum { C_MODE = 0, C_DEPTH, C_SIZE, C_PN, C_QN, C_CUT, C_TOTAL, C_NFINAL, C_BAIL };
 
 // exclusive block scan of one value per thread; returns exclusive prefix, *total = block sum
 __device__ __forceinline__ uint32_t block_excl_scan(uint32_t v, uint32_t *warp_tot, uint32_t *total) {
@@ -221,13 +235,18 @@ template <int OCT_RB, int MIN_CTAS>
 __global__ void __launch_bounds__(OCT_THREADS, MIN_CTAS)
 k_octree(const LevelDev *__restrict__ levels, int n_levels, const int *__restrict__ cand_count,
          int *__restrict__ sel_count, int level_base, int frame_base, int quota_override, int pcap, int pcap2,
-         int sort_off, int sort_bytes) {
+         int sort_off, int sort_bytes, int tbl_cap_dyn) {
     __shared__ OctStatic S;
     extern __shared__ __align__(16) uint8_t dyn[];
     const int tid = threadIdx.x, lane = tid & 31;
     const int level = blockIdx.x + level_base, frame = blockIdx.y + frame_base;
     const LevelDev &L = levels[level];
     const int N = quota_override >= 0 ? quota_override : L.nfeat;
+#ifdef ORBB_OCT_PROF
+    long long prof_t[12] = {0};
+    int prof_rounds = 0;
+#endif
+    OCT_T(0);
     int n = cand_count[frame * n_levels + level];
     n = min(n, L.cand_cap);
     int *out_count = sel_count + frame * n_levels + level;
@@ -248,15 +267,94 @@ k_octree(const LevelDev *__restrict__ levels, int n_levels, const int *__restric
 
     const size_t fo = (size_t)frame * L.cand_cap;
     const uint32_t *cand = L.cand + fo;
+    const int D = L.depth;
+
+    // ---- CELL-TABLE FAST PATH.  The selection only ever looks at the tree down to the depth at which ~N nodes exist
+    // (4-6 for the quotas of a pyramid level), while the path keys resolve single pixels (D ~ 10).  So the candidates
+    // are first binned into the 4^Dc cells of depth Dc: per cell a key count and the best key (response, then
+    // earliest upstream order).  Cell index = path prefix, so the table IS the sorted order: one prefix scan
+    // compacts the non-empty cells into "records" (path prefix, running key count) -- no radix sort, and every later
+    // pass runs over the records (a third of the keys) instead of the keys.  Node sizes come from the running key
+    // counts; everything else (parting depths, breadth-first replay, careful phase) is unchanged as long as it stays
+    // at depths <= Dc.  If it would go deeper (heavily clustered keys), the CTA falls back to the general path below.
+    const int root_bits = L.key_bits - 2 * D;
+    const int tbl_cap = tbl_cap_dyn > 0 ? tbl_cap_dyn : OCT_TBL_STATIC;
+    int Dc = 0;
+    for (int dd = min(D, 6); dd >= 1; --dd)
+        if ((1 << (root_bits + 2 * dd)) <= tbl_cap) { Dc = dd; break; }
+    const int T = 1 << (root_bits + 2 * Dc);
+    const bool try_fast = tbl_cap_dyn >= 0 && Dc > 0 && T >= 4 * N && n < L.cand_cap;
+    unsigned long long *tbl_best = tbl_cap_dyn > 0 ? reinterpret_cast<unsigned long long *>(dyn + sort_off)
+                                                   : reinterpret_cast<unsigned long long *>(&S.whist[0][0]);
+    uint32_t *tbl_cnt = tbl_cap_dyn > 0 ? reinterpret_cast<uint32_t *>(tbl_best + tbl_cap_dyn) : S.tcnt;  // 2 x u16 per word
+    const int tbl_bytes = tbl_cap_dyn > 0 ? tbl_cap_dyn * 10 : 0;
+    const int csh = 2 * (D - Dc);  // path key -> cell index
+
+    for (int attempt = try_fast ? 0 : 1; attempt < 2; ++attempt) {
+    const bool fastp = attempt == 0;
+    int m;               // items the passes below run over: records (fast path) or keys
+    uint2 *kva, *kvb;    // item arrays; kv[i].x = path key (prefix), kv[i].y = running key count (fast) / candidate
+    int key_stride;
+    bool in_smem;
+    if (fastp) {
+        const int mc = (min(T, n) + 1 + 15) & ~15;  // records + sentinel
+        in_smem = (size_t)mc * 16 + (size_t)tbl_bytes <= (size_t)sort_bytes;
+        kva = in_smem ? reinterpret_cast<uint2 *>(dyn + sort_off + tbl_bytes) : L.kv_a + fo;
+        kvb = in_smem ? kva + mc : L.kv_b + fo;
+        key_stride = in_smem ? mc : L.cand_cap;
+        for (int i = tid; i < T; i += OCT_THREADS) tbl_best[i] = 0ull;
+        for (int i = tid; i < (T + 1) / 2; i += OCT_THREADS) tbl_cnt[i] = 0u;
+        __syncthreads();
+        // ---- F1. bin the candidates
+        for (int base = tid; base < n; base += OCT_RB * OCT_THREADS) {
+            uint32_t c[OCT_RB], kx[OCT_RB], ky[OCT_RB], xo[OCT_RB], yo[OCT_RB];
+#pragma unroll
+            for (int j = 0; j < OCT_RB; ++j) c[j] = base + j * OCT_THREADS < n ? cand[base + j * OCT_THREADS] : 0u;
+#pragma unroll
+            for (int j = 0; j < OCT_RB; ++j) {
+                kx[j] = __ldg(&L.xkey[c[j] & 0xfffu]); ky[j] = __ldg(&L.ykey[(c[j] >> 12) & 0xfffu]);
+                xo[j] = __ldg(&L.xord[c[j] & 0xfffu]); yo[j] = __ldg(&L.yord[(c[j] >> 12) & 0xfffu]);
+            }
+#pragma unroll
+            for (int j = 0; j < OCT_RB; ++j)
+                if (base + j * OCT_THREADS < n) {
+                    const uint32_t cell = (kx[j] | ky[j]) >> csh;
+                    const uint32_t ord = ((yo[j] >> 6) << 19) | ((xo[j] >> 6) << 12) | ((yo[j] & 63u) << 6) | (xo[j] & 63u);
+                    const unsigned long long v = ((unsigned long long)(c[j] >> 24) << 56) |
+                                                 ((unsigned long long)(0x3ffffffu - ord) << 24) | (c[j] & 0xffffffu);
+                    atomicAdd(&tbl_cnt[cell >> 1], 1u << (16 * (cell & 1u)));
+                    atomicMax(&tbl_best[cell], v);
+                }
+        }
+        __syncthreads();
+        // ---- F2. compact the non-empty cells (already in path order) into records
+        const int per = (T + OCT_THREADS - 1) / OCT_THREADS;
+        const int c0 = min(T, tid * per), c1 = min(T, c0 + per);
+        uint32_t my_cells = 0, my_keys = 0;
+        for (int cidx = c0; cidx < c1; ++cidx) {
+            const uint32_t w = (tbl_cnt[cidx >> 1] >> (16 * (cidx & 1))) & 0xffffu;
+            my_cells += w != 0; my_keys += w;
+        }
+        uint32_t tot_cells, tot_keys;
+        uint32_t pos = block_excl_scan(my_cells, S.warp_tot, &tot_cells);
+        uint32_t run = block_excl_scan(my_keys, S.warp_tot, &tot_keys);
+        for (int cidx = c0; cidx < c1; ++cidx) {
+            const uint32_t w = (tbl_cnt[cidx >> 1] >> (16 * (cidx & 1))) & 0xffffu;
+            if (w) { kva[pos++] = make_uint2((uint32_t)cidx << csh, run); run += w; }
+        }
+        m = (int)tot_cells;
+        if (tid == 0) kva[m] = make_uint2(0xffffffffu, tot_keys);  // sentinel: closes the last record's key count
+        __syncthreads();
+    } else {
     // (path key, packed candidate) pairs, radix ping-pong.  When the launch could afford the shared memory (small
     // grids: one or two CTAs per SM) and this level's candidates fit, every per-key array lives in shared memory:
     // the scattered 8-byte stores of the sort and the strided passes over the keys then never leave the SM.
     const int n_pad = (n + 15) & ~15;
-    const bool in_smem = (size_t)n_pad * 16 <= (size_t)sort_bytes;
-    uint2 *kva = in_smem ? reinterpret_cast<uint2 *>(dyn + sort_off) : L.kv_a + fo;
-    uint2 *kvb = in_smem ? kva + n_pad : L.kv_b + fo;
-    const int key_stride = in_smem ? n_pad : L.cand_cap;  // elements between the scratch arrays carved from kvb
-    const int D = L.depth;
+    in_smem = (size_t)n_pad * 16 <= (size_t)sort_bytes;
+    kva = in_smem ? reinterpret_cast<uint2 *>(dyn + sort_off) : L.kv_a + fo;
+    kvb = in_smem ? kva + n_pad : L.kv_b + fo;
+    key_stride = in_smem ? n_pad : L.cand_cap;  // elements between the scratch arrays carved from kvb
+    m = n;
 
     // ---- 1. path keys
     for (int base = tid; base < n; base += OCT_RB * OCT_THREADS) {
@@ -272,12 +370,17 @@ k_octree(const LevelDev *__restrict__ levels, int n_levels, const int *__restric
         }
     }
     __syncthreads();
+    OCT_T(1);
     // ---- 2. LSD radix sort by path
     for (int shift = 0; shift < L.key_bits; shift += 8) {
         radix_pass<OCT_RB>(kva, kvb, n, shift, S);
         uint2 *t = kva; kva = kvb; kvb = t;
     }
+    }
     const uint2 *kv = kva;  // sorted
+    OCT_T(2);
+    // number of keys in the items [a, b): records carry a running key count
+    auto nkeys = [&](uint32_t a, uint32_t b) -> uint32_t { return fastp ? kv[b].y - kv[a].y : b - a; };
     // free ping-pong buffers become scratch: two generations of u16 segment ids, and the head flags
     uint16_t *seg_a = reinterpret_cast<uint16_t *>(kvb), *seg_b = seg_a + key_stride;
     uint8_t *head = reinterpret_cast<uint8_t *>(seg_b + key_stride);
@@ -285,37 +388,61 @@ k_octree(const LevelDev *__restrict__ levels, int n_levels, const int *__restric
 
     // ---- 3. split depths + histograms
     if (tid < 40) { S.hist_sd[tid] = 0; S.hist_g[tid] = 0; }
+    if (tid == 0) S.ctl[C_BAIL] = 0;
     __syncthreads();
-    for (int base = 0; base < n; base += OCT_THREADS) {
+    // Per-thread packed 8-bit counters, 16 bins per histogram (depths 0..D <= 15), flushed to the shared histograms
+    // once per warp (and every 255 items per thread): corners cluster, so most partings fall into two or three deep
+    // bins and per-key shared atomics would serialise on them.
+    unsigned long long cs_lo = 0, cs_hi = 0, cg_lo = 0, cg_hi = 0;
+    auto flush_counts = [&]() {
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+            const unsigned vs = (unsigned)((k < 8 ? cs_lo : cs_hi) >> (8 * (k & 7))) & 0xffu;
+            const unsigned vg = (unsigned)((k < 8 ? cg_lo : cg_hi) >> (8 * (k & 7))) & 0xffu;
+            const unsigned ts = __reduce_add_sync(FULL, vs), tg = __reduce_add_sync(FULL, vg);
+            if (lane == 0) {
+                if (ts) atomicAdd(&S.hist_sd[k], (int)ts);
+                if (tg) atomicAdd(&S.hist_g[k], (int)tg);
+            }
+        }
+        cs_lo = cs_hi = cg_lo = cg_hi = 0;
+    };
+    int since_flush = 0;
+    for (int base = 0; base < m; base += OCT_THREADS) {  // block-uniform trip count
         const int i = base + tid;
-        unsigned s = 0x100u + lane, g = 0x100u + lane;
-        if (i < n) {
+        if (i < m) {
             const uint32_t kc = kv[i].x;
             unsigned l = 0, r = 0;
             if (i > 0) {
                 const int hb = 31 - __clz(kv[i - 1].x ^ kc);
                 l = hb >= 2 * D ? 0u : (unsigned)(D - (hb >> 1));
             }
-            if (i < n - 1) {
+            if (i < m - 1) {
                 const int hb = 31 - __clz(kc ^ kv[i + 1].x);
                 r = hb >= 2 * D ? 0u : (unsigned)(D - (hb >> 1));
                 sd[i] = (uint8_t)r;
-                s = r;
+                const unsigned rb = min(r, 15u);  // r <= D <= 15 (keys are distinct pixels)
+                const unsigned long long one = 1ull << (8 * (rb & 7u));
+                if (rb < 8) cs_lo += one; else cs_hi += one;
             }
-            g = max(l, r);
+            // hist_g counts the single-key nodes by the depth at which they become isolated
+            if (!fastp || kv[i + 1].y - kv[i].y == 1u) {
+                const unsigned g = min(max(l, r), 15u);
+                const unsigned long long one = 1ull << (8 * (g & 7u));
+                if (g < 8) cg_lo += one; else cg_hi += one;
+            }
         }
-        const unsigned lt = (1u << lane) - 1u;
-        const unsigned ps = __match_any_sync(FULL, s);
-        if (i < n - 1 && (ps & lt) == 0) atomicAdd(&S.hist_sd[s], __popc(ps));
-        const unsigned pg = __match_any_sync(FULL, g);
-        if (i < n && (pg & lt) == 0) atomicAdd(&S.hist_g[g], __popc(pg));
+        if (++since_flush == 255) { flush_counts(); since_flush = 0; }
     }
+    flush_counts();
     __syncthreads();
+    OCT_T(3);
     // ---- 4. replay the breadth-first passes on the histograms
     if (tid == 0) {
         int prev = 1 + S.hist_sd[0], cumL = prev, cumS = S.hist_g[0];
         int mode = 0, depth = D + 1;
         for (int k = 1; k <= D + 1; ++k) {
+            if (fastp && Dc < D && k > Dc) { S.ctl[C_BAIL] = 1; break; }  // the records cannot tell deeper partings
             if (k <= D) { cumL += S.hist_sd[k]; cumS += S.hist_g[k]; }
             const int Ek = cumL - cumS;
             if (cumL >= N || cumL == prev) { mode = 0; depth = k; break; }
@@ -326,10 +453,12 @@ k_octree(const LevelDev *__restrict__ levels, int n_levels, const int *__restric
         S.ctl[C_PN] = 0; S.ctl[C_QN] = 0;
     }
     __syncthreads();
+    if (S.ctl[C_BAIL]) { __syncthreads(); continue; }
     const int mode = S.ctl[C_MODE], k0 = S.ctl[C_DEPTH];
-    for (int i = tid; i < n; i += OCT_THREADS) head[i] = (i == 0 || sd[i - 1] <= k0) ? 1 : 0;
+    for (int i = tid; i < m; i += OCT_THREADS) head[i] = (i == 0 || sd[i - 1] <= k0) ? 1 : 0;
     __syncthreads();
-
+    OCT_T(4);
+    bool bail = false;
     if (mode == 1) {
         // ---- 5. careful phase, key-parallel.  A round works on the current head-delimited nodes: nst[] start of
         // every node, seq[] creation sequence of the nodes created by the previous round that hold > 1 key
@@ -338,28 +467,29 @@ k_octree(const LevelDev *__restrict__ levels, int n_levels, const int *__restric
         uint32_t *nst = nst_a, *nst2 = nst_b, *seq = seq_a, *seq2 = seq_b;
         uint16_t *seg = seg_a, *seg2 = seg_b;
         {
-            head_scan(head, n, S, [&](int i, uint32_t node, bool h) {
+            head_scan(head, m, S, [&](int i, uint32_t node, bool h) {
                 seg[i] = (uint16_t)node;
                 if (h) nst[node] = (uint32_t)i;
             });
-            if (tid == 0) nst[nseg] = (uint32_t)n;
+            if (tid == 0) nst[nseg] = (uint32_t)m;
             __syncthreads();
             // closed-form creation sequence of the breadth-first pass that made the depth-k0 nodes
             const uint32_t digit_mask = 0xCCCCCCCCu & ((1u << (2 * k0)) - 1u);
             const uint32_t root_mask = (k0 & 1) ? 0u : (((1u << (L.key_bits - 2 * D)) - 1u) << (2 * k0));
             for (int sidx = tid; sidx < nseg; sidx += OCT_THREADS) {
-                const uint32_t st = nst[sidx], cnt = nst[sidx + 1] - st;
+                const uint32_t st = nst[sidx], cnt = nkeys(st, nst[sidx + 1]);
                 seq[sidx] = cnt > 1 ? (((kv[st].x >> (2 * (D - k0))) ^ digit_mask ^ root_mask) & 0x7fffffffu) : 0xffffffffu;
             }
         }
         int d = k0;
         while (true) {
+            if (fastp && Dc < D && d + 1 > Dc) { bail = true; break; }  // block-uniform: this round parts at depth d + 1
             const int size = S.ctl[C_SIZE];
             for (int sidx = tid; sidx < nseg; sidx += OCT_THREADS) { gain[sidx] = 0; rank_of[sidx] = -1; }
             if (tid == 0) { S.ctl[C_PN] = 0; S.ctl[C_CUT] = 0x7fffffff; }
             __syncthreads();
             // gains: children - 1 = number of depth-(d+1) partings inside the node
-            for (int i = tid; i < n - 1; i += OCT_THREADS)
+            for (int i = tid; i < m - 1; i += OCT_THREADS)
                 if (sd[i] == d + 1) {
                     const int sidx = seg[i];
                     if (seq[sidx] != 0xffffffffu) atomicAdd(&gain[sidx], 1u);
@@ -368,16 +498,16 @@ k_octree(const LevelDev *__restrict__ levels, int n_levels, const int *__restric
             for (int sidx = tid; sidx < nseg; sidx += OCT_THREADS)
                 if (seq[sidx] != 0xffffffffu) {
                     const int p = atomicAdd(&S.ctl[C_PN], 1);
-                    skey[p] = ((unsigned long long)(nst[sidx + 1] - nst[sidx]) << 32) | seq[sidx];
+                    skey[p] = ((unsigned long long)nkeys(nst[sidx], nst[sidx + 1]) << 32) | seq[sidx];
                     sval[p] = (uint32_t)sidx;
                 }
             __syncthreads();
             const int pn = S.ctl[C_PN];
-            int m = 1;
-            while (m < pn) m <<= 1;
-            for (int p = pn + tid; p < m; p += OCT_THREADS) { skey[p] = 0ull; sval[p] = 0xffffffffu; }
+            int mm = 1;
+            while (mm < pn) mm <<= 1;
+            for (int p = pn + tid; p < mm; p += OCT_THREADS) { skey[p] = 0ull; sval[p] = 0xffffffffu; }
             __syncthreads();
-            bitonic_desc(skey, sval, m);
+            bitonic_desc(skey, sval, mm);
             // prefix sums of the gains in processing order; first rank at which the node count reaches N
             uint32_t carry2 = 0;
             for (int base = 0; base < pn; base += OCT_THREADS) {
@@ -399,21 +529,21 @@ k_octree(const LevelDev *__restrict__ levels, int n_levels, const int *__restric
             for (int r = tid; r < nsplit; r += OCT_THREADS) rank_of[sval[r]] = r;
             __syncthreads();
             // split: every depth-(d+1) parting inside a split node starts a new node
-            for (int i = tid; i < n - 1; i += OCT_THREADS)
+            for (int i = tid; i < m - 1; i += OCT_THREADS)
                 if (sd[i] == d + 1 && rank_of[seg[i]] >= 0) head[i + 1] = 1;
             __syncthreads();
             if (found || total == 0) break;
             // next round: renumber the nodes; the new expandable ones are the children (> 1 key) of split nodes,
             // created in processing order of their parents, n1..n4 inside a parent
             const int nseg2 = size + (int)total;
-            head_scan(head, n, S, [&](int i, uint32_t node, bool h) {
+            head_scan(head, m, S, [&](int i, uint32_t node, bool h) {
                 seg2[i] = (uint16_t)node;
                 if (h) nst2[node] = (uint32_t)i;
             });
-            if (tid == 0) nst2[nseg2] = (uint32_t)n;
+            if (tid == 0) nst2[nseg2] = (uint32_t)m;
             __syncthreads();
             for (int s2 = tid; s2 < nseg2; s2 += OCT_THREADS) {
-                const uint32_t st = nst2[s2], cnt = nst2[s2 + 1] - st;
+                const uint32_t st = nst2[s2], cnt = nkeys(st, nst2[s2 + 1]);
                 const int pr = rank_of[seg[st]];
                 seq2[s2] = (pr >= 0 && cnt > 1) ? ((uint32_t)pr * 4u + ((kv[st].x >> (2 * (D - d - 1))) & 3u)) : 0xffffffffu;
             }
@@ -425,32 +555,55 @@ k_octree(const LevelDev *__restrict__ levels, int n_levels, const int *__restric
             ++d;
         }
     }
+    if (bail) { __syncthreads(); continue; }
+    OCT_T(5);
 
     // ---- 6. final nodes = head-delimited segments; keep the best key of each
-    const uint32_t n_nodes = head_scan(head, n, S, [&](int i, uint32_t node, bool) { seg_a[i] = (uint16_t)min(node, 0xffffu); });
+    const uint32_t n_nodes = head_scan(head, m, S, [&](int i, uint32_t node, bool) { seg_a[i] = (uint16_t)min(node, 0xffffu); });
     const int nfinal = min((int)n_nodes, L.sel_cap);
     for (int sidx = tid; sidx < nfinal; sidx += OCT_THREADS) best[sidx] = 0ull;
     __syncthreads();
-    for (int base = tid; base < n; base += OCT_RB * OCT_THREADS) {
+    for (int b0 = 0; b0 < m; b0 += OCT_RB * OCT_THREADS) {  // block-uniform trip count: the body shuffles
+        const int base = b0 + tid;
         uint32_t sidx[OCT_RB], c[OCT_RB], xo[OCT_RB], yo[OCT_RB];
+        unsigned long long vv[OCT_RB];
 #pragma unroll
         for (int j = 0; j < OCT_RB; ++j) {
             const int i = base + j * OCT_THREADS;
-            sidx[j] = i < n ? (uint32_t)seg_a[i] : 0xffffffffu;
-            c[j] = i < n ? kv[i].y : 0u;
+            sidx[j] = i < m ? (uint32_t)seg_a[i] : 0xffffffffu;
+            c[j] = i < m ? (fastp ? kv[i].x >> csh : kv[i].y) : 0u;
         }
+        if (fastp) {
 #pragma unroll
-        for (int j = 0; j < OCT_RB; ++j) { xo[j] = __ldg(&L.xord[c[j] & 0xfffu]); yo[j] = __ldg(&L.yord[(c[j] >> 12) & 0xfffu]); }
+            for (int j = 0; j < OCT_RB; ++j) vv[j] = sidx[j] != 0xffffffffu ? tbl_best[c[j]] : 0ull;  // the cell's best key
+        } else {
 #pragma unroll
-        for (int j = 0; j < OCT_RB; ++j)
-            if (sidx[j] < (uint32_t)nfinal) {
+            for (int j = 0; j < OCT_RB; ++j) { xo[j] = __ldg(&L.xord[c[j] & 0xfffu]); yo[j] = __ldg(&L.yord[(c[j] >> 12) & 0xfffu]); }
+#pragma unroll
+            for (int j = 0; j < OCT_RB; ++j) {
                 // (response, earliest upstream candidate order) decides; ord is unique per pixel, so the low 24 bits
                 // (x | y << 12 of the winner) never take part in the comparison
                 const uint32_t ord = ((yo[j] >> 6) << 19) | ((xo[j] >> 6) << 12) | ((yo[j] & 63u) << 6) | (xo[j] & 63u);
-                const unsigned long long v = ((unsigned long long)(c[j] >> 24) << 56) |
-                                             ((unsigned long long)(0x3ffffffu - ord) << 24) | (c[j] & 0xffffffu);
-                atomicMax(&best[sidx[j]], v);
+                vv[j] = ((unsigned long long)(c[j] >> 24) << 56) | ((unsigned long long)(0x3ffffffu - ord) << 24) |
+                        (c[j] & 0xffffffu);
             }
+        }
+#pragma unroll
+        for (int j = 0; j < OCT_RB; ++j) {
+            if (b0 + j * OCT_THREADS >= m) break;  // block-uniform
+            // the items are sorted by path, so a node's items are consecutive: segmented max over the warp's 32
+            // items, then one atomic per (warp, node) run instead of one per item (64-bit shared atomicMax is a CAS loop)
+            const uint32_t sg = sidx[j];
+            unsigned long long v = sg < (uint32_t)nfinal ? vv[j] : 0ull;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const unsigned long long ov = __shfl_up_sync(FULL, v, o);
+                const uint32_t os = __shfl_up_sync(FULL, sg, o);
+                if (lane >= o && os == sg) v = max(v, ov);
+            }
+            const uint32_t nx = __shfl_down_sync(FULL, sg, 1);
+            if (sg < (uint32_t)nfinal && (lane == 31 || nx != sg)) atomicMax(&best[sg], v);
+        }
     }
     __syncthreads();
     uint32_t *sel = L.sel + (size_t)frame * L.sel_cap;
@@ -459,6 +612,15 @@ k_octree(const LevelDev *__restrict__ levels, int n_levels, const int *__restric
         sel[sidx] = (uint32_t)(b & 0xffffffull) | ((uint32_t)(b >> 56) << 24);
     }
     if (tid == 0) *out_count = nfinal;
+    OCT_T(6);
+#ifdef ORBB_OCT_PROF
+    if (tid == 0 && blockIdx.x == 0 && blockIdx.y == 0)
+        printf("oct n=%d m=%d N=%d D=%d Dc=%d T=%d fast=%d mode=%d k0=%d in_smem=%d | build+sort %lld sd %lld replay %lld careful %lld final %lld cycles\n",
+               n, m, N, D, Dc, T, (int)fastp, mode, k0, (int)in_smem, prof_t[2] - prof_t[0], prof_t[3] - prof_t[2],
+               prof_t[4] - prof_t[3], prof_t[5] - prof_t[4], prof_t[6] - prof_t[5]);
+#endif
+    break;
+    }  // attempt
 }
 
 size_t octree_dyn_smem(int sel_cap_max, int pcap, int pcap2) {
@@ -468,16 +630,17 @@ size_t octree_dyn_smem(int sel_cap_max, int pcap, int pcap2) {
 template <int OCT_RB, int MIN_CTAS>
 static cudaError_t launch_octree_t(const LevelDev *d_levels, int n_levels, const int *d_cand_count, int *d_sel_count,
                                    int level_base, int n_launch_levels, int frame_base, int n_frames, int quota_override,
-                                   size_t smem, int sort_bytes, int pcap, int pcap2, cudaStream_t st) {
+                                   size_t smem, int sort_bytes, int tbl_cap_dyn, int pcap, int pcap2, cudaStream_t st) {
     const int sort_off = (int)((smem + 15) & ~(size_t)15);
     const size_t total = (size_t)sort_off + (size_t)sort_bytes;
-    if (total > 30 * 1024) {  // 48 KB default limit minus the 18 KB of static shared memory; the attribute is per device
+    if (total > 24 * 1024) {  // 48 KB default limit minus the 22 KB of static shared memory; the attribute is per device
         cudaError_t e = cudaFuncSetAttribute(k_octree<OCT_RB, MIN_CTAS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)total);
         if (e != cudaSuccess) return e;
     }
     dim3 grid(n_launch_levels, n_frames);
     k_octree<OCT_RB, MIN_CTAS><<<grid, OCT_THREADS, total, st>>>(d_levels, n_levels, d_cand_count, d_sel_count, level_base,
-                                                                 frame_base, quota_override, pcap, pcap2, sort_off, sort_bytes);
+                                                                 frame_base, quota_override, pcap, pcap2, sort_off, sort_bytes,
+                                                                 tbl_cap_dyn);
     return cudaGetLastError();
 }
 
@@ -486,19 +649,23 @@ cudaError_t launch_octree(const LevelDev *d_levels, int n_levels, const int *d_c
                           int sel_cap_max, int pcap, int pcap2, cudaStream_t st) {
     size_t smem = octree_dyn_smem(sel_cap_max, pcap, pcap2);
     if (getenv("ORBB_OCT_PAD")) smem = std::max(smem, (size_t)atoi(getenv("ORBB_OCT_PAD")));
+    // diagnostics / tests: ORBB_OCT_NOFAST=1 forces the general (radix sort) path of every CTA
+    const bool nofast = getenv("ORBB_OCT_NOFAST") != nullptr;
     // fewer CTAs than the GPU can hold at once: every CTA's own latency is the kernel's duration
     const long long ctas = (long long)n_launch_levels * n_frames;
     if (ctas <= 148 * 3) {
         // shared memory left per CTA when the grid is spread over the 148 SMs (227 KB each, 18 KB static per CTA)
         const int per_sm = (int)((ctas + 147) / 148);
-        long long spare = (227 * 1024) / per_sm - 18 * 1024 - (long long)smem - 1024;
+        long long spare = (227 * 1024) / per_sm - 22 * 1024 - (long long)smem - 1024;
         static const bool no_smem_sort = getenv("ORBB_OCT_NOSMEM") != nullptr;
         const int sort_bytes = (no_smem_sort || spare < 32 * 1024) ? 0 : (int)std::min<long long>(spare, 176 * 1024) & ~15;
+        // a 4096-cell table (depth 6 for one root, 5 for two to four) when it fits next to 32 KB of record arrays
+        const int tbl_cap_dyn = nofast ? -1 : (sort_bytes >= 10 * 4096 + 32 * 1024 ? 4096 : 0);
         return launch_octree_t<4, 3>(d_levels, n_levels, d_cand_count, d_sel_count, level_base, n_launch_levels, frame_base,
-                                     n_frames, quota_override, smem, sort_bytes, pcap, pcap2, st);
+                                     n_frames, quota_override, smem, sort_bytes, tbl_cap_dyn, pcap, pcap2, st);
     }
     return launch_octree_t<1, 4>(d_levels, n_levels, d_cand_count, d_sel_count, level_base, n_launch_levels, frame_base,
-                                 n_frames, quota_override, smem, 0, pcap, pcap2, st);
+                                 n_frames, quota_override, smem, 0, nofast ? -1 : 0, pcap, pcap2, st);
 }
 
 }  // namespace orbb

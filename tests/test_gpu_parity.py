@@ -43,6 +43,8 @@ CONFIGS = [  # (w, h, nfeatures, scale, nlevels, generator, seed)
     (1920, 1080, 3000, 1.2, 8, "textured_frame", 4100),  # full HD: widest tables, two quadtree roots
     (97, 83, 120, 1.2, 2, "textured_frame", 33),        # smallest useful frame: one or two cells per level
     (752, 480, 1000, 1.3, 6, "textured_frame", 77),     # EuRoC-sized, non-default scale (cells up to 37 px wide)
+    (848, 480, 405, 1.2, 1, "textured_frame", 2100),    # the reference's live shape: 1 level (defines.h:2), 405 cells
+    (640, 480, 1000, 1.2, 1, "textured_frame", 2101),   # single level carrying the whole quota
 ]
 
 
@@ -137,9 +139,14 @@ def _octree_case(orbb_ex, oracle, level, cand, quota, rng):
     assert as_set(got) == ref, (quota, len(cand))
 
 
-def test_octree_stress(orbb, oracle):
+@pytest.mark.parametrize("nofast", [False, True])
+def test_octree_stress(orbb, oracle, monkeypatch, nofast):
     """DistributeOctTree alone on synthetic candidate clouds: uniform, clustered, collinear, tiny; many quotas
-    so every exit (>=N after a full pass, careful phase with 1..k rounds, no growth, n < N) is hit."""
+    so every exit (>=N after a full pass, careful phase with 1..k rounds, no growth, n < N) is hit.  Run twice:
+    with the cell-table fast path (which falls back to the general path on the clustered / collinear clouds that
+    need depths below the table's), and with ORBB_OCT_NOFAST=1 forcing the general radix-sort path everywhere."""
+    if nofast:
+        monkeypatch.setenv("ORBB_OCT_NOFAST", "1")
     rng = np.random.default_rng(7)
     for (w, h) in ((640, 480), (848, 480), (1280, 720)):
         ex = orbb.ORBextractor(4000, 1.2, 2, 20, 7, width=w, height=h)
