@@ -301,7 +301,12 @@ k_fast_cells(const CUtensorMap *__restrict__ maps, const LevelDev *__restrict__ 
             slot = __shfl_sync(0xffffffffu, slot, 0);
             if (emit) {
                 const int dst = slot + __popc(bm & lt_mask);
-                if (dst < L.cand_cap) cand[dst] = packed;
+                if (dst < L.cand_cap) {
+                    cand[dst] = packed;
+                    // the quadtree kernel's cell table is filled here: fire-and-forget L2 atomics spread over every SM
+                    // instead of shared-memory atomics inside the one CTA that owns the (frame, level)
+                    if (L.tbl_cells) oct_bin_candidate(L, frame, packed);
+                }
             }
         }
     }

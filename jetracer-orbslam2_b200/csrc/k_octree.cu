@@ -41,14 +41,12 @@ __device__ long long g_oct_prof[64];
 #define OCT_THREADS 512
 #define OCT_WARPS (OCT_THREADS / 32)
 #define FULL 0xffffffffu
-#define OCT_TBL_STATIC 2048  // cells of the static cell table: 8 B x 2048 = the 16 KB of whist (OCT_WARPS x 256 x 4)
 
 struct OctStatic {
     uint32_t whist[OCT_WARPS][256];
     uint32_t digit_base[256];
     int hist_sd[40], hist_g[40];
     uint32_t warp_tot[OCT_WARPS];
-    uint32_t tcnt[OCT_TBL_STATIC / 2];  // cell-table key counts (2 x u16 per word); the cells' best keys alias whist
     int ctl[16];
 };
 enum { C_MODE = 0, C_DEPTH, C_SIZE, C_PN, C_QN, C_CUT, C_TOTAL, C_NFINAL, C_BAIL };
@@ -235,7 +233,7 @@ template <int OCT_RB, int MIN_CTAS>
 __global__ void __launch_bounds__(OCT_THREADS, MIN_CTAS)
 k_octree(const LevelDev *__restrict__ levels, int n_levels, const int *__restrict__ cand_count,
          int *__restrict__ sel_count, int level_base, int frame_base, int quota_override, int pcap, int pcap2,
-         int sort_off, int sort_bytes, int tbl_cap_dyn) {
+         int sort_off, int sort_bytes, int no_fast) {
     __shared__ OctStatic S;
     extern __shared__ __align__(16) uint8_t dyn[];
     const int tid = threadIdx.x, lane = tid & 31;
@@ -270,24 +268,19 @@ k_octree(const LevelDev *__restrict__ levels, int n_levels, const int *__restric
     const int D = L.depth;
 
     // ---- CELL-TABLE FAST PATH.  The selection only ever looks at the tree down to the depth at which ~N nodes exist
-    // (4-6 for the quotas of a pyramid level), while the path keys resolve single pixels (D ~ 10).  So the candidates
-    // are first binned into the 4^Dc cells of depth Dc: per cell a key count and the best key (response, then
-    // earliest upstream order).  Cell index = path prefix, so the table IS the sorted order: one prefix scan
-    // compacts the non-empty cells into "records" (path prefix, running key count) -- no radix sort, and every later
-    // pass runs over the records (a third of the keys) instead of the keys.  Node sizes come from the running key
-    // counts; everything else (parting depths, breadth-first replay, careful phase) is unchanged as long as it stays
-    // at depths <= Dc.  If it would go deeper (heavily clustered keys), the CTA falls back to the general path below.
-    const int root_bits = L.key_bits - 2 * D;
-    const int tbl_cap = tbl_cap_dyn > 0 ? tbl_cap_dyn : OCT_TBL_STATIC;
-    int Dc = 0;
-    for (int dd = min(D, 6); dd >= 1; --dd)
-        if ((1 << (root_bits + 2 * dd)) <= tbl_cap) { Dc = dd; break; }
-    const int T = 1 << (root_bits + 2 * Dc);
-    const bool try_fast = tbl_cap_dyn >= 0 && Dc > 0 && T >= 4 * N && n < L.cand_cap;
-    unsigned long long *tbl_best = tbl_cap_dyn > 0 ? reinterpret_cast<unsigned long long *>(dyn + sort_off)
-                                                   : reinterpret_cast<unsigned long long *>(&S.whist[0][0]);
-    uint32_t *tbl_cnt = tbl_cap_dyn > 0 ? reinterpret_cast<uint32_t *>(tbl_best + tbl_cap_dyn) : S.tcnt;  // 2 x u16 per word
-    const int tbl_bytes = tbl_cap_dyn > 0 ? tbl_cap_dyn * 10 : 0;
+    // (4-6 for the quotas of a pyramid level), while the path keys resolve single pixels (D ~ 10).  The FAST kernel
+    // therefore bins every candidate it emits into the 4^Dc cells of depth Dc (L.tbl_cnt / L.tbl_best in global
+    // memory: per cell a key count and the best key -- response, then earliest upstream order).  Cell index = path
+    // prefix, so the table IS the sorted order: one prefix scan compacts the non-empty cells into "records" (path
+    // prefix, running key count) -- no radix sort, and every later pass runs over the records (a quarter of the
+    // keys) instead of the keys.  Node sizes come from the running key counts; everything else (parting depths,
+    // breadth-first replay, careful phase) is unchanged as long as it stays at depths <= Dc.  If it would go deeper
+    // (heavily clustered keys), or the table does not describe this candidate list, the CTA falls back to the
+    // general path below.  The CTA clears its table before it exits.
+    const int Dc = L.tbl_dc, T = L.tbl_cells;
+    const bool try_fast = !no_fast && T > 0 && T >= 4 * N && n < L.cand_cap;
+    uint32_t *tbl_cnt = L.tbl_cnt + (size_t)frame * T;
+    unsigned long long *tbl_best = L.tbl_best + (size_t)frame * T;
     const int csh = 2 * (D - Dc);  // path key -> cell index
 
     for (int attempt = try_fast ? 0 : 1; attempt < 2; ++attempt) {
@@ -298,50 +291,26 @@ k_octree(const LevelDev *__restrict__ levels, int n_levels, const int *__restric
     bool in_smem;
     if (fastp) {
         const int mc = (min(T, n) + 1 + 15) & ~15;  // records + sentinel
-        in_smem = (size_t)mc * 16 + (size_t)tbl_bytes <= (size_t)sort_bytes;
-        kva = in_smem ? reinterpret_cast<uint2 *>(dyn + sort_off + tbl_bytes) : L.kv_a + fo;
+        in_smem = (size_t)mc * 16 <= (size_t)sort_bytes;
+        kva = in_smem ? reinterpret_cast<uint2 *>(dyn + sort_off) : L.kv_a + fo;
         kvb = in_smem ? kva + mc : L.kv_b + fo;
         key_stride = in_smem ? mc : L.cand_cap;
-        for (int i = tid; i < T; i += OCT_THREADS) tbl_best[i] = 0ull;
-        for (int i = tid; i < (T + 1) / 2; i += OCT_THREADS) tbl_cnt[i] = 0u;
-        __syncthreads();
-        // ---- F1. bin the candidates
-        for (int base = tid; base < n; base += OCT_RB * OCT_THREADS) {
-            uint32_t c[OCT_RB], kx[OCT_RB], ky[OCT_RB], xo[OCT_RB], yo[OCT_RB];
-#pragma unroll
-            for (int j = 0; j < OCT_RB; ++j) c[j] = base + j * OCT_THREADS < n ? cand[base + j * OCT_THREADS] : 0u;
-#pragma unroll
-            for (int j = 0; j < OCT_RB; ++j) {
-                kx[j] = __ldg(&L.xkey[c[j] & 0xfffu]); ky[j] = __ldg(&L.ykey[(c[j] >> 12) & 0xfffu]);
-                xo[j] = __ldg(&L.xord[c[j] & 0xfffu]); yo[j] = __ldg(&L.yord[(c[j] >> 12) & 0xfffu]);
-            }
-#pragma unroll
-            for (int j = 0; j < OCT_RB; ++j)
-                if (base + j * OCT_THREADS < n) {
-                    const uint32_t cell = (kx[j] | ky[j]) >> csh;
-                    const uint32_t ord = ((yo[j] >> 6) << 19) | ((xo[j] >> 6) << 12) | ((yo[j] & 63u) << 6) | (xo[j] & 63u);
-                    const unsigned long long v = ((unsigned long long)(c[j] >> 24) << 56) |
-                                                 ((unsigned long long)(0x3ffffffu - ord) << 24) | (c[j] & 0xffffffu);
-                    atomicAdd(&tbl_cnt[cell >> 1], 1u << (16 * (cell & 1u)));
-                    atomicMax(&tbl_best[cell], v);
-                }
-        }
-        __syncthreads();
-        // ---- F2. compact the non-empty cells (already in path order) into records
+        // ---- F. compact the non-empty cells (already in path order) into records; T <= 4096 = 8 cells per thread
         const int per = (T + OCT_THREADS - 1) / OCT_THREADS;
-        const int c0 = min(T, tid * per), c1 = min(T, c0 + per);
-        uint32_t my_cells = 0, my_keys = 0;
-        for (int cidx = c0; cidx < c1; ++cidx) {
-            const uint32_t w = (tbl_cnt[cidx >> 1] >> (16 * (cidx & 1))) & 0xffffu;
-            my_cells += w != 0; my_keys += w;
-        }
+        const int c0 = min(T, tid * per);
+        uint32_t w[8], my_cells = 0, my_keys = 0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) w[k] = (k < per && c0 + k < T) ? tbl_cnt[c0 + k] : 0u;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { my_cells += w[k] != 0; my_keys += w[k]; }
         uint32_t tot_cells, tot_keys;
         uint32_t pos = block_excl_scan(my_cells, S.warp_tot, &tot_cells);
         uint32_t run = block_excl_scan(my_keys, S.warp_tot, &tot_keys);
-        for (int cidx = c0; cidx < c1; ++cidx) {
-            const uint32_t w = (tbl_cnt[cidx >> 1] >> (16 * (cidx & 1))) & 0xffffu;
-            if (w) { kva[pos++] = make_uint2((uint32_t)cidx << csh, run); run += w; }
-        }
+        // the table must describe exactly this candidate list (it would not after, say, two detect calls in a row)
+        if (tot_keys != (uint32_t)n) continue;  // block-uniform
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+            if (w[k]) { kva[pos++] = make_uint2((uint32_t)(c0 + k) << csh, run); run += w[k]; }
         m = (int)tot_cells;
         if (tid == 0) kva[m] = make_uint2(0xffffffffu, tot_keys);  // sentinel: closes the last record's key count
         __syncthreads();
@@ -621,6 +590,26 @@ k_octree(const LevelDev *__restrict__ levels, int n_levels, const int *__restric
 #endif
     break;
     }  // attempt
+    if (T > 0) {  // hand the FAST kernel of the next batch an empty table
+        for (int i = tid; i < T; i += OCT_THREADS) { tbl_cnt[i] = 0u; tbl_best[i] = 0ull; }
+    }
+}
+
+// The cell table of a candidate list that did not come from the FAST kernel (orbb_debug_distribute uploads one).
+__global__ void k_octree_bin(const LevelDev *__restrict__ levels, int n_levels, const int *__restrict__ cand_count, int level,
+                             int frame_base) {
+    const LevelDev &L = levels[level];
+    const int frame = blockIdx.y + frame_base;
+    if (!L.tbl_cells) return;
+    const int n = min(cand_count[frame * n_levels + level], L.cand_cap - 1);
+    const uint32_t *cand = L.cand + (size_t)frame * L.cand_cap;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) oct_bin_candidate(L, frame, cand[i]);
+}
+
+cudaError_t launch_octree_bin(const LevelDev *d_levels, int n_levels, const int *d_cand_count, int level, int frame_base,
+                              int n_frames, cudaStream_t st) {
+    k_octree_bin<<<dim3(32, n_frames), 256, 0, st>>>(d_levels, n_levels, d_cand_count, level, frame_base);
+    return cudaGetLastError();
 }
 
 size_t octree_dyn_smem(int sel_cap_max, int pcap, int pcap2) {
@@ -630,17 +619,17 @@ size_t octree_dyn_smem(int sel_cap_max, int pcap, int pcap2) {
 template <int OCT_RB, int MIN_CTAS>
 static cudaError_t launch_octree_t(const LevelDev *d_levels, int n_levels, const int *d_cand_count, int *d_sel_count,
                                    int level_base, int n_launch_levels, int frame_base, int n_frames, int quota_override,
-                                   size_t smem, int sort_bytes, int tbl_cap_dyn, int pcap, int pcap2, cudaStream_t st) {
+                                   size_t smem, int sort_bytes, int no_fast, int pcap, int pcap2, cudaStream_t st) {
     const int sort_off = (int)((smem + 15) & ~(size_t)15);
     const size_t total = (size_t)sort_off + (size_t)sort_bytes;
-    if (total > 24 * 1024) {  // 48 KB default limit minus the 22 KB of static shared memory; the attribute is per device
+    if (total > 30 * 1024) {  // 48 KB default limit minus the 18 KB of static shared memory; the attribute is per device
         cudaError_t e = cudaFuncSetAttribute(k_octree<OCT_RB, MIN_CTAS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)total);
         if (e != cudaSuccess) return e;
     }
     dim3 grid(n_launch_levels, n_frames);
     k_octree<OCT_RB, MIN_CTAS><<<grid, OCT_THREADS, total, st>>>(d_levels, n_levels, d_cand_count, d_sel_count, level_base,
                                                                  frame_base, quota_override, pcap, pcap2, sort_off, sort_bytes,
-                                                                 tbl_cap_dyn);
+                                                                 no_fast);
     return cudaGetLastError();
 }
 
@@ -656,16 +645,17 @@ cudaError_t launch_octree(const LevelDev *d_levels, int n_levels, const int *d_c
     if (ctas <= 148 * 3) {
         // shared memory left per CTA when the grid is spread over the 148 SMs (227 KB each, 18 KB static per CTA)
         const int per_sm = (int)((ctas + 147) / 148);
-        long long spare = (227 * 1024) / per_sm - 22 * 1024 - (long long)smem - 1024;
+        long long spare = (227 * 1024) / per_sm - 18 * 1024 - (long long)smem - 1024;
         static const bool no_smem_sort = getenv("ORBB_OCT_NOSMEM") != nullptr;
         const int sort_bytes = (no_smem_sort || spare < 32 * 1024) ? 0 : (int)std::min<long long>(spare, 176 * 1024) & ~15;
-        // a 4096-cell table (depth 6 for one root, 5 for two to four) when it fits next to 32 KB of record arrays
-        const int tbl_cap_dyn = nofast ? -1 : (sort_bytes >= 10 * 4096 + 32 * 1024 ? 4096 : 0);
+        if (ctas <= 148)  // at most one CTA per SM: registers are free, keep 8 loads per thread in flight
+            return launch_octree_t<8, 1>(d_levels, n_levels, d_cand_count, d_sel_count, level_base, n_launch_levels, frame_base,
+                                         n_frames, quota_override, smem, sort_bytes, nofast, pcap, pcap2, st);
         return launch_octree_t<4, 3>(d_levels, n_levels, d_cand_count, d_sel_count, level_base, n_launch_levels, frame_base,
-                                     n_frames, quota_override, smem, sort_bytes, tbl_cap_dyn, pcap, pcap2, st);
+                                     n_frames, quota_override, smem, sort_bytes, nofast, pcap, pcap2, st);
     }
     return launch_octree_t<1, 4>(d_levels, n_levels, d_cand_count, d_sel_count, level_base, n_launch_levels, frame_base,
-                                 n_frames, quota_override, smem, 0, nofast ? -1 : 0, pcap, pcap2, st);
+                                 n_frames, quota_override, smem, 0, nofast, pcap, pcap2, st);
 }
 
 }  // namespace orbb

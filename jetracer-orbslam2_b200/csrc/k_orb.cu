@@ -34,7 +34,9 @@ __device__ __forceinline__ float fast_atan2_deg(float y, float x) {
 }
 
 #define ORB_WARPS 4
-#define ORB_KPW 8                       // keypoint slots per warp: the per-keypoint scalar math runs one slot per lane
+// keypoint slots per warp = template parameter KPW: the per-keypoint scalar math runs one slot per lane, so large
+// batches use 8 (fewest instructions per keypoint); small batches use 2 or 1 so that a lone frame's ~1000 keypoints
+// spread over all SMs instead of queueing 8 deep behind 40 CTAs (848x480 single frame: 18.7 -> see DESIGN.md)
 #define PATCH_R 19                      // rotated pattern reach: |(13,13)| = 18.4 -> 19
 #define PATCH_ROWS (2 * PATCH_R + 1)    // 39
 #define PATCH_PITCH 44                  // 11 aligned words cover 39 columns at any byte phase
@@ -44,13 +46,14 @@ __device__ __forceinline__ constexpr int umax_of(int av) {
     return (int)((0x3689ABCDDEEEFFFFull >> (4 * av)) & 15ull);
 }
 
-// warp = ORB_KPW consecutive keypoint slots, warp-synchronous (no block barriers):
+// warp = KPW consecutive keypoint slots, warp-synchronous (no block barriers):
 //   phase 0  lanes 0..7: slot -> (level, x, y, response, output index), kept in registers and broadcast by shuffle
 //   phase A  per slot: IC_Angle moments, lane = patch column (coalesced row reads of the un-blurred level)
 //   phase S  lanes 0..7: fastAtan2, sincos(double) and the cv::KeyPoint record -- the scalar chain that a
 //            warp-per-keypoint kernel would execute 32x redundantly now runs once per 8 keypoints
 //   phase B  per slot: stage the 39x39 blurred patch, lane i builds descriptor byte i (its 16 pattern points sit in
 //            registers as floats, converted once per warp)
+template <int ORB_KPW>
 __global__ void __launch_bounds__(ORB_WARPS * 32, 8)
 k_angle_orb(const LevelDev *__restrict__ levels, int n_levels, const int *__restrict__ sel_count,
             const int8_t *__restrict__ pattern, const int *__restrict__ slot_level, const int *__restrict__ slot_base,
@@ -191,10 +194,17 @@ k_angle_orb(const LevelDev *__restrict__ levels, int n_levels, const int *__rest
 cudaError_t launch_angle_orb(const LevelDev *d_levels, int n_levels, const int *d_sel_count, const int8_t *d_pattern,
                              const int *d_slot_level, const int *d_slot_base, int n_slots, int frame_base,
                              int n_frames, orbb_keypoint *d_kp, uint8_t *d_desc, int *d_counts, int max_kp, cudaStream_t st) {
-    const int per_cta = ORB_WARPS * ORB_KPW;
+    const long long slots = (long long)n_slots * n_frames;
+    const int kpw = slots >= 32768 ? 8 : (slots >= 8192 ? 2 : 1);
+    const int per_cta = ORB_WARPS * kpw;
     dim3 grid((n_slots + per_cta - 1) / per_cta, n_frames);
-    k_angle_orb<<<grid, ORB_WARPS * 32, 0, st>>>(d_levels, n_levels, d_sel_count, d_pattern, d_slot_level, d_slot_base,
-                                                 n_slots, d_kp, d_desc, d_counts, max_kp, frame_base);
+#define ORBB_LAUNCH_ORB(K)                                                                                             \
+    k_angle_orb<K><<<grid, ORB_WARPS * 32, 0, st>>>(d_levels, n_levels, d_sel_count, d_pattern, d_slot_level, d_slot_base, \
+                                                    n_slots, d_kp, d_desc, d_counts, max_kp, frame_base)
+    if (kpw == 8) ORBB_LAUNCH_ORB(8);
+    else if (kpw == 2) ORBB_LAUNCH_ORB(2);
+    else ORBB_LAUNCH_ORB(1);
+#undef ORBB_LAUNCH_ORB
     return cudaGetLastError();
 }
 

@@ -23,6 +23,7 @@ bool build_fast_tma_maps(void *, const LevelDev *, int, int, const FastSmemCfg &
 size_t fast_tma_maps_bytes();
 cudaError_t launch_fast_dump(const void *, const LevelDev *, const CellEntry *, int, int, int, int, const FastSmemCfg &, int,
                              uint8_t *, const long long *, cudaStream_t);
+cudaError_t launch_octree_bin(const LevelDev *, int, const int *, int, int, int, cudaStream_t);
 cudaError_t launch_octree(const LevelDev *, int, const int *, int *, int, int, int, int, int, int, int, int,
                           cudaStream_t);
 size_t octree_dyn_smem(int, int, int);
@@ -412,6 +413,19 @@ extern "C" int orbb_create(orbb_handle **out, const orbb_params *params, int wid
         CKC(dalloc(h, &L.cand, cc)); CKC(dalloc(h, &L.kv_a, cc)); CKC(dalloc(h, &L.kv_b, cc));
         CKC(dalloc(h, &L.sd, cc));
         CKC(dalloc(h, &L.sel, (size_t)L.sel_cap * B));
+        // cell table of the quadtree fast path: the shallowest depth with >= 4 x quota cells (the selection stops
+        // near the depth with ~quota nodes and may part one level deeper), at most 4096 cells and depth 6
+        L.tbl_dc = 0; L.tbl_cells = 0;
+        for (int dd = 1; dd <= std::min(D, 6) && (1 << (root_bits + 2 * dd)) <= 4096; ++dd) {
+            L.tbl_dc = dd; L.tbl_cells = 1 << (root_bits + 2 * dd);
+            if (L.tbl_cells >= 4 * L.nfeat) break;
+        }
+        if (L.tbl_cells) {
+            CKC(dalloc(h, &L.tbl_cnt, (size_t)L.tbl_cells * B));
+            CKC(dalloc(h, &L.tbl_best, (size_t)L.tbl_cells * B));
+            CKC(cudaMemset(L.tbl_cnt, 0, sizeof(uint32_t) * (size_t)L.tbl_cells * B));
+            CKC(cudaMemset(L.tbl_best, 0, sizeof(unsigned long long) * (size_t)L.tbl_cells * B));
+        }
         slot_base[l] = (int)slot_level.size();
         for (int s = 0; s < L.sel_cap; ++s) slot_level.push_back(l);
         h->sel_cap_max = std::max(h->sel_cap_max, L.sel_cap);
@@ -1077,6 +1091,7 @@ extern "C" int orbb_debug_distribute(orbb_handle *h, int level, const int32_t *h
     CK(h, cudaDeviceSynchronize());
     CK(h, cudaMemcpy(L.cand, packed.data(), sizeof(uint32_t) * (size_t)n, cudaMemcpyHostToDevice));
     CK(h, cudaMemcpy(h->d_cand_count + level, &n, sizeof(int), cudaMemcpyHostToDevice));
+    CK(h, launch_octree_bin(h->d_levels, h->nlevels, h->d_cand_count, level, 0, 1, 0));  // what the FAST kernel does while emitting
     CK(h, launch_octree(h->d_levels, h->nlevels, h->d_cand_count, h->d_sel_count, level, 1, 0, 1, quota, h->sel_cap_max,
                         h->pcap, h->pcap2, 0));
     return orbb_debug_get_selected(h, 0, level, host_out_xyr, max_out);

@@ -49,8 +49,29 @@ struct LevelDev {
     uint2 *kv_a, *kv_b;          // B x cand_cap each: (path key, candidate index) pairs, radix ping-pong
     uint8_t *sd;                 // B x cand_cap: split depth of adjacent sorted keys
     uint32_t *sel;               // B x sel_cap packed selected keys
+    // quadtree cell table (k_octree fast path), filled by the FAST kernel while it emits the candidates and cleared
+    // by the quadtree kernel: per depth-tbl_dc tree cell the number of candidates and the best one
+    int tbl_dc, tbl_cells;       // cells = 2^(root_bits + 2*tbl_dc); 0 = no table for this level
+    uint32_t *tbl_cnt;           // B x tbl_cells
+    unsigned long long *tbl_best;  // B x tbl_cells: (response << 56) | ((0x3ffffff - upstream order) << 24) | (x | y << 12)
     float scale, patch_size;     // mvScaleFactor[l], (float)(int)(31*scale)
 };
+
+#ifdef __CUDACC__
+// Adds one packed candidate (x:12 | y:12 | m:8, coordinates relative to the 16-px border) to its tree cell.
+__device__ __forceinline__ void oct_bin_candidate(const LevelDev &L, int frame, uint32_t c) {
+    const uint32_t kx = __ldg(&L.xkey[c & 0xfffu]), ky = __ldg(&L.ykey[(c >> 12) & 0xfffu]);
+    const uint32_t xo = __ldg(&L.xord[c & 0xfffu]), yo = __ldg(&L.yord[(c >> 12) & 0xfffu]);
+    const uint32_t cell = (kx | ky) >> (2 * (L.depth - L.tbl_dc));
+    // upstream candidate order = (cell row, cell col, y in cell, x in cell); unique per pixel
+    const uint32_t ord = ((yo >> 6) << 19) | ((xo >> 6) << 12) | ((yo & 63u) << 6) | (xo & 63u);
+    const unsigned long long v = ((unsigned long long)(c >> 24) << 56) | ((unsigned long long)(0x3ffffffu - ord) << 24) |
+                                 (c & 0xffffffu);
+    const size_t at = (size_t)frame * L.tbl_cells + cell;
+    atomicAdd(&L.tbl_cnt[at], 1u);
+    atomicMax(&L.tbl_best[at], v);
+}
+#endif
 
 struct CellEntry {  // one FAST work item = one upstream 30-px cell
     int16_t level, x0, y0, cw, ch, pad0, pad1, pad2;  // tested-range origin (ROI coords) and size
