@@ -80,6 +80,7 @@ k_fast_cells(const CUtensorMap *__restrict__ maps, const LevelDev *__restrict__ 
     const int tp = TMA ? cfg.tma_pitch : cfg.tile_pitch, sp = cfg.score_pitch, tpw = tp >> 2;
     const int cw = c.cw, ch = c.ch;
     const uint32_t *tile32 = reinterpret_cast<const uint32_t *>(tile);
+    pdl_wait();  // launched as a programmatic dependent of the last pyramid kernel: the levels are complete from here on
 
     // ---- stage the window, RE-ALIGNED: shared-memory byte column k <-> image column x0 - 4 + k, so the
     // cell's first tested pixel sits at byte 4 of each row and groups of 4 pixels are whole 32-bit words.
@@ -323,9 +324,8 @@ static cudaError_t launch_fast_t(const CUtensorMap *maps, const LevelDev *d_leve
         cudaError_t e = cudaFuncSetAttribute(k_fast_cells<DUMP, TMA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
     }
-    k_fast_cells<DUMP, TMA><<<grid, FAST_WARPS * 32, smem, st>>>(maps, d_levels, d_cells, n_cells, n_levels, d_cand_count,
-                                                                  t_lo, t_hi, cfg, frame_base, d_dump, d_dump_off);
-    return cudaGetLastError();
+    return launch_pdl(k_fast_cells<DUMP, TMA>, grid, dim3(FAST_WARPS * 32), smem, st, maps, d_levels, d_cells, n_cells, n_levels,
+                      d_cand_count, t_lo, t_hi, cfg, frame_base, d_dump, d_dump_off);
 }
 
 cudaError_t launch_fast(const void *tma_maps, const LevelDev *d_levels, const CellEntry *d_cells, int n_cells,

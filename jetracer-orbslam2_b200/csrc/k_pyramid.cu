@@ -27,6 +27,7 @@ __device__ __forceinline__ int reflect101(int p, int len) {
 // bytewise route.
 __global__ void __launch_bounds__(256) k_level0(const uint8_t *__restrict__ in, size_t in_pitch, size_t in_stride,
                                                 LevelDev L, int n_int, int n_edge, int frame_base) {
+    pdl_trigger();  // the first resize kernel may be scheduled now; it waits for this grid before reading level 0
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const int frame = blockIdx.y + frame_base;
     const uint8_t *fsrc = in + (size_t)blockIdx.y * in_stride;
@@ -195,6 +196,7 @@ template <bool AREA>
 __global__ void __launch_bounds__(32 * RS_ROWS) k_resize_rows(const ResizeArgs A, int frame_base) {
     const int q = blockIdx.x * 32 + threadIdx.x;
     const int py0 = blockIdx.y * (2 * RS_ROWS) + threadIdx.y;
+    pdl_trigger();
     if (q >= A.nq || py0 >= A.rows) return;
     const int frame = blockIdx.z + frame_base;
     const uint4 hx = __ldg(A.rs_h + 2 * q), hw = __ldg(A.rs_h + 2 * q + 1);
@@ -204,6 +206,7 @@ __global__ void __launch_bounds__(32 * RS_ROWS) k_resize_rows(const ResizeArgs A
     // two output rows per thread (py0 and py0 + RS_ROWS): 16 independent loads in flight
     const int py1 = min(py0 + RS_ROWS, A.rows - 1);
     int4 v[2] = {__ldg(A.rs_v + py0), __ldg(A.rs_v + py1)};
+    pdl_wait();  // the tables above are constant; the source level is written by the previous kernel
     unsigned w[2][8];
 #pragma unroll
     for (int r = 0; r < 2; ++r) {
@@ -319,9 +322,8 @@ cudaError_t launch_resize(const LevelDev *d_levels, const LevelDev *h_levels, in
         A.rs_h = Lh.rs_h; A.rs_v = Lh.rs_v;
         A.src_pitch = Sh.pitch; A.dst_pitch = Lh.pitch; A.nq = Lh.rs_nq; A.rows = Lh.rows;
         dim3 grid((Lh.rs_nq + 31) / 32, (Lh.rows + 2 * RS_ROWS - 1) / (2 * RS_ROWS), n_frames), block(32, RS_ROWS);
-        if (Lh.area2x) k_resize_rows<true><<<grid, block, 0, st>>>(A, frame_base);
-        else k_resize_rows<false><<<grid, block, 0, st>>>(A, frame_base);
-        return cudaGetLastError();
+        if (Lh.area2x) return launch_pdl(k_resize_rows<true>, grid, block, 0, st, A, frame_base);
+        return launch_pdl(k_resize_rows<false>, grid, block, 0, st, A, frame_base);
     }
     // worst-case source window of one tile (+ slack for clamping/alignment)
     const int src_cols = (int)((double)RS_TW * Sh.w / Lh.w) + 8;

@@ -58,6 +58,26 @@ struct LevelDev {
 };
 
 #ifdef __CUDACC__
+// Programmatic dependent launch (PDL): a kernel launched with launch_pdl() may become resident while its predecessor
+// in the stream is still running; it must call pdl_wait() before it touches anything the predecessor writes
+// (griddepcontrol.wait returns once the predecessor grid has completed and its writes are visible).  A kernel
+// calls pdl_trigger() as early as it likes to allow ITS successor to be scheduled.  Both are no-ops in a normal
+// launch.  Used for the level0 -> resize x7 -> FAST chain, where a lone frame's kernels are shorter than a launch gap.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                                     Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
 // Adds one packed candidate (x:12 | y:12 | m:8, coordinates relative to the 16-px border) to its tree cell.
 __device__ __forceinline__ void oct_bin_candidate(const LevelDev &L, int frame, uint32_t c) {
     const uint32_t kx = __ldg(&L.xkey[c & 0xfffu]), ky = __ldg(&L.ykey[(c >> 12) & 0xfffu]);
