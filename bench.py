@@ -39,12 +39,13 @@ MAP_SIZE = 50_000
 LEVEL_PIXELS = 950_532    # sum_l w_l*h_l for 640x480, 8 levels, 1.2
 BYTES_PER_FRAME = W * H + 2 * LEVEL_PIXELS + 60 * NFEAT  # 2,268,264 B
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE k_fast_cells launch, per frame, from the committed
-# ncu --set full capture profiles/r01j_all_kernels_full.txt (135.4 MB + 8.56 MB for a 128-frame launch)
-FAST_DRAM_TRAFFIC_PER_FRAME = (135.4e6 + 8.563e6) / 128
+# ncu --set full capture profiles/r01m_all_kernels_full.txt (146.8 MB + 17.25 MB for a 128-frame launch; the writes
+# include the quadtree cell tables the kernel fills through L2 atomics)
+FAST_DRAM_TRAFFIC_PER_FRAME = (146.8e6 + 17.25e6) / 128
 # thread instructions executed per frame by the six extraction kernels (thread_inst_executed of the same capture:
-# level0 0.286 G + resize x7 2.309 G + FAST 8.698 G + quadtree 2.016 G + blur 2.473 G + angle/rBRIEF 2.425 G per 128
+# level0 0.289 G + resize x7 2.337 G + FAST 8.777 G + quadtree 1.162 G + blur 2.473 G + angle/rBRIEF 2.425 G per 128
 # frames) -- the path is issue bound, so the step is also reported against the SM issue roofline
-THREAD_INST_PER_FRAME = (0.2857e9 + 2.3089e9 + 8.698e9 + 2.016e9 + 2.473e9 + 2.425e9) / 128
+THREAD_INST_PER_FRAME = (0.2891e9 + 2.3371e9 + 8.777e9 + 1.162e9 + 2.473e9 + 2.425e9) / 128
 
 
 def measured_peaks():
@@ -553,7 +554,7 @@ def main():
                               "issue_peak_tinst_s": 148 * 4 * 32 * f_mhz * 1e6 / 1e12,
                               "frac_of_issue": THREAD_INST_PER_FRAME * fps / world / (148 * 4 * 32 * f_mhz * 1e6),
                               "note": "integer-issue bound path: 148 SMs x 4 schedulers x 32 lanes x SM clock; "
-                                      "instruction counts from profiles/r01j_all_kernels_full.txt"},
+                                      "instruction counts from profiles/r01m_all_kernels_full.txt"},
             "stages_ms": dict(zip(stage_names, stage_ms)),
             "keypoints_per_frame": float(kp_total.item()) / (B * world),
             "gather": {"ms": gather_ms, "what": "all_gather of per-frame counts + ragged gather of {q,t,dist} match "

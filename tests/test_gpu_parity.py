@@ -546,3 +546,22 @@ def test_large_batch_paths_equal_single_frame(orbb, synth, nb):
         n = int(cnt[f])
         assert len(k1) == n and k1.tobytes() == kp[f, :n].tobytes() and d1.tobytes() == desc[f, :n].tobytes(), f"frame {f}"
     ex.close(); one.close()
+
+
+def test_reference_gpu_kernels_baseline_runs(synth, tmp_path):
+    """The timing baseline built from the reference's own .cu files (oracle/_ref/ref_gpu_bench, `make -C oracle
+    ref_gpu`) runs on this GPU and reports one keypoint per 32x32 cell.  It is a different algorithm (FAST-12, one
+    level, 32-bit hashes), so only its well-formedness is checked here; bench.py reports its timings."""
+    import json
+    import subprocess
+    exe = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "_ref", "ref_gpu_bench")
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/ref_gpu_bench not built (needs /root/reference at build time)")
+    w, h = 848, 480
+    raw = tmp_path / "frame.raw"
+    synth.textured_frame(w, h, 2000).tofile(raw)
+    r = subprocess.run([exe, str(raw), str(w), str(h), "20"], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stderr[-400:]
+    d = json.loads(r.stdout.strip().splitlines()[-1])
+    assert d["cells"] == 27 * 15 and 0 < d["keypoints"] <= d["cells"]
+    assert d["frame_latency_us"] > 0 and set(d["stages_us"]) >= {"detect", "calc_orb", "compute_fast_angle"}
