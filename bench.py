@@ -163,6 +163,13 @@ def run_reference(args):
         "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
+    refgpu = None if getattr(args, "no_refgpu", False) else run_reference_gpu_binary()
+    if refgpu is not None:
+        # the reference has no CPU extractor; what it does have are its GPU kernels, timed here on one 848x480 frame
+        # (its live configuration) -- a different algorithm, so it is reported beside the line's metric, not as it
+        line["reference_gpu_kernels"] = {"what": "reference src/cuda kernels recompiled for sm_100a, one 848x480 frame "
+                                                 "per call (FAST-12, 1 level, 405 cells, 32-bit hashes): timing only",
+                                         "reference": refgpu}
     print(json.dumps(line))
 
 
@@ -241,32 +248,40 @@ def bench_rgbd_stage(orbb, torch, device_index, steps, warmup):
                       "frac_of_hbm": align_bytes / (align_ms * 1e-3) / 1e9 / hbm_peak, "peak_kind": peak_kind}}
 
 
-def bench_reference_gpu_kernels(orbb, torch, device_index):
-    """The reference's OWN front-end kernels recompiled for sm_100a (oracle/_ref/ref_gpu_bench, built by
-    `make -C oracle ref_gpu` from the sources under /root/reference; its stage sequence of buildStream.cpp:424-466)
-    timed on this GPU in a separate process, next to the product on the same 848x480 frame (reference Context.h:16-17).
-    DIFFERENT ALGORITHM (FAST-12 float score on one blurred level, one keypoint per 32x32 cell, 32-bit hash):
-    timing baseline only, not a parity check.  Returns None when the binary did not travel with the snapshot."""
+def run_reference_gpu_binary(w=848, h=480, iters=200):
+    """Runs oracle/_ref/ref_gpu_bench (the reference's OWN front-end kernels recompiled for sm_100a by `make -C oracle
+    ref_gpu` from the sources under /root/reference; stage sequence of buildStream.cpp:424-466) in a separate process
+    on one synthetic w x h frame and returns its JSON, None when the binary did not travel with the snapshot."""
     import subprocess
     import tempfile
     exe = os.path.join(ROOT, "oracle", "_ref", "ref_gpu_bench")
     if not os.path.exists(exe):
         return None
     synth = importlib.import_module(PKG + ".synth")
-    w, h = 848, 480
     frame = synth.textured_frame(w, h, 2000)
     with tempfile.NamedTemporaryFile(suffix=".raw", delete=False) as f:
         frame.tofile(f)
         path = f.name
     try:
-        r = subprocess.run([exe, path, str(w), str(h), "200"], capture_output=True, text=True, timeout=90)
-        ref = json.loads(r.stdout.strip().splitlines()[-1]) if r.returncode == 0 and r.stdout.strip() else None
+        r = subprocess.run([exe, path, str(w), str(h), str(iters)], capture_output=True, text=True, timeout=90)
+        if r.returncode == 0 and r.stdout.strip():
+            return json.loads(r.stdout.strip().splitlines()[-1])
+        return {"error": (r.stderr or "no output")[-200:]}
     except Exception as e:  # a baseline that fails to run is reported, never fatal
-        ref = {"error": repr(e)[:200]}
+        return {"error": repr(e)[:200]}
     finally:
         os.unlink(path)
+
+
+def bench_reference_gpu_kernels(orbb, torch, device_index):
+    """The reference's own kernels on this GPU (run_reference_gpu_binary) next to the product on the same 848x480
+    frame (reference Context.h:16-17).  DIFFERENT ALGORITHM (FAST-12 float score on one blurred level, one keypoint
+    per 32x32 cell, 32-bit hash): timing baseline only, not a parity check."""
+    w, h = 848, 480
+    ref = run_reference_gpu_binary(w, h)
     if ref is None:
-        ref = {"error": (r.stderr or "no output")[-200:]}
+        return None
+    synth = importlib.import_module(PKG + ".synth")
     st = torch.cuda.current_stream()
 
     def ours(nfeat, nlevels, batch, iters):
