@@ -217,6 +217,19 @@ def test_stage_interface_matches_operator(orbb, synth):
     kp = np.frombuffer(d_kp.cpu().numpy().tobytes(), orbb.KEYPOINT_DTYPE)[:n]
     desc = d_desc.cpu().numpy().reshape(-1, 32)[:n]
     assert n == len(ref_kp) and kp.tobytes() == ref_kp.tobytes() and np.array_equal(desc, ref_desc)
+    # The quadtree stage consumes (and clears) the cell table the FAST stage filled.  Running it again on the same
+    # candidate lists finds an empty table, notices that it does not describe the lists and takes the general
+    # sorted-key path: same selection, same bytes.
+    d_kp.zero_(); d_desc.zero_()
+    ex.detect_distribute(stream=st)
+    ex.compute_fast_angle_and_orb(d_kp, d_desc, d_cnt, stream=st)
+    torch.cuda.synchronize()
+    assert int(d_cnt.item()) == n
+    assert d_kp.cpu().numpy().tobytes()[:28 * n] == ref_kp.tobytes()
+    assert np.array_equal(d_desc.cpu().numpy().reshape(-1, 32)[:n], ref_desc)
+    # ... and a fresh run of the whole chain afterwards uses the table again
+    kp3, desc3 = ex(img)
+    assert kp3.tobytes() == ref_kp.tobytes() and np.array_equal(desc3, ref_desc)
     ex.close()
 
 
