@@ -2,7 +2,9 @@
 // Replaces the "best response per 32x32 cell" selection of the reference's grid NMS
 // (src/cuda/nms.cu:86-254) with upstream ORB-SLAM2 semantics.
 //
-// Upstream is a sequential std::list algorithm.  The B200 formulation removes the list:
+// Upstream is a sequential std::list algorithm.  The B200 formulation removes the list, and in the common case
+// the sort as well (see "CELL-TABLE FAST PATH" in the kernel: the FAST kernel bins the candidates into the tree
+// cells of depth 5-6, and the passes below run over the non-empty cells).  The general path, also the fallback:
 //  * every split line of the tree depends only on the node rectangle, so the tree is a tensor
 //    product of two 1-D binary trees; the host tabulates, per coordinate, the Morton-spread path
 //    bits (xkey/ykey).  key = xkey[x] | ykey[y] is the key's full root-to-leaf path.
@@ -28,14 +30,9 @@
 namespace orbb {
 
 #ifdef ORBB_OCT_PROF  // diagnostics build only (make EXTRA=-DORBB_OCT_PROF): phase timestamps of CTA (0,0)
-__device__ long long g_oct_prof[64];
 #define OCT_T(k) do { if (threadIdx.x == 0 && blockIdx.x == 0 && blockIdx.y == 0) prof_t[k] = clock64(); } while (0)
-#define OCT_A(k, t0) do { if (threadIdx.x == 0 && blockIdx.x == 0 && blockIdx.y == 0) g_oct_prof[k] += clock64() - (t0); } while (0)
-#define OCT_NOW() clock64()
 #else
 #define OCT_T(k) do { } while (0)
-#define OCT_A(k, t0) do { } while (0)
-#define OCT_NOW() 0
 #endif
 
 #define OCT_THREADS 512
@@ -242,7 +239,6 @@ k_octree(const LevelDev *__restrict__ levels, int n_levels, const int *__restric
     const int N = quota_override >= 0 ? quota_override : L.nfeat;
 #ifdef ORBB_OCT_PROF
     long long prof_t[12] = {0};
-    int prof_rounds = 0;
 #endif
     OCT_T(0);
     int n = cand_count[frame * n_levels + level];
