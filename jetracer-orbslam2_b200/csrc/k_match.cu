@@ -141,10 +141,14 @@ k_match_merge(const int4 *__restrict__ partial, int partial_stride, int n_split,
 }
 
 // ---- windowed 1-NN with a Hamming cutoff: the reference's match_keypoints semantics on 256-bit descriptors.
-// thread = one query; train positions + descriptors go through shared memory in tiles; the position gate runs
-// first, XOR/POPC only for the few candidates inside the window.
+// WARP = one query: the 32 lanes test 32 train positions per step (coalesced reads of the position records, L1/L2
+// resident and shared by every warp of the SM); XOR/POPC only for the few candidates inside the window, whose
+// descriptors are fetched from global memory on demand; the warp's best is one REDUX.MIN over the packed key
+// (distance << 16 | train index), which keeps the lowest index among equal distances -- the scan-order rule of a
+// sequential search.  (The first version ran one THREAD per query over train tiles staged in shared memory: the same
+// work per pair, but a lone frame pair kept only ~10 CTAs busy for 66 us; this form takes the whole GPU.)
 #define WIN_THREADS 128
-#define WIN_TILE 128
+#define WIN_TILE 128  // train tile of the projection matcher below
 // Batched form (q_counts != nullptr): blockIdx.y = frame pair, rows of frame f start at f * max_kp in every array and
 // the set sizes come from the device-side count arrays.
 __global__ void __launch_bounds__(WIN_THREADS)
@@ -152,46 +156,40 @@ k_match_windowed(const uint4 *__restrict__ query, const uint8_t *__restrict__ q_
                  const uint4 *__restrict__ train, const uint8_t *__restrict__ t_xy, int t_stride, int nt, float max_px,
                  int max_hamming, int *__restrict__ out_idx, int *__restrict__ out_dist, int *__restrict__ n_matched,
                  const int *__restrict__ q_counts, const int *__restrict__ t_counts, int max_kp) {
-    __shared__ uint4 s_d[WIN_TILE * 2];
-    __shared__ float2 s_xy[WIN_TILE];
     if (q_counts) {
         const size_t f = blockIdx.y, row0 = f * max_kp;
         nq = min(q_counts[f], max_kp); nt = min(t_counts[f], max_kp);
-        if ((int)(blockIdx.x * WIN_THREADS) >= nq) return;
         query += 2 * row0; train += 2 * row0;
         q_xy += row0 * q_stride; t_xy += row0 * t_stride;
         out_idx += row0; out_dist += row0;
         n_matched = nullptr;
     }
-    const int q = blockIdx.x * WIN_THREADS + threadIdx.x;
-    const int qq = min(q, nq - 1);
-    const uint4 qa = query[(size_t)qq * 2], qb = query[(size_t)qq * 2 + 1];
-    const float qx = *reinterpret_cast<const float *>(q_xy + (size_t)qq * q_stride);
-    const float qy = *reinterpret_cast<const float *>(q_xy + (size_t)qq * q_stride + 4);
-    int best_d = max_hamming, best_i = -1;  // accept only d < max_hamming; strict '<' keeps the lowest index on ties
-    for (int tb = 0; tb < nt; tb += WIN_TILE) {
-        const int cnt = min(WIN_TILE, nt - tb);
-        __syncthreads();
-        for (int i = threadIdx.x; i < cnt * 2; i += WIN_THREADS) s_d[i] = train[(size_t)tb * 2 + i];
-        for (int i = threadIdx.x; i < cnt; i += WIN_THREADS) {
-            const uint8_t *p = t_xy + (size_t)(tb + i) * t_stride;
-            s_xy[i] = make_float2(*reinterpret_cast<const float *>(p), *reinterpret_cast<const float *>(p + 4));
-        }
-        __syncthreads();
-        for (int t = 0; t < cnt; ++t) {
-            const float2 p = s_xy[t];
-            if (fabsf(__fsub_rn(qx, p.x)) <= max_px && fabsf(__fsub_rn(qy, p.y)) <= max_px) {
-                const uint4 a = s_d[2 * t], b = s_d[2 * t + 1];
+    const int lane = threadIdx.x & 31;
+    const int q = blockIdx.x * (WIN_THREADS / 32) + (threadIdx.x >> 5);  // warp-uniform
+    if (q >= nq) return;
+    const uint4 qa = __ldg(query + (size_t)q * 2), qb = __ldg(query + (size_t)q * 2 + 1);
+    const float qx = *reinterpret_cast<const float *>(q_xy + (size_t)q * q_stride);
+    const float qy = *reinterpret_cast<const float *>(q_xy + (size_t)q * q_stride + 4);
+    // accept only d < max_hamming; the packed key orders by distance, then by train index
+    unsigned best = 0xffffffffu;
+    for (int tb = 0; tb < nt; tb += 32) {
+        const int t = tb + lane;
+        if (t < nt) {
+            const uint8_t *p = t_xy + (size_t)t * t_stride;
+            const float px = *reinterpret_cast<const float *>(p), py = *reinterpret_cast<const float *>(p + 4);
+            if (fabsf(__fsub_rn(qx, px)) <= max_px && fabsf(__fsub_rn(qy, py)) <= max_px) {
+                const uint4 a = __ldg(train + (size_t)t * 2), b = __ldg(train + (size_t)t * 2 + 1);
                 const int d = hamming256(qa, qb, a, b);
-                if (d < best_d) { best_d = d; best_i = tb + t; }
+                if (d < max_hamming) best = min(best, ((unsigned)d << 16) | (unsigned)t);
             }
         }
     }
-    const bool ok = q < nq && best_i >= 0;
-    if (q < nq) { out_idx[q] = best_i; out_dist[q] = best_i >= 0 ? best_d : -1; }
-    if (n_matched) {
-        const unsigned m = __ballot_sync(0xffffffffu, ok);
-        if ((threadIdx.x & 31) == 0 && m) atomicAdd(n_matched, __popc(m));
+    best = __reduce_min_sync(0xffffffffu, best);
+    if (lane == 0) {
+        const bool ok = best != 0xffffffffu;
+        out_idx[q] = ok ? (int)(best & 0xffffu) : -1;
+        out_dist[q] = ok ? (int)(best >> 16) : -1;
+        if (n_matched && ok) atomicAdd(n_matched, 1);
     }
 }
 
@@ -203,7 +201,9 @@ cudaError_t launch_match_windowed(const uint8_t *d_q, const void *d_q_xy, int q_
         cudaError_t e = cudaMemsetAsync(d_nmatched, 0, sizeof(int), st);
         if (e != cudaSuccess) return e;
     }
-    k_match_windowed<<<(nq + WIN_THREADS - 1) / WIN_THREADS, WIN_THREADS, 0, st>>>(
+    if (nt > 65536) return cudaErrorInvalidValue;  // the packed key holds a 16-bit train index
+    const int qpc = WIN_THREADS / 32;
+    k_match_windowed<<<(nq + qpc - 1) / qpc, WIN_THREADS, 0, st>>>(
         reinterpret_cast<const uint4 *>(d_q), static_cast<const uint8_t *>(d_q_xy), q_stride, nq,
         reinterpret_cast<const uint4 *>(d_t), static_cast<const uint8_t *>(d_t_xy), t_stride, nt, max_px, max_hamming, d_idx,
         d_dist, d_nmatched, nullptr, nullptr, 0);
@@ -238,7 +238,9 @@ cudaError_t launch_match_windowed_batch(const uint8_t *d_q, const void *d_q_xy, 
                                         const uint8_t *d_t, const void *d_t_xy, int t_stride, const int *d_t_counts,
                                         int n_frames, int max_kp, float max_px, int max_hamming, int *d_idx, int *d_dist,
                                         cudaStream_t st) {
-    dim3 grid((max_kp + WIN_THREADS - 1) / WIN_THREADS, n_frames);
+    if (max_kp > 65536) return cudaErrorInvalidValue;  // the packed key holds a 16-bit train index
+    const int qpc = WIN_THREADS / 32;
+    dim3 grid((max_kp + qpc - 1) / qpc, n_frames);
     k_match_windowed<<<grid, WIN_THREADS, 0, st>>>(
         reinterpret_cast<const uint4 *>(d_q), static_cast<const uint8_t *>(d_q_xy), q_stride, 0,
         reinterpret_cast<const uint4 *>(d_t), static_cast<const uint8_t *>(d_t_xy), t_stride, 0, max_px, max_hamming, d_idx,

@@ -11,6 +11,7 @@
 // previous batch, so "previous frame of frame f" is simply row f and "current" is row f + 1.
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <vector>
@@ -51,7 +52,11 @@ struct orbb_rgbd_stage {
     std::vector<void *> dev_allocs, host_allocs;
     long long n_submitted = 0;
     bool gate_recorded = false;
+    // diagnostics (ORBB_STAGE_PROF=1): timing events at the phase boundaries of the last submit, printed by wait()
+    bool prof = false;
+    cudaEvent_t pe[8] = {};
 };
+#define SPROF(s, k, stream) do { if ((s)->prof) cudaEventRecord((s)->pe[k], stream); } while (0)
 
 #define SCK(s, call)                                                                                       \
     do {                                                                                                   \
@@ -195,6 +200,11 @@ extern "C" int orbb_rgbd_stage_submit(orbb_rgbd_stage *s, const uint8_t *h_gray,
     orbb_rgbd_stage::Host &H = s->host[p];
     if (ticket >= 2) SCK(s, cudaEventSynchronize(s->ev_out[p]));  // batch ticket-2 owned this parity's buffers
     // ---- inputs
+    if (getenv("ORBB_STAGE_PROF") && !s->prof) {
+        s->prof = true;
+        for (auto &e : s->pe) cudaEventCreate(&e);
+    }
+    SPROF(s, 0, s->s_in);
     SCK(s, cudaMemcpyAsync(s->d_gray[p], h_gray, s->gray_bytes * n, cudaMemcpyHostToDevice, s->s_in));
     SCK(s, cudaMemcpyAsync(s->d_depth[p], h_depth, s->depth_px * n * sizeof(uint16_t), cudaMemcpyHostToDevice, s->s_in));
     if (h_T) {
@@ -202,16 +212,19 @@ extern "C" int orbb_rgbd_stage_submit(orbb_rgbd_stage *s, const uint8_t *h_gray,
         SCK(s, cudaMemcpyAsync(s->d_T[p], H.T, sizeof(double) * 16 * n, cudaMemcpyHostToDevice, s->s_in));
     }
     SCK(s, cudaEventRecord(s->ev_in[p], s->s_in));
+    SPROF(s, 1, s->s_in);
     // ---- depth alignment on its own stream; the aligned buffer is free once the previous batch's gate has read it
     SCK(s, cudaStreamWaitEvent(s->s_align, s->ev_in[p], 0));
     if (s->gate_recorded) SCK(s, cudaStreamWaitEvent(s->s_align, s->ev_gate, 0));
     SRC(orbb_align_depth_to_other(s->h, s->d_depth[p], n_frames, s->cfg.depth_scale, &s->cfg.depth_intrin,
                                   &s->cfg.image_intrin, &s->cfg.depth_to_image, s->d_aligned, s->s_align));
     SCK(s, cudaEventRecord(s->ev_align, s->s_align));
+    SPROF(s, 2, s->s_align);
     // ---- extraction
     SCK(s, cudaStreamWaitEvent(s->s_main, s->ev_in[p], 0));
     SRC(orbb_extract_batch_device(s->h, s->d_gray[p], (size_t)s->cfg.image_intrin.width, s->gray_bytes, n_frames,
                                   s->d_kp_raw, s->d_desc_raw, s->d_counts_raw, s->max_kp, s->s_main));
+    SPROF(s, 3, s->s_main);
     // ---- depth gate + 3-D lift into rows 1..n (the previous batch's D2H must have drained them)
     SCK(s, cudaStreamWaitEvent(s->s_main, s->ev_align, 0));
     if (ticket >= 1) SCK(s, cudaStreamWaitEvent(s->s_main, s->ev_out[p ^ 1], 0));
@@ -219,6 +232,7 @@ extern "C" int orbb_rgbd_stage_submit(orbb_rgbd_stage *s, const uint8_t *h_gray,
                                      s->d_counts_raw, s->max_kp, s->d_kp + mk, s->d_desc + 32 * mk, s->d_pts + 3 * mk,
                                      s->d_valid + 1, s->s_main));
     SCK(s, cudaEventRecord(s->ev_gate, s->s_main));
+    SPROF(s, 4, s->s_main);
     s->gate_recorded = true;
     // ---- previous (rows 0..n-1) -> current (rows 1..n): reproject, windowed match, compact the 3-D pairs
     SRC(orbb_reproject_points(s->h, s->d_pts, s->d_valid, n_frames, s->max_kp, h_T ? s->d_T[p] : nullptr,
@@ -228,6 +242,7 @@ extern "C" int orbb_rgbd_stage_submit(orbb_rgbd_stage *s, const uint8_t *h_gray,
                                   s->cfg.max_hamming_distance, s->d_idx, s->d_dist, s->d_pts, s->d_pts + 3 * mk,
                                   s->d_prev_m, s->d_curr_m, s->d_xy, s->d_nm, s->s_main));
     SCK(s, cudaEventRecord(s->ev_main[p], s->s_main));
+    SPROF(s, 5, s->s_main);
     // ---- results to the host
     SCK(s, cudaStreamWaitEvent(s->s_out, s->ev_main[p], 0));
     if (n_frames == s->B) {
@@ -244,6 +259,7 @@ extern "C" int orbb_rgbd_stage_submit(orbb_rgbd_stage *s, const uint8_t *h_gray,
         SCK(s, cudaMemcpyAsync(H.xy, s->d_xy, sizeof(uint16_t) * 2 * n * mk, cudaMemcpyDeviceToHost, s->s_out));
     }
     SCK(s, cudaEventRecord(s->ev_out[p], s->s_out));
+    SPROF(s, 6, s->s_out);
     H.n_frames = n_frames;
     // ---- carry: the batch's last frame becomes row 0 (read by the next batch's reprojection / match only)
     SCK(s, cudaMemcpyAsync(s->d_kp, s->d_kp + n * mk, sizeof(orbb_keypoint) * mk, cudaMemcpyDeviceToDevice, s->s_main));
@@ -260,6 +276,13 @@ extern "C" int orbb_rgbd_stage_wait(orbb_rgbd_stage *s, int ticket, orbb_slam_fr
     SCK(s, cudaSetDevice(s->device));
     const int p = ticket & 1;
     SCK(s, cudaEventSynchronize(s->ev_out[p]));
+    if (s->prof && ticket == s->n_submitted - 1 && (ticket % 50) == 49) {
+        cudaEventSynchronize(s->pe[6]);
+        float t[7] = {0};
+        for (int k = 1; k < 7; ++k) cudaEventElapsedTime(&t[k], s->pe[0], s->pe[k]);
+        fprintf(stderr, "stage prof (us since H2D start): h2d %.1f | align %.1f | extract %.1f | gate %.1f | match %.1f | d2h %.1f\n",
+                1e3f * t[1], 1e3f * t[2], 1e3f * t[3], 1e3f * t[4], 1e3f * t[5], 1e3f * t[6]);
+    }
     if (out) {
         const orbb_rgbd_stage::Host &H = s->host[p];
         out->n_frames = H.n_frames; out->max_kp = s->max_kp;

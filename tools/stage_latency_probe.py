@@ -19,11 +19,15 @@ for (w, h, nf) in ((848, 480, 1200), (640, 480, 1000)):
     fb, db = w * h, 2 * w * h
     for i in range(10):
         stage.wait(stage.submit_ptr(gray.data_ptr() + (i % 4) * fb, pd.data_ptr() + (i % 4) * db, 1))
-    ts = []
+    ts, tsub = [], []
     for i in range(200):
         t = time.perf_counter()
-        r = stage.wait(stage.submit_ptr(gray.data_ptr() + (i % 4) * fb, pd.data_ptr() + (i % 4) * db, 1))
-        ts.append(time.perf_counter() - t)
-    print(f"{w}x{h} {nf} kp: one RGB-D frame submit+wait median {1e6 * float(np.median(ts)):.1f} us, "
+        tk = stage.submit_ptr(gray.data_ptr() + (i % 4) * fb, pd.data_ptr() + (i % 4) * db, 1)
+        t1 = time.perf_counter()
+        r = stage.wait(tk)
+        ts.append(time.perf_counter() - t); tsub.append(t1 - t)
+    # ORBB_STAGE_PROF=1 additionally prints the device-side timeline of the phases (events on the stage's streams)
+    print(f"{w}x{h} {nf} kp: one RGB-D frame submit+wait median {1e6 * float(np.median(ts)):.1f} us "
+          f"(host issue inside submit {1e6 * float(np.median(tsub)):.1f} us), "
           f"valid {int(r['valid_keypoints_num'][0])}, matched {int(r['matched_keypoints_num'][0])}", flush=True)
     stage.close()
