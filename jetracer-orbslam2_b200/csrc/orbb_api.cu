@@ -104,6 +104,7 @@ struct orbb_handle {
     } graphs[4];
     long long graph_clock = 0;
     int use_graphs = 0;  // opt-in (ORBB_GRAPH=1): see orbb_extract_batch_device
+    int last_host_frames = -1, last_host_latency = -1;  // chunk layout of the previous host submission
     cudaEvent_t ev_fence = nullptr, ev_done[2] = {nullptr, nullptr};
     std::vector<cudaEvent_t> ev_in, ev_comp;
     std::vector<void *> allocs;
@@ -751,13 +752,17 @@ static int submit_host(orbb_handle *h, const uint8_t *h_images, size_t pitch, si
     orbb_keypoint *d_kp = h->d_kp2[par];
     uint8_t *d_desc = h->d_desc2[par];
     int *d_counts = h->d_counts2[par];
-    // everything already queued on the caller's stream happens-before the pipeline; the level/scratch buffers
-    // are shared by consecutive batches, so each compute stream also waits for the other one's previous tail
+    // everything already queued on the caller's stream happens-before the pipeline.  The level / scratch buffers are
+    // per frame slot and shared by consecutive batches: when this batch is chunked exactly like the previous one,
+    // every frame slot stays on the same compute stream and stream order is enough; otherwise each compute stream
+    // also waits for the other one's previous tail.
+    const bool same_layout = ticket >= 1 && h->last_host_frames == n_frames && h->last_host_latency == (int)latency_mode;
+    h->last_host_frames = n_frames; h->last_host_latency = (int)latency_mode;
     CK(h, cudaEventRecord(h->ev_fence, st));
     CK(h, cudaStreamWaitEvent(h->s_in, h->ev_fence, 0));
     for (int i = 0; i < 2; ++i) {
         CK(h, cudaStreamWaitEvent(h->s_comp[i], h->ev_fence, 0));
-        if (ticket >= 1) CK(h, cudaStreamWaitEvent(h->s_comp[i], h->ev_tail[i ^ 1], 0));
+        if (ticket >= 1 && !same_layout) CK(h, cudaStreamWaitEvent(h->s_comp[i], h->ev_tail[i ^ 1], 0));
     }
     int per = n_frames <= 32 ? n_frames : (latency_mode ? 16 : (n_frames + 1) / 2);
     for (int c = 0, f0 = 0; f0 < n_frames; ++c) {
