@@ -535,11 +535,13 @@ def test_cuda_graph_replay_opt_in(orbb, oracle, synth, monkeypatch):
     assert ex.launch_count() - l0 == 15 * 10  # replays are counted like direct launches: level0 + 5 resizes + 4
 
 
-@pytest.mark.parametrize("nb", [64, 71, 130])
+@pytest.mark.parametrize("nb", [12, 30, 64, 71, 130])
 def test_large_batch_paths_equal_single_frame(orbb, synth, nb):
     """Batches >= 64 frames take the multi-stream split with the throughput variants of the kernels (large-grid
     quadtree kernel, two batch parts); a single frame takes the small-grid variants (shared-memory per-key arrays,
-    batched loads).  Both must give the same bytes, in the same order."""
+    8 loads in flight, one keypoint per warp in the angle/rBRIEF kernel); 12 and 30 frames land on the variants in
+    between (quadtree grids of 96 and 240 CTAs, 2 and 8 keypoint slots per warp).  All must give the same bytes, in
+    the same order."""
     import torch
     w, h = 320, 240
     base = [synth.textured_frame(w, h, 300 + i) for i in range(6)] + [synth.sparse_frame(w, h, 9), synth.low_contrast_frame(w, h, 4)]
