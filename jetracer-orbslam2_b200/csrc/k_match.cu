@@ -148,7 +148,6 @@ k_match_merge(const int4 *__restrict__ partial, int partial_stride, int n_split,
 // sequential search.  (The first version ran one THREAD per query over train tiles staged in shared memory: the same
 // work per pair, but a lone frame pair kept only ~10 CTAs busy for 66 us; this form takes the whole GPU.)
 #define WIN_THREADS 128
-#define WIN_TILE 128  // train tile of the projection matcher below
 // Batched form (q_counts != nullptr): blockIdx.y = frame pair, rows of frame f start at f * max_kp in every array and
 // the set sizes come from the device-side count arrays.
 __global__ void __launch_bounds__(WIN_THREADS)
@@ -249,8 +248,9 @@ cudaError_t launch_match_windowed_batch(const uint8_t *d_q, const void *d_q_xy, 
 }
 
 // ---- ORB-SLAM2 SearchByProjection gates (upstream ORBmatcher.cc): per-query radius from the octave, octave band,
-// best distance <= th_high.  thread = one query of one frame pair, train keypoints (descriptor, position, octave) go
-// through shared memory in tiles.  Same structure as k_match_windowed.
+// best distance <= th_high.  Warp = one query of one frame pair, same structure as k_match_windowed: 32 train
+// keypoints (position, octave) per step straight from the keypoint records, descriptors only for the gated few,
+// REDUX.MIN over (distance << 16 | train index).
 struct ScaleTable { float sf[ORBB_MAX_LEVELS]; };
 
 __global__ void __launch_bounds__(WIN_THREADS)
@@ -258,43 +258,35 @@ k_match_projection(const uint4 *__restrict__ query, const float2 *__restrict__ q
                    const int *__restrict__ q_counts, const uint4 *__restrict__ train, const orbb_keypoint *__restrict__ t_kp,
                    const int *__restrict__ t_counts, int max_kp, float th, int th_high, const ScaleTable scales, int n_levels,
                    int *__restrict__ out_idx, int *__restrict__ out_dist) {
-    __shared__ uint4 s_d[WIN_TILE * 2];
-    __shared__ float2 s_xy[WIN_TILE];
-    __shared__ int s_oct[WIN_TILE];
     const size_t f = blockIdx.y, row0 = f * max_kp;
     const int nq = min(q_counts[f], max_kp), nt = min(t_counts[f], max_kp);
-    if ((int)(blockIdx.x * WIN_THREADS) >= nq) return;
-    const int q = blockIdx.x * WIN_THREADS + threadIdx.x;
-    const size_t qq = row0 + min(q, nq - 1);
-    const uint4 qa = query[qq * 2], qb = query[qq * 2 + 1];
+    const int lane = threadIdx.x & 31;
+    const int q = blockIdx.x * (WIN_THREADS / 32) + (threadIdx.x >> 5);  // warp-uniform
+    if (q >= nq) return;
+    const size_t qq = row0 + q;
+    const uint4 qa = __ldg(query + qq * 2), qb = __ldg(query + qq * 2 + 1);
     const float2 uv = q_uv[qq];
     const int oq = min(max(q_kp[qq].octave, 0), n_levels - 1);
     const float radius = __fmul_rn(th, scales.sf[oq]);
-    int best_d = 256, best_i = -1;
-    for (int tb = 0; tb < nt; tb += WIN_TILE) {
-        const int cnt = min(WIN_TILE, nt - tb);
-        __syncthreads();
-        for (int i = threadIdx.x; i < cnt * 2; i += WIN_THREADS) s_d[i] = train[(row0 + tb) * 2 + i];
-        for (int i = threadIdx.x; i < cnt; i += WIN_THREADS) {
-            const orbb_keypoint &k = t_kp[row0 + tb + i];
-            s_xy[i] = make_float2(k.x, k.y);
-            s_oct[i] = k.octave;
-        }
-        __syncthreads();
-        for (int t = 0; t < cnt; ++t) {
-            const float2 p = s_xy[t];
-            const int ot = s_oct[t];
-            if (fabsf(__fsub_rn(p.x, uv.x)) < radius && fabsf(__fsub_rn(p.y, uv.y)) < radius && ot >= oq - 1 && ot <= oq + 1) {
-                const uint4 a = s_d[2 * t], b = s_d[2 * t + 1];
+    unsigned best = 0xffffffffu;
+    for (int tb = 0; tb < nt; tb += 32) {
+        const int t = tb + lane;
+        if (t < nt) {
+            const orbb_keypoint &k = t_kp[row0 + t];
+            const float px = k.x, py = k.y;
+            const int ot = k.octave;
+            if (fabsf(__fsub_rn(px, uv.x)) < radius && fabsf(__fsub_rn(py, uv.y)) < radius && ot >= oq - 1 && ot <= oq + 1) {
+                const uint4 a = __ldg(train + (row0 + t) * 2), b = __ldg(train + (row0 + t) * 2 + 1);
                 const int d = hamming256(qa, qb, a, b);
-                if (d < best_d) { best_d = d; best_i = tb + t; }
+                if (d < 256) best = min(best, ((unsigned)d << 16) | (unsigned)t);  // ties -> lowest train index
             }
         }
     }
-    if (q < nq) {
-        const bool ok = best_i >= 0 && best_d <= th_high;
-        out_idx[row0 + q] = ok ? best_i : -1;
-        out_dist[row0 + q] = ok ? best_d : -1;
+    best = __reduce_min_sync(0xffffffffu, best);
+    if (lane == 0) {
+        const bool ok = best != 0xffffffffu && (int)(best >> 16) <= th_high;
+        out_idx[row0 + q] = ok ? (int)(best & 0xffffu) : -1;
+        out_dist[row0 + q] = ok ? (int)(best >> 16) : -1;
     }
 }
 
@@ -353,7 +345,9 @@ cudaError_t launch_match_projection(const uint8_t *d_q, const float *d_q_uv, con
                                     int *d_dist, int *d_nmatched, cudaStream_t st) {
     ScaleTable tab{};
     for (int l = 0; l < n_levels && l < ORBB_MAX_LEVELS; ++l) tab.sf[l] = sf[l];
-    dim3 grid((max_kp + WIN_THREADS - 1) / WIN_THREADS, n_frames);
+    if (max_kp > 65536) return cudaErrorInvalidValue;  // the packed key holds a 16-bit train index
+    const int qpc = WIN_THREADS / 32;
+    dim3 grid((max_kp + qpc - 1) / qpc, n_frames);
     k_match_projection<<<grid, WIN_THREADS, 0, st>>>(reinterpret_cast<const uint4 *>(d_q), reinterpret_cast<const float2 *>(d_q_uv),
                                                      d_q_kp, d_q_counts, reinterpret_cast<const uint4 *>(d_t), d_t_kp, d_t_counts,
                                                      max_kp, th, th_high, tab, n_levels, d_idx, d_dist);
