@@ -27,7 +27,8 @@ __device__ __forceinline__ int pix(const LevelDev &L, int frame, int x, int y) {
     return L.img[(size_t)frame * L.frame_stride + (size_t)(ORBB_BORDER + y) * L.pitch + ORBB_ROI_X0 + x];
 }
 
-// CTA = one stereo pair (left = resident frame 2p, right = 2p + 1); thread = one left keypoint at a time.
+// blockIdx.y = stereo pair (left = resident frame 2p, right = 2p + 1), blockIdx.x = a block of ST_THREADS left keypoints;
+// thread = one left keypoint.  (One CTA per pair walked all left keypoints: 64 pairs kept 64 of 148 SMs busy.)
 __global__ void __launch_bounds__(ST_THREADS)
 k_stereo_match(const LevelDev *__restrict__ levels, const orbb_keypoint *__restrict__ kp, const uint4 *__restrict__ desc,
                const int *__restrict__ counts, int max_kp, const StereoArgs A, float *__restrict__ uright,
@@ -35,10 +36,10 @@ k_stereo_match(const LevelDev *__restrict__ levels, const orbb_keypoint *__restr
     __shared__ uint4 s_d[ST_TILE * 2];
     __shared__ float s_u[ST_TILE];
     __shared__ int s_lo[ST_TILE], s_hi[ST_TILE], s_oct[ST_TILE];
-    const int p = blockIdx.x, fl = 2 * p, fr = 2 * p + 1;
+    const int p = blockIdx.y, fl = 2 * p, fr = 2 * p + 1;
     const size_t rowL = (size_t)fl * max_kp, rowR = (size_t)fr * max_kp, rowO = (size_t)p * max_kp;
     const int nl = min(counts[fl], max_kp), nr = min(counts[fr], max_kp);
-    for (int i0 = 0; i0 < nl; i0 += ST_THREADS) {
+    for (int i0 = blockIdx.x * ST_THREADS; i0 < nl; i0 += gridDim.x * ST_THREADS) {
         const int iL = i0 + threadIdx.x;
         const bool live = iL < nl;
         const orbb_keypoint kL = kp[rowL + (live ? iL : 0)];
@@ -169,7 +170,7 @@ cudaError_t launch_stereo(const LevelDev *d_levels, const float *sf, const float
     A.n_levels = n_levels;
     const float mb = mbf / fx;  // upstream: mb = mbf / fx; minZ = mb; minD = 0; maxD = mbf / minZ
     A.mbf = mbf; A.min_d = 0.0f; A.max_d = mbf / mb;
-    k_stereo_match<<<n_pairs, ST_THREADS, 0, st>>>(d_levels, d_kp, reinterpret_cast<const uint4 *>(d_desc), d_counts, max_kp, A,
+    k_stereo_match<<<dim3((max_kp + ST_THREADS - 1) / ST_THREADS, n_pairs), ST_THREADS, 0, st>>>(d_levels, d_kp, reinterpret_cast<const uint4 *>(d_desc), d_counts, max_kp, A,
                                                    d_uright, d_depth, d_sad);
     const size_t smem = sizeof(int) * (size_t)max_kp;
     if (smem > 48 * 1024) {
