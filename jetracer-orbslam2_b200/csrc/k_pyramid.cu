@@ -206,7 +206,8 @@ __global__ void __launch_bounds__(32 * RS_ROWS) k_resize_rows(const ResizeArgs A
     // two output rows per thread (py0 and py0 + RS_ROWS): 16 independent loads in flight
     const int py1 = min(py0 + RS_ROWS, A.rows - 1);
     int4 v[2] = {__ldg(A.rs_v + py0), __ldg(A.rs_v + py1)};
-    pdl_wait();  // the tables above are constant; the source level is written by the previous kernel
+    pdl_wait();  // the tables above are constant (ptxas still sinks their loads below the wait); the source level is
+                 // written by the previous kernel
     unsigned w[2][8];
 #pragma unroll
     for (int r = 0; r < 2; ++r) {
