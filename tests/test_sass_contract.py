@@ -1,0 +1,74 @@
+"""Static SASS checks (no GPU): the library contains sm_100a code only, no tensor-core instructions (nothing on this
+path is a dense contraction), and each kernel carries the instructions its design leans on -- the evidence
+profiles/r01m_sass_mnemonics.txt records, kept true by a test."""
+import os
+import re
+import shutil
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+LIB = os.path.join(ROOT, "jetracer-orbslam2_b200", "liborbb200.so")
+
+
+@pytest.fixture(scope="module")
+def sass():
+    if not shutil.which("cuobjdump"):
+        pytest.skip("cuobjdump not on PATH")
+    import __graft_entry__ as g
+    g.build()
+    txt = subprocess.run(["cuobjdump", "-sass", LIB], capture_output=True, text=True).stdout
+    kernels, cur = {}, None
+    for line in txt.splitlines():
+        m = re.search(r"Function : (\S+)", line)
+        if m:
+            cur = kernels.setdefault(m.group(1), [])
+            continue
+        m = re.match(r"\s+/\*[0-9a-f]{4,}\*/\s+(?:@!?U?P\d+\s+)?([A-Z0-9_.]+)", line)
+        if m and cur is not None:
+            cur.append(m.group(1))
+    archs = set(re.findall(r"arch = (sm_\w+)", txt))
+    return kernels, archs
+
+
+def _count(ops, prefix):
+    return sum(1 for o in ops if o == prefix or o.startswith(prefix + "."))
+
+
+def _kernel(kernels, *needles):
+    hits = [k for k in kernels if all(n in k for n in needles)]
+    assert hits, needles
+    return kernels[hits[0]]
+
+
+def test_sm100a_only_and_no_tensor_cores(sass):
+    kernels, archs = sass
+    assert archs == {"sm_100a"}
+    assert len(kernels) >= 25
+    for name, ops in kernels.items():
+        for tc in ("HMMA", "IMMA", "DMMA", "UTCHMMA", "UTCIMMA", "UTCQMMA", "WGMMA"):
+            assert _count(ops, tc) == 0, (name, tc)
+
+
+def test_kernels_carry_their_instructions(sass):
+    kernels, _ = sass
+    match1 = _kernel(kernels, "k_matchILi1E")
+    assert _count(match1, "POPC") >= 5 and _count(match1, "LOP3") >= 14  # carry-save popcount: 5 POPC per pair
+    fast = _kernel(kernels, "k_fast_cellsILb0ELb0E")
+    assert _count(fast, "VABSDIFF4") >= 4 and _count(fast, "VIMNMX3") >= 40  # packed precheck, arc-score min/max network
+    assert _count(fast, "ATOMG") + _count(fast, "RED") >= 1                  # cell-table atomics while emitting
+    assert _count(fast, "ACQBULK") == 1                                       # programmatic dependent of the pyramid chain
+    resize = _kernel(kernels, "k_resize_rowsILb0E")
+    assert _count(resize, "IDP.2A") == 16 and _count(resize, "ACQBULK") == 1 and _count(resize, "PREEXIT") == 1
+    # the PDL wait precedes every load of the source level
+    first_ld = min(i for i, o in enumerate(resize) if o.startswith("LDG"))
+    assert resize.index("ACQBULK") < first_ld
+    first_ld = min(i for i, o in enumerate(fast) if o.startswith("LDG"))
+    assert fast.index("ACQBULK") < first_ld
+    blur = _kernel(kernels, "k_blur")
+    assert _count(blur, "IDP.4A") >= 8
+    octree = _kernel(kernels, "k_octreeILi1ELi4E")
+    assert _count(octree, "REDUX") >= 32 and _count(octree, "BAR") >= 1
+    tma = _kernel(kernels, "k_fast_cellsILb0ELb1E")
+    assert _count(tma, "UTMALDG") == 1  # the opt-in TMA staging variant
