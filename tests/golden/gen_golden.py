@@ -282,11 +282,16 @@ def fixtures():
         ("flat_320x240", synth.flat_frame(320, 240), (300, 1.2, 8, 20, 7)),
         ("wide_424x240_seed3", synth.textured_frame(424, 240, 3), (600, 1.2, 6, 20, 7)),
         ("s15_400x300_seed9", synth.textured_frame(400, 300, 9), (400, 1.5, 4, 20, 7)),
+        # the reference's live shape (Context.h:16-17, defines.h:2): 848x480, ONE level, one keypoint per 32x32 cell's worth
+        ("refshape_848x480_1level_seed2100", synth.textured_frame(848, 480, 2100), (405, 1.2, 1, 20, 7)),
     ]
 
 
 def main():
+    only = set(sys.argv[1:])  # optional fixture names: regenerate just those
     for name, img, (nf, sc, nl, it, mt) in fixtures():
+        if only and name not in only:
+            continue
         ex = PyOrbExtractor(nf, sc, nl, it, mt)
         kp, desc, cands = ex.extract(img)
         pyr_sha = [hashlib.sha256(np.ascontiguousarray(p).tobytes()).hexdigest() for p in ex.padded]
