@@ -72,7 +72,7 @@ typedef struct orbb_handle orbb_handle;
 /* Replaces the buffer prologue of SlamGpuPipeline::buildStream (buildStream.cpp:208-341) and
  * loadPattern() (src/cuda/orb.cu:218-225).  device < 0 => current device. */
 int orbb_create(orbb_handle **out, const orbb_params *params, int width, int height, int max_batch,
-                int device);
+                int device); /* max_batch <= 65535 (ORBB_ERR_CAPACITY beyond: the frame index is a grid dimension) */
 int orbb_destroy(orbb_handle *h);
 const char *orbb_strerror(int status);
 const char *orbb_last_cuda_error(const orbb_handle *h);
@@ -122,7 +122,8 @@ int orbb_wait(orbb_handle *h, int ticket);
 
 /* ---------------------------------------------------------------- stage interface
  * Same stage names as the reference's free functions in namespace Jetracer.  All take the batch
- * resident in the handle (set by orbb_stage_upload or a previous stage) and are async on stream. */
+ * resident in the handle (set by orbb_stage_upload or a previous stage), are async on stream and may be
+ * re-run on the resident batch (orbb_detect / orbb_detect_fast restart the candidate lists). */
 /* copy frames into level 0 (+ reflect-101 frame); precedes pyramid_create_levels */
 int orbb_stage_upload(orbb_handle *h, const uint8_t *d_images, size_t pitch, size_t frame_stride,
                       int n_frames, void *cuda_stream);
@@ -143,22 +144,54 @@ int orbb_gaussian_blur(orbb_handle *h, void *cuda_stream);
 int orbb_compute_angle_and_orb(orbb_handle *h, orbb_keypoint *d_kp, uint8_t *d_desc,
                                int32_t *d_counts, int max_kp, void *cuda_stream);
 
+/* The reference calls the two halves separately (call sites src/SlamGpuPipeline/buildStream.cpp:442-460), on
+ * caller-owned arrays: these two entry points keep that shape, so the call site only swaps names.
+ *
+ * Jetracer::compute_fast_angle (src/cuda/orb.cuh:9-16, kernel orb.cu:77-142): upstream IC_Angle for n keypoints of
+ * ONE image: integer moments over the 31-px disc centred on (cvRound(x), cvRound(y)), angle = cv::fastAtan2 in
+ * DEGREES [0, 360) (the reference kernel returns atan2f radians).  d_pos_xy: DEVICE float2[n] pixel positions in the
+ * coordinates of `d_image` (e.g. an orbb_get_level() ROI: padded + 19 * pitch + 19); a keypoint whose disc leaves the
+ * image gets -1 (cv::KeyPoint's "no orientation").  Async on stream. */
+int orbb_compute_fast_angle(orbb_handle *h, float *d_angle, const float *d_pos_xy, const uint8_t *d_image,
+                            int image_pitch, int image_width, int image_height, int keypoints_num,
+                            void *cuda_stream);
+/* Jetracer::calc_orb (src/cuda/orb.cuh:18-27, kernels orb.cu:17-75 + the 32-bit squeeze :145-169, dropped): upstream
+ * computeOrbDescriptor for n keypoints of ONE image that is ALREADY smoothed (orbb_gaussian_blur's output,
+ * orbb_level::blurred): 256-bit steered BRIEF, d_desc DEVICE [n][32] (bit k of byte i = test 8i+k); there is no
+ * d_descriptors_tmp.  d_angle in degrees as written by orbb_compute_fast_angle.  A keypoint closer than 18 px to the
+ * image edge (upstream keeps >= 19) gets an all-zero descriptor.  Async on stream. */
+int orbb_calc_orb(orbb_handle *h, const float *d_angle, const float *d_pos_xy, uint8_t *d_desc,
+                  const uint8_t *d_blurred_image, int image_pitch, int image_width, int image_height,
+                  int keypoints_num, void *cuda_stream);
+/* The SoA result of Jetracer::detect (float2 d_pos / float d_score / int d_level, buildStream.cpp:289-296, 434-440)
+ * for the batch resident in the handle, after orbb_detect: per frame the selected keypoints of level 0, then level
+ * 1, ...; d_pos_xy [n_frames][max_kp] float2 in the coordinates of the keypoint's OWN level ROI (unscaled),
+ * d_score [n_frames][max_kp] (cv::FAST response), d_level [n_frames][max_kp], d_level_counts
+ * [n_frames][nlevels] (keypoints per level), d_counts [n_frames].  Any output may be NULL.  Async on stream. */
+int orbb_detect_export(orbb_handle *h, float *d_pos_xy, float *d_score, int32_t *d_level, int32_t *d_level_counts,
+                       int32_t *d_counts, int max_kp, void *cuda_stream);
+
 /* ---------------------------------------------------------------- matcher
  * Replaces Jetracer::match_keypoints (src/cuda/post_processing.cuh:40-51): brute-force Hamming
  * k-NN over 256-bit descriptors (XOR + POPC), k in {1,2}, ties -> lowest train index, accept iff
  * (k==1) or d1 < ratio*d2.  d_idx/d_dist are [nq][2] int32 (second column -1 when k==1 or nt<2),
- * d_accept [nq] u8 (may be NULL), d_naccept one int32 (may be NULL).  handle may be NULL?  No:
- * the handle supplies split-T scratch.  Async on stream. */
+ * d_accept [nq] u8 (may be NULL), d_naccept one int32 (may be NULL).  The handle supplies the split-T scratch,
+ * allocated once in orbb_create (query sets larger than it holds are processed in chunks): no allocation, no
+ * synchronisation.  The scratch is per handle, so matcher calls on one handle must share a stream (or be ordered
+ * by the caller).  Async on stream. */
 int orbb_match_knn(orbb_handle *h, const uint8_t *d_query, int nq, const uint8_t *d_train, int nt,
                    int k, float ratio, int32_t *d_idx, int32_t *d_dist, uint8_t *d_accept,
                    int32_t *d_naccept, void *cuda_stream);
 /* Segmented form: nseg independent (query set, train set) pairs, e.g. left/right or t/t+1 frames.
  * q_offsets/t_offsets are DEVICE int32 [nseg+1] row offsets into d_query/d_train; idx values are
- * relative to the segment's train set. */
+ * relative to the segment's train set.  The launch geometry comes from the HOST-side sizes the caller states
+ * (nothing is read back from the device, nothing synchronises): nq_total = q_offsets[nseg], max_q_per_seg /
+ * max_t_per_seg = upper bounds of the segment sizes (rows beyond them are not matched).  ORBB_ERR_CAPACITY when
+ * nq_total exceeds what the handle's scratch holds (about 2.4 M + max_batch * max_kp rows). */
 int orbb_match_knn_segmented(orbb_handle *h, const uint8_t *d_query, const int32_t *d_q_offsets,
-                             const uint8_t *d_train, const int32_t *d_t_offsets, int nseg,
-                             int max_q_per_seg, int k, float ratio, int32_t *d_idx, int32_t *d_dist,
-                             uint8_t *d_accept, void *cuda_stream);
+                             const uint8_t *d_train, const int32_t *d_t_offsets, int nseg, int nq_total,
+                             int max_q_per_seg, int max_t_per_seg, int k, float ratio, int32_t *d_idx,
+                             int32_t *d_dist, uint8_t *d_accept, void *cuda_stream);
 
 /* Windowed (guided) matcher with the reference's own match_keypoints semantics
  * (src/cuda/post_processing.cu:92-200, call site src/SlamGpuPipeline/buildStream.cpp:545-548): for every
@@ -267,7 +300,8 @@ int orbb_match_projection_batch(orbb_handle *h, const uint8_t *d_query_desc, con
  * and d_kp / d_desc / d_counts are that extraction's outputs.  Per LEFT keypoint: d_uright and d_depth
  * ([n_pairs][max_kp] float, -1 when there is no stereo match; depth = bf / disparity), d_nstereo [n_pairs] matches
  * surviving the median-SAD filter.  bf = fx * baseline (upstream mbf).  Row band, octave band, TH_HIGH / thOrbDist,
- * 11x11 SAD sub-pixel search and parabola fit as upstream.  Async on stream. */
+ * 11x11 SAD sub-pixel search and parabola fit as upstream.  n_pairs * max_kp must not exceed (max_batch / 2) *
+ * orbb_max_keypoints_per_frame (scratch sized in orbb_create; ORBB_ERR_CAPACITY otherwise).  Async on stream. */
 int orbb_compute_stereo_matches(orbb_handle *h, const orbb_keypoint *d_kp, const uint8_t *d_desc, const int32_t *d_counts,
                                 int max_kp, int n_pairs, float bf, float fx, float *d_uright, float *d_depth,
                                 int32_t *d_nstereo, void *cuda_stream);

@@ -203,6 +203,38 @@ inline void keypoint_pixel_to_point(orbb_handle *h, const uint32_t *d_aligned_de
                                                 d_keypoints_num, max_kp, d_kp_out, d_descriptors_out, d_points,
                                                 d_valid_keypoints_num, stream), h, "keypoint_pixel_to_point");
 }
+
+// ---- the reference's OWN signatures (src/cuda/orb.cuh:9-37), for a call site that is left as it is -------
+// The reference's free functions take no context; the handle they need here is bound once per slot thread
+// (thread-local, like the per-slot buffers of buildStream.cpp:208-341) with Jetracer::bind(handle).  Only compiled
+// where the CUDA vector types are visible (the reference's translation units include <cuda_runtime.h>).
+inline orbb_handle *&bound_handle() {
+    static thread_local orbb_handle *h = nullptr;
+    return h;
+}
+inline void bind(orbb_handle *h) { bound_handle() = h; }
+// src/cuda/orb.cuh:37: the pattern is uploaded by orbb_create; kept so the call in SlamGpuPipeline.cpp:52 still links
+inline void loadPattern() {}
+#if defined(__VECTOR_TYPES_H__) || defined(__CUDACC__)
+// src/cuda/orb.cuh:9-16.  Angles are DEGREES (upstream IC_Angle + fastAtan2); the reference kernel wrote radians
+// and then treated them as degrees, so no caller depends on the unit.
+inline void compute_fast_angle(float *d_keypoints_angle, float2 *d_keypoints_pos, unsigned char *image, int image_pitch,
+                               int image_width, int image_height, int keypoints_num, cudaStream_t stream) {
+    orbb200::check(orbb_compute_fast_angle(bound_handle(), d_keypoints_angle, reinterpret_cast<const float *>(d_keypoints_pos),
+                                           image, image_pitch, image_width, image_height, keypoints_num, stream),
+                   bound_handle(), "compute_fast_angle");
+}
+// src/cuda/orb.cuh:18-27.  d_descriptors receives EIGHT uint32_t per keypoint (the full 256 bits) instead of the
+// reference's one; d_descriptors_tmp is unused (may be nullptr); `image` must be the smoothed image.
+inline void calc_orb(float *d_keypoints_angle, float2 *d_keypoints_pos, unsigned char * /*d_descriptors_tmp*/,
+                     uint32_t *d_descriptors, unsigned char *image, int image_pitch, int image_width, int image_height,
+                     int keypoints_num, cudaStream_t stream) {
+    orbb200::check(orbb_calc_orb(bound_handle(), d_keypoints_angle, reinterpret_cast<const float *>(d_keypoints_pos),
+                                 reinterpret_cast<uint8_t *>(d_descriptors), image, image_pitch, image_width, image_height,
+                                 keypoints_num, stream),
+                   bound_handle(), "calc_orb");
+}
+#endif
 }  // namespace Jetracer
 
 #endif  // ORBB200_HPP

@@ -91,8 +91,8 @@ k_match(const uint4 *__restrict__ query, const uint4 *__restrict__ train, const 
 #pragma unroll 4
         for (int t = 0; t < cnt; ++t) {
             const uint4 a = s_t[2 * t], b = s_t[2 * t + 1];
-#pragma unroll
             const unsigned rel = (unsigned)(tb + t - ts);  // < 2^22: the host picks n_split accordingly
+#pragma unroll
             for (int j = 0; j < MATCH_QPT; ++j) {
                 const unsigned key = ((unsigned)hamming256(qa[j], qb[j], a, b) << 22) | rel;
                 if (K == 1) best[j].k1 = min(best[j].k1, key);
@@ -224,10 +224,7 @@ cudaError_t launch_match(const uint8_t *d_q, const uint8_t *d_t, const int *d_q_
                                                    d_q_off, d_t_off, nq_total, nt_one, n_split, d_partial, partial_stride);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
-    if (d_naccept) {
-        e = cudaMemsetAsync(d_naccept, 0, sizeof(int), st);
-        if (e != cudaSuccess) return e;
-    }
+    // *d_naccept is zeroed by the caller (orbb_match_knn accumulates over query chunks)
     k_match_merge<<<(nq_total + 255) / 256, 256, 0, st>>>(d_partial, partial_stride, n_split, nq_total, k, ratio, d_idx,
                                                            d_dist, d_accept, d_naccept);
     return cudaGetLastError();

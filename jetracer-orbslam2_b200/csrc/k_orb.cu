@@ -208,4 +208,125 @@ cudaError_t launch_angle_orb(const LevelDev *d_levels, int n_levels, const int *
     return cudaGetLastError();
 }
 
+// ---------------------------------------------------------------- the reference's two-call shape
+// Jetracer::compute_fast_angle / calc_orb take caller-owned arrays (float2 positions, one image) and are called
+// separately (reference src/cuda/orb.cuh:9-27, call sites src/SlamGpuPipeline/buildStream.cpp:442-460).  These two
+// kernels keep that shape with upstream arithmetic; the fused k_angle_orb above is the batch path.  Warp = keypoint.
+__global__ void __launch_bounds__(128)
+k_fast_angle_pos(float *__restrict__ angle, const float2 *__restrict__ pos, const uint8_t *__restrict__ img, int pitch, int w,
+                 int h, int n) {
+    const unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31, k = blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (k >= n) return;
+    const float2 p = pos[k];
+    const int cx = __float2int_rn(p.x), cy = __float2int_rn(p.y);  // cvRound
+    if (cx < 15 || cy < 15 || cx >= w - 15 || cy >= h - 15) {       // the disc would leave the image
+        if (lane == 0) angle[k] = -1.0f;
+        return;
+    }
+    const int u = lane - 15, au = u < 0 ? -u : u;
+    const uint8_t *rowp = img + (size_t)(cy - 15) * pitch + cx + (lane < 31 ? u : 0);
+    int colsum = 0, m01 = 0;
+#pragma unroll
+    for (int v = -15; v <= 15; ++v) {
+        const int d = umax_of(v < 0 ? -v : v);
+        const int val = (au <= d) ? (int)__ldg(rowp) : 0;  // lane 31 has au = 16 > d
+        rowp += pitch;
+        colsum += val;
+        m01 += v * val;
+    }
+    const int m10 = __reduce_add_sync(FULL, u * colsum);
+    m01 = __reduce_add_sync(FULL, m01);
+    if (lane == 0) angle[k] = fast_atan2_deg((float)m01, (float)m10);
+}
+
+__global__ void __launch_bounds__(128)
+k_calc_orb_pos(const float *__restrict__ angle, const float2 *__restrict__ pos, uint8_t *__restrict__ desc,
+               const uint8_t *__restrict__ img, int pitch, int w, int h, int n, const int8_t *__restrict__ pattern) {
+    const int lane = threadIdx.x & 31, k = blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (k >= n) return;
+    const float2 p = pos[k];
+    const int cx = __float2int_rn(p.x), cy = __float2int_rn(p.y);
+    if (cx < 18 || cy < 18 || cx > w - 19 || cy > h - 19) {  // rotated pattern reach: cvRound(13 * sqrt 2) = 18
+        desc[(size_t)k * 32 + lane] = 0;
+        return;
+    }
+    const float factor_pi = (float)(3.14159265358979323846 / 180.0);
+    const float rad = __fmul_rn(angle[k], factor_pi);
+    double sd, cd;
+    sincos((double)rad, &sd, &cd);
+    const float a = (float)cd, b = (float)sd;
+    const int8_t *pat = pattern + lane * 32;
+    const int4 q0 = *reinterpret_cast<const int4 *>(pat), q1 = *reinterpret_cast<const int4 *>(pat + 16);
+    const int wd[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
+    const uint8_t *pc = img + (size_t)cy * pitch + cx;
+    int val = 0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const float x0 = (float)(int8_t)(wd[j] & 0xff), y0 = (float)(int8_t)((wd[j] >> 8) & 0xff);
+        const float x1 = (float)(int8_t)((wd[j] >> 16) & 0xff), y1 = (float)(int8_t)((wd[j] >> 24) & 0xff);
+        const int ry0 = __float2int_rn(__fadd_rn(__fmul_rn(x0, b), __fmul_rn(y0, a)));
+        const int rx0 = __float2int_rn(__fsub_rn(__fmul_rn(x0, a), __fmul_rn(y0, b)));
+        const int ry1 = __float2int_rn(__fadd_rn(__fmul_rn(x1, b), __fmul_rn(y1, a)));
+        const int rx1 = __float2int_rn(__fsub_rn(__fmul_rn(x1, a), __fmul_rn(y1, b)));
+        const int t0 = __ldg(pc + (ptrdiff_t)ry0 * pitch + rx0), t1 = __ldg(pc + (ptrdiff_t)ry1 * pitch + rx1);
+        val |= (t0 < t1) << j;
+    }
+    desc[(size_t)k * 32 + lane] = (uint8_t)val;
+}
+
+// SoA view of the quadtree selection (the reference's detect() outputs): thread = (frame, slot)
+__global__ void __launch_bounds__(128)
+k_detect_export(const LevelDev *__restrict__ levels, int n_levels, const int *__restrict__ sel_count,
+                const int *__restrict__ slot_level, const int *__restrict__ slot_base, int n_slots, float2 *__restrict__ pos,
+                float *__restrict__ score, int *__restrict__ level, int *__restrict__ level_counts, int *__restrict__ counts,
+                int max_kp) {
+    const int gslot = blockIdx.x * blockDim.x + threadIdx.x, frame = blockIdx.y;
+    if (gslot >= n_slots) return;
+    const int *cnt = sel_count + frame * n_levels;
+    const int l = slot_level[gslot], slot = gslot - slot_base[l];
+    const LevelDev &L = levels[l];
+    int off = 0;
+    for (int i = 0; i < l; ++i) off += min(cnt[i], levels[i].sel_cap);
+    if (gslot == 0) {
+        int total = 0;
+        for (int i = 0; i < n_levels; ++i) {
+            const int c = min(cnt[i], levels[i].sel_cap);
+            if (level_counts) level_counts[frame * n_levels + i] = max(0, min(c, max_kp - total));
+            total += c;
+        }
+        if (counts) counts[frame] = min(total, max_kp);
+    }
+    if (slot >= min(cnt[l], L.sel_cap) || off + slot >= max_kp) return;
+    const uint32_t c = L.sel[(size_t)frame * L.sel_cap + slot];
+    const size_t o = (size_t)frame * max_kp + off + slot;
+    if (pos) pos[o] = make_float2((float)((int)(c & 0xfffu) + ORBB_MIN_BORDER), (float)((int)((c >> 12) & 0xfffu) + ORBB_MIN_BORDER));
+    if (score) score[o] = (float)((int)(c >> 24) - 1);
+    if (level) level[o] = l;
+}
+
+cudaError_t launch_fast_angle_pos(float *d_angle, const float *d_pos, const uint8_t *d_img, int pitch, int w, int h, int n,
+                                  cudaStream_t st) {
+    if (n <= 0) return cudaSuccess;
+    k_fast_angle_pos<<<(n + 3) / 4, 128, 0, st>>>(d_angle, reinterpret_cast<const float2 *>(d_pos), d_img, pitch, w, h, n);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_calc_orb_pos(const float *d_angle, const float *d_pos, uint8_t *d_desc, const uint8_t *d_img, int pitch, int w,
+                                int h, int n, const int8_t *d_pattern, cudaStream_t st) {
+    if (n <= 0) return cudaSuccess;
+    k_calc_orb_pos<<<(n + 3) / 4, 128, 0, st>>>(d_angle, reinterpret_cast<const float2 *>(d_pos), d_desc, d_img, pitch, w, h, n,
+                                                d_pattern);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_detect_export(const LevelDev *d_levels, int n_levels, const int *d_sel_count, const int *d_slot_level,
+                                 const int *d_slot_base, int n_slots, int n_frames, float *d_pos, float *d_score, int *d_level,
+                                 int *d_level_counts, int *d_counts, int max_kp, cudaStream_t st) {
+    dim3 grid((n_slots + 127) / 128, n_frames);
+    k_detect_export<<<grid, 128, 0, st>>>(d_levels, n_levels, d_sel_count, d_slot_level, d_slot_base, n_slots,
+                                          reinterpret_cast<float2 *>(d_pos), d_score, d_level, d_level_counts, d_counts, max_kp);
+    return cudaGetLastError();
+}
+
 }  // namespace orbb

@@ -31,6 +31,11 @@ cudaError_t launch_match_windowed(const uint8_t *, const void *, int, int, const
                                   int *, int *, int *, cudaStream_t);
 cudaError_t launch_angle_orb(const LevelDev *, int, const int *, const int8_t *, const int *, const int *, int, int, int,
                              orbb_keypoint *, uint8_t *, int *, int, cudaStream_t);
+cudaError_t launch_fast_angle_pos(float *, const float *, const uint8_t *, int, int, int, int, cudaStream_t);
+cudaError_t launch_calc_orb_pos(const float *, const float *, uint8_t *, const uint8_t *, int, int, int, int, const int8_t *,
+                                cudaStream_t);
+cudaError_t launch_detect_export(const LevelDev *, int, const int *, const int *, const int *, int, int, float *, float *, int *,
+                                 int *, int *, int, cudaStream_t);
 cudaError_t launch_match(const uint8_t *, const uint8_t *, const int *, const int *, int, int, int, int, int, int4 *,
                          int, int, float, int *, int *, uint8_t *, int *, cudaStream_t);
 cudaError_t launch_align(const uint16_t *, int, float, const orbb_intrinsics &, const orbb_intrinsics &, const orbb_extrinsics &,
@@ -54,6 +59,9 @@ cudaError_t launch_match_windowed_batch(const uint8_t *, const void *, int, cons
 using namespace orbb;
 
 #define ORBB_MAX_CHUNKS 16  // pipeline depth of orbb_extract_batch_host
+// Split-T scratch of the matcher: one int4 per (train split, query), allocated ONCE in orbb_create.  This bounds
+// n_split * nq beyond nq itself (pick_split asks for at most 64 CTAs per SM of 256 queries each, plus one round-up).
+#define ORBB_MATCH_SPLIT_ROWS ((size_t)64 * 148 * 256 + 256)
 
 static const int8_t k_pattern_host[1024] = {
 #include "../../include/orb_pattern_31.inc"
@@ -76,7 +84,7 @@ struct orbb_handle {
     int n_slots = 0, sel_cap_max = 0, pcap = 0, pcap2 = 0, max_kp = 0;
     int4 *d_partial = nullptr;
     size_t partial_cap = 0;
-    int *d_stereo_sad = nullptr;  // SAD cost per left keypoint (stereo matcher scratch), grows on demand
+    int *d_stereo_sad = nullptr;  // SAD cost per left keypoint (stereo matcher scratch), (max_batch/2) x max_kp
     size_t stereo_cap = 0;
     // staging of the *_host entry points, double-buffered so consecutive batches overlap
     uint8_t *d_in2[2] = {nullptr, nullptr};
@@ -223,6 +231,7 @@ extern "C" int orbb_create(orbb_handle **out, const orbb_params *params, int wid
     if (params->nlevels < 1 || params->nlevels > ORBB_MAX_LEVELS || !(params->scale_factor > 1.0f) ||
         params->nfeatures < 1 || max_batch < 1 || width < 1 || height < 1 || width > 4096 || height > 4096)
         return ORBB_ERR_INVALID;
+    if (max_batch > 65535) return ORBB_ERR_CAPACITY;  // the frame index rides in gridDim.y / gridDim.z
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { cudaGetLastError(); return ORBB_ERR_NO_DEVICE; }
     if (device < 0 && cudaGetDevice(&device) != cudaSuccess) return ORBB_ERR_NO_DEVICE;
@@ -483,6 +492,12 @@ extern "C" int orbb_create(orbb_handle **out, const orbb_params *params, int wid
         CKC(cudaEventCreateWithFlags(&h->ev_tail[i], cudaEventDisableTiming));
     }
     CKC(dalloc(h, &h->d_dump, (size_t)dump_total));
+    // matcher / stereo scratch, allocated once (no call on the per-batch path allocates): split-T partial results for
+    // the query sets this handle can produce (larger ones are chunked), SAD costs for max_batch/2 stereo pairs
+    h->partial_cap = ORBB_MATCH_SPLIT_ROWS + std::max<size_t>((size_t)B * h->max_kp, (size_t)1 << 18);
+    CKC(dalloc(h, &h->d_partial, h->partial_cap));
+    h->stereo_cap = (size_t)std::max(B / 2, 1) * h->max_kp;
+    CKC(dalloc(h, &h->d_stereo_sad, h->stereo_cap));
     CKC(cudaStreamCreateWithFlags(&h->s_in, cudaStreamNonBlocking));
     CKC(cudaStreamCreateWithFlags(&h->s_out, cudaStreamNonBlocking));
     for (int i = 0; i < 2; ++i) {
@@ -615,6 +630,7 @@ static int run_all(orbb_handle *h, const uint8_t *d_images, size_t pitch, size_t
 extern "C" int orbb_stage_upload(orbb_handle *h, const uint8_t *d_images, size_t pitch, size_t frame_stride,
                                  int n_frames, void *stream) {
     if (!h || !d_images || n_frames < 1 || pitch < (size_t)h->w) return ORBB_ERR_INVALID;
+    if (n_frames > 1 && frame_stride < pitch * (size_t)h->h) return ORBB_ERR_INVALID;  // frames would overlap
     if (n_frames > h->max_batch) return ORBB_ERR_CAPACITY;
     CK(h, cudaSetDevice(h->device));
     h->n_frames_last = n_frames;
@@ -628,6 +644,12 @@ extern "C" int orbb_pyramid_create_levels(orbb_handle *h, void *stream) {
 
 extern "C" int orbb_detect_fast(orbb_handle *h, void *stream) {
     if (!h || h->n_frames_last < 1) return ORBB_ERR_INVALID;
+    // re-runnable on the resident batch: the candidate lists restart from zero (the whole-extractor path clears
+    // them in run_upload instead, which keeps the pyramid -> FAST chain free of a memset node).  The quadtree cell
+    // tables are cleared by the quadtree kernel that consumed them; a second detect_fast WITHOUT a distribute in
+    // between leaves them double-counted, which the quadtree kernel detects (table total != list length) and answers
+    // with its general sorted-key path -- same selection.
+    CK(h, cudaMemsetAsync(h->d_cand_count, 0, sizeof(int) * (size_t)h->n_frames_last * h->nlevels, static_cast<cudaStream_t>(stream)));
     return run_fast(h, 0, h->n_frames_last, static_cast<cudaStream_t>(stream));
 }
 
@@ -652,11 +674,48 @@ extern "C" int orbb_compute_angle_and_orb(orbb_handle *h, orbb_keypoint *d_kp, u
     return run_angle_orb(h, 0, h->n_frames_last, d_kp, d_desc, d_counts, max_kp, static_cast<cudaStream_t>(stream));
 }
 
+extern "C" int orbb_compute_fast_angle(orbb_handle *h, float *d_angle, const float *d_pos_xy, const uint8_t *d_image,
+                                       int image_pitch, int image_width, int image_height, int keypoints_num, void *stream) {
+    if (!h || !d_angle || !d_pos_xy || !d_image || keypoints_num < 0 || image_width < 1 || image_height < 1 ||
+        image_pitch < image_width || (reinterpret_cast<uintptr_t>(d_pos_xy) & 7))
+        return ORBB_ERR_INVALID;
+    CK(h, cudaSetDevice(h->device));
+    CK(h, launch_fast_angle_pos(d_angle, d_pos_xy, d_image, image_pitch, image_width, image_height, keypoints_num,
+                                static_cast<cudaStream_t>(stream)));
+    h->n_launches += keypoints_num > 0;
+    return ORBB_OK;
+}
+
+extern "C" int orbb_calc_orb(orbb_handle *h, const float *d_angle, const float *d_pos_xy, uint8_t *d_desc,
+                             const uint8_t *d_blurred_image, int image_pitch, int image_width, int image_height,
+                             int keypoints_num, void *stream) {
+    if (!h || !d_angle || !d_pos_xy || !d_desc || !d_blurred_image || keypoints_num < 0 || image_width < 1 ||
+        image_height < 1 || image_pitch < image_width || (reinterpret_cast<uintptr_t>(d_pos_xy) & 7))
+        return ORBB_ERR_INVALID;
+    CK(h, cudaSetDevice(h->device));
+    CK(h, launch_calc_orb_pos(d_angle, d_pos_xy, d_desc, d_blurred_image, image_pitch, image_width, image_height,
+                              keypoints_num, h->d_pattern, static_cast<cudaStream_t>(stream)));
+    h->n_launches += keypoints_num > 0;
+    return ORBB_OK;
+}
+
+extern "C" int orbb_detect_export(orbb_handle *h, float *d_pos_xy, float *d_score, int32_t *d_level, int32_t *d_level_counts,
+                                  int32_t *d_counts, int max_kp, void *stream) {
+    if (!h || max_kp < 1 || h->n_frames_last < 1 || (reinterpret_cast<uintptr_t>(d_pos_xy) & 7)) return ORBB_ERR_INVALID;
+    CK(h, cudaSetDevice(h->device));
+    CK(h, launch_detect_export(h->d_levels, h->nlevels, h->d_sel_count, h->d_slot_level, h->d_slot_base, h->n_slots,
+                               h->n_frames_last, d_pos_xy, d_score, d_level, d_level_counts, d_counts, max_kp,
+                               static_cast<cudaStream_t>(stream)));
+    h->n_launches += 1;
+    return ORBB_OK;
+}
+
 extern "C" int orbb_extract_batch_device(orbb_handle *h, const uint8_t *d_images, size_t pitch, size_t frame_stride,
                                          int n_frames, orbb_keypoint *d_kp, uint8_t *d_desc, int32_t *d_counts,
                                          int max_kp, void *stream) {
     if (!h || !d_images || !d_kp || !d_desc || !d_counts || max_kp < 1 || n_frames < 1 || pitch < (size_t)h->w)
         return ORBB_ERR_INVALID;
+    if (n_frames > 1 && frame_stride < pitch * (size_t)h->h) return ORBB_ERR_INVALID;  // frames would overlap
     if (n_frames > h->max_batch) return ORBB_ERR_CAPACITY;
     CK(h, cudaSetDevice(h->device));
     h->n_frames_last = n_frames;
@@ -741,6 +800,7 @@ static int submit_host(orbb_handle *h, const uint8_t *h_images, size_t pitch, si
                        bool latency_mode) {
     if (!h || !h_images || !h_kp || !h_desc || !h_counts || max_kp < 1 || pitch < (size_t)h->w) return ORBB_ERR_INVALID;
     if (n_frames < 1 || n_frames > h->max_batch) return ORBB_ERR_CAPACITY;
+    if (n_frames > 1 && frame_stride < pitch * (size_t)h->h) return ORBB_ERR_INVALID;  // frames would overlap
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     CK(h, cudaSetDevice(h->device));
     const int ticket = (int)h->n_submitted, par = ticket & 1;
@@ -818,22 +878,17 @@ extern "C" int orbb_extract_batch_host(orbb_handle *h, const uint8_t *h_images, 
 }
 
 // ---------------------------------------------------------------- matcher
-static int ensure_partial(orbb_handle *h, size_t need) {
-    if (need <= h->partial_cap) return ORBB_OK;
-    int4 *p = nullptr;
-    CK(h, dalloc(h, &p, need));  // grows monotonically; old block is released in orbb_destroy
-    h->d_partial = p;
-    h->partial_cap = need;
-    return ORBB_OK;
-}
+// The split-T scratch (ORBB_MATCH_SPLIT_ROWS + the handle's own keypoint capacity) is allocated in orbb_create; larger
+// query sets are processed in query chunks that fit, so no call allocates or synchronises.  The scratch is per
+// handle: matcher calls on one handle must be issued on one stream (or be ordered by the caller).
 
 // Split of the train range across blockIdx.y.  Measured on B200: the kernel keeps gaining until about 64 CTAs per SM
 // are queued (796 -> 886 Gpairs/s for 257 k x 50 k): small CTAs even out the tail and keep every SM's POPC pipe fed.
-static int pick_split(int qblocks_total, int nt) {
+static int pick_split(int qblocks_total, long long nt) {
     static const int per_sm = getenv("ORBB_MATCH_CTAS") ? std::max(atoi(getenv("ORBB_MATCH_CTAS")), 1) : 64;
     int want = (per_sm * 148 + qblocks_total - 1) / std::max(qblocks_total, 1);
-    want = std::min(want, std::max(1, nt / 128));  // at least one shared-memory tile of train rows per split
-    want = std::max(want, (int)(((long long)nt + (1 << 22) - 1) >> 22));  // packed keys hold 22 index bits per split
+    want = (int)std::min<long long>(want, std::max<long long>(1, nt / 128));  // at least one shared-memory tile of train rows per split
+    want = std::max(want, (int)((nt + (1 << 22) - 1) >> 22));  // packed keys hold 22 index bits per split
     return std::max(1, std::min(want, 64));
 }
 
@@ -842,37 +897,47 @@ extern "C" int orbb_match_knn(orbb_handle *h, const uint8_t *d_query, int nq, co
                               void *stream) {
     if (!h || !d_query || !d_train || !d_idx || !d_dist || nq < 0 || nt < 0 || k < 1 || k > 2) return ORBB_ERR_INVALID;
     if ((reinterpret_cast<uintptr_t>(d_query) | reinterpret_cast<uintptr_t>(d_train)) & 15) return ORBB_ERR_INVALID;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    CK(h, cudaSetDevice(h->device));
+    if (d_naccept) CK(h, cudaMemsetAsync(d_naccept, 0, sizeof(int), st));
     if (nq == 0) return ORBB_OK;
     if (nt > 64 * (1 << 22)) return ORBB_ERR_CAPACITY;  // 268 M train rows per call
-    const int qblocks = (nq + 255) / 256;
-    const int n_split = pick_split(qblocks, nt);
-    int rc = ensure_partial(h, (size_t)n_split * nq);
-    if (rc) return rc;
-    CK(h, launch_match(d_query, d_train, nullptr, nullptr, 1, nq, nq, nt, n_split, h->d_partial, nq, k, ratio, d_idx,
-                       d_dist, d_accept, d_naccept, static_cast<cudaStream_t>(stream)));
-    h->n_launches += 2;
+    const int max_chunk = (int)std::min<size_t>((h->partial_cap - ORBB_MATCH_SPLIT_ROWS) & ~(size_t)255, (size_t)1 << 30);
+    for (int q0 = 0; q0 < nq;) {
+        int n = std::min(nq - q0, max_chunk);
+        int n_split = pick_split((n + 255) / 256, nt);
+        if ((size_t)n_split * n > h->partial_cap) {  // only when a huge train set forces many splits
+            n = (int)((h->partial_cap / n_split) & ~(size_t)255);
+            n_split = pick_split((n + 255) / 256, nt);
+        }
+        CK(h, launch_match(d_query + 32 * (size_t)q0, d_train, nullptr, nullptr, 1, n, n, nt, n_split, h->d_partial, n, k, ratio,
+                           d_idx + 2 * (size_t)q0, d_dist + 2 * (size_t)q0, d_accept ? d_accept + q0 : nullptr, d_naccept, st));
+        h->n_launches += 2;
+        q0 += n;
+    }
     return ORBB_OK;
 }
 
 extern "C" int orbb_match_knn_segmented(orbb_handle *h, const uint8_t *d_query, const int32_t *d_q_offsets,
-                                        const uint8_t *d_train, const int32_t *d_t_offsets, int nseg,
-                                        int max_q_per_seg, int k, float ratio, int32_t *d_idx, int32_t *d_dist,
-                                        uint8_t *d_accept, void *stream) {
-    if (!h || !d_query || !d_train || !d_q_offsets || !d_t_offsets || !d_idx || !d_dist || nseg < 1 ||
-        max_q_per_seg < 1 || k < 1 || k > 2)
+                                        const uint8_t *d_train, const int32_t *d_t_offsets, int nseg, int nq_total,
+                                        int max_q_per_seg, int max_t_per_seg, int k, float ratio, int32_t *d_idx,
+                                        int32_t *d_dist, uint8_t *d_accept, void *stream) {
+    if (!h || !d_query || !d_train || !d_q_offsets || !d_t_offsets || !d_idx || !d_dist || nseg < 1 || nseg > 65535 ||
+        nq_total < 0 || max_q_per_seg < 1 || max_t_per_seg < 0 || k < 1 || k > 2)
         return ORBB_ERR_INVALID;
     if ((reinterpret_cast<uintptr_t>(d_query) | reinterpret_cast<uintptr_t>(d_train)) & 15) return ORBB_ERR_INVALID;
-    cudaStream_t st = static_cast<cudaStream_t>(stream);
-    int nq_total = 0;  // last offset; one small D2H (the offsets are the caller's, sizes are needed for the grid)
-    CK(h, cudaMemcpyAsync(&nq_total, d_q_offsets + nseg, sizeof(int), cudaMemcpyDeviceToHost, st));
-    CK(h, cudaStreamSynchronize(st));
-    if (nq_total <= 0) return ORBB_OK;
+    if (nq_total == 0) return ORBB_OK;
+    if (max_t_per_seg > 64 * (1 << 22)) return ORBB_ERR_CAPACITY;
+    CK(h, cudaSetDevice(h->device));
     const int qblocks = (max_q_per_seg + 255) / 256 * nseg;
-    const int n_split = pick_split(qblocks, 1024);
-    int rc = ensure_partial(h, (size_t)n_split * nq_total);
-    if (rc) return rc;
+    int n_split = pick_split(qblocks, std::max(max_t_per_seg, 1));
+    // the sizes are the caller's (no device read-back, no synchronisation): fewer splits if the scratch would not hold
+    // n_split x nq_total rows, as long as every split still indexes its train rows with 22 bits
+    const int min_split = std::max(1, (int)(((long long)max_t_per_seg + (1 << 22) - 1) >> 22));
+    if ((size_t)n_split * nq_total > h->partial_cap) n_split = (int)(h->partial_cap / (size_t)nq_total);
+    if (n_split < min_split) return ORBB_ERR_CAPACITY;
     CK(h, launch_match(d_query, d_train, d_q_offsets, d_t_offsets, nseg, nq_total, max_q_per_seg, 0, n_split,
-                       h->d_partial, nq_total, k, ratio, d_idx, d_dist, d_accept, nullptr, st));
+                       h->d_partial, nq_total, k, ratio, d_idx, d_dist, d_accept, nullptr, static_cast<cudaStream_t>(stream)));
     h->n_launches += 2;
     return ORBB_OK;
 }
@@ -996,13 +1061,7 @@ extern "C" int orbb_compute_stereo_matches(orbb_handle *h, const orbb_keypoint *
     if (2 * n_pairs > h->n_frames_last) return ORBB_ERR_CAPACITY;  // the pairs' pyramids must be resident
     if (reinterpret_cast<uintptr_t>(d_desc) & 15) return ORBB_ERR_INVALID;
     CK(h, cudaSetDevice(h->device));
-    const size_t need = (size_t)n_pairs * max_kp;
-    if (need > h->stereo_cap) {
-        int *p = nullptr;
-        CK(h, dalloc(h, &p, need));  // grows monotonically; released in orbb_destroy
-        h->d_stereo_sad = p;
-        h->stereo_cap = need;
-    }
+    if ((size_t)n_pairs * max_kp > h->stereo_cap) return ORBB_ERR_CAPACITY;  // scratch sized once in orbb_create
     CK(h, launch_stereo(h->d_levels, h->sf, h->inv_sf, h->nlevels, d_kp, d_desc, d_counts, max_kp, n_pairs, bf, fx, d_uright,
                         d_depth, h->d_stereo_sad, d_nstereo, static_cast<cudaStream_t>(stream)));
     h->n_launches += 2;

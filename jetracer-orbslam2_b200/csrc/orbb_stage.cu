@@ -32,7 +32,7 @@ struct orbb_rgbd_stage {
     uint32_t *d_aligned = nullptr;
     orbb_keypoint *d_kp_raw = nullptr, *d_kp = nullptr;
     uint8_t *d_desc_raw = nullptr, *d_desc = nullptr;
-    int *d_counts_raw = nullptr, *d_valid = nullptr, *d_idx = nullptr, *d_dist = nullptr, *d_nm = nullptr;
+    int *d_counts_raw = nullptr, *d_counts_blk = nullptr, *d_valid = nullptr, *d_idx = nullptr, *d_dist = nullptr, *d_nm = nullptr;
     double *d_pts = nullptr, *d_prev_m = nullptr, *d_curr_m = nullptr;
     float *d_pos = nullptr;
     uint16_t *d_xy = nullptr;
@@ -52,6 +52,7 @@ struct orbb_rgbd_stage {
     std::vector<void *> dev_allocs, host_allocs;
     long long n_submitted = 0;
     bool gate_recorded = false;
+    int carry_from = 0;  // > 0: row `carry_from` of the result block (the previous batch's last frame) still has to become row 0
     // diagnostics (ORBB_STAGE_PROF=1): timing events at the phase boundaries of the last submit, printed by wait()
     bool prof = false;
     cudaEvent_t pe[8] = {};
@@ -146,6 +147,9 @@ extern "C" int orbb_rgbd_stage_create(orbb_rgbd_stage **out, const orbb_rgbd_con
     SCKC(sdev(s, &s->d_aligned, s->img_px * B));
     SCKC(sdev(s, &s->d_kp_raw, B * mk)); SCKC(sdev(s, &s->d_desc_raw, B * mk * 32));
     SCKC(sdev(s, &s->d_pos, B * mk * 2)); SCKC(sdev(s, &s->d_idx, B * mk)); SCKC(sdev(s, &s->d_dist, B * mk));
+    // the extraction's per-frame counts land OUTSIDE the result block: batch k+1's extraction is enqueued before the
+    // wait for batch k's D2H of the block, so it must not write into it
+    SCKC(sdev(s, &s->d_counts_raw, B));
     {
         // result block layout (256-byte aligned slices); rows 0 of kp/desc/pts/valid carry the previous batch's last frame
         size_t off = 0;
@@ -159,7 +163,7 @@ extern "C" int orbb_rgbd_stage_create(orbb_rgbd_stage **out, const orbb_rgbd_con
         uint8_t *d = s->d_block;
         s->d_kp = reinterpret_cast<orbb_keypoint *>(d + o_kp); s->d_desc = d + o_desc; s->d_pts = reinterpret_cast<double *>(d + o_pts);
         s->d_prev_m = reinterpret_cast<double *>(d + o_prev); s->d_curr_m = reinterpret_cast<double *>(d + o_curr);
-        s->d_xy = reinterpret_cast<uint16_t *>(d + o_xy); s->d_counts_raw = reinterpret_cast<int *>(d + o_cnt);
+        s->d_xy = reinterpret_cast<uint16_t *>(d + o_xy); s->d_counts_blk = reinterpret_cast<int *>(d + o_cnt);
         s->d_valid = reinterpret_cast<int *>(d + o_valid); s->d_nm = reinterpret_cast<int *>(d + o_nm);
         for (int i = 0; i < 2; ++i) {
             SCKC(shost(s, &s->h_block[i], off));
@@ -186,6 +190,7 @@ extern "C" orbb_handle *orbb_rgbd_stage_handle(orbb_rgbd_stage *s) { return s ? 
 extern "C" int orbb_rgbd_stage_reset(orbb_rgbd_stage *s) {
     if (!s) return ORBB_ERR_INVALID;
     SCK(s, cudaSetDevice(s->device));
+    s->carry_from = 0;  // a pending carry would overwrite the reset
     SCK(s, cudaMemsetAsync(s->d_valid, 0, sizeof(int), s->s_main));  // row 0 = "no previous frame"
     return ORBB_OK;
 }
@@ -228,6 +233,17 @@ extern "C" int orbb_rgbd_stage_submit(orbb_rgbd_stage *s, const uint8_t *h_gray,
     // ---- depth gate + 3-D lift into rows 1..n (the previous batch's D2H must have drained them)
     SCK(s, cudaStreamWaitEvent(s->s_main, s->ev_align, 0));
     if (ticket >= 1) SCK(s, cudaStreamWaitEvent(s->s_main, s->ev_out[p ^ 1], 0));
+    // From here on the previous batch's D2H of the result block has completed, so the block may be written:
+    // first the carry (the previous batch's last frame becomes row 0, read by this batch's reprojection / match
+    // only), then this batch's counts and rows 1..n.
+    if (s->carry_from > 0) {
+        const size_t c = (size_t)s->carry_from;
+        SCK(s, cudaMemcpyAsync(s->d_kp, s->d_kp + c * mk, sizeof(orbb_keypoint) * mk, cudaMemcpyDeviceToDevice, s->s_main));
+        SCK(s, cudaMemcpyAsync(s->d_desc, s->d_desc + 32 * c * mk, 32 * mk, cudaMemcpyDeviceToDevice, s->s_main));
+        SCK(s, cudaMemcpyAsync(s->d_pts, s->d_pts + 3 * c * mk, sizeof(double) * 3 * mk, cudaMemcpyDeviceToDevice, s->s_main));
+        SCK(s, cudaMemcpyAsync(s->d_valid, s->d_valid + c, sizeof(int), cudaMemcpyDeviceToDevice, s->s_main));
+    }
+    SCK(s, cudaMemcpyAsync(s->d_counts_blk, s->d_counts_raw, sizeof(int) * n, cudaMemcpyDeviceToDevice, s->s_main));
     SRC(orbb_keypoint_pixel_to_point(s->h, s->d_aligned, &s->cfg.image_intrin, n_frames, s->d_kp_raw, s->d_desc_raw,
                                      s->d_counts_raw, s->max_kp, s->d_kp + mk, s->d_desc + 32 * mk, s->d_pts + 3 * mk,
                                      s->d_valid + 1, s->s_main));
@@ -248,7 +264,7 @@ extern "C" int orbb_rgbd_stage_submit(orbb_rgbd_stage *s, const uint8_t *h_gray,
     if (n_frames == s->B) {
         SCK(s, cudaMemcpyAsync(s->h_block[p], s->d_block, s->block_bytes, cudaMemcpyDeviceToHost, s->s_out));
     } else {  // partial batch: only the rows in use
-        SCK(s, cudaMemcpyAsync(H.counts, s->d_counts_raw, sizeof(int) * n, cudaMemcpyDeviceToHost, s->s_out));
+        SCK(s, cudaMemcpyAsync(H.counts, s->d_counts_blk, sizeof(int) * n, cudaMemcpyDeviceToHost, s->s_out));
         SCK(s, cudaMemcpyAsync(H.valid, s->d_valid + 1, sizeof(int) * n, cudaMemcpyDeviceToHost, s->s_out));
         SCK(s, cudaMemcpyAsync(H.matched, s->d_nm, sizeof(int) * n, cudaMemcpyDeviceToHost, s->s_out));
         SCK(s, cudaMemcpyAsync(H.kp, s->d_kp + mk, sizeof(orbb_keypoint) * n * mk, cudaMemcpyDeviceToHost, s->s_out));
@@ -261,11 +277,9 @@ extern "C" int orbb_rgbd_stage_submit(orbb_rgbd_stage *s, const uint8_t *h_gray,
     SCK(s, cudaEventRecord(s->ev_out[p], s->s_out));
     SPROF(s, 6, s->s_out);
     H.n_frames = n_frames;
-    // ---- carry: the batch's last frame becomes row 0 (read by the next batch's reprojection / match only)
-    SCK(s, cudaMemcpyAsync(s->d_kp, s->d_kp + n * mk, sizeof(orbb_keypoint) * mk, cudaMemcpyDeviceToDevice, s->s_main));
-    SCK(s, cudaMemcpyAsync(s->d_desc, s->d_desc + 32 * n * mk, 32 * mk, cudaMemcpyDeviceToDevice, s->s_main));
-    SCK(s, cudaMemcpyAsync(s->d_pts, s->d_pts + 3 * n * mk, sizeof(double) * 3 * mk, cudaMemcpyDeviceToDevice, s->s_main));
-    SCK(s, cudaMemcpyAsync(s->d_valid, s->d_valid + n, sizeof(int), cudaMemcpyDeviceToDevice, s->s_main));
+    // ---- carry: the batch's last frame (row n) becomes row 0 at the START of the next submit, after that submit's
+    // wait for this batch's D2H -- copying it here would write row 0 of the block while the D2H above reads it
+    s->carry_from = n_frames;
     s->n_submitted++;
     return ticket;
 }

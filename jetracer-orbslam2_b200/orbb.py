@@ -32,7 +32,8 @@ EXPORTS = [
     "orbb_get_launch_count", "orbb_get_level",
     "orbb_extract_batch_device", "orbb_extract_batch_host", "orbb_extract_batch_host_async", "orbb_wait",
     "orbb_stage_upload", "orbb_pyramid_create_levels",
-    "orbb_detect", "orbb_detect_fast", "orbb_detect_distribute", "orbb_gaussian_blur", "orbb_compute_angle_and_orb", "orbb_match_knn",
+    "orbb_detect", "orbb_detect_fast", "orbb_detect_distribute", "orbb_gaussian_blur", "orbb_compute_angle_and_orb",
+    "orbb_compute_fast_angle", "orbb_calc_orb", "orbb_detect_export", "orbb_match_knn",
     "orbb_match_knn_segmented", "orbb_match_windowed", "orbb_debug_get_padded", "orbb_debug_get_blurred", "orbb_debug_get_scores",
     "orbb_debug_get_candidates", "orbb_debug_get_selected", "orbb_debug_distribute",
     "orbb_align_depth_to_other", "orbb_keypoint_pixel_to_point", "orbb_reproject_points", "orbb_match_windowed_batch",
@@ -132,7 +133,10 @@ def load_library():
     L.orbb_gaussian_blur.argtypes = [vp, vp]
     L.orbb_compute_angle_and_orb.argtypes = [vp, vp, vp, vp, i32, vp]
     L.orbb_match_knn.argtypes = [vp, vp, i32, vp, i32, i32, f32, vp, vp, vp, vp, vp]
-    L.orbb_match_knn_segmented.argtypes = [vp, vp, vp, vp, vp, i32, i32, i32, f32, vp, vp, vp, vp]
+    L.orbb_compute_fast_angle.argtypes = [vp, vp, vp, vp, i32, i32, i32, i32, vp]
+    L.orbb_calc_orb.argtypes = [vp, vp, vp, vp, vp, i32, i32, i32, i32, vp]
+    L.orbb_detect_export.argtypes = [vp, vp, vp, vp, vp, vp, i32, vp]
+    L.orbb_match_knn_segmented.argtypes = [vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, f32, vp, vp, vp, vp]
     L.orbb_match_windowed.argtypes = [vp, vp, vp, i32, i32, vp, vp, i32, i32, f32, i32, vp, vp, vp, vp]
     L.orbb_debug_get_padded.argtypes = [vp, i32, i32, vp]
     L.orbb_debug_get_blurred.argtypes = [vp, i32, i32, vp]
@@ -332,6 +336,25 @@ class ORBextractor:
         self._check(self._lib.orbb_compute_angle_and_orb(self._h, _dev_ptr(d_kp), _dev_ptr(d_desc), _dev_ptr(d_counts),
                                                          self.max_kp, _stream_ptr(stream)))
 
+    def compute_fast_angle(self, d_angle, d_pos, image_ptr: int, pitch: int, width: int, height: int, n: int, stream=None):
+        """Jetracer::compute_fast_angle(d_keypoints_angle, d_keypoints_pos, image, pitch, w, h, n, stream): IC_Angle in
+        degrees for n float2 positions of one device image (``image_ptr`` = raw device address, e.g. a level ROI)."""
+        self._check(self._lib.orbb_compute_fast_angle(self._h, _dev_ptr(d_angle), _dev_ptr(d_pos), C.c_void_p(int(image_ptr)),
+                                                      pitch, width, height, n, _stream_ptr(stream)))
+
+    def calc_orb(self, d_angle, d_pos, d_desc, blurred_ptr: int, pitch: int, width: int, height: int, n: int, stream=None):
+        """Jetracer::calc_orb: 256-bit steered BRIEF for n float2 positions on one smoothed device image."""
+        self._check(self._lib.orbb_calc_orb(self._h, _dev_ptr(d_angle), _dev_ptr(d_pos), _dev_ptr(d_desc),
+                                            C.c_void_p(int(blurred_ptr)), pitch, width, height, n, _stream_ptr(stream)))
+
+    def detect_export(self, d_pos=None, d_score=None, d_level=None, d_level_counts=None, d_counts=None, max_kp=None,
+                      stream=None):
+        """SoA outputs of Jetracer::detect (pos / score / level per selected keypoint) for the resident batch."""
+        opt = lambda t: _dev_ptr(t) if t is not None else C.c_void_p(0)  # noqa: E731
+        self._check(self._lib.orbb_detect_export(self._h, opt(d_pos), opt(d_score), opt(d_level), opt(d_level_counts),
+                                                 opt(d_counts), self.max_kp if max_kp is None else max_kp,
+                                                 _stream_ptr(stream)))
+
     def match_keypoints(self, d_query, nq: int, d_train, nt: int, d_idx, d_dist, d_accept=None, d_naccept=None,
                         k: int = 2, ratio: float = 0.7, stream=None):
         """Jetracer::match_keypoints slot: brute-force Hamming k-NN + ratio test on device descriptors."""
@@ -341,10 +364,13 @@ class ORBextractor:
                                              _dev_ptr(d_naccept) if d_naccept is not None else C.c_void_p(0),
                                              _stream_ptr(stream)))
 
-    def match_keypoints_segmented(self, d_query, d_q_off, d_train, d_t_off, nseg: int, max_q_per_seg: int, d_idx,
-                                  d_dist, d_accept=None, k: int = 2, ratio: float = 0.7, stream=None):
+    def match_keypoints_segmented(self, d_query, d_q_off, d_train, d_t_off, nseg: int, nq_total: int, max_q_per_seg: int,
+                                  max_t_per_seg: int, d_idx, d_dist, d_accept=None, k: int = 2, ratio: float = 0.7,
+                                  stream=None):
+        """nq_total / max_q_per_seg / max_t_per_seg are HOST-side sizes (the call never reads the offsets back)."""
         self._check(self._lib.orbb_match_knn_segmented(self._h, _dev_ptr(d_query), _dev_ptr(d_q_off), _dev_ptr(d_train),
-                                                       _dev_ptr(d_t_off), nseg, max_q_per_seg, k, ratio,
+                                                       _dev_ptr(d_t_off), nseg, nq_total, max_q_per_seg, max_t_per_seg,
+                                                       k, ratio,
                                                        _dev_ptr(d_idx), _dev_ptr(d_dist),
                                                        _dev_ptr(d_accept) if d_accept is not None else C.c_void_p(0),
                                                        _stream_ptr(stream)))

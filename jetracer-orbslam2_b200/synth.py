@@ -94,3 +94,15 @@ def shifted_frame(img: np.ndarray, dx: int, dy: int, seed: int, noise: int = 3) 
     xs = np.clip(np.arange(w) - dx, 0, w - 1)
     out = img[ys][:, xs].astype(np.int16) + rng.integers(-noise, noise + 1, size=img.shape).astype(np.int16)
     return np.clip(out, 0, 255).astype(np.uint8)
+
+
+def rolled_batch(width: int, height: int, n: int, seed0: int, n_base: int = 16) -> np.ndarray:
+    """[n, height, width] distinct textured frames, cheap to make: n_base seeded frames, then cyclic shifts of them
+    (frame i = base[i % n_base] rolled by (37k, 53k) pixels, k = i // n_base).  bench.py's workload generator."""
+    base = [textured_frame(width, height, seed0 + i) for i in range(min(n, n_base))]
+    out = np.empty((n, height, width), np.uint8)
+    for i in range(n):
+        b = base[i % len(base)]
+        k = i // len(base)
+        out[i] = np.roll(b, (37 * k, 53 * k), axis=(0, 1)) if k else b
+    return out

@@ -1,0 +1,332 @@
+"""GPU tier, part 2: the paths behind the headline numbers and the boundary contract of include/orbb200.h.
+
+  * the bench workloads themselves -- 256 x 640x480 through the two-stream device path and through the double-buffered
+    host path, 64 x 848x480 (cfg 2) -- against the oracle on sampled frames of BOTH batch parts;
+  * Jetracer::compute_fast_angle / calc_orb as separate calls (reference src/cuda/orb.cuh:9-27) == the fused kernel;
+  * stage calls are re-runnable; no entry point other than *_host / wait / debug_* blocks the calling thread;
+  * matcher scratch is fixed-size: query sets larger than it are chunked, results unchanged.
+"""
+import importlib
+import os
+import time
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def orbb():
+    import torch
+    assert torch.cuda.is_available(), "GPU tier needs a CUDA device"
+    import __graft_entry__ as g
+    g.build()
+    return importlib.import_module("jetracer-orbslam2_b200.orbb")
+
+
+def canon(kp, desc):
+    order = np.lexsort((kp["x"], kp["y"], kp["octave"]))
+    return kp[order], desc[order]
+
+
+def _check_frames(oracle, frames, sample, kp, desc, cnt, w, h, nf):
+    o = oracle.Oracle(w, h, nf)
+    for f in sample:
+        okp, odesc = canon(*o.extract(frames[f]))
+        gkp, gdesc = canon(kp[f, :cnt[f]], desc[f, :cnt[f]])
+        assert len(gkp) == len(okp), f"frame {f}: {len(gkp)} vs {len(okp)} keypoints"
+        assert gkp.tobytes() == okp.tobytes(), f"frame {f}: keypoint fields differ"
+        assert np.array_equal(gdesc, odesc), f"frame {f}: descriptor bits differ"
+
+
+def test_headline_batch_256x640x480_vs_oracle(orbb, oracle, synth):
+    """bench.py's timed call: 256 frames of 640x480 / 1000 kp in ONE orbb_extract_batch_device (two batch parts on two
+    streams, throughput kernel variants) and in ONE orbb_extract_batch_host_async (chunked H2D -> compute -> D2H).
+    Sampled frames of both parts, first / last frame of each part included, must equal the oracle bit for bit."""
+    import torch
+    w, h, nf, nb = 640, 480, 1000, 256
+    frames = synth.rolled_batch(w, h, nb, 1000)
+    ex = orbb.ORBextractor(nf, 1.2, 8, 20, 7, width=w, height=h, max_batch=nb)
+    st = torch.cuda.current_stream()
+    d_in = torch.from_numpy(frames).cuda()
+    d_kp = torch.zeros((nb, ex.max_kp, 7), dtype=torch.float32, device="cuda")
+    d_desc = torch.zeros((nb, ex.max_kp, 32), dtype=torch.uint8, device="cuda")
+    d_cnt = torch.zeros(nb, dtype=torch.int32, device="cuda")
+    ex.extract_batch_device(d_in, nb, d_kp, d_desc, d_cnt, stream=st)
+    torch.cuda.synchronize()
+    kp = d_kp.cpu().numpy().view(orbb.KEYPOINT_DTYPE).reshape(nb, ex.max_kp)
+    desc, cnt = d_desc.cpu().numpy(), d_cnt.cpu().numpy()
+    sample = [0, 1, 63, 127, 128, 129, 200, 255]
+    _check_frames(oracle, frames, sample, kp, desc, cnt, w, h, nf)
+    # the end-to-end path of the headline e2e number: same bytes as the device path for EVERY frame
+    pin = torch.from_numpy(frames).pin_memory()
+    hk = torch.zeros(nb * ex.max_kp * 28, dtype=torch.uint8).pin_memory()
+    hd = torch.zeros(nb * ex.max_kp * 32, dtype=torch.uint8).pin_memory()
+    hc = torch.zeros(nb, dtype=torch.int32).pin_memory()
+    for _ in range(2):  # second submission: same chunk layout, streams not cross-serialised
+        t = ex.extract_batch_host_async(pin.data_ptr(), w, w * h, nb, hk.data_ptr(), hd.data_ptr(), hc.data_ptr(), stream=st)
+        ex.wait(t)
+        assert np.array_equal(hc.numpy(), cnt)
+        k2 = np.frombuffer(hk.numpy().tobytes(), orbb.KEYPOINT_DTYPE).reshape(nb, ex.max_kp)
+        d2 = hd.numpy().reshape(nb, ex.max_kp, 32)
+        for f in range(nb):
+            n = int(cnt[f])
+            assert k2[f, :n].tobytes() == kp[f, :n].tobytes() and d2[f, :n].tobytes() == desc[f, :n].tobytes(), f
+        hk.zero_(); hd.zero_(); hc.zero_()
+    ex.close()
+
+
+def test_cfg2_batch_64x848x480_vs_oracle(orbb, oracle, synth):
+    """BASELINE cfg 2: 64 frames of 848x480, 1200 kp, one batch (the multi-stream split starts at 64 frames)."""
+    w, h, nf, nb = 848, 480, 1200, 64
+    frames = synth.rolled_batch(w, h, nb, 2000, n_base=8)
+    ex = orbb.ORBextractor(nf, 1.2, 8, 20, 7, width=w, height=h, max_batch=nb)
+    kp, desc, cnt = ex.extract_batch(frames)
+    _check_frames(oracle, frames, [0, 31, 32, 47, 63], kp, desc, cnt, w, h, nf)
+    ex.close()
+
+
+def test_separate_angle_and_orb_entry_points(orbb, oracle, synth):
+    """The reference calls compute_fast_angle and calc_orb one after the other on caller-owned SoA arrays
+    (buildStream.cpp:442-460).  orbb_detect_export + orbb_compute_fast_angle + orbb_calc_orb per level must give the
+    angles and descriptor bits of the fused kernel (and so of the oracle)."""
+    import torch
+    w, h, nf = 640, 480, 1000
+    frames = np.stack([synth.textured_frame(w, h, 8100), synth.low_contrast_frame(w, h, 8101)])
+    ex = orbb.ORBextractor(nf, 1.2, 8, 20, 7, width=w, height=h, max_batch=2)
+    st = torch.cuda.current_stream()
+    d_in = torch.from_numpy(frames).cuda()
+    mk = ex.max_kp
+    ex.stage_upload(d_in, 2, stream=st)
+    ex.pyramid_create_levels(stream=st)
+    ex.detect(stream=st)
+    ex.gaussian_blur(stream=st)
+    d_kp = torch.zeros((2, mk, 7), dtype=torch.float32, device="cuda")
+    d_desc = torch.zeros((2, mk, 32), dtype=torch.uint8, device="cuda")
+    d_cnt = torch.zeros(2, dtype=torch.int32, device="cuda")
+    ex.compute_fast_angle_and_orb(d_kp, d_desc, d_cnt, stream=st)
+    # the two-call form
+    d_pos = torch.zeros((2, mk, 2), dtype=torch.float32, device="cuda")
+    d_score = torch.zeros((2, mk), dtype=torch.float32, device="cuda")
+    d_level = torch.full((2, mk), -1, dtype=torch.int32, device="cuda")
+    d_lc = torch.zeros((2, 8), dtype=torch.int32, device="cuda")
+    d_c2 = torch.zeros(2, dtype=torch.int32, device="cuda")
+    ex.detect_export(d_pos, d_score, d_level, d_lc, d_c2, stream=st)
+    torch.cuda.synchronize()
+    lc = d_lc.cpu().numpy()
+    assert np.array_equal(d_c2.cpu().numpy(), d_cnt.cpu().numpy()) and np.array_equal(lc.sum(1), d_cnt.cpu().numpy())
+    d_angle = torch.full((2, mk), -7.0, dtype=torch.float32, device="cuda")
+    d_desc2 = torch.zeros((2, mk, 32), dtype=torch.uint8, device="cuda")
+    for f in range(2):
+        off = 0
+        for l in range(8):
+            n = int(lc[f, l])
+            li = ex.level_info(l, frame=f)
+            roi = li.padded + 19 * li.pitch + 19
+            ex.compute_fast_angle(d_angle[f, off:], d_pos[f, off:], roi, li.pitch, li.width, li.height, n, stream=st)
+            ex.calc_orb(d_angle[f, off:], d_pos[f, off:], d_desc2[f, off:], li.blurred, li.pitch, li.width, li.height, n, stream=st)
+            off += n
+    torch.cuda.synchronize()
+    kp = d_kp.cpu().numpy().view(orbb.KEYPOINT_DTYPE).reshape(2, mk)
+    cnt = d_cnt.cpu().numpy()
+    for f in range(2):
+        n = int(cnt[f])
+        assert n > 500
+        assert np.array_equal(d_angle[f, :n].cpu().numpy(), kp[f, :n]["angle"])
+        assert np.array_equal(d_desc2[f, :n].cpu().numpy(), d_desc[f, :n].cpu().numpy())
+        assert np.array_equal(d_level[f, :n].cpu().numpy(), kp[f, :n]["octave"])
+        assert np.array_equal(d_score[f, :n].cpu().numpy(), kp[f, :n]["response"])
+        sc = ex.GetScaleFactors()[kp[f, :n]["octave"]]
+        pos = d_pos[f, :n].cpu().numpy()
+        lvl0 = kp[f, :n]["octave"] == 0
+        assert np.array_equal(np.where(lvl0, pos[:, 0], pos[:, 0] * sc), kp[f, :n]["x"])
+        okp, odesc = canon(*oracle.Oracle(w, h, nf).extract(frames[f]))
+        gk, gd = canon(kp[f, :n], d_desc2[f, :n].cpu().numpy())
+        assert gk.tobytes() == okp.tobytes() and np.array_equal(gd, odesc)
+    # keypoints too close to the edge: angle -1 / zero descriptor, never an out-of-bounds read
+    li = ex.level_info(0)
+    edge = torch.tensor([[3.0, 3.0], [w - 2.0, 100.0], [100.0, h - 1.0], [320.0, 240.0]], dtype=torch.float32, device="cuda")
+    a = torch.zeros(4, dtype=torch.float32, device="cuda")
+    dd = torch.full((4, 32), 9, dtype=torch.uint8, device="cuda")
+    ex.compute_fast_angle(a, edge, li.padded + 19 * li.pitch + 19, li.pitch, w, h, 4, stream=st)
+    ex.calc_orb(a, edge, dd, li.blurred, li.pitch, w, h, 4, stream=st)
+    torch.cuda.synchronize()
+    assert a[:3].cpu().tolist() == [-1.0, -1.0, -1.0] and 0.0 <= float(a[3]) < 360.0
+    assert int(dd[:3].sum()) == 0 and int(dd[3].sum()) > 0
+    ex.close()
+
+
+def test_stage_calls_are_rerunnable(orbb, synth):
+    """orbb_detect twice on the resident batch: same selection, no duplicated candidates; also
+    detect_fast twice WITHOUT a distribute in between (the cell tables are then stale and the quadtree kernel must
+    notice and take its general path)."""
+    import torch
+    w, h = 424, 240
+    frames = np.stack([synth.textured_frame(w, h, 61), synth.sparse_frame(w, h, 62)])
+    ex = orbb.ORBextractor(600, 1.2, 6, 20, 7, width=w, height=h, max_batch=2)
+    rk, rd, rc = ex.extract_batch(frames)
+    st = torch.cuda.current_stream()
+    d_in = torch.from_numpy(frames).cuda()
+    d_kp = torch.zeros((2, ex.max_kp, 7), dtype=torch.float32, device="cuda")
+    d_desc = torch.zeros((2, ex.max_kp, 32), dtype=torch.uint8, device="cuda")
+    d_cnt = torch.zeros(2, dtype=torch.int32, device="cuda")
+    ex.stage_upload(d_in, 2, stream=st)
+    ex.pyramid_create_levels(stream=st)
+    ex.detect(stream=st)
+    ex.detect(stream=st)             # second detect on the same batch
+    ncand = [len(ex.debug_candidates(l, f)) for f in range(2) for l in range(6)]
+    ex.detect_fast(stream=st)
+    ex.detect_fast(stream=st)        # stale cell tables now
+    assert ncand == [len(ex.debug_candidates(l, f)) for f in range(2) for l in range(6)]
+    ex.detect_distribute(stream=st)
+    ex.gaussian_blur(stream=st)
+    ex.gaussian_blur(stream=st)
+    ex.compute_fast_angle_and_orb(d_kp, d_desc, d_cnt, stream=st)
+    ex.compute_fast_angle_and_orb(d_kp, d_desc, d_cnt, stream=st)
+    torch.cuda.synchronize()
+    cnt = d_cnt.cpu().numpy()
+    assert np.array_equal(cnt, rc)
+    kp = d_kp.cpu().numpy().view(orbb.KEYPOINT_DTYPE).reshape(2, ex.max_kp)
+    for f in range(2):
+        n = int(cnt[f])
+        assert kp[f, :n].tobytes() == rk[f, :n].tobytes() and np.array_equal(d_desc[f, :n].cpu().numpy(), rd[f, :n])
+    # and the whole-extractor call afterwards starts from clean tables
+    k3, d3, c3 = ex.extract_batch(frames)
+    assert np.array_equal(c3, rc) and k3.tobytes() == rk.tobytes() and d3.tobytes() == rd.tobytes()
+    ex.close()
+
+
+def test_no_device_entry_point_blocks(orbb, synth):
+    """orbb200.h: "all work is enqueued on the stream given, no hidden synchronisation".  A long spin kernel is put
+    on the stream first; every device-side entry point must return while it is still running (stream.query() False
+    right after the call).  Only *_host, orbb_wait and debug_* may block."""
+    import torch
+    w, h, nb = 320, 240, 4
+    frames = np.stack([synth.textured_frame(w, h, 70 + i) for i in range(nb)])
+    ex = orbb.ORBextractor(400, 1.2, 4, 20, 7, width=w, height=h, max_batch=nb)
+    mk = ex.max_kp
+    st = torch.cuda.Stream()
+    d_in = torch.from_numpy(frames).cuda()
+    d_kp = torch.zeros((nb, mk, 7), dtype=torch.float32, device="cuda")
+    d_kp2 = torch.zeros((nb, mk, 7), dtype=torch.float32, device="cuda")
+    d_desc = torch.zeros((nb, mk, 32), dtype=torch.uint8, device="cuda")
+    d_desc2 = torch.zeros((nb, mk, 32), dtype=torch.uint8, device="cuda")
+    d_cnt = torch.zeros(nb, dtype=torch.int32, device="cuda")
+    d_valid = torch.zeros(nb, dtype=torch.int32, device="cuda")
+    d_idx = torch.zeros((nb * mk, 2), dtype=torch.int32, device="cuda")
+    d_dist = torch.zeros((nb * mk, 2), dtype=torch.int32, device="cuda")
+    d_acc = torch.zeros(nb * mk, dtype=torch.uint8, device="cuda")
+    d_nacc = torch.zeros(1, dtype=torch.int32, device="cuda")
+    d_pos = torch.zeros((nb, mk, 2), dtype=torch.float32, device="cuda")
+    d_angle = torch.zeros((nb, mk), dtype=torch.float32, device="cuda")
+    d_off = torch.tensor([0, mk, 2 * mk], dtype=torch.int32, device="cuda")
+    d_rgb = torch.zeros((nb, h, w, 3), dtype=torch.uint8, device="cuda")
+    d_gray = torch.zeros((nb, h, w), dtype=torch.uint8, device="cuda")
+    d_depth = torch.full((nb, h, w), 1500, dtype=torch.int16, device="cuda")
+    d_al = torch.zeros((nb, h, w), dtype=torch.int32, device="cuda")
+    d_pts = torch.zeros((nb, mk, 3), dtype=torch.float64, device="cuda")
+    d_ur = torch.zeros((nb // 2, mk), dtype=torch.float32, device="cuda")
+    d_dp = torch.zeros((nb // 2, mk), dtype=torch.float32, device="cuda")
+    d_ns = torch.zeros(nb // 2, dtype=torch.int32, device="cuda")
+    intr = orbb.make_intrinsics(w, h, w / 2, h / 2, 300.0, 300.0)
+    extr = orbb.make_extrinsics()
+    li = ex.level_info(0)
+    calls = [
+        ("extract_batch_device", lambda: ex.extract_batch_device(d_in, nb, d_kp, d_desc, d_cnt, stream=st)),
+        ("stage_upload", lambda: ex.stage_upload(d_in, nb, stream=st)),
+        ("pyramid_create_levels", lambda: ex.pyramid_create_levels(stream=st)),
+        ("detect", lambda: ex.detect(stream=st)),
+        ("detect_fast", lambda: ex.detect_fast(stream=st)),
+        ("detect_distribute", lambda: ex.detect_distribute(stream=st)),
+        ("gaussian_blur", lambda: ex.gaussian_blur(stream=st)),
+        ("compute_angle_and_orb", lambda: ex.compute_fast_angle_and_orb(d_kp, d_desc, d_cnt, stream=st)),
+        ("detect_export", lambda: ex.detect_export(d_pos, None, None, None, None, stream=st)),
+        ("compute_fast_angle", lambda: ex.compute_fast_angle(d_angle, d_pos, li.padded + 19 * li.pitch + 19, li.pitch, w, h, 64, stream=st)),
+        ("calc_orb", lambda: ex.calc_orb(d_angle, d_pos, d_desc2, li.blurred, li.pitch, w, h, 64, stream=st)),
+        ("match_knn", lambda: ex.match_keypoints(d_desc, nb * mk, d_desc, nb * mk, d_idx, d_dist, d_acc, d_nacc, k=2, stream=st)),
+        ("match_knn_segmented", lambda: ex.match_keypoints_segmented(d_desc, d_off, d_desc, d_off, 2, 2 * mk, mk, mk, d_idx, d_dist, d_acc, stream=st)),
+        ("match_windowed", lambda: ex.match_keypoints_windowed(d_desc, d_kp, 28, mk, d_desc, d_kp, 28, mk, 2.0, 64, d_idx, d_dist, d_nacc, stream=st)),
+        ("rgb_to_grayscale", lambda: ex.rgb_to_grayscale(d_rgb, nb, d_gray, stream=st)),
+        ("align_depth_to_other", lambda: ex.align_depth_to_other(d_depth, nb, 0.001, intr, intr, extr, d_al, stream=st)),
+        ("keypoint_pixel_to_point", lambda: ex.keypoint_pixel_to_point(d_al, intr, nb, d_kp, d_desc, d_cnt, d_kp2, d_desc2, d_pts, d_valid, stream=st)),
+        ("reproject_points", lambda: ex.reproject_points(d_pts, d_valid, nb, None, intr, d_pos, stream=st)),
+        ("match_windowed_batch", lambda: ex.match_keypoints_windowed_batch(d_desc2, d_pos, d_valid, d_desc2, d_kp2, 28, d_valid, nb, 2.0, 64, d_idx, d_dist, stream=st)),
+        ("match_projection_batch", lambda: ex.match_keypoints_projection_batch(d_desc2, d_pos, d_kp2, d_valid, d_desc2, d_kp2, d_valid, nb, 7.0, 100, True, d_idx, d_dist, d_ns, stream=st)),
+        ("compute_stereo_matches", lambda: ex.compute_stereo_matches(d_kp, d_desc, d_cnt, nb // 2, 40.0, 300.0, d_ur, d_dp, d_ns, stream=st)),
+    ]
+    for _, c in calls:   # warm up: module load, first-use attribute calls
+        c()
+    torch.cuda.synchronize()
+    spin = int(0.25 * 1.9e9)  # ~0.25 s at 1.9 GHz
+    blocked = []
+    for name, c in calls:
+        with torch.cuda.stream(st):
+            torch.cuda._sleep(spin)
+        t0 = time.perf_counter()
+        c()
+        dt = time.perf_counter() - t0
+        still_running = not st.query()
+        st.synchronize()
+        if not still_running or dt > 0.1:
+            blocked.append((name, round(dt, 4)))
+    assert not blocked, f"entry points that waited for the stream: {blocked}"
+    # the async host form may not block either (its ticket is waited for separately)
+    pin = torch.from_numpy(frames).pin_memory()
+    hk = torch.zeros(nb * mk * 28, dtype=torch.uint8).pin_memory()
+    hd = torch.zeros(nb * mk * 32, dtype=torch.uint8).pin_memory()
+    hc = torch.zeros(nb, dtype=torch.int32).pin_memory()
+    with torch.cuda.stream(st):
+        torch.cuda._sleep(spin)
+    t0 = time.perf_counter()
+    t = ex.extract_batch_host_async(pin.data_ptr(), w, w * h, nb, hk.data_ptr(), hd.data_ptr(), hc.data_ptr(), stream=st)
+    assert time.perf_counter() - t0 < 0.1 and not st.query()
+    ex.wait(t)
+    assert int(hc.sum()) > 0
+    ex.close()
+
+
+def test_matcher_scratch_is_fixed_and_chunks(orbb, oracle):
+    """The split-T scratch is allocated in orbb_create; a query set larger than it holds goes through in chunks and
+    the per-chunk accept counts accumulate.  300 k queries against 700 train rows, checked against the oracle."""
+    import torch
+    rng = np.random.default_rng(17)
+    ex = orbb.ORBextractor(300, 1.2, 2, 20, 7, width=200, height=150, max_batch=1)
+    nq, nt = 300_000, 700
+    t = rng.integers(0, 256, size=(nt, 32), dtype=np.uint8)
+    q = t[rng.integers(0, nt, size=nq)].copy()
+    q[:, :4] ^= rng.integers(0, 256, size=(nq, 4), dtype=np.uint8) & rng.integers(0, 256, size=(nq, 4), dtype=np.uint8)
+    free0 = torch.cuda.mem_get_info()[0]
+    for k in (1, 2):
+        idx, dist, acc, nacc = orbb.match_knn_host(ex, q, t, k=k, ratio=0.7)
+        oidx, odist, oacc = oracle.match_knn(q, t, k=k, ratio=0.7, threads=os.cpu_count() or 4)
+        if k == 1:
+            oidx[:, 1] = -1; odist[:, 1] = -1
+        assert np.array_equal(idx, oidx) and np.array_equal(dist, odist)
+        assert np.array_equal(acc, oacc) and nacc == int(oacc.sum())
+    dq = torch.from_numpy(q).cuda(); dt = torch.from_numpy(t).cuda()
+    idx = torch.zeros((nq, 2), dtype=torch.int32, device="cuda"); dist = torch.zeros_like(idx)
+    free1 = torch.cuda.mem_get_info()[0]
+    ex.match_keypoints(dq, nq, dt, nt, idx, dist, k=1)
+    torch.cuda.synchronize()
+    assert torch.cuda.mem_get_info()[0] == free1  # nothing was allocated by the call
+    del free0
+    ex.close()
+
+
+def test_create_and_stride_validation(orbb):
+    with pytest.raises(orbb.OrbbError):
+        orbb.ORBextractor(100, 1.2, 2, 20, 7, width=200, height=150, max_batch=70000)  # frame index is a grid dimension
+    import torch
+    ex = orbb.ORBextractor(100, 1.2, 2, 20, 7, width=200, height=150, max_batch=2)
+    d_in = torch.zeros((2, 150, 200), dtype=torch.uint8, device="cuda")
+    d_kp = torch.zeros((2, ex.max_kp, 7), dtype=torch.float32, device="cuda")
+    d_desc = torch.zeros((2, ex.max_kp, 32), dtype=torch.uint8, device="cuda")
+    d_cnt = torch.zeros(2, dtype=torch.int32, device="cuda")
+    with pytest.raises(orbb.OrbbError):
+        ex.extract_batch_device(d_in, 2, d_kp, d_desc, d_cnt, stride=200 * 100)  # frames would overlap
+    with pytest.raises(orbb.OrbbError):
+        ex.stage_upload(d_in, 2, stride=100)
+    ex.extract_batch_device(d_in, 1, d_kp, d_desc, d_cnt, stride=0)  # a single frame ignores the stride
+    torch.cuda.synchronize()
+    ex.close()

@@ -268,7 +268,7 @@ def test_matcher_segmented(orbb, oracle):
     idx = torch.zeros((len(q), 2), dtype=torch.int32, device="cuda")
     dist = torch.zeros((len(q), 2), dtype=torch.int32, device="cuda")
     acc = torch.zeros(len(q), dtype=torch.uint8, device="cuda")
-    ex.match_keypoints_segmented(dq, dqo, dt, dto, 4, max(nqs), idx, dist, acc, k=2, ratio=0.8,
+    ex.match_keypoints_segmented(dq, dqo, dt, dto, 4, sum(nqs), max(nqs), max(nts), idx, dist, acc, k=2, ratio=0.8,
                                  stream=torch.cuda.current_stream())
     torch.cuda.synchronize()
     idx, dist, acc = idx.cpu().numpy(), dist.cpu().numpy(), acc.cpu().numpy().astype(bool)
@@ -364,8 +364,9 @@ def test_cfg3_stereo_and_temporal_matching(orbb, oracle, synth):
     idx = torch.zeros((len(q), 2), dtype=torch.int32, device="cuda")
     dist = torch.zeros((len(q), 2), dtype=torch.int32, device="cuda")
     acc = torch.zeros(len(q), dtype=torch.uint8, device="cuda")
-    ex.match_keypoints_segmented(dq, torch.from_numpy(qo).cuda(), dt, torch.from_numpy(to).cuda(), 2, len(odesc[0]),
-                                 idx, dist, acc, k=2, ratio=0.7, stream=torch.cuda.current_stream())
+    ex.match_keypoints_segmented(dq, torch.from_numpy(qo).cuda(), dt, torch.from_numpy(to).cuda(), 2, len(q), len(odesc[0]),
+                                 max(len(odesc[1]), len(odesc[2])), idx, dist, acc, k=2, ratio=0.7,
+                                 stream=torch.cuda.current_stream())
     torch.cuda.synchronize()
     idx, dist, acc = idx.cpu().numpy(), dist.cpu().numpy(), acc.cpu().numpy().astype(bool)
     for s_ in range(2):

@@ -55,6 +55,9 @@ def test_kernels_carry_their_instructions(sass):
     kernels, _ = sass
     match1 = _kernel(kernels, "k_matchILi1E")
     assert _count(match1, "POPC") >= 5 and _count(match1, "LOP3") >= 14  # carry-save popcount: 5 POPC per pair
+    for kk in ("k_matchILi1E", "k_matchILi2E"):  # query descriptors and running bests stay in registers
+        ops = _kernel(kernels, kk)
+        assert _count(ops, "LDL") == 0 and _count(ops, "STL") == 0, kk
     fast = _kernel(kernels, "k_fast_cellsILb0ELb0E")
     assert _count(fast, "VABSDIFF4") >= 4 and _count(fast, "VIMNMX3") >= 40  # packed precheck, arc-score min/max network
     assert _count(fast, "ATOMG") + _count(fast, "RED") >= 1                  # cell-table atomics while emitting
