@@ -15,10 +15,17 @@ the data path; NCCL only gathers the per-rank keypoint counts after the timed re
   cpu_baseline : the CPU oracle (a port of upstream ORBextractor; the reference repo has no compilable CPU
                  extractor) on the box's host cores, bounded sample
   matcher      : Hamming 1-NN of one batch's descriptors against a 50k-descriptor map, Gpairs/s vs POPC roof
+                 (the POPC issue rate is measured by a register-only microbenchmark, orbb_debug_popc_rate)
+  parity       : K frames of the TIMED batch (both stream parts) compared with the CPU oracle after the timed region
+  sustained    : the same device-resident call repeated for >= 2 s with NVML clock / power samples
+  cfg5         : BASELINE config 5 as written -- a 1024-frame batch sharded 1024/N per rank (STRONG scaling), one map
+                 built on rank 0 and broadcast (NCCL), extraction -> 1-NN vs the 50 k map -> one fixed-stride
+                 all_gather timed as one pipeline; sha256 of rank 0's gathered records (must not depend on N)
 """
 from __future__ import annotations
 
 import argparse
+import hashlib
 import importlib
 import json
 import os
@@ -36,6 +43,7 @@ W, H, NFEAT, NLEVELS, SCALE, INI_TH, MIN_TH = 640, 480, 1000, 8, 1.2, 20, 7
 FRAMES_PER_GPU = 256
 N_INPUT_SETS = 2          # rotate over 2 resident batches: 2 x 78.6 MB of inputs > 126 MB L2
 MAP_SIZE = 50_000
+CFG5_FRAMES = 1024        # BASELINE config 5: one 1024-frame batch sharded across the ranks
 LEVEL_PIXELS = 950_532    # sum_l w_l*h_l for 640x480, 8 levels, 1.2
 BYTES_PER_FRAME = W * H + 2 * LEVEL_PIXELS + 60 * NFEAT  # 2,268,264 B
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE k_fast_cells launch, per frame, from the committed
@@ -46,6 +54,7 @@ FAST_DRAM_TRAFFIC_PER_FRAME = (146.8e6 + 17.25e6) / 128
 # level0 0.289 G + resize x7 2.337 G + FAST 8.777 G + quadtree 1.162 G + blur 2.473 G + angle/rBRIEF 2.425 G per 128
 # frames) -- the path is issue bound, so the step is also reported against the SM issue roofline
 THREAD_INST_PER_FRAME = (0.2891e9 + 2.3371e9 + 8.777e9 + 1.162e9 + 2.473e9 + 2.425e9) / 128
+PROFILE_SOURCE = "profiles/r01m_all_kernels_full.txt"
 
 
 def measured_peaks():
@@ -59,22 +68,16 @@ def measured_peaks():
 def make_frames(n: int, seed0: int) -> np.ndarray:
     """n distinct 640x480 textured frames: 16 seeded base frames, then cyclic shifts of them (cheap, distinct)."""
     synth = importlib.import_module(PKG + ".synth")
-    base = [synth.textured_frame(W, H, seed0 + i) for i in range(min(n, 16))]
-    out = np.empty((n, H, W), np.uint8)
-    for i in range(n):
-        b = base[i % len(base)]
-        k = i // len(base)
-        out[i] = np.roll(b, (37 * k, 53 * k), axis=(0, 1)) if k else b
-    return out
+    return synth.rolled_batch(W, H, n, seed0)
 
 
 class ClockSampler(threading.Thread):
     """SM clock / throttle reasons sampled DURING the timed region (NVML; nvidia-smi as fallback)."""
 
-    def __init__(self, index: int):
+    def __init__(self, index: int, period_s: float = 0.004):
         super().__init__(daemon=True)
         self.index, self.stop_flag, self.samples, self.reasons = index, False, [], set()
-        self.sm_max = None
+        self.sm_max, self.period_s, self.power_w = None, period_s, []
         try:
             import pynvml
             pynvml.nvmlInit()
@@ -93,13 +96,17 @@ class ClockSampler(threading.Thread):
         while not self.stop_flag:
             try:
                 self.samples.append(nv.nvmlDeviceGetClockInfo(self.dev, nv.NVML_CLOCK_SM))
+                try:
+                    self.power_w.append(nv.nvmlDeviceGetPowerUsage(self.dev) / 1000.0)
+                except Exception:
+                    pass
                 r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.dev)
                 for bit, nm in names.items():
                     if r & bit:
                         self.reasons.add(nm)
             except Exception:
                 pass
-            time.sleep(0.02)
+            time.sleep(self.period_s)
 
     def result(self):
         if not self.samples:
@@ -107,8 +114,8 @@ class ClockSampler(threading.Thread):
         return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.sm_max, "reasons": sorted(self.reasons)}
 
 
-def cpu_oracle_fps(frames: np.ndarray, threads: int, budget_s: float = 12.0):
-    """Time the CPU oracle (checker code; here only as the reported CPU baseline) on a bounded sample."""
+def _oracle_module():
+    """The CPU oracle (checker code; bench.py may execute it only for the cpu_baseline / --impl reference / parity legs)."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import oracle as O
     native = False
@@ -117,6 +124,12 @@ def cpu_oracle_fps(frames: np.ndarray, threads: int, budget_s: float = 12.0):
         native = True
     except Exception:
         O.build()
+    return O, native
+
+
+def cpu_oracle_fps(frames: np.ndarray, threads: int, budget_s: float = 10.0):
+    """Time the CPU oracle on a bounded sample: frames/s on `threads` threads."""
+    O, native = _oracle_module()
     n0 = max(threads, 4)
     t = time.perf_counter()
     O.extract_many(frames[:n0], NFEAT, SCALE, NLEVELS, INI_TH, MIN_TH, threads=threads, native=native)
@@ -129,37 +142,73 @@ def cpu_oracle_fps(frames: np.ndarray, threads: int, budget_s: float = 12.0):
     return n / dt, n, native
 
 
+def cpu_matcher_gpairs(threads: int, budget_s: float = 3.0):
+    """Brute-force popcount 1-NN on the host cores (orbo_match_many, __builtin_popcountll), Gpairs/s: BASELINE.md 4.4."""
+    O, native = _oracle_module()
+    rng = np.random.default_rng(7)
+    t = rng.integers(0, 256, size=(MAP_SIZE, 32), dtype=np.uint8)
+    nq = 64 * threads
+    q = rng.integers(0, 256, size=(nq, 32), dtype=np.uint8)
+    t0 = time.perf_counter()
+    O.match_knn(q, t, k=1, threads=threads, native=native)
+    dt = time.perf_counter() - t0
+    nq2 = int(max(nq, min(200_000, nq * budget_s / max(dt, 1e-4)))) // threads * threads
+    q = rng.integers(0, 256, size=(nq2, 32), dtype=np.uint8)
+    t0 = time.perf_counter()
+    O.match_knn(q, t, k=1, threads=threads, native=native)
+    dt = time.perf_counter() - t0
+    return nq2 * MAP_SIZE / dt / 1e9, nq2
+
+
+def cpu_baseline_block(frames: np.ndarray, cores: int):
+    """All-core and 1-core rows of BASELINE.md section 4.3a / 4.4 (bounded samples, about 20 s of CPU work in total)."""
+    fps_all, n_all, native = cpu_oracle_fps(frames, cores, 9.0)
+    fps_1, n_1, _ = cpu_oracle_fps(frames, 1, 3.0)
+    mg_all, nq_all = cpu_matcher_gpairs(cores, 3.0)
+    mg_1, nq_1 = cpu_matcher_gpairs(1, 1.5)
+    return {"value": fps_all, "unit": "frames/s", "cores": cores, "kind": "port",
+            "sample": f"{n_all} of the step's 640x480 frames on {cores} threads; {n_1} frames on 1 thread; matcher "
+                      f"{nq_all} (all cores) / {nq_1} (1 core) queries x {MAP_SIZE} map rows; oracle "
+                      f"{'-march=native' if native else 'x86-64-v2'}",
+            "one_core_value": fps_1, "matcher_gpairs": mg_all, "matcher_gpairs_one_core": mg_1,
+            "matcher_what": "brute-force 256-bit Hamming 1-NN, __builtin_popcountll, orbo_match_many"}
+
+
 def run_reference(args):
     """--impl reference: the reference path's CPU implementation on the host cores.  The reference repo's own
-    CPU extractor (src_trash1/orb_extractor.cpp) is a stub, so this is the oracle port of upstream ORBextractor."""
+    CPU extractor (src_trash1/orb_extractor.cpp) is a stub, so this is the oracle port of upstream ORBextractor.
+    Same config as the product arm: every step is one 256-frame batch of the same workload."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    sys.path.insert(0, os.path.join(ROOT, "oracle"))
-    import oracle as O
-    native = False
-    try:
-        O.build(native=True)
-        native = True
-    except Exception:
-        O.build()
-    per_step = max(4 * cores, 16)
-    frames = make_frames(per_step, 5000)
-    for _ in range(args.warmup):
-        O.extract_many(frames, NFEAT, SCALE, NLEVELS, INI_TH, MIN_TH, threads=cores, native=native)
-    t = time.perf_counter()
+    O, native = _oracle_module()
+    per_step = args.frames
+    frames = make_frames(per_step, 1000)
+    for _ in range(min(args.warmup, 2)):
+        O.extract_many(frames[: 4 * cores], NFEAT, SCALE, NLEVELS, INI_TH, MIN_TH, threads=cores, native=native)
+    step_s = []
     for _ in range(args.steps):
+        t = time.perf_counter()
         O.extract_many(frames, NFEAT, SCALE, NLEVELS, INI_TH, MIN_TH, threads=cores, native=native)
-    dt = time.perf_counter() - t
+        step_s.append(time.perf_counter() - t)
+    dt = float(np.sum(step_s))
     fps = per_step * args.steps / dt
-    sample = f"{per_step} frames/step x {args.steps} steps of the same 640x480 textured workload, {cores} threads"
+    sample = (f"{per_step} frames/step x {args.steps} steps of the same 640x480 textured workload, {cores} threads "
+              f"(warm-up: {min(args.warmup, 2)} x {4 * cores} frames)")
+    fps_1, n_1, _ = cpu_oracle_fps(frames, 1, 3.0)
+    mg_all, nq_all = cpu_matcher_gpairs(cores, 3.0)
+    mg_1, _ = cpu_matcher_gpairs(1, 1.5)
     line = {
         "impl": "reference", "metric": "ORB frames/s (640x480, 1000 kp)", "value": fps, "unit": "frames/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
         "config": workload_config(per_step),
-        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port", "sample": sample},
+        "value_stats": {"median": per_step / float(np.median(step_s)), "best": per_step / float(np.min(step_s))},
+        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port", "sample": sample,
+                         "one_core_value": fps_1, "matcher_gpairs": mg_all, "matcher_gpairs_one_core": mg_1,
+                         "matcher_what": f"brute-force 256-bit Hamming 1-NN, {nq_all} queries x {MAP_SIZE} map rows, "
+                                         "__builtin_popcountll"},
         "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -323,6 +372,213 @@ def bench_reference_gpu_kernels(orbb, torch, device_index):
             "ours_orbslam2_8_levels_1200_kp_batch_64": ours(1200, NLEVELS, 64, 20)}
 
 
+def parity_block(orbb, frames, sample, kp, desc, cnt):
+    """The measured batch itself against the CPU oracle (north_star: bit-exact, except keypoints whose IC_Angle lands
+    on a pattern-rotation rounding boundary: angle within 1e-3 rad and descriptor within 8 bits are 'tolerated' and
+    their fraction is reported).  `sample` = frame indices of the timed batch, taken from both stream parts."""
+    O, _ = _oracle_module()
+    o = O.Oracle(W, H, NFEAT, SCALE, NLEVELS, INI_TH, MIN_TH)
+    n_exact = n_tol = n_fail = n_kp = 0
+    frames_exact = 0
+    for f in sample:
+        okp, odesc = o.extract(frames[f])
+        gkp, gdesc = kp[f, :cnt[f]], desc[f, :cnt[f]]
+        oo = np.lexsort((okp["x"], okp["y"], okp["octave"]))
+        go = np.lexsort((gkp["x"], gkp["y"], gkp["octave"]))
+        okp, odesc, gkp, gdesc = okp[oo], odesc[oo], gkp[go], gdesc[go]
+        n_kp += len(okp)
+        if len(okp) == len(gkp) and okp.tobytes() == gkp.tobytes() and np.array_equal(odesc, gdesc):
+            n_exact += len(okp)
+            frames_exact += 1
+            continue
+        gmap = {(int(k["octave"]), float(k["x"]), float(k["y"])): i for i, k in enumerate(gkp)}
+        for i, k in enumerate(okp):
+            j = gmap.get((int(k["octave"]), float(k["x"]), float(k["y"])))
+            if j is None or gkp[j]["response"] != k["response"] or gkp[j]["size"] != k["size"]:
+                n_fail += 1
+                continue
+            bits = int(np.unpackbits(odesc[i] ^ gdesc[j]).sum())
+            dang = abs(float(gkp[j]["angle"]) - float(k["angle"]))
+            dang = min(dang, 360.0 - dang) * np.pi / 180.0
+            if bits == 0 and dang == 0.0:
+                n_exact += 1
+            elif bits <= 8 and dang <= 1e-3:
+                n_tol += 1
+            else:
+                n_fail += 1
+        n_fail += max(0, len(gkp) - len(okp))
+    return {"frames": len(sample), "frame_indices": [int(f) for f in sample], "frames_bit_exact": frames_exact,
+            "keypoints": n_kp, "exact": n_exact, "tolerated": n_tol, "failed": n_fail,
+            "tolerated_fraction": n_tol / max(n_kp, 1),
+            "what": "keypoint fields (x, y, size, angle, response, octave) and 256 descriptor bits of sampled frames of the "
+                    "timed batch vs the CPU oracle"}
+
+
+def sustained_leg(ex, torch, d_sets, B, d_kp, d_desc, d_cnt, st, device_index, seconds):
+    """The device-resident call repeated back to back for >= `seconds` s, with NVML SM clock and power sampled
+    throughout: the rate the path holds once the burst clocks are gone."""
+    sampler = ClockSampler(device_index, period_s=0.02)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    sampler.start()
+    t0 = time.perf_counter()
+    e0.record(st)
+    n = 0
+    while True:
+        for _ in range(50):
+            ex.extract_batch_device(d_sets[n % N_INPUT_SETS], B, d_kp, d_desc, d_cnt, stream=st)
+            n += 1
+        torch.cuda.synchronize()  # bounds the queue depth; 50 steps ~ 70 ms between syncs
+        if time.perf_counter() - t0 >= seconds:
+            break
+    e1.record(st)
+    torch.cuda.synchronize()
+    sampler.stop_flag = True
+    sampler.join()
+    ms = e0.elapsed_time(e1)
+    c = sampler.result()
+    pw = sampler.power_w
+    return {"seconds": ms * 1e-3, "steps": n, "value": n * B / (ms * 1e-3), "unit": "frames/s", "ms_per_step": ms / n,
+            "sm_mhz_median": c["sm_mhz"], "sm_mhz_min": float(np.min(sampler.samples)) if sampler.samples else None,
+            "power_w_median": float(np.median(pw)) if pw else None, "power_w_max": float(np.max(pw)) if pw else None,
+            "reasons": c["reasons"], "clock_samples": len(sampler.samples)}
+
+
+def bench_cfg5(orbb, torch, dist, rank, world, local_rank, reps, warmup):
+    """BASELINE config 5 as written: ONE 1024-frame batch sharded across the ranks (strong scaling), extraction +
+    1-NN Hamming match against ONE 50 k-descriptor map (built on rank 0, broadcast over NCCL) + gather of counts and
+    match results to rank 0, timed as one pipeline.  Returns the block for the JSON line (rank 0) or None."""
+    sharding = importlib.import_module(PKG + ".sharding")
+    synth = importlib.import_module(PKG + ".synth")
+    dev = torch.device("cuda", local_rank)
+    st = torch.cuda.current_stream()
+    lo, hi = sharding.shard_range(CFG5_FRAMES, rank, world)
+    n_pad = (CFG5_FRAMES + world - 1) // world          # every rank gathers the same number of frame rows
+    n_loc = hi - lo
+    ex = orbb.ORBextractor(NFEAT, SCALE, NLEVELS, INI_TH, MIN_TH, width=W, height=H, max_batch=n_pad, device=local_rank)
+    mk = ex.max_kp
+    frames = synth.rolled_frames(W, H, range(lo, hi), 777_000)
+    pin_frames = torch.from_numpy(frames).pin_memory()
+    d_frames = torch.empty((n_pad, H, W), dtype=torch.uint8, device=dev)
+    d_frames[:n_loc].copy_(pin_frames)
+    lay = sharding.GatherLayout(n_pad, mk)
+    gbuf = torch.zeros(lay.total, dtype=torch.int32, device=dev)
+    d_cnt, d_idx, d_dist = lay.views(gbuf)
+    gout = torch.empty(world * lay.total, dtype=torch.int32, device=dev)
+    d_kp = torch.zeros(n_pad * mk * 28, dtype=torch.uint8, device=dev)
+    d_desc = torch.zeros(n_pad * mk * 32, dtype=torch.uint8, device=dev)
+    pin_gout = torch.empty(world * lay.total, dtype=torch.int32).pin_memory() if rank == 0 else None
+
+    # ---- the map: descriptors of the batch's first 50 frames (they live on rank 0 for every N <= 8), tiled to 50 000
+    # rows, 5 % of the bits flipped with a fixed seed; then ONE broadcast
+    d_map = torch.empty((MAP_SIZE, 32), dtype=torch.uint8, device=dev)
+    if rank == 0:
+        ex.extract_batch_device(d_frames, min(50, n_loc), d_kp, d_desc, d_cnt, stream=st)
+        torch.cuda.synchronize()
+        c = d_cnt[:50].cpu().numpy()
+        dv = d_desc.view(n_pad, mk, 32)
+        rows = np.concatenate([dv[f, :c[f]].cpu().numpy() for f in range(min(50, n_loc))])
+        rows = np.tile(rows, ((MAP_SIZE + len(rows) - 1) // len(rows), 1))[:MAP_SIZE]
+        flips = np.random.default_rng(50_000).random((MAP_SIZE, 256)) < 0.05
+        rows = rows ^ np.packbits(flips, axis=1, bitorder="little")
+        d_map.copy_(torch.from_numpy(np.ascontiguousarray(rows)))
+    b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    b0.record(st)
+    sharding.broadcast_map(d_map, src=0)
+    b1.record(st)
+    torch.cuda.synchronize()
+    bcast_ms = b0.elapsed_time(b1)
+
+    def pipeline(ev=None, from_host=False):
+        if ev is not None:
+            ev[0].record(st)
+        if from_host:  # e2e form: this rank's shard comes from pinned host memory
+            d_frames[:n_loc].copy_(pin_frames, non_blocking=True)
+        ex.extract_batch_device(d_frames, n_loc, d_kp, d_desc, d_cnt, stream=st)
+        if ev is not None:
+            ev[1].record(st)
+        ex.match_keypoints_batch(d_desc, d_cnt, n_loc, d_map, MAP_SIZE, d_idx, d_dist, k=1, stream=st)
+        if ev is not None:
+            ev[2].record(st)
+        sharding.gather_fixed(gbuf, out=gout)
+        if ev is not None:
+            ev[3].record(st)
+        if from_host and rank == 0:
+            pin_gout.copy_(gout, non_blocking=True)
+        if ev is not None:
+            ev[4].record(st)
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def timed(n, from_host):
+        rows = []
+        for _ in range(n):
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
+            sync_all()
+            pipeline(ev, from_host)
+            torch.cuda.synchronize()
+            rows.append([ev[i].elapsed_time(ev[i + 1]) for i in range(4)] + [ev[0].elapsed_time(ev[4])])
+        t = torch.tensor(rows, dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)  # per repeat and phase: the slowest rank
+        return t.cpu().numpy()
+
+    for _ in range(max(warmup, 3)):
+        pipeline()
+    sync_all()
+    l0 = ex.launch_count()
+    dev_rows = timed(max(reps, 10), False)
+    launches = (ex.launch_count() - l0) // max(reps, 10)
+    e2e_rows = timed(max(reps // 2, 5), True)
+
+    # ---- result identity across N: sha256 of the gathered match records and of every frame's keypoints + descriptors
+    torch.cuda.synchronize()
+    cnt_h = d_cnt[:n_loc].cpu().numpy()
+    kp_h = d_kp.cpu().numpy().reshape(n_pad, mk, 28)
+    desc_h = d_desc.cpu().numpy().reshape(n_pad, mk, 32)
+    digests = np.zeros((n_pad, 32), np.uint8)
+    for f in range(n_loc):
+        c = int(cnt_h[f])
+        digests[f] = np.frombuffer(hashlib.sha256(kp_h[f, :c].tobytes() + desc_h[f, :c].tobytes()).digest(), np.uint8)
+    d_dig = torch.from_numpy(digests).to(dev)
+    all_dig = sharding.gather_fixed(d_dig.view(-1)).cpu().numpy().reshape(-1, 32)
+    out = None
+    if rank == 0:
+        rec = lay.records(gout.cpu().numpy(), CFG5_FRAMES)
+        med = np.median(dev_rows, axis=0)
+        total_med, total_best = float(med[4]), float(dev_rows[:, 4].min())
+        e2e_med = float(np.median(e2e_rows[:, 4]))
+        pairs = float(rec.shape[0]) * MAP_SIZE
+        out = {"what": "BASELINE config 5: ONE 1024-frame batch sharded across the ranks, extraction + 1-NN Hamming match "
+                       "against one 50k-descriptor map (rank 0 builds it, NCCL broadcast) + one fixed-stride all_gather of "
+                       "counts and (train index, distance) rows, timed as one pipeline, max over ranks per repeat",
+               "scaling": "strong", "frames_total": CFG5_FRAMES, "frames_per_gpu": n_loc, "map_size": MAP_SIZE,
+               "repeats": int(dev_rows.shape[0]),
+               "ms": {"extract": float(med[0]), "match": float(med[1]), "gather": float(med[2]), "total": total_med,
+                      "total_best": total_best},
+               "frames_per_s": CFG5_FRAMES / (total_med * 1e-3), "frames_per_s_best": CFG5_FRAMES / (total_best * 1e-3),
+               "match_gpairs_per_s": pairs / (float(med[1]) * 1e-3) / 1e9,
+               "gather": {"ms": float(med[2]), "ms_best": float(dev_rows[:, 2].min()), "bytes_per_rank": lay.total * 4,
+                          "collective": "one all_gather_into_tensor (counts ride in the same buffer)"},
+               "map_broadcast_ms": bcast_ms,
+               "e2e": {"ms_total": e2e_med, "frames_per_s": CFG5_FRAMES / (e2e_med * 1e-3),
+                       "what": "same pipeline with each rank's shard copied from pinned host memory first and the gathered "
+                               "buffer copied to rank 0's host memory last",
+                       "h2d_bytes_per_rank": n_loc * W * H, "d2h_bytes_rank0": world * lay.total * 4},
+               "gpu_launches_per_pipeline": int(launches),
+               "records": int(rec.shape[0]),
+               "records_sha256": hashlib.sha256(rec.tobytes()).hexdigest(),
+               "keypoints_descriptors_sha256": hashlib.sha256(all_dig[:CFG5_FRAMES].tobytes()).hexdigest(),
+               "l2_policy": "every repeat rewrites the shard's whole pyramid / scratch working set (>= 0.9 GB per 128 frames), "
+                            "which evicts the inputs from the 126 MB L2 between repeats"}
+    ex.close()
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -333,6 +589,9 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-rgbd", action="store_true", help="skip the RGB-D frame-stage leg (cfg 2 geometry)")
     ap.add_argument("--no-refgpu", action="store_true", help="skip the leg that times the reference's own kernels")
+    ap.add_argument("--no-cfg5", action="store_true", help="skip the BASELINE config 5 pipeline (1024-frame batch, strong scaling)")
+    ap.add_argument("--no-parity", action="store_true", help="skip the oracle check of the timed batch")
+    ap.add_argument("--sustain-s", type=float, default=2.5, help="length of the sustained device-resident leg (0 = skip)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -401,18 +660,24 @@ def main():
     sync_all()
     sampler = ClockSampler(local_rank)
     sampler.start()
-    v0, v1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    step_ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
     launches0 = ex.launch_count()
-    v0.record(st)
     for i in range(args.steps):
+        step_ev[i].record(st)      # step_ev[0] .. step_ev[K] bracket exactly K steps; the inner ones give median / best
         dev_step(i)
-    v1.record(st)
+    step_ev[args.steps].record(st)
     gpu_launches = ex.launch_count() - launches0
     sync_all()
     sampler.stop_flag = True
     sampler.join()
-    total_ms = v0.elapsed_time(v1)
+    total_ms = step_ev[0].elapsed_time(step_ev[args.steps])
+    per_step_ms = [step_ev[i].elapsed_time(step_ev[i + 1]) for i in range(args.steps)]
     counts = d_cnt.cpu().numpy()
+    # outputs of the LAST timed step, kept for the parity block (later legs overwrite the device arrays)
+    last_set = (args.steps - 1) % N_INPUT_SETS
+    timed_kp = d_kp.cpu().numpy().view(orbb.KEYPOINT_DTYPE).reshape(B, ex.max_kp).copy()
+    timed_desc = d_desc.cpu().numpy().reshape(B, ex.max_kp, 32).copy()
+
     # per-stage breakdown (stage interface, one stream, events between stages) -- explains `value`, and gives the
     # live duration of the dominant kernel for the roofline entry
     evs = [[torch.cuda.Event(enable_timing=True) for _ in range(len(stage_names) + 1)] for _ in range(args.steps)]
@@ -469,25 +734,47 @@ def main():
     sync_all()
     h2d = B * W * H
     d2h = B * ex.max_kp * 60 + 4 * B
-    # PCIe H2D rate of this box for the same pinned buffer (explains the e2e ceiling)
+    # the e2e call's last result (host buffers) must be the device path's bytes for the same input set
+    k_e, d_e, c_e = pin_out[(args.steps - 1) % 2]
+    e2e_equal = bool(np.array_equal(c_e.numpy(), counts))
+    if e2e_equal:
+        ke = np.frombuffer(k_e.numpy().tobytes(), orbb.KEYPOINT_DTYPE).reshape(B, ex.max_kp)
+        de = d_e.numpy().reshape(B, ex.max_kp, 32)
+        for f in range(B):
+            n = int(counts[f])
+            if ke[f, :n].tobytes() != timed_kp[f, :n].tobytes() or de[f, :n].tobytes() != timed_desc[f, :n].tobytes():
+                e2e_equal = False
+                break
+    # PCIe H2D rate of this box for the same pinned buffer: this rank alone is not measurable under torchrun (all ranks
+    # run this line together), so the figure below IS the concurrent one -- barrier-aligned, every rank copying at once
     p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     d_sets[0].copy_(pin_frames[0], non_blocking=True)
-    torch.cuda.synchronize()
+    sync_all()
     p0.record(st)
-    for _ in range(3):
+    for _ in range(5):
         d_sets[0].copy_(pin_frames[0], non_blocking=True)
     p1.record(st)
     torch.cuda.synchronize()
-    h2d_gbs = 3 * h2d / (p0.elapsed_time(p1) * 1e-3) / 1e9
+    h2d_gbs = 5 * h2d / (p0.elapsed_time(p1) * 1e-3) / 1e9
+    sync_all()
 
-    # ---- matcher: this rank's batch descriptors (1-NN) against a 50k map (cfg 5)
-    nq = int(counts.sum())
+    # ---- sustained leg: >= args.sustain_s seconds of the device-resident call, NVML clock / power sampled throughout
+    sustained = None
+    if args.sustain_s > 0:
+        sustained = sustained_leg(ex, torch, d_sets, B, d_kp, d_desc, d_cnt, st, local_rank, args.sustain_s)
+        sync_all()
+
+    # ---- matcher: this rank's batch descriptors (1-NN) against a 50k map (cfg 5 geometry, weak scaling here)
+    dev_step(0)
+    torch.cuda.synchronize()
+    counts_m = d_cnt.cpu().numpy()
+    nq = int(counts_m.sum())
     d_q = torch.empty((nq, 32), dtype=torch.uint8, device=dev)
     off = 0
     desc_view = d_desc.view(B, ex.max_kp, 32)
     for f in range(B):
-        d_q[off:off + counts[f]] = desc_view[f, :counts[f]]
-        off += int(counts[f])
+        d_q[off:off + counts_m[f]] = desc_view[f, :counts_m[f]]
+        off += int(counts_m[f])
     gen = torch.Generator(device=dev).manual_seed(1234)
     reps = (MAP_SIZE + nq - 1) // max(nq, 1)
     d_map = d_q.repeat(reps, 1)[:MAP_SIZE].clone()
@@ -507,6 +794,7 @@ def main():
     torch.cuda.synchronize()
     match_ms = m0.elapsed_time(m1) / m_iters
     gpairs = nq * MAP_SIZE / (match_ms * 1e-3) / 1e9
+    popc_rate = ex.debug_popc_rate() if rank == 0 else None
 
     # ---- RGB-D frame stage (BASELINE cfg 2 geometry: 848x480, 1200 kp, batches of 64 frames):
     # pinned gray + depth in, align + extract + depth gate + reproject + windowed match + compaction, results D2H.
@@ -518,21 +806,25 @@ def main():
     if rank == 0 and world == 1 and not args.no_refgpu:
         refgpu = bench_reference_gpu_kernels(orbb, torch, local_rank)
 
-    # ---- the only collectives (after the timed region): gather per-frame counts and match records to rank 0
-    sharding = importlib.import_module(PKG + ".sharding")
-    g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    g0.record(st)
-    all_counts = sharding.gather_counts(d_cnt, B * world)
-    records = torch.stack([torch.arange(nq, dtype=torch.int32, device=dev), m_idx[:, 0], m_dist[:, 0]], 1)
-    gathered, _ = sharding.gather_ragged_to_rank0(records)
-    g1.record(st)
-    torch.cuda.synchronize()
-    gather_ms = g0.elapsed_time(g1)
-    t = torch.tensor([total_ms, e2e_ms, match_ms, gather_ms, e2e_sync_ms], dtype=torch.float64, device=dev)
+    t = torch.tensor([total_ms, e2e_ms, match_ms, e2e_sync_ms, 1.0 / h2d_gbs] + per_step_ms, dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    total_ms, e2e_ms, match_ms_max, gather_ms, e2e_sync_ms = [float(v) for v in t.tolist()]
-    kp_total = all_counts.sum().to(torch.float64).reshape(1)
+    tl = [float(v) for v in t.tolist()]
+    total_ms, e2e_ms, match_ms_max, e2e_sync_ms, inv_h2d = tl[:5]
+    per_step_ms = tl[5:]
+    h2d_slowest = 1.0 / inv_h2d
+    agg = torch.tensor([h2d_gbs, float(counts.sum())], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(agg, op=dist.ReduceOp.SUM)
+    h2d_aggregate, kp_total = float(agg[0]), float(agg[1])
+    ex.close()
+    del d_sets, d_kp, d_desc, d_q, d_map
+    torch.cuda.empty_cache()
+
+    # ---- BASELINE config 5 as written (strong scaling; the only legs with collectives)
+    cfg5 = None
+    if not args.no_cfg5:
+        cfg5 = bench_cfg5(orbb, torch, dist, rank, world, local_rank, max(args.steps // 2, 10), min(args.warmup, 3))
 
     if rank == 0:
         hbm_peak, peak_kind, sm_max = measured_peaks()
@@ -544,19 +836,29 @@ def main():
         achieved = fast_bytes / (fast_ms * 1e-3) / 1e9
         clocks = sampler.result()
         f_mhz = clocks["sm_mhz"] or sm_max
-        # POPC issues at 16 lanes/clk/SM.  The matcher folds 7 of the 8 XOR words through three carry-save adders, so a
-        # 256-bit pair costs 5 POPC (the plain form's 8 POPC gave the 582 Gpairs/s roof quoted in SURVEY 8d)
-        popc_roof = 148 * 16 * f_mhz * 1e6 / 5 / 1e9
+        # The matcher folds 7 of the 8 XOR words through three carry-save adders, so a 256-bit pair costs 5 POPC (the
+        # plain form's 8 POPC gave the 582 Gpairs/s roof quoted in SURVEY 8d).  POPC lanes/clk/SM: measured by the
+        # register-only microbenchmark (orbb_debug_popc_rate); 16 is the programming guide's figure.
+        popc_lanes = popc_rate if popc_rate else 16.0
+        popc_roof = 148 * popc_lanes * f_mhz * 1e6 / 5 / 1e9
         line = {
             "metric": "ORB frames/s (640x480, 1000 kp)", "value": fps, "unit": "frames/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
             "config": workload_config(B),
             "clocks": clocks,
+            "value_stats": {"median": B * world / (float(np.median(per_step_ms)) * 1e-3),
+                            "best": B * world / (float(np.min(per_step_ms)) * 1e-3),
+                            "what": "per-step CUDA-event times inside the same timed region (max over ranks per step)"},
             "e2e": {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "api": "orbb_extract_batch_host_async + orbb_wait, double-buffered (2 batches in flight)",
-                    "sync_api_value": frames_total / (e2e_sync_ms * 1e-3), "pcie_h2d_gbs": h2d_gbs,
-                    "h2d_bound_fps": world * h2d_gbs * 1e9 / (W * H)},
+                    "sync_api_value": frames_total / (e2e_sync_ms * 1e-3),
+                    "equals_device_path": e2e_equal,
+                    "h2d_concurrent_gbs_per_gpu_slowest": h2d_slowest, "h2d_concurrent_gbs_aggregate": h2d_aggregate,
+                    "h2d_bound_fps": h2d_aggregate * 1e9 / (W * H),
+                    "frac_of_h2d_bound": e2e_fps / (h2d_aggregate * 1e9 / (W * H)),
+                    "h2d_what": "pinned-host -> device copies of one 78.6 MB batch, all ranks copying at the same time "
+                                "(barrier-aligned), 5 repeats"},
             "gpu_launches": gpu_launches,
             "roofline": {"bound": "hbm", "kernel": "k_fast_cells", "achieved": achieved, "peak": hbm_peak,
                          "unit": "GB/s", "frac": achieved / hbm_peak,
@@ -569,30 +871,33 @@ def main():
                               "issue_peak_tinst_s": 148 * 4 * 32 * f_mhz * 1e6 / 1e12,
                               "frac_of_issue": THREAD_INST_PER_FRAME * fps / world / (148 * 4 * 32 * f_mhz * 1e6),
                               "note": "integer-issue bound path: 148 SMs x 4 schedulers x 32 lanes x SM clock; "
-                                      "instruction counts from profiles/r01m_all_kernels_full.txt"},
+                                      "instruction counts from " + PROFILE_SOURCE},
             "stages_ms": dict(zip(stage_names, stage_ms)),
-            "keypoints_per_frame": float(kp_total.item()) / (B * world),
-            "gather": {"ms": gather_ms, "what": "all_gather of per-frame counts + ragged gather of {q,t,dist} match "
-                                               "records to rank 0 (NCCL), after the timed region",
-                       "records_on_rank0": int(gathered.shape[0]) if gathered is not None else 0},
+            "keypoints_per_frame": kp_total / (B * world),
             "matcher": {"value": gpairs * world * (match_ms / match_ms_max), "unit": "Gpairs/s", "nq_per_gpu": nq,
-                        "nt": MAP_SIZE, "k": 1, "ms": match_ms_max, "popc_per_pair": 5, "popc_roof_gpairs_per_gpu": popc_roof,
+                        "nt": MAP_SIZE, "k": 1, "ms": match_ms_max, "popc_per_pair": 5,
+                        "popc_lanes_per_clk_per_sm_measured": popc_rate,
+                        "popc_roof_gpairs_per_gpu": popc_roof,
                         "plain_8popc_roof_gpairs_per_gpu": popc_roof * 5 / 8,
                         "frac_of_popc_roof": gpairs / popc_roof},
         }
+        if sustained is not None:
+            line["sustained"] = sustained
+        if not args.no_parity:
+            sample = sorted({0, B // 8, B // 2 - 1, B // 2, B // 2 + 1, (3 * B) // 4, B - 2, B - 1} & set(range(B)))
+            line["parity"] = parity_block(orbb, host_sets[last_set], sample, timed_kp, timed_desc, counts)
+        if cfg5 is not None:
+            line["cfg5"] = cfg5
+            line["gather"] = cfg5["gather"]
         if rgbd is not None:
             line["rgbd_stage"] = rgbd
         if refgpu is not None:
             line["reference_gpu_kernels"] = refgpu
         if world == 1 and not args.no_cpu:
-            cores = os.cpu_count() or 1
-            cfps, nsample, native = cpu_oracle_fps(host_sets[0], cores)
-            line["cpu_baseline"] = {"value": cfps, "unit": "frames/s", "cores": cores, "kind": "port",
-                                    "sample": f"{nsample} of the step's 640x480 frames, {cores} threads, oracle "
-                                              f"{'-march=native' if native else 'x86-64-v2'}"}
+            line["cpu_baseline"] = cpu_baseline_block(host_sets[0], os.cpu_count() or 1)
         print(json.dumps(line))
-    ex.close()
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
 
 

@@ -182,6 +182,14 @@ int orbb_detect_export(orbb_handle *h, float *d_pos_xy, float *d_score, int32_t 
 int orbb_match_knn(orbb_handle *h, const uint8_t *d_query, int nq, const uint8_t *d_train, int nt,
                    int k, float ratio, int32_t *d_idx, int32_t *d_dist, uint8_t *d_accept,
                    int32_t *d_naccept, void *cuda_stream);
+/* Batch form (BASELINE cfg 5: every frame of a batch against one descriptor map): d_query is an extraction output
+ * [n_frames][max_kp][32] with DEVICE counts [n_frames]; all frames are matched against the same train set.  Outputs
+ * keep the inputs' fixed stride -- d_idx / d_dist [n_frames][max_kp][2], d_accept [n_frames][max_kp] -- and rows
+ * past a frame's count report -1 / 0, so the result can be gathered across GPUs as it is.  No host round trip of
+ * the counts.  Async on stream. */
+int orbb_match_knn_batch(orbb_handle *h, const uint8_t *d_query, const int32_t *d_q_counts, int n_frames,
+                         int max_kp, const uint8_t *d_train, int nt, int k, float ratio, int32_t *d_idx,
+                         int32_t *d_dist, uint8_t *d_accept, int32_t *d_naccept, void *cuda_stream);
 /* Segmented form: nseg independent (query set, train set) pairs, e.g. left/right or t/t+1 frames.
  * q_offsets/t_offsets are DEVICE int32 [nseg+1] row offsets into d_query/d_train; idx values are
  * relative to the segment's train set.  The launch geometry comes from the HOST-side sizes the caller states
@@ -374,6 +382,8 @@ long long orbb_slam_frame_to_bson(int32_t ax, int32_t ay, int32_t az, int32_t wi
 
 /* ---------------------------------------------------------------- debug / parity access
  * Download stage outputs of frame `frame` of the last batch to HOST memory (synchronises). */
+/* measured POPC issue rate (lanes per clock per SM) of this device: the matcher's roofline denominator */
+int orbb_debug_popc_rate(orbb_handle *h, double *popc_per_clk_per_sm);
 /* padded level, contiguous (w+38) x (h+38) */
 int orbb_debug_get_padded(orbb_handle *h, int frame, int level, uint8_t *host_out);
 /* blurred ROI, contiguous w x h */

@@ -166,10 +166,10 @@ k_fast_cells(const CUtensorMap *__restrict__ maps, const LevelDev *__restrict__ 
     __syncwarp();
 
     const int npix = cw * ch;
-    const unsigned inv_cw = (1u << 20) / (unsigned)cw + 1u;  // exact floor(idx/cw) for idx*cw < 2^20
     const unsigned lt_mask = (1u << lane) - 1u;
     const int nux = (cw + 3) >> 2, nunits = nux * ch;        // 4-pixel units per row / per cell
-    const unsigned inv_nux = (1u << 20) / (unsigned)nux + 1u;
+    const unsigned inv_nux = (1u << 20) / (unsigned)nux + 1u;  // exact floor(u / nux) for u * nux < 2^20
+    // Queue entries are (y << 6 | x), cell-relative (cells are at most 63 px wide / high): decoding is a shift and a mask.
 
     // Upstream order: FAST(ini) on the cell; only if that leaves nothing, FAST(min).  Running the high
     // threshold first rejects most pixels in the precheck (the low-threshold pass is rare on textured input).
@@ -177,16 +177,26 @@ k_fast_cells(const CUtensorMap *__restrict__ maps, const LevelDev *__restrict__ 
     for (int pass = DUMP ? 1 : 0; pass < 2; ++pass) {
         const int thr = pass == 0 ? t_hi : t_lo;
         if (pass == 1 && !DUMP && t_lo == t_hi) break;
-        // ---- phase 1: packed precheck, 4 pixels per lane.  Necessary condition for a 9-arc: every antipodal
-        // pair holds a pixel with |d| > thr; tested on the pairs (0,8) and (4,12) with VABSDIFF4 and a
-        // carry-free SWAR compare on |d|>>1 (a superset of |d| > thr -- exactness comes from phase 2).
-        const unsigned kadd = (unsigned)(128 - ((thr + 1) >> 1)) * 0x01010101u;
+        // ---- phase 1: packed precheck, 4 pixels per lane and step.  Necessary condition for a 9-arc: every antipodal
+        // pair holds a pixel with |d| > thr; tested on the pairs (0,8) and (4,12): VABSDIFF4, then per byte
+        // "a >= K" as bit 7 of (a + (128 - K)) | a  (K = min(thr + 1, 128); a carry out of a byte can only add 1 to
+        // its neighbour, i.e. let a few more pixels through -- exactness comes from phase 2).
+        //
+        // Each lane owns a CONTIGUOUS run of U = ceil(units / 32) units, keeps the flags of its run in a 64-bit register
+        // (4 bits per unit), and the queue positions come from ONE warp prefix sum of the per-lane counts per cell --
+        // not from four ballots per 32 units: on B200 VOTE and POPC issue at 16 lanes/clk/SM, a quarter of the ALU
+        // rate (tools/pipe_probe.cu, profiles/r02_pipe_probe.txt), and the ballot form spent 12 of them per 128 pixels.
+        // The queue order (lane, unit, pixel) differs from raster order; nothing downstream depends on it.
+        const unsigned cadd = (unsigned)(128 - min(thr + 1, 128)) * 0x01010101u;
+        const unsigned last_mask = (cw & 3) ? (0x80808080u >> (8 * (4 - (cw & 3)))) : 0x80808080u;  // ragged last unit of a row
         int qn = 0;
-        for (int base = 0; base < nunits; base += 32) {
-            const int u = base + lane;
-            unsigned flags = 0;
-            int pix0 = 0;
-            if (u < nunits) {
+        for (int ub = 0; ub < nunits; ub += 512) {  // 16 units per lane per round: one round unless the cell is > 512 units
+            const int nr = min(nunits - ub, 512);
+            const int U = (nr + 31) >> 5;
+            const int u0 = ub + lane * U, u_end = ub + nr;
+            unsigned wlo = 0, whi = 0;
+            for (int i = 0; i < U; ++i) {  // warp-uniform trip count; lanes past the end re-test the last unit with a zero mask
+                const int u = min(u0 + i, u_end - 1);
                 const int y = (int)(((unsigned)u * inv_nux) >> 20), j = u - y * nux;
                 unsigned cc, up, dn, lf, rt;
                 if (TMA) {  // arbitrary byte phase: every 4-pixel window is a funnel shift of two words
@@ -200,7 +210,7 @@ k_fast_cells(const CUtensorMap *__restrict__ maps, const LevelDev *__restrict__ 
                     lf = __funnelshift_r(r0[bl >> 2], r0[(bl >> 2) + 1], (bl & 3) * 8);
                     rt = __funnelshift_r(r0[br >> 2], r0[(br >> 2) + 1], (br & 3) * 8);
                 } else {
-                    const uint32_t *row = tile32 + (y + 3) * tpw + j;  // row[0]=left word, row[1]=centre, row[2]=right
+                    const uint32_t *row = tile32 + (y + 3) * tpw + j;  // row[0] = left word, row[1] = centre, row[2] = right
                     cc = row[1];
                     dn = row[1 + 3 * tpw]; up = row[1 - 3 * tpw];
                     rt = __funnelshift_r(cc, row[2], 24);
@@ -208,19 +218,38 @@ k_fast_cells(const CUtensorMap *__restrict__ maps, const LevelDev *__restrict__ 
                 }
                 const unsigned a0 = __vabsdiffu4(dn, cc), a8 = __vabsdiffu4(up, cc);
                 const unsigned a4 = __vabsdiffu4(rt, cc), a12 = __vabsdiffu4(lf, cc);
-                const unsigned x0 = ((a0 >> 1) & 0x7f7f7f7fu) + kadd, x8 = ((a8 >> 1) & 0x7f7f7f7fu) + kadd;
-                const unsigned x4 = ((a4 >> 1) & 0x7f7f7f7fu) + kadd, x12 = ((a12 >> 1) & 0x7f7f7f7fu) + kadd;
-                const int nvalid = cw - 4 * j;
-                const unsigned vmask = nvalid >= 4 ? 0x80808080u : (0x80808080u >> (8 * (4 - nvalid)));
-                flags = (x0 | x8) & (x4 | x12) & vmask;
-                pix0 = y * cw + 4 * j;
+                const unsigned p08 = (a0 + cadd) | a0 | (a8 + cadd) | a8, p412 = (a4 + cadd) | a4 | (a12 + cadd) | a12;
+                const unsigned vm = u0 + i < u_end ? (j == nux - 1 ? last_mask : 0x80808080u) : 0u;
+                const unsigned flags = p08 & p412 & vm;  // bits 7 / 15 / 23 / 31
+                // -> one nibble, pushed into the lane's 64-bit flag word: the multiply moves the four bits to 28..31 (no
+                // two partial products meet there), two funnel shifts push them in
+                const unsigned prod = flags * 0x00204081u;
+                whi = __funnelshift_l(wlo, whi, 4);
+                wlo = __funnelshift_l(prod, wlo, 4);
             }
+            // queue positions: exclusive prefix sum of the lanes' counts (5 shuffles per cell)
+            const int c_own = __popc(wlo) + __popc(whi);
+            int incl = c_own;
 #pragma unroll
-            for (int b = 0; b < 4; ++b) {
-                const bool ok = (flags >> (8 * b + 7)) & 1u;
-                const unsigned m = __ballot_sync(0xffffffffu, ok);
-                if (ok) queue[qn + __popc(m & lt_mask)] = (uint16_t)(pix0 + b);
-                qn += __popc(m);
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += t;
+            }
+            uint16_t *qp = queue + qn + incl - c_own;
+            qn += __shfl_sync(0xffffffffu, incl, 31);
+            // pop the nibbles (last unit first) and store the flagged pixels of the run
+            const int ystep = 64 - 4 * nux;
+            for (int i = U - 1; i >= 0; --i) {
+                const unsigned nib = wlo & 15u;
+                wlo = __funnelshift_r(wlo, whi, 4);
+                whi >>= 4;
+                const int u = u0 + i;
+                const int y = (int)(((unsigned)u * inv_nux) >> 20);
+                const int e0 = y * ystep + 4 * u;  // (y << 6) | (4 * j)
+                if (nib & 1u) *qp++ = (uint16_t)e0;
+                if (nib & 2u) *qp++ = (uint16_t)(e0 + 1);
+                if (nib & 4u) *qp++ = (uint16_t)(e0 + 2);
+                if (nib & 8u) *qp++ = (uint16_t)(e0 + 3);
             }
         }
         __syncwarp();
@@ -232,7 +261,7 @@ k_fast_cells(const CUtensorMap *__restrict__ maps, const LevelDev *__restrict__ 
             int idx = 0, m = 0;
             if (i < qn) {
                 idx = queue[i];
-                const int y = (int)(((unsigned)idx * inv_cw) >> 20), x = idx - y * cw;
+                const int y = idx >> 6, x = idx & 63;
                 m = arc_score(tile + (y + 3) * tp + x + off, tp);
                 m = m > thr ? m : 0;
                 if (m) score[(y + 1) * sp + x + 1] = (uint8_t)min(m, 255);
@@ -262,8 +291,7 @@ k_fast_cells(const CUtensorMap *__restrict__ maps, const LevelDev *__restrict__ 
             bool keep = false;
             if (i < cn) {
                 idx = queue[i];
-                const int y = (int)(((unsigned)idx * inv_cw) >> 20), x = idx - y * cw;
-                const uint8_t *s = score + (y + 1) * sp + x + 1;
+                const uint8_t *s = score + ((idx >> 6) + 1) * sp + (idx & 63) + 1;
                 const int v = s[0];
                 const int n0 = max3(s[-sp - 1], s[-sp], s[-sp + 1]);
                 const int n1 = max3(s[-1], s[1], s[sp - 1]);
@@ -288,7 +316,7 @@ k_fast_cells(const CUtensorMap *__restrict__ maps, const LevelDev *__restrict__ 
         uint32_t packed = 0;
         if (i < kn) {
             const int idx = queue[i];
-            const int y = (int)(((unsigned)idx * inv_cw) >> 20), x = idx - y * cw;
+            const int y = idx >> 6, x = idx & 63;
             const int m = score[(y + 1) * sp + x + 1];
             emit = true;
             // coordinates relative to (minBorderX, minBorderY) = (16,16), as upstream's vToDistributeKeys

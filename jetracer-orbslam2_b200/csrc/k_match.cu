@@ -62,10 +62,13 @@ template <int K>  // K = 1: only the nearest neighbour is tracked (one min per p
 __global__ void __launch_bounds__(MATCH_THREADS)
 k_match(const uint4 *__restrict__ query, const uint4 *__restrict__ train, const int *__restrict__ q_off,
         const int *__restrict__ t_off, int nq_one, int nt_one, int n_split, int4 *__restrict__ partial,
-        int partial_stride) {
+        int partial_stride, const int *__restrict__ q_counts, int max_kp) {
     __shared__ uint4 s_t[MATCH_TILE * 2];
     const int seg = blockIdx.z;
-    const int q0 = q_off ? q_off[seg] : 0, q1 = q_off ? q_off[seg + 1] : nq_one;
+    // query rows of this segment: explicit offsets, or (batch form) frame `seg` of a [n_frames][max_kp] array whose
+    // row counts live on the device, or the whole array
+    const int q0 = q_counts ? seg * max_kp : (q_off ? q_off[seg] : 0);
+    const int q1 = q_counts ? q0 + min(q_counts[seg], max_kp) : (q_off ? q_off[seg + 1] : nq_one);
     const int t0 = t_off ? t_off[seg] : 0, t1 = t_off ? t_off[seg + 1] : nt_one;
     const int qbase = q0 + blockIdx.x * (MATCH_THREADS * MATCH_QPT);
     if (qbase >= q1) return;
@@ -115,12 +118,14 @@ k_match(const uint4 *__restrict__ query, const uint4 *__restrict__ train, const 
 __global__ void __launch_bounds__(256)
 k_match_merge(const int4 *__restrict__ partial, int partial_stride, int n_split, int nq, int k, float ratio,
               int *__restrict__ out_idx, int *__restrict__ out_dist, uint8_t *__restrict__ accept,
-              int *__restrict__ n_accept) {
+              int *__restrict__ n_accept, const int *__restrict__ q_counts, int max_kp) {
     const int q = blockIdx.x * blockDim.x + threadIdx.x;
     bool ok = false;
     if (q < nq) {
         Best2 b = {257, -1, 257, -1};
-        for (int s = 0; s < n_split; ++s) {
+        bool live = true;  // batch form: rows past the frame's count were never matched and report "no match"
+        if (q_counts) { const int f = q / max_kp; live = q - f * max_kp < min(q_counts[f], max_kp); }
+        for (int s = 0; live && s < n_split; ++s) {
             const int4 p = partial[(size_t)s * partial_stride + q];
             if (p.y >= 0) best2_update(b, p.x, p.y);
             if (p.w >= 0) best2_update(b, p.z, p.w);
@@ -212,21 +217,23 @@ cudaError_t launch_match_windowed(const uint8_t *d_q, const void *d_q_xy, int q_
 cudaError_t launch_match(const uint8_t *d_q, const uint8_t *d_t, const int *d_q_off, const int *d_t_off, int nseg,
                          int nq_total, int max_q_per_seg, int nt_one, int n_split, int4 *d_partial,
                          int partial_stride, int k, float ratio, int *d_idx, int *d_dist, uint8_t *d_accept,
-                         int *d_naccept, cudaStream_t st) {
+                         int *d_naccept, cudaStream_t st, const int *d_q_counts, int max_kp) {
     if (nq_total <= 0) return cudaSuccess;
     const int qblocks = (max_q_per_seg + MATCH_THREADS * MATCH_QPT - 1) / (MATCH_THREADS * MATCH_QPT);
     dim3 grid(qblocks, n_split, nseg);
     if (k == 1)
         k_match<1><<<grid, MATCH_THREADS, 0, st>>>(reinterpret_cast<const uint4 *>(d_q), reinterpret_cast<const uint4 *>(d_t),
-                                                   d_q_off, d_t_off, nq_total, nt_one, n_split, d_partial, partial_stride);
+                                                   d_q_off, d_t_off, nq_total, nt_one, n_split, d_partial, partial_stride,
+                                                   d_q_counts, max_kp);
     else
         k_match<2><<<grid, MATCH_THREADS, 0, st>>>(reinterpret_cast<const uint4 *>(d_q), reinterpret_cast<const uint4 *>(d_t),
-                                                   d_q_off, d_t_off, nq_total, nt_one, n_split, d_partial, partial_stride);
+                                                   d_q_off, d_t_off, nq_total, nt_one, n_split, d_partial, partial_stride,
+                                                   d_q_counts, max_kp);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     // *d_naccept is zeroed by the caller (orbb_match_knn accumulates over query chunks)
     k_match_merge<<<(nq_total + 255) / 256, 256, 0, st>>>(d_partial, partial_stride, n_split, nq_total, k, ratio, d_idx,
-                                                           d_dist, d_accept, d_naccept);
+                                                           d_dist, d_accept, d_naccept, d_q_counts, max_kp);
     return cudaGetLastError();
 }
 
@@ -349,6 +356,30 @@ cudaError_t launch_match_projection(const uint8_t *d_q, const float *d_q_uv, con
                                                      d_q_kp, d_q_counts, reinterpret_cast<const uint4 *>(d_t), d_t_kp, d_t_counts,
                                                      max_kp, th, th_high, tab, n_levels, d_idx, d_dist);
     k_rotation_filter<<<n_frames, 256, 0, st>>>(d_q_kp, d_t_kp, d_q_counts, max_kp, check, d_idx, d_dist, d_nmatched);
+    return cudaGetLastError();
+}
+
+// ---- POPC issue-rate microbenchmark (SURVEY 8d asks for the matcher's roof to be measured, not quoted): one CTA of
+// 1024 threads per SM, every thread runs 8 independent POPC chains (no memory traffic), the CTA reports the SM
+// cycles it took.  rate = 1024 * 8 * iters POPC / cycles = POPC lanes per clock per SM.
+__global__ void __launch_bounds__(1024, 1) k_popc_rate(int iters, unsigned seed, long long *__restrict__ cycles, unsigned *__restrict__ sink) {
+    unsigned a0 = seed + threadIdx.x, a1 = a0 * 3u, a2 = a0 * 5u, a3 = a0 * 7u, a4 = a0 * 11u, a5 = a0 * 13u, a6 = a0 * 17u, a7 = a0 * 19u;
+    __syncthreads();
+    const long long t0 = clock64();
+#pragma unroll 1
+    for (int i = 0; i < iters; ++i) {
+        // the POPC result feeds the next POPC operand of its own chain only: 8 chains in flight per thread
+        a0 = __popc(a0) + seed; a1 = __popc(a1) + seed; a2 = __popc(a2) + seed; a3 = __popc(a3) + seed;
+        a4 = __popc(a4) + seed; a5 = __popc(a5) + seed; a6 = __popc(a6) + seed; a7 = __popc(a7) + seed;
+    }
+    __syncthreads();
+    const long long t1 = clock64();
+    if (threadIdx.x == 0) cycles[blockIdx.x] = t1 - t0;
+    if ((a0 ^ a1 ^ a2 ^ a3 ^ a4 ^ a5 ^ a6 ^ a7) == 0xdeadbeefu) sink[0] = a0;  // keeps the chains alive
+}
+
+cudaError_t launch_popc_rate(int n_ctas, int iters, long long *d_cycles, unsigned *d_sink, cudaStream_t st) {
+    k_popc_rate<<<n_ctas, 1024, 0, st>>>(iters, 0x9e3779b9u, d_cycles, d_sink);
     return cudaGetLastError();
 }
 

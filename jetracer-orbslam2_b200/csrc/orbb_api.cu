@@ -37,7 +37,8 @@ cudaError_t launch_calc_orb_pos(const float *, const float *, uint8_t *, const u
 cudaError_t launch_detect_export(const LevelDev *, int, const int *, const int *, const int *, int, int, float *, float *, int *,
                                  int *, int *, int, cudaStream_t);
 cudaError_t launch_match(const uint8_t *, const uint8_t *, const int *, const int *, int, int, int, int, int, int4 *,
-                         int, int, float, int *, int *, uint8_t *, int *, cudaStream_t);
+                         int, int, float, int *, int *, uint8_t *, int *, cudaStream_t, const int * = nullptr, int = 0);
+cudaError_t launch_popc_rate(int, int, long long *, unsigned *, cudaStream_t);
 cudaError_t launch_align(const uint16_t *, int, float, const orbb_intrinsics &, const orbb_intrinsics &, const orbb_extrinsics &,
                          uint32_t *, cudaStream_t);
 cudaError_t launch_kp_to_point(const uint32_t *, const orbb_intrinsics &, int, const orbb_keypoint *, const uint8_t *,
@@ -918,6 +919,41 @@ extern "C" int orbb_match_knn(orbb_handle *h, const uint8_t *d_query, int nq, co
     return ORBB_OK;
 }
 
+// Batch form for the map-matching use (BASELINE cfg 5): the query sets are the frames of an extraction output
+// ([n_frames][max_kp][32] with device-side counts), all against ONE train set.  blockIdx.z = frame; rows past a
+// frame's count report "no match" (-1), so the outputs keep the fixed [n_frames][max_kp] stride of the inputs and
+// can be gathered across GPUs without a compaction step or a host round trip.
+extern "C" int orbb_match_knn_batch(orbb_handle *h, const uint8_t *d_query, const int32_t *d_q_counts, int n_frames,
+                                    int max_kp, const uint8_t *d_train, int nt, int k, float ratio, int32_t *d_idx,
+                                    int32_t *d_dist, uint8_t *d_accept, int32_t *d_naccept, void *stream) {
+    if (!h || !d_query || !d_q_counts || !d_train || !d_idx || !d_dist || n_frames < 0 || max_kp < 1 || nt < 0 || k < 1 ||
+        k > 2)
+        return ORBB_ERR_INVALID;
+    if ((reinterpret_cast<uintptr_t>(d_query) | reinterpret_cast<uintptr_t>(d_train)) & 15) return ORBB_ERR_INVALID;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    CK(h, cudaSetDevice(h->device));
+    if (d_naccept) CK(h, cudaMemsetAsync(d_naccept, 0, sizeof(int), st));
+    if (n_frames == 0) return ORBB_OK;
+    if (nt > 64 * (1 << 22)) return ORBB_ERR_CAPACITY;
+    const int qb = (max_kp + 255) / 256;
+    for (int f0 = 0; f0 < n_frames;) {  // frame chunks: gridDim.z <= 65535 and n_split x rows within the scratch
+        int n = std::min(n_frames - f0, 65535);
+        int n_split = pick_split(qb * n, nt);
+        if ((size_t)n_split * n * max_kp > h->partial_cap) {
+            n = (int)std::min<size_t>(n, std::max<size_t>(h->partial_cap / ((size_t)n_split * max_kp), 1));
+            n_split = pick_split(qb * n, nt);
+            if ((size_t)n_split * n * max_kp > h->partial_cap) return ORBB_ERR_CAPACITY;  // a single frame does not fit
+        }
+        const size_t r0 = (size_t)f0 * max_kp;
+        CK(h, launch_match(d_query + 32 * r0, d_train, nullptr, nullptr, n, n * max_kp, max_kp, nt, n_split, h->d_partial,
+                           n * max_kp, k, ratio, d_idx + 2 * r0, d_dist + 2 * r0, d_accept ? d_accept + r0 : nullptr,
+                           d_naccept, st, d_q_counts + f0, max_kp));
+        h->n_launches += 2;
+        f0 += n;
+    }
+    return ORBB_OK;
+}
+
 extern "C" int orbb_match_knn_segmented(orbb_handle *h, const uint8_t *d_query, const int32_t *d_q_offsets,
                                         const uint8_t *d_train, const int32_t *d_t_offsets, int nseg, int nq_total,
                                         int max_q_per_seg, int max_t_per_seg, int k, float ratio, int32_t *d_idx,
@@ -1082,6 +1118,26 @@ extern "C" int orbb_rgb_to_grayscale(orbb_handle *h, const uint8_t *d_rgb, size_
 }
 
 // ---------------------------------------------------------------- debug / parity access
+// POPC lanes per clock per SM, measured: one 1024-thread CTA per SM running register-only POPC chains (k_popc_rate);
+// the median over the CTAs' own cycle counts is clock independent.  Synchronises.
+extern "C" int orbb_debug_popc_rate(orbb_handle *h, double *popc_per_clk_per_sm) {
+    if (!h || !popc_per_clk_per_sm) return ORBB_ERR_INVALID;
+    CK(h, cudaSetDevice(h->device));
+    cudaDeviceProp prop;
+    CK(h, cudaGetDeviceProperties(&prop, h->device));
+    const int n = prop.multiProcessorCount, iters = 20000;
+    long long *d_cyc = reinterpret_cast<long long *>(h->d_partial);  // scratch: n x 8 bytes + 4
+    unsigned *d_sink = reinterpret_cast<unsigned *>(d_cyc + n);
+    for (int rep = 0; rep < 2; ++rep) CK(h, launch_popc_rate(n, iters, d_cyc, d_sink, 0));  // first run warms the clocks
+    CK(h, cudaDeviceSynchronize());
+    std::vector<long long> cyc((size_t)n);
+    CK(h, cudaMemcpy(cyc.data(), d_cyc, sizeof(long long) * n, cudaMemcpyDeviceToHost));
+    std::sort(cyc.begin(), cyc.end());
+    *popc_per_clk_per_sm = 1024.0 * 8.0 * iters / (double)std::max<long long>(cyc[n / 2], 1);
+    h->n_launches += 2;
+    return ORBB_OK;
+}
+
 extern "C" int orbb_debug_get_padded(orbb_handle *h, int frame, int level, uint8_t *host_out) {
     if (!h || !host_out || level < 0 || level >= h->nlevels || frame < 0 || frame >= h->max_batch) return ORBB_ERR_INVALID;
     const LevelDev &L = h->lv[level];

@@ -33,9 +33,9 @@ EXPORTS = [
     "orbb_extract_batch_device", "orbb_extract_batch_host", "orbb_extract_batch_host_async", "orbb_wait",
     "orbb_stage_upload", "orbb_pyramid_create_levels",
     "orbb_detect", "orbb_detect_fast", "orbb_detect_distribute", "orbb_gaussian_blur", "orbb_compute_angle_and_orb",
-    "orbb_compute_fast_angle", "orbb_calc_orb", "orbb_detect_export", "orbb_match_knn",
+    "orbb_compute_fast_angle", "orbb_calc_orb", "orbb_detect_export", "orbb_match_knn", "orbb_match_knn_batch",
     "orbb_match_knn_segmented", "orbb_match_windowed", "orbb_debug_get_padded", "orbb_debug_get_blurred", "orbb_debug_get_scores",
-    "orbb_debug_get_candidates", "orbb_debug_get_selected", "orbb_debug_distribute",
+    "orbb_debug_popc_rate", "orbb_debug_get_candidates", "orbb_debug_get_selected", "orbb_debug_distribute",
     "orbb_align_depth_to_other", "orbb_keypoint_pixel_to_point", "orbb_reproject_points", "orbb_match_windowed_batch",
     "orbb_rgb_to_grayscale", "orbb_match_projection_batch", "orbb_compute_stereo_matches",
     "orbb_slam_frame_bson_size", "orbb_slam_frame_to_bson",
@@ -133,11 +133,13 @@ def load_library():
     L.orbb_gaussian_blur.argtypes = [vp, vp]
     L.orbb_compute_angle_and_orb.argtypes = [vp, vp, vp, vp, i32, vp]
     L.orbb_match_knn.argtypes = [vp, vp, i32, vp, i32, i32, f32, vp, vp, vp, vp, vp]
+    L.orbb_match_knn_batch.argtypes = [vp, vp, vp, i32, i32, vp, i32, i32, f32, vp, vp, vp, vp, vp]
     L.orbb_compute_fast_angle.argtypes = [vp, vp, vp, vp, i32, i32, i32, i32, vp]
     L.orbb_calc_orb.argtypes = [vp, vp, vp, vp, vp, i32, i32, i32, i32, vp]
     L.orbb_detect_export.argtypes = [vp, vp, vp, vp, vp, vp, i32, vp]
     L.orbb_match_knn_segmented.argtypes = [vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, f32, vp, vp, vp, vp]
     L.orbb_match_windowed.argtypes = [vp, vp, vp, i32, i32, vp, vp, i32, i32, f32, i32, vp, vp, vp, vp]
+    L.orbb_debug_popc_rate.argtypes = [vp, C.POINTER(C.c_double)]
     L.orbb_debug_get_padded.argtypes = [vp, i32, i32, vp]
     L.orbb_debug_get_blurred.argtypes = [vp, i32, i32, vp]
     L.orbb_debug_get_scores.argtypes = [vp, i32, i32, vp]
@@ -364,6 +366,15 @@ class ORBextractor:
                                              _dev_ptr(d_naccept) if d_naccept is not None else C.c_void_p(0),
                                              _stream_ptr(stream)))
 
+    def match_keypoints_batch(self, d_query, d_q_counts, n_frames: int, d_train, nt: int, d_idx, d_dist, d_accept=None,
+                              d_naccept=None, k: int = 1, ratio: float = 0.7, max_kp=None, stream=None):
+        """Every frame of an extraction output ([n][max_kp][32] + device counts) against one train set (cfg 5)."""
+        opt = lambda t: _dev_ptr(t) if t is not None else C.c_void_p(0)  # noqa: E731
+        self._check(self._lib.orbb_match_knn_batch(self._h, _dev_ptr(d_query), _dev_ptr(d_q_counts), n_frames,
+                                                   self.max_kp if max_kp is None else max_kp, _dev_ptr(d_train), nt, k,
+                                                   ratio, _dev_ptr(d_idx), _dev_ptr(d_dist), opt(d_accept),
+                                                   opt(d_naccept), _stream_ptr(stream)))
+
     def match_keypoints_segmented(self, d_query, d_q_off, d_train, d_t_off, nseg: int, nq_total: int, max_q_per_seg: int,
                                   max_t_per_seg: int, d_idx, d_dist, d_accept=None, k: int = 2, ratio: float = 0.7,
                                   stream=None):
@@ -441,6 +452,12 @@ class ORBextractor:
             _dev_ptr(d_depth), _dev_ptr(d_nstereo) if d_nstereo is not None else C.c_void_p(0), _stream_ptr(stream)))
 
     # -- parity / debug access --------------------------------------------------------------
+    def debug_popc_rate(self) -> float:
+        """measured POPC lanes / clock / SM (register-only microbenchmark; synchronises)"""
+        out = C.c_double(0)
+        self._check(self._lib.orbb_debug_popc_rate(self._h, C.byref(out)))
+        return float(out.value)
+
     def debug_padded(self, level: int, frame: int = 0) -> np.ndarray:
         li = self.level_info(level)
         out = np.zeros((li.height + 38, li.width + 38), np.uint8)

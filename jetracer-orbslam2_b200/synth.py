@@ -106,3 +106,16 @@ def rolled_batch(width: int, height: int, n: int, seed0: int, n_base: int = 16) 
         k = i // len(base)
         out[i] = np.roll(b, (37 * k, 53 * k), axis=(0, 1)) if k else b
     return out
+
+
+def rolled_frames(width: int, height: int, indices, seed0: int, n_base: int = 16) -> np.ndarray:
+    """frames `indices` of the (unbounded) rolled_batch sequence with n >= n_base: what a rank generates for its shard of
+    a global batch, identical to slicing rolled_batch(width, height, n, seed0, n_base) for any n > max(indices)."""
+    indices = [int(i) for i in indices]
+    need = sorted({i % n_base for i in indices})
+    base = {b: textured_frame(width, height, seed0 + b) for b in need}
+    out = np.empty((len(indices), height, width), np.uint8)
+    for j, i in enumerate(indices):
+        k = i // n_base
+        out[j] = np.roll(base[i % n_base], (37 * k, 53 * k), axis=(0, 1)) if k else base[i % n_base]
+    return out

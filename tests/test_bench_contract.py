@@ -15,7 +15,7 @@ def _run(*args, timeout=600):
 
 
 def test_reference_arm_line():
-    r = _run("--impl", "reference", "--steps", "1", "--warmup", "0", "--no-refgpu")
+    r = _run("--impl", "reference", "--steps", "1", "--warmup", "0", "--no-refgpu", "--frames", "16")
     assert r.returncode == 0, r.stderr[-400:]
     lines = [ln for ln in r.stdout.splitlines() if ln.strip()]
     assert len(lines) == 1
@@ -26,6 +26,8 @@ def test_reference_arm_line():
     assert d["dtype"] == "u8" and d["data"] == "synthetic" and "workload" in d["config"]
     cb = d["cpu_baseline"]
     assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and cb["unit"] == "frames/s" and cb["sample"]
+    assert cb["one_core_value"] > 0 and cb["matcher_gpairs"] > 0 and cb["matcher_gpairs_one_core"] > 0
+    assert d["config"]["frames_per_gpu_per_step"] == 16 and d["value_stats"]["best"] >= d["value_stats"]["median"] > 0
     e = d["e2e"]
     assert e["value"] == d["value"] and e["unit"] == "frames/s" and e["h2d_bytes_per_step"] == 0 and e["d2h_bytes_per_step"] == 0
 

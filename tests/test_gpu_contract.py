@@ -330,3 +330,58 @@ def test_create_and_stride_validation(orbb):
     ex.extract_batch_device(d_in, 1, d_kp, d_desc, d_cnt, stride=0)  # a single frame ignores the stride
     torch.cuda.synchronize()
     ex.close()
+
+
+def test_match_knn_batch_fixed_stride(orbb, oracle, synth):
+    """orbb_match_knn_batch (cfg 5: every frame of an extraction output against one map): rows below each frame's
+    device-side count equal the oracle's 1-NN / 2-NN, rows past it report -1, nothing is compacted."""
+    import torch
+    w, h, nb = 320, 240, 5
+    frames = np.stack([synth.textured_frame(w, h, 900 + i) for i in range(3)] + [synth.sparse_frame(w, h, 5), synth.flat_frame(w, h)])
+    ex = orbb.ORBextractor(500, 1.2, 8, 20, 7, width=w, height=h, max_batch=nb)
+    mk = ex.max_kp
+    st = torch.cuda.current_stream()
+    d_in = torch.from_numpy(frames).cuda()
+    d_kp = torch.zeros((nb, mk, 7), dtype=torch.float32, device="cuda")
+    d_desc = torch.full((nb, mk, 32), 0xAB, dtype=torch.uint8, device="cuda")  # rows past the counts hold junk
+    d_cnt = torch.zeros(nb, dtype=torch.int32, device="cuda")
+    ex.extract_batch_device(d_in, nb, d_kp, d_desc, d_cnt, stream=st)
+    torch.cuda.synchronize()
+    cnt = d_cnt.cpu().numpy()
+    assert cnt[4] == 0 and 0 < cnt[3] < 300 and cnt[0] > 400
+    desc = d_desc.cpu().numpy()
+    rng = np.random.default_rng(2)
+    tmap = np.concatenate([desc[0, :cnt[0]], desc[1, :cnt[1]], rng.integers(0, 256, size=(3000, 32), dtype=np.uint8)])
+    tmap[7] = tmap[2]  # duplicate rows: ties -> lowest train index
+    d_map = torch.from_numpy(tmap).cuda()
+    for k in (1, 2):
+        d_idx = torch.full((nb * mk, 2), -9, dtype=torch.int32, device="cuda")
+        d_dist = torch.full((nb * mk, 2), -9, dtype=torch.int32, device="cuda")
+        d_acc = torch.full((nb * mk,), 9, dtype=torch.uint8, device="cuda")
+        d_nacc = torch.zeros(1, dtype=torch.int32, device="cuda")
+        ex.match_keypoints_batch(d_desc, d_cnt, nb, d_map, len(tmap), d_idx, d_dist, d_acc, d_nacc, k=k, ratio=0.7, stream=st)
+        torch.cuda.synchronize()
+        idx = d_idx.cpu().numpy().reshape(nb, mk, 2); dist = d_dist.cpu().numpy().reshape(nb, mk, 2)
+        acc = d_acc.cpu().numpy().reshape(nb, mk)
+        nacc = 0
+        for f in range(nb):
+            c = int(cnt[f])
+            assert (idx[f, c:] == -1).all() and (dist[f, c:] == -1).all() and (acc[f, c:] == 0).all()
+            if c == 0:
+                continue
+            oi, od, oa = oracle.match_knn(desc[f, :c], tmap, k=k, ratio=0.7)
+            if k == 1:
+                oi[:, 1] = -1; od[:, 1] = -1
+            assert np.array_equal(idx[f, :c], oi) and np.array_equal(dist[f, :c], od), (f, k)
+            assert np.array_equal(acc[f, :c].astype(bool), oa)
+            nacc += int(oa.sum())
+        assert int(d_nacc.item()) == nacc
+    ex.close()
+
+
+def test_popc_rate_microbenchmark(orbb):
+    """The matcher's roofline denominator is measured, not quoted: POPC lanes per clock per SM."""
+    ex = orbb.ORBextractor(100, 1.2, 2, 20, 7, width=200, height=150, max_batch=1)
+    r = ex.debug_popc_rate()
+    assert 8.0 < r < 40.0, r
+    ex.close()

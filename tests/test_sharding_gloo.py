@@ -31,11 +31,25 @@ def _worker(rank, world, port, n_frames, q):
     rows = torch.stack([torch.arange(lo, hi), torch.arange(lo, hi) * 2, torch.full((hi - lo,), rank)], 1).to(torch.int32)
     rows = rows[: (hi - lo) - rank]  # ragged: rank 1 contributes one row less
     gathered, per_rank = sh.gather_ragged_to_rank0(rows)
-    q.put((rank, allc.tolist(), int(m.sum()), None if gathered is None else gathered.tolist(), per_rank))
+    # fixed-stride form (bench.py cfg 5): counts and [frames][max_kp] result rows in ONE all_gather_into_tensor
+    max_kp, n_pad = 5, (n_frames + world - 1) // world
+    lay = sh.GatherLayout(n_pad, max_kp)
+    buf = torch.full((lay.total,), -1, dtype=torch.int32)
+    cnt, idx, dst = lay.views(buf)
+    cnt.zero_()
+    for f in range(lo, hi):
+        c = f % (max_kp + 1)                       # "keypoints of frame f"
+        cnt[f - lo] = c
+        for s_ in range(c):
+            idx[(f - lo) * max_kp + s_, 0] = 100 * f + s_   # "train index"
+            dst[(f - lo) * max_kp + s_, 0] = f + s_         # "distance"
+    g = sh.gather_fixed(buf)
+    rec = lay.records(g.numpy(), n_frames)
+    q.put((rank, allc.tolist(), int(m.sum()), None if gathered is None else gathered.tolist(), per_rank, rec.tolist()))
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("n_frames", [7, 8, 1])
+@pytest.mark.parametrize("n_frames", [7, 8, 1])  # 7 and 1: uneven shards, padded gather rows
 def test_shard_and_gather_world2(n_frames):
     world, port = 2, _free_port()
     ctx = mp.get_context("spawn")
@@ -48,9 +62,11 @@ def test_shard_and_gather_world2(n_frames):
         p.join(timeout=60)
         assert p.exitcode == 0
     expect_counts = [3 * f + 1 for f in range(n_frames)]
-    for rank, allc, msum, gathered, per_rank in res:
+    exp_rec = [[f, s_, 100 * f + s_, f + s_] for f in range(n_frames) for s_ in range(f % 6)]
+    for rank, allc, msum, gathered, per_rank, rec in res:
         assert allc == expect_counts
         assert msum == 1600 * 32 * 7  # map broadcast from rank 0
+        assert rec == exp_rec         # every rank holds the same gathered records, in global frame order
     sh = importlib.import_module("jetracer-orbslam2_b200.sharding")
     sizes = [sh.shard_range(n_frames, r, world) for r in range(world)]
     exp_rows = []
