@@ -61,7 +61,10 @@ __device__ __forceinline__ int arc_score(const uint8_t *p, int tp) {
     return (int)max(best & 0xffffu, best >> 16) - 256;
 }
 
-template <bool DUMP, bool TMA>
+// TP: the tile's row pitch in bytes as a compile-time constant (0 = read it from cfg): with it the 16 ring offsets of
+// the arc score and the +-3-row offsets of the precheck are instruction immediates off ONE base register, which takes
+// about a dozen address instructions out of every scored pixel.  The score tile's pitch is tied to it (TP - 8).
+template <bool DUMP, bool TMA, int TP>
 __global__ void __launch_bounds__(FAST_WARPS * 32)
 k_fast_cells(const CUtensorMap *__restrict__ maps, const LevelDev *__restrict__ levels, const CellEntry *__restrict__ cells, int n_cells, int n_levels,
              int *__restrict__ cand_count, int t_lo, int t_hi, FastSmemCfg cfg, int frame_base,
@@ -77,7 +80,7 @@ k_fast_cells(const CUtensorMap *__restrict__ maps, const LevelDev *__restrict__ 
     uint8_t *tile = smem + (size_t)warp * cfg.warp_bytes;
     uint8_t *score = tile + max(cfg.tile_pitch, cfg.tma_pitch) * cfg.tile_rows;
     uint16_t *queue = reinterpret_cast<uint16_t *>(score + cfg.score_pitch * cfg.score_rows);
-    const int tp = TMA ? cfg.tma_pitch : cfg.tile_pitch, sp = cfg.score_pitch, tpw = tp >> 2;
+    const int tp = TMA ? cfg.tma_pitch : (TP ? TP : cfg.tile_pitch), sp = (!TMA && TP) ? TP - 8 : cfg.score_pitch, tpw = tp >> 2;
     const int cw = c.cw, ch = c.ch;
     const uint32_t *tile32 = reinterpret_cast<const uint32_t *>(tile);
     pdl_wait();  // launched as a programmatic dependent of the last pyramid kernel: the levels are complete from here on
@@ -182,52 +185,77 @@ k_fast_cells(const CUtensorMap *__restrict__ maps, const LevelDev *__restrict__ 
         // "a >= K" as bit 7 of (a + (128 - K)) | a  (K = min(thr + 1, 128); a carry out of a byte can only add 1 to
         // its neighbour, i.e. let a few more pixels through -- exactness comes from phase 2).
         //
-        // Each lane owns a CONTIGUOUS run of U = ceil(units / 32) units, keeps the flags of its run in a 64-bit register
-        // (4 bits per unit), and the queue positions come from ONE warp prefix sum of the per-lane counts per cell --
-        // not from four ballots per 32 units: on B200 VOTE and POPC issue at 16 lanes/clk/SM, a quarter of the ALU
-        // rate (tools/pipe_probe.cu, profiles/r02_pipe_probe.txt), and the ballot form spent 12 of them per 128 pixels.
-        // The queue order (lane, unit, pixel) differs from raster order; nothing downstream depends on it.
+        // Lane = tile row, step = unit column: every lane walks along ITS row, keeps the flags of the row in a 64-bit
+        // register (4 bits per unit) and slides the left / centre / right words through registers (3 loads per unit;
+        // with the odd word pitch of the tile the 32 rows of a step sit in 32 different banks: no replays).  The queue
+        // positions then come from ONE warp prefix sum of the per-lane counts -- not from four ballots per 32 units:
+        // on B200 VOTE and POPC issue at 16 lanes/clk/SM, a quarter of the ALU rate (tools/pipe_probe.cu,
+        // profiles/r02_pipe_probe.txt), and the ballot form spent 12 of them per 128 pixels.  Rows beyond the 32nd
+        // (cells up to 63 px high) go through a second round in linear unit order.  The queue order (row, unit, pixel
+        // for round A) is raster order; nothing downstream depends on it.
         const unsigned cadd = (unsigned)(128 - min(thr + 1, 128)) * 0x01010101u;
         const unsigned last_mask = (cw & 3) ? (0x80808080u >> (8 * (4 - (cw & 3)))) : 0x80808080u;  // ragged last unit of a row
+        // precheck of one unit from its five words: bit 7 of byte b set <=> pixel b passes
+        auto precheck = [&](unsigned cc, unsigned up, unsigned dn, unsigned lf, unsigned rt) -> unsigned {
+            const unsigned a0 = __vabsdiffu4(dn, cc), a8 = __vabsdiffu4(up, cc);
+            const unsigned a4 = __vabsdiffu4(rt, cc), a12 = __vabsdiffu4(lf, cc);
+            return ((a0 + cadd) | a0 | (a8 + cadd) | a8) & ((a4 + cadd) | a4 | (a12 + cadd) | a12);
+        };
         int qn = 0;
-        for (int ub = 0; ub < nunits; ub += 512) {  // 16 units per lane per round: one round unless the cell is > 512 units
-            const int nr = min(nunits - ub, 512);
-            const int U = (nr + 31) >> 5;
-            const int u0 = ub + lane * U, u_end = ub + nr;
+        const int rows_a = min(ch, 32), units_a = rows_a * nux;
+        for (int round = 0; round < 2; ++round) {
+            const int U = round == 0 ? nux : (nunits - units_a + 31) >> 5;  // steps of this round (<= 16: 64 flag bits)
+            if (U <= 0) break;
             unsigned wlo = 0, whi = 0;
-            for (int i = 0; i < U; ++i) {  // warp-uniform trip count; lanes past the end re-test the last unit with a zero mask
-                const int u = min(u0 + i, u_end - 1);
-                const int y = (int)(((unsigned)u * inv_nux) >> 20), j = u - y * nux;
-                unsigned cc, up, dn, lf, rt;
-                if (TMA) {  // arbitrary byte phase: every 4-pixel window is a funnel shift of two words
-                    const int bc = off + 4 * j;  // byte column of the unit's first pixel
-                    const uint32_t *r0 = tile32 + (y + 3) * tpw;
-                    const int wc = bc >> 2, sc = (bc & 3) * 8;
-                    cc = __funnelshift_r(r0[wc], r0[wc + 1], sc);
-                    up = __funnelshift_r(r0[wc - 3 * tpw], r0[wc + 1 - 3 * tpw], sc);
-                    dn = __funnelshift_r(r0[wc + 3 * tpw], r0[wc + 1 + 3 * tpw], sc);
-                    const int bl = bc - 3, br = bc + 3;
-                    lf = __funnelshift_r(r0[bl >> 2], r0[(bl >> 2) + 1], (bl & 3) * 8);
-                    rt = __funnelshift_r(r0[br >> 2], r0[(br >> 2) + 1], (br & 3) * 8);
-                } else {
-                    const uint32_t *row = tile32 + (y + 3) * tpw + j;  // row[0] = left word, row[1] = centre, row[2] = right
-                    cc = row[1];
-                    dn = row[1 + 3 * tpw]; up = row[1 - 3 * tpw];
-                    rt = __funnelshift_r(cc, row[2], 24);
-                    lf = __funnelshift_r(row[0], cc, 8);
+            if (round == 0 && !TMA) {
+                // rows past the cell repeat row 0 (same addresses as lane 0: a broadcast, not a bank conflict)
+                const uint32_t *row = tile32 + ((lane < rows_a ? lane : 0) + 3) * tpw;  // row[0] = left word of unit 0
+                const unsigned live = lane < rows_a ? 0x80808080u : 0u;
+                unsigned left = row[0], cc = row[1];
+                for (int j = 0; j < U; ++j) {
+                    const unsigned right = row[j + 2], dn = row[j + 1 + 3 * tpw], up = row[j + 1 - 3 * tpw];
+                    const unsigned rt = __funnelshift_r(cc, right, 24), lf = __funnelshift_r(left, cc, 8);
+                    const unsigned flags = precheck(cc, up, dn, lf, rt) & (j == U - 1 ? last_mask & live : live);
+                    left = cc; cc = right;
+                    // bits 7 / 15 / 23 / 31 -> one nibble pushed into the lane's 64-bit flag word: the multiply moves the
+                    // four bits to 28..31 (no two partial products meet there), two funnel shifts push them in
+                    const unsigned prod = flags * 0x00204081u;
+                    whi = __funnelshift_l(wlo, whi, 4);
+                    wlo = __funnelshift_l(prod, wlo, 4);
                 }
-                const unsigned a0 = __vabsdiffu4(dn, cc), a8 = __vabsdiffu4(up, cc);
-                const unsigned a4 = __vabsdiffu4(rt, cc), a12 = __vabsdiffu4(lf, cc);
-                const unsigned p08 = (a0 + cadd) | a0 | (a8 + cadd) | a8, p412 = (a4 + cadd) | a4 | (a12 + cadd) | a12;
-                const unsigned vm = u0 + i < u_end ? (j == nux - 1 ? last_mask : 0x80808080u) : 0u;
-                const unsigned flags = p08 & p412 & vm;  // bits 7 / 15 / 23 / 31
-                // -> one nibble, pushed into the lane's 64-bit flag word: the multiply moves the four bits to 28..31 (no
-                // two partial products meet there), two funnel shifts push them in
-                const unsigned prod = flags * 0x00204081u;
-                whi = __funnelshift_l(wlo, whi, 4);
-                wlo = __funnelshift_l(prod, wlo, 4);
+            } else {
+                // generic form (second round, TMA staging): unit = first + step * 32 + lane, index math per step
+                const int first = round == 0 ? 0 : units_a, total = round == 0 ? units_a : nunits;
+                for (int i = 0; i < U; ++i) {
+                    const int ur = round == 0 ? lane * nux + i : first + i * 32 + lane;
+                    const bool valid = round == 0 ? lane < rows_a : ur < total;
+                    const int u = valid ? ur : first + i;
+                    const int y = (int)(((unsigned)u * inv_nux) >> 20), j = u - y * nux;
+                    unsigned cc, up, dn, lf, rt;
+                    if (TMA) {  // arbitrary byte phase: every 4-pixel window is a funnel shift of two words
+                        const int bc = off + 4 * j;  // byte column of the unit's first pixel
+                        const uint32_t *r0 = tile32 + (y + 3) * tpw;
+                        const int wc = bc >> 2, sc = (bc & 3) * 8;
+                        cc = __funnelshift_r(r0[wc], r0[wc + 1], sc);
+                        up = __funnelshift_r(r0[wc - 3 * tpw], r0[wc + 1 - 3 * tpw], sc);
+                        dn = __funnelshift_r(r0[wc + 3 * tpw], r0[wc + 1 + 3 * tpw], sc);
+                        const int bl = bc - 3, br = bc + 3;
+                        lf = __funnelshift_r(r0[bl >> 2], r0[(bl >> 2) + 1], (bl & 3) * 8);
+                        rt = __funnelshift_r(r0[br >> 2], r0[(br >> 2) + 1], (br & 3) * 8);
+                    } else {
+                        const uint32_t *row = tile32 + (y + 3) * tpw + j;  // row[0] = left word, row[1] = centre, row[2] = right
+                        cc = row[1];
+                        dn = row[1 + 3 * tpw]; up = row[1 - 3 * tpw];
+                        rt = __funnelshift_r(cc, row[2], 24);
+                        lf = __funnelshift_r(row[0], cc, 8);
+                    }
+                    const unsigned vm = valid ? (j == nux - 1 ? last_mask : 0x80808080u) : 0u;
+                    const unsigned prod = (precheck(cc, up, dn, lf, rt) & vm) * 0x00204081u;
+                    whi = __funnelshift_l(wlo, whi, 4);
+                    wlo = __funnelshift_l(prod, wlo, 4);
+                }
             }
-            // queue positions: exclusive prefix sum of the lanes' counts (5 shuffles per cell)
+            // queue positions: exclusive prefix sum of the lanes' counts (5 shuffles per round)
             const int c_own = __popc(wlo) + __popc(whi);
             int incl = c_own;
 #pragma unroll
@@ -237,15 +265,18 @@ k_fast_cells(const CUtensorMap *__restrict__ maps, const LevelDev *__restrict__ 
             }
             uint16_t *qp = queue + qn + incl - c_own;
             qn += __shfl_sync(0xffffffffu, incl, 31);
-            // pop the nibbles (last unit first) and store the flagged pixels of the run
-            const int ystep = 64 - 4 * nux;
+            // pop the nibbles (last step first) and store the flagged pixels as (y << 6 | x)
             for (int i = U - 1; i >= 0; --i) {
                 const unsigned nib = wlo & 15u;
                 wlo = __funnelshift_r(wlo, whi, 4);
                 whi >>= 4;
-                const int u = u0 + i;
-                const int y = (int)(((unsigned)u * inv_nux) >> 20);
-                const int e0 = y * ystep + 4 * u;  // (y << 6) | (4 * j)
+                int e0;
+                if (round == 0) e0 = (lane << 6) + 4 * i;
+                else {
+                    const int u = units_a + i * 32 + lane;
+                    const int y = (int)(((unsigned)u * inv_nux) >> 20);
+                    e0 = y * (64 - 4 * nux) + 4 * u;  // (y << 6) | (4 * j)
+                }
                 if (nib & 1u) *qp++ = (uint16_t)e0;
                 if (nib & 2u) *qp++ = (uint16_t)(e0 + 1);
                 if (nib & 4u) *qp++ = (uint16_t)(e0 + 2);
@@ -341,7 +372,7 @@ k_fast_cells(const CUtensorMap *__restrict__ maps, const LevelDev *__restrict__ 
     }
 }
 
-template <bool DUMP, bool TMA>
+template <bool DUMP, bool TMA, int TP>
 static cudaError_t launch_fast_t(const CUtensorMap *maps, const LevelDev *d_levels, const CellEntry *d_cells, int n_cells,
                                  int n_levels, int *d_cand_count, int t_lo, int t_hi, const FastSmemCfg &cfg,
                                  int frame_base, int n_frames, uint8_t *d_dump, const long long *d_dump_off,
@@ -349,10 +380,10 @@ static cudaError_t launch_fast_t(const CUtensorMap *maps, const LevelDev *d_leve
     dim3 grid((n_cells + FAST_WARPS - 1) / FAST_WARPS, n_frames);
     const size_t smem = (size_t)cfg.warp_bytes * FAST_WARPS;
     if (smem > 48 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(k_fast_cells<DUMP, TMA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(k_fast_cells<DUMP, TMA, TP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
     }
-    return launch_pdl(k_fast_cells<DUMP, TMA>, grid, dim3(FAST_WARPS * 32), smem, st, maps, d_levels, d_cells, n_cells, n_levels,
+    return launch_pdl(k_fast_cells<DUMP, TMA, TP>, grid, dim3(FAST_WARPS * 32), smem, st, maps, d_levels, d_cells, n_cells, n_levels,
                       d_cand_count, t_lo, t_hi, cfg, frame_base, d_dump, d_dump_off);
 }
 
@@ -360,10 +391,20 @@ cudaError_t launch_fast(const void *tma_maps, const LevelDev *d_levels, const Ce
                         int n_levels, int *d_cand_count, int t_lo, int t_hi, const FastSmemCfg &cfg, int frame_base,
                         int n_frames, cudaStream_t st) {
     if (tma_maps)
-        return launch_fast_t<false, true>(static_cast<const CUtensorMap *>(tma_maps), d_levels, d_cells, n_cells, n_levels,
-                                          d_cand_count, t_lo, t_hi, cfg, frame_base, n_frames, nullptr, nullptr, st);
-    return launch_fast_t<false, false>(nullptr, d_levels, d_cells, n_cells, n_levels, d_cand_count, t_lo, t_hi, cfg,
-                                       frame_base, n_frames, nullptr, nullptr, st);
+        return launch_fast_t<false, true, 0>(static_cast<const CUtensorMap *>(tma_maps), d_levels, d_cells, n_cells, n_levels,
+                                             d_cand_count, t_lo, t_hi, cfg, frame_base, n_frames, nullptr, nullptr, st);
+#define ORBB_FAST_TP(P)                                                                                                     \
+    case P: return launch_fast_t<false, false, P>(nullptr, d_levels, d_cells, n_cells, n_levels, d_cand_count, t_lo, t_hi, cfg, \
+                                                  frame_base, n_frames, nullptr, nullptr, st)
+    if (cfg.score_pitch == cfg.tile_pitch - 8) {
+        switch (cfg.tile_pitch) {  // the pitches orbb_create produces: round_up(widest cell + 12, 4) | 4
+            ORBB_FAST_TP(44); ORBB_FAST_TP(52); ORBB_FAST_TP(60); ORBB_FAST_TP(68); ORBB_FAST_TP(76);
+            default: break;
+        }
+    }
+#undef ORBB_FAST_TP
+    return launch_fast_t<false, false, 0>(nullptr, d_levels, d_cells, n_cells, n_levels, d_cand_count, t_lo, t_hi, cfg,
+                                          frame_base, n_frames, nullptr, nullptr, st);
 }
 
 // parity-test variant: one frame, dumps the per-pixel score (m > t_lo ? m : 0) of every cell
@@ -371,10 +412,10 @@ cudaError_t launch_fast_dump(const void *tma_maps, const LevelDev *d_levels, con
                              int n_levels, int t_lo, int t_hi, const FastSmemCfg &cfg, int frame, uint8_t *d_dump,
                              const long long *d_dump_off, cudaStream_t st) {
     if (tma_maps)
-        return launch_fast_t<true, true>(static_cast<const CUtensorMap *>(tma_maps), d_levels, d_cells, n_cells, n_levels,
-                                         nullptr, t_lo, t_hi, cfg, frame, 1, d_dump, d_dump_off, st);
-    return launch_fast_t<true, false>(nullptr, d_levels, d_cells, n_cells, n_levels, nullptr, t_lo, t_hi, cfg, frame, 1,
-                                      d_dump, d_dump_off, st);
+        return launch_fast_t<true, true, 0>(static_cast<const CUtensorMap *>(tma_maps), d_levels, d_cells, n_cells, n_levels,
+                                            nullptr, t_lo, t_hi, cfg, frame, 1, d_dump, d_dump_off, st);
+    return launch_fast_t<true, false, 0>(nullptr, d_levels, d_cells, n_cells, n_levels, nullptr, t_lo, t_hi, cfg, frame, 1,
+                                         d_dump, d_dump_off, st);
 }
 
 // Build the per-level tensor maps (driver entry point fetched through the runtime: no -lcuda needed).

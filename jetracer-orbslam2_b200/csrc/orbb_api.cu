@@ -450,7 +450,7 @@ extern "C" int orbb_create(orbb_handle **out, const orbb_params *params, int wid
     h->fcfg.tile_pitch = (int)round_up(max_cw + 12, 4) | 4;  // odd number of words: rows never share a bank pattern
     h->fcfg.tma_pitch = (int)round_up(max_cw + 10 + 15 + 4, 16);  // 16-byte aligned box start: up to 15 bytes of phase
     h->fcfg.tile_rows = max_ch + 6;
-    h->fcfg.score_pitch = (int)round_up(max_cw + 2, 4);
+    h->fcfg.score_pitch = h->fcfg.tile_pitch - 8;  // >= max_cw + 4, multiple of 4; tied to the tile pitch (k_fast_cells<.., TP>)
     h->fcfg.score_rows = max_ch + 2;
     h->fcfg.queue_len = (int)round_up((size_t)max_cw * max_ch, 8);
     // TMA staging of the FAST windows is opt-in (ORBB_FAST_TMA=1): measured on B200 it is not faster than the
