@@ -382,6 +382,9 @@ long long orbb_slam_frame_to_bson(int32_t ax, int32_t ay, int32_t az, int32_t wi
 
 /* ---------------------------------------------------------------- debug / parity access
  * Download stage outputs of frame `frame` of the last batch to HOST memory (synchronises). */
+/* fill every stateless scratch buffer of the handle with `value` (0..255): extraction results must not change
+ * (stand-in for compute-sanitizer initcheck where the sanitizer cannot run).  Synchronises. */
+int orbb_debug_poison(orbb_handle *h, int value);
 /* measured POPC issue rate (lanes per clock per SM) of this device: the matcher's roofline denominator */
 int orbb_debug_popc_rate(orbb_handle *h, double *popc_per_clk_per_sm);
 /* padded level, contiguous (w+38) x (h+38) */

@@ -89,7 +89,9 @@ k_fast_cells(const CUtensorMap *__restrict__ maps, const LevelDev *__restrict__ 
     // cell's first tested pixel sits at byte 4 of each row and groups of 4 pixels are whole 32-bit words.
     // Global loads stay aligned (ROI rows are 16-byte aligned); a funnel shift moves the bytes into place.
     // tested pixel x lives at tile byte column x + off.  Manual staging re-aligns (off = 4); the TMA box must
-    // start on a 16-byte boundary, so its rows keep a byte phase of (x0 - 4) & 15 that phase 1 absorbs.
+    // start on a 16-byte boundary, so its rows keep a byte phase of (x0 - 4) & 15 that phase 1 absorbs.  (Measured
+    // in round 2: a box whose first coordinate is NOT a multiple of 16 bytes -- which would let TMA do the
+    // re-alignment -- makes the copy fault with "an illegal instruction was encountered".)
     const int off = TMA ? 4 + ((c.x0 - 4) & 15) : 4;
     if (TMA) {
         // One bulk-tensor copy per cell: the TMA unit fetches the (box_w x box_h) window at byte column

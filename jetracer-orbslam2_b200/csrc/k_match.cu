@@ -31,6 +31,11 @@ __device__ __forceinline__ void best2_update(Best2 &b, int d, int idx) {
 // of the integer rate (16 lanes/clk/SM), so 8 POPC per pair bound the plain form.  x0..x6 are folded by
 // (sum, carry) = (a^b^c, maj(a,b,c)) -- one LOP3 each -- into two weight-1 words and three weight-2 words:
 // 5 POPC + 6 LOP3 instead of 8 POPC, which balances the POPC pipe against the integer pipe.
+// FOLD4 adds a fourth adder (4 POPC + 8 LOP3).  POPC issues at 16 lanes/clk/SM and LOP3 at 64 (tools/pipe_probe.cu), so
+// which form wins depends on what else the caller puts on the ALU pipe: measured on B200, 257 k x 50 k, the 1-NN kernel
+// (one min per pair) runs at 906 Gpairs/s with 4 POPC vs 884 with 5; the 2-NN kernel (three min/max per pair) at 828
+// vs 848 -- so k_match<1> folds four times and k_match<2> three.
+template <bool FOLD4 = false>
 __device__ __forceinline__ int hamming256(const uint4 &qa, const uint4 &qb, const uint4 &a, const uint4 &b) {
     const unsigned x0 = qa.x ^ a.x, x1 = qa.y ^ a.y, x2 = qa.z ^ a.z, x3 = qa.w ^ a.w;
     const unsigned x4 = qb.x ^ b.x, x5 = qb.y ^ b.y, x6 = qb.z ^ b.z, x7 = qb.w ^ b.w;
@@ -41,7 +46,12 @@ __device__ __forceinline__ int hamming256(const uint4 &qa, const uint4 &qb, cons
     asm("lop3.b32 %0, %1, %2, %3, 0xE8;" : "=r"(cb) : "r"(x3), "r"(x4), "r"(x5));
     asm("lop3.b32 %0, %1, %2, %3, 0x96;" : "=r"(sc) : "r"(sa), "r"(sb), "r"(x6));
     asm("lop3.b32 %0, %1, %2, %3, 0xE8;" : "=r"(cc) : "r"(sa), "r"(sb), "r"(x6));
-    return __popc(sc) + __popc(x7) + 2 * (__popc(ca) + __popc(cb) + __popc(cc));
+    if (!FOLD4) return __popc(sc) + __popc(x7) + 2 * (__popc(ca) + __popc(cb) + __popc(cc));
+    // the fourth adder folds the three weight-2 words into one weight-2 and one weight-4 word
+    unsigned st, ct;
+    asm("lop3.b32 %0, %1, %2, %3, 0x96;" : "=r"(st) : "r"(ca), "r"(cb), "r"(cc));
+    asm("lop3.b32 %0, %1, %2, %3, 0xE8;" : "=r"(ct) : "r"(ca), "r"(cb), "r"(cc));
+    return __popc(sc) + __popc(x7) + 2 * __popc(st) + 4 * __popc(ct);
 }
 
 // running two smallest (distance, index) pairs as packed keys (distance << 22 | index relative to the split's first
@@ -76,6 +86,9 @@ k_match(const uint4 *__restrict__ query, const uint4 *__restrict__ train, const 
     const int per = (nt + n_split - 1) / n_split;
     const int ts = min(nt, (int)blockIdx.y * per), te = min(nt, ts + per);
 
+    // 2^22 as a value ptxas cannot see through (n_split <= 64): with the literal it turns distance * 2^22 + index into
+    // SHL + LOP3 or LEA, which issue to the ALU pipe -- the pipe this kernel saturates; IMAD goes to the FMA pipe
+    const unsigned m22 = 0x400000u + ((unsigned)n_split >> 30);
     uint4 qa[MATCH_QPT], qb[MATCH_QPT];
     Best2K best[MATCH_QPT];
 #pragma unroll
@@ -97,7 +110,7 @@ k_match(const uint4 *__restrict__ query, const uint4 *__restrict__ train, const 
             const unsigned rel = (unsigned)(tb + t - ts);  // < 2^22: the host picks n_split accordingly
 #pragma unroll
             for (int j = 0; j < MATCH_QPT; ++j) {
-                const unsigned key = ((unsigned)hamming256(qa[j], qb[j], a, b) << 22) | rel;
+                const unsigned key = (unsigned)hamming256<K == 1>(qa[j], qb[j], a, b) * m22 + rel;  // one IMAD (fma pipe); the fields do not overlap
                 if (K == 1) best[j].k1 = min(best[j].k1, key);
                 else best2k_update(best[j], key);
             }

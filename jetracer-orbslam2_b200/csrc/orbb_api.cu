@@ -1118,6 +1118,40 @@ extern "C" int orbb_rgb_to_grayscale(orbb_handle *h, const uint8_t *d_rgb, size_
 }
 
 // ---------------------------------------------------------------- debug / parity access
+// Overwrites every scratch buffer of the handle that carries no state between calls (pyramid levels incl. their
+// unused pad bytes, blurred levels, candidate lists, quadtree sort / selection scratch, host-path staging, matcher and
+// stereo scratch) with `value`.  A following extraction must give the same bytes as before: the stand-in for
+// compute-sanitizer's initcheck on pools where the sanitizer is not available (tests/test_gpu_contract.py).  The
+// quadtree cell tables, the candidate / selection counters and the chain counters are state (zero / monotonic by
+// contract) and are left alone.  Synchronises.
+extern "C" int orbb_debug_poison(orbb_handle *h, int value) {
+    if (!h) return ORBB_ERR_INVALID;
+    CK(h, cudaSetDevice(h->device));
+    CK(h, cudaDeviceSynchronize());
+    const size_t B = (size_t)h->max_batch;
+    for (int l = 0; l < h->nlevels; ++l) {
+        LevelDev &L = h->lv[l];
+        CK(h, cudaMemset(L.img, value, (size_t)L.frame_stride * B));
+        CK(h, cudaMemset(L.blur, value, (size_t)L.blur_stride * B));
+        CK(h, cudaMemset(L.cand, value, sizeof(uint32_t) * (size_t)L.cand_cap * B));
+        CK(h, cudaMemset(L.kv_a, value, sizeof(uint2) * (size_t)L.cand_cap * B));
+        CK(h, cudaMemset(L.kv_b, value, sizeof(uint2) * (size_t)L.cand_cap * B));
+        CK(h, cudaMemset(L.sd, value, (size_t)L.cand_cap * B));
+        CK(h, cudaMemset(L.sel, value, sizeof(uint32_t) * (size_t)L.sel_cap * B));
+    }
+    for (int i = 0; i < 2; ++i) {
+        CK(h, cudaMemset(h->d_in2[i], value, (size_t)h->w * h->h * B));
+        CK(h, cudaMemset(h->d_kp2[i], value, sizeof(orbb_keypoint) * (size_t)h->max_kp * B));
+        CK(h, cudaMemset(h->d_desc2[i], value, (size_t)h->max_kp * B * 32));
+        CK(h, cudaMemset(h->d_counts2[i], value, sizeof(int) * B));
+    }
+    CK(h, cudaMemset(h->d_partial, value, sizeof(int4) * h->partial_cap));
+    CK(h, cudaMemset(h->d_stereo_sad, value, sizeof(int) * h->stereo_cap));
+    CK(h, cudaMemset(h->d_dump, value, (size_t)h->dump_off[h->nlevels]));
+    CK(h, cudaDeviceSynchronize());
+    return ORBB_OK;
+}
+
 // POPC lanes per clock per SM, measured: one 1024-thread CTA per SM running register-only POPC chains (k_popc_rate);
 // the median over the CTAs' own cycle counts is clock independent.  Synchronises.
 extern "C" int orbb_debug_popc_rate(orbb_handle *h, double *popc_per_clk_per_sm) {

@@ -35,7 +35,7 @@ EXPORTS = [
     "orbb_detect", "orbb_detect_fast", "orbb_detect_distribute", "orbb_gaussian_blur", "orbb_compute_angle_and_orb",
     "orbb_compute_fast_angle", "orbb_calc_orb", "orbb_detect_export", "orbb_match_knn", "orbb_match_knn_batch",
     "orbb_match_knn_segmented", "orbb_match_windowed", "orbb_debug_get_padded", "orbb_debug_get_blurred", "orbb_debug_get_scores",
-    "orbb_debug_popc_rate", "orbb_debug_get_candidates", "orbb_debug_get_selected", "orbb_debug_distribute",
+    "orbb_debug_popc_rate", "orbb_debug_poison", "orbb_debug_get_candidates", "orbb_debug_get_selected", "orbb_debug_distribute",
     "orbb_align_depth_to_other", "orbb_keypoint_pixel_to_point", "orbb_reproject_points", "orbb_match_windowed_batch",
     "orbb_rgb_to_grayscale", "orbb_match_projection_batch", "orbb_compute_stereo_matches",
     "orbb_slam_frame_bson_size", "orbb_slam_frame_to_bson",
@@ -140,6 +140,7 @@ def load_library():
     L.orbb_match_knn_segmented.argtypes = [vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, f32, vp, vp, vp, vp]
     L.orbb_match_windowed.argtypes = [vp, vp, vp, i32, i32, vp, vp, i32, i32, f32, i32, vp, vp, vp, vp]
     L.orbb_debug_popc_rate.argtypes = [vp, C.POINTER(C.c_double)]
+    L.orbb_debug_poison.argtypes = [vp, i32]
     L.orbb_debug_get_padded.argtypes = [vp, i32, i32, vp]
     L.orbb_debug_get_blurred.argtypes = [vp, i32, i32, vp]
     L.orbb_debug_get_scores.argtypes = [vp, i32, i32, vp]
@@ -452,6 +453,10 @@ class ORBextractor:
             _dev_ptr(d_depth), _dev_ptr(d_nstereo) if d_nstereo is not None else C.c_void_p(0), _stream_ptr(stream)))
 
     # -- parity / debug access --------------------------------------------------------------
+    def debug_poison(self, value: int = 0xCD):
+        """fill the handle's stateless scratch with a byte pattern (results must not depend on it)"""
+        self._check(self._lib.orbb_debug_poison(self._h, value))
+
     def debug_popc_rate(self) -> float:
         """measured POPC lanes / clock / SM (register-only microbenchmark; synchronises)"""
         out = C.c_double(0)

@@ -385,3 +385,73 @@ def test_popc_rate_microbenchmark(orbb):
     r = ex.debug_popc_rate()
     assert 8.0 < r < 40.0, r
     ex.close()
+
+
+def test_results_do_not_depend_on_scratch_contents_or_touch_guards(orbb, oracle, synth):
+    """Stand-in for compute-sanitizer (closed on this GPU pool, see profiles/r02_sanitizer_unavailable.txt):
+      * initcheck: every stateless scratch buffer of the handle is filled with 0xCD / 0x00 / 0xFF before an extraction --
+        pyramid pad bytes, candidate lists, sort scratch, staging -- and the result must stay bit-identical;
+      * memcheck (writes): all output arrays sit between 64 KB guard bands that must come back untouched, for the
+        extractor, the matcher (all three forms) and the two-call angle / descriptor entry points;
+      * racecheck: the same batch is extracted 12 times, alternating batch sizes so different kernel variants and the
+        one-launch pyramid run, and every run must give the same bytes as the oracle-checked first one."""
+    import torch
+    w, h, nb = 424, 240, 6
+    frames = np.stack([synth.textured_frame(w, h, 7300 + i) for i in range(nb - 2)] + [synth.sparse_frame(w, h, 7), synth.low_contrast_frame(w, h, 8)])
+    ex = orbb.ORBextractor(600, 1.2, 6, 20, 7, width=w, height=h, max_batch=nb)
+    mk, G = ex.max_kp, 65536
+    st = torch.cuda.current_stream()
+
+    def guarded(nbytes, fill):
+        buf = torch.full((nbytes + 2 * G,), fill, dtype=torch.uint8, device="cuda")
+        return buf, buf[G:G + nbytes]
+
+    def guards_ok(buf, nbytes, fill):
+        return bool((buf[:G] == fill).all()) and bool((buf[G + nbytes:] == fill).all())
+
+    d_in = torch.from_numpy(frames).cuda()
+    bk, d_kp = guarded(nb * mk * 28, 0x5A)
+    bd, d_desc = guarded(nb * mk * 32, 0x5A)
+    bc, d_cnt8 = guarded(nb * 4, 0x5A)
+    d_cnt = d_cnt8.view(torch.int32)
+    ref = None
+    for rep, poison in enumerate([None, 0xCD, 0x00, 0xFF, 0xCD, None, 0x37, 0xFF, 0x00, 0xCD, None, 0x11]):
+        if poison is not None:
+            ex.debug_poison(poison)
+        n = nb if rep % 3 == 0 else (1 if rep % 3 == 1 else 3)  # 1 and 3 frames: the small-grid kernel variants
+        d_kp.fill_(0x5A); d_desc.fill_(0x5A); d_cnt8.fill_(0x5A)
+        ex.extract_batch_device(d_in, n, d_kp, d_desc, d_cnt, stream=st)
+        torch.cuda.synchronize()
+        assert guards_ok(bk, nb * mk * 28, 0x5A) and guards_ok(bd, nb * mk * 32, 0x5A) and guards_ok(bc, nb * 4, 0x5A)
+        cnt = d_cnt.cpu().numpy()[:n]
+        kp = d_kp.cpu().numpy().view(orbb.KEYPOINT_DTYPE).reshape(nb, mk)
+        desc = d_desc.cpu().numpy().reshape(nb, mk, 32)
+        if ref is None:
+            assert n == nb
+            o = oracle.Oracle(w, h, 600, 1.2, 6)
+            for f in range(nb):
+                okp, od = canon(*o.extract(frames[f]))
+                gk, gd = canon(kp[f, :cnt[f]], desc[f, :cnt[f]])
+                assert gk.tobytes() == okp.tobytes() and np.array_equal(gd, od)
+            ref = (cnt.copy(), kp.copy(), desc.copy())
+        for f in range(n):
+            c = int(ref[0][f])
+            assert cnt[f] == c and kp[f, :c].tobytes() == ref[1][f, :c].tobytes() and desc[f, :c].tobytes() == ref[2][f, :c].tobytes(), (rep, f)
+            # rows past the count are never written
+            assert (d_desc.view(nb, mk, 32)[f, c:] == 0x5A).all()
+    # matcher outputs between guards (plain, batch, segmented, windowed)
+    nq = int(ref[0][0])
+    q = torch.from_numpy(ref[2][0, :nq].copy()).cuda()
+    t = torch.from_numpy(ref[2][1, :int(ref[0][1])].copy()).cuda()
+    bi, d_idx8 = guarded(nb * mk * 8, 0xA5); bdst, d_dist8 = guarded(nb * mk * 8, 0xA5); ba, d_acc = guarded(nb * mk, 0xA5)
+    d_idx, d_dist = d_idx8.view(torch.int32).view(-1, 2), d_dist8.view(torch.int32).view(-1, 2)
+    ex.debug_poison(0xEE)
+    ex.match_keypoints(q, nq, t, t.shape[0], d_idx, d_dist, d_acc, None, k=2, stream=st)
+    ex.extract_batch_device(d_in, nb, d_kp, d_desc, d_cnt, stream=st)
+    ex.match_keypoints_batch(d_desc.view(nb, mk, 32), d_cnt, nb, t, t.shape[0], d_idx, d_dist, d_acc, None, k=1, stream=st)
+    torch.cuda.synchronize()
+    assert guards_ok(bi, nb * mk * 8, 0xA5) and guards_ok(bdst, nb * mk * 8, 0xA5) and guards_ok(ba, nb * mk, 0xA5)
+    oi, od, _ = oracle.match_knn(ref[2][0, :nq], ref[2][1, :int(ref[0][1])], k=1)
+    got = d_idx.cpu().numpy().reshape(nb, mk, 2)[0, :nq, 0]
+    assert np.array_equal(got, oi[:, 0])
+    ex.close()
