@@ -372,6 +372,35 @@ def bench_reference_gpu_kernels(orbb, torch, device_index):
             "ours_orbslam2_8_levels_1200_kp_batch_64": ours(1200, NLEVELS, 64, 20)}
 
 
+def numa_bind(torch, local_rank):
+    """Pin this rank's host threads to the CPUs of its GPU's NUMA node BEFORE any pinned buffer is allocated (first
+    touch decides where the pages live): with 8 ranks copying 78.6 MB per step each, buffers that sit on the other
+    socket halve the H2D rate.  Returns what was found / done for the JSON line; a VM that hides the topology
+    (numa_node = -1, one node) leaves everything as it is."""
+    info = {"nodes": 0, "gpu_node": None, "bound_cpus": None}
+    try:
+        nodes = sorted(int(d[4:]) for d in os.listdir("/sys/devices/system/node") if d.startswith("node") and d[4:].isdigit())
+        info["nodes"] = len(nodes)
+        bus = torch.cuda.get_device_properties(local_rank).pci_bus_id
+        dom = torch.cuda.get_device_properties(local_rank).pci_domain_id
+        dev = torch.cuda.get_device_properties(local_rank).pci_device_id
+        path = f"/sys/bus/pci/devices/{dom:04x}:{bus:02x}:{dev:02x}.0/numa_node"
+        node = int(open(path).read().strip()) if os.path.exists(path) else -1
+        info["gpu_node"] = node
+        if node >= 0 and len(nodes) > 1:
+            cpus = set()
+            for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+                a, _, b = part.partition("-")
+                cpus.update(range(int(a), int(b or a) + 1))
+            cpus &= os.sched_getaffinity(0)
+            if cpus:
+                os.sched_setaffinity(0, cpus)
+                info["bound_cpus"] = len(cpus)
+    except Exception as e:  # topology files missing: report, never fail the bench
+        info["error"] = repr(e)[:80]
+    return info
+
+
 def parity_block(orbb, frames, sample, kp, desc, cnt):
     """The measured batch itself against the CPU oracle (north_star: bit-exact, except keypoints whose IC_Angle lands
     on a pattern-rotation rounding boundary: angle within 1e-3 rad and descriptor within 8 bits are 'tolerated' and
@@ -482,6 +511,12 @@ def bench_cfg5(orbb, torch, dist, rank, world, local_rank, reps, warmup):
         flips = np.random.default_rng(50_000).random((MAP_SIZE, 256)) < 0.05
         rows = rows ^ np.packbits(flips, axis=1, bitorder="little")
         d_map.copy_(torch.from_numpy(np.ascontiguousarray(rows)))
+    if world > 1:  # the first collective of a process sets up the NCCL channels (hundreds of ms): not the map's cost
+        warm = torch.zeros(1024, dtype=torch.uint8, device=dev)
+        sharding.broadcast_map(warm, src=0)
+        sharding.gather_fixed(warm.view(-1))
+        torch.cuda.synchronize()
+        dist.barrier()
     b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     b0.record(st)
     sharding.broadcast_map(d_map, src=0)
@@ -605,6 +640,7 @@ def main():
         raise SystemExit("bench.py needs a CUDA device: the product has no CPU fallback")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    numa = numa_bind(torch, local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
@@ -757,6 +793,22 @@ def main():
     torch.cuda.synchronize()
     h2d_gbs = 5 * h2d / (p0.elapsed_time(p1) * 1e-3) / 1e9
     sync_all()
+    # ... and the same with the step's D2H running against it (an e2e step moves both; on a host whose memory system,
+    # not the PCIe link, is the limit the two directions share one budget): 5 x (78.6 MB in || 16.3 MB out)
+    s2 = torch.cuda.Stream()
+    d_out_probe = torch.zeros(d2h, dtype=torch.uint8, device=dev)
+    pin_out_probe = torch.zeros(d2h, dtype=torch.uint8).pin_memory()
+    sync_all()
+    p0.record(st)
+    for _ in range(5):
+        d_sets[0].copy_(pin_frames[0], non_blocking=True)
+        with torch.cuda.stream(s2):
+            pin_out_probe.copy_(d_out_probe, non_blocking=True)
+    s2.synchronize()
+    p1.record(st)
+    torch.cuda.synchronize()
+    duplex_steps_per_s = 5 / (p0.elapsed_time(p1) * 1e-3)
+    sync_all()
 
     # ---- sustained leg: >= args.sustain_s seconds of the device-resident call, NVML clock / power sampled throughout
     sustained = None
@@ -806,12 +858,13 @@ def main():
     if rank == 0 and world == 1 and not args.no_refgpu:
         refgpu = bench_reference_gpu_kernels(orbb, torch, local_rank)
 
-    t = torch.tensor([total_ms, e2e_ms, match_ms, e2e_sync_ms, 1.0 / h2d_gbs] + per_step_ms, dtype=torch.float64, device=dev)
+    t = torch.tensor([total_ms, e2e_ms, match_ms, e2e_sync_ms, 1.0 / h2d_gbs, 1.0 / duplex_steps_per_s] + per_step_ms,
+                     dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     tl = [float(v) for v in t.tolist()]
-    total_ms, e2e_ms, match_ms_max, e2e_sync_ms, inv_h2d = tl[:5]
-    per_step_ms = tl[5:]
+    total_ms, e2e_ms, match_ms_max, e2e_sync_ms, inv_h2d, inv_duplex = tl[:6]
+    per_step_ms = tl[6:]
     h2d_slowest = 1.0 / inv_h2d
     agg = torch.tensor([h2d_gbs, float(counts.sum())], dtype=torch.float64, device=dev)
     if world > 1:
@@ -857,8 +910,12 @@ def main():
                     "h2d_concurrent_gbs_per_gpu_slowest": h2d_slowest, "h2d_concurrent_gbs_aggregate": h2d_aggregate,
                     "h2d_bound_fps": h2d_aggregate * 1e9 / (W * H),
                     "frac_of_h2d_bound": e2e_fps / (h2d_aggregate * 1e9 / (W * H)),
+                    "copy_bound_fps": B * world / inv_duplex, "frac_of_copy_bound": e2e_fps / (B * world / inv_duplex),
+                    "copy_bound_what": "one step's H2D (78.6 MB) and D2H (16.3 MB) copies issued together on two streams, all "
+                                       "ranks at once, slowest rank: what the host <-> device path of this box sustains",
                     "h2d_what": "pinned-host -> device copies of one 78.6 MB batch, all ranks copying at the same time "
-                                "(barrier-aligned), 5 repeats"},
+                                "(barrier-aligned), 5 repeats",
+                    "numa_rank0": numa, "host_cpus": os.cpu_count()},
             "gpu_launches": gpu_launches,
             "roofline": {"bound": "hbm", "kernel": "k_fast_cells", "achieved": achieved, "peak": hbm_peak,
                          "unit": "GB/s", "frac": achieved / hbm_peak,

@@ -119,46 +119,50 @@ k_fast_cells(const CUtensorMap *__restrict__ maps, const LevelDev *__restrict__ 
             asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0; selp.u32 %0, 1, 0, p; }"
                          : "=r"(done) : "r"(bar) : "memory");
     } else {
-        // 128-bit staging WITH re-alignment: a lane loads the two aligned 16-byte chunks around four output words
-        // (ROI rows are 128-byte aligned by layout), forms the words with funnel shifts -- the word offset of the
-        // window inside its first chunk is uniform per cell, so the four variants are a uniform switch -- and writes
-        // them to the tile.  10 instructions per 16 pixels instead of 16.
+        // 128-bit staging WITH re-alignment.  Each lane loads ONE aligned 16-byte chunk of a window row (ROI rows are
+        // 128-byte aligned by layout) -- 4 lanes per row, 8 when a row spans more than four chunks -- and gets the
+        // chunk to its right from the next lane with four shuffles; the output words are funnel shifts of the two
+        // (the word offset of the window inside its first chunk is uniform per cell, so the four variants are a
+        // uniform switch).  Round 1 loaded both chunks per lane: every chunk travelled twice through the LSU data
+        // pipe, which is what bounds this kernel (profiles/r02_k_fast_cells_wavefronts.txt); a shuffle is one
+        // conflict-free wavefront.
         const int gx = c.x0 - 4, xa16 = gx & ~15, wo = (gx - xa16) >> 2, sh = (gx & 3) * 8;
         const int nwords = (cw + 7 + 3) >> 2, ng = (nwords + 3) >> 2;  // output words per row, 4-word groups per row
-        const int nrows = ch + 6, nitems = nrows * ng;
-        const uint8_t *src = L.img + (size_t)frame * L.frame_stride + (size_t)(ORBB_BORDER + c.y0 - 3) * L.pitch + ORBB_ROI_X0 + xa16;
-        const int row_left = L.pitch - (ORBB_ROI_X0 + xa16);          // bytes from the first chunk to the end of the padded row
-        const unsigned inv_ng = (1u << 16) / (unsigned)ng + 1u;       // exact i / ng for i < 2^10, ng <= 5
-        for (int i0 = 0; i0 < nitems; i0 += 64) {                     // two items (four 128-bit loads) in flight per lane
-            uint4 a[2], b[2];
-            int r[2], g[2];
+        const int nrows = ch + 6;
+        const int lps = ng + 1 <= 4 ? 2 : 3, rpi = 32 >> lps;        // log2(lanes per row), rows per step
+        const int g = lane & ((1 << lps) - 1), rl = lane >> lps;
+        const uint8_t *src = L.img + (size_t)frame * L.frame_stride + (size_t)(ORBB_BORDER + c.y0 - 3) * L.pitch + ORBB_ROI_X0 + xa16 + 16 * g;
+        const bool in_row = 16 * g + 16 <= L.pitch - (ORBB_ROI_X0 + xa16);  // never read past the padded row
+        for (int r0 = 0; r0 < nrows; r0 += 2 * rpi) {                 // two rows (two 128-bit loads) in flight per lane
+            uint4 a[2];
 #pragma unroll
             for (int u = 0; u < 2; ++u) {
-                const int i = min(i0 + 32 * u + lane, nitems - 1);
-                r[u] = (int)(((unsigned)i * inv_ng) >> 16); g[u] = i - r[u] * ng;
-                const uint4 *p = reinterpret_cast<const uint4 *>(src + (size_t)r[u] * L.pitch + 16 * g[u]);
-                a[u] = __ldg(p);
-                b[u] = 16 * g[u] + 32 <= row_left ? __ldg(p + 1) : make_uint4(0u, 0u, 0u, 0u);  // never past the row
+                const int r = min(r0 + u * rpi + rl, nrows - 1);
+                a[u] = in_row ? __ldg(reinterpret_cast<const uint4 *>(src + (size_t)r * L.pitch)) : make_uint4(0u, 0u, 0u, 0u);
             }
 #pragma unroll
             for (int u = 0; u < 2; ++u) {
+                uint4 bq;  // the chunk to the right: lane + 1 (the last lane of a row group produces no output)
+                bq.x = __shfl_down_sync(0xffffffffu, a[u].x, 1); bq.y = __shfl_down_sync(0xffffffffu, a[u].y, 1);
+                bq.z = __shfl_down_sync(0xffffffffu, a[u].z, 1); bq.w = __shfl_down_sync(0xffffffffu, a[u].w, 1);
                 uint4 o;
                 switch (wo) {  // uniform per cell
                     case 0: o = make_uint4(__funnelshift_r(a[u].x, a[u].y, sh), __funnelshift_r(a[u].y, a[u].z, sh),
-                                           __funnelshift_r(a[u].z, a[u].w, sh), __funnelshift_r(a[u].w, b[u].x, sh)); break;
+                                           __funnelshift_r(a[u].z, a[u].w, sh), __funnelshift_r(a[u].w, bq.x, sh)); break;
                     case 1: o = make_uint4(__funnelshift_r(a[u].y, a[u].z, sh), __funnelshift_r(a[u].z, a[u].w, sh),
-                                           __funnelshift_r(a[u].w, b[u].x, sh), __funnelshift_r(b[u].x, b[u].y, sh)); break;
-                    case 2: o = make_uint4(__funnelshift_r(a[u].z, a[u].w, sh), __funnelshift_r(a[u].w, b[u].x, sh),
-                                           __funnelshift_r(b[u].x, b[u].y, sh), __funnelshift_r(b[u].y, b[u].z, sh)); break;
-                    default: o = make_uint4(__funnelshift_r(a[u].w, b[u].x, sh), __funnelshift_r(b[u].x, b[u].y, sh),
-                                            __funnelshift_r(b[u].y, b[u].z, sh), __funnelshift_r(b[u].z, b[u].w, sh)); break;
+                                           __funnelshift_r(a[u].w, bq.x, sh), __funnelshift_r(bq.x, bq.y, sh)); break;
+                    case 2: o = make_uint4(__funnelshift_r(a[u].z, a[u].w, sh), __funnelshift_r(a[u].w, bq.x, sh),
+                                           __funnelshift_r(bq.x, bq.y, sh), __funnelshift_r(bq.y, bq.z, sh)); break;
+                    default: o = make_uint4(__funnelshift_r(a[u].w, bq.x, sh), __funnelshift_r(bq.x, bq.y, sh),
+                                            __funnelshift_r(bq.y, bq.z, sh), __funnelshift_r(bq.z, bq.w, sh)); break;
                 }
                 // four 32-bit stores: the tile keeps an odd word pitch, so the byte loads of the arc score (pixels
                 // of many rows in one warp instruction) spread over all banks; a 16-byte pitch would fold rows 8
                 // apart onto the same banks
-                if (i0 + 32 * u + lane < nitems) {
-                    uint32_t *t = reinterpret_cast<uint32_t *>(tile + r[u] * tp) + 4 * g[u];
-                    const int left = tpw - 4 * g[u];
+                const int r = r0 + u * rpi + rl;
+                if (r < nrows && g < ng) {
+                    uint32_t *t = reinterpret_cast<uint32_t *>(tile + r * tp) + 4 * g;
+                    const int left = tpw - 4 * g;
                     t[0] = o.x;
                     if (left > 1) t[1] = o.y;
                     if (left > 2) t[2] = o.z;

@@ -246,6 +246,148 @@ __global__ void __launch_bounds__(32 * RS_ROWS) k_resize_rows(const ResizeArgs A
     }
 }
 
+// ---- several levels per launch for SMALL batches (a lone frame is the reference's operating mode).  A frame's
+// per-level kernels are each shorter than a launch gap (4-5 us per level for ~1 us of work, even as programmatic
+// dependents: every level costs a full L2 round trip chain).  Here a CTA owns a tile of the FIRST level of a group of
+// up to PF_GROUP levels and derives its share of every level of the group in shared memory: the source window is
+// staged once, level l+1 is computed from the level-l tile that is still in shared memory, and only the pixels the
+// CTA owns are written out.  The halo a tile needs from its neighbours is recomputed, not exchanged (no inter-CTA
+// synchronisation): 20-60 % more pixel operations, which a lone frame can afford (most SMs idle otherwise) and a
+// large batch cannot -- large batches keep the per-level kernels above.  Every pixel value is the same integer
+// formula whoever computes it, so the output is identical.  x coordinates are in "c" units: c = padded column + 1,
+// so that c = 0 is byte 12 of a padded row and aligned 4-byte words are c = 4i .. 4i+3 (same grouping as k_resize_rows).
+#define PF_THREADS 1024  // the per-warp row loops are latency bound: 32 warps per tile, one or two rows each
+#define PF_WARPS (PF_THREADS / 32)
+__global__ void __launch_bounds__(PF_THREADS) k_pyramid_fused(const uint8_t *__restrict__ in, size_t in_pitch, size_t in_stride,
+                                                       const LevelDev *__restrict__ levels, int g0, int ng,
+                                                       const PfTile *__restrict__ tiles, int frame_base) {
+    extern __shared__ __align__(16) uint8_t pf_smem[];
+    pdl_trigger();
+    const PfTile &T = tiles[blockIdx.x];  // read through the pointer: the per-level arrays are indexed at run time
+    const int frame = blockIdx.y + frame_base, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    // Shared memory: [row tables][column tables][source window][level tiles ...].  The tables hold, for every row /
+    // column this CTA computes on every level of the group, the source offsets (already relative to the source tile
+    // in shared memory) and the fixed-point weights -- loaded ONCE, in parallel with the source window, so the
+    // per-pixel loops below contain no global load (a dependent table load per pixel made the first version of this
+    // kernel latency bound: 17 us per launch).
+    int ntab_r = 0, ntab_c = 0;
+    for (int k = 0; k < ng; ++k) { ntab_r += T.nh[k]; ntab_c += T.nw[k]; }
+    int4 *rowt = reinterpret_cast<int4 *>(pf_smem);                       // {offset of source row 0, of source row 1, b0, b1}
+    int2 *colt = reinterpret_cast<int2 *>(pf_smem + 16 * (size_t)ntab_r); // {offset of source column, a0 | a1 << 16}
+    const int sw = T.sw, sh = T.sh, sp = (sw + 3) & ~3;
+    uint8_t *S = pf_smem + 16 * (size_t)ntab_r + 8 * (size_t)ntab_c;      // source window (pitch = sw rounded up to 4)
+    // ---- tables (constant data: may be read before the grid dependency resolves)
+    {
+        int rbase = 0, cbase = 0, src_x0 = T.sx0, src_y0 = T.sy0, src_p = sp;
+        for (int k = 0; k < ng; ++k) {
+            const LevelDev &L = levels[g0 + k];
+            const int nw = T.nw[k], nh = T.nh[k], nx0 = T.nx0[k], ny0 = T.ny0[k];
+            const int lw = L.w, lh = L.h, pw = lw + 2 * ORBB_BORDER, ph = lh + 2 * ORBB_BORDER;
+            const bool copy0 = g0 == 0 && k == 0, area = L.area2x != 0;
+            for (int y = tid; y < nh; y += PF_THREADS) {
+                const int ry = reflect101(min(ny0 + y, ph - 1) - ORBB_BORDER, lh);
+                int4 e;
+                if (copy0) e = make_int4((ry - src_y0) * src_p, 0, 0, 0);
+                else {
+                    int r0, r1, b0 = 0, b1 = 0;
+                    if (area) { r0 = 2 * ry; r1 = r0 + 1; }
+                    else {
+                        const int2 rr = __ldg(&L.yrows[ry]);
+                        const short2 b = __ldg(&L.ybeta[ry]);
+                        r0 = rr.x; r1 = rr.y; b0 = b.x; b1 = b.y;
+                    }
+                    // source pixel (ROI col sx, ROI row r) of the level below: c = sx + BORDER + 1, padded row r + BORDER
+                    e = make_int4((r0 + ORBB_BORDER - src_y0) * src_p, (r1 + ORBB_BORDER - src_y0) * src_p, b0, b1);
+                }
+                rowt[rbase + y] = e;
+            }
+            for (int x = tid; x < nw; x += PF_THREADS) {
+                const int rx = reflect101(min(max(nx0 + x - 1, 0), pw - 1) - ORBB_BORDER, lw);
+                int2 e;
+                if (copy0) e = make_int2(rx - src_x0, 0);
+                else if (area) e = make_int2(2 * rx + ORBB_BORDER + 1 - src_x0, 1 | (1 << 16));
+                else {
+                    const short2 a = __ldg(&L.xalpha[rx]);
+                    e = make_int2(__ldg(&L.xofs[rx]) + ORBB_BORDER + 1 - src_x0, (int)(unsigned short)a.x | ((int)a.y << 16));
+                }
+                colt[cbase + x] = e;
+            }
+            rbase += nh; cbase += nw;
+            src_x0 = nx0; src_y0 = ny0; src_p = nw;  // the next level reads this level's tile
+        }
+    }
+    pdl_wait();  // group >= 1 reads a level written by the previous launch
+    // ---- source window: rows go to warps, columns to lanes (no index divisions)
+    if (g0 == 0) {
+        const uint8_t *src = in + (size_t)blockIdx.y * in_stride + (size_t)T.sy0 * in_pitch + T.sx0;
+        for (int y = warp; y < sh; y += PF_WARPS)
+            for (int x = lane; x < sw; x += 32) S[y * sp + x] = __ldg(src + (size_t)y * in_pitch + x);
+    } else {
+        const LevelDev &P = levels[g0 - 1];
+        const uint8_t *src = P.img + (size_t)frame * P.frame_stride + (size_t)T.sy0 * P.pitch + 12 + T.sx0;  // sx0 multiple of 4
+        const int wpr = sp >> 2;
+        for (int y = warp; y < sh; y += PF_WARPS)
+            for (int xw = lane; xw < wpr; xw += 32)
+                reinterpret_cast<uint32_t *>(S + y * sp)[xw] = __ldcg(reinterpret_cast<const uint32_t *>(src + (size_t)y * P.pitch) + xw);
+    }
+    __syncthreads();
+    const uint8_t *src_tile = S;
+    uint8_t *D = S + sp * sh;
+    int rbase = 0, cbase = 0;
+    for (int k = 0; k < ng; ++k) {
+        const LevelDev &L = levels[g0 + k];
+        const int nw = T.nw[k], nh = T.nh[k], nx0 = T.nx0[k], ny0 = T.ny0[k];  // nw, nx0 multiples of 4
+        const bool copy0 = g0 == 0 && k == 0, area = L.area2x != 0;
+        for (int y = warp; y < nh; y += PF_WARPS) {
+            const int4 rt = rowt[rbase + y];
+            uint8_t *drow = D + y * nw;
+            const uint8_t *p0 = src_tile + rt.x, *p1 = src_tile + rt.y;
+            if (copy0) {  // level 0: the frame itself + its reflect-101 border
+                for (int x = lane; x < nw; x += 32) drow[x] = p0[colt[cbase + x].x];
+            } else if (area) {
+                for (int x = lane; x < nw; x += 32) {
+                    const int sx = colt[cbase + x].x;
+                    drow[x] = (uint8_t)((p0[sx] + p0[sx + 1] + p1[sx] + p1[sx + 1] + 2) >> 2);
+                }
+            } else {
+                for (int x = lane; x < nw; x += 32) {
+                    const int2 ct = colt[cbase + x];
+                    const int a0 = (short)(ct.y & 0xffff), a1 = ct.y >> 16;
+                    const int t0 = p0[ct.x] * a0 + p0[ct.x + 1] * a1, t1 = p1[ct.x] * a0 + p1[ct.x + 1] * a1;
+                    drow[x] = (uint8_t)((((rt.z * (t0 >> 4)) >> 16) + ((rt.w * (t1 >> 4)) >> 16) + 2) >> 2);
+                }
+            }
+        }
+        __syncthreads();
+        // ---- write the owned rectangle, one aligned word per lane and step
+        {
+            uint8_t *dst = L.img + (size_t)frame * L.frame_stride + 12 + T.ox0[k];
+            const int owq = T.ow[k] >> 2, oh = T.oh[k], oy0 = T.oy0[k];
+            const uint8_t *drow0 = D + (oy0 - ny0) * nw + (T.ox0[k] - nx0);
+            for (int y = warp; y < oh; y += PF_WARPS)
+                for (int xw = lane; xw < owq; xw += 32)
+                    *reinterpret_cast<uint32_t *>(dst + (size_t)(oy0 + y) * L.pitch + 4 * xw) =
+                        *reinterpret_cast<const uint32_t *>(drow0 + y * nw + 4 * xw);
+        }
+        // the level just computed is the next level's source (it stays in shared memory; D moves on)
+        src_tile = D;
+        D += nw * nh;
+        rbase += nh; cbase += nw;
+    }
+}
+
+cudaError_t launch_pyramid_fused(const uint8_t *d_in, size_t pitch, size_t stride, const LevelDev *d_levels, int g0, int ng,
+                                 const void *d_tiles, int n_tiles, size_t smem, int frame_base, int n_frames, cudaStream_t st) {
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(k_pyramid_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+    }
+    return launch_pdl(k_pyramid_fused, dim3(n_tiles, n_frames), dim3(PF_THREADS), smem, st, d_in, pitch, stride, d_levels, g0, ng,
+                      static_cast<const PfTile *>(d_tiles), frame_base);
+}
+
+size_t pyramid_fused_tile_bytes() { return sizeof(PfTile); }
+
 // ---- 7x7 sigma=2 Gaussian of the ROI, OpenCV 4.13 fixed point: k = [18,34,48,56,48,34,18]/256 per
 // pass, dst = (V + 32768) >> 16.  Reads the padded level, so REFLECT_101 at the ROI
 // edge is already materialised by the border.

@@ -16,6 +16,8 @@
 namespace orbb {
 cudaError_t launch_level0(const uint8_t *, size_t, size_t, const LevelDev &, int, int, cudaStream_t);
 cudaError_t launch_resize(const LevelDev *, const LevelDev *, int, int, int, cudaStream_t);
+cudaError_t launch_pyramid_fused(const uint8_t *, size_t, size_t, const LevelDev *, int, int, const void *, int, size_t, int, int,
+                                 cudaStream_t);
 cudaError_t launch_blur(const LevelDev *, const LevelDev *, int, int, int, cudaStream_t);
 cudaError_t launch_fast(const void *, const LevelDev *, const CellEntry *, int, int, int *, int, int, const FastSmemCfg &,
                         int, int, cudaStream_t);
@@ -114,6 +116,15 @@ struct orbb_handle {
     long long graph_clock = 0;
     int use_graphs = 0;  // opt-in (ORBB_GRAPH=1): see orbb_extract_batch_device
     int last_host_frames = -1, last_host_latency = -1;  // chunk layout of the previous host submission
+    // several pyramid levels per launch (k_pyramid_fused), small batches only: per group of <= 4 levels a tile table
+    struct FusedGroup { int g0 = 0, ng = 0, n_tiles = 0; size_t smem = 0; PfTile *d_tiles = nullptr; };
+    std::vector<FusedGroup> fused;
+    // Opt-in (ORBB_FUSED_PYRAMID=<largest batch>, default 0 = never).  Measured on B200, one 848x480 frame, 8 levels:
+    // the two fused launches take 15.5 + 14.1 us against 2.9 + 7 x 4.4 us for level0 + seven resizes that overlap as
+    // programmatic dependents; the call latency is 79 us fused vs 65-68 us per level.  The tile pyramids are latency
+    // bound (dependent shared-memory loads, ~2 IPC per SM, 1.5-2.2 x redundant halo pixels), so fewer launches do not
+    // pay here; kept because it is bit-exact, tested, and the starting point if the per-pixel cost can be halved.
+    int fused_max_frames = 0;
     cudaEvent_t ev_fence = nullptr, ev_done[2] = {nullptr, nullptr};
     std::vector<cudaEvent_t> ev_in, ev_comp;
     std::vector<void *> allocs;
@@ -225,6 +236,111 @@ static void build_resize_tables(int sw, int sh, int dw, int dh, std::vector<int>
     }
 }
 
+// Tile tables of k_pyramid_fused.  Levels are grouped by ORBB_PF_GROUP; a tile owns a rectangle of the group's first
+// level, and on every further level the rectangle between the same scaled boundaries (rounded to multiples of 4 in c
+// units, so all stores are aligned words and the rectangles partition each padded level).  The rectangle a tile must
+// COMPUTE on level l is what it owns plus the source footprint of what it computes on level l+1.
+static bool build_fused_tiles(orbb_handle *h, const std::vector<std::vector<int>> &xofs, const std::vector<std::vector<int2>> &yrows,
+                              std::vector<std::vector<PfTile>> &out_tiles) {
+    const int nl = h->nlevels;
+    auto refl = [](int p, int len) { p = p < 0 ? -p : p; return p >= len ? 2 * len - 2 - p : p; };
+    for (int g0 = 0; g0 < nl; g0 += ORBB_PF_GROUP) {
+        const int ng = std::min(ORBB_PF_GROUP, nl - g0);
+        for (int k = (g0 == 0 ? 1 : 0); k < ng; ++k)
+            if (!h->lv[g0 + k].rs_ok && !h->lv[g0 + k].area2x) return false;  // scale step > 2: tiled fallback kernel only
+        const LevelDev &F = h->lv[g0];
+        // tile size on the group's first level: enough tiles to cover the SMs for ONE frame, at most ~8 KB of pixels each
+        const int cw_total = (F.w + 2 * ORBB_BORDER + 1 + 3) & ~3, ph_total = F.h + 2 * ORBB_BORDER;
+        static const int cand_tiles[4][2] = {{64, 32}, {64, 16}, {32, 16}, {32, 8}};
+        int tw = 16, th = 8;
+        for (const auto &c : cand_tiles)
+            if ((long long)((cw_total + c[0] - 1) / c[0]) * ((ph_total + c[1] - 1) / c[1]) >= 120) { tw = c[0]; th = c[1]; break; }
+        const int ntx = (cw_total + tw - 1) / tw, nty = (ph_total + th - 1) / th;
+        std::vector<PfTile> tiles;
+        size_t smem_max = 0;
+        for (int ty = 0; ty < nty; ++ty)
+            for (int tx = 0; tx < ntx; ++tx) {
+                PfTile T{};
+                int nx0[ORBB_PF_GROUP], nx1[ORBB_PF_GROUP], ny0[ORBB_PF_GROUP], ny1[ORBB_PF_GROUP];
+                for (int k = 0; k < ng; ++k) {  // owned rectangles: scaled tile boundaries
+                    const LevelDev &L = h->lv[g0 + k];
+                    const int cwl = (L.w + 2 * ORBB_BORDER + 1 + 3) & ~3, phl = L.h + 2 * ORBB_BORDER;
+                    auto bx = [&](int t) { return t >= ntx ? cwl : (int)(((long long)t * tw * cwl / cw_total) + 2) / 4 * 4; };
+                    auto by = [&](int t) { return t >= nty ? phl : (int)((long long)t * th * phl / ph_total); };
+                    T.ox0[k] = (short)bx(tx); T.ow[k] = (short)(bx(tx + 1) - bx(tx));
+                    T.oy0[k] = (short)by(ty); T.oh[k] = (short)(by(ty + 1) - by(ty));
+                }
+                for (int k = ng - 1; k >= 0; --k) {  // compute rectangles, last level first
+                    int x0 = T.ox0[k], x1 = T.ox0[k] + T.ow[k], y0 = T.oy0[k], y1 = T.oy0[k] + T.oh[k];
+                    if (k < ng - 1 && nx1[k + 1] > nx0[k + 1] && ny1[k + 1] > ny0[k + 1]) {
+                        const LevelDev &N = h->lv[g0 + k + 1];  // the level that reads level g0 + k
+                        const int pwn = N.w + 2 * ORBB_BORDER, phn = N.h + 2 * ORBB_BORDER;
+                        int fx0 = 1 << 30, fx1 = -1, fy0 = 1 << 30, fy1 = -1;
+                        for (int c = nx0[k + 1]; c < nx1[k + 1]; ++c) {
+                            const int rx = refl(std::min(std::max(c - 1, 0), pwn - 1) - ORBB_BORDER, N.w);
+                            const int sx = N.area2x ? 2 * rx : xofs[g0 + k + 1][rx];
+                            fx0 = std::min(fx0, sx + ORBB_BORDER + 1); fx1 = std::max(fx1, sx + ORBB_BORDER + 1 + 2);
+                        }
+                        for (int py = ny0[k + 1]; py < ny1[k + 1]; ++py) {
+                            const int ry = refl(std::min(py, phn - 1) - ORBB_BORDER, N.h);
+                            const int r0 = N.area2x ? 2 * ry : yrows[g0 + k + 1][ry].x, r1 = N.area2x ? 2 * ry + 1 : yrows[g0 + k + 1][ry].y;
+                            fy0 = std::min(fy0, std::min(r0, r1) + ORBB_BORDER); fy1 = std::max(fy1, std::max(r0, r1) + ORBB_BORDER + 1);
+                        }
+                        if (T.ow[k] <= 0 || T.oh[k] <= 0) { x0 = fx0; x1 = fx1; y0 = fy0; y1 = fy1; }
+                        else { x0 = std::min(x0, fx0); x1 = std::max(x1, fx1); y0 = std::min(y0, fy0); y1 = std::max(y1, fy1); }
+                    }
+                    nx0[k] = x0 & ~3; nx1[k] = (x1 + 3) & ~3; ny0[k] = y0; ny1[k] = y1;
+                    if (nx1[k] <= nx0[k] || ny1[k] <= ny0[k]) { nx1[k] = nx0[k]; ny1[k] = ny0[k]; }
+                    T.nx0[k] = (short)nx0[k]; T.nw[k] = (short)(nx1[k] - nx0[k]); T.ny0[k] = (short)ny0[k]; T.nh[k] = (short)(ny1[k] - ny0[k]);
+                }
+                // source window of the first level of the group
+                int sx0 = 1 << 30, sx1 = -1, sy0 = 1 << 30, sy1 = -1;
+                {
+                    const LevelDev &N = h->lv[g0];
+                    const int pwn = N.w + 2 * ORBB_BORDER, phn = N.h + 2 * ORBB_BORDER;
+                    for (int c = nx0[0]; c < nx1[0]; ++c) {
+                        const int rx = refl(std::min(std::max(c - 1, 0), pwn - 1) - ORBB_BORDER, N.w);
+                        if (g0 == 0) { sx0 = std::min(sx0, rx); sx1 = std::max(sx1, rx + 1); }
+                        else {
+                            const int sx = N.area2x ? 2 * rx : xofs[g0][rx];
+                            sx0 = std::min(sx0, sx + ORBB_BORDER + 1); sx1 = std::max(sx1, sx + ORBB_BORDER + 1 + 2);
+                        }
+                    }
+                    for (int py = ny0[0]; py < ny1[0]; ++py) {
+                        const int ry = refl(std::min(py, phn - 1) - ORBB_BORDER, N.h);
+                        if (g0 == 0) { sy0 = std::min(sy0, ry); sy1 = std::max(sy1, ry + 1); }
+                        else {
+                            const int r0 = N.area2x ? 2 * ry : yrows[g0][ry].x, r1 = N.area2x ? 2 * ry + 1 : yrows[g0][ry].y;
+                            sy0 = std::min(sy0, std::min(r0, r1) + ORBB_BORDER); sy1 = std::max(sy1, std::max(r0, r1) + ORBB_BORDER + 1);
+                        }
+                    }
+                    if (sx1 < 0 || sy1 < 0) { sx0 = sx1 = sy0 = sy1 = 0; }
+                    if (g0 > 0) { sx0 &= ~3; sx1 = (sx1 + 3) & ~3; }
+                }
+                T.sx0 = (short)sx0; T.sy0 = (short)sy0; T.sw = (short)(sx1 - sx0); T.sh = (short)(sy1 - sy0);
+                size_t bytes = (size_t)((T.sw + 3) & ~3) * T.sh;
+                for (int k = 0; k < ng; ++k) bytes += (size_t)T.nw[k] * T.nh[k] + 8 * (size_t)T.nw[k] + 16 * (size_t)T.nh[k];  // tile + tables
+                smem_max = std::max(smem_max, bytes);
+                tiles.push_back(T);
+            }
+        if (smem_max + 64 > 200 * 1024) return false;
+        orbb_handle::FusedGroup G;
+        G.g0 = g0; G.ng = ng; G.n_tiles = (int)tiles.size(); G.smem = (smem_max + 15) & ~(size_t)15;
+        if (getenv("ORBB_FUSED_DEBUG")) {
+            long long need = 0, own = 0;
+            for (const PfTile &T : tiles) for (int k = 0; k < ng; ++k) { need += (long long)T.nw[k] * T.nh[k]; own += (long long)T.ow[k] * T.oh[k]; }
+            fprintf(stderr, "fused pyramid group %d..%d: %d tiles of %dx%d (grid %dx%d), smem %zu B, computed / written pixels %.2f\n", g0,
+                    g0 + ng - 1, G.n_tiles, tw, th, ntx, nty, G.smem, (double)need / (double)std::max(own, 1LL));
+            const PfTile &T = tiles[tiles.size() / 2];
+            for (int k = 0; k < ng; ++k) fprintf(stderr, "  mid tile level %d: need %dx%d @(%d,%d) own %dx%d @(%d,%d)\n", g0 + k, T.nw[k], T.nh[k], T.nx0[k], T.ny0[k], T.ow[k], T.oh[k], T.ox0[k], T.oy0[k]);
+            fprintf(stderr, "  source %dx%d @(%d,%d)\n", T.sw, T.sh, T.sx0, T.sy0);
+        }
+        h->fused.push_back(G);
+        out_tiles.push_back(tiles);
+    }
+    return true;
+}
+
 extern "C" int orbb_create(orbb_handle **out, const orbb_params *params, int width, int height, int max_batch,
                            int device) {
     if (!out || !params) return ORBB_ERR_INVALID;
@@ -278,6 +394,8 @@ extern "C" int orbb_create(orbb_handle **out, const orbb_params *params, int wid
 
     std::vector<CellEntry> cells;
     std::vector<int> slot_level, slot_base(nl);
+    std::vector<std::vector<int>> h_xofs(nl);    // host copies of the resize tables: the fused-pyramid tile builder needs
+    std::vector<std::vector<int2>> h_yrows(nl);  // every level's source footprint
     int max_cw = 1, max_ch = 1;
     h->dump_off.resize(nl + 1);
     long long dump_total = 0;
@@ -305,6 +423,7 @@ extern "C" int orbb_create(orbb_handle **out, const orbb_params *params, int wid
             L.area2x = (S.w == 2 * L.w && S.h == 2 * L.h) ? 1 : 0;
             std::vector<int> xofs; std::vector<short2> xa; std::vector<int2> yr; std::vector<short2> yb;
             build_resize_tables(S.w, S.h, L.w, L.h, xofs, xa, yr, yb);
+            h_xofs[l] = xofs; h_yrows[l] = yr;
             int *dxofs; short2 *dxa; int2 *dyr; short2 *dyb;
             CKC(upload(h, &dxofs, xofs)); CKC(upload(h, &dxa, xa)); CKC(upload(h, &dyr, yr)); CKC(upload(h, &dyb, yb));
             L.xofs = dxofs; L.xalpha = dxa; L.yrows = dyr; L.ybeta = dyb;
@@ -470,6 +589,15 @@ extern "C" int orbb_create(orbb_handle **out, const orbb_params *params, int wid
             h->tma_maps = dm;
         }
     }
+    {
+        if (const char *e = getenv("ORBB_FUSED_PYRAMID")) h->fused_max_frames = std::max(atoi(e), 0);
+        std::vector<std::vector<PfTile>> ft;
+        if (h->fused_max_frames > 0 && build_fused_tiles(h, h_xofs, h_yrows, ft)) {
+            for (size_t g = 0; g < ft.size(); ++g) CKC(upload(h, &h->fused[g].d_tiles, ft[g]));
+        } else {
+            h->fused.clear();
+        }
+    }
     CKC(upload(h, &h->d_cells, cells));
     CKC(upload(h, &h->d_slot_level, slot_level));
     CKC(upload(h, &h->d_slot_base, slot_base));
@@ -611,8 +739,16 @@ static int run_all(orbb_handle *h, const uint8_t *d_images, size_t pitch, size_t
                    uint8_t *d_desc, int32_t *d_counts, int max_kp, cudaStream_t st, cudaStream_t side = nullptr,
                    cudaEvent_t ev_fork = nullptr, cudaEvent_t ev_join = nullptr) {
     int rc;
-    if ((rc = run_upload(h, d_images, pitch, stride, f0, n, st))) return rc;
-    if ((rc = run_pyramid(h, f0, n, st))) return rc;
+    if (!h->fused.empty() && n <= h->fused_max_frames) {
+        // small batch: level 0 and every further level in ceil(nlevels / 4) launches (k_pyramid_fused)
+        CK(h, cudaMemsetAsync(h->d_cand_count + (size_t)f0 * h->nlevels, 0, sizeof(int) * (size_t)n * h->nlevels, st));
+        for (const auto &G : h->fused)
+            CK(h, launch_pyramid_fused(d_images, pitch, stride, h->d_levels, G.g0, G.ng, G.d_tiles, G.n_tiles, G.smem, f0, n, st));
+        h->n_launches += (long long)h->fused.size();
+    } else {
+        if ((rc = run_upload(h, d_images, pitch, stride, f0, n, st))) return rc;
+        if ((rc = run_pyramid(h, f0, n, st))) return rc;
+    }
     if ((rc = run_fast(h, f0, n, st))) return rc;
     // The blur depends only on the pyramid.  FAST saturates the issue slots, the quadtree kernel does not
     // (barrier/latency bound), so with a side stream the blur is forked to run under the quadtree.

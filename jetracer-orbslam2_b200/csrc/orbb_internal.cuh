@@ -93,6 +93,16 @@ __device__ __forceinline__ void oct_bin_candidate(const LevelDev &L, int frame, 
 }
 #endif
 
+// k_pyramid_fused (several pyramid levels per launch, small batches): rectangles of one tile, per level of its group
+// (k = 0 .. n-1).  x coordinates are in "c" units (c = padded column + 1: c = 0 is byte 12 of a padded row, aligned
+// 4-byte words are c = 4i .. 4i+3) and multiples of 4; y in padded rows.
+#define ORBB_PF_GROUP 4
+struct PfTile {
+    short sx0, sy0, sw, sh;  // source window: image ROI coordinates (group 0) or c / padded-row units of the level below
+    short nx0[ORBB_PF_GROUP], ny0[ORBB_PF_GROUP], nw[ORBB_PF_GROUP], nh[ORBB_PF_GROUP];  // pixels to COMPUTE
+    short ox0[ORBB_PF_GROUP], oy0[ORBB_PF_GROUP], ow[ORBB_PF_GROUP], oh[ORBB_PF_GROUP];  // pixels to WRITE (partition)
+};
+
 struct CellEntry {  // one FAST work item = one upstream 30-px cell
     int16_t level, x0, y0, cw, ch, pad0, pad1, pad2;  // tested-range origin (ROI coords) and size
 };

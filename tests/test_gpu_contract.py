@@ -455,3 +455,26 @@ def test_results_do_not_depend_on_scratch_contents_or_touch_guards(orbb, oracle,
     got = d_idx.cpu().numpy().reshape(nb, mk, 2)[0, :nq, 0]
     assert np.array_equal(got, oi[:, 0])
     ex.close()
+
+
+def test_fused_pyramid_opt_in(orbb, oracle, synth, monkeypatch):
+    """ORBB_FUSED_PYRAMID=n: batches of up to n frames build level 0 and every further level in ceil(nlevels / 4)
+    launches (k_pyramid_fused: tile pyramids in shared memory, halos recomputed).  Opt-in because it measured slower
+    than the per-level kernels; it must stay bit-exact -- every padded pixel of every level, odd sizes, scale 2.0
+    (INTER_AREA route) and more than four levels (two groups)."""
+    monkeypatch.setenv("ORBB_FUSED_PYRAMID", "4")
+    for (w, h, nf, sc, nl, seed) in ((640, 480, 1000, 1.2, 8, 1000), (333, 251, 400, 1.2, 6, 5), (512, 384, 600, 2.0, 3, 21),
+                                     (97, 83, 120, 1.2, 2, 33), (848, 480, 405, 1.2, 1, 2100), (400, 300, 400, 1.5, 4, 9)):
+        frames = np.stack([synth.textured_frame(w, h, seed), synth.textured_frame(w, h, seed + 1), synth.sparse_frame(w, h, 3)])
+        ex = orbb.ORBextractor(nf, sc, nl, 20, 7, width=w, height=h, max_batch=3)
+        l0 = ex.launch_count()
+        kp, desc, cnt = ex.extract_batch(frames)
+        assert ex.launch_count() - l0 == (nl + 3) // 4 + 4  # fused groups + FAST + quadtree + blur + angle/rBRIEF
+        o = oracle.Oracle(w, h, nf, sc, nl, 20, 7)
+        for f in range(3):
+            okp, od = canon(*o.extract(frames[f]))
+            for l in range(nl):
+                assert np.array_equal(ex.debug_padded(l, frame=f), o.level_padded(l)), (w, h, l, f)
+            gk, gd = canon(kp[f, :cnt[f]], desc[f, :cnt[f]])
+            assert gk.tobytes() == okp.tobytes() and np.array_equal(gd, od)
+        ex.close()
