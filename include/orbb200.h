@@ -380,6 +380,30 @@ long long orbb_slam_frame_to_bson(int32_t ax, int32_t ay, int32_t az, int32_t wi
                                   const uint16_t *keypoints_x, const uint16_t *keypoints_y, int n_matched,
                                   const uint8_t *image, size_t image_bytes, uint8_t *out, size_t out_capacity);
 
+/* ---------------------------------------------------------------- JPEG preview
+ * The image the reference attaches to every frame message: its gray frame as three equal planes, the keypoints painted
+ * into the G plane (Jetracer::overlay_keypoints, src/cuda/post_processing.cu:45-70: the 2x2 block
+ * [int(x-1), x+1) x [int(y-1), y+1) set to 255), encoded by nvJPEG with quality 90 and 4:2:0 subsampling
+ * (src/SlamGpuPipeline/buildStream.cpp:266-277, 491-521, 613-621).  The planes and the encoder state live in the
+ * object (the reference mallocs per frame); libnvjpeg is opened with dlopen on first use, so the rest of the library
+ * does not depend on it (ORBB_ERR_NO_DEVICE from create when it is missing).  The bytes go into
+ * orbb_slam_frame_to_bson(image = ...). */
+typedef struct orbb_preview orbb_preview;
+int orbb_preview_create(orbb_preview **out, int width, int height, int quality, int device);
+int orbb_preview_destroy(orbb_preview *p);
+const char *orbb_preview_last_error(const orbb_preview *p);
+/* d_gray: DEVICE u8 frame (row pitch gray_pitch).  d_xy: DEVICE keypoint positions, two floats (x, y) every xy_stride
+ * bytes -- an orbb_keypoint array (stride 28) or packed float2 (stride 8) -- or NULL for no overlay; n_kp = number of
+ * positions, further limited by *d_n_kp (DEVICE int32, e.g. one entry of the extraction's counts) when that is not
+ * NULL.  Writes at most `capacity` bytes of JPEG to HOST memory and its length to *length (h_jpeg == NULL: only the
+ * length).  Blocks until the bitstream is on the host (the encoder needs the stream drained, as in the reference). */
+int orbb_preview_encode_host(orbb_preview *p, const uint8_t *d_gray, size_t gray_pitch, const void *d_xy, int xy_stride,
+                             int n_kp, const int32_t *d_n_kp, uint8_t *h_jpeg, size_t capacity, size_t *length,
+                             void *cuda_stream);
+/* parity access: the three planes handed to the encoder, HOST [3][height][width].  Synchronises. */
+int orbb_preview_debug_planes(orbb_preview *p, const uint8_t *d_gray, size_t gray_pitch, const void *d_xy, int xy_stride,
+                              int n_kp, const int32_t *d_n_kp, uint8_t *h_planes);
+
 /* ---------------------------------------------------------------- debug / parity access
  * Download stage outputs of frame `frame` of the last batch to HOST memory (synchronises). */
 /* fill every stateless scratch buffer of the handle with `value` (0..255): extraction results must not change

@@ -41,6 +41,8 @@ EXPORTS = [
     "orbb_slam_frame_bson_size", "orbb_slam_frame_to_bson",
     "orbb_rgbd_stage_create", "orbb_rgbd_stage_destroy", "orbb_rgbd_stage_reset", "orbb_rgbd_stage_handle",
     "orbb_rgbd_stage_submit", "orbb_rgbd_stage_wait",
+    "orbb_preview_create", "orbb_preview_destroy", "orbb_preview_last_error", "orbb_preview_encode_host",
+    "orbb_preview_debug_planes",
 ]
 
 
@@ -164,10 +166,16 @@ def load_library():
     L.orbb_rgbd_stage_handle.argtypes = [vp]
     L.orbb_rgbd_stage_submit.argtypes = [vp, vp, vp, i32, vp]
     L.orbb_rgbd_stage_wait.argtypes = [vp, i32, C.POINTER(SlamFrames)]
+    L.orbb_preview_create.argtypes = [C.POINTER(vp), i32, i32, i32, i32]
+    L.orbb_preview_destroy.argtypes = [vp]
+    L.orbb_preview_last_error.argtypes = [vp]
+    L.orbb_preview_last_error.restype = C.c_char_p
+    L.orbb_preview_encode_host.argtypes = [vp, vp, sz, vp, i32, i32, vp, vp, sz, C.POINTER(C.c_size_t), vp]
+    L.orbb_preview_debug_planes.argtypes = [vp, vp, sz, vp, i32, i32, vp, vp]
     for name in EXPORTS:
         fn = getattr(L, name)
         if name not in ("orbb_strerror", "orbb_last_cuda_error", "orbb_get_launch_count", "orbb_rgbd_stage_handle",
-                        "orbb_slam_frame_bson_size", "orbb_slam_frame_to_bson"):
+                        "orbb_slam_frame_bson_size", "orbb_slam_frame_to_bson", "orbb_preview_last_error"):
             fn.restype = C.c_int
     L.orbb_slam_frame_bson_size.restype = C.c_size_t
     L.orbb_slam_frame_to_bson.restype = C.c_longlong
@@ -580,6 +588,53 @@ class RgbdFrameStage:
                     previous_matched_points=view(out.previous_matched_points, np.float64, (n, mk, 3)),
                     current_matched_points=view(out.current_matched_points, np.float64, (n, mk, 3)),
                     matched_xy=view(out.matched_xy, np.uint16, (n, 2, mk)))
+
+
+class Preview:
+    """The JPEG the reference sends with every frame (buildStream.cpp:491-521, 613-621): gray frame, keypoints painted
+    into the G plane, nvJPEG quality 90 / 4:2:0."""
+
+    def __init__(self, width: int, height: int, quality: int = 90, device: int = -1):
+        self._lib = load_library()
+        self._p = C.c_void_p()
+        self.width, self.height = width, height
+        rc = self._lib.orbb_preview_create(C.byref(self._p), width, height, quality, device)
+        if rc != 0:
+            self._p = C.c_void_p()
+            raise OrbbError(f"orbb_preview_create: {self._lib.orbb_strerror(rc).decode()} ({rc})")
+        self._buf = np.empty(width * height * 3 + 4096, np.uint8)  # a JPEG never needs more than the raw planes
+
+    def close(self):
+        if getattr(self, "_p", None) and self._p.value:
+            self._lib.orbb_preview_destroy(self._p)
+            self._p = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc < 0:
+            raise OrbbError(f"{self._lib.orbb_strerror(rc).decode()}: {self._lib.orbb_preview_last_error(self._p).decode()}")
+
+    def encode(self, d_gray, d_xy=None, xy_stride: int = 28, n_kp: int = 0, d_n_kp=None, gray_pitch=None, stream=None) -> bytes:
+        n = C.c_size_t(0)
+        self._check(self._lib.orbb_preview_encode_host(
+            self._p, _dev_ptr(d_gray), self.width if gray_pitch is None else gray_pitch,
+            _dev_ptr(d_xy) if d_xy is not None else C.c_void_p(0), xy_stride, n_kp,
+            _dev_ptr(d_n_kp) if d_n_kp is not None else C.c_void_p(0), _np_ptr(self._buf), self._buf.size, C.byref(n),
+            _stream_ptr(stream)))
+        return self._buf[: n.value].tobytes()
+
+    def debug_planes(self, d_gray, d_xy=None, xy_stride: int = 28, n_kp: int = 0, d_n_kp=None, gray_pitch=None) -> np.ndarray:
+        out = np.zeros((3, self.height, self.width), np.uint8)
+        self._check(self._lib.orbb_preview_debug_planes(
+            self._p, _dev_ptr(d_gray), self.width if gray_pitch is None else gray_pitch,
+            _dev_ptr(d_xy) if d_xy is not None else C.c_void_p(0), xy_stride, n_kp,
+            _dev_ptr(d_n_kp) if d_n_kp is not None else C.c_void_p(0), _np_ptr(out)))
+        return out
 
 
 def slam_frame_to_bson(ax: int, ay: int, az: int, width: int, height: int, keypoints_x, keypoints_y, image=b"",

@@ -357,3 +357,55 @@ def test_compute_stereo_matches(orbb, oracle, synth):
         assert abs(np.median(kp[2 * p, :a]["x"][m] - our[m]) - (7 + 5 * p)) < 0.15
     with pytest.raises(orbb.OrbbError):
         ex.compute_stereo_matches(d_kp, d_desc, d_cnt, npairs + 1, bf, fx, d_ur, d_z)  # more pairs than resident frames
+
+
+def test_jpeg_preview(orbb, synth):
+    """SURVEY 8f-4, the nvJPEG preview of the reference (buildStream.cpp:491-521, 613-621; overlay kernel
+    post_processing.cu:45-70): the three planes handed to the encoder equal a numpy restatement of "gray x 3, 2x2 block
+    per keypoint set to 255 in G" exactly; the JPEG decodes (cv2) to that image within JPEG error; the keypoint count
+    can live on the device; the bytes slot into the frame message."""
+    import torch
+    cv2 = pytest.importorskip("cv2")
+    w, h = 848, 480
+    img = synth.textured_frame(w, h, 9900)
+    ex = orbb.ORBextractor(400, 1.2, 4, 20, 7, width=w, height=h, max_batch=1)
+    d_in = torch.from_numpy(img[None]).cuda()
+    d_kp = torch.zeros((1, ex.max_kp, 7), dtype=torch.float32, device="cuda")
+    d_desc = torch.zeros((1, ex.max_kp, 32), dtype=torch.uint8, device="cuda")
+    d_cnt = torch.zeros(1, dtype=torch.int32, device="cuda")
+    st = torch.cuda.current_stream()
+    ex.extract_batch_device(d_in, 1, d_kp, d_desc, d_cnt, stream=st)
+    torch.cuda.synchronize()
+    n = int(d_cnt.item())
+    kp = d_kp.cpu().numpy().reshape(-1, 7)[:n]
+    pv = orbb.Preview(w, h, 90)
+    # expected planes: reference loop bounds for (int x = pos.x - 1; x < pos.x + 1; x++), clamped to the image
+    exp = np.stack([img, img.copy(), img])
+    for x, y in kp[:, :2]:
+        xs = [v for v in range(int(np.float32(x) - np.float32(1)), int(np.ceil(np.float32(x) + np.float32(1)))) if v < np.float32(x) + np.float32(1)]
+        ys = [v for v in range(int(np.float32(y) - np.float32(1)), int(np.ceil(np.float32(y) + np.float32(1)))) if v < np.float32(y) + np.float32(1)]
+        for xx in xs:
+            for yy in ys:
+                if 0 <= xx < w and 0 <= yy < h:
+                    exp[1, yy, xx] = 255
+    planes = pv.debug_planes(d_in[0], d_kp, 28, ex.max_kp, d_cnt)  # count read on the device
+    assert np.array_equal(planes, exp)
+    assert (exp[1] != img).sum() > 1000
+    assert np.array_equal(pv.debug_planes(d_in[0]), np.stack([img] * 3))  # no overlay
+    jpg = pv.encode(d_in[0], d_kp, 28, ex.max_kp, d_cnt, stream=st)
+    assert jpg[:2] == b"\xff\xd8" and jpg[-2:] == b"\xff\xd9" and 10_000 < len(jpg) < w * h
+    dec = cv2.imdecode(np.frombuffer(jpg, np.uint8), cv2.IMREAD_COLOR)  # BGR
+    assert dec.shape == (h, w, 3)
+    err = dec[:, :, 1].astype(np.float32) - exp[1].astype(np.float32)  # G plane; 4:2:0 chroma smears the overlay a little
+    assert 10 * np.log10(255.0 ** 2 / np.mean(err ** 2)) > 24.0
+    gray_err = dec[:, :, 2].astype(np.float32)[exp[1] == img] - img.astype(np.float32)[exp[1] == img]
+    assert np.abs(gray_err).mean() < 12.0
+    # a second frame re-uses planes and encoder state; a strided frame (pitch > width) works too
+    wide = torch.zeros((h, w + 64), dtype=torch.uint8, device="cuda")
+    wide[:, :w] = d_in[0]
+    jpg2 = pv.encode(wide, None, gray_pitch=w + 64, stream=st)
+    dec2 = cv2.imdecode(np.frombuffer(jpg2, np.uint8), cv2.IMREAD_GRAYSCALE)
+    assert np.abs(dec2.astype(np.float32) - img.astype(np.float32)).mean() < 6.0
+    msg = orbb.slam_frame_to_bson(1, 2, 3, w, h, kp[:10, 0].astype(np.uint16), kp[:10, 1].astype(np.uint16), image=jpg, channels=3)
+    assert jpg in msg
+    pv.close(); ex.close()
