@@ -322,6 +322,115 @@ def run_reference_gpu_binary(w=848, h=480, iters=200):
         os.unlink(path)
 
 
+def bench_other_configs(orbb, torch, device_index, steps):
+    """BASELINE.json configs 2-4 through the same device-resident call (inputs in HBM, CUDA events, median of `steps`),
+    each with two frames of the timed batch checked against the CPU oracle:
+      cfg2  848x480 / 1200 kp, batch of 64 frames
+      cfg3  848x800 / 1000 kp stereo pairs, extraction + left/right and frame-to-frame 2-NN with the 0.7 ratio test
+      cfg4  1280x720 / 2000 kp, batch of 256 frames"""
+    synth = importlib.import_module(PKG + ".synth")
+    O, _ = _oracle_module()
+    st = torch.cuda.current_stream()
+    out = {}
+
+    def one(name, w, h, nf, batch, frames, after=None, pairs_per_step=0):
+        ex = orbb.ORBextractor(nf, SCALE, NLEVELS, INI_TH, MIN_TH, width=w, height=h, max_batch=batch, device=device_index)
+        d_in = [torch.from_numpy(frames).cuda(), torch.from_numpy(np.ascontiguousarray(frames[::-1])).cuda()]
+        d_kp = torch.zeros(batch * ex.max_kp * 28, dtype=torch.uint8, device="cuda")
+        d_desc = torch.zeros(batch * ex.max_kp * 32, dtype=torch.uint8, device="cuda")
+        d_cnt = torch.zeros(batch, dtype=torch.int32, device="cuda")
+        ctx = after(ex, batch, d_kp, d_desc, d_cnt) if after else None
+
+        def step(i):
+            ex.extract_batch_device(d_in[i % 2], batch, d_kp, d_desc, d_cnt, stream=st)
+            if ctx:
+                ctx["run"]()
+        for i in range(3):
+            step(i)
+        torch.cuda.synchronize()
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
+        for i in range(steps):
+            ev[i].record(st)
+            step(i)
+        ev[steps].record(st)
+        torch.cuda.synchronize()
+        ms = [ev[i].elapsed_time(ev[i + 1]) for i in range(steps)]
+        step(0)  # leave frames[...] (not the reversed set) in the outputs for the parity check
+        torch.cuda.synchronize()
+        cnt = d_cnt.cpu().numpy()
+        kp = d_kp.cpu().numpy().view(orbb.KEYPOINT_DTYPE).reshape(batch, ex.max_kp)
+        desc = d_desc.cpu().numpy().reshape(batch, ex.max_kp, 32)
+        o = O.Oracle(w, h, nf, SCALE, NLEVELS, INI_TH, MIN_TH)
+        exact = 0
+        for f in (0, batch - 1):
+            okp, od = o.extract(frames[f])
+            oo, go = np.lexsort((okp["x"], okp["y"], okp["octave"])), np.lexsort((kp[f, :cnt[f]]["x"], kp[f, :cnt[f]]["y"], kp[f, :cnt[f]]["octave"]))
+            exact += int(len(okp) == cnt[f] and okp[oo].tobytes() == kp[f, :cnt[f]][go].tobytes() and np.array_equal(od[oo], desc[f, :cnt[f]][go]))
+        med, best = float(np.median(ms)), float(np.min(ms))
+        levels = sum(int(np.rint(np.float32(w) / np.float32(1.2) ** l)) * int(np.rint(np.float32(h) / np.float32(1.2) ** l)) for l in range(NLEVELS))
+        bpf = w * h + 2 * levels + 60 * nf
+        hbm_peak, _, _ = measured_peaks()
+        r = {"frames_per_step": batch, "ms_per_step": med, "frames_per_s": batch / (med * 1e-3), "frames_per_s_best": batch / (best * 1e-3),
+             "keypoints_per_frame": float(cnt.mean()), "bytes_per_frame": bpf, "frac_of_hbm": bpf * batch / (med * 1e-3) / 1e9 / hbm_peak,
+             "parity_frames_exact": f"{exact}/2"}
+        if ctx:
+            r.update(ctx["report"](med))
+        out[name] = r
+        ex.close()
+        del d_in, d_kp, d_desc
+        torch.cuda.empty_cache()
+
+    base = [synth.textured_frame(848, 480, 2000 + i) for i in range(8)]
+    one("cfg2_848x480_1200kp_batch64", 848, 480, 1200, 64,
+        np.stack([np.roll(base[i % 8], (5 * (i // 8), 3 * (i // 8)), axis=(0, 1)) for i in range(64)]))
+
+    # cfg3: 16 time steps of a stereo rig -> 32 frames ordered (L0, R0, L1, R1, ...); right = left shifted by a disparity,
+    # frame t+1 = frame t translated by (3, 1).  Matching: L_t -> R_t and L_t -> L_{t+1}, 2-NN + ratio 0.7, one segmented call
+    w3, h3, nt3 = 848, 800, 16
+    l0 = synth.textured_frame(w3, h3, 3100)
+    fr3 = []
+    for t in range(nt3):
+        left = synth.shifted_frame(l0, 3 * t, t, 3200 + t, noise=2) if t else l0
+        fr3 += [left, synth.shifted_frame(left, -24, 0, 3300 + t, noise=2)]
+
+    def cfg3_after(ex, batch, d_kp, d_desc, d_cnt):
+        mk = ex.max_kp
+        # fixed-stride segments: query set = left frame 2t (rows [2t*mk, ...)), train sets = right frame 2t+1 / left 2t+2
+        segs = [(2 * t, 2 * t + 1) for t in range(nt3)] + [(2 * t, 2 * t + 2) for t in range(nt3 - 1)]
+        nseg = len(segs)
+        d_q = torch.zeros((nseg * mk, 32), dtype=torch.uint8, device="cuda")
+        d_t = torch.zeros((nseg * mk, 32), dtype=torch.uint8, device="cuda")
+        qsel = torch.tensor([a for a, _ in segs], device="cuda"); tsel = torch.tensor([b for _, b in segs], device="cuda")
+        d_qo = torch.zeros(nseg + 1, dtype=torch.int32, device="cuda"); d_to = torch.zeros(nseg + 1, dtype=torch.int32, device="cuda")
+        d_idx = torch.zeros((nseg * mk, 2), dtype=torch.int32, device="cuda"); d_dist = torch.zeros_like(d_idx)
+        d_acc = torch.zeros(nseg * mk, dtype=torch.uint8, device="cuda")
+        dv = d_desc.view(batch, mk, 32)
+
+        def run():
+            # gather the segments' descriptor rows (torch plumbing: two index_selects), offsets = fixed stride; rows past a
+            # frame's count are matched too and ignored afterwards (they are < 7 % of the rows)
+            d_q.view(nseg, mk, 32).copy_(dv.index_select(0, qsel)); d_t.view(nseg, mk, 32).copy_(dv.index_select(0, tsel))
+            torch.arange(0, (nseg + 1) * mk, mk, dtype=torch.int32, device="cuda", out=d_qo); d_to.copy_(d_qo)
+            ex.match_keypoints_segmented(d_q, d_qo, d_t, d_to, nseg, nseg * mk, mk, mk, d_idx, d_dist, d_acc, k=2, ratio=0.7, stream=st)
+
+        def report(med_ms):
+            cnt = d_cnt.cpu().numpy()
+            acc = d_acc.view(nseg, mk).cpu().numpy()
+            stereo = float(np.mean([acc[i, :cnt[segs[i][0]]].mean() for i in range(nt3)]))
+            temporal = float(np.mean([acc[i, :cnt[segs[i][0]]].mean() for i in range(nt3, nseg)]))
+            return {"match_segments": nseg, "match_pairs_per_step": int(nseg) * mk * mk, "accepted_fraction_stereo": stereo,
+                    "accepted_fraction_temporal": temporal,
+                    "what": "extraction of 16 stereo pairs + left/right and frame-to-frame 2-NN (ratio 0.7) in one step"}
+        return {"run": run, "report": report}
+
+    one("cfg3_848x800_1000kp_stereo16_match", w3, h3, 1000, 2 * nt3, np.stack(fr3), after=cfg3_after)
+
+    base4 = [synth.textured_frame(1280, 720, 4000 + i) for i in range(8)]
+    one("cfg4_1280x720_2000kp_batch256", 1280, 720, 2000, 256,
+        np.stack([np.roll(base4[i % 8], (5 * (i // 8), 3 * (i // 8)), axis=(0, 1)) for i in range(256)]))
+    return out
+
+
 def bench_reference_gpu_kernels(orbb, torch, device_index):
     """The reference's own kernels on this GPU (run_reference_gpu_binary) next to the product on the same 848x480
     frame (reference Context.h:16-17).  DIFFERENT ALGORITHM (FAST-12 float score on one blurred level, one keypoint
@@ -624,6 +733,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-rgbd", action="store_true", help="skip the RGB-D frame-stage leg (cfg 2 geometry)")
     ap.add_argument("--no-refgpu", action="store_true", help="skip the leg that times the reference's own kernels")
+    ap.add_argument("--no-configs", action="store_true", help="skip BASELINE configs 2-4 (848x480 x64, 848x800 stereo + matching, 1280x720 x256)")
     ap.add_argument("--no-cfg5", action="store_true", help="skip the BASELINE config 5 pipeline (1024-frame batch, strong scaling)")
     ap.add_argument("--no-parity", action="store_true", help="skip the oracle check of the timed batch")
     ap.add_argument("--sustain-s", type=float, default=2.5, help="length of the sustained device-resident leg (0 = skip)")
@@ -874,6 +984,11 @@ def main():
     del d_sets, d_kp, d_desc, d_q, d_map
     torch.cuda.empty_cache()
 
+    # ---- BASELINE configs 2-4 (single GPU; the multi-GPU lines carry cfg 1 / 5 only)
+    other = None
+    if rank == 0 and world == 1 and not args.no_configs:
+        other = bench_other_configs(orbb, torch, local_rank, min(args.steps, 10))
+
     # ---- BASELINE config 5 as written (strong scaling; the only legs with collectives)
     cfg5 = None
     if not args.no_cfg5:
@@ -946,6 +1061,8 @@ def main():
         if cfg5 is not None:
             line["cfg5"] = cfg5
             line["gather"] = cfg5["gather"]
+        if other is not None:
+            line["other_configs"] = other
         if rgbd is not None:
             line["rgbd_stage"] = rgbd
         if refgpu is not None:
