@@ -78,6 +78,7 @@ struct orbb_handle {
     float sf[ORBB_MAX_LEVELS]{}, inv_sf[ORBB_MAX_LEVELS]{};
     CellEntry *d_cells = nullptr;
     int n_cells = 0;
+    int cell_first[ORBB_MAX_LEVELS + 1] = {};  // cells are stored level by level: level l owns [cell_first[l], cell_first[l+1])
     FastSmemCfg fcfg{};
     void *tma_maps = nullptr;  // DEVICE array of CUtensorMap, one per level (nullptr: FAST stages manually)
     int t_lo = 7, t_hi = 20;
@@ -114,7 +115,8 @@ struct orbb_handle {
         int max_kp = 0; cudaGraphExec_t exec = nullptr; long long launches = 0, stamp = 0;
     } graphs[4];
     long long graph_clock = 0;
-    int use_graphs = 0;  // opt-in (ORBB_GRAPH=1): see orbb_extract_batch_device
+    int use_graphs = 1;  // small batches replay a captured graph (ORBB_GRAPH=0: plain stream launches); see orbb_extract_batch_device
+    int graph_miss_streak = 0;
     int last_host_frames = -1, last_host_latency = -1;  // chunk layout of the previous host submission
     // several pyramid levels per launch (k_pyramid_fused), small batches only: per group of <= 4 levels a tile table
     struct FusedGroup { int g0 = 0, ng = 0, n_tiles = 0; size_t smem = 0; PfTile *d_tiles = nullptr; };
@@ -465,6 +467,7 @@ extern "C" int orbb_create(orbb_handle **out, const orbb_params *params, int wid
             L.rs_h = drsh; L.rs_v = drsv; L.rs_nq = nq;
             L.rs_ok = (ok && !getenv("ORBB_RESIZE_TILED")) ? 1 : 0;
         }
+        h->cell_first[l] = (int)cells.size();
         // ---- per-cell FAST grid (upstream ComputeKeyPointsOctTree)
         const int W = L.w - 32, H = L.h - 32;  // maxBorder - minBorder
         const float fw = (float)W, fh = (float)H;
@@ -562,6 +565,7 @@ extern "C" int orbb_create(orbb_handle **out, const orbb_params *params, int wid
     }
     h->dump_off[nl] = dump_total;
     h->n_cells = (int)cells.size(); h->n_slots = (int)slot_level.size();
+    for (int l = nl; l <= ORBB_MAX_LEVELS; ++l) h->cell_first[l] = h->n_cells;
     h->max_kp = h->n_slots;
     h->pcap = h->sel_cap_max; h->pcap2 = 1;
     while (h->pcap2 < h->pcap) h->pcap2 <<= 1;
@@ -723,6 +727,18 @@ static int run_distribute(orbb_handle *h, int f0, int n, cudaStream_t st) {
     h->n_launches += 1;
     return ORBB_OK;
 }
+// FAST + quadtree restricted to levels [l0, l1): the cells of a level are contiguous and every (frame, level) has its
+// own candidate list, counters and cell table, so disjoint level ranges may run concurrently on different streams
+static int run_detect_levels(orbb_handle *h, int l0, int l1, int f0, int n, cudaStream_t st) {
+    const int c0 = h->cell_first[l0], c1 = h->cell_first[l1];
+    if (c1 > c0)
+        CK(h, launch_fast(h->tma_maps, h->d_levels, h->d_cells + c0, c1 - c0, h->nlevels, h->d_cand_count, h->t_lo, h->t_hi, h->fcfg,
+                          f0, n, st));
+    CK(h, launch_octree(h->d_levels, h->nlevels, h->d_cand_count, h->d_sel_count, l0, l1 - l0, f0, n, -1, h->sel_cap_max,
+                        h->pcap, h->pcap2, st));
+    h->n_launches += 2;
+    return ORBB_OK;
+}
 static int run_blur(orbb_handle *h, int f0, int n, cudaStream_t st) {
     CK(h, launch_blur(h->d_levels, h->lv, h->nlevels, f0, n, st));
     h->n_launches += 1;
@@ -739,6 +755,34 @@ static int run_all(orbb_handle *h, const uint8_t *d_images, size_t pitch, size_t
                    uint8_t *d_desc, int32_t *d_counts, int max_kp, cudaStream_t st, cudaStream_t side = nullptr,
                    cudaEvent_t ev_fork = nullptr, cudaEvent_t ev_join = nullptr) {
     int rc;
+    // Small batches (a lone frame is the reference's operating mode): the chain level0 -> 7 resizes -> FAST -> quadtree
+    // -> angle/rBRIEF is latency bound end to end (each kernel a few us on a fraction of the SMs).  Detection of the
+    // big levels does not need the small ones: after level `ls - 1` is built, FAST + quadtree of levels [0, ls) move to a
+    // second stream and run NEXT TO the rest of the pyramid and the detection of levels [ls, n); the blur (needs the
+    // pyramid only) runs on a third.  Same kernels, same results.  Only as part of a captured graph (ORBB_GRAPH=1): with
+    // plain stream operations the two cross-stream joins cost more than the overlap gains (one 848x480 frame, 8 levels:
+    // 65 us sequential, 82 us split without a graph, 57 us split inside a graph).
+    static const int lone_split = getenv("ORBB_LONE_SPLIT") ? atoi(getenv("ORBB_LONE_SPLIT")) : 4;
+    if (side && h->use_graphs && n <= lone_split && h->nlevels >= 4 && (h->fused.empty() || n > h->fused_max_frames)) {
+        const int ls = std::min(4, h->nlevels - 1);
+        cudaStream_t sa = h->s_dev[0];
+        if ((rc = run_upload(h, d_images, pitch, stride, f0, n, st))) return rc;
+        for (int l = 1; l < ls; ++l) CK(h, launch_resize(h->d_levels, h->lv, l, f0, n, st));
+        CK(h, cudaEventRecord(h->ev_dev[0], st));
+        CK(h, cudaStreamWaitEvent(sa, h->ev_dev[0], 0));
+        if ((rc = run_detect_levels(h, 0, ls, f0, n, sa))) return rc;
+        CK(h, cudaEventRecord(h->ev_dev[1], sa));
+        for (int l = ls; l < h->nlevels; ++l) CK(h, launch_resize(h->d_levels, h->lv, l, f0, n, st));
+        h->n_launches += h->nlevels - 1;
+        CK(h, cudaEventRecord(ev_fork, st));
+        CK(h, cudaStreamWaitEvent(side, ev_fork, 0));
+        if ((rc = run_blur(h, f0, n, side))) return rc;
+        CK(h, cudaEventRecord(ev_join, side));
+        if ((rc = run_detect_levels(h, ls, h->nlevels, f0, n, st))) return rc;
+        CK(h, cudaStreamWaitEvent(st, h->ev_dev[1], 0));
+        CK(h, cudaStreamWaitEvent(st, ev_join, 0));
+        return run_angle_orb(h, f0, n, d_kp, d_desc, d_counts, max_kp, st);
+    }
     if (!h->fused.empty() && n <= h->fused_max_frames) {
         // small batch: level 0 and every further level in ceil(nlevels / 4) launches (k_pyramid_fused)
         CK(h, cudaMemsetAsync(h->d_cand_count + (size_t)f0 * h->nlevels, 0, sizeof(int) * (size_t)n * h->nlevels, st));
@@ -861,13 +905,15 @@ extern "C" int orbb_extract_batch_device(orbb_handle *h, const uint8_t *d_images
         if (!h->use_graphs)
             return run_all(h, d_images, pitch, frame_stride, 0, n_frames, d_kp, d_desc, d_counts, max_kp, st, h->s_side,
                            h->ev_fork, h->ev_join);
-        // Opt-in (ORBB_GRAPH=1): the whole stage sequence (memset + 14 kernels, blur forked onto the side stream) is
-        // captured once per argument set into a CUDA graph and replayed; a caller that cycles through a few buffer
-        // sets (double buffering) hits the 4-entry cache, anything else re-captures.  Measured on B200: an isolated
-        // single-frame call (launch, then synchronise -- the reference's per-frame loop) drops from 151 to 127 us at
-        // 640x480 because the CPU no longer issues 15 launches, but back-to-back calls get slower (B=4: 149 -> 188 us,
-        // 848x480 B=1: 164 -> 226 us): graph nodes pay more dependency latency than stream-ordered launches whose
-        // submission the CPU has already run ahead of.  Hence not the default.
+        // Small batches are launch / latency bound (a lone frame: ~17 stream operations for ~60 us of GPU work), so the
+        // whole stage sequence -- memset, pyramid chain, detection of the big levels forked next to the rest of the
+        // pyramid, blur on a third stream, angle/rBRIEF after the joins -- is captured once per argument set into a
+        // CUDA graph and replayed.  A caller that cycles through a few buffer sets (the reference's slots own fixed
+        // buffers, buildStream.cpp:208-341) hits the 4-entry cache; a miss re-captures and patches the evicted
+        // executable graph in place (cudaGraphExecUpdate: same topology).  Eight misses in a row mean the caller passes
+        // fresh pointers every call: the handle then goes back to plain stream launches for good.  Measured on B200,
+        // one 848x480 frame: 8 levels / 1200 kp 65 -> 58 us per call (53 back to back), 1 level / 405 kp 45 -> 38 us
+        // (34 back to back), host time inside the call 34 -> 5 us.  ORBB_GRAPH=0 disables.
         orbb_handle::GraphSlot *slot = nullptr, *victim = &h->graphs[0];
         for (auto &g : h->graphs) {
             if (g.exec && g.img == d_images && g.pitch == pitch && g.stride == frame_stride && g.n == n_frames &&
@@ -875,9 +921,14 @@ extern "C" int orbb_extract_batch_device(orbb_handle *h, const uint8_t *d_images
                 slot = &g;
             if (g.stamp < victim->stamp) victim = &g;
         }
+        if (slot) h->graph_miss_streak = 0;
+        else if (++h->graph_miss_streak > 8 && h->graphs[0].exec) {
+            h->use_graphs = 0;
+            return run_all(h, d_images, pitch, frame_stride, 0, n_frames, d_kp, d_desc, d_counts, max_kp, st, h->s_side,
+                           h->ev_fork, h->ev_join);
+        }
         if (!slot) {
             slot = victim;
-            if (slot->exec) { cudaGraphExecDestroy(slot->exec); slot->exec = nullptr; }
             cudaStream_t cs = h->s_comp[1];  // capture on an internal stream: the caller's may be the legacy stream
             const long long l0 = h->n_launches;
             CK(h, cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal));
@@ -887,9 +938,22 @@ extern "C" int orbb_extract_batch_device(orbb_handle *h, const uint8_t *d_images
             const cudaError_t ce = cudaStreamEndCapture(cs, &graph);
             slot->launches = h->n_launches - l0;
             h->n_launches = l0;
-            if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
-            CK(h, ce);
-            const cudaError_t ie = cudaGraphInstantiate(&slot->exec, graph, 0);
+            if (rc || ce != cudaSuccess) {
+                if (graph) cudaGraphDestroy(graph);
+                if (slot->exec) { cudaGraphExecDestroy(slot->exec); slot->exec = nullptr; }
+                if (rc) return rc;
+                CK(h, ce);
+            }
+            cudaError_t ie = cudaErrorUnknown;
+            if (slot->exec && slot->n == n_frames) {  // same node topology: patch the kernel / memset arguments in place
+                cudaGraphExecUpdateResultInfo info;
+                ie = cudaGraphExecUpdate(slot->exec, graph, &info);
+                if (ie != cudaSuccess) cudaGetLastError();
+            }
+            if (ie != cudaSuccess) {
+                if (slot->exec) { cudaGraphExecDestroy(slot->exec); slot->exec = nullptr; }
+                ie = cudaGraphInstantiate(&slot->exec, graph, 0);
+            }
             cudaGraphDestroy(graph);
             CK(h, ie);
             slot->img = d_images; slot->pitch = pitch; slot->stride = frame_stride; slot->n = n_frames;

@@ -478,3 +478,46 @@ def test_fused_pyramid_opt_in(orbb, oracle, synth, monkeypatch):
             gk, gd = canon(kp[f, :cnt[f]], desc[f, :cnt[f]])
             assert gk.tobytes() == okp.tobytes() and np.array_equal(gd, od)
         ex.close()
+
+
+def test_small_batch_graph_cache_and_fallback(orbb, oracle, synth, monkeypatch):
+    """Small batches replay a captured graph keyed by the argument set (4 slots).  A caller that hands in fresh buffers on
+    every call misses every time: after eight misses in a row the handle must fall back to plain stream launches, and
+    every call on the way -- captured, patched in place (cudaGraphExecUpdate) or direct -- must give the oracle's
+    bytes.  ORBB_GRAPH=0 (never capture) is checked on the same frames."""
+    import torch
+    w, h = 424, 240
+    frames = np.stack([synth.textured_frame(w, h, 8800 + i) for i in range(2)])
+    o = oracle.Oracle(w, h, 500, 1.2, 6)
+    ref = [canon(*o.extract(f)) for f in frames]
+    st = torch.cuda.current_stream()
+
+    def check(ex, d_kp, d_desc, d_cnt, n):
+        cnt = d_cnt.cpu().numpy()
+        kp = d_kp.cpu().numpy().view(orbb.KEYPOINT_DTYPE).reshape(-1, ex.max_kp)
+        desc = d_desc.cpu().numpy()
+        for f in range(n):
+            gk, gd = canon(kp[f, :cnt[f]], desc[f, :cnt[f]])
+            assert gk.tobytes() == ref[f][0].tobytes() and np.array_equal(gd, ref[f][1])
+
+    for graph in ("1", "0"):
+        monkeypatch.setenv("ORBB_GRAPH", graph)
+        ex = orbb.ORBextractor(500, 1.2, 6, 20, 7, width=w, height=h, max_batch=2)
+        per_call, keep = [], []  # `keep` stops the caching allocator from handing the same addresses out again
+        for i in range(14):  # a new set of device buffers every call
+            n = 1 + (i % 2)
+            d_in = torch.from_numpy(frames[:n].copy()).cuda()
+            d_kp = torch.zeros((n, ex.max_kp, 7), dtype=torch.float32, device="cuda")
+            d_desc = torch.zeros((n, ex.max_kp, 32), dtype=torch.uint8, device="cuda")
+            d_cnt = torch.zeros(n, dtype=torch.int32, device="cuda")
+            l0 = ex.launch_count()
+            ex.extract_batch_device(d_in, n, d_kp, d_desc, d_cnt, stream=st)
+            torch.cuda.synchronize()
+            per_call.append(ex.launch_count() - l0)
+            check(ex, d_kp, d_desc, d_cnt, n)
+            keep.append((d_in, d_kp, d_desc, d_cnt))
+        if graph == "1":
+            assert per_call[0] == 12 and per_call[-1] == 10  # captured (split detection: 2 more launches), then direct
+        else:
+            assert set(per_call) == {10}
+        ex.close()

@@ -24,5 +24,11 @@ for nf, nl in ((405, 1), (1200, 8)):
     for _ in range(iters):
         e0.record(st); ex.extract_batch_device(d_in, 1, d_kp, d_desc, d_cnt, stream=st); e1.record(st)
         torch.cuda.synchronize(); lat.append(e0.elapsed_time(e1))
-    print(f"{w}x{h} levels={nl} nfeatures={nf}: call latency median {1e3*np.median(lat):.1f} us, best {1e3*min(lat):.1f} us", flush=True)
+    import time
+    enq = []
+    for _ in range(iters):  # host time spent inside the call (enqueue only), GPU idle at entry
+        t0 = time.perf_counter(); ex.extract_batch_device(d_in, 1, d_kp, d_desc, d_cnt, stream=st); enq.append(time.perf_counter() - t0)
+        torch.cuda.synchronize()
+    print(f"{w}x{h} levels={nl} nfeatures={nf}: call latency median {1e3*np.median(lat):.1f} us, best {1e3*min(lat):.1f} us; "
+          f"host enqueue time median {1e6*np.median(enq):.1f} us", flush=True)
     ex.close()
