@@ -63,7 +63,7 @@ __device__ __forceinline__ int arc_score(const uint8_t *p, int tp) {
 
 // TP: the tile's row pitch in bytes as a compile-time constant (0 = read it from cfg): with it the 16 ring offsets of
 // the arc score and the +-3-row offsets of the precheck are instruction immediates off ONE base register, which takes
-// about a dozen address instructions out of every scored pixel.  The score tile's pitch is tied to it (TP - 8).
+// about a dozen address instructions out of every scored pixel.  The score tile has the same pitch.
 template <bool DUMP, bool TMA, int TP>
 __global__ void __launch_bounds__(FAST_WARPS * 32)
 k_fast_cells(const CUtensorMap *__restrict__ maps, const LevelDev *__restrict__ levels, const CellEntry *__restrict__ cells, int n_cells, int n_levels,
@@ -78,9 +78,9 @@ k_fast_cells(const CUtensorMap *__restrict__ maps, const LevelDev *__restrict__ 
     const LevelDev &L = levels[c.level];
 
     uint8_t *tile = smem + (size_t)warp * cfg.warp_bytes;
-    uint8_t *score = tile + max(cfg.tile_pitch, cfg.tma_pitch) * cfg.tile_rows;
-    uint16_t *queue = reinterpret_cast<uint16_t *>(score + cfg.score_pitch * cfg.score_rows);
-    const int tp = TMA ? cfg.tma_pitch : (TP ? TP : cfg.tile_pitch), sp = (!TMA && TP) ? TP - 8 : cfg.score_pitch, tpw = tp >> 2;
+    uint8_t *score = tile + cfg.tile_bytes;  // 16-byte aligned
+    uint16_t *queue = reinterpret_cast<uint16_t *>(score + cfg.score_bytes);
+    const int tp = TMA ? cfg.tma_pitch : (TP ? TP : cfg.tile_pitch), sp = tp, tpw = tp >> 2;  // score tile: same pitch as the window tile
     const int cw = c.cw, ch = c.ch;
     const uint32_t *tile32 = reinterpret_cast<const uint32_t *>(tile);
     pdl_wait();  // launched as a programmatic dependent of the last pyramid kernel: the levels are complete from here on
@@ -112,7 +112,7 @@ k_fast_cells(const CUtensorMap *__restrict__ maps, const LevelDev *__restrict__ 
                 ::"r"(dst), "l"(maps + c.level), "r"((ORBB_ROI_X0 + c.x0 - 4) & ~15), "r"(ORBB_BORDER + c.y0 - 3), "r"(frame), "r"(bar)
                 : "memory");
         }
-        for (int i = lane; i < (sp * cfg.score_rows) >> 2; i += 32) reinterpret_cast<uint32_t *>(score)[i] = 0;
+        for (int i = lane; i < cfg.score_bytes >> 4; i += 32) reinterpret_cast<uint4 *>(score)[i] = make_uint4(0u, 0u, 0u, 0u);
         __syncwarp();
         unsigned done = 0;
         while (!done)
@@ -170,15 +170,16 @@ k_fast_cells(const CUtensorMap *__restrict__ maps, const LevelDev *__restrict__ 
                 }
             }
         }
-        for (int i = lane; i < (sp * cfg.score_rows) >> 2; i += 32) reinterpret_cast<uint32_t *>(score)[i] = 0;
+        for (int i = lane; i < cfg.score_bytes >> 4; i += 32) reinterpret_cast<uint4 *>(score)[i] = make_uint4(0u, 0u, 0u, 0u);
     }
     __syncwarp();
 
     const int npix = cw * ch;
     const unsigned lt_mask = (1u << lane) - 1u;
     const int nux = (cw + 3) >> 2, nunits = nux * ch;        // 4-pixel units per row / per cell
-    const unsigned inv_nux = (1u << 20) / (unsigned)nux + 1u;  // exact floor(u / nux) for u * nux < 2^20
-    // Queue entries are (y << 6 | x), cell-relative (cells are at most 63 px wide / high): decoding is a shift and a mask.
+    const unsigned inv_nux = c.inv_nux;  // (1 << 20) / nux + 1, tabulated by the host: exact floor(u / nux) for u * nux < 2^20
+    // Queue entries are y * tp + x, cell-relative: the byte offset of the pixel inside the window tile AND inside the score
+    // tile (same pitch), so phases 2 and 3 add them to one base pointer; only the emitted survivors are decoded back to (y, x).
 
     // Upstream order: FAST(ini) on the cell; only if that leaves nothing, FAST(min).  Running the high
     // threshold first rejects most pixels in the precheck (the low-threshold pass is rare on textured input).
@@ -271,17 +272,17 @@ k_fast_cells(const CUtensorMap *__restrict__ maps, const LevelDev *__restrict__ 
             }
             uint16_t *qp = queue + qn + incl - c_own;
             qn += __shfl_sync(0xffffffffu, incl, 31);
-            // pop the nibbles (last step first) and store the flagged pixels as (y << 6 | x)
+            // pop the nibbles (last step first) and store the flagged pixels as y * tp + x
             for (int i = U - 1; i >= 0; --i) {
                 const unsigned nib = wlo & 15u;
                 wlo = __funnelshift_r(wlo, whi, 4);
                 whi >>= 4;
                 int e0;
-                if (round == 0) e0 = (lane << 6) + 4 * i;
+                if (round == 0) e0 = lane * tp + 4 * i;
                 else {
                     const int u = units_a + i * 32 + lane;
                     const int y = (int)(((unsigned)u * inv_nux) >> 20);
-                    e0 = y * (64 - 4 * nux) + 4 * u;  // (y << 6) | (4 * j)
+                    e0 = y * (tp - 4 * nux) + 4 * u;  // y * tp + 4 * j
                 }
                 if (nib & 1u) *qp++ = (uint16_t)e0;
                 if (nib & 2u) *qp++ = (uint16_t)(e0 + 1);
@@ -298,10 +299,9 @@ k_fast_cells(const CUtensorMap *__restrict__ maps, const LevelDev *__restrict__ 
             int idx = 0, m = 0;
             if (i < qn) {
                 idx = queue[i];
-                const int y = idx >> 6, x = idx & 63;
-                m = arc_score(tile + (y + 3) * tp + x + off, tp);
+                m = arc_score(tile + 3 * tp + off + idx, tp);
                 m = m > thr ? m : 0;
-                if (m) score[(y + 1) * sp + x + 1] = (uint8_t)min(m, 255);
+                if (m) score[sp + 1 + idx] = (uint8_t)min(m, 255);
             }
             __syncwarp();
             const unsigned bm = __ballot_sync(0xffffffffu, m != 0);
@@ -328,7 +328,7 @@ k_fast_cells(const CUtensorMap *__restrict__ maps, const LevelDev *__restrict__ 
             bool keep = false;
             if (i < cn) {
                 idx = queue[i];
-                const uint8_t *s = score + ((idx >> 6) + 1) * sp + (idx & 63) + 1;
+                const uint8_t *s = score + sp + 1 + idx;
                 const int v = s[0];
                 const int n0 = max3(s[-sp - 1], s[-sp], s[-sp + 1]);
                 const int n1 = max3(s[-1], s[1], s[sp - 1]);
@@ -353,8 +353,8 @@ k_fast_cells(const CUtensorMap *__restrict__ maps, const LevelDev *__restrict__ 
         uint32_t packed = 0;
         if (i < kn) {
             const int idx = queue[i];
-            const int y = idx >> 6, x = idx & 63;
-            const int m = score[(y + 1) * sp + x + 1];
+            const int y = idx / tp, x = idx - y * tp;  // compile-time pitch: a multiply-high
+            const int m = score[sp + 1 + idx];
             emit = true;
             // coordinates relative to (minBorderX, minBorderY) = (16,16), as upstream's vToDistributeKeys
             packed = (uint32_t)(c.x0 + x - ORBB_MIN_BORDER) | ((uint32_t)(c.y0 + y - ORBB_MIN_BORDER) << 12) |
@@ -402,7 +402,7 @@ cudaError_t launch_fast(const void *tma_maps, const LevelDev *d_levels, const Ce
 #define ORBB_FAST_TP(P)                                                                                                     \
     case P: return launch_fast_t<false, false, P>(nullptr, d_levels, d_cells, n_cells, n_levels, d_cand_count, t_lo, t_hi, cfg, \
                                                   frame_base, n_frames, nullptr, nullptr, st)
-    if (cfg.score_pitch == cfg.tile_pitch - 8) {
+    {
         switch (cfg.tile_pitch) {  // the pitches orbb_create produces: round_up(widest cell + 12, 4) | 4
             ORBB_FAST_TP(44); ORBB_FAST_TP(52); ORBB_FAST_TP(60); ORBB_FAST_TP(68); ORBB_FAST_TP(76);
             default: break;

@@ -486,6 +486,7 @@ extern "C" int orbb_create(orbb_handle **out, const orbb_params *params, int wid
                 L.n_cell_x = std::max(L.n_cell_x, j + 1);
                 CellEntry c{};
                 c.level = (int16_t)l; c.x0 = (int16_t)x0; c.y0 = (int16_t)y0; c.cw = (int16_t)cw; c.ch = (int16_t)ch;
+                c.inv_nux = (1u << 20) / (unsigned)((cw + 3) >> 2) + 1u;
                 cells.push_back(c);
                 max_cw = std::max(max_cw, cw); max_ch = std::max(max_ch, ch);
                 cap += ((cw + 1) / 2) * ((ch + 1) / 2);  // strict 3x3 maxima: at most one per 2x2 block
@@ -573,7 +574,6 @@ extern "C" int orbb_create(orbb_handle **out, const orbb_params *params, int wid
     h->fcfg.tile_pitch = (int)round_up(max_cw + 12, 4) | 4;  // odd number of words: rows never share a bank pattern
     h->fcfg.tma_pitch = (int)round_up(max_cw + 10 + 15 + 4, 16);  // 16-byte aligned box start: up to 15 bytes of phase
     h->fcfg.tile_rows = max_ch + 6;
-    h->fcfg.score_pitch = h->fcfg.tile_pitch - 8;  // >= max_cw + 4, multiple of 4; tied to the tile pitch (k_fast_cells<.., TP>)
     h->fcfg.score_rows = max_ch + 2;
     h->fcfg.queue_len = (int)round_up((size_t)max_cw * max_ch, 8);
     // TMA staging of the FAST windows is opt-in (ORBB_FAST_TMA=1): measured on B200 it is not faster than the
@@ -581,8 +581,11 @@ extern "C" int orbb_create(orbb_handle **out, const orbb_params *params, int wid
     // 1.4 KB more shared memory per warp), see DESIGN.md.
     const bool want_tma = getenv("ORBB_FAST_TMA") && atoi(getenv("ORBB_FAST_TMA")) != 0;
     if (!want_tma) h->fcfg.tma_pitch = 0;
-    h->fcfg.warp_bytes = (int)round_up((size_t)std::max(h->fcfg.tile_pitch, h->fcfg.tma_pitch) * h->fcfg.tile_rows +
-                                           (size_t)h->fcfg.score_pitch * h->fcfg.score_rows + 2 * (size_t)h->fcfg.queue_len, 128);  // 128-byte aligned TMA destination per warp
+    // the score tile shares the window tile's pitch, so ONE queue entry (y * pitch + x) addresses both
+    h->fcfg.score_pitch = std::max(h->fcfg.tile_pitch, h->fcfg.tma_pitch);
+    h->fcfg.tile_bytes = (int)round_up((size_t)h->fcfg.score_pitch * h->fcfg.tile_rows, 16);
+    h->fcfg.score_bytes = (int)round_up((size_t)h->fcfg.score_pitch * h->fcfg.score_rows, 16);
+    h->fcfg.warp_bytes = (int)round_up((size_t)h->fcfg.tile_bytes + h->fcfg.score_bytes + 2 * (size_t)h->fcfg.queue_len, 128);  // 128-byte aligned TMA destination per warp
     if (want_tma && h->fcfg.tma_pitch <= 256 && h->fcfg.tile_rows <= 256) {
         std::vector<unsigned char> store(fast_tma_maps_bytes() + 128);
         void *hm = reinterpret_cast<void *>((reinterpret_cast<uintptr_t>(store.data()) + 63) & ~(uintptr_t)63);

@@ -104,13 +104,15 @@ struct PfTile {
 };
 
 struct CellEntry {  // one FAST work item = one upstream 30-px cell
-    int16_t level, x0, y0, cw, ch, pad0, pad1, pad2;  // tested-range origin (ROI coords) and size
+    int16_t level, x0, y0, cw, ch, pad0;  // tested-range origin (ROI coords) and size
+    uint32_t inv_nux;                      // (1 << 20) / ceil(cw / 4) + 1: floor(u / units per row) by multiply + shift
 };
 
 struct FastSmemCfg {
     int tile_pitch, tile_rows;    // bytes, rows of the per-warp image tile (manual staging)
     int tma_pitch;                // row bytes of the TMA box (16-byte aligned start => up to 15 bytes of phase)
-    int score_pitch, score_rows;  // per-warp score tile (1-px zero frame)
+    int score_pitch, score_rows;  // per-warp score tile (1-px zero frame); pitch == tile pitch (one offset addresses both)
+    int tile_bytes, score_bytes;  // sizes of the two tiles inside the warp's block, multiples of 16
     int queue_len;                // u16 entries
     int warp_bytes;               // total per warp (multiple of 16)
 };
