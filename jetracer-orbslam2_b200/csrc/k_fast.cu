@@ -219,11 +219,16 @@ k_fast_cells(const CUtensorMap *__restrict__ maps, const LevelDev *__restrict__ 
                 const uint32_t *row = tile32 + ((lane < rows_a ? lane : 0) + 3) * tpw;  // row[0] = left word of unit 0
                 const unsigned live = lane < rows_a ? 0x80808080u : 0u;
                 unsigned left = row[0], cc = row[1];
+                // rows +-2 slide the same way: they feed the two diagonal pairs (2,10) and (6,14)
+                unsigned lp = row[2 * tpw], cp = row[1 + 2 * tpw], lm = row[-2 * tpw], cm = row[1 - 2 * tpw];
                 for (int j = 0; j < U; ++j) {
                     const unsigned right = row[j + 2], dn = row[j + 1 + 3 * tpw], up = row[j + 1 - 3 * tpw];
+                    const unsigned rp = row[j + 2 + 2 * tpw], rm = row[j + 2 - 2 * tpw];
                     const unsigned rt = __funnelshift_r(cc, right, 24), lf = __funnelshift_r(left, cc, 8);
-                    const unsigned flags = precheck(cc, up, dn, lf, rt) & (j == U - 1 ? last_mask & live : live);
-                    left = cc; cc = right;
+                    unsigned flags = precheck(cc, up, dn, lf, rt) & (j == U - 1 ? last_mask & live : live);
+                    flags &= precheck(cc, __funnelshift_r(lm, cm, 16), __funnelshift_r(cp, rp, 16),   // (-2,-2) | (+2,+2)
+                                      __funnelshift_r(lp, cp, 16), __funnelshift_r(cm, rm, 16));      // (-2,+2) | (+2,-2)
+                    left = cc; cc = right; lp = cp; cp = rp; lm = cm; cm = rm;
                     // bits 7 / 15 / 23 / 31 -> one nibble pushed into the lane's 64-bit flag word: the multiply moves the
                     // four bits to 28..31 (no two partial products meet there), two funnel shifts push them in
                     const unsigned prod = flags * 0x00204081u;
