@@ -65,7 +65,7 @@ __device__ __forceinline__ int arc_score(const uint8_t *p, int tp) {
 // the arc score and the +-3-row offsets of the precheck are instruction immediates off ONE base register, which takes
 // about a dozen address instructions out of every scored pixel.  The score tile has the same pitch.
 template <bool DUMP, bool TMA, int TP>
-__global__ void __launch_bounds__(FAST_WARPS * 32)
+__global__ void __launch_bounds__(FAST_WARPS * 32, 9)
 k_fast_cells(const CUtensorMap *__restrict__ maps, const LevelDev *__restrict__ levels, const CellEntry *__restrict__ cells, int n_cells, int n_levels,
              int *__restrict__ cand_count, int t_lo, int t_hi, FastSmemCfg cfg, int frame_base,
              uint8_t *__restrict__ dump, const long long *__restrict__ dump_off) {
@@ -120,54 +120,51 @@ k_fast_cells(const CUtensorMap *__restrict__ maps, const LevelDev *__restrict__ 
                          : "=r"(done) : "r"(bar) : "memory");
     } else {
         // 128-bit staging WITH re-alignment.  Each lane loads ONE aligned 16-byte chunk of a window row (ROI rows are
-        // 128-byte aligned by layout) -- 4 lanes per row, 8 when a row spans more than four chunks -- and gets the
-        // chunk to its right from the next lane with four shuffles; the output words are funnel shifts of the two
-        // (the word offset of the window inside its first chunk is uniform per cell, so the four variants are a
-        // uniform switch).  Round 1 loaded both chunks per lane: every chunk travelled twice through the LSU data
-        // pipe, which is what bounds this kernel (profiles/r02_k_fast_cells_wavefronts.txt); a shuffle is one
-        // conflict-free wavefront.
+        // 128-byte aligned by layout) -- 4 lanes per row, 8 when a row spans more than four chunks -- and every row of
+        // the lane is in flight before the first one is used (one exposed L2 round trip per cell).  The lane shifts its
+        // own four words right by the byte phase of the window (the word after the chunk comes from the next lane: one
+        // shuffle) and stores them at the tile position its chunk lands on, word 4 * chunk - (word offset of the
+        // window inside its first chunk): the re-alignment by whole words is an address, not a data movement (round 1
+        // loaded both chunks per lane, the first round-2 form selected the four output words with a uniform switch after
+        // four shuffles: 14 % of the kernel's instructions, profiles/r02b_k_fast_cells_phases.txt).  32-bit stores:
+        // the tile keeps an odd word pitch, so the byte loads of the arc score (pixels of many rows in one warp
+        // instruction) spread over all banks; a 16-byte pitch would fold rows 8 apart onto the same banks.
         const int gx = c.x0 - 4, xa16 = gx & ~15, wo = (gx - xa16) >> 2, sh = (gx & 3) * 8;
-        const int nwords = (cw + 7 + 3) >> 2, ng = (nwords + 3) >> 2;  // output words per row, 4-word groups per row
+        const int nwords = (cw + 7 + 3) >> 2;               // window words per row
+        const int nld = ((wo + nwords) >> 2) + 1;           // chunks per row that hold them (the funnel shift reads one word ahead)
         const int nrows = ch + 6;
-        const int lps = ng + 1 <= 4 ? 2 : 3, rpi = 32 >> lps;        // log2(lanes per row), rows per step
+        const int lps = nld <= 4 ? 2 : 3, rpi = 32 >> lps;  // log2(lanes per row), rows per step
         const int g = lane & ((1 << lps) - 1), rl = lane >> lps;
         const uint8_t *src = L.img + (size_t)frame * L.frame_stride + (size_t)(ORBB_BORDER + c.y0 - 3) * L.pitch + ORBB_ROI_X0 + xa16 + 16 * g;
+        const unsigned pitch = (unsigned)L.pitch;
         const bool in_row = 16 * g + 16 <= L.pitch - (ORBB_ROI_X0 + xa16);  // never read past the padded row
-        for (int r0 = 0; r0 < nrows; r0 += 2 * rpi) {                 // two rows (two 128-bit loads) in flight per lane
-            uint4 a[2];
+        const int k0 = 4 * g - wo;                          // tile word of the lane's first output
+        unsigned keep = 0;                                  // which of the four outputs land inside the tile row
 #pragma unroll
-            for (int u = 0; u < 2; ++u) {
-                const int r = min(r0 + u * rpi + rl, nrows - 1);
-                a[u] = in_row ? __ldg(reinterpret_cast<const uint4 *>(src + (size_t)r * L.pitch)) : make_uint4(0u, 0u, 0u, 0u);
+        for (int i = 0; i < 4; ++i) keep |= (g < nld && k0 + i >= 0 && k0 + i < tpw) ? 1u << i : 0u;
+        uint32_t *t0 = reinterpret_cast<uint32_t *>(tile) + k0;
+        constexpr int NF = 4;                               // rows in flight per lane (38-row windows at 8 rows per step: one round)
+        for (int rb = 0; rb < nrows; rb += NF * rpi) {  // rb: first row of the round, warp-uniform (the shuffles need every lane)
+            const int r0 = rb + rl;
+            uint4 a[NF];
+#pragma unroll
+            for (int u = 0; u < NF; ++u) {
+                const unsigned r = (unsigned)min(r0 + u * rpi, nrows - 1);
+                a[u] = make_uint4(0u, 0u, 0u, 0u);
+                if (in_row && rb + u * rpi < nrows)  // (whole steps past the window are skipped: warp-uniform)
+                    a[u] = __ldg(reinterpret_cast<const uint4 *>(src + r * pitch));
             }
 #pragma unroll
-            for (int u = 0; u < 2; ++u) {
-                uint4 bq;  // the chunk to the right: lane + 1 (the last lane of a row group produces no output)
-                bq.x = __shfl_down_sync(0xffffffffu, a[u].x, 1); bq.y = __shfl_down_sync(0xffffffffu, a[u].y, 1);
-                bq.z = __shfl_down_sync(0xffffffffu, a[u].z, 1); bq.w = __shfl_down_sync(0xffffffffu, a[u].w, 1);
-                uint4 o;
-                switch (wo) {  // uniform per cell
-                    case 0: o = make_uint4(__funnelshift_r(a[u].x, a[u].y, sh), __funnelshift_r(a[u].y, a[u].z, sh),
-                                           __funnelshift_r(a[u].z, a[u].w, sh), __funnelshift_r(a[u].w, bq.x, sh)); break;
-                    case 1: o = make_uint4(__funnelshift_r(a[u].y, a[u].z, sh), __funnelshift_r(a[u].z, a[u].w, sh),
-                                           __funnelshift_r(a[u].w, bq.x, sh), __funnelshift_r(bq.x, bq.y, sh)); break;
-                    case 2: o = make_uint4(__funnelshift_r(a[u].z, a[u].w, sh), __funnelshift_r(a[u].w, bq.x, sh),
-                                           __funnelshift_r(bq.x, bq.y, sh), __funnelshift_r(bq.y, bq.z, sh)); break;
-                    default: o = make_uint4(__funnelshift_r(a[u].w, bq.x, sh), __funnelshift_r(bq.x, bq.y, sh),
-                                            __funnelshift_r(bq.y, bq.z, sh), __funnelshift_r(bq.z, bq.w, sh)); break;
-                }
-                // four 32-bit stores: the tile keeps an odd word pitch, so the byte loads of the arc score (pixels
-                // of many rows in one warp instruction) spread over all banks; a 16-byte pitch would fold rows 8
-                // apart onto the same banks
-                const int r = r0 + u * rpi + rl;
-                if (r < nrows && g < ng) {
-                    uint32_t *t = reinterpret_cast<uint32_t *>(tile + r * tp) + 4 * g;
-                    const int left = tpw - 4 * g;
-                    t[0] = o.x;
-                    if (left > 1) t[1] = o.y;
-                    if (left > 2) t[2] = o.z;
-                    if (left > 3) t[3] = o.w;
-                }
+            for (int u = 0; u < NF; ++u) {
+                if (rb + u * rpi >= nrows) break;
+                const unsigned nx = __shfl_down_sync(0xffffffffu, a[u].x, 1);  // first word of the chunk to the right
+                const int r = r0 + u * rpi;
+                const unsigned m = r < nrows ? keep : 0u;
+                uint32_t *t = t0 + r * tpw;
+                if (m & 1u) t[0] = __funnelshift_r(a[u].x, a[u].y, sh);
+                if (m & 2u) t[1] = __funnelshift_r(a[u].y, a[u].z, sh);
+                if (m & 4u) t[2] = __funnelshift_r(a[u].z, a[u].w, sh);
+                if (m & 8u) t[3] = __funnelshift_r(a[u].w, nx, sh);
             }
         }
         for (int i = lane; i < cfg.score_bytes >> 4; i += 32) reinterpret_cast<uint4 *>(score)[i] = make_uint4(0u, 0u, 0u, 0u);
