@@ -135,28 +135,25 @@ k_fast_cells(const CUtensorMap *__restrict__ maps, const LevelDev *__restrict__ 
         const int nrows = ch + 6;
         const int lps = nld <= 4 ? 2 : 3, rpi = 32 >> lps;  // log2(lanes per row), rows per step
         const int g = lane & ((1 << lps) - 1), rl = lane >> lps;
-        const uint8_t *src = L.img + (size_t)frame * L.frame_stride + (size_t)(ORBB_BORDER + c.y0 - 3) * L.pitch + ORBB_ROI_X0 + xa16 + 16 * g;
+        // a chunk that would reach past the padded row is never part of a window (those lanes re-read chunk 0 and store nothing)
+        const bool in_row = 16 * g + 16 <= L.pitch - (ORBB_ROI_X0 + xa16);
+        const uint8_t *src = L.img + (size_t)frame * L.frame_stride + (size_t)(ORBB_BORDER + c.y0 - 3) * L.pitch + ORBB_ROI_X0 + xa16 + (in_row ? 16 * g : 0);
+        asm volatile("" : "+l"(src));                       // one pointer register pair, not re-derived per load
         const unsigned pitch = (unsigned)L.pitch;
-        const bool in_row = 16 * g + 16 <= L.pitch - (ORBB_ROI_X0 + xa16);  // never read past the padded row
         const int k0 = 4 * g - wo;                          // tile word of the lane's first output
         unsigned keep = 0;                                  // which of the four outputs land inside the tile row
 #pragma unroll
-        for (int i = 0; i < 4; ++i) keep |= (g < nld && k0 + i >= 0 && k0 + i < tpw) ? 1u << i : 0u;
+        for (int i = 0; i < 4; ++i) keep |= (in_row && g < nld && k0 + i >= 0 && k0 + i < tpw) ? 1u << i : 0u;
         uint32_t *t0 = reinterpret_cast<uint32_t *>(tile) + k0;
-        constexpr int NF = 4;                               // rows in flight per lane (38-row windows at 8 rows per step: one round)
-        for (int rb = 0; rb < nrows; rb += NF * rpi) {  // rb: first row of the round, warp-uniform (the shuffles need every lane)
+        constexpr int NF = 5;                               // rows in flight per lane: a 38-row window at 8 rows per step is one round
+        for (int rb = 0; rb < nrows; rb += NF * rpi) {      // rb: first row of the round, warp-uniform (the shuffles need every lane)
             const int r0 = rb + rl;
             uint4 a[NF];
 #pragma unroll
-            for (int u = 0; u < NF; ++u) {
-                const unsigned r = (unsigned)min(r0 + u * rpi, nrows - 1);
-                a[u] = make_uint4(0u, 0u, 0u, 0u);
-                if (in_row && rb + u * rpi < nrows)  // (whole steps past the window are skipped: warp-uniform)
-                    a[u] = __ldg(reinterpret_cast<const uint4 *>(src + r * pitch));
-            }
+            for (int u = 0; u < NF; ++u)                    // rows past the window re-read its last row
+                a[u] = __ldg(reinterpret_cast<const uint4 *>(src + (unsigned)min(r0 + u * rpi, nrows - 1) * pitch));
 #pragma unroll
             for (int u = 0; u < NF; ++u) {
-                if (rb + u * rpi >= nrows) break;
                 const unsigned nx = __shfl_down_sync(0xffffffffu, a[u].x, 1);  // first word of the chunk to the right
                 const int r = r0 + u * rpi;
                 const unsigned m = r < nrows ? keep : 0u;
