@@ -223,11 +223,13 @@ k_fast_cells(const CUtensorMap *__restrict__ maps, const LevelDev *__restrict__ 
                     flags &= precheck(cc, __funnelshift_r(lm, cm, 16), __funnelshift_r(cp, rp, 16),   // (-2,-2) | (+2,+2)
                                       __funnelshift_r(lp, cp, 16), __funnelshift_r(cm, rm, 16));      // (-2,+2) | (+2,-2)
                     left = cc; cc = right; lp = cp; cp = rp; lm = cm; cm = rm;
-                    // bits 7 / 15 / 23 / 31 -> one nibble pushed into the lane's 64-bit flag word: the multiply moves the
-                    // four bits to 28..31 (no two partial products meet there), two funnel shifts push them in
-                    const unsigned prod = flags * 0x00204081u;
-                    whi = __funnelshift_l(wlo, whi, 4);
-                    wlo = __funnelshift_l(prod, wlo, 4);
+                    // bits 7 / 15 / 23 / 31 -> one nibble pushed into the TOP of the lane's 64-bit flag word: the high half of
+                    // the product holds the four bits at 0..3 (no two partial products meet at or below them; what lies
+                    // above is dropped by the funnel shift), two funnel shifts push them in.  After U steps pixel x of
+                    // the row sits at bit x + 64 - 4 * U.
+                    const unsigned nib = __umulhi(flags, 0x02040810u);
+                    wlo = __funnelshift_r(wlo, whi, 4);
+                    whi = __funnelshift_r(whi, nib, 4);
                 }
             } else {
                 // generic form (second round, TMA staging): unit = first + step * 32 + lane, index math per step
@@ -256,9 +258,9 @@ k_fast_cells(const CUtensorMap *__restrict__ maps, const LevelDev *__restrict__ 
                         lf = __funnelshift_r(row[0], cc, 8);
                     }
                     const unsigned vm = valid ? (j == nux - 1 ? last_mask : 0x80808080u) : 0u;
-                    const unsigned prod = (precheck(cc, up, dn, lf, rt) & vm) * 0x00204081u;
-                    whi = __funnelshift_l(wlo, whi, 4);
-                    wlo = __funnelshift_l(prod, wlo, 4);
+                    const unsigned nib = __umulhi(precheck(cc, up, dn, lf, rt) & vm, 0x02040810u);
+                    wlo = __funnelshift_r(wlo, whi, 4);
+                    whi = __funnelshift_r(whi, nib, 4);
                 }
             }
             // queue positions: exclusive prefix sum of the lanes' counts (5 shuffles per round)
@@ -271,22 +273,25 @@ k_fast_cells(const CUtensorMap *__restrict__ maps, const LevelDev *__restrict__ 
             }
             uint16_t *qp = queue + qn + incl - c_own;
             qn += __shfl_sync(0xffffffffu, incl, 31);
-            // pop the nibbles (last step first) and store the flagged pixels as y * tp + x
-            for (int i = U - 1; i >= 0; --i) {
-                const unsigned nib = wlo & 15u;
-                wlo = __funnelshift_r(wlo, whi, 4);
-                whi >>= 4;
-                int e0;
-                if (round == 0) e0 = lane * tp + 4 * i;
-                else {
-                    const int u = units_a + i * 32 + lane;
-                    const int y = (int)(((unsigned)u * inv_nux) >> 20);
-                    e0 = y * (tp - 4 * nux) + 4 * u;  // y * tp + 4 * j
+            // walk the SET bits only (most significant first) and store the flagged pixels as y * tp + x: a lane spends
+            // one short iteration per flagged pixel of its row (~6 of 30 on the bench texture; the warp runs as long as its
+            // fullest row) instead of a fixed 30 instructions per 4-pixel unit
+            const int xoff = 4 * U - 64;  // bit position -> 4 * step + pixel
+            const int row_e = lane * tp + xoff;
+#pragma unroll
+            for (int half = 1; half >= 0; --half) {
+                unsigned w = half ? whi : wlo;
+                while (w) {
+                    const int b = 31 - __clz(w);
+                    w &= ~(1u << b);
+                    int e = row_e + 32 * half + b;
+                    if (round != 0) {
+                        const int pos = 32 * half + b + xoff, u = units_a + (pos >> 2) * 32 + lane;
+                        const int y = (int)(((unsigned)u * inv_nux) >> 20);
+                        e = y * (tp - 4 * nux) + 4 * u + (pos & 3);  // y * tp + 4 * j + pixel
+                    }
+                    *qp++ = (uint16_t)e;
                 }
-                if (nib & 1u) *qp++ = (uint16_t)e0;
-                if (nib & 2u) *qp++ = (uint16_t)(e0 + 1);
-                if (nib & 4u) *qp++ = (uint16_t)(e0 + 2);
-                if (nib & 8u) *qp++ = (uint16_t)(e0 + 3);
             }
         }
         __syncwarp();
