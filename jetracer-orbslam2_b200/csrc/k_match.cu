@@ -166,6 +166,7 @@ k_match_merge(const int4 *__restrict__ partial, int partial_stride, int n_split,
 // sequential search.  (The first version ran one THREAD per query over train tiles staged in shared memory: the same
 // work per pair, but a lone frame pair kept only ~10 CTAs busy for 66 us; this form takes the whole GPU.)
 #define WIN_THREADS 128
+#define WIN_CHUNK 2048  // train positions staged per round (16 KB)
 // Batched form (q_counts != nullptr): blockIdx.y = frame pair, rows of frame f start at f * max_kp in every array and
 // the set sizes come from the device-side count arrays.
 __global__ void __launch_bounds__(WIN_THREADS)
@@ -181,26 +182,47 @@ k_match_windowed(const uint4 *__restrict__ query, const uint8_t *__restrict__ q_
         out_idx += row0; out_dist += row0;
         n_matched = nullptr;
     }
+    // The CTA's four queries walk the SAME train positions: they are staged once per CTA in shared memory, WIN_CHUNK at
+    // a time, with every load of a thread in flight together -- read straight from global memory the 38 steps of a
+    // 1200-keypoint frame were 38 exposed L2 round trips per warp (19 us for a lone frame pair).
+    __shared__ float2 s_txy[WIN_CHUNK];
     const int lane = threadIdx.x & 31;
     const int q = blockIdx.x * (WIN_THREADS / 32) + (threadIdx.x >> 5);  // warp-uniform
-    if (q >= nq) return;
-    const uint4 qa = __ldg(query + (size_t)q * 2), qb = __ldg(query + (size_t)q * 2 + 1);
-    const float qx = *reinterpret_cast<const float *>(q_xy + (size_t)q * q_stride);
-    const float qy = *reinterpret_cast<const float *>(q_xy + (size_t)q * q_stride + 4);
+    if (blockIdx.x * (WIN_THREADS / 32) >= nq) return;  // block-uniform: no query for this CTA
+    const bool active = q < nq;
+    uint4 qa = make_uint4(0u, 0u, 0u, 0u), qb = qa;
+    float qx = 0.0f, qy = 0.0f;
+    if (active) {
+        qa = __ldg(query + (size_t)q * 2); qb = __ldg(query + (size_t)q * 2 + 1);
+        qx = *reinterpret_cast<const float *>(q_xy + (size_t)q * q_stride);
+        qy = *reinterpret_cast<const float *>(q_xy + (size_t)q * q_stride + 4);
+    }
     // accept only d < max_hamming; the packed key orders by distance, then by train index
     unsigned best = 0xffffffffu;
-    for (int tb = 0; tb < nt; tb += 32) {
-        const int t = tb + lane;
-        if (t < nt) {
-            const uint8_t *p = t_xy + (size_t)t * t_stride;
-            const float px = *reinterpret_cast<const float *>(p), py = *reinterpret_cast<const float *>(p + 4);
-            if (fabsf(__fsub_rn(qx, px)) <= max_px && fabsf(__fsub_rn(qy, py)) <= max_px) {
-                const uint4 a = __ldg(train + (size_t)t * 2), b = __ldg(train + (size_t)t * 2 + 1);
-                const int d = hamming256(qa, qb, a, b);
-                if (d < max_hamming) best = min(best, ((unsigned)d << 16) | (unsigned)t);
+    for (int c0 = 0; c0 < nt; c0 += WIN_CHUNK) {
+        const int cn = min(nt - c0, WIN_CHUNK);
+        if (c0) __syncthreads();
+#pragma unroll 4
+        for (int i = threadIdx.x; i < cn; i += WIN_THREADS) {
+            const uint8_t *p = t_xy + (size_t)(c0 + i) * t_stride;
+            s_txy[i] = make_float2(*reinterpret_cast<const float *>(p), *reinterpret_cast<const float *>(p + 4));
+        }
+        __syncthreads();
+        if (!active) continue;
+        for (int tb = 0; tb < cn; tb += 32) {
+            const int i = tb + lane;
+            if (i < cn) {
+                const float2 pt = s_txy[i];
+                if (fabsf(__fsub_rn(qx, pt.x)) <= max_px && fabsf(__fsub_rn(qy, pt.y)) <= max_px) {
+                    const int t = c0 + i;
+                    const uint4 a = __ldg(train + (size_t)t * 2), b = __ldg(train + (size_t)t * 2 + 1);
+                    const int d = hamming256(qa, qb, a, b);
+                    if (d < max_hamming) best = min(best, ((unsigned)d << 16) | (unsigned)t);
+                }
             }
         }
     }
+    if (!active) return;
     best = __reduce_min_sync(0xffffffffu, best);
     if (lane == 0) {
         const bool ok = best != 0xffffffffu;

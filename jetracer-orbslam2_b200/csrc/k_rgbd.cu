@@ -144,8 +144,9 @@ __device__ __forceinline__ int block_rank(bool keep, int *s_warp, int *chunk_tot
     return before + __popc(m & ((1u << lane) - 1u));
 }
 
-// ---- keypoints -> 3-D points.  CTA = one frame.
-#define KP_THREADS 256
+// ---- keypoints -> 3-D points.  CTA = one frame; 1024 threads, so ~1000 keypoints are one or two chunks (each chunk is
+// a chain of two dependent global loads and two barriers: a lone frame took 15.6 us with 256 threads, five chunks)
+#define KP_THREADS 1024
 __global__ void __launch_bounds__(KP_THREADS)
 k_kp_to_point(const uint32_t *__restrict__ aligned, const orbb_intrinsics in, const orbb_keypoint *__restrict__ kp_in,
               const uint4 *__restrict__ desc_in, const int *__restrict__ counts_in, int max_kp,
@@ -312,6 +313,31 @@ cudaError_t launch_compact_pairs(const int *idx, const int *q_counts, int n_fram
     k_compact_pairs<<<n_frames, KP_THREADS, 0, st>>>(idx, q_counts, max_kp, q_points, t_points,
                                                      static_cast<const uint8_t *>(t_xy), t_stride, prev_out, curr_out, xy_out,
                                                      n_matched);
+    return cudaGetLastError();
+}
+
+// Stage bookkeeping between batches in ONE launch (it used to be five device-to-device copies, 2-3 us each inside a graph):
+// the previous batch's last frame (row `carry` of the keypoint / descriptor / point / valid-count arrays) becomes row 0, and
+// the extraction's per-frame counts are copied into the result block.  Rows are multiples of 4 bytes.
+__global__ void k_stage_carry(uint32_t *kp, uint32_t *desc, uint32_t *pts, int *valid, int carry, int kp_w, int desc_w, int pts_w,
+                              int *counts_dst, const int *counts_src, int n_counts) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_counts) counts_dst[i] = counts_src[i];
+    if (carry <= 0) return;
+    if (i == 0) valid[0] = valid[carry];
+    if (i < kp_w) kp[i] = kp[(size_t)carry * kp_w + i];
+    else if (i < kp_w + desc_w) desc[i - kp_w] = desc[(size_t)carry * desc_w + i - kp_w];
+    else if (i < kp_w + desc_w + pts_w) pts[i - kp_w - desc_w] = pts[(size_t)carry * pts_w + i - kp_w - desc_w];
+}
+
+cudaError_t launch_stage_carry(orbb_keypoint *kp, uint8_t *desc, double *pts, int *valid, int carry, int max_kp, int *counts_dst,
+                               const int *counts_src, int n_counts, cudaStream_t st) {
+    const int kp_w = (int)(sizeof(orbb_keypoint) / 4) * max_kp, desc_w = 8 * max_kp, pts_w = 6 * max_kp;
+    const int total = carry > 0 ? kp_w + desc_w + pts_w : 0;
+    const int n = total > n_counts ? total : n_counts;
+    k_stage_carry<<<(n + 255) / 256, 256, 0, st>>>(reinterpret_cast<uint32_t *>(kp), reinterpret_cast<uint32_t *>(desc),
+                                                   reinterpret_cast<uint32_t *>(pts), valid, carry, kp_w, desc_w, pts_w, counts_dst,
+                                                   counts_src, n_counts);
     return cudaGetLastError();
 }
 

@@ -986,6 +986,15 @@ extern "C" int orbb_extract_batch_device(orbb_handle *h, const uint8_t *d_images
     return ORBB_OK;
 }
 
+// Internal (same library, orbb_stage.cu)
+namespace orbb {
+// a replay of a graph that holds entry points of this handle: the handle's bookkeeping follows
+void note_replay(orbb_handle *h, int n_frames, long long launches) {
+    h->n_frames_last = n_frames;
+    h->n_launches += launches;
+}
+}  // namespace orbb
+
 // Host entry points: chunks of the batch flow through the handle's streams (H2D copy stream -> two alternating
 // compute streams -> D2H copy stream) linked by events, so PCIe transfers overlap the kernels; staging buffers
 // are double-buffered by ticket parity so the next batch's H2D runs under the current batch's kernels.

@@ -57,6 +57,12 @@ struct LevelDev {
     float scale, patch_size;     // mvScaleFactor[l], (float)(int)(31*scale)
 };
 
+// orbb_api.cu, used by orbb_stage.cu: see the definition
+void note_replay(orbb_handle *h, int n_frames, long long launches);
+// k_rgbd.cu, used by orbb_stage.cu
+cudaError_t launch_stage_carry(orbb_keypoint *kp, uint8_t *desc, double *pts, int *valid, int carry, int max_kp, int *counts_dst,
+                               const int *counts_src, int n_counts, cudaStream_t st);
+
 #ifdef __CUDACC__
 // Programmatic dependent launch (PDL): a kernel launched with launch_pdl() may become resident while its predecessor
 // in the stream is still running; it must call pdl_wait() before it touches anything the predecessor writes

@@ -189,11 +189,19 @@ def test_reproject_match_compact(orbb, oracle, synth, with_T):
     assert total > 50, "test too weak: hardly any match went through"
 
 
-def test_rgbd_frame_stage_sequence(orbb, oracle, synth):
-    """The host stage over a moving sequence fed as batches of 3 + 1 + 4 frames (two in flight):
+@pytest.mark.parametrize("plan,max_batch,graph", [
+    ((3, 1, 4), 4, "1"),         # small batches: every submit replays a captured graph (partial and full-block D2H forms)
+    ((3, 1, 4), 4, "0"),         # the same through the streamed path
+    ((1,) * 8, 1, "1"),          # the reference's operating mode: one frame per wake-up
+    ((5, 1, 2), 8, "1"),         # streamed batch -> graph -> graph: the hand-over between the two paths, carry row 5 -> 1
+    ((1, 6, 1), 8, "1"),         # graph -> streamed -> graph
+])
+def test_rgbd_frame_stage_sequence(orbb, oracle, synth, plan, max_batch, graph, monkeypatch):
+    """The host stage over a moving sequence of 8 frames fed as the batches of `plan` (two in flight):
     every frame's gated keypoints / descriptors / 3-D points and its matches against the previous frame -- across
     batch boundaries -- equal the oracle chain run frame by frame on the GPU extractor's raw output."""
     import torch
+    monkeypatch.setenv("ORBB_STAGE_GRAPH", graph)
     w, h, nfeat = 640, 480, 600
     base = synth.textured_frame(w, h, 4242)
     gray = [base]
@@ -205,17 +213,19 @@ def test_rgbd_frame_stage_sequence(orbb, oracle, synth):
     odi, ooi, oe = d435_pair(oracle, w, h, False)
     params = orbb.Params(nfeat, 1.2, 8, 20, 7)
     stage = orbb.RgbdFrameStage(params, di, oi, e, depth_scale=0.001, max_pixel_distance=6.0, max_hamming_distance=60,
-                                max_batch=4)
+                                max_batch=max_batch)
     rng = np.random.default_rng(11)
     T = np.tile(np.eye(4), (8, 1, 1))
     T[:, :3, 3] = rng.normal(0, 1.5, (8, 3))  # millimetres: depth units are raw
-    t0 = stage.submit(gray[0:3], depth[0:3], T[0:3])
-    t1 = stage.submit(gray[3:4], depth[3:4], T[3:4])
-    r0 = {k: (v.copy() if isinstance(v, np.ndarray) else v) for k, v in stage.wait(t0).items()}
-    t2 = stage.submit(gray[4:8], depth[4:8], T[4:8])
-    r1 = {k: (v.copy() if isinstance(v, np.ndarray) else v) for k, v in stage.wait(t1).items()}
-    r2 = {k: (v.copy() if isinstance(v, np.ndarray) else v) for k, v in stage.wait(t2).items()}
-    got = {k: np.concatenate([r[k] for r in (r0, r1, r2)]) for k in r0 if isinstance(r0[k], np.ndarray)}
+    assert sum(plan) == 8
+    results, pending, f0 = [], None, 0
+    for n in plan:  # submit batch k + 1 before waiting for batch k
+        t = stage.submit(gray[f0:f0 + n], depth[f0:f0 + n], T[f0:f0 + n])
+        if pending is not None:
+            results.append({k: (v.copy() if isinstance(v, np.ndarray) else v) for k, v in stage.wait(pending).items()})
+        pending, f0 = t, f0 + n
+    results.append({k: (v.copy() if isinstance(v, np.ndarray) else v) for k, v in stage.wait(pending).items()})
+    got = {k: np.concatenate([r[k] for r in results]) for k in results[0] if isinstance(results[0][k], np.ndarray)}
 
     ex = orbb.ORBextractor(nfeat, 1.2, 8, 20, 7, width=w, height=h, max_batch=8)
     kp, desc, counts = ex.extract_batch(gray)  # raw GPU output, GPU order (deterministic)
@@ -250,8 +260,9 @@ def test_rgbd_frame_stage_sequence(orbb, oracle, synth):
     stage.reset()
     r = stage.wait(stage.submit(gray[0:1], depth[0:1]))
     assert int(r["matched_keypoints_num"][0]) == 0
-    with pytest.raises(orbb.OrbbError):
-        stage.submit(gray[0:5], depth[0:5])  # over the stage's batch capacity
+    if max_batch < 8:
+        with pytest.raises(orbb.OrbbError):
+            stage.submit(gray[0:max_batch + 1], depth[0:max_batch + 1])  # over the stage's batch capacity
 
 
 @pytest.mark.parametrize("w,h", [(848, 480), (333, 251), (5, 3)])
