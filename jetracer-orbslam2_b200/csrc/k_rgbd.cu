@@ -157,39 +157,51 @@ k_kp_to_point(const uint32_t *__restrict__ aligned, const orbb_intrinsics in, co
     const int n = min(counts_in[f], max_kp);
     const uint32_t *dimg = aligned + f * in.width * in.height;
     int base = 0;
-    for (int i0 = 0; i0 < n; i0 += KP_THREADS) {
-        const int i = i0 + threadIdx.x;
-        bool keep = false;
-        orbb_keypoint k{};
-        int depth = 0;
-        if (i < n) {
-            k = kp_in[f * max_kp + i];
-            const int xi = (int)((double)k.x + 0.5), yi = (int)((double)k.y + 0.5);
-            if (xi >= 0 && yi >= 0 && xi < in.width && yi < in.height) depth = (int)dimg[(size_t)yi * in.width + xi];
-            keep = depth > 1 && k.response > 1.0f;
+    // two chunks per round: both chunks' keypoint and depth loads are in flight before the first barrier (the ranking
+    // barriers would otherwise serialise one dependent load chain per chunk)
+    for (int i0 = 0; i0 < n; i0 += 2 * KP_THREADS) {
+        orbb_keypoint k[2];
+        int depth[2] = {0, 0};
+        bool keep[2] = {false, false};
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const int i = i0 + u * KP_THREADS + threadIdx.x;
+            k[u] = kp_in[f * max_kp + min(i, n - 1)];
         }
-        int total;
-        const int r = base + block_rank(keep, s_warp, &total);
-        if (keep) {
-            const size_t o = f * max_kp + r;
-            kp_out[o] = k;
-            desc_out[2 * o] = desc_in[2 * (f * max_kp + i)];
-            desc_out[2 * o + 1] = desc_in[2 * (f * max_kp + i) + 1];
-            // deproject_pixel_to_point_double (cuda-align.cu:85-110): float32 normalisation, float64 afterwards
-            double x = (double)__fdiv_rn(__fsub_rn(k.x, in.ppx), in.fx);
-            double y = (double)__fdiv_rn(__fsub_rn(k.y, in.ppy), in.fy);
-            if (in.model == ORBB_DISTORTION_INVERSE_BROWN_CONRADY) {
-                const double c0 = in.coeffs[0], c1 = in.coeffs[1], c2 = in.coeffs[2], c3 = in.coeffs[3], c4 = in.coeffs[4];
-                const double r2 = dadd(dmul(x, x), dmul(y, y));
-                const double fr = dadd(dadd(dadd(1.0, dmul(c0, r2)), dmul(dmul(c1, r2), r2)), dmul(dmul(dmul(c4, r2), r2), r2));
-                const double ux = dadd(dadd(dmul(x, fr), dmul(dmul(dmul(2.0, c2), x), y)), dmul(c3, dadd(r2, dmul(dmul(2.0, x), x))));
-                const double uy = dadd(dadd(dmul(y, fr), dmul(dmul(dmul(2.0, c3), x), y)), dmul(c2, dadd(r2, dmul(dmul(2.0, y), y))));
-                x = ux; y = uy;
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const int i = i0 + u * KP_THREADS + threadIdx.x;
+            const int xi = (int)((double)k[u].x + 0.5), yi = (int)((double)k[u].y + 0.5);
+            if (i < n && xi >= 0 && yi >= 0 && xi < in.width && yi < in.height) depth[u] = (int)dimg[(size_t)yi * in.width + xi];
+        }
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const int i = i0 + u * KP_THREADS + threadIdx.x;
+            keep[u] = i < n && depth[u] > 1 && k[u].response > 1.0f;
+            if (u == 1 && i0 + KP_THREADS >= n) break;  // block-uniform: no second chunk
+            int total;
+            const int r = base + block_rank(keep[u], s_warp, &total);
+            if (keep[u]) {
+                const size_t o = f * max_kp + r;
+                kp_out[o] = k[u];
+                desc_out[2 * o] = desc_in[2 * (f * max_kp + i)];
+                desc_out[2 * o + 1] = desc_in[2 * (f * max_kp + i) + 1];
+                // deproject_pixel_to_point_double (cuda-align.cu:85-110): float32 normalisation, float64 afterwards
+                double x = (double)__fdiv_rn(__fsub_rn(k[u].x, in.ppx), in.fx);
+                double y = (double)__fdiv_rn(__fsub_rn(k[u].y, in.ppy), in.fy);
+                if (in.model == ORBB_DISTORTION_INVERSE_BROWN_CONRADY) {
+                    const double c0 = in.coeffs[0], c1 = in.coeffs[1], c2 = in.coeffs[2], c3 = in.coeffs[3], c4 = in.coeffs[4];
+                    const double r2 = dadd(dmul(x, x), dmul(y, y));
+                    const double fr = dadd(dadd(dadd(1.0, dmul(c0, r2)), dmul(dmul(c1, r2), r2)), dmul(dmul(dmul(c4, r2), r2), r2));
+                    const double ux = dadd(dadd(dmul(x, fr), dmul(dmul(dmul(2.0, c2), x), y)), dmul(c3, dadd(r2, dmul(dmul(2.0, x), x))));
+                    const double uy = dadd(dadd(dmul(y, fr), dmul(dmul(dmul(2.0, c3), x), y)), dmul(c2, dadd(r2, dmul(dmul(2.0, y), y))));
+                    x = ux; y = uy;
+                }
+                const double dd = (double)(float)depth[u];
+                points[3 * o] = dmul(dd, x); points[3 * o + 1] = dmul(dd, y); points[3 * o + 2] = dd;
             }
-            const double dd = (double)(float)depth;
-            points[3 * o] = dmul(dd, x); points[3 * o + 1] = dmul(dd, y); points[3 * o + 2] = dd;
+            base += total;
         }
-        base += total;
     }
     if (threadIdx.x == 0) valid_counts[f] = base;
 }

@@ -24,7 +24,7 @@ struct orbb_rgbd_stage {
     int device = 0, B = 0, max_kp = 0;
     size_t gray_bytes = 0, depth_px = 0, img_px = 0;
     cudaStream_t s_in = nullptr, s_align = nullptr, s_main = nullptr, s_out = nullptr;
-    cudaEvent_t ev_in[2] = {}, ev_gray[2] = {}, ev_out[2] = {}, ev_main[2] = {}, ev_align = nullptr, ev_gate = nullptr;
+    cudaEvent_t ev_gfork = nullptr, ev_gjoin = nullptr, ev_in[2] = {}, ev_gray[2] = {}, ev_out[2] = {}, ev_main[2] = {}, ev_align = nullptr, ev_gate = nullptr;
     // device
     uint8_t *d_gray[2] = {};
     uint16_t *d_depth[2] = {};
@@ -54,8 +54,8 @@ struct orbb_rgbd_stage {
     bool gate_recorded = false;
     int carry_from = 0;  // > 0: row `carry_from` of the result block (the previous batch's last frame) still has to become row 0
     // Small batches (a lone frame per wake-up is the reference's operating mode) replay a captured CUDA graph of
-    // everything after the H2D copies; one graph per (parity, frame count, pose given, row to carry)
-    struct FrameGraph { int p, n, has_T, carry; cudaGraphExec_t exec; long long launches; };
+    // everything after the H2D copies; one graph per (parity, frame count, pose given)
+    struct FrameGraph { int p, n, has_T; cudaGraphExec_t exec; long long launches; };
     std::vector<FrameGraph> graphs;
     int use_graph = 1, graph_max_frames = 4;
     // diagnostics (ORBB_STAGE_PROF=1): timing events at the phase boundaries of the last submit, printed by wait()
@@ -107,6 +107,8 @@ extern "C" int orbb_rgbd_stage_destroy(orbb_rgbd_stage *s) {
     }
     if (s->ev_align) cudaEventDestroy(s->ev_align);
     if (s->ev_gate) cudaEventDestroy(s->ev_gate);
+    if (s->ev_gfork) cudaEventDestroy(s->ev_gfork);
+    if (s->ev_gjoin) cudaEventDestroy(s->ev_gjoin);
     for (auto &g : s->graphs)
         if (g.exec) cudaGraphExecDestroy(g.exec);
     for (cudaStream_t st : {s->s_in, s->s_align, s->s_main, s->s_out})
@@ -153,6 +155,8 @@ extern "C" int orbb_rgbd_stage_create(orbb_rgbd_stage **out, const orbb_rgbd_con
     }
     SCKC(cudaEventCreateWithFlags(&s->ev_align, cudaEventDisableTiming));
     SCKC(cudaEventCreateWithFlags(&s->ev_gate, cudaEventDisableTiming));
+    SCKC(cudaEventCreateWithFlags(&s->ev_gfork, cudaEventDisableTiming));
+    SCKC(cudaEventCreateWithFlags(&s->ev_gjoin, cudaEventDisableTiming));
     if (const char *e = getenv("ORBB_STAGE_GRAPH")) s->use_graph = atoi(e);
     SCKC(sdev(s, &s->d_aligned, s->img_px * B));
     SCKC(sdev(s, &s->d_kp_raw, B * mk)); SCKC(sdev(s, &s->d_desc_raw, B * mk * 32));
@@ -205,21 +209,33 @@ extern "C" int orbb_rgbd_stage_reset(orbb_rgbd_stage *s) {
     return ORBB_OK;
 }
 
-// The second half of one small batch -- carry row + counts, depth gate / 3-D lift, reprojection, windowed match, pair
+// The second half of one small batch -- depth gate / 3-D lift, reprojection, counts, windowed match, pair
 // compaction and the D2H of the results -- enqueued on s_main: the body of the graph.  (The first half needs no graph of
 // the stage's own: the alignment is one call on s_align and the extraction replays the extractor's graph.)  Same calls,
 // same arguments, same results as the streamed path below.
-static int enqueue_small_batch_tail(orbb_rgbd_stage *s, int p, int n_frames, bool has_T, int carry) {
+static int enqueue_small_batch_tail(orbb_rgbd_stage *s, int p, int n_frames, bool has_T) {
     const size_t n = n_frames, mk = s->max_kp;
     orbb_rgbd_stage::Host &H = s->host[p];
     cudaStream_t m = s->s_main;
-    SCK(s, orbb::launch_stage_carry(s->d_kp, s->d_desc, s->d_pts, s->d_valid, carry, s->max_kp, s->d_counts_blk, s->d_counts_raw,
-                                    n_frames, m));
+    // A lone frame's "previous" points are row 0 only, carried before the graph starts (see submit): their reprojection and
+    // the counts for the result block run on s_align next to the depth gate / 3-D lift of the new frame.  With more frames
+    // the previous rows 1..n-1 are this batch's own, so the reprojection follows the lift.
+    const bool fork = n_frames == 1;
+    cudaStream_t side = fork ? s->s_align : m;
+    if (fork) {
+        SCK(s, cudaEventRecord(s->ev_gfork, m));
+        SCK(s, cudaStreamWaitEvent(side, s->ev_gfork, 0));
+    }
     SRC(orbb_keypoint_pixel_to_point(s->h, s->d_aligned, &s->cfg.image_intrin, n_frames, s->d_kp_raw, s->d_desc_raw,
                                      s->d_counts_raw, s->max_kp, s->d_kp + mk, s->d_desc + 32 * mk, s->d_pts + 3 * mk,
                                      s->d_valid + 1, m));
+    SCK(s, cudaMemcpyAsync(s->d_counts_blk, s->d_counts_raw, sizeof(int) * n, cudaMemcpyDeviceToDevice, side));
     SRC(orbb_reproject_points(s->h, s->d_pts, s->d_valid, n_frames, s->max_kp, has_T ? s->d_T[p] : nullptr,
-                              &s->cfg.image_intrin, s->d_pos, m));
+                              &s->cfg.image_intrin, s->d_pos, side));
+    if (fork) {
+        SCK(s, cudaEventRecord(s->ev_gjoin, side));
+        SCK(s, cudaStreamWaitEvent(m, s->ev_gjoin, 0));
+    }
     SRC(orbb_match_windowed_batch(s->h, s->d_desc, s->d_pos, s->d_valid, s->d_desc + 32 * mk, s->d_kp + mk,
                                   (int)sizeof(orbb_keypoint), s->d_valid + 1, n_frames, s->max_kp, s->cfg.max_pixel_distance,
                                   s->cfg.max_hamming_distance, s->d_idx, s->d_dist, s->d_pts, s->d_pts + 3 * mk,
@@ -240,14 +256,14 @@ static int enqueue_small_batch_tail(orbb_rgbd_stage *s, int p, int n_frames, boo
     return ORBB_OK;
 }
 
-// The graph for this (parity, frame count, pose given, carry row): captured on first use.  nullptr = use the streamed path.
-static orbb_rgbd_stage::FrameGraph *small_batch_graph(orbb_rgbd_stage *s, int p, int n_frames, bool has_T, int carry) {
+// The graph for this (parity, frame count, pose given): captured on first use.  nullptr = use the streamed path.
+static orbb_rgbd_stage::FrameGraph *small_batch_graph(orbb_rgbd_stage *s, int p, int n_frames, bool has_T) {
     for (auto &g : s->graphs)
-        if (g.p == p && g.n == n_frames && g.has_T == (int)has_T && g.carry == carry) return &g;
+        if (g.p == p && g.n == n_frames && g.has_T == (int)has_T) return &g;
     if (s->graphs.size() >= 32) return nullptr;  // a caller that varies the batch size a lot: not worth more graphs
     const long long l0 = orbb_get_launch_count(s->h);
     if (cudaStreamBeginCapture(s->s_main, cudaStreamCaptureModeThreadLocal) != cudaSuccess) { cudaGetLastError(); return nullptr; }
-    const int rc = enqueue_small_batch_tail(s, p, n_frames, has_T, carry);
+    const int rc = enqueue_small_batch_tail(s, p, n_frames, has_T);
     cudaGraph_t graph = nullptr;
     const cudaError_t ce = cudaStreamEndCapture(s->s_main, &graph);
     const long long launches = orbb_get_launch_count(s->h) - l0;
@@ -256,7 +272,7 @@ static orbb_rgbd_stage::FrameGraph *small_batch_graph(orbb_rgbd_stage *s, int p,
     if (rc == ORBB_OK && ce == cudaSuccess && cudaGraphInstantiate(&exec, graph, 0) != cudaSuccess) exec = nullptr;
     if (graph) cudaGraphDestroy(graph);
     if (!exec) { cudaGetLastError(); s->use_graph = 0; return nullptr; }  // fall back to the streamed path for good
-    s->graphs.push_back({p, n_frames, (int)has_T, carry, exec, launches});
+    s->graphs.push_back({p, n_frames, (int)has_T, exec, launches});
     return &s->graphs.back();
 }
 
@@ -289,20 +305,25 @@ extern "C" int orbb_rgbd_stage_submit(orbb_rgbd_stage *s, const uint8_t *h_gray,
     // has arrived, and everything after the two -- carry, depth gate, reprojection, match, compaction, D2H -- is ONE graph
     // launch of the stage's own.  The host issues ~15 calls instead of ~40 and the GPU starts ~25 us earlier.
     if (s->use_graph && n_frames <= s->graph_max_frames) {
-        if (orbb_rgbd_stage::FrameGraph *g = small_batch_graph(s, p, n_frames, h_T != nullptr, s->carry_from)) {
+        if (orbb_rgbd_stage::FrameGraph *g = small_batch_graph(s, p, n_frames, h_T != nullptr)) {
             SCK(s, cudaStreamWaitEvent(s->s_main, s->ev_gray[p], 0));
             SRC(orbb_extract_batch_device(s->h, s->d_gray[p], (size_t)s->cfg.image_intrin.width, s->gray_bytes, n_frames,
                                           s->d_kp_raw, s->d_desc_raw, s->d_counts_raw, s->max_kp, s->s_main));
             SPROF(s, 3, s->s_main);
-            SCK(s, cudaStreamWaitEvent(s->s_align, s->ev_in[p], 0));
+            // s_align: once the previous batch has let go of the result block and the aligned-depth buffer, its last frame
+            // becomes row 0 (under this batch's extraction), then the alignment as soon as the depth frames are there
             if (s->gate_recorded) SCK(s, cudaStreamWaitEvent(s->s_align, s->ev_gate, 0));
+            if (ticket >= 1) SCK(s, cudaStreamWaitEvent(s->s_align, s->ev_out[p ^ 1], 0));  // a streamed batch's D2H (s_out)
+            if (s->carry_from > 0)
+                SCK(s, orbb::launch_stage_carry(s->d_kp, s->d_desc, s->d_pts, s->d_valid, s->carry_from, s->max_kp, nullptr, nullptr,
+                                                0, s->s_align));
+            SCK(s, cudaStreamWaitEvent(s->s_align, s->ev_in[p], 0));
             SRC(orbb_align_depth_to_other(s->h, s->d_depth[p], n_frames, s->cfg.depth_scale, &s->cfg.depth_intrin,
                                           &s->cfg.image_intrin, &s->cfg.depth_to_image, s->d_aligned, s->s_align));
             SCK(s, cudaEventRecord(s->ev_align, s->s_align));
             SPROF(s, 2, s->s_align);
             SCK(s, cudaStreamWaitEvent(s->s_main, s->ev_align, 0));
             SCK(s, cudaStreamWaitEvent(s->s_main, s->ev_in[p], 0));                         // the pose matrices
-            if (ticket >= 1) SCK(s, cudaStreamWaitEvent(s->s_main, s->ev_out[p ^ 1], 0));  // a streamed batch's D2H (s_out)
             SPROF(s, 4, s->s_main);
             SCK(s, cudaGraphLaunch(g->exec, s->s_main));
             orbb::note_replay(s->h, n_frames, g->launches);
