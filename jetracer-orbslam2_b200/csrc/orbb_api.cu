@@ -9,6 +9,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <new>
+#include <string>
 #include <vector>
 
 #include "orbb_internal.cuh"
@@ -759,30 +760,50 @@ static int run_all(orbb_handle *h, const uint8_t *d_images, size_t pitch, size_t
                    cudaEvent_t ev_fork = nullptr, cudaEvent_t ev_join = nullptr) {
     int rc;
     // Small batches (a lone frame is the reference's operating mode): the chain level0 -> 7 resizes -> FAST -> quadtree
-    // -> angle/rBRIEF is latency bound end to end (each kernel a few us on a fraction of the SMs).  Detection of the
-    // big levels does not need the small ones: after level `ls - 1` is built, FAST + quadtree of levels [0, ls) move to a
-    // second stream and run NEXT TO the rest of the pyramid and the detection of levels [ls, n); the blur (needs the
-    // pyramid only) runs on a third.  Same kernels, same results.  Only as part of a captured graph (ORBB_GRAPH=1): with
-    // plain stream operations the two cross-stream joins cost more than the overlap gains (one 848x480 frame, 8 levels:
-    // 65 us sequential, 82 us split without a graph, 57 us split inside a graph).
+    // -> angle/rBRIEF is latency bound end to end (each kernel a few us on a fraction of the SMs).  Detection of a level
+    // needs only that level: FAST + quadtree of level 0 -- the longest of them -- move to a side stream right after the
+    // level-0 kernel, those of levels 1-3 to a second one once level 3 exists, and both run NEXT TO the rest of the pyramid
+    // and the detection of the small levels; the blur (needs the pyramid only) runs on another stream.  Same kernels,
+    // same results.  Only as part of a captured graph: with plain stream operations the cross-stream joins cost more
+    // than the overlap gains.  One 848x480 frame, 8 levels, inside the graph: one chain 65 us, groups {0-3}{4-7} 55 us,
+    // {0}{1-3}{4-7} 47 us (finer splits change nothing: the level-0 chain level0 -> FAST -> quadtree -> angle/rBRIEF is
+    // what remains, profiles/r02b_single_frame.txt).  ORBB_LONE_GROUPS="b0,b1,.." overrides the group boundaries.
     static const int lone_split = getenv("ORBB_LONE_SPLIT") ? atoi(getenv("ORBB_LONE_SPLIT")) : 4;
     if (side && h->use_graphs && n <= lone_split && h->nlevels >= 4 && (h->fused.empty() || n > h->fused_max_frames)) {
-        const int ls = std::min(4, h->nlevels - 1);
-        cudaStream_t sa = h->s_dev[0];
+        // level groups [0, b0), [b0, b1), ..., [b_last, nlevels): every group but the last detects on its own side stream as
+        // soon as its levels exist; the last one stays on `st` behind the rest of the pyramid
+        int bounds[4], nb = 0;
+        {
+            const char *e = getenv("ORBB_LONE_GROUPS");  // e.g. "1,4": level 0 alone, levels 1-3, the rest
+            std::string spec = e ? e : "1,4";
+            for (size_t pos = 0; pos < spec.size() && nb < 3;) {
+                const int v = atoi(spec.c_str() + pos);
+                if (v > (nb ? bounds[nb - 1] : 0) && v < h->nlevels) bounds[nb++] = v;
+                const size_t c = spec.find(',', pos);
+                if (c == std::string::npos) break;
+                pos = c + 1;
+            }
+            if (nb == 0) bounds[nb++] = 1;
+        }
         if ((rc = run_upload(h, d_images, pitch, stride, f0, n, st))) return rc;
-        for (int l = 1; l < ls; ++l) CK(h, launch_resize(h->d_levels, h->lv, l, f0, n, st));
-        CK(h, cudaEventRecord(h->ev_dev[0], st));
-        CK(h, cudaStreamWaitEvent(sa, h->ev_dev[0], 0));
-        if ((rc = run_detect_levels(h, 0, ls, f0, n, sa))) return rc;
-        CK(h, cudaEventRecord(h->ev_dev[1], sa));
-        for (int l = ls; l < h->nlevels; ++l) CK(h, launch_resize(h->d_levels, h->lv, l, f0, n, st));
+        int built = 1, g0 = 0;  // levels [0, built) exist
+        for (int gi = 0; gi < nb; ++gi) {
+            for (; built < bounds[gi]; ++built) CK(h, launch_resize(h->d_levels, h->lv, built, f0, n, st));
+            cudaStream_t sg = h->s_dev[gi];
+            CK(h, cudaEventRecord(h->ev_dev[2 * gi], st));
+            CK(h, cudaStreamWaitEvent(sg, h->ev_dev[2 * gi], 0));
+            if ((rc = run_detect_levels(h, g0, bounds[gi], f0, n, sg))) return rc;
+            CK(h, cudaEventRecord(h->ev_dev[2 * gi + 1], sg));
+            g0 = bounds[gi];
+        }
+        for (; built < h->nlevels; ++built) CK(h, launch_resize(h->d_levels, h->lv, built, f0, n, st));
         h->n_launches += h->nlevels - 1;
         CK(h, cudaEventRecord(ev_fork, st));
         CK(h, cudaStreamWaitEvent(side, ev_fork, 0));
         if ((rc = run_blur(h, f0, n, side))) return rc;
         CK(h, cudaEventRecord(ev_join, side));
-        if ((rc = run_detect_levels(h, ls, h->nlevels, f0, n, st))) return rc;
-        CK(h, cudaStreamWaitEvent(st, h->ev_dev[1], 0));
+        if ((rc = run_detect_levels(h, g0, h->nlevels, f0, n, st))) return rc;
+        for (int gi = 0; gi < nb; ++gi) CK(h, cudaStreamWaitEvent(st, h->ev_dev[2 * gi + 1], 0));
         CK(h, cudaStreamWaitEvent(st, ev_join, 0));
         return run_angle_orb(h, f0, n, d_kp, d_desc, d_counts, max_kp, st);
     }

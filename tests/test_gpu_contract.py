@@ -517,7 +517,7 @@ def test_small_batch_graph_cache_and_fallback(orbb, oracle, synth, monkeypatch):
             check(ex, d_kp, d_desc, d_cnt, n)
             keep.append((d_in, d_kp, d_desc, d_cnt))
         if graph == "1":
-            assert per_call[0] == 12 and per_call[-1] == 10  # captured (split detection: 2 more launches), then direct
+            assert per_call[0] == 14 and per_call[-1] == 10  # captured (detection in three level groups: 4 more launches), then direct
         else:
             assert set(per_call) == {10}
         ex.close()

@@ -534,11 +534,11 @@ def test_cuda_graph_replay_opt_in(orbb, oracle, synth, monkeypatch):
                 gkp, gdesc = canon(kp[f, :cnt[f]], desc[f, :cnt[f]])
                 assert len(gkp) == len(okp)
                 assert np.array_equal(gkp.view(np.uint8), okp.view(np.uint8)) and np.array_equal(gdesc, odesc)
-    # replays are counted like direct launches: level0 + 5 resizes + (FAST + quadtree) x 2 level ranges (the captured
-    # graph runs the detection of levels 0..3 next to the rest of the pyramid) + blur + angle/rBRIEF = 12.  Five argument
+    # replays are counted like direct launches: level0 + 5 resizes + (FAST + quadtree) x 3 level groups (the captured
+    # graph runs the detection of level 0 and of levels 1..3 next to the rest of the pyramid) + blur + angle/rBRIEF = 14.  Five argument
     # sets round-robin over four slots miss every time: eight captures / in-place updates, then the handle falls back
     # to plain launches (10 per call) for the remaining seven calls
-    assert ex.launch_count() - l0 == 8 * 12 + 7 * 10
+    assert ex.launch_count() - l0 == 8 * 14 + 7 * 10
 
 
 @pytest.mark.parametrize("nb", [12, 30, 64, 71, 130])
