@@ -12,7 +12,7 @@ def line_of(pat, nth=0):
     return hits[nth]
 marks = [(1, "arc_score fn" ), (line_of("k_fast_cells(const CUtensorMap"), "prologue"), (line_of("const int gx = c.x0 - 4"), "staging"),
          (line_of("score_bytes >> 4", 1), "score clear + setup"), (line_of("auto precheck"), "precheck"), (line_of("const int c_own"), "scan"),
-         (line_of("for (int i = U - 1"), "queue pop"), (line_of("int cn = 0;"), "arc loop"), (line_of("if (DUMP) {"), "dump"),
+         (line_of("const int xoff = 4 * U - 64"), "queue fill"), (line_of("int cn = 0;"), "arc loop"), (line_of("if (DUMP) {"), "dump"),
          (line_of("        kn = 0;"), "nms"), (line_of("int *counter"), "emit")]
 marks.sort()
 def phase(l):

@@ -16,11 +16,13 @@ ncu --set full --import-source on --clock-control none \
     --kernel-name regex:'k_level0|k_resize_rows|k_fast_cells|k_octree|k_blur|k_angle_orb' --launch-skip 48 --launch-count 14 \
     -f -o $out/${tag}_all $cmd > $out/${tag}_ncu_all.log 2>&1
 # the matcher (cfg 5 geometry: one rank's 257 k descriptors against the 50 k map)
-ncu --set full --import-source on --clock-control none --kernel-name regex:'k_match<' --launch-skip 2 --launch-count 1 \
+ncu --set full --import-source on --clock-control none --kernel-name regex:'^k_match$' --launch-skip 2 --launch-count 1 \
     -f -o $out/${tag}_match python tools/matcher_probe.py > $out/${tag}_ncu_match.log 2>&1
 [ -x tools/_build/pipe_probe ] && ./tools/_build/pipe_probe > $out/${tag}_pipe_probe.txt 2>&1
 python tools/single_frame_probe.py 300 > $out/${tag}_single_frame.txt 2>&1
 ncu --metrics gpu__time_duration.sum --clock-control none -c 120 --csv --log-file $out/${tag}_single_frame_launches.csv \
     python tools/single_frame_probe.py 3 > /dev/null 2>&1
 python tools/latency_probe.py > $out/${tag}_latency_probe.txt 2>&1
+python tools/stage_latency_probe.py > $out/${tag}_stage_latency.txt 2>&1
+ORBB_STAGE_PROF=1 python tools/stage_latency_probe.py 2>&1 | grep 'stage prof' | tail -4 >> $out/${tag}_stage_latency.txt
 ls -la $out | tail -14
