@@ -24,7 +24,7 @@ __device__ __forceinline__ unsigned op(unsigned a, unsigned b, unsigned c) {
     if (KIND == K_IMAD) return a * b + c;
     if (KIND == K_LOP3) { unsigned r; asm volatile("lop3.b32 %0, %1, %2, %3, 0x96;" : "=r"(r) : "r"(a), "r"(b), "r"(c)); return r; }
     if (KIND == K_VABSDIFF4) return __vabsdiffu4(a, b);
-    if (KIND == K_POPC) return __popc(a) + b;
+    if (KIND == K_POPC) { unsigned r; asm volatile("popc.b32 %0, %1;" : "=r"(r) : "r"(a)); return r + b; }  // volatile: the plain chain is folded away
     if (KIND == K_SHFL) return __shfl_up_sync(0xffffffffu, a, 1) + b;
     if (KIND == K_VOTE) return __ballot_sync(0xffffffffu, a & 1) ^ b;
     if (KIND == K_IADD3) { unsigned r; asm volatile("add.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
