@@ -521,3 +521,33 @@ def test_small_batch_graph_cache_and_fallback(orbb, oracle, synth, monkeypatch):
         else:
             assert set(per_call) == {10}
         ex.close()
+
+
+@pytest.mark.parametrize("groups", ["1,4", "4", "1,2,5", "3", "2,9", "x"])
+def test_lone_frame_level_groups(orbb, oracle, synth, monkeypatch, groups):
+    """Inside the small-batch graph the detection runs in level groups on side streams (default {0}{1-3}{rest}).  Any
+    grouping -- also boundaries past the level count and a malformed spec, which fall back to usable ones -- must give
+    the oracle's bytes: the groups only change which stream a (frame, level)'s FAST + quadtree kernels run on."""
+    import torch
+    monkeypatch.setenv("ORBB_LONE_GROUPS", groups)
+    st = torch.cuda.current_stream()
+    for (w, h, nf, nl, n) in ((424, 240, 500, 8, 1), (640, 480, 1000, 5, 2), (333, 251, 300, 4, 3)):
+        frames = np.stack([synth.textured_frame(w, h, 6100 + i) for i in range(n)])
+        ex = orbb.ORBextractor(nf, 1.2, nl, 20, 7, width=w, height=h, max_batch=n)
+        o = oracle.Oracle(w, h, nf, 1.2, nl, 20, 7)
+        d_in = torch.from_numpy(frames).cuda()
+        d_kp = torch.zeros((n, ex.max_kp, 7), dtype=torch.float32, device="cuda")
+        d_desc = torch.zeros((n, ex.max_kp, 32), dtype=torch.uint8, device="cuda")
+        d_cnt = torch.zeros(n, dtype=torch.int32, device="cuda")
+        for rep in range(2):  # captured, then replayed
+            d_kp.zero_(); d_desc.zero_(); d_cnt.zero_()
+            ex.extract_batch_device(d_in, n, d_kp, d_desc, d_cnt, stream=st)
+            torch.cuda.synchronize()
+            cnt = d_cnt.cpu().numpy()
+            kp = d_kp.cpu().numpy().view(orbb.KEYPOINT_DTYPE).reshape(n, ex.max_kp)
+            desc = d_desc.cpu().numpy()
+            for f in range(n):
+                okp, od = canon(*o.extract(frames[f]))
+                gk, gd = canon(kp[f, :cnt[f]], desc[f, :cnt[f]])
+                assert gk.tobytes() == okp.tobytes() and np.array_equal(gd, od), (groups, w, h, f, rep)
+        ex.close()
