@@ -39,8 +39,20 @@ namespace orbb {
 #define OCT_WARPS (OCT_THREADS / 32)
 #define FULL 0xffffffffu
 
-struct OctStatic {
-    uint32_t whist[OCT_WARPS][256];
+// Count / best pyramids of the PYRAMID PATH (see the kernel): every tree level above the cell table, deepest level
+// first: level k (R * 4^k nodes) starts at node offset (T - R * 4^(k+1)) / 3, so every level is 4-node aligned and a
+// node's four children are one 16-byte (counts) or two 16-byte (best keys) shared-memory loads.  (T - R) / 3 <= 1365.
+#define OCT_PYR_NODES 1368
+struct __align__(16) OctPyr {
+    unsigned long long pb[OCT_PYR_NODES];  // best key below the node
+    uint32_t pc[OCT_PYR_NODES];            // keys below the node
+    uint16_t pinfo[OCT_PYR_NODES];         // bits 0..2: non-empty children; bits 3..15: 1 + split rank (0 = not split)
+};
+struct __align__(16) OctStatic {
+    union {  // the general path (radix sort) only ever runs after the pyramid path has given up
+        uint32_t whist[OCT_WARPS][256];
+        OctPyr pyr;
+    };
     uint32_t digit_base[256];
     int hist_sd[40], hist_g[40];
     uint32_t warp_tot[OCT_WARPS];
@@ -226,6 +238,243 @@ __device__ __forceinline__ void bitonic_desc(unsigned long long *key, uint32_t *
     }
 }
 
+// ---- PYRAMID PATH (default).  The selection only ever looks at the tree down to the depth at which ~N nodes exist
+// (3-5 for the quotas of a pyramid level), and it looks at the keys only through (a) how many lie below a tree node and
+// (b) which is the best one there.  The FAST kernel bins every candidate it emits into the 4^Dc tree cells of depth Dc
+// (L.tbl_cnt / L.tbl_best in global memory, cell index = path prefix); this CTA sums the table up the tree and reads
+// everything off the pyramid -- no sort, no per-key pass, no per-record pass:
+//   * L(k) = non-empty nodes of level k is the list size after upstream's k-th breadth-first pass, E(k) = nodes holding
+//     more than one key is what that pass could still expand: the pass loop stops at the first k with L >= N,
+//     L == L(k-1) or L + 3 E > N;
+//   * the careful phase ranks the expandable nodes of a level by (count, creation sequence), splits the largest first
+//     until N nodes exist (gain of a split = non-empty children - 1) and goes one level down if all of them were split;
+//   * a node is final iff it is non-empty, not split, and sits at the stop depth or below a split parent; its keypoint
+//     is the best key below it.  Final nodes are numbered in path order through a bit mask over the cells.
+// tests/test_octree_pyramid_model.py restates this in numpy and checks it against the oracle on the CPU.
+// Returns false (block-uniform) when the answer lies below depth Dc or the table does not describe this candidate
+// list: the CTA then takes the general sorted-key path.  The caller clears the table afterwards.
+__device__ __forceinline__ bool octree_pyramid(const LevelDev &L, OctStatic &S, const uint32_t *tbl_cnt, const unsigned long long *tbl_best,
+                                               int n, int N, unsigned long long *skey, uint32_t *sval, int pcap2,
+                                               uint32_t *sel, int *out_count, long long *prof_t) {
+    (void)prof_t;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const unsigned lt = (1u << lane) - 1u;
+    const int Dc = L.tbl_dc, T = L.tbl_cells, rb = L.key_bits - 2 * L.depth, R = 1 << rb;
+    OctPyr &P = S.pyr;
+    auto lvl_off = [&](int k) -> int { return (T - (R << (2 * (k + 1)))) / 3; };
+    // ---- A. level Dc-1 from the table: one node (four cells) per thread and step, all loads up front
+    const int M1 = T >> 2;
+    uint4 w[2];
+    ulonglong2 b[2][2];
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+        const int j = tid + q * OCT_THREADS;
+        w[q] = make_uint4(0u, 0u, 0u, 0u);
+        b[q][0] = b[q][1] = make_ulonglong2(0ull, 0ull);
+        if (j < M1) {
+            w[q] = reinterpret_cast<const uint4 *>(tbl_cnt)[j];
+            b[q][0] = reinterpret_cast<const ulonglong2 *>(tbl_best)[2 * j];
+            b[q][1] = reinterpret_cast<const ulonglong2 *>(tbl_best)[2 * j + 1];
+        }
+    }
+    if (tid < 40) { S.hist_sd[tid] = 0; S.hist_g[tid] = 0; }  // hist_sd[k] = L(k), hist_g[k] = E(k)
+    if (tid < 128) S.digit_base[tid] = 0u;                    // bit mask of the cells a final node starts at
+    __syncthreads();
+    {
+        unsigned acc_c = 0, acc_1 = 0;  // (L | E << 16) of the cell level and of level Dc-1
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+            const int j = tid + q * OCT_THREADS;
+            if (j < M1) {
+                const uint32_t c1 = w[q].x + w[q].y + w[q].z + w[q].w;
+                const unsigned nz = (w[q].x != 0) + (w[q].y != 0) + (w[q].z != 0) + (w[q].w != 0);
+                const unsigned ne = (w[q].x > 1) + (w[q].y > 1) + (w[q].z > 1) + (w[q].w > 1);
+                P.pc[j] = c1;
+                P.pb[j] = max(max(b[q][0].x, b[q][0].y), max(b[q][1].x, b[q][1].y));
+                P.pinfo[j] = (uint16_t)nz;
+                acc_c += nz | (ne << 16);
+                acc_1 += (c1 != 0 ? 1u : 0u) | (c1 > 1 ? 0x10000u : 0u);
+            }
+        }
+        acc_c = __reduce_add_sync(FULL, acc_c);
+        acc_1 = __reduce_add_sync(FULL, acc_1);
+        if (lane == 0) {
+            if (acc_c) { atomicAdd(&S.hist_sd[Dc], (int)(acc_c & 0xffffu)); atomicAdd(&S.hist_g[Dc], (int)(acc_c >> 16)); }
+            if (acc_1) { atomicAdd(&S.hist_sd[Dc - 1], (int)(acc_1 & 0xffffu)); atomicAdd(&S.hist_g[Dc - 1], (int)(acc_1 >> 16)); }
+        }
+    }
+    __syncthreads();
+    // ---- B. the levels above: block-wide while a level has more than 64 nodes, then warp 0 alone
+    auto level_up = [&](int k, int j) -> unsigned {  // node j of level k from its four children; returns L | E << 16
+        const int src = lvl_off(k + 1) + 4 * j, dst = lvl_off(k) + j;
+        const uint4 c4 = *reinterpret_cast<const uint4 *>(&P.pc[src]);
+        const ulonglong2 b0 = *reinterpret_cast<const ulonglong2 *>(&P.pb[src]), b1 = *reinterpret_cast<const ulonglong2 *>(&P.pb[src + 2]);
+        const uint32_t c = c4.x + c4.y + c4.z + c4.w;
+        P.pc[dst] = c;
+        P.pb[dst] = max(max(b0.x, b0.y), max(b1.x, b1.y));
+        P.pinfo[dst] = (uint16_t)((c4.x != 0) + (c4.y != 0) + (c4.z != 0) + (c4.w != 0));
+        return (c != 0 ? 1u : 0u) | (c > 1 ? 0x10000u : 0u);
+    };
+    int k = Dc - 2;
+    for (; k >= 0 && (R << (2 * k)) > 64; --k) {
+        const int M = R << (2 * k);  // <= 256
+        unsigned acc = tid < M ? level_up(k, tid) : 0u;
+        if (warp * 32 < M) {
+            acc = __reduce_add_sync(FULL, acc);
+            if (lane == 0 && acc) { atomicAdd(&S.hist_sd[k], (int)(acc & 0xffffu)); atomicAdd(&S.hist_g[k], (int)(acc >> 16)); }
+        }
+        __syncthreads();
+    }
+    if (warp == 0) {
+        for (; k >= 0; --k) {
+            const int M = R << (2 * k);  // <= 64
+            unsigned acc = 0;
+            for (int j = lane; j < M; j += 32) acc += level_up(k, j);
+            acc = __reduce_add_sync(FULL, acc);
+            if (lane == 0) { S.hist_sd[k] = (int)(acc & 0xffffu); S.hist_g[k] = (int)(acc >> 16); }
+            __syncwarp();
+        }
+    }
+    __syncthreads();
+    OCT_T(1);
+    // ---- C. replay of the breadth-first passes (every thread, same answer)
+    {
+        uint32_t tot = 0;
+        for (int r = 0; r < R; ++r) tot += P.pc[lvl_off(0) + r];
+        if (tot != (uint32_t)n) return false;  // the table must describe exactly this candidate list
+    }
+    int mode = -1, k0 = 0, size = 0;
+    {
+        int prev = S.hist_sd[0];
+        for (int kk = 1; kk <= Dc; ++kk) {
+            const int Lk = S.hist_sd[kk], Ek = S.hist_g[kk];
+            if (Lk >= N || Lk == prev) { mode = 0; k0 = kk; size = Lk; break; }
+            if (Lk + 3 * Ek > N) { mode = 1; k0 = kk; size = Lk; break; }
+            prev = Lk;
+        }
+    }
+    if (mode < 0) return false;  // the passes go below the table
+    // ---- D. careful phase: one round per level
+    int last = k0;  // deepest level that holds final nodes
+    if (mode == 1) {
+        const uint32_t digit_mask = 0xCCCCCCCCu & ((1u << (2 * k0)) - 1u);
+        const uint32_t root_mask = (k0 & 1) ? 0u : ((uint32_t)(R - 1) << (2 * k0));
+        for (int d = k0;; ++d) {
+            if (d + 1 > Dc) return false;  // this round parts at depth d + 1
+            const int Md = R << (2 * d), base = lvl_off(d), pbase = d > 0 ? lvl_off(d - 1) : 0;
+            if (tid == 0) { S.ctl[C_PN] = 0; S.ctl[C_CUT] = 0x7fffffff; }
+            __syncthreads();
+            // expandable nodes of this level -> sort list keyed by (count, creation sequence); list order is irrelevant
+            for (int j0 = 0; j0 < Md; j0 += OCT_THREADS) {  // block-uniform trip count (<= 2)
+                const int j = j0 + tid;
+                uint32_t cnt = 0, seq = 0;
+                bool live = false;
+                if (j < Md) {
+                    cnt = P.pc[base + j];
+                    if (d == k0) {  // closed-form creation sequence of the breadth-first pass that made these nodes
+                        live = cnt > 1;
+                        seq = ((uint32_t)j ^ digit_mask ^ root_mask) & 0x7fffffffu;
+                    } else {        // children of the nodes the previous round split, in processing order of the parents
+                        const unsigned pr = P.pinfo[pbase + (j >> 2)] >> 3;
+                        live = cnt > 1 && pr != 0;
+                        seq = (pr - 1u) * 4u + ((unsigned)j & 3u);
+                    }
+                }
+                const unsigned bal = __ballot_sync(FULL, live);
+                int p0 = 0;
+                if (lane == 0 && bal) p0 = atomicAdd(&S.ctl[C_PN], __popc(bal));
+                p0 = __shfl_sync(FULL, p0, 0);
+                if (live) {
+                    const int p = p0 + __popc(bal & lt);
+                    if (p < pcap2) { skey[p] = ((unsigned long long)cnt << 32) | seq; sval[p] = (uint32_t)j; }
+                }
+            }
+            __syncthreads();
+            const int pn = S.ctl[C_PN];
+            if (pn > pcap2) return false;  // cannot happen (pn <= list size < N <= pcap); keeps the sort in bounds
+            int mm = 1;
+            while (mm < pn) mm <<= 1;
+            for (int p = pn + tid; p < mm; p += OCT_THREADS) { skey[p] = 0ull; sval[p] = 0xffffffffu; }
+            __syncthreads();
+            bitonic_desc(skey, sval, mm);
+            // prefix sums of the gains in processing order; first rank at which the node count reaches N
+            uint32_t carry = 0;
+            for (int r0 = 0; r0 < pn; r0 += OCT_THREADS) {
+                const int r = r0 + tid;
+                const uint32_t g = r < pn ? (uint32_t)(P.pinfo[base + sval[r]] & 7u) - 1u : 0u;
+                uint32_t tot;
+                const uint32_t inc = block_excl_scan(g, S.warp_tot, &tot) + carry + g;
+                if (r < pn) {
+                    skey[r] = inc;  // reuse: inclusive gain prefix at rank r
+                    if ((int)(size + inc) >= N) atomicMin(&S.ctl[C_CUT], r);
+                }
+                carry += tot;
+            }
+            __syncthreads();
+            const int cut = S.ctl[C_CUT];
+            const bool found = cut != 0x7fffffff;
+            const int nsplit = found ? cut + 1 : pn;
+            const uint32_t total = nsplit > 0 ? (uint32_t)skey[nsplit - 1] : 0u;
+            for (int r = tid; r < nsplit; r += OCT_THREADS) P.pinfo[base + sval[r]] |= (uint16_t)((r + 1) << 3);
+            __syncthreads();
+            if (nsplit > 0) last = d + 1;
+            if (found || total == 0) break;
+            size += (int)total;
+        }
+    }
+    OCT_T(2);
+    // ---- E. final nodes -> bit mask over their first cells -> path-order index -> selection
+    uint32_t *fmask = S.digit_base, *fpre = S.digit_base + 128;
+    auto for_final = [&](auto &&f) {  // f(first cell, best key) for every final node this thread owns
+        for (int kk = k0; kk <= min(last, Dc - 1); ++kk) {
+            const int Mk = R << (2 * kk), base = lvl_off(kk), pbase = kk > 0 ? lvl_off(kk - 1) : 0;
+            for (int j = tid; j < Mk; j += OCT_THREADS) {
+                const bool fin = P.pc[base + j] != 0 && (P.pinfo[base + j] >> 3) == 0 &&
+                                 (kk == k0 || (P.pinfo[pbase + (j >> 2)] >> 3) != 0);
+                if (fin) f(j << (2 * (Dc - kk)), P.pb[base + j]);
+            }
+        }
+        if (last >= Dc) {  // cells as nodes (rare): read them again, the table is still intact
+            for (int j = tid; j < M1; j += OCT_THREADS)
+                if (k0 == Dc || (P.pinfo[j] >> 3) != 0) {
+                    const uint4 c4 = reinterpret_cast<const uint4 *>(tbl_cnt)[j];
+                    const ulonglong2 b0 = reinterpret_cast<const ulonglong2 *>(tbl_best)[2 * j];
+                    const ulonglong2 b1 = reinterpret_cast<const ulonglong2 *>(tbl_best)[2 * j + 1];
+                    if (c4.x) f(4 * j, b0.x);
+                    if (c4.y) f(4 * j + 1, b0.y);
+                    if (c4.z) f(4 * j + 2, b1.x);
+                    if (c4.w) f(4 * j + 3, b1.y);
+                }
+        }
+    };
+    for_final([&](int c, unsigned long long) { atomicOr(&fmask[c >> 5], 1u << (c & 31)); });
+    __syncthreads();
+    if (warp == 0) {  // exclusive prefix of the mask words' populations (<= 128 words, four per lane)
+        uint32_t m4[4], s = 0;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { m4[i] = fmask[4 * lane + i]; s += __popc(m4[i]); }
+        uint32_t inc = s;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t t = __shfl_up_sync(FULL, inc, o);
+            if (lane >= o) inc += t;
+        }
+        uint32_t run = inc - s;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { fpre[4 * lane + i] = run; run += __popc(m4[i]); }
+        if (lane == 31) S.ctl[C_NFINAL] = (int)inc;
+    }
+    __syncthreads();
+    const int sel_cap = L.sel_cap;
+    for_final([&](int c, unsigned long long bk) {
+        const uint32_t idx = fpre[c >> 5] + __popc(fmask[c >> 5] & ((1u << (c & 31)) - 1u));
+        if (idx < (uint32_t)sel_cap) sel[idx] = (uint32_t)(bk & 0xffffffull) | ((uint32_t)(bk >> 56) << 24);
+    });
+    if (tid == 0) *out_count = min(S.ctl[C_NFINAL], sel_cap);
+    OCT_T(3);
+    return true;
+}
+
 template <int OCT_RB, int MIN_CTAS>
 __global__ void __launch_bounds__(OCT_THREADS, MIN_CTAS)
 k_octree(const LevelDev *__restrict__ levels, int n_levels, const int *__restrict__ cand_count,
@@ -279,7 +528,21 @@ k_octree(const LevelDev *__restrict__ levels, int n_levels, const int *__restric
     unsigned long long *tbl_best = L.tbl_best + (size_t)frame * T;
     const int csh = 2 * (D - Dc);  // path key -> cell index
 
-    for (int attempt = try_fast ? 0 : 1; attempt < 2; ++attempt) {
+    // no_fast: bit 0 = general path only (ORBB_OCT_NOFAST), bit 1 = the round-2a record path instead of the pyramid path
+    bool done = false;
+    if (try_fast && no_fast == 0 && pcap2 <= 8190) {
+#ifdef ORBB_OCT_PROF
+        done = octree_pyramid(L, S, tbl_cnt, tbl_best, n, N, skey, sval, pcap2, L.sel + (size_t)frame * L.sel_cap, out_count, prof_t);
+        if (done && tid == 0 && blockIdx.x == 0 && blockIdx.y == 0)
+            printf("oct-pyr n=%d N=%d Dc=%d T=%d | table+pyramid %lld replay+careful %lld final %lld cycles\n", n, N, Dc, T,
+                   prof_t[1] - prof_t[0], prof_t[2] - prof_t[1], prof_t[3] - prof_t[2]);
+#else
+        done = octree_pyramid(L, S, tbl_cnt, tbl_best, n, N, skey, sval, pcap2, L.sel + (size_t)frame * L.sel_cap, out_count, nullptr);
+#endif
+        __syncthreads();  // the general path reuses the shared arrays
+    }
+    if (!done)
+    for (int attempt = (try_fast && (no_fast & 2)) ? 0 : 1; attempt < 2; ++attempt) {
     const bool fastp = attempt == 0;
     int m;               // items the passes below run over: records (fast path) or keys
     uint2 *kva, *kvb;    // item arrays; kv[i].x = path key (prefix), kv[i].y = running key count (fast) / candidate
@@ -586,8 +849,12 @@ k_octree(const LevelDev *__restrict__ levels, int n_levels, const int *__restric
 #endif
     break;
     }  // attempt
-    if (T > 0) {  // hand the FAST kernel of the next batch an empty table
-        for (int i = tid; i < T; i += OCT_THREADS) { tbl_cnt[i] = 0u; tbl_best[i] = 0ull; }
+    if (T > 0) {  // hand the FAST kernel of the next batch an empty table (T is a multiple of 4)
+        for (int i = tid; i < (T >> 2); i += OCT_THREADS) {
+            reinterpret_cast<uint4 *>(tbl_cnt)[i] = make_uint4(0u, 0u, 0u, 0u);
+            reinterpret_cast<ulonglong2 *>(tbl_best)[2 * i] = make_ulonglong2(0ull, 0ull);
+            reinterpret_cast<ulonglong2 *>(tbl_best)[2 * i + 1] = make_ulonglong2(0ull, 0ull);
+        }
     }
 }
 
@@ -618,7 +885,7 @@ static cudaError_t launch_octree_t(const LevelDev *d_levels, int n_levels, const
                                    size_t smem, int sort_bytes, int no_fast, int pcap, int pcap2, cudaStream_t st) {
     const int sort_off = (int)((smem + 15) & ~(size_t)15);
     const size_t total = (size_t)sort_off + (size_t)sort_bytes;
-    if (total > 30 * 1024) {  // 48 KB default limit minus the 18 KB of static shared memory; the attribute is per device
+    if (total > 26 * 1024) {  // 48 KB default limit minus the 20.2 KB of static shared memory; the attribute is per device
         cudaError_t e = cudaFuncSetAttribute(k_octree<OCT_RB, MIN_CTAS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)total);
         if (e != cudaSuccess) return e;
     }
@@ -635,13 +902,13 @@ cudaError_t launch_octree(const LevelDev *d_levels, int n_levels, const int *d_c
     size_t smem = octree_dyn_smem(sel_cap_max, pcap, pcap2);
     if (getenv("ORBB_OCT_PAD")) smem = std::max(smem, (size_t)atoi(getenv("ORBB_OCT_PAD")));
     // diagnostics / tests: ORBB_OCT_NOFAST=1 forces the general (radix sort) path of every CTA
-    const bool nofast = getenv("ORBB_OCT_NOFAST") != nullptr;
+    const int nofast = (getenv("ORBB_OCT_NOFAST") ? 1 : 0) | (getenv("ORBB_OCT_RECORDS") ? 2 : 0);
     // fewer CTAs than the GPU can hold at once: every CTA's own latency is the kernel's duration
     const long long ctas = (long long)n_launch_levels * n_frames;
     if (ctas <= 148 * 3) {
-        // shared memory left per CTA when the grid is spread over the 148 SMs (227 KB each, 18 KB static per CTA)
+        // shared memory left per CTA when the grid is spread over the 148 SMs (227 KB each, 20.2 KB static per CTA)
         const int per_sm = (int)((ctas + 147) / 148);
-        long long spare = (227 * 1024) / per_sm - 18 * 1024 - (long long)smem - 1024;
+        long long spare = (227 * 1024) / per_sm - 21 * 1024 - (long long)smem - 1024;
         static const bool no_smem_sort = getenv("ORBB_OCT_NOSMEM") != nullptr;
         const int sort_bytes = (no_smem_sort || spare < 32 * 1024) ? 0 : (int)std::min<long long>(spare, 176 * 1024) & ~15;
         if (ctas <= 148)  // at most one CTA per SM: registers are free, keep 8 loads per thread in flight

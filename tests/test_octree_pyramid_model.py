@@ -1,0 +1,221 @@
+"""CPU model of the quadtree kernel's COUNT-PYRAMID path (csrc/k_octree.cu, "PYRAMID PATH"), checked against the oracle.
+
+The kernel never sorts and never walks keys: the FAST kernel bins every candidate into the 4^Dc tree cells of depth Dc
+(count + best key per cell); the quadtree CTA sums the cell counts up the tree (level k has R * 4^k nodes, R = root
+nodes rounded up to a power of two) and reads everything DistributeOctTree needs from that pyramid:
+
+  * L(k) = non-empty nodes of level k = list size after the k-th breadth-first pass, E(k) = nodes of level k holding
+    more than one key = nodes that pass could still expand; the pass loop stops at the first k with L >= N,
+    L == L(k-1) or L + 3 E > N (the "careful" phase);
+  * the careful phase sorts the expandable nodes by (count, creation sequence) and splits them largest first until N
+    nodes exist; gain of a split = non-empty children - 1; creation sequence of the first round has a closed form
+    (upstream pushes children to the list FRONT: alternating digit complement of the path), later rounds use
+    (rank of the parent, child index);
+  * a node is final iff it is non-empty, not split, and (it sits at the stop depth or its parent was split); its
+    keypoint is the best key below it (max-pyramid of the cells' best keys).
+
+This file restates exactly that in numpy (same arrays, same tie rules, same bail-outs: anything that would part below
+depth Dc returns None and the kernel takes its general sorted-key path) and compares the selected SET with
+oracle.distribute_octree over random clouds, quotas, ties and geometries.  CPU only; the GPU tier checks the kernel
+itself against the oracle (tests/test_gpu_parity.py::test_octree_stress and the extraction parity tests)."""
+import numpy as np
+import pytest
+from hypothesis import HealthCheck, given, settings
+from hypothesis import strategies as st
+
+from test_octree_cell_invariance import _axis_cells, _canonical_order
+
+
+def _spread(v, bits):
+    out = np.zeros_like(v)
+    for b in range(bits):
+        out |= ((v >> b) & 1) << (2 * b)
+    return out
+
+
+def table_depth(W, H, N):
+    """orbb_create's rule: the shallowest depth with >= 4 N cells, at most 4096 cells, depth <= min(D, 6)"""
+    n_ini = int(round(float(np.float32(W) / np.float32(H))))
+    root_bits = 0
+    while (1 << root_bits) < n_ini:
+        root_bits += 1
+    hx = np.float32(W) / np.float32(n_ini)
+    max_dim = max([H] + [int(hx * np.float32(r + 1)) - int(hx * np.float32(r)) for r in range(n_ini)])
+    D = 1
+    while (1 << D) < max_dim:
+        D += 1
+    D += 1
+    dc = 0
+    for dd in range(1, min(D, 6) + 1):
+        if (1 << (root_bits + 2 * dd)) > 4096:
+            break
+        dc = dd
+        if (1 << (root_bits + 2 * dd)) >= 4 * N:
+            break
+    return n_ini, root_bits, D, dc
+
+
+def pyramid_select(xy, resp, W, H, N, dc=None):
+    """returns the selected set {(x, y, response)} or None when the pyramid path bails out"""
+    n_ini, root_bits, D, dc_rule = table_depth(W, H, N)
+    Dc = dc_rule if dc is None else dc
+    R = 1 << root_bits
+    T = R << (2 * Dc)
+    if Dc < 1 or T < 4 * N:
+        return None
+    cx, _, _ = _axis_cells(W, Dc, n_ini)
+    cy, _, _ = _axis_cells(H, Dc, 1)
+    xb, yb = cx[xy[:, 0]] & ((1 << Dc) - 1), cy[xy[:, 1]]
+    root = cx[xy[:, 0]] >> Dc
+    cell = (root << (2 * Dc)) | _spread(xb, Dc) | (_spread(yb, Dc) << 1)
+    order = _canonical_order(xy, W, H)
+    rank = np.empty(len(xy), np.int64)
+    rank[order] = np.arange(len(xy))
+    # ---- the cell table the FAST kernel fills: count + best key (response, then earliest upstream order)
+    cnt = [None] * (Dc + 1)
+    best = [None] * (Dc + 1)
+    cnt[Dc] = np.bincount(cell, minlength=T).astype(np.int64)
+    key = (resp.astype(np.int64) << 32) | (0xFFFFFFF - rank)  # larger = better
+    best[Dc] = np.zeros(T, np.int64)
+    np.maximum.at(best[Dc], cell, key)
+    best_idx = {int(k): i for i, k in enumerate(key)}
+    # ---- count / best pyramids
+    for k in range(Dc - 1, -1, -1):
+        cnt[k] = cnt[k + 1].reshape(-1, 4).sum(1)
+        best[k] = best[k + 1].reshape(-1, 4).max(1)
+    L = [int((cnt[k] != 0).sum()) for k in range(Dc + 1)]
+    E = [int((cnt[k] > 1).sum()) for k in range(Dc + 1)]
+    # ---- replay of the breadth-first passes
+    prev, mode, k0 = L[0], None, None
+    for k in range(1, D + 2):
+        if k > Dc:
+            return None  # the table cannot tell deeper partings
+        if L[k] >= N or L[k] == prev:
+            mode, k0 = 0, k
+            break
+        if L[k] + 3 * E[k] > N:
+            mode, k0 = 1, k
+            break
+        prev = L[k]
+    split_rank = [np.full(R << (2 * k), -1, np.int64) for k in range(Dc + 1)]
+    last = k0  # deepest level that holds final nodes
+    if mode == 1:
+        size, d = L[k0], k0
+        digit_mask = 0xCCCCCCCC & ((1 << (2 * k0)) - 1)
+        root_mask = 0 if (k0 & 1) else ((R - 1) << (2 * k0))
+        j = np.flatnonzero(cnt[k0] > 1)
+        seq = (j ^ digit_mask ^ root_mask) & 0x7FFFFFFF
+        while True:
+            if d + 1 > Dc:
+                return None
+            nzc = (cnt[d + 1].reshape(-1, 4) != 0).sum(1)
+            skey = (cnt[d][j] << 32) | seq
+            o = np.argsort(-skey, kind="stable")  # keys are unique
+            js = j[o]
+            inc = np.cumsum(nzc[js] - 1)
+            hit = np.flatnonzero(size + inc >= N)
+            found = len(hit) > 0
+            nsplit = int(hit[0]) + 1 if found else len(js)
+            total = int(inc[nsplit - 1]) if nsplit > 0 else 0
+            split_rank[d][js[:nsplit]] = np.arange(nsplit)
+            last = d + 1 if nsplit > 0 else last
+            if found or total == 0:
+                break
+            size += total
+            d += 1
+            j = np.flatnonzero((cnt[d] > 1) & (split_rank[d - 1][np.arange(len(cnt[d])) >> 2] >= 0))
+            seq = split_rank[d - 1][j >> 2] * 4 + (j & 3)
+    # ---- final nodes, in path order
+    final = []
+    for k in range(k0, min(last, Dc) + 1):
+        jj = np.arange(len(cnt[k]))
+        exists = cnt[k] != 0
+        if k > k0:
+            exists &= split_rank[k - 1][jj >> 2] >= 0
+        for q in np.flatnonzero(exists & (split_rank[k] < 0)):
+            final.append((int(q) << (2 * (Dc - k)), int(best[k][q])))
+    final.sort()
+    out = set()
+    for _, b in final:
+        i = best_idx[b]
+        out.add((int(xy[i, 0]), int(xy[i, 1]), int(resp[i])))
+    return out
+
+
+def _oracle_set(oracle, xy, resp, W, H, quota):
+    order = _canonical_order(xy, W, H)
+    c = np.zeros(len(xy), oracle.CAND_DTYPE)
+    c["x"], c["y"], c["response"] = xy[order, 0], xy[order, 1], resp[order]
+    sel = oracle.distribute_octree(c, 16, 16 + W, 16, 16 + H, quota)
+    return {(int(c["x"][s]), int(c["y"][s]), int(c["response"][s])) for s in sel}
+
+
+GEOMS = [(608, 448), (816, 448), (1248, 688), (147, 102), (816, 768), (225, 161), (1888, 1048), (412, 302), (1200, 380)]
+
+
+@st.composite
+def clouds(draw):
+    W, H = draw(st.sampled_from(GEOMS))
+    kind = draw(st.sampled_from(["uniform", "uniform", "clustered", "lines", "grid"]))
+    seed = draw(st.integers(0, 2 ** 31 - 1))
+    rng = np.random.default_rng(seed)
+    n = draw(st.sampled_from([1, 2, 5, 40, 300, 900, 3000, W * H // 45]))
+    if kind == "uniform":
+        xy = np.stack([rng.integers(3, W - 3, n), rng.integers(3, H - 3, n)], 1)
+    elif kind == "clustered":
+        k = draw(st.integers(1, 6))
+        ccx, ccy = rng.integers(3, W - 3, k), rng.integers(3, H - 3, k)
+        pick = rng.integers(0, k, n)
+        sx = draw(st.sampled_from([2, 8, 30, 90]))
+        xy = np.stack([np.clip(ccx[pick] + rng.normal(0, sx, n).astype(int), 3, W - 4),
+                       np.clip(ccy[pick] + rng.normal(0, sx, n).astype(int), 3, H - 4)], 1)
+    elif kind == "lines":
+        xy = np.stack([rng.integers(3, W - 3, n), np.full(n, int(rng.integers(3, H - 3)))], 1)
+    else:
+        step = draw(st.sampled_from([2, 7, 16, 31]))
+        gx, gy = np.meshgrid(np.arange(3, W - 3, step), np.arange(3, H - 3, step))
+        xy = np.stack([gx.ravel(), gy.ravel()], 1)
+        xy = xy[rng.permutation(len(xy))[:n]]
+    xy = np.unique(xy.astype(np.int64), axis=0)
+    n_resp = draw(st.sampled_from([1, 2, 5, 248]))
+    resp = rng.integers(7, 7 + n_resp, len(xy))
+    quota = draw(st.one_of(st.integers(1, 40), st.integers(40, 500), st.sampled_from([len(xy), len(xy) + 5, 1000])))
+    return W, H, xy, resp, int(quota)
+
+
+_taken = {"pyramid": 0, "bail": 0}
+
+
+@settings(max_examples=400, deadline=None, suppress_health_check=[HealthCheck.too_slow, HealthCheck.function_scoped_fixture,
+                                                                  HealthCheck.data_too_large], derandomize=True)
+@given(case=clouds())
+def test_pyramid_selection_equals_oracle(oracle, case):
+    W, H, xy, resp, quota = case
+    got = pyramid_select(xy, resp, W, H, quota)
+    if got is None:
+        _taken["bail"] += 1
+        return
+    _taken["pyramid"] += 1
+    assert got == _oracle_set(oracle, xy, resp, W, H, quota), f"{W}x{H} n={len(xy)} quota={quota}"
+
+
+def test_pyramid_path_is_the_common_case():
+    """runs after the fuzz: the model must have decided most clouds itself (a model that always bails proves nothing)"""
+    assert _taken["pyramid"] >= 100, _taken
+
+
+def test_pyramid_real_candidates(oracle, synth):
+    """candidate clouds of real frames at every level with the real quotas: the path the bench takes"""
+    for w, h, seed in ((640, 480, 501), (848, 480, 502), (1280, 720, 503)):
+        img = synth.textured_frame(w, h, seed)
+        o = oracle.Oracle(w, h, 1000 if w < 1000 else 2000)
+        o.extract(img)
+        for lvl in range(8):
+            cand = o.level_candidates(lvl)
+            W, H = int(o.lw[lvl]) - 32, int(o.lh[lvl]) - 32
+            xy = np.stack([cand["x"], cand["y"]], 1).astype(np.int64)
+            resp = cand["response"].astype(np.int64)
+            for quota in (int(o.nfeat[lvl]), 17):
+                got = pyramid_select(xy, resp, W, H, quota)
+                assert got is not None, (w, h, lvl, quota)
+                assert got == _oracle_set(oracle, xy, resp, W, H, quota), (w, h, lvl, quota)
