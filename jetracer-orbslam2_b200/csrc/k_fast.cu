@@ -20,6 +20,8 @@
 // Bound: SM issue slots / shared-memory bandwidth, not HBM.
 #include <cuda.h>
 
+#include <cstdlib>
+
 #include "orbb_internal.cuh"
 
 namespace orbb {
@@ -382,6 +384,257 @@ k_fast_cells(const CUtensorMap *__restrict__ maps, const LevelDev *__restrict__ 
     }
 }
 
+// ---- Small grids (a lone frame, the reference's operating mode): ONE CTA OF FOUR WARPS PER CELL.  With fewer cells
+// than the GPU has warp slots, the warp-per-cell kernel above is a chain of ~2 000 dependent warp instructions per cell
+// (10-11 us for one 848x480 level on an otherwise idle GPU).  Here the four warps of a CTA share the cell: the window rows
+// of the staging, the unit columns of the precheck and the entries of the arc-score / NMS / emit queues are dealt out
+// over 128 threads, with one block barrier between phases and shared-memory counters for the queue lengths.  Same
+// tiles, same arithmetic, same per-cell threshold decision; queue order differs, which nothing downstream depends on
+// (candidates reach their list through atomics in the warp-per-cell kernel too).  Corners and NMS survivors ping-pong
+// between two queues (in place, one warp's compaction would overwrite entries another warp has not read yet).
+template <int TP>
+__global__ void __launch_bounds__(128)
+k_fast_cell_cta(const LevelDev *__restrict__ levels, const CellEntry *__restrict__ cells, int n_cells, int n_levels,
+                int *__restrict__ cand_count, int t_lo, int t_hi, FastSmemCfg cfg, int frame_base) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    __shared__ int s_cnt[2][3];  // per pass: queued pixels, corners, NMS survivors
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int cell_id = blockIdx.x;
+    const int frame = blockIdx.y + frame_base;
+    const CellEntry c = cells[cell_id];
+    const LevelDev &L = levels[c.level];
+    uint8_t *tile = smem;
+    uint8_t *score = tile + cfg.tile_bytes;
+    uint16_t *queue = reinterpret_cast<uint16_t *>(score + cfg.score_bytes);
+    uint16_t *queue2 = queue + cfg.queue_len;
+    constexpr int tp = TP, sp = TP, tpw = TP >> 2;
+    const int cw = c.cw, ch = c.ch;
+    const uint32_t *tile32 = reinterpret_cast<const uint32_t *>(tile);
+    if (tid < 6) (&s_cnt[0][0])[tid] = 0;
+    pdl_wait();
+
+    {   // ---- staging (see k_fast_cells): the rows of a step are dealt out over the four warps
+        const int gx = c.x0 - 4, xa16 = gx & ~15, wo = (gx - xa16) >> 2, sh = (gx & 3) * 8;
+        const int nwords = (cw + 7 + 3) >> 2;
+        const int nld = ((wo + nwords) >> 2) + 1;
+        const int nrows = ch + 6;
+        const int lps = nld <= 4 ? 2 : 3, rpi = 32 >> lps;
+        const int g = lane & ((1 << lps) - 1), rl = lane >> lps;
+        const bool in_row = 16 * g + 16 <= L.pitch - (ORBB_ROI_X0 + xa16);
+        const uint8_t *src = L.img + (size_t)frame * L.frame_stride + (size_t)(ORBB_BORDER + c.y0 - 3) * L.pitch + ORBB_ROI_X0 + xa16 + (in_row ? 16 * g : 0);
+        asm volatile("" : "+l"(src));
+        const unsigned pitch = (unsigned)L.pitch;
+        const int k0 = 4 * g - wo;
+        unsigned keep = 0;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) keep |= (in_row && g < nld && k0 + i >= 0 && k0 + i < tpw) ? 1u << i : 0u;
+        uint32_t *t0 = reinterpret_cast<uint32_t *>(tile) + k0;
+        constexpr int NF = 3;  // rows in flight per lane: 4 warps x 8 (4) rows x 3 = 96 (48) rows per round
+        for (int rb = 0; rb < nrows; rb += NF * 4 * rpi) {
+            const int r0 = rb + warp * rpi + rl;
+            uint4 a[NF];
+#pragma unroll
+            for (int u = 0; u < NF; ++u)
+                a[u] = __ldg(reinterpret_cast<const uint4 *>(src + (unsigned)min(r0 + u * 4 * rpi, nrows - 1) * pitch));
+#pragma unroll
+            for (int u = 0; u < NF; ++u) {
+                const unsigned nx = __shfl_down_sync(0xffffffffu, a[u].x, 1);
+                const int r = r0 + u * 4 * rpi;
+                const unsigned m = r < nrows ? keep : 0u;
+                uint32_t *t = t0 + r * tpw;
+                if (m & 1u) t[0] = __funnelshift_r(a[u].x, a[u].y, sh);
+                if (m & 2u) t[1] = __funnelshift_r(a[u].y, a[u].z, sh);
+                if (m & 4u) t[2] = __funnelshift_r(a[u].z, a[u].w, sh);
+                if (m & 8u) t[3] = __funnelshift_r(a[u].w, nx, sh);
+            }
+        }
+        for (int i = tid; i < cfg.score_bytes >> 4; i += 128) reinterpret_cast<uint4 *>(score)[i] = make_uint4(0u, 0u, 0u, 0u);
+    }
+    __syncthreads();
+
+    const unsigned lt_mask = (1u << lane) - 1u;
+    const int nux = (cw + 3) >> 2, nunits = nux * ch;
+    const unsigned inv_nux = c.inv_nux;
+    int kn = 0;
+    uint16_t *qsurv = queue;
+    for (int pass = 0; pass < 2; ++pass) {
+        const int thr = pass == 0 ? t_hi : t_lo;
+        if (pass == 1 && t_lo == t_hi) break;
+        int *cnt = s_cnt[pass];
+        // ---- phase 1: precheck (k_fast_cells: lane = tile row, sliding word windows); warp w takes the unit columns
+        // [w * Uw, (w + 1) * Uw) of round A and the steps w, w + 4, ... of round B
+        const unsigned cadd = (unsigned)(128 - min(thr + 1, 128)) * 0x01010101u;
+        const unsigned last_mask = (cw & 3) ? (0x80808080u >> (8 * (4 - (cw & 3)))) : 0x80808080u;
+        auto precheck = [&](unsigned cc, unsigned up, unsigned dn, unsigned lf, unsigned rt) -> unsigned {
+            const unsigned a0 = __vabsdiffu4(dn, cc), a8 = __vabsdiffu4(up, cc);
+            const unsigned a4 = __vabsdiffu4(rt, cc), a12 = __vabsdiffu4(lf, cc);
+            return ((a0 + cadd) | a0 | (a8 + cadd) | a8) & ((a4 + cadd) | a4 | (a12 + cadd) | a12);
+        };
+        const int rows_a = min(ch, 32), units_a = rows_a * nux;
+        for (int round = 0; round < 2; ++round) {
+            int nst;  // steps of this warp in this round (<= 16: 64 flag bits)
+            int jb = 0;
+            unsigned wlo = 0, whi = 0;
+            if (round == 0) {
+                const int Uw = (nux + 3) >> 2;
+                jb = warp * Uw;
+                nst = max(0, min(nux, jb + Uw) - jb);
+                if (nst > 0) {
+                    const uint32_t *row = tile32 + ((lane < rows_a ? lane : 0) + 3) * tpw + jb;  // row[0] = left word of unit jb
+                    const unsigned live = lane < rows_a ? 0x80808080u : 0u;
+                    unsigned left = row[0], cc = row[1];
+                    unsigned lp = row[2 * tpw], cp = row[1 + 2 * tpw], lm = row[-2 * tpw], cm = row[1 - 2 * tpw];
+                    for (int j = 0; j < nst; ++j) {
+                        const unsigned right = row[j + 2], dn = row[j + 1 + 3 * tpw], up = row[j + 1 - 3 * tpw];
+                        const unsigned rp = row[j + 2 + 2 * tpw], rm = row[j + 2 - 2 * tpw];
+                        const unsigned rt = __funnelshift_r(cc, right, 24), lf = __funnelshift_r(left, cc, 8);
+                        unsigned flags = precheck(cc, up, dn, lf, rt) & (jb + j == nux - 1 ? last_mask & live : live);
+                        flags &= precheck(cc, __funnelshift_r(lm, cm, 16), __funnelshift_r(cp, rp, 16),
+                                          __funnelshift_r(lp, cp, 16), __funnelshift_r(cm, rm, 16));
+                        left = cc; cc = right; lp = cp; cp = rp; lm = cm; cm = rm;
+                        const unsigned nib = __umulhi(flags, 0x02040810u);
+                        wlo = __funnelshift_r(wlo, whi, 4);
+                        whi = __funnelshift_r(whi, nib, 4);
+                    }
+                }
+            } else {
+                const int U = (nunits - units_a + 31) >> 5;  // steps of round B in all
+                nst = U > warp ? (U - warp + 3) >> 2 : 0;
+                for (int s = 0; s < nst; ++s) {
+                    const int ur = units_a + (warp + 4 * s) * 32 + lane;
+                    const bool valid = ur < nunits;
+                    const int u = valid ? ur : units_a;
+                    const int y = (int)(((unsigned)u * inv_nux) >> 20), j = u - y * nux;
+                    const uint32_t *row = tile32 + (y + 3) * tpw + j;
+                    const unsigned cc = row[1], dn = row[1 + 3 * tpw], up = row[1 - 3 * tpw];
+                    const unsigned rt = __funnelshift_r(cc, row[2], 24), lf = __funnelshift_r(row[0], cc, 8);
+                    const unsigned vm = valid ? (j == nux - 1 ? last_mask : 0x80808080u) : 0u;
+                    const unsigned nib = __umulhi(precheck(cc, up, dn, lf, rt) & vm, 0x02040810u);
+                    wlo = __funnelshift_r(wlo, whi, 4);
+                    whi = __funnelshift_r(whi, nib, 4);
+                }
+            }
+            if (round == 1 && nunits <= units_a) break;  // block-uniform: no round B in this cell
+            // queue positions: warp prefix sum of the lanes' counts + one shared-memory atomic per warp
+            const int c_own = __popc(wlo) + __popc(whi);
+            int incl = c_own;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += t;
+            }
+            int wbase = 0;
+            if (lane == 31 && incl) wbase = atomicAdd(&cnt[0], incl);
+            wbase = __shfl_sync(0xffffffffu, wbase, 31);
+            uint16_t *qp = queue + wbase + incl - c_own;
+            const int xoff = 4 * nst - 64;  // bit position -> 4 * step + pixel
+            const int row_e = lane * tp + xoff + 4 * jb;
+#pragma unroll
+            for (int half = 1; half >= 0; --half) {
+                unsigned w = half ? whi : wlo;
+                while (w) {
+                    const int b = 31 - __clz(w);
+                    w &= ~(1u << b);
+                    int e = row_e + 32 * half + b;
+                    if (round != 0) {
+                        const int pos = 32 * half + b + xoff, u = units_a + (warp + 4 * (pos >> 2)) * 32 + lane;
+                        const int y = (int)(((unsigned)u * inv_nux) >> 20);
+                        e = y * (tp - 4 * nux) + 4 * u + (pos & 3);
+                    }
+                    *qp++ = (uint16_t)e;
+                }
+            }
+        }
+        __syncthreads();
+        const int qn = cnt[0];
+
+        // ---- phase 2: exact arc score; corners go to the score tile and to the second queue
+        for (int base = 0; base < qn; base += 128) {  // block-uniform trip count
+            const int i = base + tid;
+            int idx = 0, m = 0;
+            if (i < qn) {
+                idx = queue[i];
+                m = arc_score(tile + 3 * tp + 4 + idx, tp);
+                m = m > thr ? m : 0;
+                if (m) score[sp + 1 + idx] = (uint8_t)min(m, 255);
+            }
+            const unsigned bm = __ballot_sync(0xffffffffu, m != 0);
+            int wb = 0;
+            if (lane == 0 && bm) wb = atomicAdd(&cnt[1], __popc(bm));
+            wb = __shfl_sync(0xffffffffu, wb, 0);
+            if (m) queue2[wb + __popc(bm & lt_mask)] = (uint16_t)idx;
+        }
+        __syncthreads();
+        const int cn = cnt[1];
+
+        // ---- phase 3: strict 3x3 NMS inside the cell; survivors go back to the first queue
+        for (int base = 0; base < cn; base += 128) {
+            const int i = base + tid;
+            int idx = 0;
+            bool keep = false;
+            if (i < cn) {
+                idx = queue2[i];
+                const uint8_t *s = score + sp + 1 + idx;
+                const int v = s[0];
+                const int n0 = max3(s[-sp - 1], s[-sp], s[-sp + 1]);
+                const int n1 = max3(s[-1], s[1], s[sp - 1]);
+                const int n2 = max3(s[sp], s[sp + 1], n0);
+                keep = v > max(n1, n2);
+            }
+            const unsigned bm = __ballot_sync(0xffffffffu, keep);
+            int wb = 0;
+            if (lane == 0 && bm) wb = atomicAdd(&cnt[2], __popc(bm));
+            wb = __shfl_sync(0xffffffffu, wb, 0);
+            if (keep) queue[wb + __popc(bm & lt_mask)] = (uint16_t)idx;
+        }
+        __syncthreads();
+        kn = cnt[2];
+        if (kn > 0) break;  // cv::FAST(ini) found keypoints: no fallback for this cell
+    }
+
+    // ---- phase 4: append to the (frame, level) candidate list, one atomicAdd per warp and 32 survivors
+    int *counter = cand_count + frame * n_levels + c.level;
+    uint32_t *cand = L.cand + (size_t)frame * L.cand_cap;
+    for (int base = 0; base < kn; base += 128) {
+        const int i = base + tid;
+        bool emit = false;
+        uint32_t packed = 0;
+        if (i < kn) {
+            const int idx = qsurv[i];
+            const int y = idx / tp, x = idx - y * tp;
+            const int m = score[sp + 1 + idx];
+            emit = true;
+            packed = (uint32_t)(c.x0 + x - ORBB_MIN_BORDER) | ((uint32_t)(c.y0 + y - ORBB_MIN_BORDER) << 12) | ((uint32_t)m << 24);
+        }
+        const unsigned bm = __ballot_sync(0xffffffffu, emit);
+        if (bm) {
+            int slot = 0;
+            if (lane == 0) slot = atomicAdd(counter, __popc(bm));
+            slot = __shfl_sync(0xffffffffu, slot, 0);
+            if (emit) {
+                const int dst = slot + __popc(bm & lt_mask);
+                if (dst < L.cand_cap) {
+                    cand[dst] = packed;
+                    if (L.tbl_cells) oct_bin_candidate(L, frame, packed);
+                }
+            }
+        }
+    }
+}
+
+template <int TP>
+static cudaError_t launch_fast_cta_t(const LevelDev *d_levels, const CellEntry *d_cells, int n_cells, int n_levels,
+                                     int *d_cand_count, int t_lo, int t_hi, const FastSmemCfg &cfg, int frame_base, int n_frames,
+                                     cudaStream_t st) {
+    const size_t smem = (size_t)cfg.tile_bytes + cfg.score_bytes + 4 * (size_t)cfg.queue_len;  // two queues
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(k_fast_cell_cta<TP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+    }
+    return launch_pdl(k_fast_cell_cta<TP>, dim3(n_cells, n_frames), dim3(128), smem, st, d_levels, d_cells, n_cells, n_levels,
+                      d_cand_count, t_lo, t_hi, cfg, frame_base);
+}
+
 template <bool DUMP, bool TMA, int TP>
 static cudaError_t launch_fast_t(const CUtensorMap *maps, const LevelDev *d_levels, const CellEntry *d_cells, int n_cells,
                                  int n_levels, int *d_cand_count, int t_lo, int t_hi, const FastSmemCfg &cfg,
@@ -403,6 +656,18 @@ cudaError_t launch_fast(const void *tma_maps, const LevelDev *d_levels, const Ce
     if (tma_maps)
         return launch_fast_t<false, true, 0>(static_cast<const CUtensorMap *>(tma_maps), d_levels, d_cells, n_cells, n_levels,
                                              d_cand_count, t_lo, t_hi, cfg, frame_base, n_frames, nullptr, nullptr, st);
+    // small grids: one CTA of four warps per cell while every cell still gets its own CTA slot (148 SMs x 8 CTAs);
+    // ORBB_FAST_CTA=0 keeps the warp-per-cell kernel (diagnostics / A-B timing)
+    static const bool cta_ok = !(getenv("ORBB_FAST_CTA") && atoi(getenv("ORBB_FAST_CTA")) == 0);
+    if (cta_ok && (long long)n_cells * n_frames <= 148 * 8) {
+#define ORBB_FAST_CTA_TP(P)                                                                                                 \
+    case P: return launch_fast_cta_t<P>(d_levels, d_cells, n_cells, n_levels, d_cand_count, t_lo, t_hi, cfg, frame_base, n_frames, st)
+        switch (cfg.tile_pitch) {
+            ORBB_FAST_CTA_TP(44); ORBB_FAST_CTA_TP(52); ORBB_FAST_CTA_TP(60); ORBB_FAST_CTA_TP(68); ORBB_FAST_CTA_TP(76);
+            default: break;
+        }
+#undef ORBB_FAST_CTA_TP
+    }
 #define ORBB_FAST_TP(P)                                                                                                     \
     case P: return launch_fast_t<false, false, P>(nullptr, d_levels, d_cells, n_cells, n_levels, d_cand_count, t_lo, t_hi, cfg, \
                                                   frame_base, n_frames, nullptr, nullptr, st)

@@ -3,8 +3,9 @@
 // (src/cuda/nms.cu:86-254) with upstream ORB-SLAM2 semantics.
 //
 // Upstream is a sequential std::list algorithm.  The B200 formulation removes the list, and in the common case
-// the sort as well (see "CELL-TABLE FAST PATH" in the kernel: the FAST kernel bins the candidates into the tree
-// cells of depth 5-6, and the passes below run over the non-empty cells).  The general path, also the fallback:
+// the keys as well (see "PYRAMID PATH" below: the FAST kernel bins the candidates into the tree cells of depth
+// 4-6, and the selection is read off a count / best-key pyramid over those cells).  The general path, also the
+// fallback when the selection has to part keys below the table's depth:
 //  * every split line of the tree depends only on the node rectangle, so the tree is a tensor
 //    product of two 1-D binary trees; the host tabulates, per coordinate, the Morton-spread path
 //    bits (xkey/ykey).  key = xkey[x] | ykey[y] is the key's full root-to-leaf path.
@@ -58,7 +59,7 @@ struct __align__(16) OctStatic {
     uint32_t warp_tot[OCT_WARPS];
     int ctl[16];
 };
-enum { C_MODE = 0, C_DEPTH, C_SIZE, C_PN, C_QN, C_CUT, C_TOTAL, C_NFINAL, C_BAIL };
+enum { C_MODE = 0, C_DEPTH, C_SIZE, C_PN, C_QN, C_CUT, C_TOTAL, C_NFINAL };
 
 // exclusive block scan of one value per thread; returns exclusive prefix, *total = block sum
 __device__ __forceinline__ uint32_t block_excl_scan(uint32_t v, uint32_t *warp_tot, uint32_t *total) {
@@ -362,6 +363,56 @@ __device__ __forceinline__ bool octree_pyramid(const LevelDev &L, OctStatic &S, 
         for (int d = k0;; ++d) {
             if (d + 1 > Dc) return false;  // this round parts at depth d + 1
             const int Md = R << (2 * d), base = lvl_off(d), pbase = d > 0 ? lvl_off(d - 1) : 0;
+            if (Md <= 256 && Md <= pcap2) {
+                // Small level (the usual case: 64 or 128 nodes): no list, no sort, no scan.  Upstream's processing order is
+                // descending (count, creation sequence); what the round needs per node is how much the nodes processed
+                // BEFORE it have added to the list -- G = sum of their gains (the node is split iff size + G < N) -- and its
+                // rank among them (the creation order of its children).  Both are sums over the nodes with a larger key:
+                // G_ threads per node each compare it with a slice of the level, one shuffle reduction per group.  The
+                // same sums give the level's total gain, so the round ends without a block-wide reduction.
+                if (tid < Md) {
+                    const uint32_t cnt = P.pc[base + tid];
+                    const unsigned info = P.pinfo[base + tid];
+                    bool live;
+                    uint32_t seq;
+                    if (d == k0) {
+                        live = cnt > 1;
+                        seq = ((uint32_t)tid ^ digit_mask ^ root_mask) & 0x7fffffffu;
+                    } else {
+                        const unsigned pr = P.pinfo[pbase + (tid >> 2)] >> 3;
+                        live = cnt > 1 && pr != 0;
+                        seq = (pr - 1u) * 4u + ((unsigned)tid & 3u);
+                    }
+                    // (count, sequence) is unique per live node, so the gain in the low bits never decides a comparison
+                    skey[tid] = live ? ((unsigned long long)cnt << 40) | ((unsigned long long)seq << 3) | ((info & 7u) - 1u) : 0ull;
+                }
+                __syncthreads();
+                const int G_ = min(32, min(OCT_THREADS / Md, Md)), Sl = Md / G_;
+                const int node = min(tid / G_, Md - 1), part = tid & (G_ - 1);
+                const unsigned long long my = skey[node];
+                uint32_t rank = 0, gsum = 0, gall = 0;
+                for (int i = 0; i < Sl; ++i) {
+                    const unsigned long long o = skey[i * G_ + part];  // the group's lanes read consecutive keys
+                    const uint32_t g = (uint32_t)o & 7u;
+                    gall += g;
+                    if (o > my) { ++rank; gsum += g; }
+                }
+                for (int o = 1; o < G_; o <<= 1) {
+                    rank += __shfl_xor_sync(FULL, rank, o);
+                    gsum += __shfl_xor_sync(FULL, gsum, o);
+                    gall += __shfl_xor_sync(FULL, gall, o);
+                }
+                const bool is_live = my != 0ull && tid / G_ < Md;
+                const bool split = is_live && (int)(size + gsum) < N;
+                const bool any_live = __syncthreads_or(is_live);
+                if (split && part == 0) P.pinfo[base + node] |= (uint16_t)((rank + 1u) << 3);
+                __syncthreads();
+                if (any_live) last = d + 1;
+                // the cut falls inside this level iff splitting all of it reaches N; otherwise everything was split
+                if (!any_live || (int)(size + gall) >= N || gall == 0) break;
+                size += (int)gall;
+                continue;
+            }
             if (tid == 0) { S.ctl[C_PN] = 0; S.ctl[C_CUT] = 0x7fffffff; }
             __syncthreads();
             // expandable nodes of this level -> sort list keyed by (count, creation sequence); list order is irrelevant
@@ -512,68 +563,32 @@ k_octree(const LevelDev *__restrict__ levels, int n_levels, const int *__restric
     const uint32_t *cand = L.cand + fo;
     const int D = L.depth;
 
-    // ---- CELL-TABLE FAST PATH.  The selection only ever looks at the tree down to the depth at which ~N nodes exist
-    // (4-6 for the quotas of a pyramid level), while the path keys resolve single pixels (D ~ 10).  The FAST kernel
-    // therefore bins every candidate it emits into the 4^Dc cells of depth Dc (L.tbl_cnt / L.tbl_best in global
-    // memory: per cell a key count and the best key -- response, then earliest upstream order).  Cell index = path
-    // prefix, so the table IS the sorted order: one prefix scan compacts the non-empty cells into "records" (path
-    // prefix, running key count) -- no radix sort, and every later pass runs over the records (a quarter of the
-    // keys) instead of the keys.  Node sizes come from the running key counts; everything else (parting depths,
-    // breadth-first replay, careful phase) is unchanged as long as it stays at depths <= Dc.  If it would go deeper
-    // (heavily clustered keys), or the table does not describe this candidate list, the CTA falls back to the
-    // general path below.  The CTA clears its table before it exits.
-    const int Dc = L.tbl_dc, T = L.tbl_cells;
+    // The pyramid path (above) answers from the FAST kernel's cell table when the table is deep enough for the quota
+    // (T >= 4 N), describes this candidate list, and the selection stays at depths <= Dc; otherwise the general
+    // sorted-key path below runs.  Either way the CTA clears its table before it exits.
+    const int T = L.tbl_cells;
     const bool try_fast = !no_fast && T > 0 && T >= 4 * N && n < L.cand_cap;
     uint32_t *tbl_cnt = L.tbl_cnt + (size_t)frame * T;
     unsigned long long *tbl_best = L.tbl_best + (size_t)frame * T;
-    const int csh = 2 * (D - Dc);  // path key -> cell index
 
-    // no_fast: bit 0 = general path only (ORBB_OCT_NOFAST), bit 1 = the round-2a record path instead of the pyramid path
     bool done = false;
-    if (try_fast && no_fast == 0 && pcap2 <= 8190) {
+    if (try_fast && pcap2 <= 8190) {
 #ifdef ORBB_OCT_PROF
         done = octree_pyramid(L, S, tbl_cnt, tbl_best, n, N, skey, sval, pcap2, L.sel + (size_t)frame * L.sel_cap, out_count, prof_t);
         if (done && tid == 0 && blockIdx.x == 0 && blockIdx.y == 0)
-            printf("oct-pyr n=%d N=%d Dc=%d T=%d | table+pyramid %lld replay+careful %lld final %lld cycles\n", n, N, Dc, T,
+            printf("oct-pyr n=%d N=%d Dc=%d T=%d | table+pyramid %lld replay+careful %lld final %lld cycles\n", n, N, L.tbl_dc, T,
                    prof_t[1] - prof_t[0], prof_t[2] - prof_t[1], prof_t[3] - prof_t[2]);
 #else
         done = octree_pyramid(L, S, tbl_cnt, tbl_best, n, N, skey, sval, pcap2, L.sel + (size_t)frame * L.sel_cap, out_count, nullptr);
 #endif
         __syncthreads();  // the general path reuses the shared arrays
     }
-    if (!done)
-    for (int attempt = (try_fast && (no_fast & 2)) ? 0 : 1; attempt < 2; ++attempt) {
-    const bool fastp = attempt == 0;
-    int m;               // items the passes below run over: records (fast path) or keys
-    uint2 *kva, *kvb;    // item arrays; kv[i].x = path key (prefix), kv[i].y = running key count (fast) / candidate
+    if (!done) {
+    int m;               // keys
+    uint2 *kva, *kvb;    // kv[i].x = path key, kv[i].y = packed candidate
     int key_stride;
     bool in_smem;
-    if (fastp) {
-        const int mc = (min(T, n) + 1 + 15) & ~15;  // records + sentinel
-        in_smem = (size_t)mc * 16 <= (size_t)sort_bytes;
-        kva = in_smem ? reinterpret_cast<uint2 *>(dyn + sort_off) : L.kv_a + fo;
-        kvb = in_smem ? kva + mc : L.kv_b + fo;
-        key_stride = in_smem ? mc : L.cand_cap;
-        // ---- F. compact the non-empty cells (already in path order) into records; T <= 4096 = 8 cells per thread
-        const int per = (T + OCT_THREADS - 1) / OCT_THREADS;
-        const int c0 = min(T, tid * per);
-        uint32_t w[8], my_cells = 0, my_keys = 0;
-#pragma unroll
-        for (int k = 0; k < 8; ++k) w[k] = (k < per && c0 + k < T) ? tbl_cnt[c0 + k] : 0u;
-#pragma unroll
-        for (int k = 0; k < 8; ++k) { my_cells += w[k] != 0; my_keys += w[k]; }
-        uint32_t tot_cells, tot_keys;
-        uint32_t pos = block_excl_scan(my_cells, S.warp_tot, &tot_cells);
-        uint32_t run = block_excl_scan(my_keys, S.warp_tot, &tot_keys);
-        // the table must describe exactly this candidate list (it would not after, say, two detect calls in a row)
-        if (tot_keys != (uint32_t)n) continue;  // block-uniform
-#pragma unroll
-        for (int k = 0; k < 8; ++k)
-            if (w[k]) { kva[pos++] = make_uint2((uint32_t)(c0 + k) << csh, run); run += w[k]; }
-        m = (int)tot_cells;
-        if (tid == 0) kva[m] = make_uint2(0xffffffffu, tot_keys);  // sentinel: closes the last record's key count
-        __syncthreads();
-    } else {
+    {
     // (path key, packed candidate) pairs, radix ping-pong.  When the launch could afford the shared memory (small
     // grids: one or two CTAs per SM) and this level's candidates fit, every per-key array lives in shared memory:
     // the scattered 8-byte stores of the sort and the strided passes over the keys then never leave the SM.
@@ -607,8 +622,7 @@ k_octree(const LevelDev *__restrict__ levels, int n_levels, const int *__restric
     }
     const uint2 *kv = kva;  // sorted
     OCT_T(2);
-    // number of keys in the items [a, b): records carry a running key count
-    auto nkeys = [&](uint32_t a, uint32_t b) -> uint32_t { return fastp ? kv[b].y - kv[a].y : b - a; };
+    auto nkeys = [&](uint32_t a, uint32_t b) -> uint32_t { return b - a; };
     // free ping-pong buffers become scratch: two generations of u16 segment ids, and the head flags
     uint16_t *seg_a = reinterpret_cast<uint16_t *>(kvb), *seg_b = seg_a + key_stride;
     uint8_t *head = reinterpret_cast<uint8_t *>(seg_b + key_stride);
@@ -616,7 +630,6 @@ k_octree(const LevelDev *__restrict__ levels, int n_levels, const int *__restric
 
     // ---- 3. split depths + histograms
     if (tid < 40) { S.hist_sd[tid] = 0; S.hist_g[tid] = 0; }
-    if (tid == 0) S.ctl[C_BAIL] = 0;
     __syncthreads();
     // Per-thread packed 8-bit counters, 16 bins per histogram (depths 0..D <= 15), flushed to the shared histograms
     // once per warp (and every 255 items per thread): corners cluster, so most partings fall into two or three deep
@@ -654,7 +667,7 @@ k_octree(const LevelDev *__restrict__ levels, int n_levels, const int *__restric
                 if (rb < 8) cs_lo += one; else cs_hi += one;
             }
             // hist_g counts the single-key nodes by the depth at which they become isolated
-            if (!fastp || kv[i + 1].y - kv[i].y == 1u) {
+            {
                 const unsigned g = min(max(l, r), 15u);
                 const unsigned long long one = 1ull << (8 * (g & 7u));
                 if (g < 8) cg_lo += one; else cg_hi += one;
@@ -670,7 +683,6 @@ k_octree(const LevelDev *__restrict__ levels, int n_levels, const int *__restric
         int prev = 1 + S.hist_sd[0], cumL = prev, cumS = S.hist_g[0];
         int mode = 0, depth = D + 1;
         for (int k = 1; k <= D + 1; ++k) {
-            if (fastp && Dc < D && k > Dc) { S.ctl[C_BAIL] = 1; break; }  // the records cannot tell deeper partings
             if (k <= D) { cumL += S.hist_sd[k]; cumS += S.hist_g[k]; }
             const int Ek = cumL - cumS;
             if (cumL >= N || cumL == prev) { mode = 0; depth = k; break; }
@@ -681,12 +693,10 @@ k_octree(const LevelDev *__restrict__ levels, int n_levels, const int *__restric
         S.ctl[C_PN] = 0; S.ctl[C_QN] = 0;
     }
     __syncthreads();
-    if (S.ctl[C_BAIL]) { __syncthreads(); continue; }
     const int mode = S.ctl[C_MODE], k0 = S.ctl[C_DEPTH];
     for (int i = tid; i < m; i += OCT_THREADS) head[i] = (i == 0 || sd[i - 1] <= k0) ? 1 : 0;
     __syncthreads();
     OCT_T(4);
-    bool bail = false;
     if (mode == 1) {
         // ---- 5. careful phase, key-parallel.  A round works on the current head-delimited nodes: nst[] start of
         // every node, seq[] creation sequence of the nodes created by the previous round that hold > 1 key
@@ -711,7 +721,6 @@ k_octree(const LevelDev *__restrict__ levels, int n_levels, const int *__restric
         }
         int d = k0;
         while (true) {
-            if (fastp && Dc < D && d + 1 > Dc) { bail = true; break; }  // block-uniform: this round parts at depth d + 1
             const int size = S.ctl[C_SIZE];
             for (int sidx = tid; sidx < nseg; sidx += OCT_THREADS) { gain[sidx] = 0; rank_of[sidx] = -1; }
             if (tid == 0) { S.ctl[C_PN] = 0; S.ctl[C_CUT] = 0x7fffffff; }
@@ -783,7 +792,6 @@ k_octree(const LevelDev *__restrict__ levels, int n_levels, const int *__restric
             ++d;
         }
     }
-    if (bail) { __syncthreads(); continue; }
     OCT_T(5);
 
     // ---- 6. final nodes = head-delimited segments; keep the best key of each
@@ -799,12 +807,9 @@ k_octree(const LevelDev *__restrict__ levels, int n_levels, const int *__restric
         for (int j = 0; j < OCT_RB; ++j) {
             const int i = base + j * OCT_THREADS;
             sidx[j] = i < m ? (uint32_t)seg_a[i] : 0xffffffffu;
-            c[j] = i < m ? (fastp ? kv[i].x >> csh : kv[i].y) : 0u;
+            c[j] = i < m ? kv[i].y : 0u;
         }
-        if (fastp) {
-#pragma unroll
-            for (int j = 0; j < OCT_RB; ++j) vv[j] = sidx[j] != 0xffffffffu ? tbl_best[c[j]] : 0ull;  // the cell's best key
-        } else {
+        {
 #pragma unroll
             for (int j = 0; j < OCT_RB; ++j) { xo[j] = __ldg(&L.xord[c[j] & 0xfffu]); yo[j] = __ldg(&L.yord[(c[j] >> 12) & 0xfffu]); }
 #pragma unroll
@@ -843,12 +848,11 @@ k_octree(const LevelDev *__restrict__ levels, int n_levels, const int *__restric
     OCT_T(6);
 #ifdef ORBB_OCT_PROF
     if (tid == 0 && blockIdx.x == 0 && blockIdx.y == 0)
-        printf("oct n=%d m=%d N=%d D=%d Dc=%d T=%d fast=%d mode=%d k0=%d in_smem=%d | build+sort %lld sd %lld replay %lld careful %lld final %lld cycles\n",
-               n, m, N, D, Dc, T, (int)fastp, mode, k0, (int)in_smem, prof_t[2] - prof_t[0], prof_t[3] - prof_t[2],
+        printf("oct n=%d m=%d N=%d D=%d Dc=%d T=%d mode=%d k0=%d in_smem=%d | build+sort %lld sd %lld replay %lld careful %lld final %lld cycles\n",
+               n, m, N, D, L.tbl_dc, T, mode, k0, (int)in_smem, prof_t[2] - prof_t[0], prof_t[3] - prof_t[2],
                prof_t[4] - prof_t[3], prof_t[5] - prof_t[4], prof_t[6] - prof_t[5]);
 #endif
-    break;
-    }  // attempt
+    }  // general path
     if (T > 0) {  // hand the FAST kernel of the next batch an empty table (T is a multiple of 4)
         for (int i = tid; i < (T >> 2); i += OCT_THREADS) {
             reinterpret_cast<uint4 *>(tbl_cnt)[i] = make_uint4(0u, 0u, 0u, 0u);
@@ -902,7 +906,7 @@ cudaError_t launch_octree(const LevelDev *d_levels, int n_levels, const int *d_c
     size_t smem = octree_dyn_smem(sel_cap_max, pcap, pcap2);
     if (getenv("ORBB_OCT_PAD")) smem = std::max(smem, (size_t)atoi(getenv("ORBB_OCT_PAD")));
     // diagnostics / tests: ORBB_OCT_NOFAST=1 forces the general (radix sort) path of every CTA
-    const int nofast = (getenv("ORBB_OCT_NOFAST") ? 1 : 0) | (getenv("ORBB_OCT_RECORDS") ? 2 : 0);
+    const bool nofast = getenv("ORBB_OCT_NOFAST") != nullptr;
     // fewer CTAs than the GPU can hold at once: every CTA's own latency is the kernel's duration
     const long long ctas = (long long)n_launch_levels * n_frames;
     if (ctas <= 148 * 3) {
