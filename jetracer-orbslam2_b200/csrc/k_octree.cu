@@ -563,11 +563,12 @@ k_octree(const LevelDev *__restrict__ levels, int n_levels, const int *__restric
     const uint32_t *cand = L.cand + fo;
     const int D = L.depth;
 
-    // The pyramid path (above) answers from the FAST kernel's cell table when the table is deep enough for the quota
-    // (T >= 4 N), describes this candidate list, and the selection stays at depths <= Dc; otherwise the general
+    // The pyramid path (above) answers from the FAST kernel's cell table when the table describes this candidate list
+    // and the selection stays at depths <= Dc (it decides that itself: orbb_create sizes the table for 4 x the level's
+    // quota, capped at 4096 cells, so a level with a very large quota may still part deeper); otherwise the general
     // sorted-key path below runs.  Either way the CTA clears its table before it exits.
     const int T = L.tbl_cells;
-    const bool try_fast = !no_fast && T > 0 && T >= 4 * N && n < L.cand_cap;
+    const bool try_fast = !no_fast && T > 0 && n < L.cand_cap;  // an overflowed list no longer matches its table
     uint32_t *tbl_cnt = L.tbl_cnt + (size_t)frame * T;
     unsigned long long *tbl_best = L.tbl_best + (size_t)frame * T;
 
