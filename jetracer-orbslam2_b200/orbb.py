@@ -573,10 +573,16 @@ class RgbdFrameStage:
         self._check(self._lib.orbb_rgbd_stage_wait(self._s, ticket, C.byref(out)))
         n, mk = out.n_frames, out.max_kp
 
+        cache = self.__dict__.setdefault("_views", {})  # the result arrays are stage-owned pinned buffers (two parities)
+
         def view(ptr, dtype, shape):
-            count = int(np.prod(shape))
-            buf = (C.c_uint8 * (count * np.dtype(dtype).itemsize)).from_address(ptr)
-            return np.frombuffer(buf, dtype, count).reshape(shape)
+            key = (ptr, np.dtype(dtype).str, shape)
+            v = cache.get(key)
+            if v is None:
+                count = int(np.prod(shape))
+                buf = (C.c_uint8 * (count * np.dtype(dtype).itemsize)).from_address(ptr)
+                v = cache[key] = np.frombuffer(buf, dtype, count).reshape(shape)
+            return v
 
         return dict(n_frames=n, max_kp=mk,
                     keypoints_count=view(out.keypoints_count, np.int32, (n,)),

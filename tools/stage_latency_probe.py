@@ -1,14 +1,18 @@
 #!/usr/bin/env python3
 """Latency of one RGB-D frame through orbb_rgbd_stage_submit + wait (max_batch = 1, the reference's per-wake-up
-use), 848x480 gray + depth from pinned memory, median over 200 frames.  usage (GPU box): python tools/stage_latency_probe.py"""
-import importlib, os, sys, time
+use), 848x480 gray + depth from pinned memory, median over 200 frames: through the Python wrapper, and from a C++ host
+(tools/stage_latency.cpp, compiled here with g++) the way the reference's pipeline thread would call the C ABI.  Consecutive
+frames are the same texture shifted by one pixel, so the windowed matcher finds its pairs.
+usage (GPU box): python tools/stage_latency_probe.py"""
+import importlib, os, subprocess, sys, tempfile, time
 import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 orbb = importlib.import_module("jetracer-orbslam2_b200.orbb")
 synth = importlib.import_module("jetracer-orbslam2_b200.synth")
 for (w, h, nf) in ((848, 480, 1200), (640, 480, 1000)):
-    gray = torch.from_numpy(np.stack([synth.textured_frame(w, h, 50 + i) for i in range(4)])).pin_memory()
+    base = synth.textured_frame(w, h, 50)
+    gray = torch.from_numpy(np.stack([np.roll(base, i if i < 3 else 1, axis=1) for i in range(4)])).pin_memory()
     yy, xx = np.mgrid[0:h, 0:w].astype(np.float32)
     depth = np.clip(1500 + 900 * np.sin(xx / 97.0) * np.cos(yy / 61.0), 1, 65535).astype(np.uint16)
     pd = torch.from_numpy(np.stack([depth] * 4).view(np.int16)).pin_memory()
@@ -31,3 +35,14 @@ for (w, h, nf) in ((848, 480, 1200), (640, 480, 1000)):
           f"(host issue inside submit {1e6 * float(np.median(tsub)):.1f} us), "
           f"valid {int(r['valid_keypoints_num'][0])}, matched {int(r['matched_keypoints_num'][0])}", flush=True)
     stage.close()
+    # the same frames from a C++ host
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "tools", "_build", "stage_latency")
+    lib = os.path.join(root, "jetracer-orbslam2_b200")
+    os.makedirs(os.path.dirname(exe), exist_ok=True)
+    subprocess.run(["g++", "-O2", "-std=c++17", "-I" + os.path.join(root, "include"), "-I/usr/local/cuda/include",
+                    os.path.join(root, "tools", "stage_latency.cpp"), "-o", exe, "-L" + lib, "-lorbb200",
+                    "-L/usr/local/cuda/lib64", "-lcudart", "-Wl,-rpath," + lib], check=True)
+    with tempfile.NamedTemporaryFile(suffix=".bin") as f:
+        f.write(gray.numpy().tobytes()); f.write(pd.numpy().tobytes()); f.flush()
+        subprocess.run([exe, f.name, str(w), str(h), str(nf)], check=True)
