@@ -202,7 +202,7 @@ k_match_windowed(const uint4 *__restrict__ query, const uint8_t *__restrict__ q_
     for (int c0 = 0; c0 < nt; c0 += WIN_CHUNK) {
         const int cn = min(nt - c0, WIN_CHUNK);
         if (c0) __syncthreads();
-#pragma unroll 4
+#pragma unroll 8
         for (int i = threadIdx.x; i < cn; i += WIN_THREADS) {
             const uint8_t *p = t_xy + (size_t)(c0 + i) * t_stride;
             s_txy[i] = make_float2(*reinterpret_cast<const float *>(p), *reinterpret_cast<const float *>(p + 4));

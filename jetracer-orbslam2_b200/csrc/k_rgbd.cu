@@ -144,6 +144,22 @@ __device__ __forceinline__ int block_rank(bool keep, int *s_warp, int *chunk_tot
     return before + __popc(m & ((1u << lane) - 1u));
 }
 
+// deproject_pixel_to_point_double (cuda-align.cu:85-110): float32 normalisation, float64 afterwards
+__device__ __forceinline__ void lift_point(const orbb_intrinsics &in, float kx, float ky, int depth, double *p) {
+    double x = (double)__fdiv_rn(__fsub_rn(kx, in.ppx), in.fx);
+    double y = (double)__fdiv_rn(__fsub_rn(ky, in.ppy), in.fy);
+    if (in.model == ORBB_DISTORTION_INVERSE_BROWN_CONRADY) {
+        const double c0 = in.coeffs[0], c1 = in.coeffs[1], c2 = in.coeffs[2], c3 = in.coeffs[3], c4 = in.coeffs[4];
+        const double r2 = dadd(dmul(x, x), dmul(y, y));
+        const double fr = dadd(dadd(dadd(1.0, dmul(c0, r2)), dmul(dmul(c1, r2), r2)), dmul(dmul(dmul(c4, r2), r2), r2));
+        const double ux = dadd(dadd(dmul(x, fr), dmul(dmul(dmul(2.0, c2), x), y)), dmul(c3, dadd(r2, dmul(dmul(2.0, x), x))));
+        const double uy = dadd(dadd(dmul(y, fr), dmul(dmul(dmul(2.0, c3), x), y)), dmul(c2, dadd(r2, dmul(dmul(2.0, y), y))));
+        x = ux; y = uy;
+    }
+    const double dd = (double)(float)depth;
+    p[0] = dmul(dd, x); p[1] = dmul(dd, y); p[2] = dd;
+}
+
 // ---- keypoints -> 3-D points.  CTA = one frame; 1024 threads, so ~1000 keypoints are one or two chunks (each chunk is
 // a chain of two dependent global loads and two barriers: a lone frame took 15.6 us with 256 threads, five chunks)
 #define KP_THREADS 1024
@@ -186,24 +202,66 @@ k_kp_to_point(const uint32_t *__restrict__ aligned, const orbb_intrinsics in, co
                 kp_out[o] = k[u];
                 desc_out[2 * o] = desc_in[2 * (f * max_kp + i)];
                 desc_out[2 * o + 1] = desc_in[2 * (f * max_kp + i) + 1];
-                // deproject_pixel_to_point_double (cuda-align.cu:85-110): float32 normalisation, float64 afterwards
-                double x = (double)__fdiv_rn(__fsub_rn(k[u].x, in.ppx), in.fx);
-                double y = (double)__fdiv_rn(__fsub_rn(k[u].y, in.ppy), in.fy);
-                if (in.model == ORBB_DISTORTION_INVERSE_BROWN_CONRADY) {
-                    const double c0 = in.coeffs[0], c1 = in.coeffs[1], c2 = in.coeffs[2], c3 = in.coeffs[3], c4 = in.coeffs[4];
-                    const double r2 = dadd(dmul(x, x), dmul(y, y));
-                    const double fr = dadd(dadd(dadd(1.0, dmul(c0, r2)), dmul(dmul(c1, r2), r2)), dmul(dmul(dmul(c4, r2), r2), r2));
-                    const double ux = dadd(dadd(dmul(x, fr), dmul(dmul(dmul(2.0, c2), x), y)), dmul(c3, dadd(r2, dmul(dmul(2.0, x), x))));
-                    const double uy = dadd(dadd(dmul(y, fr), dmul(dmul(dmul(2.0, c3), x), y)), dmul(c2, dadd(r2, dmul(dmul(2.0, y), y))));
-                    x = ux; y = uy;
-                }
-                const double dd = (double)(float)depth[u];
-                points[3 * o] = dmul(dd, x); points[3 * o + 1] = dmul(dd, y); points[3 * o + 2] = dd;
+                lift_point(in, k[u].x, k[u].y, depth[u], points + 3 * o);
             }
             base += total;
         }
     }
     if (threadIdx.x == 0) valid_counts[f] = base;
+}
+
+// ---- the same for SMALL batches (a lone frame): CTA = one chunk of 128 keypoints of one frame.  A chunk's output offset is
+// the number of valid keypoints before it, which the CTA counts itself -- the gate of a keypoint is two loads (position and
+// response, then the aligned depth), all of them in flight at once -- so ten CTAs on ten SMs each run ONE short chain
+// instead of one CTA walking two 1024-keypoint rounds with their ranking barriers (12 us -> see profiles/).
+#define KPC_THREADS 128
+__global__ void __launch_bounds__(KPC_THREADS)
+k_kp_to_point_chunks(const uint32_t *__restrict__ aligned, const orbb_intrinsics in, const orbb_keypoint *__restrict__ kp_in,
+                     const uint4 *__restrict__ desc_in, const int *__restrict__ counts_in, int max_kp,
+                     orbb_keypoint *__restrict__ kp_out, uint4 *__restrict__ desc_out, double *__restrict__ points,
+                     int *__restrict__ valid_counts) {
+    __shared__ int s_warp[KPC_THREADS / 32], s_before[KPC_THREADS / 32];
+    const size_t f = blockIdx.y;
+    const int n = min(counts_in[f], max_kp);
+    const int c0 = blockIdx.x * KPC_THREADS;
+    if (c0 >= n && !(n == 0 && blockIdx.x == 0)) return;  // block-uniform
+    const uint32_t *dimg = aligned + f * in.width * in.height;
+    const orbb_keypoint *kin = kp_in + f * max_kp;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    auto gate = [&](float x, float y, float response, bool in_range) -> int {  // the aligned depth if the keypoint is kept, else 0
+        const int xi = (int)((double)x + 0.5), yi = (int)((double)y + 0.5);
+        int d = 0;
+        if (in_range && xi >= 0 && yi >= 0 && xi < in.width && yi < in.height) d = (int)dimg[(size_t)yi * in.width + xi];
+        return (d > 1 && response > 1.0f) ? d : 0;
+    };
+    // own keypoint: the whole record and its descriptor travel with the gate's loads
+    const int i = c0 + threadIdx.x;
+    const bool mine = i < n;
+    const orbb_keypoint k = kin[mine ? i : 0];
+    const uint4 d0 = desc_in[2 * (f * max_kp + (mine ? i : 0))], d1 = desc_in[2 * (f * max_kp + (mine ? i : 0)) + 1];
+    // valid keypoints of the chunks before this one
+    int before = 0;
+#pragma unroll 4
+    for (int j = threadIdx.x; j < c0; j += KPC_THREADS) before += gate(kin[j].x, kin[j].y, kin[j].response, true) != 0;
+    const int depth = gate(k.x, k.y, k.response, mine);
+    const unsigned m = __ballot_sync(0xffffffffu, depth != 0);
+    before = __reduce_add_sync(0xffffffffu, before);
+    if (lane == 0) { s_warp[warp] = __popc(m); s_before[warp] = before; }
+    __syncthreads();
+    int base = 0, own_before = 0, own_total = 0;
+#pragma unroll
+    for (int w2 = 0; w2 < KPC_THREADS / 32; ++w2) {
+        base += s_before[w2];
+        own_before += w2 < warp ? s_warp[w2] : 0;
+        own_total += s_warp[w2];
+    }
+    if (depth != 0) {
+        const size_t o = f * max_kp + base + own_before + __popc(m & ((1u << lane) - 1u));
+        kp_out[o] = k;
+        desc_out[2 * o] = d0; desc_out[2 * o + 1] = d1;
+        lift_point(in, k.x, k.y, depth, points + 3 * o);
+    }
+    if (threadIdx.x == 0 && c0 + KPC_THREADS >= n) valid_counts[f] = base + own_total;  // the frame's last chunk
 }
 
 // ---- reprojection of the previous frame's points.  thread = one point.
@@ -257,6 +315,60 @@ k_compact_pairs(const int *__restrict__ idx, const int *__restrict__ q_counts, i
     if (threadIdx.x == 0 && n_matched) n_matched[f] = base;
 }
 
+// ---- the same for SMALL batches: CTA = one chunk of 128 queries of one frame pair; the chunk's output offset (matches
+// before it) is one int load per earlier query, counted by the CTA itself (see k_kp_to_point_chunks).
+__global__ void __launch_bounds__(KPC_THREADS)
+k_compact_pairs_chunks(const int *__restrict__ idx, const int *__restrict__ q_counts, int max_kp,
+                       const double *__restrict__ q_points, const double *__restrict__ t_points,
+                       const uint8_t *__restrict__ t_xy, int t_stride, double *__restrict__ prev_out,
+                       double *__restrict__ curr_out, uint16_t *__restrict__ xy_out, int *__restrict__ n_matched) {
+    __shared__ int s_warp[KPC_THREADS / 32], s_before[KPC_THREADS / 32];
+    const size_t f = blockIdx.y;
+    const int n = min(q_counts[f], max_kp);
+    const int c0 = blockIdx.x * KPC_THREADS;
+    if (c0 >= n && !(n == 0 && blockIdx.x == 0)) return;  // block-uniform
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int i = c0 + threadIdx.x;
+    const int t = i < n ? idx[f * max_kp + i] : -1;
+    int before = 0;
+#pragma unroll 4
+    for (int j = threadIdx.x; j < c0; j += KPC_THREADS) before += idx[f * max_kp + j] >= 0;
+    // the pair's records do not depend on the rank: fetch them next to the counting loads
+    double qp[3] = {0, 0, 0}, tp[3] = {0, 0, 0};
+    float tx = 0.f, ty = 0.f;
+    if (t >= 0) {
+        const size_t q = f * max_kp + i, tt = f * max_kp + t;
+        if (prev_out && q_points) { qp[0] = q_points[3 * q]; qp[1] = q_points[3 * q + 1]; qp[2] = q_points[3 * q + 2]; }
+        if (curr_out && t_points) { tp[0] = t_points[3 * tt]; tp[1] = t_points[3 * tt + 1]; tp[2] = t_points[3 * tt + 2]; }
+        if (xy_out) {
+            const float *p = reinterpret_cast<const float *>(t_xy + tt * t_stride);
+            tx = p[0]; ty = p[1];
+        }
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, t >= 0);
+    before = __reduce_add_sync(0xffffffffu, before);
+    if (lane == 0) { s_warp[warp] = __popc(m); s_before[warp] = before; }
+    __syncthreads();
+    int base = 0, own_before = 0, own_total = 0;
+#pragma unroll
+    for (int w2 = 0; w2 < KPC_THREADS / 32; ++w2) {
+        base += s_before[w2];
+        own_before += w2 < warp ? s_warp[w2] : 0;
+        own_total += s_warp[w2];
+    }
+    if (t >= 0) {
+        const int r = base + own_before + __popc(m & ((1u << lane) - 1u));
+        const size_t o = f * max_kp + r;
+        if (prev_out && q_points) { prev_out[3 * o] = qp[0]; prev_out[3 * o + 1] = qp[1]; prev_out[3 * o + 2] = qp[2]; }
+        if (curr_out && t_points) { curr_out[3 * o] = tp[0]; curr_out[3 * o + 1] = tp[1]; curr_out[3 * o + 2] = tp[2]; }
+        if (xy_out) {
+            xy_out[(2 * f) * max_kp + r] = (uint16_t)tx;
+            xy_out[(2 * f + 1) * max_kp + r] = (uint16_t)ty;
+        }
+    }
+    if (threadIdx.x == 0 && c0 + KPC_THREADS >= n && n_matched) n_matched[f] = base + own_total;
+}
+
 // ---- RGB8 -> gray (reference cuda_RGB_to_Grayscale.cu:10-24).  thread = 4 pixels: three aligned 32-bit loads, one
 // 32-bit store (the reference: 3 byte loads + 1 byte store per thread).  float64 like the reference's expression.
 __global__ void __launch_bounds__(256) k_rgb_to_gray(const uint8_t *__restrict__ rgb, size_t rgb_pitch, size_t rgb_stride,
@@ -307,6 +419,12 @@ cudaError_t launch_align(const uint16_t *d_depth, int n_frames, float depth_scal
 cudaError_t launch_kp_to_point(const uint32_t *d_aligned, const orbb_intrinsics &in, int n_frames, const orbb_keypoint *kp_in,
                                const uint8_t *desc_in, const int *counts_in, int max_kp, orbb_keypoint *kp_out,
                                uint8_t *desc_out, double *points, int *valid, cudaStream_t st) {
+    if (n_frames <= 4) {  // small batches: one CTA per 128-keypoint chunk
+        dim3 grid((max_kp + KPC_THREADS - 1) / KPC_THREADS, n_frames);
+        k_kp_to_point_chunks<<<grid, KPC_THREADS, 0, st>>>(d_aligned, in, kp_in, reinterpret_cast<const uint4 *>(desc_in), counts_in,
+                                                           max_kp, kp_out, reinterpret_cast<uint4 *>(desc_out), points, valid);
+        return cudaGetLastError();
+    }
     k_kp_to_point<<<n_frames, KP_THREADS, 0, st>>>(d_aligned, in, kp_in, reinterpret_cast<const uint4 *>(desc_in), counts_in,
                                                    max_kp, kp_out, reinterpret_cast<uint4 *>(desc_out), points, valid);
     return cudaGetLastError();
@@ -322,6 +440,13 @@ cudaError_t launch_reproject(const double *points, const int *counts, int n_fram
 cudaError_t launch_compact_pairs(const int *idx, const int *q_counts, int n_frames, int max_kp, const double *q_points,
                                  const double *t_points, const void *t_xy, int t_stride, double *prev_out,
                                  double *curr_out, uint16_t *xy_out, int *n_matched, cudaStream_t st) {
+    if (n_frames <= 4) {  // small batches: one CTA per 128-query chunk
+        dim3 grid((max_kp + KPC_THREADS - 1) / KPC_THREADS, n_frames);
+        k_compact_pairs_chunks<<<grid, KPC_THREADS, 0, st>>>(idx, q_counts, max_kp, q_points, t_points,
+                                                             static_cast<const uint8_t *>(t_xy), t_stride, prev_out, curr_out,
+                                                             xy_out, n_matched);
+        return cudaGetLastError();
+    }
     k_compact_pairs<<<n_frames, KP_THREADS, 0, st>>>(idx, q_counts, max_kp, q_points, t_points,
                                                      static_cast<const uint8_t *>(t_xy), t_stride, prev_out, curr_out, xy_out,
                                                      n_matched);

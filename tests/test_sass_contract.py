@@ -73,5 +73,12 @@ def test_kernels_carry_their_instructions(sass):
     assert _count(blur, "IDP.4A") >= 8
     octree = _kernel(kernels, "k_octreeILi1ELi4E")
     assert _count(octree, "REDUX") >= 32 and _count(octree, "BAR") >= 1
+    assert _count(octree, "LDS") >= 20 and _count(octree, "LDL") == 0 and _count(octree, "STL") == 0  # pyramid in shared memory, 32 registers, no spills
+    cta = _kernel(kernels, "k_fast_cell_cta")  # small grids: four warps share a cell (barriers between the phases)
+    assert _count(cta, "VABSDIFF4") >= 4 and _count(cta, "VIMNMX3") >= 40 and _count(cta, "BAR") >= 4
+    assert _count(cta, "ACQBULK") == 1 and _count(cta, "LDL") == 0 and _count(cta, "STL") == 0
+    # the cell / level tables are constants and may be read before the wait; the window rows (128-bit loads) may not
+    first_ld = min(i for i, o in enumerate(cta) if o.startswith("LDG") and ".128" in o)
+    assert cta.index("ACQBULK") < first_ld
     tma = _kernel(kernels, "k_fast_cellsILb0ELb1E")
     assert _count(tma, "UTMALDG") == 1  # the opt-in TMA staging variant
