@@ -293,6 +293,16 @@ extern "C" int orbb_rgbd_stage_submit(orbb_rgbd_stage *s, const uint8_t *h_gray,
     SPROF(s, 0, s->s_in);
     SCK(s, cudaMemcpyAsync(s->d_gray[p], h_gray, s->gray_bytes * n, cudaMemcpyHostToDevice, s->s_in));
     SCK(s, cudaEventRecord(s->ev_gray[p], s->s_in));  // the extraction needs nothing else
+    // small batch: the extraction (a replay of the extractor's graph, the start of the critical path) is enqueued before
+    // the host spends time on the depth copy and the pose upload
+    orbb_rgbd_stage::FrameGraph *g_small =
+        (s->use_graph && n_frames <= s->graph_max_frames) ? small_batch_graph(s, p, n_frames, h_T != nullptr) : nullptr;
+    if (g_small) {
+        SCK(s, cudaStreamWaitEvent(s->s_main, s->ev_gray[p], 0));
+        SRC(orbb_extract_batch_device(s->h, s->d_gray[p], (size_t)s->cfg.image_intrin.width, s->gray_bytes, n_frames,
+                                      s->d_kp_raw, s->d_desc_raw, s->d_counts_raw, s->max_kp, s->s_main));
+        SPROF(s, 3, s->s_main);
+    }
     SCK(s, cudaMemcpyAsync(s->d_depth[p], h_depth, s->depth_px * n * sizeof(uint16_t), cudaMemcpyHostToDevice, s->s_in));
     if (h_T) {
         std::memcpy(H.T, h_T, sizeof(double) * 16 * n);
@@ -304,12 +314,8 @@ extern "C" int orbb_rgbd_stage_submit(orbb_rgbd_stage *s, const uint8_t *h_gray,
     // gray frame is on the device and replays the extractor's graph, the alignment runs next to it once the depth frame
     // has arrived, and everything after the two -- carry, depth gate, reprojection, match, compaction, D2H -- is ONE graph
     // launch of the stage's own.  The host issues ~15 calls instead of ~40 and the GPU starts ~25 us earlier.
-    if (s->use_graph && n_frames <= s->graph_max_frames) {
-        if (orbb_rgbd_stage::FrameGraph *g = small_batch_graph(s, p, n_frames, h_T != nullptr)) {
-            SCK(s, cudaStreamWaitEvent(s->s_main, s->ev_gray[p], 0));
-            SRC(orbb_extract_batch_device(s->h, s->d_gray[p], (size_t)s->cfg.image_intrin.width, s->gray_bytes, n_frames,
-                                          s->d_kp_raw, s->d_desc_raw, s->d_counts_raw, s->max_kp, s->s_main));
-            SPROF(s, 3, s->s_main);
+    {
+        if (orbb_rgbd_stage::FrameGraph *g = g_small) {
             // s_align: once the previous batch has let go of the result block and the aligned-depth buffer, its last frame
             // becomes row 0 (under this batch's extraction), then the alignment as soon as the depth frames are there
             if (s->gate_recorded) SCK(s, cudaStreamWaitEvent(s->s_align, s->ev_gate, 0));

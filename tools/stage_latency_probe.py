@@ -45,4 +45,4 @@ for (w, h, nf) in ((848, 480, 1200), (640, 480, 1000)):
                     "-L/usr/local/cuda/lib64", "-lcudart", "-Wl,-rpath," + lib], check=True)
     with tempfile.NamedTemporaryFile(suffix=".bin") as f:
         f.write(gray.numpy().tobytes()); f.write(pd.numpy().tobytes()); f.flush()
-        subprocess.run([exe, f.name, str(w), str(h), str(nf)], check=True)
+        subprocess.run([exe, f.name, str(w), str(h), str(nf), "1000"], check=True)
