@@ -47,14 +47,15 @@ CFG5_FRAMES = 1024        # BASELINE config 5: one 1024-frame batch sharded acro
 LEVEL_PIXELS = 950_532    # sum_l w_l*h_l for 640x480, 8 levels, 1.2
 BYTES_PER_FRAME = W * H + 2 * LEVEL_PIXELS + 60 * NFEAT  # 2,268,264 B
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE k_fast_cells launch, per frame, from the committed
-# ncu --set full capture profiles/r02b_all_kernels_full.txt (146.8 MB + 14.47 MB for a 128-frame launch; the writes
+# ncu --set full capture profiles/r02c_all_kernels_full.txt (146.8 MB + 13.51 MB for a 128-frame launch; the writes
 # include the quadtree cell tables the kernel fills through L2 atomics)
-FAST_DRAM_TRAFFIC_PER_FRAME = (146.8e6 + 14.47e6) / 128
+FAST_DRAM_TRAFFIC_PER_FRAME = (146.8e6 + 13.51e6) / 128
 # thread instructions executed per frame by the six extraction kernels (thread_inst_executed of the same capture:
-# level0 0.289 G + resize x7 2.337 G + FAST 5.881 G + quadtree 1.162 G + blur 2.473 G + angle/rBRIEF 2.425 G per 128
-# frames) -- the path is issue bound, so the step is also reported against the SM issue roofline
-THREAD_INST_PER_FRAME = (0.2891e9 + 2.3371e9 + 5.881e9 + 1.162e9 + 2.473e9 + 2.425e9) / 128
-PROFILE_SOURCE = "profiles/r02b_all_kernels_full.txt"
+# level0 0.289 G + resize x7 2.337 G + FAST 5.881 G + quadtree 0.363 G + blur 2.473 G + angle/rBRIEF 2.425 G per 128
+# frames; the quadtree kernel executed 1.162 G before the count-pyramid path) -- the path is issue bound, so the step is
+# also reported against the SM issue roofline
+THREAD_INST_PER_FRAME = (0.2891e9 + 2.3371e9 + 5.881e9 + 0.3631e9 + 2.473e9 + 2.425e9) / 128
+PROFILE_SOURCE = "profiles/r02c_all_kernels_full.txt"
 
 
 def measured_peaks():
