@@ -45,6 +45,11 @@ CONFIGS = [  # (w, h, nfeatures, scale, nlevels, generator, seed)
     (752, 480, 1000, 1.3, 6, "textured_frame", 77),     # EuRoC-sized, non-default scale (cells up to 37 px wide)
     (848, 480, 405, 1.2, 1, "textured_frame", 2100),    # the reference's live shape: 1 level (defines.h:2), 405 cells
     (640, 480, 1000, 1.2, 1, "textured_frame", 2101),   # single level carrying the whole quota
+    # quotas the 4096-cell table cap cannot serve with 4 cells per keypoint: the quadtree kernel's pyramid path decides by
+    # itself whether the selection stays inside the table (table cells become final nodes here) or takes the general path
+    (848, 480, 1200, 1.2, 1, "textured_frame", 2102),
+    (848, 480, 1200, 1.2, 2, "textured_frame", 2103),
+    (1280, 720, 2000, 1.2, 2, "textured_frame", 2104),
 ]
 
 
