@@ -10,6 +10,8 @@
 // The train set may be split across blockIdx.y (split-T) so small query sets still fill 148 SMs;
 // partial (d1,i1,d2,i2) are merged in ascending split order, which preserves the tie rule.
 // Bound: POPC issue rate (16/clk/SM), see DESIGN.md.
+#include <cstdlib>
+
 #include "orbb_internal.cuh"
 
 namespace orbb {
@@ -121,6 +123,157 @@ k_match(const uint4 *__restrict__ query, const uint4 *__restrict__ train, const 
         const int q = qbase + j * MATCH_THREADS + threadIdx.x;
         if (q < q1) {
             const unsigned k1 = best[j].k1, k2 = best[j].k2;
+            partial[(size_t)blockIdx.y * partial_stride + q] =
+                make_int4(k1 == 0xffffffffu ? 257 : (int)(k1 >> 22), k1 == 0xffffffffu ? -1 : ts + (int)(k1 & 0x3fffffu),
+                          k2 == 0xffffffffu ? 257 : (int)(k2 >> 22), k2 == 0xffffffffu ? -1 : ts + (int)(k2 & 0x3fffffu));
+        }
+    }
+}
+
+// ---- the same search on the tensor cores.  Brute-force Hamming k-NN IS a dense contraction: with every descriptor bit
+// written as +1 / -1, the dot product of two 256-bit descriptors is 256 - 2 * Hamming, so a 16 x 8 block of distances is
+// eight int8 MMAs (m16n8k32) -- 128 pairs per eight instructions instead of 128 x (8 XOR + 4-5 POPC + adds).  The
+// legacy warp-level form (mma.sync -> IMMA.16832.S8.S8) issues once per two cycles per SM on B200 (tools/imma_probe.cu:
+// 2048 int8 MAC/clk/SM), i.e. 8 pairs per clock per SM = 2.33 Tpairs/s per GPU, 2.5 x the POPC roof of k_match.
+//   * Warp = 32 queries (two 16-row A tiles), expanded ONCE into 64 registers; CTA = 8 warps = 256 queries (the query
+//     block of k_match, so grids, split-T and the merge kernel are shared).
+//   * Train descriptors are staged 64 at a time: 2 KB of packed bits are expanded into shared memory as s8 (320-byte row
+//     pitch: the 128-bit fragment loads of a quarter warp then cover all 32 banks).
+//   * A dot product does not care about the order of its terms, so the bit -> k mapping is chosen for the loads: lane
+//     (g, tig) owns halfwords tig, 4 + tig, 8 + tig, 12 + tig of a descriptor; one 128-bit shared load is the B fragment
+//     of two k-steps.
+//   * Epilogue per accumulator: key = acc * -(2^21) + ((256 << 21) | train index) -- one IMAD gives the packed
+//     (distance << 22 | index) key of k_match (256 - dot is even, so bit 21 stays free for the index) -- and one min
+//     (three min / max for K = 2).  The four lanes of a quad hold different columns of the same rows and merge at the end.
+#define MI_THREADS 256
+#define MI_TILE 64
+#define MI_PITCH 320
+
+__device__ __forceinline__ unsigned expand4(unsigned nib) {  // four descriptor bits -> four s8: 1 -> +1, 0 -> -1
+    const unsigned w = (nib * 0x00204081u) & 0x01010101u;   // bit i -> bit 0 of byte i (no two partial products meet)
+    return w | ((w ^ 0x01010101u) * 0xFFu);
+}
+
+__device__ __forceinline__ void imma16832(int (&d)[4], const unsigned (&a)[4], unsigned b0, unsigned b1, bool first) {
+    if (first)
+        asm volatile("mma.sync.aligned.m16n8k32.row.col.s32.s8.s8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%10,%10,%10,%10};"
+                     : "=r"(d[0]), "=r"(d[1]), "=r"(d[2]), "=r"(d[3])
+                     : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1), "r"(0));
+    else
+        asm volatile("mma.sync.aligned.m16n8k32.row.col.s32.s8.s8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                     : "+r"(d[0]), "+r"(d[1]), "+r"(d[2]), "+r"(d[3])
+                     : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+template <int K>
+__global__ void __launch_bounds__(MI_THREADS, 2)
+k_match_imma(const uint4 *__restrict__ query, const uint4 *__restrict__ train, const int *__restrict__ q_off,
+             const int *__restrict__ t_off, int nq_one, int nt_one, int n_split, int4 *__restrict__ partial,
+             int partial_stride, const int *__restrict__ q_counts, int max_kp) {
+    __shared__ __align__(16) uint8_t s_t[MI_TILE * MI_PITCH];
+    const int seg = blockIdx.z;
+    const int q0 = q_counts ? seg * max_kp : (q_off ? q_off[seg] : 0);
+    const int q1 = q_counts ? q0 + min(q_counts[seg], max_kp) : (q_off ? q_off[seg + 1] : nq_one);
+    const int t0 = t_off ? t_off[seg] : 0, t1 = t_off ? t_off[seg + 1] : nt_one;
+    const int qbase = q0 + blockIdx.x * MI_THREADS;
+    if (qbase >= q1) return;
+    const int nt = t1 - t0;
+    const int per = (nt + n_split - 1) / n_split;
+    const int ts = min(nt, (int)blockIdx.y * per), te = min(nt, ts + per);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, tig = lane & 3;
+
+    // A fragments: rows qw + {g, g + 8, 16 + g, 24 + g}, eight k-steps each
+    const int qw = qbase + warp * 32;
+    unsigned a[2][8][4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        const int q = min(qw + (r >> 1) * 16 + (r & 1) * 8 + g, q1 - 1);
+        const uint4 d0 = query[(size_t)q * 2], d1 = query[(size_t)q * 2 + 1];
+        const unsigned wds[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            // halfword j * 4 + tig of the descriptor = half (tig & 1) of word j * 2 + (tig >> 1)
+            const unsigned wsel = (tig & 2) ? wds[2 * j + 1] : wds[2 * j];
+            const unsigned hw = (tig & 1) ? wsel >> 16 : wsel & 0xffffu;
+#pragma unroll
+            for (int sb = 0; sb < 2; ++sb) {
+                const unsigned byte = (hw >> (8 * sb)) & 0xffu;
+                a[r >> 1][2 * j + sb][(r & 1)] = expand4(byte & 15u);      // a0 (row g) / a1 (row g + 8)
+                a[r >> 1][2 * j + sb][2 + (r & 1)] = expand4(byte >> 4);   // a2 / a3
+            }
+        }
+    }
+    unsigned best[4][K];
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int k = 0; k < K; ++k) best[r][k] = 0xffffffffu;
+    const unsigned neg21 = 0xFFE00000u + ((unsigned)n_split >> 30);  // -(2^21), opaque to ptxas: keeps the key an IMAD
+
+    for (int tb = ts; tb < te; tb += MI_TILE) {
+        const int cnt = min(MI_TILE, te - tb);
+        __syncthreads();
+        {   // stage + expand: thread = (train row n, quarter c): 8 packed bytes -> units (j = c, tig = 0..3) = 64 bytes
+            const int n = threadIdx.x >> 2, c = threadIdx.x & 3;
+            uint2 pk = make_uint2(0u, 0u);
+            if (n < cnt) pk = *reinterpret_cast<const uint2 *>(reinterpret_cast<const uint8_t *>(train) + (size_t)(t0 + tb + n) * 32 + c * 8);
+            uint4 *dst = reinterpret_cast<uint4 *>(s_t + n * MI_PITCH + c * 64);
+#pragma unroll
+            for (int t4 = 0; t4 < 4; ++t4) {
+                const unsigned hw = t4 < 2 ? (pk.x >> (16 * t4)) & 0xffffu : (pk.y >> (16 * (t4 - 2))) & 0xffffu;
+                dst[t4] = make_uint4(expand4(hw & 15u), expand4((hw >> 4) & 15u), expand4((hw >> 8) & 15u), expand4(hw >> 12));
+            }
+        }
+        __syncthreads();
+        const unsigned colbase0 = (256u << 21) | (unsigned)(tb - ts + tig * 2);
+#pragma unroll 2
+        for (int cg = 0; cg < MI_TILE / 8; ++cg) {
+            if (cg * 8 >= cnt) break;  // block-uniform
+            int acc[2][4];
+            const uint8_t *bp = s_t + (cg * 8 + g) * MI_PITCH + tig * 16;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const uint4 b = *reinterpret_cast<const uint4 *>(bp + j * 64);
+                imma16832(acc[0], a[0][2 * j], b.x, b.y, j == 0);
+                imma16832(acc[1], a[1][2 * j], b.x, b.y, j == 0);
+                imma16832(acc[0], a[0][2 * j + 1], b.z, b.w, false);
+                imma16832(acc[1], a[1][2 * j + 1], b.z, b.w, false);
+            }
+            const unsigned cb = colbase0 + cg * 8;
+            const bool full = cg * 8 + 8 <= cnt;  // block-uniform
+#pragma unroll
+            for (int m = 0; m < 2; ++m)
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const int r = m * 2 + (e >> 1);  // c0,c1: row g; c2,c3: row g + 8
+                    unsigned key = (unsigned)acc[m][e] * neg21 + (cb + (e & 1));
+                    if (!full && cg * 8 + tig * 2 + (e & 1) >= cnt) key = 0xffffffffu;
+                    if (K == 1) best[r][0] = min(best[r][0], key);
+                    else {
+                        const unsigned hi = max(key, best[r][0]);
+                        best[r][0] = min(key, best[r][0]);
+                        best[r][K - 1] = min(best[r][K - 1], hi);
+                    }
+                }
+        }
+    }
+    // the four lanes of a quad saw different columns of the same rows
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+#pragma unroll
+        for (int o = 1; o <= 2; o <<= 1) {
+            const unsigned o1 = __shfl_xor_sync(0xffffffffu, best[r][0], o);
+            if (K == 1) best[r][0] = min(best[r][0], o1);
+            else {
+                const unsigned o2 = __shfl_xor_sync(0xffffffffu, best[r][K - 1], o);
+                const unsigned hi = max(o1, best[r][0]);
+                best[r][0] = min(o1, best[r][0]);
+                best[r][K - 1] = min(min(best[r][K - 1], o2), hi);
+            }
+        }
+        const int q = qw + (r >> 1) * 16 + (r & 1) * 8 + g;
+        if (tig == 0 && q < q1) {
+            const unsigned k1 = best[r][0], k2 = K == 2 ? best[r][K - 1] : 0xffffffffu;
             partial[(size_t)blockIdx.y * partial_stride + q] =
                 make_int4(k1 == 0xffffffffu ? 257 : (int)(k1 >> 22), k1 == 0xffffffffu ? -1 : ts + (int)(k1 & 0x3fffffu),
                           k2 == 0xffffffffu ? 257 : (int)(k2 >> 22), k2 == 0xffffffffu ? -1 : ts + (int)(k2 & 0x3fffffu));
@@ -256,7 +409,18 @@ cudaError_t launch_match(const uint8_t *d_q, const uint8_t *d_t, const int *d_q_
     if (nq_total <= 0) return cudaSuccess;
     const int qblocks = (max_q_per_seg + MATCH_THREADS * MATCH_QPT - 1) / (MATCH_THREADS * MATCH_QPT);
     dim3 grid(qblocks, n_split, nseg);
-    if (k == 1)
+    // default: the tensor-core form (same grid, same partial records); ORBB_MATCH_POPC=1 keeps the XOR / POPC kernel
+    static const bool use_popc = getenv("ORBB_MATCH_POPC") && atoi(getenv("ORBB_MATCH_POPC")) != 0;
+    if (!use_popc) {
+        if (k == 1)
+            k_match_imma<1><<<grid, MI_THREADS, 0, st>>>(reinterpret_cast<const uint4 *>(d_q), reinterpret_cast<const uint4 *>(d_t),
+                                                         d_q_off, d_t_off, nq_total, nt_one, n_split, d_partial, partial_stride,
+                                                         d_q_counts, max_kp);
+        else
+            k_match_imma<2><<<grid, MI_THREADS, 0, st>>>(reinterpret_cast<const uint4 *>(d_q), reinterpret_cast<const uint4 *>(d_t),
+                                                         d_q_off, d_t_off, nq_total, nt_one, n_split, d_partial, partial_stride,
+                                                         d_q_counts, max_kp);
+    } else if (k == 1)
         k_match<1><<<grid, MATCH_THREADS, 0, st>>>(reinterpret_cast<const uint4 *>(d_q), reinterpret_cast<const uint4 *>(d_t),
                                                    d_q_off, d_t_off, nq_total, nt_one, n_split, d_partial, partial_stride,
                                                    d_q_counts, max_kp);
