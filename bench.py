@@ -15,7 +15,7 @@ the data path; NCCL only gathers the per-rank keypoint counts after the timed re
   cpu_baseline : the CPU oracle (a port of upstream ORBextractor; the reference repo has no compilable CPU
                  extractor) on the box's host cores, bounded sample
   matcher      : Hamming 1-NN of one batch's descriptors against a 50k-descriptor map, Gpairs/s vs POPC roof
-                 (the POPC issue rate is measured by a register-only microbenchmark, orbb_debug_popc_rate)
+                 (the POPC and int8-MMA issue rates are measured by register-only microbenchmarks, orbb_debug_popc_rate / orbb_debug_imma_rate)
   parity       : K frames of the TIMED batch (both stream parts) compared with the CPU oracle after the timed region
   sustained    : the same device-resident call repeated for >= 2 s with NVML clock / power samples
   cfg5         : BASELINE config 5 as written -- a 1024-frame batch sharded 1024/N per rank (STRONG scaling), one map
@@ -958,6 +958,7 @@ def main():
     match_ms = m0.elapsed_time(m1) / m_iters
     gpairs = nq * MAP_SIZE / (match_ms * 1e-3) / 1e9
     popc_rate = ex.debug_popc_rate() if rank == 0 else None
+    imma_rate = ex.debug_imma_rate() if rank == 0 else None
 
     # ---- RGB-D frame stage (BASELINE cfg 2 geometry: 848x480, 1200 kp, batches of 64 frames):
     # pinned gray + depth in, align + extract + depth gate + reproject + windowed match + compaction, results D2H.
@@ -1010,6 +1011,11 @@ def main():
         # register-only microbenchmark (orbb_debug_popc_rate); 16 is the programming guide's figure.
         popc_lanes = popc_rate if popc_rate else 16.0
         popc_roof = 148 * popc_lanes * f_mhz * 1e6 / 5 / 1e9
+        # The default matcher runs on the tensor cores: descriptor bits as +1 / -1, one int8 MMA (m16n8k32) covers 16
+        # descriptor pairs of 256 bits.  Its roof is the issue rate of that instruction, measured the same way
+        # (orbb_debug_imma_rate: 0.5 per clock per SM on B200); the XOR / POPC kernel's roof is kept for comparison.
+        imma_per_clk = imma_rate if imma_rate else 0.5
+        imma_roof = 148 * imma_per_clk * 16 * f_mhz * 1e6 / 1e9
         line = {
             "metric": "ORB frames/s (640x480, 1000 kp)", "value": fps, "unit": "frames/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps,
@@ -1048,11 +1054,18 @@ def main():
             "stages_ms": dict(zip(stage_names, stage_ms)),
             "keypoints_per_frame": kp_total / (B * world),
             "matcher": {"value": gpairs * world * (match_ms / match_ms_max), "unit": "Gpairs/s", "nq_per_gpu": nq,
-                        "nt": MAP_SIZE, "k": 1, "ms": match_ms_max, "popc_per_pair": 5,
+                        "nt": MAP_SIZE, "k": 1, "ms": match_ms_max,
+                        "kernel": "k_match_imma (int8 mma.sync m16n8k32, 16 pairs per MMA)",
+                        "imma_per_clk_per_sm_measured": imma_rate,
+                        "imma_roof_gpairs_per_gpu": imma_roof,
+                        "frac_of_imma_roof": gpairs / imma_roof,
+                        "popc_per_pair": 5,
                         "popc_lanes_per_clk_per_sm_measured": popc_rate,
                         "popc_roof_gpairs_per_gpu": popc_roof,
                         "plain_8popc_roof_gpairs_per_gpu": popc_roof * 5 / 8,
-                        "frac_of_popc_roof": gpairs / popc_roof},
+                        "vs_popc_roof": gpairs / popc_roof,
+                        "popc_what": "roof of the XOR / POPC kernel (ORBB_MATCH_POPC=1: 905 Gpairs/s = 98 % of it), "
+                                     "which the tensor-core form exceeds"},
         }
         if sustained is not None:
             line["sustained"] = sustained

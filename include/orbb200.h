@@ -411,6 +411,9 @@ int orbb_preview_debug_planes(orbb_preview *p, const uint8_t *d_gray, size_t gra
 int orbb_debug_poison(orbb_handle *h, int value);
 /* measured POPC issue rate (lanes per clock per SM) of this device: the matcher's roofline denominator */
 int orbb_debug_popc_rate(orbb_handle *h, double *popc_per_clk_per_sm);
+/* int8 tensor-core MMAs (m16n8k32) per clock per SM of this GPU, from a register-only microbenchmark: the roof of the
+ * tensor-core matcher (16 descriptor pairs per MMA).  Synchronises. */
+int orbb_debug_imma_rate(orbb_handle *h, double *imma_per_clk_per_sm);
 /* padded level, contiguous (w+38) x (h+38) */
 int orbb_debug_get_padded(orbb_handle *h, int frame, int level, uint8_t *host_out);
 /* blurred ROI, contiguous w x h */

@@ -4,12 +4,14 @@
 // per-call cudaMalloc).  Definition: SURVEY.md A.7 -- two smallest distances over all train rows,
 // ties -> lowest train index, accept iff d1 < ratio * d2 (k == 2).
 //
-// XOR + POPC only: no tensor cores (nothing here is a floating-point contraction).  Each thread
-// keeps QPT query descriptors in registers; train descriptors are staged through shared memory in
-// tiles and read with 128-bit broadcast loads, so the inner loop is 8 LOP3 + 8 POPC + adds per pair.
-// The train set may be split across blockIdx.y (split-T) so small query sets still fill 148 SMs;
-// partial (d1,i1,d2,i2) are merged in ascending split order, which preserves the tie rule.
-// Bound: POPC issue rate (16/clk/SM), see DESIGN.md.
+// Two kernels with identical results.  k_match_imma (default): the all-pairs distance matrix as an int8
+// tensor-core contraction over +1 / -1 expanded descriptor bits (dot = 256 - 2 * Hamming), bound by the
+// issue rate of IMMA.16832 (0.5 per clock per SM).  k_match (ORBB_MATCH_POPC=1): XOR + POPC, each thread
+// keeps QPT query descriptors in registers, train descriptors are staged through shared memory in tiles
+// and read with 128-bit broadcast loads, carry-save adders fold the eight XOR words before 4-5 POPC per
+// pair; bound by the POPC issue rate (16 lanes/clk/SM).  In both, the train set may be split across
+// blockIdx.y (split-T) so small query sets still fill 148 SMs; partial (d1,i1,d2,i2) are merged in
+// ascending split order, which preserves the tie rule.  See DESIGN.md section 4.
 #include <cstdlib>
 
 #include "orbb_internal.cuh"
@@ -601,6 +603,37 @@ __global__ void __launch_bounds__(1024, 1) k_popc_rate(int iters, unsigned seed,
     const long long t1 = clock64();
     if (threadIdx.x == 0) cycles[blockIdx.x] = t1 - t0;
     if ((a0 ^ a1 ^ a2 ^ a3 ^ a4 ^ a5 ^ a6 ^ a7) == 0xdeadbeefu) sink[0] = a0;  // keeps the chains alive
+}
+
+// ---- IMMA.16832.S8.S8 issue-rate microbenchmark (the roof of k_match_imma): one CTA of 1024 threads per SM (so that no SM
+// gets two), every warp runs 8 independent accumulator chains with register operands.
+// rate = 32 warps * 8 * iters / cycles = MMAs per clock per SM.
+__global__ void __launch_bounds__(1024, 1) k_imma_rate(int iters, unsigned seed, long long *__restrict__ cycles, unsigned *__restrict__ sink) {
+    unsigned a[4], b0 = 0xff01ff01u * (seed + threadIdx.x * 3), b1 = 0x01ff01ffu * (seed + threadIdx.x * 5);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) a[i] = 0x01ff01ffu * (seed + threadIdx.x + i);
+    int c[8][4];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) imma16832(c[j], a, b0, b1, true);
+    __syncthreads();
+    const long long t0 = clock64();
+#pragma unroll 1
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) imma16832(c[j], a, b0, b1, false);
+    }
+    __syncthreads();
+    const long long t1 = clock64();
+    if (threadIdx.x == 0) cycles[blockIdx.x] = t1 - t0;
+    int x = 0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) x ^= c[j][0] ^ c[j][1] ^ c[j][2] ^ c[j][3];
+    if (x == 0x5eadbeef) sink[0] = (unsigned)x;  // keeps the chains alive
+}
+
+cudaError_t launch_imma_rate(int n_ctas, int iters, long long *d_cycles, unsigned *d_sink, cudaStream_t st) {
+    k_imma_rate<<<n_ctas, 1024, 0, st>>>(iters, 0x9e3779b9u, d_cycles, d_sink);
+    return cudaGetLastError();
 }
 
 cudaError_t launch_popc_rate(int n_ctas, int iters, long long *d_cycles, unsigned *d_sink, cudaStream_t st) {

@@ -42,6 +42,7 @@ cudaError_t launch_detect_export(const LevelDev *, int, const int *, const int *
 cudaError_t launch_match(const uint8_t *, const uint8_t *, const int *, const int *, int, int, int, int, int, int4 *,
                          int, int, float, int *, int *, uint8_t *, int *, cudaStream_t, const int * = nullptr, int = 0);
 cudaError_t launch_popc_rate(int, int, long long *, unsigned *, cudaStream_t);
+cudaError_t launch_imma_rate(int, int, long long *, unsigned *, cudaStream_t);
 cudaError_t launch_align(const uint16_t *, int, float, const orbb_intrinsics &, const orbb_intrinsics &, const orbb_extrinsics &,
                          uint32_t *, cudaStream_t);
 cudaError_t launch_kp_to_point(const uint32_t *, const orbb_intrinsics &, int, const orbb_keypoint *, const uint8_t *,
@@ -1405,6 +1406,26 @@ extern "C" int orbb_debug_popc_rate(orbb_handle *h, double *popc_per_clk_per_sm)
     CK(h, cudaMemcpy(cyc.data(), d_cyc, sizeof(long long) * n, cudaMemcpyDeviceToHost));
     std::sort(cyc.begin(), cyc.end());
     *popc_per_clk_per_sm = 1024.0 * 8.0 * iters / (double)std::max<long long>(cyc[n / 2], 1);
+    h->n_launches += 2;
+    return ORBB_OK;
+}
+
+// int8 tensor-core MMAs (mma.sync m16n8k32 = IMMA.16832.S8.S8) per clock per SM, measured the same way (k_imma_rate):
+// the roof of the tensor-core matcher, 16 descriptor pairs per MMA.  Synchronises.
+extern "C" int orbb_debug_imma_rate(orbb_handle *h, double *imma_per_clk_per_sm) {
+    if (!h || !imma_per_clk_per_sm) return ORBB_ERR_INVALID;
+    CK(h, cudaSetDevice(h->device));
+    cudaDeviceProp prop;
+    CK(h, cudaGetDeviceProperties(&prop, h->device));
+    const int n = prop.multiProcessorCount, iters = 4000;
+    long long *d_cyc = reinterpret_cast<long long *>(h->d_partial);  // scratch: n x 8 bytes + 4
+    unsigned *d_sink = reinterpret_cast<unsigned *>(d_cyc + n);
+    for (int rep = 0; rep < 2; ++rep) CK(h, launch_imma_rate(n, iters, d_cyc, d_sink, 0));  // first run warms the clocks
+    CK(h, cudaDeviceSynchronize());
+    std::vector<long long> cyc((size_t)n);
+    CK(h, cudaMemcpy(cyc.data(), d_cyc, sizeof(long long) * n, cudaMemcpyDeviceToHost));
+    std::sort(cyc.begin(), cyc.end());
+    *imma_per_clk_per_sm = 32.0 * 8.0 * iters / (double)std::max<long long>(cyc[n / 2], 1);
     h->n_launches += 2;
     return ORBB_OK;
 }

@@ -1,6 +1,6 @@
-"""Static SASS checks (no GPU): the library contains sm_100a code only, no tensor-core instructions (nothing on this
-path is a dense contraction), and each kernel carries the instructions its design leans on -- the evidence
-profiles/r01m_sass_mnemonics.txt records, kept true by a test."""
+"""Static SASS checks (no GPU): the library contains sm_100a code only, tensor-core instructions only where the path has a
+dense contraction (the brute-force Hamming matcher: int8 IMMA), and each kernel carries the instructions its design
+leans on -- the evidence profiles/r01m_sass_mnemonics.txt records, kept true by a test."""
 import os
 import re
 import shutil
@@ -47,8 +47,11 @@ def test_sm100a_only_and_no_tensor_cores(sass):
     assert archs == {"sm_100a"}
     assert len(kernels) >= 25
     for name, ops in kernels.items():
-        for tc in ("HMMA", "IMMA", "DMMA", "UTCHMMA", "UTCIMMA", "UTCQMMA", "WGMMA"):
+        for tc in ("HMMA", "DMMA", "UTCHMMA", "UTCIMMA", "UTCQMMA", "WGMMA"):
             assert _count(ops, tc) == 0, (name, tc)
+        # the one dense contraction of the path -- all-pairs Hamming distances -- runs as int8 MMAs; nothing else may
+        if "k_match_imma" not in name and "k_imma_rate" not in name:
+            assert _count(ops, "IMMA") == 0, name
 
 
 def test_kernels_carry_their_instructions(sass):
@@ -58,6 +61,10 @@ def test_kernels_carry_their_instructions(sass):
     for kk in ("k_matchILi1E", "k_matchILi2E"):  # query descriptors and running bests stay in registers
         ops = _kernel(kernels, kk)
         assert _count(ops, "LDL") == 0 and _count(ops, "STL") == 0, kk
+    for kk in ("k_match_immaILi1E", "k_match_immaILi2E"):  # 32 MMAs per pair of column groups, A fragments in registers
+        ops = _kernel(kernels, kk)
+        assert _count(ops, "IMMA.16832.S8.S8") >= 32 and _count(ops, "LDS.128") >= 8, kk
+        assert _count(ops, "LDL") == 0 and _count(ops, "STL") == 0 and _count(ops, "POPC") == 0, kk
     fast = _kernel(kernels, "k_fast_cellsILb0ELb0E")
     assert _count(fast, "VABSDIFF4") >= 4 and _count(fast, "VIMNMX3") >= 40  # packed precheck, arc-score min/max network
     assert _count(fast, "ATOMG") + _count(fast, "RED") >= 1                  # cell-table atomics while emitting
