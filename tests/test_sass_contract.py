@@ -42,7 +42,7 @@ def _kernel(kernels, *needles):
     return kernels[hits[0]]
 
 
-def test_sm100a_only_and_no_tensor_cores(sass):
+def test_sm100a_only_and_tensor_cores_only_in_the_matcher(sass):
     kernels, archs = sass
     assert archs == {"sm_100a"}
     assert len(kernels) >= 25
