@@ -369,6 +369,134 @@ k_compact_pairs_chunks(const int *__restrict__ idx, const int *__restrict__ q_co
     if (threadIdx.x == 0 && c0 + KPC_THREADS >= n && n_matched) n_matched[f] = base + own_total;
 }
 
+// ---- A lone frame's depth gate + 3-D lift + windowed match in ONE launch (the RGB-D stage's tail for max_batch = 1).
+// k_kp_to_point_chunks followed by k_match_windowed were two dependent launches of ~8 and ~11 us for ~1 us of work each;
+// the match only needs to know WHICH current keypoints survive the depth gate and where they land after compaction,
+// and that costs a CTA two loads per keypoint.  So every CTA (= four previous-frame points, one per warp, as in
+// k_match_windowed) gates ALL current keypoints itself and builds the compacted position table in shared memory --
+// compacted index, position, and the raw index under which the descriptor still lives -- and CTA c < ceil(n / 128)
+// additionally writes chunk c of the compacted keypoints / descriptors / 3-D points (the work of k_kp_to_point_chunks).
+// Results are identical to the two-kernel form: same gate, same compaction order, same packed (distance, index) key.
+#define GM_THREADS 128
+#define GM_MAX_KP 2048   // 16 gate slots per thread; 20 KB of shared memory
+__global__ void __launch_bounds__(GM_THREADS)
+k_gate_match_lone(const uint32_t *__restrict__ aligned, const orbb_intrinsics in, const orbb_keypoint *__restrict__ kp_raw,
+                  const uint4 *__restrict__ desc_raw, const int *__restrict__ count_raw, int max_kp,
+                  orbb_keypoint *__restrict__ kp_out, uint4 *__restrict__ desc_out, double *__restrict__ points,
+                  int *__restrict__ valid_out, int *__restrict__ count_blk,
+                  const uint4 *__restrict__ q_desc, const float2 *__restrict__ q_pos, const int *__restrict__ q_count,
+                  float max_px, int max_hamming, int *__restrict__ out_idx, int *__restrict__ out_dist) {
+    __shared__ float2 s_txy[GM_MAX_KP];
+    __shared__ uint16_t s_raw[GM_MAX_KP];
+    __shared__ int s_cnt[GM_MAX_KP / 32 + 1];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int n = min(count_raw[0], max_kp), nq = min(q_count[0], max_kp);
+    const int nchunks = (n + GM_THREADS - 1) / GM_THREADS;
+    const int q = blockIdx.x * (GM_THREADS / 32) + warp;
+    if (blockIdx.x * (GM_THREADS / 32) >= nq && (int)blockIdx.x >= nchunks && blockIdx.x != 0) return;  // block-uniform
+    // the query's descriptor and position travel with the gate's loads
+    uint4 qa = make_uint4(0u, 0u, 0u, 0u), qb = qa;
+    float2 qp = make_float2(0.f, 0.f);
+    const bool active = q < nq;
+    if (active) { qa = q_desc[(size_t)q * 2]; qb = q_desc[(size_t)q * 2 + 1]; qp = q_pos[q]; }
+    // ---- gate of every current keypoint: item i = c * 128 + thread, all loads of all chunks in flight
+    float kx[GM_MAX_KP / GM_THREADS], ky[GM_MAX_KP / GM_THREADS], kr[GM_MAX_KP / GM_THREADS];
+    int depth[GM_MAX_KP / GM_THREADS];
+#pragma unroll
+    for (int c = 0; c < GM_MAX_KP / GM_THREADS; ++c) {
+        const int i = c * GM_THREADS + threadIdx.x;
+        kx[c] = ky[c] = kr[c] = 0.f;
+        if (c < nchunks && i < n) { kx[c] = kp_raw[i].x; ky[c] = kp_raw[i].y; kr[c] = kp_raw[i].response; }
+    }
+#pragma unroll
+    for (int c = 0; c < GM_MAX_KP / GM_THREADS; ++c) {
+        const int i = c * GM_THREADS + threadIdx.x;
+        const int xi = (int)((double)kx[c] + 0.5), yi = (int)((double)ky[c] + 0.5);
+        depth[c] = 0;
+        if (c < nchunks && i < n && xi >= 0 && yi >= 0 && xi < in.width && yi < in.height) depth[c] = (int)aligned[(size_t)yi * in.width + xi];
+    }
+    unsigned keep = 0, below = 0;  // bit c: item kept; rank of the item among the kept ones of its warp step
+    int rank[GM_MAX_KP / GM_THREADS];
+#pragma unroll
+    for (int c = 0; c < GM_MAX_KP / GM_THREADS; ++c) {
+        const bool k = c < nchunks && depth[c] > 1 && kr[c] > 1.0f;
+        const unsigned m = __ballot_sync(0xffffffffu, k);
+        rank[c] = __popc(m & ((1u << lane) - 1u));
+        if (k) keep |= 1u << c;
+        if (lane == 0 && c < nchunks) s_cnt[c * 4 + warp] = __popc(m);
+    }
+    (void)below;
+    __syncthreads();
+    if (warp == 0) {  // exclusive prefix over the (chunk, warp) counts in raw order: <= 64 entries, two per lane
+        const int e0 = 2 * lane, e1 = 2 * lane + 1, ne = nchunks * 4;
+        const int v0 = e0 < ne ? s_cnt[e0] : 0, v1 = e1 < ne ? s_cnt[e1] : 0;
+        int inc = v0 + v1;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += t;
+        }
+        const int total = __shfl_sync(0xffffffffu, inc, 31);
+        __syncwarp();
+        if (e0 < ne) s_cnt[e0] = inc - v0 - v1;
+        if (e1 < ne) s_cnt[e1] = inc - v1;
+        if (lane == 0) s_cnt[GM_MAX_KP / 32] = total;
+    }
+    __syncthreads();
+    const int nt = s_cnt[GM_MAX_KP / 32];
+#pragma unroll
+    for (int c = 0; c < GM_MAX_KP / GM_THREADS; ++c) {
+        if (!((keep >> c) & 1u)) continue;
+        const int i = c * GM_THREADS + threadIdx.x, ci = s_cnt[c * 4 + warp] + rank[c];
+        s_txy[ci] = make_float2(kx[c], ky[c]);
+        s_raw[ci] = (uint16_t)i;
+        if ((int)blockIdx.x == c) {  // this CTA writes chunk c of the compacted frame
+            kp_out[ci] = kp_raw[i];
+            desc_out[2 * ci] = desc_raw[2 * (size_t)i];
+            desc_out[2 * ci + 1] = desc_raw[2 * (size_t)i + 1];
+            lift_point(in, kx[c], ky[c], depth[c], points + 3 * (size_t)ci);
+        }
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) { valid_out[0] = nt; if (count_blk) count_blk[0] = count_raw[0]; }
+    __syncthreads();
+    if (!active) return;
+    // ---- windowed 1-NN of this warp's previous-frame point against the gated keypoints (k_match_windowed)
+    unsigned best = 0xffffffffu;
+    for (int tb = 0; tb < nt; tb += 32) {
+        const int i = tb + lane;
+        if (i < nt) {
+            const float2 pt = s_txy[i];
+            if (fabsf(__fsub_rn(qp.x, pt.x)) <= max_px && fabsf(__fsub_rn(qp.y, pt.y)) <= max_px) {
+                const size_t t = s_raw[i];
+                const uint4 a = __ldg(desc_raw + t * 2), b = __ldg(desc_raw + t * 2 + 1);
+                const int d = __popc(qa.x ^ a.x) + __popc(qa.y ^ a.y) + __popc(qa.z ^ a.z) + __popc(qa.w ^ a.w) +
+                              __popc(qb.x ^ b.x) + __popc(qb.y ^ b.y) + __popc(qb.z ^ b.z) + __popc(qb.w ^ b.w);
+                if (d < max_hamming) best = min(best, ((unsigned)d << 16) | (unsigned)i);
+            }
+        }
+    }
+    best = __reduce_min_sync(0xffffffffu, best);
+    if (lane == 0) {
+        const bool ok = best != 0xffffffffu;
+        out_idx[q] = ok ? (int)(best & 0xffffu) : -1;
+        out_dist[q] = ok ? (int)(best >> 16) : -1;
+    }
+}
+
+cudaError_t launch_gate_match_lone(const uint32_t *d_aligned, const orbb_intrinsics &in, const orbb_keypoint *kp_raw,
+                                   const uint8_t *desc_raw, const int *count_raw, int max_kp, orbb_keypoint *kp_out,
+                                   uint8_t *desc_out, double *points, int *valid_out, int *count_blk, const uint8_t *q_desc,
+                                   const float *q_pos, const int *q_count, float max_px, int max_hamming, int *out_idx,
+                                   int *out_dist, cudaStream_t st) {
+    if (max_kp > GM_MAX_KP) return cudaErrorInvalidValue;
+    const int grid = (max_kp + GM_THREADS / 32 - 1) / (GM_THREADS / 32);
+    k_gate_match_lone<<<grid, GM_THREADS, 0, st>>>(d_aligned, in, kp_raw, reinterpret_cast<const uint4 *>(desc_raw), count_raw,
+                                                   max_kp, kp_out, reinterpret_cast<uint4 *>(desc_out), points, valid_out, count_blk,
+                                                   reinterpret_cast<const uint4 *>(q_desc), reinterpret_cast<const float2 *>(q_pos),
+                                                   q_count, max_px, max_hamming, out_idx, out_dist);
+    return cudaGetLastError();
+}
+
 // ---- RGB8 -> gray (reference cuda_RGB_to_Grayscale.cu:10-24).  thread = 4 pixels: three aligned 32-bit loads, one
 // 32-bit store (the reference: 3 byte loads + 1 byte store per thread).  float64 like the reference's expression.
 __global__ void __launch_bounds__(256) k_rgb_to_gray(const uint8_t *__restrict__ rgb, size_t rgb_pitch, size_t rgb_stride,

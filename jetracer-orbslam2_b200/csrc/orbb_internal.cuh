@@ -57,6 +57,15 @@ struct LevelDev {
     float scale, patch_size;     // mvScaleFactor[l], (float)(int)(31*scale)
 };
 
+// k_rgbd.cu, used by orbb_stage.cu: a lone frame's depth gate + 3-D lift + windowed match in one launch, and the pair compaction
+cudaError_t launch_gate_match_lone(const uint32_t *d_aligned, const orbb_intrinsics &in, const orbb_keypoint *kp_raw,
+                                   const uint8_t *desc_raw, const int *count_raw, int max_kp, orbb_keypoint *kp_out,
+                                   uint8_t *desc_out, double *points, int *valid_out, int *count_blk, const uint8_t *q_desc,
+                                   const float *q_pos, const int *q_count, float max_px, int max_hamming, int *out_idx,
+                                   int *out_dist, cudaStream_t st);
+cudaError_t launch_compact_pairs(const int *idx, const int *q_counts, int n_frames, int max_kp, const double *q_points,
+                                 const double *t_points, const void *t_xy, int t_stride, double *prev_out,
+                                 double *curr_out, uint16_t *xy_out, int *n_matched, cudaStream_t st);
 // orbb_api.cu, used by orbb_stage.cu: see the definition
 void note_replay(orbb_handle *h, int n_frames, long long launches);
 // k_rgbd.cu, used by orbb_stage.cu

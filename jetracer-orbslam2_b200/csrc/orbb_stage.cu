@@ -58,6 +58,7 @@ struct orbb_rgbd_stage {
     struct FrameGraph { int p, n, has_T; cudaGraphExec_t exec; long long launches; };
     std::vector<FrameGraph> graphs;
     int use_graph = 1, graph_max_frames = 4;
+    int lone_fused = 1;  // max_batch-1 graph path: gate + lift + match in one launch, reprojection under the extraction
     // diagnostics (ORBB_STAGE_PROF=1): timing events at the phase boundaries of the last submit, printed by wait()
     bool prof = false;
     cudaEvent_t pe[8] = {};
@@ -158,6 +159,7 @@ extern "C" int orbb_rgbd_stage_create(orbb_rgbd_stage **out, const orbb_rgbd_con
     SCKC(cudaEventCreateWithFlags(&s->ev_gfork, cudaEventDisableTiming));
     SCKC(cudaEventCreateWithFlags(&s->ev_gjoin, cudaEventDisableTiming));
     if (const char *e = getenv("ORBB_STAGE_GRAPH")) s->use_graph = atoi(e);
+    if (const char *e = getenv("ORBB_STAGE_FUSED")) s->lone_fused = atoi(e);
     SCKC(sdev(s, &s->d_aligned, s->img_px * B));
     SCKC(sdev(s, &s->d_kp_raw, B * mk)); SCKC(sdev(s, &s->d_desc_raw, B * mk * 32));
     SCKC(sdev(s, &s->d_pos, B * mk * 2)); SCKC(sdev(s, &s->d_idx, B * mk)); SCKC(sdev(s, &s->d_dist, B * mk));
@@ -209,6 +211,26 @@ extern "C" int orbb_rgbd_stage_reset(orbb_rgbd_stage *s) {
     return ORBB_OK;
 }
 
+// results of a small batch to the host on stream m: the whole block for a full batch, else only the rows in use
+static int enqueue_results_d2h(orbb_rgbd_stage *s, int p, int n_frames, cudaStream_t m) {
+    const size_t n = n_frames, mk = s->max_kp;
+    orbb_rgbd_stage::Host &H = s->host[p];
+    if (n_frames == s->B) {
+        SCK(s, cudaMemcpyAsync(s->h_block[p], s->d_block, s->block_bytes, cudaMemcpyDeviceToHost, m));
+    } else {
+        SCK(s, cudaMemcpyAsync(H.counts, s->d_counts_blk, sizeof(int) * n, cudaMemcpyDeviceToHost, m));
+        SCK(s, cudaMemcpyAsync(H.valid, s->d_valid + 1, sizeof(int) * n, cudaMemcpyDeviceToHost, m));
+        SCK(s, cudaMemcpyAsync(H.matched, s->d_nm, sizeof(int) * n, cudaMemcpyDeviceToHost, m));
+        SCK(s, cudaMemcpyAsync(H.kp, s->d_kp + mk, sizeof(orbb_keypoint) * n * mk, cudaMemcpyDeviceToHost, m));
+        SCK(s, cudaMemcpyAsync(H.desc, s->d_desc + 32 * mk, 32 * n * mk, cudaMemcpyDeviceToHost, m));
+        SCK(s, cudaMemcpyAsync(H.pts, s->d_pts + 3 * mk, sizeof(double) * 3 * n * mk, cudaMemcpyDeviceToHost, m));
+        SCK(s, cudaMemcpyAsync(H.prev_m, s->d_prev_m, sizeof(double) * 3 * n * mk, cudaMemcpyDeviceToHost, m));
+        SCK(s, cudaMemcpyAsync(H.curr_m, s->d_curr_m, sizeof(double) * 3 * n * mk, cudaMemcpyDeviceToHost, m));
+        SCK(s, cudaMemcpyAsync(H.xy, s->d_xy, sizeof(uint16_t) * 2 * n * mk, cudaMemcpyDeviceToHost, m));
+    }
+    return ORBB_OK;
+}
+
 // The second half of one small batch -- depth gate / 3-D lift, reprojection, counts, windowed match, pair
 // compaction and the D2H of the results -- enqueued on s_main: the body of the graph.  (The first half needs no graph of
 // the stage's own: the alignment is one call on s_align and the extraction replays the extractor's graph.)  Same calls,
@@ -220,6 +242,18 @@ static int enqueue_small_batch_tail(orbb_rgbd_stage *s, int p, int n_frames, boo
     // A lone frame's "previous" points are row 0 only, carried before the graph starts (see submit): their reprojection and
     // the counts for the result block run on s_align next to the depth gate / 3-D lift of the new frame.  With more frames
     // the previous rows 1..n-1 are this batch's own, so the reprojection follows the lift.
+    if (n_frames == 1 && s->lone_fused && s->max_kp <= 2048) {
+        // A lone frame: the previous points were reprojected on s_align under the extraction (see submit), so what is left is
+        // ONE launch for depth gate + 3-D lift + windowed match (k_gate_match_lone), the pair compaction and the D2H.
+        SCK(s, orbb::launch_gate_match_lone(s->d_aligned, s->cfg.image_intrin, s->d_kp_raw, s->d_desc_raw, s->d_counts_raw, s->max_kp,
+                                            s->d_kp + mk, s->d_desc + 32 * mk, s->d_pts + 3 * mk, s->d_valid + 1, s->d_counts_blk,
+                                            s->d_desc, s->d_pos, s->d_valid, s->cfg.max_pixel_distance,
+                                            std::min(s->cfg.max_hamming_distance, 257), s->d_idx, s->d_dist, m));
+        SCK(s, orbb::launch_compact_pairs(s->d_idx, s->d_valid, 1, s->max_kp, s->d_pts, s->d_pts + 3 * mk, s->d_kp + mk,
+                                          (int)sizeof(orbb_keypoint), s->d_prev_m, s->d_curr_m, s->d_xy, s->d_nm, m));
+        orbb::note_replay(s->h, 1, 2);
+        return enqueue_results_d2h(s, p, n_frames, m);
+    }
     const bool fork = n_frames == 1;
     cudaStream_t side = fork ? s->s_align : m;
     if (fork) {
@@ -240,20 +274,7 @@ static int enqueue_small_batch_tail(orbb_rgbd_stage *s, int p, int n_frames, boo
                                   (int)sizeof(orbb_keypoint), s->d_valid + 1, n_frames, s->max_kp, s->cfg.max_pixel_distance,
                                   s->cfg.max_hamming_distance, s->d_idx, s->d_dist, s->d_pts, s->d_pts + 3 * mk,
                                   s->d_prev_m, s->d_curr_m, s->d_xy, s->d_nm, m));
-    if (n_frames == s->B) {
-        SCK(s, cudaMemcpyAsync(s->h_block[p], s->d_block, s->block_bytes, cudaMemcpyDeviceToHost, m));
-    } else {
-        SCK(s, cudaMemcpyAsync(H.counts, s->d_counts_blk, sizeof(int) * n, cudaMemcpyDeviceToHost, m));
-        SCK(s, cudaMemcpyAsync(H.valid, s->d_valid + 1, sizeof(int) * n, cudaMemcpyDeviceToHost, m));
-        SCK(s, cudaMemcpyAsync(H.matched, s->d_nm, sizeof(int) * n, cudaMemcpyDeviceToHost, m));
-        SCK(s, cudaMemcpyAsync(H.kp, s->d_kp + mk, sizeof(orbb_keypoint) * n * mk, cudaMemcpyDeviceToHost, m));
-        SCK(s, cudaMemcpyAsync(H.desc, s->d_desc + 32 * mk, 32 * n * mk, cudaMemcpyDeviceToHost, m));
-        SCK(s, cudaMemcpyAsync(H.pts, s->d_pts + 3 * mk, sizeof(double) * 3 * n * mk, cudaMemcpyDeviceToHost, m));
-        SCK(s, cudaMemcpyAsync(H.prev_m, s->d_prev_m, sizeof(double) * 3 * n * mk, cudaMemcpyDeviceToHost, m));
-        SCK(s, cudaMemcpyAsync(H.curr_m, s->d_curr_m, sizeof(double) * 3 * n * mk, cudaMemcpyDeviceToHost, m));
-        SCK(s, cudaMemcpyAsync(H.xy, s->d_xy, sizeof(uint16_t) * 2 * n * mk, cudaMemcpyDeviceToHost, m));
-    }
-    return ORBB_OK;
+    return enqueue_results_d2h(s, p, n_frames, m);
 }
 
 // The graph for this (parity, frame count, pose given): captured on first use.  nullptr = use the streamed path.
@@ -324,6 +345,9 @@ extern "C" int orbb_rgbd_stage_submit(orbb_rgbd_stage *s, const uint8_t *h_gray,
                 SCK(s, orbb::launch_stage_carry(s->d_kp, s->d_desc, s->d_pts, s->d_valid, s->carry_from, s->max_kp, nullptr, nullptr,
                                                 0, s->s_align));
             SCK(s, cudaStreamWaitEvent(s->s_align, s->ev_in[p], 0));
+            if (n_frames == 1 && s->lone_fused && s->max_kp <= 2048)  // previous points (row 0) -> current image, under the extraction
+                SRC(orbb_reproject_points(s->h, s->d_pts, s->d_valid, 1, s->max_kp, h_T ? s->d_T[p] : nullptr, &s->cfg.image_intrin,
+                                          s->d_pos, s->s_align));
             SRC(orbb_align_depth_to_other(s->h, s->d_depth[p], n_frames, s->cfg.depth_scale, &s->cfg.depth_intrin,
                                           &s->cfg.image_intrin, &s->cfg.depth_to_image, s->d_aligned, s->s_align));
             SCK(s, cudaEventRecord(s->ev_align, s->s_align));

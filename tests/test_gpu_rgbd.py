@@ -189,19 +189,22 @@ def test_reproject_match_compact(orbb, oracle, synth, with_T):
     assert total > 50, "test too weak: hardly any match went through"
 
 
-@pytest.mark.parametrize("plan,max_batch,graph", [
-    ((3, 1, 4), 4, "1"),         # small batches: every submit replays a captured graph (partial and full-block D2H forms)
-    ((3, 1, 4), 4, "0"),         # the same through the streamed path
-    ((1,) * 8, 1, "1"),          # the reference's operating mode: one frame per wake-up
-    ((5, 1, 2), 8, "1"),         # streamed batch -> graph -> graph: the hand-over between the two paths, carry row 5 -> 1
-    ((1, 6, 1), 8, "1"),         # graph -> streamed -> graph
+@pytest.mark.parametrize("plan,max_batch,graph,fused", [
+    ((3, 1, 4), 4, "1", "1"),    # small batches: every submit replays a captured graph (partial and full-block D2H forms)
+    ((3, 1, 4), 4, "0", "1"),    # the same through the streamed path
+    ((1,) * 8, 1, "1", "1"),     # the reference's operating mode: one frame per wake-up (gate + lift + match in one launch)
+    ((1,) * 8, 1, "1", "0"),     # the same with the lone frame's tail as separate launches
+    ((3, 1, 4), 4, "1", "0"),
+    ((5, 1, 2), 8, "1", "1"),    # streamed batch -> graph -> graph: the hand-over between the two paths, carry row 5 -> 1
+    ((1, 6, 1), 8, "1", "1"),    # graph -> streamed -> graph
 ])
-def test_rgbd_frame_stage_sequence(orbb, oracle, synth, plan, max_batch, graph, monkeypatch):
+def test_rgbd_frame_stage_sequence(orbb, oracle, synth, plan, max_batch, graph, fused, monkeypatch):
     """The host stage over a moving sequence of 8 frames fed as the batches of `plan` (two in flight):
     every frame's gated keypoints / descriptors / 3-D points and its matches against the previous frame -- across
     batch boundaries -- equal the oracle chain run frame by frame on the GPU extractor's raw output."""
     import torch
     monkeypatch.setenv("ORBB_STAGE_GRAPH", graph)
+    monkeypatch.setenv("ORBB_STAGE_FUSED", fused)
     w, h, nfeat = 640, 480, 600
     base = synth.textured_frame(w, h, 4242)
     gray = [base]
