@@ -309,6 +309,202 @@ k_match_imma(const uint4 *__restrict__ query, const uint4 *__restrict__ train, c
     }
 }
 
+// ---- the same search on the 5th-generation tensor cores (tcgen05.mma kind::i8, accumulators in TMEM).  Opt-in
+// (ORBB_MATCH_UMMA=1) until it has been through the parity tier on a B200; k_match_imma stays the default.
+// Same contraction as k_match_imma (+1 / -1 bits, dot = 256 - 2 * Hamming), same grid / split-T / partial records /
+// packed key, so the merge kernel and every caller are shared.  CTA = 256 queries = two M = 128 A tiles, expanded ONCE
+// into 64 KB of shared memory; train descriptors are expanded 128 at a time into a double-buffered 32 KB B tile; one
+// thread issues 2 x 8 MMAs (128 x 128 x 32, s8 x s8 -> s32) per train tile into one of two 256-column accumulator
+// sets (2 sets x 2 A tiles x 128 columns = all 512 TMEM columns: one CTA per SM, which 128 KB of shared memory
+// enforces) and commits to an mbarrier.  Software pipeline per train tile t (all 256 threads walk it together):
+//     expand tile t+1 -> B[(t+1)&1]   (its last reader, MMA(t-1), was waited for in the previous round; the packed bits
+//                                      were fetched a round earlier), fetch the packed bits of tile t+2
+//     fence.proxy.async + barrier     (generic-proxy stores -> visible to the tensor core's async proxy)
+//     thread 0: MMA(t+1) -> acc[(t+1)&1], commit -> bar[(t+1)&1]   (that set was drained by epilogue(t-1))
+//     wait bar[t&1]; epilogue(t): thread = one query row (TMEM lane), 128 columns by tcgen05.ld.32x32b.x32,
+//                                 one IMAD + one min per pair (three min / max for K = 2)
+// so MMA(t+1) runs under epilogue(t) and the expansion of t+1 under MMA(t).
+// Operand layout: K-major, no swizzle.  Shared memory holds 16-byte K chunks: [chunk c = 0..15][row group of 8][row in
+// group][16 B]; core matrix = 8 rows x 16 B contiguous (128 B), SBO (next row group) = 128 B, LBO (the second 16-byte
+// chunk of an MMA's K = 32) = one chunk plane = 2048 B; K step j starts 2 planes further (CUTLASS
+// cute/atom/mma_traits_sm100.hpp, make_umma_desc<Major::K>, LayoutType::INTERLEAVE).  Chunk c holds halfword c of the
+// descriptor, byte i of the chunk = bit i of that halfword (the same mapping for A and B; a dot product does not care).
+#define MU_THREADS 256
+#define MU_N 128
+#define MU_PLANE 2048                    // 128 rows x 16 B
+#define MU_TILE_BYTES (16 * MU_PLANE)    // 32 KB: 128 rows x 256 expanded bits
+#define MU_SMEM_BYTES (4 * MU_TILE_BYTES)  // A0, A1, B0, B1
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// 128 packed bits (one uint4 = halfwords 0..7 of its half) -> eight 16-byte chunks, plane stride MU_PLANE
+__device__ __forceinline__ void mu_expand_store(const uint4 d, uint8_t *dst) {
+    const unsigned w[4] = {d.x, d.y, d.z, d.w};
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+        const unsigned hw = (w[c >> 1] >> (16 * (c & 1))) & 0xffffu;
+        *reinterpret_cast<uint4 *>(dst + c * MU_PLANE) =
+            make_uint4(expand4(hw & 15u), expand4((hw >> 4) & 15u), expand4((hw >> 8) & 15u), expand4(hw >> 12));
+    }
+}
+
+__device__ __forceinline__ void mu_wait(uint32_t bar, uint32_t parity) {
+    // bounded: a commit that never arrives (a descriptor the hardware rejects) must end in an error, not in a hung GPU
+    const long long t_start = clock64();
+    while (clock64() - t_start < 4000000000ll) {  // ~2 s
+        uint32_t done;
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+        if (done) return;
+    }
+    __trap();
+}
+
+template <int K>
+__global__ void __launch_bounds__(MU_THREADS, 1)
+k_match_umma(const uint4 *__restrict__ query, const uint4 *__restrict__ train, const int *__restrict__ q_off,
+             const int *__restrict__ t_off, int nq_one, int nt_one, int n_split, int4 *__restrict__ partial,
+             int partial_stride, const int *__restrict__ q_counts, int max_kp, int variant) {
+    extern __shared__ __align__(1024) uint8_t mu_smem[];
+    __shared__ __align__(8) uint64_t s_bar[2];
+    __shared__ uint32_t s_tmem;
+    const int seg = blockIdx.z;
+    const int q0 = q_counts ? seg * max_kp : (q_off ? q_off[seg] : 0);
+    const int q1 = q_counts ? q0 + min(q_counts[seg], max_kp) : (q_off ? q_off[seg + 1] : nq_one);
+    const int t0 = t_off ? t_off[seg] : 0, t1 = t_off ? t_off[seg + 1] : nt_one;
+    const int qbase = q0 + blockIdx.x * MU_THREADS;
+    if (qbase >= q1) return;  // block-uniform, before anything is allocated
+    const int nt = t1 - t0;
+    const int per = (nt + n_split - 1) / n_split;
+    const int ts = min(nt, (int)blockIdx.y * per), te = min(nt, ts + per);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int a_tile = warp >> 2, lane_q = warp & 3;  // a warp may only read TMEM lanes 32 * (warp % 4) .. + 31
+    const int q = qbase + a_tile * 128 + lane_q * 32 + lane;  // this thread's query row in the epilogue
+    unsigned best[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) best[k] = 0xffffffffu;
+
+    if (ts < te) {  // block-uniform
+        uint8_t *sA = mu_smem, *sB = mu_smem + 2 * MU_TILE_BYTES;
+        const uint32_t bar0 = smem_u32(&s_bar[0]), bar1 = smem_u32(&s_bar[1]);
+        if (warp == 0) {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)), "r"(512));
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+        }
+        if (tid == 32) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar0));
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar1));
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        // staging role: thread = (row of the tile, half of the descriptor)
+        const int srow = tid & 127, shalf = tid >> 7;
+        const uint32_t soff = (uint32_t)(shalf * 8 * MU_PLANE + (srow >> 3) * 128 + (srow & 7) * 16);
+#pragma unroll
+        for (int a = 0; a < 2; ++a) {
+            const int qq = min(qbase + a * 128 + srow, q1 - 1);
+            mu_expand_store(query[(size_t)qq * 2 + shalf], sA + a * MU_TILE_BYTES + soff);
+        }
+        // the packed bits of a train tile are fetched one tile ahead of their expansion (the round trip hides under the epilogue)
+        auto fetch = [&](int tb) -> uint4 {
+            const int t = tb + srow;
+            return t < te ? train[(size_t)(t0 + t) * 2 + shalf] : make_uint4(0u, 0u, 0u, 0u);
+        };
+        // descriptors: start address >> 4 in bits 0-13, LBO >> 4 in bits 16-29, SBO >> 4 in bits 32-45, version 1 in bits 46-47
+        const uint32_t lbo = variant == 1 ? 128u : (uint32_t)MU_PLANE, sbo = variant == 1 ? (uint32_t)MU_PLANE : 128u;
+        const uint64_t desc_hi = ((uint64_t)(sbo >> 4) << 32) | (1ull << 46);
+        auto desc_of = [&](const uint8_t *p) -> uint64_t {
+            return desc_hi | ((uint64_t)(lbo >> 4) << 16) | (uint64_t)((smem_u32(p) & 0x3FFFFu) >> 4);
+        };
+        // instruction descriptor: D = s32 (2 << 4), A = B = signed 8 bit (1 << 7, 1 << 10), K-major both, N >> 3 at bit 17, M >> 4 at bit 24
+        const uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(MU_N >> 3) << 17) | ((128u >> 4) << 24);
+        auto issue = [&](int buf, uint32_t tmem) {  // one thread
+#pragma unroll
+            for (int a = 0; a < 2; ++a) {
+                const uint64_t da = desc_of(sA + a * MU_TILE_BYTES), db = desc_of(sB + buf * MU_TILE_BYTES);
+                const uint32_t d_tmem = tmem + (uint32_t)(buf * 256 + a * 128);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const uint64_t adv = (uint64_t)((2 * MU_PLANE * j) >> 4);
+                    asm volatile(
+                        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                        "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n\t}"
+                        ::"r"(d_tmem), "l"(da + adv), "l"(db + adv), "r"(idesc), "r"(j ? 1u : 0u), "r"(0u) : "memory");
+                }
+            }
+            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(buf ? bar1 : bar0) : "memory");
+        };
+        mu_expand_store(fetch(ts), sB + soff);
+        uint4 pk_next = fetch(ts + MU_N);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t tmem = s_tmem;
+        if (tid == 0) issue(0, tmem);
+        const unsigned neg21 = 0xFFE00000u + ((unsigned)n_split >> 30);  // -(2^21), opaque to ptxas: keeps the key an IMAD
+        int it = 0;
+        for (int tb = ts; tb < te; tb += MU_N, ++it) {
+            const int cur = it & 1;
+            const bool more = tb + MU_N < te;  // block-uniform
+            if (more) {
+                mu_expand_store(pk_next, sB + (cur ^ 1) * MU_TILE_BYTES + soff);
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                pk_next = fetch(tb + 2 * MU_N);
+            }
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncthreads();
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            if (more && tid == 0) issue(cur ^ 1, tmem);
+            mu_wait(cur ? bar1 : bar0, (uint32_t)((it >> 1) & 1));
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            // ---- epilogue of tile `it`: this thread's row, 128 columns
+            const int cnt = min(MU_N, te - tb);
+            const uint32_t taddr = tmem + ((uint32_t)(lane_q * 32) << 16) + (uint32_t)(cur * 256 + a_tile * 128);
+            const unsigned colbase = (256u << 21) + (unsigned)(tb - ts);
+#pragma unroll
+            for (int ch = 0; ch < MU_N / 32; ++ch) {
+                if (ch * 32 >= cnt) break;  // block-uniform
+                unsigned v[32];
+                asm volatile(
+                    "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                    "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                    "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                    : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                      "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+                      "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+                      "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+                    : "r"(taddr + (uint32_t)(ch * 32)));
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                auto update = [&](unsigned key) {
+                    if (K == 1) best[0] = min(best[0], key);
+                    else {
+                        const unsigned hi = max(key, best[0]);
+                        best[0] = min(key, best[0]);
+                        best[K - 1] = min(best[K - 1], hi);
+                    }
+                };
+                if (ch * 32 + 32 <= cnt) {  // block-uniform: all 32 columns are train rows
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) update(v[i] * neg21 + (colbase + (unsigned)(ch * 32 + i)));
+                } else {  // the split's last, partial chunk
+#pragma unroll
+                    for (int i = 0; i < 32; ++i)
+                        if (ch * 32 + i < cnt) update(v[i] * neg21 + (colbase + (unsigned)(ch * 32 + i)));
+                }
+            }
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();
+        if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512));
+    }
+    if (q < q1) {
+        const unsigned k1 = best[0], k2 = K == 2 ? best[K - 1] : 0xffffffffu;
+        partial[(size_t)blockIdx.y * partial_stride + q] =
+            make_int4(k1 == 0xffffffffu ? 257 : (int)(k1 >> 22), k1 == 0xffffffffu ? -1 : ts + (int)(k1 & 0x3fffffu),
+                      k2 == 0xffffffffu ? 257 : (int)(k2 >> 22), k2 == 0xffffffffu ? -1 : ts + (int)(k2 & 0x3fffffu));
+    }
+}
+
 __global__ void __launch_bounds__(256)
 k_match_merge(const int4 *__restrict__ partial, int partial_stride, int n_split, int nq, int k, float ratio,
               int *__restrict__ out_idx, int *__restrict__ out_dist, uint8_t *__restrict__ accept,
@@ -439,7 +635,22 @@ cudaError_t launch_match(const uint8_t *d_q, const uint8_t *d_t, const int *d_q_
     dim3 grid(qblocks, n_split, nseg);
     // default: the tensor-core form (same grid, same partial records); ORBB_MATCH_POPC=1 keeps the XOR / POPC kernel
     static const bool use_popc = getenv("ORBB_MATCH_POPC") && atoi(getenv("ORBB_MATCH_POPC")) != 0;
-    if (!use_popc) {
+    static const int use_umma = getenv("ORBB_MATCH_UMMA") ? atoi(getenv("ORBB_MATCH_UMMA")) : 0;  // 1: tcgen05 form; 2: its LBO / SBO swapped (probe)
+    if (use_umma && !use_popc) {
+        static const cudaError_t attr = [] {
+            cudaError_t e = cudaFuncSetAttribute(k_match_umma<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, MU_SMEM_BYTES);
+            return e != cudaSuccess ? e : cudaFuncSetAttribute(k_match_umma<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, MU_SMEM_BYTES);
+        }();
+        if (attr != cudaSuccess) return attr;
+        if (k == 1)
+            k_match_umma<1><<<grid, MU_THREADS, MU_SMEM_BYTES, st>>>(reinterpret_cast<const uint4 *>(d_q), reinterpret_cast<const uint4 *>(d_t),
+                                                                     d_q_off, d_t_off, nq_total, nt_one, n_split, d_partial,
+                                                                     partial_stride, d_q_counts, max_kp, use_umma - 1);
+        else
+            k_match_umma<2><<<grid, MU_THREADS, MU_SMEM_BYTES, st>>>(reinterpret_cast<const uint4 *>(d_q), reinterpret_cast<const uint4 *>(d_t),
+                                                                     d_q_off, d_t_off, nq_total, nt_one, n_split, d_partial,
+                                                                     partial_stride, d_q_counts, max_kp, use_umma - 1);
+    } else if (!use_popc) {
         if (k == 1)
             k_match_imma<1><<<grid, MI_THREADS, 0, st>>>(reinterpret_cast<const uint4 *>(d_q), reinterpret_cast<const uint4 *>(d_t),
                                                          d_q_off, d_t_off, nq_total, nt_one, n_split, d_partial, partial_stride,

@@ -415,7 +415,7 @@ k_gate_match_lone(const uint32_t *__restrict__ aligned, const orbb_intrinsics in
         depth[c] = 0;
         if (c < nchunks && i < n && xi >= 0 && yi >= 0 && xi < in.width && yi < in.height) depth[c] = (int)aligned[(size_t)yi * in.width + xi];
     }
-    unsigned keep = 0, below = 0;  // bit c: item kept; rank of the item among the kept ones of its warp step
+    unsigned keep = 0;  // bit c: item kept; rank[c]: its place among the kept items of its warp step
     int rank[GM_MAX_KP / GM_THREADS];
 #pragma unroll
     for (int c = 0; c < GM_MAX_KP / GM_THREADS; ++c) {
@@ -425,7 +425,6 @@ k_gate_match_lone(const uint32_t *__restrict__ aligned, const orbb_intrinsics in
         if (k) keep |= 1u << c;
         if (lane == 0 && c < nchunks) s_cnt[c * 4 + warp] = __popc(m);
     }
-    (void)below;
     __syncthreads();
     if (warp == 0) {  // exclusive prefix over the (chunk, warp) counts in raw order: <= 64 entries, two per lane
         const int e0 = 2 * lane, e1 = 2 * lane + 1, ne = nchunks * 4;

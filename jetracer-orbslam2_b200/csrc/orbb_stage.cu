@@ -237,7 +237,6 @@ static int enqueue_results_d2h(orbb_rgbd_stage *s, int p, int n_frames, cudaStre
 // same arguments, same results as the streamed path below.
 static int enqueue_small_batch_tail(orbb_rgbd_stage *s, int p, int n_frames, bool has_T) {
     const size_t n = n_frames, mk = s->max_kp;
-    orbb_rgbd_stage::Host &H = s->host[p];
     cudaStream_t m = s->s_main;
     // A lone frame's "previous" points are row 0 only, carried before the graph starts (see submit): their reprojection and
     // the counts for the result block run on s_align next to the depth gate / 3-D lift of the new frame.  With more frames

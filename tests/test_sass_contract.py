@@ -47,11 +47,14 @@ def test_sm100a_only_and_tensor_cores_only_in_the_matcher(sass):
     assert archs == {"sm_100a"}
     assert len(kernels) >= 25
     for name, ops in kernels.items():
-        for tc in ("HMMA", "DMMA", "UTCHMMA", "UTCIMMA", "UTCQMMA", "WGMMA"):
+        for tc in ("HMMA", "DMMA", "UTCHMMA", "UTCQMMA", "WGMMA"):
             assert _count(ops, tc) == 0, (name, tc)
-        # the one dense contraction of the path -- all-pairs Hamming distances -- runs as int8 MMAs; nothing else may
+        # the one dense contraction of the path -- all-pairs Hamming distances -- runs as int8 MMAs; nothing else may:
+        # warp-level IMMA in k_match_imma, tcgen05 (UTCIMMA, accumulators read back with LDTM) in k_match_umma
         if "k_match_imma" not in name and "k_imma_rate" not in name:
             assert _count(ops, "IMMA") == 0, name
+        if "k_match_umma" not in name:
+            assert _count(ops, "UTCIMMA") == 0 and _count(ops, "LDTM") == 0, name
 
 
 def test_kernels_carry_their_instructions(sass):
@@ -64,6 +67,10 @@ def test_kernels_carry_their_instructions(sass):
     for kk in ("k_match_immaILi1E", "k_match_immaILi2E"):  # 32 MMAs per pair of column groups, A fragments in registers
         ops = _kernel(kernels, kk)
         assert _count(ops, "IMMA.16832.S8.S8") >= 32 and _count(ops, "LDS.128") >= 8, kk
+        assert _count(ops, "LDL") == 0 and _count(ops, "STL") == 0 and _count(ops, "POPC") == 0, kk
+    for kk in ("k_match_ummaILi1E", "k_match_ummaILi2E"):  # tcgen05: 2 issue sites x 2 A tiles x 8 K steps, 128 columns per LDTM round
+        ops = _kernel(kernels, kk)
+        assert _count(ops, "UTCIMMA") == 32 and _count(ops, "LDTM") == 4 and _count(ops, "STS.128") >= 24, kk
         assert _count(ops, "LDL") == 0 and _count(ops, "STL") == 0 and _count(ops, "POPC") == 0, kk
     fast = _kernel(kernels, "k_fast_cellsILb0ELb0E")
     assert _count(fast, "VABSDIFF4") >= 4 and _count(fast, "VIMNMX3") >= 40  # packed precheck, arc-score min/max network
