@@ -153,7 +153,7 @@ k_match(const uint4 *__restrict__ query, const uint4 *__restrict__ train, const 
 
 __device__ __forceinline__ unsigned expand4(unsigned nib) {  // four descriptor bits -> four s8: 1 -> +1, 0 -> -1
     const unsigned w = (nib * 0x00204081u) & 0x01010101u;   // bit i -> bit 0 of byte i (no two partial products meet)
-    return w | ((w ^ 0x01010101u) * 0xFFu);
+    return w * 0xFFFFFF02u + 0xFFFFFFFFu;                    // per byte 255 - 254 * w: 1 -> 0x01, 0 -> 0xFF (no borrow between bytes)
 }
 
 __device__ __forceinline__ void imma16832(int (&d)[4], const unsigned (&a)[4], unsigned b0, unsigned b1, bool first) {
@@ -309,27 +309,34 @@ k_match_imma(const uint4 *__restrict__ query, const uint4 *__restrict__ train, c
     }
 }
 
-// ---- the same search on the 5th-generation tensor cores (tcgen05.mma kind::i8, accumulators in TMEM).  Opt-in
-// (ORBB_MATCH_UMMA=1) until it has been through the parity tier on a B200; k_match_imma stays the default.
+// ---- the same search on the 5th-generation tensor cores (tcgen05.mma kind::i8, accumulators in TMEM).
 // Same contraction as k_match_imma (+1 / -1 bits, dot = 256 - 2 * Hamming), same grid / split-T / partial records /
 // packed key, so the merge kernel and every caller are shared.  CTA = 256 queries = two M = 128 A tiles, expanded ONCE
-// into 64 KB of shared memory; train descriptors are expanded 128 at a time into a double-buffered 32 KB B tile; one
-// thread issues 2 x 8 MMAs (128 x 128 x 32, s8 x s8 -> s32) per train tile into one of two 256-column accumulator
-// sets (2 sets x 2 A tiles x 128 columns = all 512 TMEM columns: one CTA per SM, which 128 KB of shared memory
-// enforces) and commits to an mbarrier.  Software pipeline per train tile t (all 256 threads walk it together):
-//     expand tile t+1 -> B[(t+1)&1]   (its last reader, MMA(t-1), was waited for in the previous round; the packed bits
-//                                      were fetched a round earlier), fetch the packed bits of tile t+2
-//     fence.proxy.async + barrier     (generic-proxy stores -> visible to the tensor core's async proxy)
-//     thread 0: MMA(t+1) -> acc[(t+1)&1], commit -> bar[(t+1)&1]   (that set was drained by epilogue(t-1))
-//     wait bar[t&1]; epilogue(t): thread = one query row (TMEM lane), 128 columns by tcgen05.ld.32x32b.x32,
-//                                 one IMAD + one min per pair (three min / max for K = 2)
-// so MMA(t+1) runs under epilogue(t) and the expansion of t+1 under MMA(t).
+// into 64 KB of shared memory; train descriptors are expanded 128 at a time into a double-buffered 32 KB B tile; per
+// train tile 2 x 8 MMAs (128 x 128 x 32, s8 x s8 -> s32) go into one of two 256-column accumulator sets (2 sets x 2 A
+// tiles x 128 columns = all 512 TMEM columns: one CTA per SM, which 128 KB of shared memory enforces).
+// Warp-specialised, no CTA-wide barrier inside the loop -- three mbarrier pairs carry the hand-overs:
+//     full[b]    (256 arrivals)  workers  -> issuer : B[b] holds tile t, expanded and fenced for the async proxy
+//     accfree[b] (256 arrivals)  workers  -> issuer : epilogue(t-2) has drained accumulator set b
+//     done[b]    (tcgen05.commit) issuer  -> workers: MMA(t) complete -- set b is readable, B[b] may be overwritten
+//   warps 0-7 (workers), tile t: wait done[t&1]; epilogue(t): thread = one query row (TMEM lane), 128 columns by four
+//       tcgen05.ld.32x32b.x32; arrive accfree[t&1]; expand tile t+2 -> B[t&1] (its packed bits were fetched two tiles
+//       earlier); arrive full[t&1]
+//   warp 8 (issuer), tile t: wait full[t&1], accfree[t&1]; one lane issues the 16 MMAs and commits to done[t&1]
+// (A first version had thread 0 of the workers issue the MMAs between two CTA barriers: the issuing warp blocks while
+// the tensor queue is full, everyone else then waits for it at the next barrier, and MMA and ALU work took turns --
+// 3.26 Tpairs/s, tensor pipe 38 %, profiles/r02g_k_match_umma_full.txt.)
+// Epilogue: a column can only matter if its dot product exceeds that of the current K-th best (equal distance at a
+// higher index never wins), so a chunk of 32 columns is first reduced to its maximum (3-input max, four chains) and the
+// packed-key pass -- one IMAD + one min per pair, three min / max for K = 2 -- runs only for chunks that hold an
+// improvement (after the first few tiles: rarely).  Same keys, same tie rule, same results.
 // Operand layout: K-major, no swizzle.  Shared memory holds 16-byte K chunks: [chunk c = 0..15][row group of 8][row in
 // group][16 B]; core matrix = 8 rows x 16 B contiguous (128 B), SBO (next row group) = 128 B, LBO (the second 16-byte
 // chunk of an MMA's K = 32) = one chunk plane = 2048 B; K step j starts 2 planes further (CUTLASS
 // cute/atom/mma_traits_sm100.hpp, make_umma_desc<Major::K>, LayoutType::INTERLEAVE).  Chunk c holds halfword c of the
 // descriptor, byte i of the chunk = bit i of that halfword (the same mapping for A and B; a dot product does not care).
-#define MU_THREADS 256
+#define MU_THREADS 256                   // worker threads = queries per CTA (the query block of k_match / k_match_imma)
+#define MU_BLOCK (MU_THREADS + 32)       // + the issuing warp
 #define MU_N 128
 #define MU_PLANE 2048                    // 128 rows x 16 B
 #define MU_TILE_BYTES (16 * MU_PLANE)    // 32 KB: 128 rows x 256 expanded bits
@@ -349,7 +356,8 @@ __device__ __forceinline__ void mu_expand_store(const uint4 d, uint8_t *dst) {
 }
 
 __device__ __forceinline__ void mu_wait(uint32_t bar, uint32_t parity) {
-    // bounded: a commit that never arrives (a descriptor the hardware rejects) must end in an error, not in a hung GPU
+    // bounded: a hand-over that never arrives (a descriptor the hardware rejects, a phase slip) must end in an error,
+    // not in a hung GPU
     const long long t_start = clock64();
     while (clock64() - t_start < 4000000000ll) {  // ~2 s
         uint32_t done;
@@ -360,13 +368,31 @@ __device__ __forceinline__ void mu_wait(uint32_t bar, uint32_t parity) {
     __trap();
 }
 
+__device__ __forceinline__ void mu_arrive(uint32_t bar) {
+    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"(bar) : "memory");
+}
+
+__device__ __forceinline__ int max3(int a, int b, int c) { return max(max(a, b), c); }
+
+#define MU_LDTM32(v, o, addr)                                                                                              \
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "                                                                 \
+                 "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "                                 \
+                 "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"                 \
+                 : "=r"(v[o + 0]), "=r"(v[o + 1]), "=r"(v[o + 2]), "=r"(v[o + 3]), "=r"(v[o + 4]), "=r"(v[o + 5]),         \
+                   "=r"(v[o + 6]), "=r"(v[o + 7]), "=r"(v[o + 8]), "=r"(v[o + 9]), "=r"(v[o + 10]), "=r"(v[o + 11]),       \
+                   "=r"(v[o + 12]), "=r"(v[o + 13]), "=r"(v[o + 14]), "=r"(v[o + 15]), "=r"(v[o + 16]), "=r"(v[o + 17]),   \
+                   "=r"(v[o + 18]), "=r"(v[o + 19]), "=r"(v[o + 20]), "=r"(v[o + 21]), "=r"(v[o + 22]), "=r"(v[o + 23]),   \
+                   "=r"(v[o + 24]), "=r"(v[o + 25]), "=r"(v[o + 26]), "=r"(v[o + 27]), "=r"(v[o + 28]), "=r"(v[o + 29]),   \
+                   "=r"(v[o + 30]), "=r"(v[o + 31])                                                                        \
+                 : "r"(addr))
+
 template <int K>
-__global__ void __launch_bounds__(MU_THREADS, 1)
+__global__ void __launch_bounds__(MU_BLOCK, 1)
 k_match_umma(const uint4 *__restrict__ query, const uint4 *__restrict__ train, const int *__restrict__ q_off,
              const int *__restrict__ t_off, int nq_one, int nt_one, int n_split, int4 *__restrict__ partial,
-             int partial_stride, const int *__restrict__ q_counts, int max_kp, int variant) {
+             int partial_stride, const int *__restrict__ q_counts, int max_kp, int plain_epilogue) {
     extern __shared__ __align__(1024) uint8_t mu_smem[];
-    __shared__ __align__(8) uint64_t s_bar[2];
+    __shared__ __align__(8) uint64_t s_bar[6];  // full[2], accfree[2], done[2]
     __shared__ uint32_t s_tmem;
     const int seg = blockIdx.z;
     const int q0 = q_counts ? seg * max_kp : (q_off ? q_off[seg] : 0);
@@ -378,126 +404,153 @@ k_match_umma(const uint4 *__restrict__ query, const uint4 *__restrict__ train, c
     const int per = (nt + n_split - 1) / n_split;
     const int ts = min(nt, (int)blockIdx.y * per), te = min(nt, ts + per);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int a_tile = warp >> 2, lane_q = warp & 3;  // a warp may only read TMEM lanes 32 * (warp % 4) .. + 31
-    const int q = qbase + a_tile * 128 + lane_q * 32 + lane;  // this thread's query row in the epilogue
+    const int a_tile = (warp >> 2) & 1, lane_q = warp & 3;  // a warp may only read TMEM lanes 32 * (warp % 4) .. + 31
+    const int q = qbase + a_tile * 128 + lane_q * 32 + lane;  // a worker's query row in the epilogue
     unsigned best[K];
 #pragma unroll
     for (int k = 0; k < K; ++k) best[k] = 0xffffffffu;
 
     if (ts < te) {  // block-uniform
         uint8_t *sA = mu_smem, *sB = mu_smem + 2 * MU_TILE_BYTES;
-        const uint32_t bar0 = smem_u32(&s_bar[0]), bar1 = smem_u32(&s_bar[1]);
-        if (warp == 0) {
+        const uint32_t bar_full = smem_u32(&s_bar[0]), bar_free = smem_u32(&s_bar[2]), bar_done = smem_u32(&s_bar[4]);
+        const int ntiles = (te - ts + MU_N - 1) / MU_N;
+        if (warp == 8) {
             asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)), "r"(512));
             asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
         }
-        if (tid == 32) {
-            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar0));
-            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar1));
+        if (tid == 0) {
+#pragma unroll
+            for (int b = 0; b < 2; ++b) {
+                asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar_full + 8 * b), "r"(MU_THREADS));
+                asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar_free + 8 * b), "r"(MU_THREADS));
+                asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar_done + 8 * b), "r"(1));
+            }
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
-        // staging role: thread = (row of the tile, half of the descriptor)
-        const int srow = tid & 127, shalf = tid >> 7;
-        const uint32_t soff = (uint32_t)(shalf * 8 * MU_PLANE + (srow >> 3) * 128 + (srow & 7) * 16);
-#pragma unroll
-        for (int a = 0; a < 2; ++a) {
-            const int qq = min(qbase + a * 128 + srow, q1 - 1);
-            mu_expand_store(query[(size_t)qq * 2 + shalf], sA + a * MU_TILE_BYTES + soff);
-        }
-        // the packed bits of a train tile are fetched one tile ahead of their expansion (the round trip hides under the epilogue)
-        auto fetch = [&](int tb) -> uint4 {
-            const int t = tb + srow;
-            return t < te ? train[(size_t)(t0 + t) * 2 + shalf] : make_uint4(0u, 0u, 0u, 0u);
-        };
-        // descriptors: start address >> 4 in bits 0-13, LBO >> 4 in bits 16-29, SBO >> 4 in bits 32-45, version 1 in bits 46-47
-        const uint32_t lbo = variant == 1 ? 128u : (uint32_t)MU_PLANE, sbo = variant == 1 ? (uint32_t)MU_PLANE : 128u;
-        const uint64_t desc_hi = ((uint64_t)(sbo >> 4) << 32) | (1ull << 46);
-        auto desc_of = [&](const uint8_t *p) -> uint64_t {
-            return desc_hi | ((uint64_t)(lbo >> 4) << 16) | (uint64_t)((smem_u32(p) & 0x3FFFFu) >> 4);
-        };
-        // instruction descriptor: D = s32 (2 << 4), A = B = signed 8 bit (1 << 7, 1 << 10), K-major both, N >> 3 at bit 17, M >> 4 at bit 24
-        const uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(MU_N >> 3) << 17) | ((128u >> 4) << 24);
-        auto issue = [&](int buf, uint32_t tmem) {  // one thread
-#pragma unroll
-            for (int a = 0; a < 2; ++a) {
-                const uint64_t da = desc_of(sA + a * MU_TILE_BYTES), db = desc_of(sB + buf * MU_TILE_BYTES);
-                const uint32_t d_tmem = tmem + (uint32_t)(buf * 256 + a * 128);
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const uint64_t adv = (uint64_t)((2 * MU_PLANE * j) >> 4);
-                    asm volatile(
-                        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-                        "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n\t}"
-                        ::"r"(d_tmem), "l"(da + adv), "l"(db + adv), "r"(idesc), "r"(j ? 1u : 0u), "r"(0u) : "memory");
-                }
-            }
-            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(buf ? bar1 : bar0) : "memory");
-        };
-        mu_expand_store(fetch(ts), sB + soff);
-        uint4 pk_next = fetch(ts + MU_N);
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncthreads();
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t tmem = s_tmem;
-        if (tid == 0) issue(0, tmem);
-        const unsigned neg21 = 0xFFE00000u + ((unsigned)n_split >> 30);  // -(2^21), opaque to ptxas: keeps the key an IMAD
-        int it = 0;
-        for (int tb = ts; tb < te; tb += MU_N, ++it) {
-            const int cur = it & 1;
-            const bool more = tb + MU_N < te;  // block-uniform
-            if (more) {
-                mu_expand_store(pk_next, sB + (cur ^ 1) * MU_TILE_BYTES + soff);
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                pk_next = fetch(tb + 2 * MU_N);
-            }
-            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-            __syncthreads();
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            if (more && tid == 0) issue(cur ^ 1, tmem);
-            mu_wait(cur ? bar1 : bar0, (uint32_t)((it >> 1) & 1));
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            // ---- epilogue of tile `it`: this thread's row, 128 columns
-            const int cnt = min(MU_N, te - tb);
-            const uint32_t taddr = tmem + ((uint32_t)(lane_q * 32) << 16) + (uint32_t)(cur * 256 + a_tile * 128);
-            const unsigned colbase = (256u << 21) + (unsigned)(tb - ts);
+
+        if (warp == 8) {
+            // ================= issuer =================
+            // descriptors: start address >> 4 in bits 0-13, LBO >> 4 in bits 16-29, SBO >> 4 in bits 32-45, version 1 in bits 46-47
+            const uint64_t desc_hi = ((uint64_t)(128u >> 4) << 32) | (1ull << 46) | ((uint64_t)(MU_PLANE >> 4) << 16);
+            auto desc_of = [&](const uint8_t *p) -> uint64_t { return desc_hi | (uint64_t)((smem_u32(p) & 0x3FFFFu) >> 4); };
+            // instruction descriptor: D = s32 (2 << 4), A = B = signed 8 bit (1 << 7, 1 << 10), K-major both, N >> 3 at bit 17, M >> 4 at bit 24
+            const uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(MU_N >> 3) << 17) | ((128u >> 4) << 24);
+            for (int t = 0; t < ntiles; ++t) {
+                const int b = t & 1, k = t >> 1;
+                mu_wait(bar_full + 8 * b, (uint32_t)(k & 1));
+                if (k > 0) mu_wait(bar_free + 8 * b, (uint32_t)((k - 1) & 1));
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                if (lane == 0) {
 #pragma unroll
-            for (int ch = 0; ch < MU_N / 32; ++ch) {
-                if (ch * 32 >= cnt) break;  // block-uniform
-                unsigned v[32];
-                asm volatile(
-                    "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-                    "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-                    "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-                    : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-                      "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
-                      "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
-                      "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-                    : "r"(taddr + (uint32_t)(ch * 32)));
-                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                auto update = [&](unsigned key) {
-                    if (K == 1) best[0] = min(best[0], key);
-                    else {
-                        const unsigned hi = max(key, best[0]);
-                        best[0] = min(key, best[0]);
-                        best[K - 1] = min(best[K - 1], hi);
+                    for (int a = 0; a < 2; ++a) {
+                        const uint64_t da = desc_of(sA + a * MU_TILE_BYTES), db = desc_of(sB + b * MU_TILE_BYTES);
+                        const uint32_t d_tmem = tmem + (uint32_t)(b * 256 + a * 128);
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            const uint64_t adv = (uint64_t)((2 * MU_PLANE * j) >> 4);
+                            asm volatile(
+                                "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                                "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n\t}"
+                                ::"r"(d_tmem), "l"(da + adv), "l"(db + adv), "r"(idesc), "r"(j ? 1u : 0u), "r"(0u) : "memory");
+                        }
                     }
-                };
-                if (ch * 32 + 32 <= cnt) {  // block-uniform: all 32 columns are train rows
+                    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar_done + 8 * b) : "memory");
+                }
+                __syncwarp();
+            }
+        } else {
+            // ================= workers =================
+            // staging role: thread = (row of the tile, half of the descriptor)
+            const int srow = tid & 127, shalf = tid >> 7;
+            const uint32_t soff = (uint32_t)(shalf * 8 * MU_PLANE + (srow >> 3) * 128 + (srow & 7) * 16);
+            auto fetch = [&](int tile) -> uint4 {  // packed bits of this thread's part of a train tile (zeros past the split's end)
+                const int t = ts + tile * MU_N + srow;
+                return t < te ? train[(size_t)(t0 + t) * 2 + shalf] : make_uint4(0u, 0u, 0u, 0u);
+            };
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) update(v[i] * neg21 + (colbase + (unsigned)(ch * 32 + i)));
-                } else {  // the split's last, partial chunk
+            for (int a = 0; a < 2; ++a) {
+                const int qq = min(qbase + a * 128 + srow, q1 - 1);
+                mu_expand_store(query[(size_t)qq * 2 + shalf], sA + a * MU_TILE_BYTES + soff);
+            }
+            uint4 pk0 = fetch(0), pk1 = fetch(1);
+            mu_expand_store(pk0, sB + soff);
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            mu_arrive(bar_full);
+            if (ntiles > 1) {
+                mu_expand_store(pk1, sB + MU_TILE_BYTES + soff);
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                mu_arrive(bar_full + 8);
+            }
+            pk0 = fetch(2); pk1 = fetch(3);  // for tiles t + 2 of the rounds t = 0, 1
+            const unsigned neg21 = 0xFFE00000u + ((unsigned)n_split >> 30);  // -(2^21), opaque to ptxas: keeps the key an IMAD
+            int thr = plain_epilogue ? -100000 : 256 - 2 * (int)(0xffffffffu >> 22);  // dot product of the current K-th best (none yet)
+            auto update = [&](unsigned key) {
+                if (K == 1) best[0] = min(best[0], key);
+                else {
+                    const unsigned hi = max(key, best[0]);
+                    best[0] = min(key, best[0]);
+                    best[K - 1] = min(best[K - 1], hi);
+                }
+            };
+            for (int t = 0; t < ntiles; ++t) {
+                const int b = t & 1, k = t >> 1;
+                mu_wait(bar_done + 8 * b, (uint32_t)(k & 1));
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                // ---- epilogue of tile t: this thread's row, 128 columns
+                const int tb = ts + t * MU_N;
+                const int cnt = min(MU_N, te - tb);
+                const uint32_t taddr = tmem + ((uint32_t)(lane_q * 32) << 16) + (uint32_t)(b * 256 + a_tile * 128);
+                const unsigned colbase = (256u << 21) + (unsigned)(tb - ts);
+                unsigned v[MU_N];
+                MU_LDTM32(v, 0, taddr);
+                MU_LDTM32(v, 32, taddr + 32u);
+                MU_LDTM32(v, 64, taddr + 64u);
+                MU_LDTM32(v, 96, taddr + 96u);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                // the accumulator set is in registers: hand it back before the ALU work
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                mu_arrive(bar_free + 8 * b);
 #pragma unroll
-                    for (int i = 0; i < 32; ++i)
-                        if (ch * 32 + i < cnt) update(v[i] * neg21 + (colbase + (unsigned)(ch * 32 + i)));
+                for (int ch = 0; ch < MU_N / 32; ++ch) {
+                    if (ch * 32 >= cnt) break;  // block-uniform
+                    if (ch * 32 + 32 <= cnt) {  // block-uniform: all 32 columns are train rows
+                        int m[4];
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) {
+                            const int o = ch * 32 + c * 8;
+                            m[c] = max(max3(max3(max3((int)v[o], (int)v[o + 1], (int)v[o + 2]), (int)v[o + 3], (int)v[o + 4]),
+                                            (int)v[o + 5], (int)v[o + 6]), (int)v[o + 7]);
+                        }
+                        if (max(max3(m[0], m[1], m[2]), m[3]) > thr) {  // rare after the first tiles
+#pragma unroll
+                            for (int i = 0; i < 32; ++i) update(v[ch * 32 + i] * neg21 + (colbase + (unsigned)(ch * 32 + i)));
+                            if (!plain_epilogue) thr = 256 - 2 * (int)(best[K - 1] >> 22);
+                        }
+                    } else {  // the split's last, partial chunk
+#pragma unroll
+                        for (int i = 0; i < 32; ++i)
+                            if (ch * 32 + i < cnt) update(v[ch * 32 + i] * neg21 + (colbase + (unsigned)(ch * 32 + i)));
+                        if (!plain_epilogue) thr = 256 - 2 * (int)(best[K - 1] >> 22);
+                    }
+                }
+                // ---- tile t + 2 into the B buffer MMA(t) has just released
+                if (t + 2 < ntiles) {  // block-uniform
+                    mu_expand_store(b ? pk1 : pk0, sB + b * MU_TILE_BYTES + soff);
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    mu_arrive(bar_full + 8 * b);
+                    if (b) pk1 = fetch(t + 4); else pk0 = fetch(t + 4);
                 }
             }
         }
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncthreads();
-        if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512));
+        if (warp == 8) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512));
     }
-    if (q < q1) {
+    if (warp < 8 && q < q1) {
         const unsigned k1 = best[0], k2 = K == 2 ? best[K - 1] : 0xffffffffu;
         partial[(size_t)blockIdx.y * partial_stride + q] =
             make_int4(k1 == 0xffffffffu ? 257 : (int)(k1 >> 22), k1 == 0xffffffffu ? -1 : ts + (int)(k1 & 0x3fffffu),
@@ -635,7 +688,7 @@ cudaError_t launch_match(const uint8_t *d_q, const uint8_t *d_t, const int *d_q_
     dim3 grid(qblocks, n_split, nseg);
     // default: the tensor-core form (same grid, same partial records); ORBB_MATCH_POPC=1 keeps the XOR / POPC kernel
     static const bool use_popc = getenv("ORBB_MATCH_POPC") && atoi(getenv("ORBB_MATCH_POPC")) != 0;
-    static const int use_umma = getenv("ORBB_MATCH_UMMA") ? atoi(getenv("ORBB_MATCH_UMMA")) : 0;  // 1: tcgen05 form; 2: its LBO / SBO swapped (probe)
+    static const int use_umma = getenv("ORBB_MATCH_UMMA") ? atoi(getenv("ORBB_MATCH_UMMA")) : 0;  // 1: tcgen05 form; 2: with the plain epilogue (every pair keyed)
     if (use_umma && !use_popc) {
         static const cudaError_t attr = [] {
             cudaError_t e = cudaFuncSetAttribute(k_match_umma<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, MU_SMEM_BYTES);
@@ -643,11 +696,11 @@ cudaError_t launch_match(const uint8_t *d_q, const uint8_t *d_t, const int *d_q_
         }();
         if (attr != cudaSuccess) return attr;
         if (k == 1)
-            k_match_umma<1><<<grid, MU_THREADS, MU_SMEM_BYTES, st>>>(reinterpret_cast<const uint4 *>(d_q), reinterpret_cast<const uint4 *>(d_t),
+            k_match_umma<1><<<grid, MU_BLOCK, MU_SMEM_BYTES, st>>>(reinterpret_cast<const uint4 *>(d_q), reinterpret_cast<const uint4 *>(d_t),
                                                                      d_q_off, d_t_off, nq_total, nt_one, n_split, d_partial,
                                                                      partial_stride, d_q_counts, max_kp, use_umma - 1);
         else
-            k_match_umma<2><<<grid, MU_THREADS, MU_SMEM_BYTES, st>>>(reinterpret_cast<const uint4 *>(d_q), reinterpret_cast<const uint4 *>(d_t),
+            k_match_umma<2><<<grid, MU_BLOCK, MU_SMEM_BYTES, st>>>(reinterpret_cast<const uint4 *>(d_q), reinterpret_cast<const uint4 *>(d_t),
                                                                      d_q_off, d_t_off, nq_total, nt_one, n_split, d_partial,
                                                                      partial_stride, d_q_counts, max_kp, use_umma - 1);
     } else if (!use_popc) {

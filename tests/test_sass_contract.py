@@ -68,9 +68,10 @@ def test_kernels_carry_their_instructions(sass):
         ops = _kernel(kernels, kk)
         assert _count(ops, "IMMA.16832.S8.S8") >= 32 and _count(ops, "LDS.128") >= 8, kk
         assert _count(ops, "LDL") == 0 and _count(ops, "STL") == 0 and _count(ops, "POPC") == 0, kk
-    for kk in ("k_match_ummaILi1E", "k_match_ummaILi2E"):  # tcgen05: 2 issue sites x 2 A tiles x 8 K steps, 128 columns per LDTM round
+    for kk in ("k_match_ummaILi1E", "k_match_ummaILi2E"):  # tcgen05: 2 A tiles x 8 K steps per train tile, 128 columns per LDTM round
         ops = _kernel(kernels, kk)
-        assert _count(ops, "UTCIMMA") == 32 and _count(ops, "LDTM") == 4 and _count(ops, "STS.128") >= 24, kk
+        assert _count(ops, "UTCIMMA") == 16 and _count(ops, "LDTM") == 4 and _count(ops, "STS.128") >= 24, kk
+        assert _count(ops, "VIMNMX3") >= 56, kk  # the chunk-maximum pass in front of the packed-key pass
         assert _count(ops, "LDL") == 0 and _count(ops, "STL") == 0 and _count(ops, "POPC") == 0, kk
     fast = _kernel(kernels, "k_fast_cellsILb0ELb0E")
     assert _count(fast, "VABSDIFF4") >= 4 and _count(fast, "VIMNMX3") >= 40  # packed precheck, arc-score min/max network

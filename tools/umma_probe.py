@@ -1,5 +1,6 @@
 #!/usr/bin/env python3
-"""tcgen05 matcher (k_match_umma, ORBB_MATCH_UMMA=1) against the XOR / POPC matcher on the same inputs, then its throughput.
+"""tcgen05 matcher (k_match_umma; ORBB_MATCH_UMMA=2: every pair keyed in the epilogue) against the XOR / POPC matcher on the
+same inputs, then its throughput.
 The matcher's kernel choice is read once per process, so every form runs in a child process (bounded by a timeout: a
 kernel whose MMA never completes traps after ~2 s instead of hanging).  Shapes cover full and partial train tiles,
 split-T, k = 1 and 2, and duplicate train rows (tie rule: lowest train index).
@@ -80,7 +81,7 @@ def main():
     if ref is None:
         sys.exit(1)
     good = []
-    for name, env in (("umma(lbo=plane,sbo=128)", {"ORBB_MATCH_UMMA": "1"}), ("umma(lbo=128,sbo=plane)", {"ORBB_MATCH_UMMA": "2"}),
+    for name, env in (("umma", {"ORBB_MATCH_UMMA": "1"}), ("umma(plain epilogue)", {"ORBB_MATCH_UMMA": "2"}),
                       ("imma", {})):
         got = run(name, env, os.path.join(tmp, "umma_got.npz"))
         if got is None:
