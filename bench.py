@@ -1016,6 +1016,16 @@ def main():
         # (orbb_debug_imma_rate: 0.5 per clock per SM on B200); the XOR / POPC kernel's roof is kept for comparison.
         imma_per_clk = imma_rate if imma_rate else 0.5
         imma_roof = 148 * imma_per_clk * 16 * f_mhz * 1e6 / 1e9
+        # The default matcher issues the same contraction as tcgen05 kind::i8 MMAs (128 x 128 x 32 from shared memory,
+        # accumulators in TMEM).  Its roof: 8192 int8 MAC per clock per SM (the dense int8 rate behind the 4.5 POP/s
+        # figure; 256 MAC per descriptor pair -> 32 pairs per clock per SM), which for 128 x 128 tiles with both operands
+        # in shared memory coincides with the shared-memory bound (8 KB of operands per MMA at 128 B per clock).
+        matcher_kind = ex.debug_matcher_kind()
+        umma_roof = 148 * 32 * f_mhz * 1e6 / 1e9
+        matcher_kernel = {0: "k_match (XOR + POPC, carry-save folded)",
+                          1: "k_match_imma (int8 mma.sync m16n8k32, 16 pairs per MMA)",
+                          2: "k_match_umma (tcgen05.mma kind::i8 128x128x32 from shared memory, accumulators in TMEM, "
+                             "warp-specialised: 8 worker warps + 1 issuing warp)"}[matcher_kind]
         line = {
             "metric": "ORB frames/s (640x480, 1000 kp)", "value": fps, "unit": "frames/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps,
@@ -1055,17 +1065,22 @@ def main():
             "keypoints_per_frame": kp_total / (B * world),
             "matcher": {"value": gpairs * world * (match_ms / match_ms_max), "unit": "Gpairs/s", "nq_per_gpu": nq,
                         "nt": MAP_SIZE, "k": 1, "ms": match_ms_max,
-                        "kernel": "k_match_imma (int8 mma.sync m16n8k32, 16 pairs per MMA)",
+                        "kernel": matcher_kernel, "kernel_kind": matcher_kind,
+                        "umma_roof_gpairs_per_gpu": umma_roof,
+                        "frac_of_umma_roof": gpairs / umma_roof,
+                        "umma_roof_what": "148 SMs x 32 pairs/clk (8192 int8 MAC/clk/SM, 256 MAC per pair) x SM clock: the "
+                                          "nominal dense int8 tensor rate, not a measured one",
                         "imma_per_clk_per_sm_measured": imma_rate,
                         "imma_roof_gpairs_per_gpu": imma_roof,
-                        "frac_of_imma_roof": gpairs / imma_roof,
+                        "vs_imma_roof": gpairs / imma_roof,
+                        "imma_what": "roof of the warp-level int8 MMA kernel (ORBB_MATCH_UMMA=0: 1646 Gpairs/s = 62 % of it)",
                         "popc_per_pair": 5,
                         "popc_lanes_per_clk_per_sm_measured": popc_rate,
                         "popc_roof_gpairs_per_gpu": popc_roof,
                         "plain_8popc_roof_gpairs_per_gpu": popc_roof * 5 / 8,
                         "vs_popc_roof": gpairs / popc_roof,
                         "popc_what": "roof of the XOR / POPC kernel (ORBB_MATCH_POPC=1: 905 Gpairs/s = 98 % of it), "
-                                     "which the tensor-core form exceeds"},
+                                     "which the tensor-core forms exceed"},
         }
         if sustained is not None:
             line["sustained"] = sustained

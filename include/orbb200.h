@@ -414,6 +414,9 @@ int orbb_debug_popc_rate(orbb_handle *h, double *popc_per_clk_per_sm);
 /* int8 tensor-core MMAs (m16n8k32) per clock per SM of this GPU, from a register-only microbenchmark: the roof of the
  * tensor-core matcher (16 descriptor pairs per MMA).  Synchronises. */
 int orbb_debug_imma_rate(orbb_handle *h, double *imma_per_clk_per_sm);
+/* which brute-force matcher kernel this process runs (read once from the environment): 0 = XOR / POPC (ORBB_MATCH_POPC=1),
+ * 1 = warp-level int8 MMA (ORBB_MATCH_UMMA=0), 2 = tcgen05 int8 MMA with TMEM accumulators (default).  Same results. */
+int orbb_debug_matcher_kind(void);
 /* padded level, contiguous (w+38) x (h+38) */
 int orbb_debug_get_padded(orbb_handle *h, int frame, int level, uint8_t *host_out);
 /* blurred ROI, contiguous w x h */

@@ -12,6 +12,7 @@
 // pair; bound by the POPC issue rate (16 lanes/clk/SM).  In both, the train set may be split across
 // blockIdx.y (split-T) so small query sets still fill 148 SMs; partial (d1,i1,d2,i2) are merged in
 // ascending split order, which preserves the tie rule.  See DESIGN.md section 4.
+#include <algorithm>
 #include <cstdlib>
 
 #include "orbb_internal.cuh"
@@ -359,12 +360,15 @@ __device__ __forceinline__ void mu_wait(uint32_t bar, uint32_t parity) {
     // bounded: a hand-over that never arrives (a descriptor the hardware rejects, a phase slip) must end in an error,
     // not in a hung GPU
     const long long t_start = clock64();
-    while (clock64() - t_start < 4000000000ll) {  // ~2 s
-        uint32_t done;
-        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                     : "=r"(done) : "r"(bar), "r"(parity) : "memory");
-        if (done) return;
-    }
+    do {
+#pragma unroll 1
+        for (int spin = 0; spin < 4096; ++spin) {
+            uint32_t done;
+            asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                         : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+            if (done) return;
+        }
+    } while (clock64() - t_start < 4000000000ll);  // ~2 s
     __trap();
 }
 
@@ -679,6 +683,16 @@ cudaError_t launch_match_windowed(const uint8_t *d_q, const void *d_q_xy, int q_
     return cudaGetLastError();
 }
 
+// which brute-force matcher kernel this process runs: 0 = XOR / POPC, 1 = warp-level int8 MMA, 2 = tcgen05 (default)
+int matcher_kind() {
+    static const int kind = [] {
+        if (getenv("ORBB_MATCH_POPC") && atoi(getenv("ORBB_MATCH_POPC")) != 0) return 0;
+        if (getenv("ORBB_MATCH_UMMA") && atoi(getenv("ORBB_MATCH_UMMA")) == 0) return 1;
+        return 2;
+    }();
+    return kind;
+}
+
 cudaError_t launch_match(const uint8_t *d_q, const uint8_t *d_t, const int *d_q_off, const int *d_t_off, int nseg,
                          int nq_total, int max_q_per_seg, int nt_one, int n_split, int4 *d_partial,
                          int partial_stride, int k, float ratio, int *d_idx, int *d_dist, uint8_t *d_accept,
@@ -687,9 +701,11 @@ cudaError_t launch_match(const uint8_t *d_q, const uint8_t *d_t, const int *d_q_
     const int qblocks = (max_q_per_seg + MATCH_THREADS * MATCH_QPT - 1) / (MATCH_THREADS * MATCH_QPT);
     dim3 grid(qblocks, n_split, nseg);
     // default: the tensor-core form (same grid, same partial records); ORBB_MATCH_POPC=1 keeps the XOR / POPC kernel
-    static const bool use_popc = getenv("ORBB_MATCH_POPC") && atoi(getenv("ORBB_MATCH_POPC")) != 0;
-    static const int use_umma = getenv("ORBB_MATCH_UMMA") ? atoi(getenv("ORBB_MATCH_UMMA")) : 0;  // 1: tcgen05 form; 2: with the plain epilogue (every pair keyed)
-    if (use_umma && !use_popc) {
+    // default: the tcgen05 form; ORBB_MATCH_UMMA=0 keeps the warp-level int8 MMA kernel, ORBB_MATCH_POPC=1 the XOR / POPC
+    // kernel (same grid, same partial records); ORBB_MATCH_UMMA=2: tcgen05 with every pair keyed in the epilogue
+    const bool use_popc = matcher_kind() == 0;
+    static const int use_umma = matcher_kind() == 2 ? (getenv("ORBB_MATCH_UMMA") ? std::max(atoi(getenv("ORBB_MATCH_UMMA")), 1) : 1) : 0;
+    if (use_umma) {
         static const cudaError_t attr = [] {
             cudaError_t e = cudaFuncSetAttribute(k_match_umma<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, MU_SMEM_BYTES);
             return e != cudaSuccess ? e : cudaFuncSetAttribute(k_match_umma<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, MU_SMEM_BYTES);

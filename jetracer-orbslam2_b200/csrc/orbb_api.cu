@@ -41,6 +41,7 @@ cudaError_t launch_detect_export(const LevelDev *, int, const int *, const int *
                                  int *, int *, int, cudaStream_t);
 cudaError_t launch_match(const uint8_t *, const uint8_t *, const int *, const int *, int, int, int, int, int, int4 *,
                          int, int, float, int *, int *, uint8_t *, int *, cudaStream_t, const int * = nullptr, int = 0);
+int matcher_kind();
 cudaError_t launch_popc_rate(int, int, long long *, unsigned *, cudaStream_t);
 cudaError_t launch_imma_rate(int, int, long long *, unsigned *, cudaStream_t);
 cudaError_t launch_align(const uint16_t *, int, float, const orbb_intrinsics &, const orbb_intrinsics &, const orbb_extrinsics &,
@@ -1143,8 +1144,21 @@ extern "C" int orbb_extract_batch_host(orbb_handle *h, const uint8_t *h_images, 
 // Split of the train range across blockIdx.y.  Measured on B200: the kernel keeps gaining until about 64 CTAs per SM
 // are queued (796 -> 886 Gpairs/s for 257 k x 50 k): small CTAs even out the tail and keep every SM's POPC pipe fed.
 static int pick_split(int qblocks_total, long long nt) {
-    static const int per_sm = getenv("ORBB_MATCH_CTAS") ? std::max(atoi(getenv("ORBB_MATCH_CTAS")), 1) : 64;
+    // The tcgen05 kernel wants LONG scans instead: a CTA pays for expanding its 256 queries into shared memory once, and its
+    // epilogue skips every 32-column chunk that cannot improve a row's best -- which is most of them only after the
+    // first ~1000 columns of a scan.  A few CTAs per SM still even out the tail.
+    // (Measured, 257 k x 50 k / 100 k x 200 k, 1-NN: 64 CTAs per SM 4197 / 4428 Gpairs/s, 16: 4530 / 4649, 4: 4629 / 4287 --
+    // the last one is a 5.3-wave tail.)  So: the FEWEST splits whose CTA count fills its last wave of one-CTA-per-SM to
+    // 95 %, and at least four CTAs per SM queued; profiles/r02i_umma_split_sweep.txt.
+    static const int per_sm_env = getenv("ORBB_MATCH_CTAS") ? std::max(atoi(getenv("ORBB_MATCH_CTAS")), 1) : 0;
+    const int per_sm = per_sm_env ? per_sm_env : (matcher_kind() == 2 ? 4 : 64);
     int want = (per_sm * 148 + qblocks_total - 1) / std::max(qblocks_total, 1);
+    if (matcher_kind() == 2 && !per_sm_env) {
+        for (int s = want; s <= std::min(want + 8, 64); ++s) {
+            const long long ctas = (long long)std::max(qblocks_total, 1) * s, waves = (ctas + 147) / 148;
+            if (ctas * 100 >= waves * 148 * 95) { want = s; break; }
+        }
+    }
     want = (int)std::min<long long>(want, std::max<long long>(1, nt / 128));  // at least one shared-memory tile of train rows per split
     want = std::max(want, (int)((nt + (1 << 22) - 1) >> 22));  // packed keys hold 22 index bits per split
     return std::max(1, std::min(want, 64));
@@ -1428,6 +1442,8 @@ extern "C" int orbb_debug_popc_rate(orbb_handle *h, double *popc_per_clk_per_sm)
     h->n_launches += 2;
     return ORBB_OK;
 }
+
+extern "C" int orbb_debug_matcher_kind(void) { return matcher_kind(); }
 
 // int8 tensor-core MMAs (mma.sync m16n8k32 = IMMA.16832.S8.S8) per clock per SM, measured the same way (k_imma_rate):
 // the roof of the tensor-core matcher, 16 descriptor pairs per MMA.  Synchronises.

@@ -35,7 +35,7 @@ EXPORTS = [
     "orbb_detect", "orbb_detect_fast", "orbb_detect_distribute", "orbb_gaussian_blur", "orbb_compute_angle_and_orb",
     "orbb_compute_fast_angle", "orbb_calc_orb", "orbb_detect_export", "orbb_match_knn", "orbb_match_knn_batch",
     "orbb_match_knn_segmented", "orbb_match_windowed", "orbb_debug_get_padded", "orbb_debug_get_blurred", "orbb_debug_get_scores",
-    "orbb_debug_popc_rate", "orbb_debug_imma_rate", "orbb_debug_poison", "orbb_debug_get_candidates", "orbb_debug_get_selected", "orbb_debug_distribute",
+    "orbb_debug_popc_rate", "orbb_debug_imma_rate", "orbb_debug_matcher_kind", "orbb_debug_poison", "orbb_debug_get_candidates", "orbb_debug_get_selected", "orbb_debug_distribute",
     "orbb_align_depth_to_other", "orbb_keypoint_pixel_to_point", "orbb_reproject_points", "orbb_match_windowed_batch",
     "orbb_rgb_to_grayscale", "orbb_match_projection_batch", "orbb_compute_stereo_matches",
     "orbb_slam_frame_bson_size", "orbb_slam_frame_to_bson",
@@ -143,6 +143,7 @@ def load_library():
     L.orbb_match_windowed.argtypes = [vp, vp, vp, i32, i32, vp, vp, i32, i32, f32, i32, vp, vp, vp, vp]
     L.orbb_debug_popc_rate.argtypes = [vp, C.POINTER(C.c_double)]
     L.orbb_debug_imma_rate.argtypes = [vp, C.POINTER(C.c_double)]
+    L.orbb_debug_matcher_kind.argtypes = []
     L.orbb_debug_poison.argtypes = [vp, i32]
     L.orbb_debug_get_padded.argtypes = [vp, i32, i32, vp]
     L.orbb_debug_get_blurred.argtypes = [vp, i32, i32, vp]
@@ -471,6 +472,10 @@ class ORBextractor:
         out = C.c_double(0)
         self._check(self._lib.orbb_debug_popc_rate(self._h, C.byref(out)))
         return float(out.value)
+
+    def debug_matcher_kind(self) -> int:
+        """0 = XOR / POPC kernel, 1 = warp-level int8 MMA, 2 = tcgen05 int8 MMA (the default)"""
+        return int(self._lib.orbb_debug_matcher_kind())
 
     def debug_imma_rate(self) -> float:
         """measured int8 tensor-core MMAs (m16n8k32) / clock / SM (register-only microbenchmark; synchronises)"""
