@@ -390,13 +390,26 @@ __device__ __forceinline__ int max3(int a, int b, int c) { return max(max(a, b),
                    "=r"(v[o + 30]), "=r"(v[o + 31])                                                                        \
                  : "r"(addr))
 
-template <int K>
-__global__ void __launch_bounds__(MU_BLOCK, 1)
+// The train set in the B-tile image, once per call: tile i = rows 128 i .. 128 i + 127 as the 32 KB block a CTA's
+// shared-memory B buffer holds (zeros past the last row expand to all -1: masked by the epilogue's column count).
+__global__ void __launch_bounds__(MU_THREADS) k_expand_train(const uint4 *__restrict__ train, int nt, uint8_t *__restrict__ out) {
+    const int srow = threadIdx.x & 127, shalf = threadIdx.x >> 7;
+    const int t = blockIdx.x * MU_N + srow;
+    const uint4 d = t < nt ? train[(size_t)t * 2 + shalf] : make_uint4(0u, 0u, 0u, 0u);
+    mu_expand_store(d, out + (size_t)blockIdx.x * MU_TILE_BYTES + shalf * 8 * MU_PLANE + (srow >> 3) * 128 + (srow & 7) * 16);
+}
+
+// PRE: the B tiles come from the pre-expanded image (k_expand_train) by one 32 KB bulk copy each, issued by a tenth warp
+// (full[b] then counts that copy's bytes instead of 256 arrivals) and the workers are left with the epilogue; splits
+// start at multiples of 128 train rows so that a split's tiles are the image's tiles.
+template <int K, bool PRE>
+__global__ void __launch_bounds__(MU_BLOCK + 32, 1)
 k_match_umma(const uint4 *__restrict__ query, const uint4 *__restrict__ train, const int *__restrict__ q_off,
              const int *__restrict__ t_off, int nq_one, int nt_one, int n_split, int4 *__restrict__ partial,
-             int partial_stride, const int *__restrict__ q_counts, int max_kp, int plain_epilogue) {
+             int partial_stride, const int *__restrict__ q_counts, int max_kp, int plain_epilogue,
+             const uint8_t *__restrict__ train_exp) {
     extern __shared__ __align__(1024) uint8_t mu_smem[];
-    __shared__ __align__(8) uint64_t s_bar[6];  // full[2], accfree[2], done[2]
+    __shared__ __align__(8) uint64_t s_bar[7];  // full[2], accfree[2], done[2], a_ready
     __shared__ uint32_t s_tmem;
     const int seg = blockIdx.z;
     const int q0 = q_counts ? seg * max_kp : (q_off ? q_off[seg] : 0);
@@ -405,8 +418,8 @@ k_match_umma(const uint4 *__restrict__ query, const uint4 *__restrict__ train, c
     const int qbase = q0 + blockIdx.x * MU_THREADS;
     if (qbase >= q1) return;  // block-uniform, before anything is allocated
     const int nt = t1 - t0;
-    const int per = (nt + n_split - 1) / n_split;
-    const int ts = min(nt, (int)blockIdx.y * per), te = min(nt, ts + per);
+    const int per = PRE ? ((nt + n_split - 1) / n_split + MU_N - 1) / MU_N * MU_N : (nt + n_split - 1) / n_split;
+    const int ts = (int)min((long long)nt, (long long)blockIdx.y * per), te = (int)min((long long)nt, (long long)ts + per);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int a_tile = (warp >> 2) & 1, lane_q = warp & 3;  // a warp may only read TMEM lanes 32 * (warp % 4) .. + 31
     const int q = qbase + a_tile * 128 + lane_q * 32 + lane;  // a worker's query row in the epilogue
@@ -417,6 +430,7 @@ k_match_umma(const uint4 *__restrict__ query, const uint4 *__restrict__ train, c
     if (ts < te) {  // block-uniform
         uint8_t *sA = mu_smem, *sB = mu_smem + 2 * MU_TILE_BYTES;
         const uint32_t bar_full = smem_u32(&s_bar[0]), bar_free = smem_u32(&s_bar[2]), bar_done = smem_u32(&s_bar[4]);
+        const uint32_t bar_aready = smem_u32(&s_bar[6]);
         const int ntiles = (te - ts + MU_N - 1) / MU_N;
         if (warp == 8) {
             asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)), "r"(512));
@@ -425,10 +439,11 @@ k_match_umma(const uint4 *__restrict__ query, const uint4 *__restrict__ train, c
         if (tid == 0) {
 #pragma unroll
             for (int b = 0; b < 2; ++b) {
-                asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar_full + 8 * b), "r"(MU_THREADS));
+                asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar_full + 8 * b), "r"(PRE ? 1 : MU_THREADS));
                 asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar_free + 8 * b), "r"(MU_THREADS));
                 asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar_done + 8 * b), "r"(1));
             }
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar_aready), "r"(MU_THREADS));
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -436,13 +451,31 @@ k_match_umma(const uint4 *__restrict__ query, const uint4 *__restrict__ train, c
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t tmem = s_tmem;
 
-        if (warp == 8) {
+        if (warp == 9) {
+            // ================= copier (PRE): tile t of the split = tile ts / 128 + t of the image -> B[t & 1] =================
+            if (PRE) {
+                const uint8_t *src = train_exp + (size_t)(ts / MU_N) * MU_TILE_BYTES;
+                for (int t = 0; t < ntiles; ++t) {
+                    const int b = t & 1, k = t >> 1;
+                    if (k > 0) mu_wait(bar_done + 8 * b, (uint32_t)((k - 1) & 1));  // MMA(t - 2) has read B[b]
+                    if (lane == 0) {
+                        asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}"
+                                     ::"r"(bar_full + 8 * b), "r"((uint32_t)MU_TILE_BYTES) : "memory");
+                        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                                     ::"r"(smem_u32(sB + b * MU_TILE_BYTES)), "l"(__cvta_generic_to_global(src + (size_t)t * MU_TILE_BYTES)),
+                                       "r"((uint32_t)MU_TILE_BYTES), "r"(bar_full + 8 * b) : "memory");
+                    }
+                    __syncwarp();
+                }
+            }
+        } else if (warp == 8) {
             // ================= issuer =================
             // descriptors: start address >> 4 in bits 0-13, LBO >> 4 in bits 16-29, SBO >> 4 in bits 32-45, version 1 in bits 46-47
             const uint64_t desc_hi = ((uint64_t)(128u >> 4) << 32) | (1ull << 46) | ((uint64_t)(MU_PLANE >> 4) << 16);
             auto desc_of = [&](const uint8_t *p) -> uint64_t { return desc_hi | (uint64_t)((smem_u32(p) & 0x3FFFFu) >> 4); };
             // instruction descriptor: D = s32 (2 << 4), A = B = signed 8 bit (1 << 7, 1 << 10), K-major both, N >> 3 at bit 17, M >> 4 at bit 24
             const uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(MU_N >> 3) << 17) | ((128u >> 4) << 24);
+            if (PRE) mu_wait(bar_aready, 0u);  // the A tiles (without PRE they are part of full[0]'s first phase)
             for (int t = 0; t < ntiles; ++t) {
                 const int b = t & 1, k = t >> 1;
                 mu_wait(bar_full + 8 * b, (uint32_t)(k & 1));
@@ -480,16 +513,22 @@ k_match_umma(const uint4 *__restrict__ query, const uint4 *__restrict__ train, c
                 const int qq = min(qbase + a * 128 + srow, q1 - 1);
                 mu_expand_store(query[(size_t)qq * 2 + shalf], sA + a * MU_TILE_BYTES + soff);
             }
-            uint4 pk0 = fetch(0), pk1 = fetch(1);
-            mu_expand_store(pk0, sB + soff);
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            mu_arrive(bar_full);
-            if (ntiles > 1) {
-                mu_expand_store(pk1, sB + MU_TILE_BYTES + soff);
+            uint4 pk0 = make_uint4(0u, 0u, 0u, 0u), pk1 = pk0;
+            if (PRE) {
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                mu_arrive(bar_full + 8);
+                mu_arrive(bar_aready);
+            } else {
+                pk0 = fetch(0); pk1 = fetch(1);
+                mu_expand_store(pk0, sB + soff);
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                mu_arrive(bar_full);
+                if (ntiles > 1) {
+                    mu_expand_store(pk1, sB + MU_TILE_BYTES + soff);
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    mu_arrive(bar_full + 8);
+                }
+                pk0 = fetch(2); pk1 = fetch(3);  // for tiles t + 2 of the rounds t = 0, 1
             }
-            pk0 = fetch(2); pk1 = fetch(3);  // for tiles t + 2 of the rounds t = 0, 1
             const unsigned neg21 = 0xFFE00000u + ((unsigned)n_split >> 30);  // -(2^21), opaque to ptxas: keeps the key an IMAD
             int thr = plain_epilogue ? -100000 : 256 - 2 * (int)(0xffffffffu >> 22);  // dot product of the current K-th best (none yet)
             auto update = [&](unsigned key) {
@@ -542,7 +581,7 @@ k_match_umma(const uint4 *__restrict__ query, const uint4 *__restrict__ train, c
                     }
                 }
                 // ---- tile t + 2 into the B buffer MMA(t) has just released
-                if (t + 2 < ntiles) {  // block-uniform
+                if (!PRE && t + 2 < ntiles) {  // block-uniform
                     mu_expand_store(b ? pk1 : pk0, sB + b * MU_TILE_BYTES + soff);
                     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                     mu_arrive(bar_full + 8 * b);
@@ -693,10 +732,17 @@ int matcher_kind() {
     return kind;
 }
 
+// tcgen05 matcher: train set expanded once per call into the handle's image buffer, B tiles by bulk copy (ORBB_MATCH_PRE)
+bool matcher_pre() {
+    static const bool on = getenv("ORBB_MATCH_PRE") ? atoi(getenv("ORBB_MATCH_PRE")) != 0 : false;
+    return on;
+}
+
 cudaError_t launch_match(const uint8_t *d_q, const uint8_t *d_t, const int *d_q_off, const int *d_t_off, int nseg,
                          int nq_total, int max_q_per_seg, int nt_one, int n_split, int4 *d_partial,
                          int partial_stride, int k, float ratio, int *d_idx, int *d_dist, uint8_t *d_accept,
-                         int *d_naccept, cudaStream_t st, const int *d_q_counts, int max_kp) {
+                         int *d_naccept, cudaStream_t st, const int *d_q_counts, int max_kp, uint8_t *d_exp, size_t exp_rows,
+                         bool expand_now) {
     if (nq_total <= 0) return cudaSuccess;
     const int qblocks = (max_q_per_seg + MATCH_THREADS * MATCH_QPT - 1) / (MATCH_THREADS * MATCH_QPT);
     dim3 grid(qblocks, n_split, nseg);
@@ -707,18 +753,33 @@ cudaError_t launch_match(const uint8_t *d_q, const uint8_t *d_t, const int *d_q_
     static const int use_umma = matcher_kind() == 2 ? (getenv("ORBB_MATCH_UMMA") ? std::max(atoi(getenv("ORBB_MATCH_UMMA")), 1) : 1) : 0;
     if (use_umma) {
         static const cudaError_t attr = [] {
-            cudaError_t e = cudaFuncSetAttribute(k_match_umma<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, MU_SMEM_BYTES);
-            return e != cudaSuccess ? e : cudaFuncSetAttribute(k_match_umma<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, MU_SMEM_BYTES);
+            cudaError_t e = cudaFuncSetAttribute(k_match_umma<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, MU_SMEM_BYTES);
+            if (e == cudaSuccess) e = cudaFuncSetAttribute(k_match_umma<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, MU_SMEM_BYTES);
+            if (e == cudaSuccess) e = cudaFuncSetAttribute(k_match_umma<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, MU_SMEM_BYTES);
+            if (e == cudaSuccess) e = cudaFuncSetAttribute(k_match_umma<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, MU_SMEM_BYTES);
+            return e;
         }();
         if (attr != cudaSuccess) return attr;
-        if (k == 1)
-            k_match_umma<1><<<grid, MU_BLOCK, MU_SMEM_BYTES, st>>>(reinterpret_cast<const uint4 *>(d_q), reinterpret_cast<const uint4 *>(d_t),
-                                                                     d_q_off, d_t_off, nq_total, nt_one, n_split, d_partial,
-                                                                     partial_stride, d_q_counts, max_kp, use_umma - 1);
+        // one train set, large enough a query set, room in the handle's image buffer: expand the train set once per call and
+        // let the CTAs copy their B tiles (ORBB_MATCH_PRE=1; default off until it has been through the parity tier)
+        const bool pre_on = matcher_pre();
+        const size_t tiles = ((size_t)nt_one + MU_N - 1) / MU_N;
+        const bool pre = pre_on && !d_t_off && d_exp && tiles * MU_N <= exp_rows && nt_one > 0 && (long long)qblocks * nseg >= 4;
+        const uint4 *q4 = reinterpret_cast<const uint4 *>(d_q), *t4 = reinterpret_cast<const uint4 *>(d_t);
+        if (pre) {
+            if (expand_now) k_expand_train<<<(unsigned)tiles, MU_THREADS, 0, st>>>(t4, nt_one, d_exp);
+            if (k == 1)
+                k_match_umma<1, true><<<grid, MU_BLOCK + 32, MU_SMEM_BYTES, st>>>(q4, t4, d_q_off, d_t_off, nq_total, nt_one, n_split, d_partial,
+                                                                                    partial_stride, d_q_counts, max_kp, use_umma - 1, d_exp);
+            else
+                k_match_umma<2, true><<<grid, MU_BLOCK + 32, MU_SMEM_BYTES, st>>>(q4, t4, d_q_off, d_t_off, nq_total, nt_one, n_split, d_partial,
+                                                                                    partial_stride, d_q_counts, max_kp, use_umma - 1, d_exp);
+        } else if (k == 1)
+            k_match_umma<1, false><<<grid, MU_BLOCK + 32, MU_SMEM_BYTES, st>>>(q4, t4, d_q_off, d_t_off, nq_total, nt_one, n_split, d_partial,
+                                                                                 partial_stride, d_q_counts, max_kp, use_umma - 1, nullptr);
         else
-            k_match_umma<2><<<grid, MU_BLOCK, MU_SMEM_BYTES, st>>>(reinterpret_cast<const uint4 *>(d_q), reinterpret_cast<const uint4 *>(d_t),
-                                                                     d_q_off, d_t_off, nq_total, nt_one, n_split, d_partial,
-                                                                     partial_stride, d_q_counts, max_kp, use_umma - 1);
+            k_match_umma<2, false><<<grid, MU_BLOCK + 32, MU_SMEM_BYTES, st>>>(q4, t4, d_q_off, d_t_off, nq_total, nt_one, n_split, d_partial,
+                                                                                 partial_stride, d_q_counts, max_kp, use_umma - 1, nullptr);
     } else if (!use_popc) {
         if (k == 1)
             k_match_imma<1><<<grid, MI_THREADS, 0, st>>>(reinterpret_cast<const uint4 *>(d_q), reinterpret_cast<const uint4 *>(d_t),

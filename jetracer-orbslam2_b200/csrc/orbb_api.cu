@@ -40,8 +40,10 @@ cudaError_t launch_calc_orb_pos(const float *, const float *, uint8_t *, const u
 cudaError_t launch_detect_export(const LevelDev *, int, const int *, const int *, const int *, int, int, float *, float *, int *,
                                  int *, int *, int, cudaStream_t);
 cudaError_t launch_match(const uint8_t *, const uint8_t *, const int *, const int *, int, int, int, int, int, int4 *,
-                         int, int, float, int *, int *, uint8_t *, int *, cudaStream_t, const int * = nullptr, int = 0);
+                         int, int, float, int *, int *, uint8_t *, int *, cudaStream_t, const int * = nullptr, int = 0,
+                         uint8_t * = nullptr, size_t = 0, bool = true);
 int matcher_kind();
+bool matcher_pre();
 cudaError_t launch_popc_rate(int, int, long long *, unsigned *, cudaStream_t);
 cudaError_t launch_imma_rate(int, int, long long *, unsigned *, cudaStream_t);
 cudaError_t launch_align(const uint16_t *, int, float, const orbb_intrinsics &, const orbb_intrinsics &, const orbb_extrinsics &,
@@ -68,6 +70,7 @@ using namespace orbb;
 // Split-T scratch of the matcher: one int4 per (train split, query), allocated ONCE in orbb_create.  This bounds
 // n_split * nq beyond nq itself (pick_split asks for at most 64 CTAs per SM of 256 queries each, plus one round-up).
 #define ORBB_MATCH_SPLIT_ROWS ((size_t)64 * 148 * 256 + 256)
+#define ORBB_MATCH_EXP_ROWS ((size_t)1 << 18)  // 64 MB: train sets up to 262 144 rows take the pre-expanded path
 
 static const int8_t k_pattern_host[1024] = {
 #include "../../include/orb_pattern_31.inc"
@@ -91,6 +94,8 @@ struct orbb_handle {
     int n_slots = 0, sel_cap_max = 0, pcap = 0, pcap2 = 0, max_kp = 0;
     int4 *d_partial = nullptr;
     size_t partial_cap = 0;
+    uint8_t *d_train_exp = nullptr;  // the train set as tcgen05 B tiles (256 B per row), ORBB_MATCH_EXP_ROWS rows
+    size_t train_exp_rows = 0;
     int *d_stereo_sad = nullptr;  // SAD cost per left keypoint (stereo matcher scratch), (max_batch/2) x max_kp
     size_t stereo_cap = 0;
     // staging of the *_host entry points, double-buffered so consecutive batches overlap
@@ -635,6 +640,10 @@ extern "C" int orbb_create(orbb_handle **out, const orbb_params *params, int wid
     // the query sets this handle can produce (larger ones are chunked), SAD costs for max_batch/2 stereo pairs
     h->partial_cap = ORBB_MATCH_SPLIT_ROWS + std::max<size_t>((size_t)B * h->max_kp, (size_t)1 << 18);
     CKC(dalloc(h, &h->d_partial, h->partial_cap));
+    if (matcher_kind() == 2 && matcher_pre()) {
+        h->train_exp_rows = ORBB_MATCH_EXP_ROWS;
+        CKC(dalloc(h, &h->d_train_exp, h->train_exp_rows * 256));
+    }
     h->stereo_cap = (size_t)std::max(B / 2, 1) * h->max_kp;
     CKC(dalloc(h, &h->d_stereo_sad, h->stereo_cap));
     CKC(cudaStreamCreateWithFlags(&h->s_in, cudaStreamNonBlocking));
@@ -1183,7 +1192,8 @@ extern "C" int orbb_match_knn(orbb_handle *h, const uint8_t *d_query, int nq, co
             n_split = pick_split((n + 255) / 256, nt);
         }
         CK(h, launch_match(d_query + 32 * (size_t)q0, d_train, nullptr, nullptr, 1, n, n, nt, n_split, h->d_partial, n, k, ratio,
-                           d_idx + 2 * (size_t)q0, d_dist + 2 * (size_t)q0, d_accept ? d_accept + q0 : nullptr, d_naccept, st));
+                           d_idx + 2 * (size_t)q0, d_dist + 2 * (size_t)q0, d_accept ? d_accept + q0 : nullptr, d_naccept, st,
+                           nullptr, 0, h->d_train_exp, h->train_exp_rows, q0 == 0));
         h->n_launches += 2;
         q0 += n;
     }
@@ -1218,7 +1228,7 @@ extern "C" int orbb_match_knn_batch(orbb_handle *h, const uint8_t *d_query, cons
         const size_t r0 = (size_t)f0 * max_kp;
         CK(h, launch_match(d_query + 32 * r0, d_train, nullptr, nullptr, n, n * max_kp, max_kp, nt, n_split, h->d_partial,
                            n * max_kp, k, ratio, d_idx + 2 * r0, d_dist + 2 * r0, d_accept ? d_accept + r0 : nullptr,
-                           d_naccept, st, d_q_counts + f0, max_kp));
+                           d_naccept, st, d_q_counts + f0, max_kp, h->d_train_exp, h->train_exp_rows, f0 == 0));
         h->n_launches += 2;
         f0 += n;
     }

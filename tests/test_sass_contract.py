@@ -68,9 +68,12 @@ def test_kernels_carry_their_instructions(sass):
         ops = _kernel(kernels, kk)
         assert _count(ops, "IMMA.16832.S8.S8") >= 32 and _count(ops, "LDS.128") >= 8, kk
         assert _count(ops, "LDL") == 0 and _count(ops, "STL") == 0 and _count(ops, "POPC") == 0, kk
-    for kk in ("k_match_ummaILi1E", "k_match_ummaILi2E"):  # tcgen05: 2 A tiles x 8 K steps per train tile, 128 columns per LDTM round
+    for kk in ("k_match_ummaILi1ELb0E", "k_match_ummaILi2ELb0E", "k_match_ummaILi1ELb1E", "k_match_ummaILi2ELb1E"):
+        # tcgen05: 2 A tiles x 8 K steps per train tile, 128 columns per LDTM round; B tiles expanded by the workers
+        # (Lb0: 16-byte stores of the A tiles, the first two and the refill B tiles) or bulk-copied from the image (Lb1)
         ops = _kernel(kernels, kk)
-        assert _count(ops, "UTCIMMA") == 16 and _count(ops, "LDTM") == 4 and _count(ops, "STS.128") >= 24, kk
+        assert _count(ops, "UTCIMMA") == 16 and _count(ops, "LDTM") == 4, kk
+        assert _count(ops, "STS.128") >= (16 if "Lb1E" in kk else 24) and _count(ops, "UBLKCP") == (1 if "Lb1E" in kk else 0), kk
         assert _count(ops, "VIMNMX3") >= 56, kk  # the chunk-maximum pass in front of the packed-key pass
         assert _count(ops, "LDL") == 0 and _count(ops, "STL") == 0 and _count(ops, "POPC") == 0, kk
     fast = _kernel(kernels, "k_fast_cellsILb0ELb0E")

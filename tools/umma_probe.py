@@ -10,7 +10,7 @@ import importlib, os, subprocess, sys
 import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-SHAPES = ((2000, 2000), (257, 50000), (5000, 333), (300, 1), (1027, 4099), (40000, 12345))
+SHAPES = ((2000, 2000), (257, 50000), (5000, 333), (300, 1), (1027, 4099), (40000, 12345), (3000, 128), (1500, 262144))
 
 
 def child(out):
@@ -81,8 +81,11 @@ def main():
     if ref is None:
         sys.exit(1)
     good = []
-    for name, env in (("umma", {"ORBB_MATCH_UMMA": "1"}), ("umma(plain epilogue)", {"ORBB_MATCH_UMMA": "2"}),
-                      ("imma", {})):
+    for name, env in (("umma", {"ORBB_MATCH_UMMA": "1"}), ("umma+pre (train set expanded once, B tiles by bulk copy)", {"ORBB_MATCH_UMMA": "1", "ORBB_MATCH_PRE": "1"}),
+                      ("umma(plain epilogue)", {"ORBB_MATCH_UMMA": "2"}),
+                      ("imma", {"ORBB_MATCH_UMMA": "0"})):
+        if os.environ.get("UMMA_PROBE_ONLY") and not any(name.startswith(o) for o in os.environ["UMMA_PROBE_ONLY"].split(",")):
+            continue
         got = run(name, env, os.path.join(tmp, "umma_got.npz"))
         if got is None:
             continue
@@ -100,7 +103,7 @@ def main():
             print(f"{name}: all {len(ref.files)} result arrays identical to the POPC matcher", flush=True)
             good.append((name, env))
     for name, env in good:
-        if name.startswith("umma"):
+        if name.startswith("umma") and "plain" not in name:
             run(name, env, os.path.join(tmp, "umma_got.npz"), time_it=True)
     for f in ("umma_ref.npz", "umma_got.npz"):
         try:
