@@ -1024,8 +1024,9 @@ def main():
         umma_roof = 148 * 32 * f_mhz * 1e6 / 1e9
         matcher_kernel = {0: "k_match (XOR + POPC, carry-save folded)",
                           1: "k_match_imma (int8 mma.sync m16n8k32, 16 pairs per MMA)",
-                          2: "k_match_umma (tcgen05.mma kind::i8 128x128x32 from shared memory, accumulators in TMEM, "
-                             "warp-specialised: 8 worker warps + 1 issuing warp)"}[matcher_kind]
+                          2: "k_expand_train + k_match_umma (tcgen05.mma kind::i8 128x128x32 from shared memory, accumulators "
+                             "in TMEM; warp-specialised: 8 epilogue warps, 1 issuing warp, 1 warp bulk-copying the "
+                             "pre-expanded B tiles)"}[matcher_kind]
         line = {
             "metric": "ORB frames/s (640x480, 1000 kp)", "value": fps, "unit": "frames/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps,

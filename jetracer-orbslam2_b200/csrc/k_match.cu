@@ -732,9 +732,10 @@ int matcher_kind() {
     return kind;
 }
 
-// tcgen05 matcher: train set expanded once per call into the handle's image buffer, B tiles by bulk copy (ORBB_MATCH_PRE)
+// tcgen05 matcher: train set expanded once per call into the handle's image buffer, B tiles by bulk copy (default;
+// ORBB_MATCH_PRE=0 keeps the expansion inside the matcher's CTAs for every call)
 bool matcher_pre() {
-    static const bool on = getenv("ORBB_MATCH_PRE") ? atoi(getenv("ORBB_MATCH_PRE")) != 0 : false;
+    static const bool on = getenv("ORBB_MATCH_PRE") ? atoi(getenv("ORBB_MATCH_PRE")) != 0 : true;
     return on;
 }
 
@@ -742,8 +743,9 @@ cudaError_t launch_match(const uint8_t *d_q, const uint8_t *d_t, const int *d_q_
                          int nq_total, int max_q_per_seg, int nt_one, int n_split, int4 *d_partial,
                          int partial_stride, int k, float ratio, int *d_idx, int *d_dist, uint8_t *d_accept,
                          int *d_naccept, cudaStream_t st, const int *d_q_counts, int max_kp, uint8_t *d_exp, size_t exp_rows,
-                         bool expand_now) {
+                         bool expand_now, long long *n_launches) {
     if (nq_total <= 0) return cudaSuccess;
+    if (n_launches) *n_launches += 2;  // matcher + merge; the train-set expansion below counts itself
     const int qblocks = (max_q_per_seg + MATCH_THREADS * MATCH_QPT - 1) / (MATCH_THREADS * MATCH_QPT);
     dim3 grid(qblocks, n_split, nseg);
     // default: the tensor-core form (same grid, same partial records); ORBB_MATCH_POPC=1 keeps the XOR / POPC kernel
@@ -760,14 +762,18 @@ cudaError_t launch_match(const uint8_t *d_q, const uint8_t *d_t, const int *d_q_
             return e;
         }();
         if (attr != cudaSuccess) return attr;
-        // one train set, large enough a query set, room in the handle's image buffer: expand the train set once per call and
-        // let the CTAs copy their B tiles (ORBB_MATCH_PRE=1; default off until it has been through the parity tier)
+        // one train set, room in the handle's image buffer, and at least 16 query blocks to share the image (a 2000 x 2000
+        // call is 14 us with the expansion inside its few CTAs and 20 us with the extra launch): expand the train set once
+        // per call and let the CTAs copy their B tiles
         const bool pre_on = matcher_pre();
         const size_t tiles = ((size_t)nt_one + MU_N - 1) / MU_N;
-        const bool pre = pre_on && !d_t_off && d_exp && tiles * MU_N <= exp_rows && nt_one > 0 && (long long)qblocks * nseg >= 4;
+        const bool pre = pre_on && !d_t_off && d_exp && tiles * MU_N <= exp_rows && nt_one > 0 && (long long)qblocks * nseg >= 16;
         const uint4 *q4 = reinterpret_cast<const uint4 *>(d_q), *t4 = reinterpret_cast<const uint4 *>(d_t);
         if (pre) {
-            if (expand_now) k_expand_train<<<(unsigned)tiles, MU_THREADS, 0, st>>>(t4, nt_one, d_exp);
+            if (expand_now) {
+                k_expand_train<<<(unsigned)tiles, MU_THREADS, 0, st>>>(t4, nt_one, d_exp);
+                if (n_launches) *n_launches += 1;
+            }
             if (k == 1)
                 k_match_umma<1, true><<<grid, MU_BLOCK + 32, MU_SMEM_BYTES, st>>>(q4, t4, d_q_off, d_t_off, nq_total, nt_one, n_split, d_partial,
                                                                                     partial_stride, d_q_counts, max_kp, use_umma - 1, d_exp);

@@ -41,7 +41,7 @@ cudaError_t launch_detect_export(const LevelDev *, int, const int *, const int *
                                  int *, int *, int, cudaStream_t);
 cudaError_t launch_match(const uint8_t *, const uint8_t *, const int *, const int *, int, int, int, int, int, int4 *,
                          int, int, float, int *, int *, uint8_t *, int *, cudaStream_t, const int * = nullptr, int = 0,
-                         uint8_t * = nullptr, size_t = 0, bool = true);
+                         uint8_t * = nullptr, size_t = 0, bool = true, long long * = nullptr);
 int matcher_kind();
 bool matcher_pre();
 cudaError_t launch_popc_rate(int, int, long long *, unsigned *, cudaStream_t);
@@ -1193,8 +1193,7 @@ extern "C" int orbb_match_knn(orbb_handle *h, const uint8_t *d_query, int nq, co
         }
         CK(h, launch_match(d_query + 32 * (size_t)q0, d_train, nullptr, nullptr, 1, n, n, nt, n_split, h->d_partial, n, k, ratio,
                            d_idx + 2 * (size_t)q0, d_dist + 2 * (size_t)q0, d_accept ? d_accept + q0 : nullptr, d_naccept, st,
-                           nullptr, 0, h->d_train_exp, h->train_exp_rows, q0 == 0));
-        h->n_launches += 2;
+                           nullptr, 0, h->d_train_exp, h->train_exp_rows, q0 == 0, &h->n_launches));
         q0 += n;
     }
     return ORBB_OK;
@@ -1228,8 +1227,7 @@ extern "C" int orbb_match_knn_batch(orbb_handle *h, const uint8_t *d_query, cons
         const size_t r0 = (size_t)f0 * max_kp;
         CK(h, launch_match(d_query + 32 * r0, d_train, nullptr, nullptr, n, n * max_kp, max_kp, nt, n_split, h->d_partial,
                            n * max_kp, k, ratio, d_idx + 2 * r0, d_dist + 2 * r0, d_accept ? d_accept + r0 : nullptr,
-                           d_naccept, st, d_q_counts + f0, max_kp, h->d_train_exp, h->train_exp_rows, f0 == 0));
-        h->n_launches += 2;
+                           d_naccept, st, d_q_counts + f0, max_kp, h->d_train_exp, h->train_exp_rows, f0 == 0, &h->n_launches));
         f0 += n;
     }
     return ORBB_OK;
