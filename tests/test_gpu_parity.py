@@ -591,3 +591,23 @@ def test_reference_gpu_kernels_baseline_runs(synth, tmp_path):
     d = json.loads(r.stdout.strip().splitlines()[-1])
     assert d["cells"] == 27 * 15 and 0 < d["keypoints"] <= d["cells"]
     assert d["frame_latency_us"] > 0 and set(d["stages_us"]) >= {"detect", "calc_orb", "compute_fast_angle"}
+
+
+@pytest.mark.gpu
+def test_every_matcher_kernel_reproduces_the_popc_matcher():
+    """The brute-force matcher has four kernels behind one interface, chosen once per process from the environment:
+    tcgen05 with the pre-expanded train image (default), tcgen05 expanding its tiles in the CTAs (ORBB_MATCH_PRE=0; also
+    what small and segmented calls use), tcgen05 with every pair keyed (ORBB_MATCH_UMMA=2), warp-level int8 MMA
+    (ORBB_MATCH_UMMA=0) and XOR / POPC (ORBB_MATCH_POPC=1).  tools/umma_probe.py runs each in a child process on the same
+    inputs -- full and partial train tiles, split-T, duplicate train rows, k = 1 and 2, a 262 144-row map -- and compares
+    every result array with the POPC kernel's (which the other matcher tests check against the oracle)."""
+    import os, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, UMMA_PROBE_NOTIME="1")
+    for k in ("ORBB_MATCH_UMMA", "ORBB_MATCH_PRE", "ORBB_MATCH_POPC", "ORBB_MATCH_CTAS", "UMMA_PROBE_ONLY"):
+        env.pop(k, None)
+    r = subprocess.run([sys.executable, os.path.join(root, "tools", "umma_probe.py")], env=env, capture_output=True, text=True,
+                       timeout=900)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert r.stdout.count("result arrays identical to the POPC matcher") == 4, r.stdout
+    assert "MISMATCH" not in r.stdout and "TIMEOUT" not in r.stdout

@@ -5,7 +5,9 @@ The matcher's kernel choice is read once per process, so every form runs in a ch
 kernel whose MMA never completes traps after ~2 s instead of hanging).  Shapes cover full and partial train tiles,
 split-T, k = 1 and 2, and duplicate train rows (tie rule: lowest train index).
 usage (GPU box): python tools/umma_probe.py            # parent: compares, then times the forms that matched
-                 python tools/umma_probe.py child out.npz   # child: results of the form selected by the environment"""
+                 python tools/umma_probe.py child out.npz   # child: results of the form selected by the environment
+UMMA_PROBE_NOTIME=1 skips the throughput part (tests/test_gpu_parity.py runs the comparison that way); exit code 1 if any
+form failed to run or differs."""
 import importlib, os, subprocess, sys
 import numpy as np
 
@@ -81,7 +83,8 @@ def main():
     if ref is None:
         sys.exit(1)
     good = []
-    for name, env in (("umma", {"ORBB_MATCH_UMMA": "1"}), ("umma+pre (train set expanded once, B tiles by bulk copy)", {"ORBB_MATCH_UMMA": "1", "ORBB_MATCH_PRE": "1"}),
+    for name, env in (("umma (tiles expanded inside the CTAs)", {"ORBB_MATCH_UMMA": "1", "ORBB_MATCH_PRE": "0"}),
+                      ("umma+pre (train set expanded once, B tiles by bulk copy: the default)", {"ORBB_MATCH_UMMA": "1", "ORBB_MATCH_PRE": "1"}),
                       ("umma(plain epilogue)", {"ORBB_MATCH_UMMA": "2"}),
                       ("imma", {"ORBB_MATCH_UMMA": "0"})):
         if os.environ.get("UMMA_PROBE_ONLY") and not any(name.startswith(o) for o in os.environ["UMMA_PROBE_ONLY"].split(",")):
@@ -103,13 +106,18 @@ def main():
             print(f"{name}: all {len(ref.files)} result arrays identical to the POPC matcher", flush=True)
             good.append((name, env))
     for name, env in good:
+        if os.environ.get("UMMA_PROBE_NOTIME"):
+            break
         if name.startswith("umma") and "plain" not in name:
             run(name, env, os.path.join(tmp, "umma_got.npz"), time_it=True)
+    n_forms = 4 if not os.environ.get("UMMA_PROBE_ONLY") else None
     for f in ("umma_ref.npz", "umma_got.npz"):
         try:
             os.remove(os.path.join(tmp, f))
         except OSError:
             pass
+    if n_forms is not None and len(good) != n_forms:
+        sys.exit(1)
 
 
 if __name__ == "__main__":
