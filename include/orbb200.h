@@ -173,11 +173,14 @@ int orbb_detect_export(orbb_handle *h, float *d_pos_xy, float *d_score, int32_t 
 
 /* ---------------------------------------------------------------- matcher
  * Replaces Jetracer::match_keypoints (src/cuda/post_processing.cuh:40-51): brute-force Hamming
- * k-NN over 256-bit descriptors (XOR + POPC), k in {1,2}, ties -> lowest train index, accept iff
+ * k-NN over 256-bit descriptors, k in {1,2}, ties -> lowest train index, accept iff
  * (k==1) or d1 < ratio*d2.  d_idx/d_dist are [nq][2] int32 (second column -1 when k==1 or nt<2),
- * d_accept [nq] u8 (may be NULL), d_naccept one int32 (may be NULL).  The handle supplies the split-T scratch,
- * allocated once in orbb_create (query sets larger than it holds are processed in chunks): no allocation, no
- * synchronisation.  The scratch is per handle, so matcher calls on one handle must share a stream (or be ordered
+ * d_accept [nq] u8 (may be NULL), d_naccept one int32 (may be NULL).  The all-pairs distances are computed on the
+ * tensor cores (descriptor bits as +1 / -1 int8: dot = 256 - 2 * Hamming; tcgen05 MMAs with TMEM accumulators by
+ * default, see orbb_debug_matcher_kind for the other two kernels); every kernel gives the same results.  The handle
+ * supplies the split-T scratch and the 64 MB image of the expanded train set (train sets up to 262 144 rows use it),
+ * both allocated once in orbb_create (query sets larger than the scratch holds are processed in chunks): no allocation,
+ * no synchronisation.  The scratch is per handle, so matcher calls on one handle must share a stream (or be ordered
  * by the caller).  Async on stream. */
 int orbb_match_knn(orbb_handle *h, const uint8_t *d_query, int nq, const uint8_t *d_train, int nt,
                    int k, float ratio, int32_t *d_idx, int32_t *d_dist, uint8_t *d_accept,
