@@ -368,7 +368,7 @@ __device__ __forceinline__ void mu_wait(uint32_t bar, uint32_t parity) {
                          : "=r"(done) : "r"(bar), "r"(parity) : "memory");
             if (done) return;
         }
-    } while (clock64() - t_start < 4000000000ll);  // ~2 s
+    } while (clock64() - t_start < 20000000000ll);  // ~10 s of SM clocks: far beyond any legitimate wait, also under time-slicing
     __trap();
 }
 

@@ -2,7 +2,7 @@
 """tcgen05 matcher (k_match_umma; ORBB_MATCH_UMMA=2: every pair keyed in the epilogue) against the XOR / POPC matcher on the
 same inputs, then its throughput.
 The matcher's kernel choice is read once per process, so every form runs in a child process (bounded by a timeout: a
-kernel whose MMA never completes traps after ~2 s instead of hanging).  Shapes cover full and partial train tiles,
+kernel whose MMA never completes traps after a bounded wait (~10 s) instead of hanging).  Shapes cover full and partial train tiles,
 split-T, k = 1 and 2, and duplicate train rows (tie rule: lowest train index).
 usage (GPU box): python tools/umma_probe.py            # parent: compares, then times the forms that matched
                  python tools/umma_probe.py child out.npz   # child: results of the form selected by the environment
