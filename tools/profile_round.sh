@@ -16,8 +16,10 @@ ncu --set full --import-source on --clock-control none \
     --kernel-name regex:'k_level0|k_resize_rows|k_fast_cells|k_octree|k_blur|k_angle_orb' --launch-skip 48 --launch-count 14 \
     -f -o $out/${tag}_all $cmd > $out/${tag}_ncu_all.log 2>&1
 # the matcher (cfg 5 geometry: one rank's 257 k descriptors against the 50 k map)
-ncu --set full --import-source on --clock-control none --kernel-name regex:'^k_match$' --launch-skip 2 --launch-count 1 \
+# (the default kernel: tcgen05 form; ORBB_MATCH_UMMA=0 / ORBB_MATCH_POPC=1 + regex k_match_imma / '^k_match$' for the other two)
+ncu --set full --import-source on --clock-control none --kernel-name regex:'k_match_umma' --launch-count 1 \
     -f -o $out/${tag}_match python tools/matcher_probe.py > $out/${tag}_ncu_match.log 2>&1
+UMMA_PROBE_NOTIME=1 python tools/umma_probe.py > $out/${tag}_umma_probe.txt 2>&1
 [ -x tools/_build/pipe_probe ] && ./tools/_build/pipe_probe > $out/${tag}_pipe_probe.txt 2>&1
 python tools/single_frame_probe.py 300 > $out/${tag}_single_frame.txt 2>&1
 ncu --metrics gpu__time_duration.sum --clock-control none -c 120 --csv --log-file $out/${tag}_single_frame_launches.csv \
