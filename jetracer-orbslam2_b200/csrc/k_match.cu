@@ -4,12 +4,15 @@
 // per-call cudaMalloc).  Definition: SURVEY.md A.7 -- two smallest distances over all train rows,
 // ties -> lowest train index, accept iff d1 < ratio * d2 (k == 2).
 //
-// Two kernels with identical results.  k_match_imma (default): the all-pairs distance matrix as an int8
-// tensor-core contraction over +1 / -1 expanded descriptor bits (dot = 256 - 2 * Hamming), bound by the
-// issue rate of IMMA.16832 (0.5 per clock per SM).  k_match (ORBB_MATCH_POPC=1): XOR + POPC, each thread
+// Three kernels with identical results.  k_match_umma (default): the all-pairs distance matrix as an int8
+// tensor-core contraction over +1 / -1 expanded descriptor bits (dot = 256 - 2 * Hamming), issued as tcgen05.mma
+// kind::i8 from shared memory with the accumulators in TMEM (6.5 Tpairs/s; train tiles bulk-copied from an image that
+// k_expand_train writes once per call).  k_match_imma (ORBB_MATCH_UMMA=0): the same contraction as warp-level
+// mma.sync m16n8k32, bound by the issue rate of IMMA.16832 (0.5 per clock per SM; 1.65 Tpairs/s).
+// k_match (ORBB_MATCH_POPC=1): XOR + POPC, each thread
 // keeps QPT query descriptors in registers, train descriptors are staged through shared memory in tiles
 // and read with 128-bit broadcast loads, carry-save adders fold the eight XOR words before 4-5 POPC per
-// pair; bound by the POPC issue rate (16 lanes/clk/SM).  In both, the train set may be split across
+// pair; bound by the POPC issue rate (16 lanes/clk/SM; 0.9 Tpairs/s).  In all three, the train set may be split across
 // blockIdx.y (split-T) so small query sets still fill 148 SMs; partial (d1,i1,d2,i2) are merged in
 // ascending split order, which preserves the tie rule.  See DESIGN.md section 4.
 #include <algorithm>
